@@ -1,0 +1,228 @@
+/*
+ * libmcn — C ABI of the B200-native layer-op backend.
+ *
+ * The reference (dooyounggo/MyConvNet) has no native boundary: its layer ops are Python
+ * methods of ConvNet (convnet.py:1382-2577) that call TensorFlow library ops, and its gradient
+ * averaging is optimizers.py:89-177.  Each entry point below replaces one of those TF call sites;
+ * the citation names the reference line whose op it replaces.  The Python host
+ * (myconvnet_b200/) binds these with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*
+ *   - the caller owns all memory; the library never allocates or frees caller buffers
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*)
+ *   - return value: 0 on success, negative mcn_status otherwise; mcn_last_error() gives text
+ *   - activations are NHWC, dense conv weights HWIO, exactly as in the reference
+ */
+#ifndef MCN_H_
+#define MCN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum { MCN_OK = 0, MCN_EINVAL = -1, MCN_ECUDA = -2, MCN_EUNSUPPORTED = -3 } mcn_status;
+typedef enum { MCN_F32 = 0, MCN_BF16 = 1 } mcn_dtype;
+typedef enum {
+  MCN_ACT_NONE = 0,
+  MCN_ACT_RELU = 1,
+  MCN_ACT_RELU6 = 2,
+  MCN_ACT_LRELU = 3,
+  MCN_ACT_TANH = 4,
+  MCN_ACT_SIGMOID = 5,
+  MCN_ACT_SWISH = 6
+} mcn_act;
+
+/* Geometry of one convolution.  pad_t/pad_l are the resolved TF SAME/VALID leading pads
+ * (extra padding goes bottom/right); Ho/Wo the resulting output size. */
+typedef struct {
+  int N, H, W, Cin;
+  int Cout;
+  int kh, kw;
+  int sh, sw;
+  int dh, dw;
+  int pad_t, pad_l;
+  int Ho, Wo;
+} mcn_conv_desc;
+
+const char* mcn_last_error(void);
+int mcn_version(void);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+long long mcn_launch_count(void);
+
+/* ---- dense convolution, tensor-core path (tcgen05/TMEM + TMA), bf16 in / fp32 accumulate.
+ * Replaces tf.nn.conv2d (convnet.py:1659), its autodiff Conv2DBackpropInput/Filter,
+ * tf.nn.conv2d_transpose (convnet.py:2463, = dgrad) and tf.matmul (convnet.py:1743,1755; a
+ * 1x1 conv on a [N,1,1,in] tensor).
+ *   w_ohwi : bf16 [kh*kw][Cout][Cin]   (fprop operand; produced by mcn_weight_prep)
+ *   w_hwio : bf16 [kh*kw][Cin][Cout]   (dgrad operand; the reference's own layout)
+ *   dw     : fp32 [kh*kw][Cin][Cout]   (wgrad ACCUMULATES into it: zero it first)
+ * a_mode: 0 = tiled TMA boxes (spatial tiles), 1 = im2col TMA (exact 128-pixel tiles). */
+int mcn_conv2d_fprop_tc(const mcn_conv_desc* d, const void* x, const void* w_ohwi,
+                        const float* bias, void* y, int y_dtype, int a_mode, void* stream);
+int mcn_conv2d_dgrad_tc(const mcn_conv_desc* d, const void* dy, const void* w_hwio, void* dx,
+                        int dx_dtype, int a_mode, void* stream);
+int mcn_conv2d_wgrad_tc(const mcn_conv_desc* d, const void* x, const void* dy, float* dw,
+                        int a_mode, void* stream);
+
+/* ---- dense / depthwise convolution, CUDA-core direct path (any dtype, any geometry).
+ * Same call sites as above plus tf.nn.depthwise_conv2d (convnet.py:1645).  Weights HWIO
+ * (depthwise: [kh][kw][C][mult]) in `wdtype`; wgrad writes fp32 (overwrites). */
+int mcn_conv2d_fprop_direct(const mcn_conv_desc* d, int dtype, const void* x, int wdtype,
+                            const void* w, const float* bias, void* y, void* stream);
+int mcn_conv2d_dgrad_direct(const mcn_conv_desc* d, int dtype, const void* dy, int wdtype,
+                            const void* w, void* dx, void* stream);
+int mcn_conv2d_wgrad_direct(const mcn_conv_desc* d, int dtype, const void* x, const void* dy,
+                            float* dw, void* stream);
+int mcn_dwconv2d_fwd(const mcn_conv_desc* d, int mult, int dtype, const void* x, int wdtype,
+                     const void* w, void* y, void* stream);
+int mcn_dwconv2d_bwd_data(const mcn_conv_desc* d, int mult, int dtype, const void* dy, int wdtype,
+                          const void* w, void* dx, void* stream);
+int mcn_dwconv2d_bwd_filter(const mcn_conv_desc* d, int mult, int dtype, const void* x,
+                            const void* dy, float* dw, void* stream);
+
+/* fp32 master weight [taps][Cin][Cout] -> bf16 copies in both operand layouts. */
+int mcn_weight_prep(const float* w_hwio_f32, int taps, int cin, int cout, void* w_hwio_bf16,
+                    void* w_ohwi_bf16, void* stream);
+/* Explicit im2col for channel counts the TMA path cannot address (Cin % 8 != 0: RGB stems).
+ * col: bf16 [N*Ho*Wo][kpad], kpad >= kh*kw*Cin, zero padded. */
+int mcn_im2col(const mcn_conv_desc* d, int dtype, const void* x, void* col, int kpad, void* stream);
+int mcn_col2im(const mcn_conv_desc* d, const void* dcol, int kpad, void* dx, int dx_dtype,
+               void* stream);
+
+/* ---- batch normalisation (tf.nn.fused_batch_norm, convnet.py:1883-1896,1916) ----
+ * rows = N*H*W, C channels.
+ * stats: sums[0..C) += sum x, sums[C..2C) += sum x^2 in fp64 (ACCUMULATES: zero first; for
+ *        synchronised BN all-reduce this 2C vector across ranks before finalize).
+ * finalize: mean, biased var -> invstd; also the reference's moving-stat EMA
+ *        (convnet.py:1898-1901) with the Bessel-corrected variance; count = global rows.
+ *        moving_mean/moving_var may be NULL (update_batch_norm off).
+ * apply: y = act(gamma*(x-mean)*invstd + beta [+ residual]) in one pass; gamma/beta may be NULL
+ *        (scale=False / shift=False). */
+int mcn_bn_stats(int dtype, const void* x, long long rows, int C, double* sums, void* stream);
+int mcn_bn_finalize(const double* sums, double count, int C, float eps, float momentum,
+                    float* mean, float* invstd, float* moving_mean, float* moving_var,
+                    void* stream);
+int mcn_bn_apply(int dtype, const void* x, long long rows, int C, const float* mean,
+                 const float* invstd, const float* gamma, const float* beta, const void* residual,
+                 int act, float act_alpha, void* y, void* stream);
+/* inference mode: y = act(gamma*(x-mean)/sqrt(var+eps)+beta [+ residual]) */
+int mcn_bn_infer(int dtype, const void* x, long long rows, int C, const float* mean,
+                 const float* var, float eps, const float* gamma, const float* beta,
+                 const void* residual, int act, float act_alpha, void* y, void* stream);
+/* backward, two passes.  dz = dy * act'(.): with `y` (the forward OUTPUT, post-activation and
+ * post-residual) the derivative is rebuilt from the output (relu family); with y == NULL the
+ * pre-activation is recomputed from x (swish etc.; only valid without a fused residual).
+ * reduce: sum_dz[c] += sum dz (= dbeta), sum_dz_xhat[c] += sum dz*xhat (= dgamma): the LOCAL
+ *         sums are the parameter gradients; for synchronised BN all-reduce a copy before apply.
+ * apply : dx = gamma*invstd*(dz - sum_dz/count - xhat*sum_dz_xhat/count); d_residual = dz
+ *         (may be NULL). */
+int mcn_bn_bwd_reduce(int dtype, const void* dy, const void* x, const void* y, long long rows,
+                      int C, const float* mean, const float* invstd, const float* gamma,
+                      const float* beta, int act, float act_alpha, float* sum_dz,
+                      float* sum_dz_xhat, void* stream);
+int mcn_bn_bwd_apply(int dtype, const void* dy, const void* x, const void* y, long long rows,
+                     int C, const float* mean, const float* invstd, const float* gamma,
+                     const float* beta, int act, float act_alpha, const float* sum_dz,
+                     const float* sum_dz_xhat, double count, void* dx, void* d_residual,
+                     void* stream);
+
+/* ---- pooling (tf.nn.max_pool convnet.py:1509, tf.nn.avg_pool :1548, tf.reduce_mean over H,W
+ * resnet_v1_5.py:73).  argmax is the flattened input offset (h*W + w)*C + c within the image,
+ * first maximum in row-major window order (TF CPU tie rule). */
+int mcn_maxpool_fwd(int dtype, const void* x, int N, int H, int W, int C, int kh, int kw, int sh,
+                    int sw, int pad_t, int pad_l, int Ho, int Wo, void* y, int32_t* argmax,
+                    void* stream);
+int mcn_maxpool_bwd(int dtype, const void* dy, const int32_t* argmax, int N, int H, int W, int C,
+                    int kh, int kw, int sh, int sw, int pad_t, int pad_l, int Ho, int Wo, void* dx,
+                    void* stream);
+int mcn_avgpool_fwd(int dtype, const void* x, int N, int H, int W, int C, int kh, int kw, int sh,
+                    int sw, int pad_t, int pad_l, int Ho, int Wo, void* y, void* stream);
+int mcn_avgpool_bwd(int dtype, const void* dy, int N, int H, int W, int C, int kh, int kw, int sh,
+                    int sw, int pad_t, int pad_l, int Ho, int Wo, void* dx, void* stream);
+int mcn_gap_fwd(int dtype, const void* x, int N, int HW, int C, void* y, int y_dtype, void* stream);
+int mcn_gap_bwd(int dtype, const void* dy, int dy_dtype, int N, int HW, int C, void* dx,
+                void* stream);
+
+/* ---- element-wise (convnet.py:2500-2556, efficientnet.py:163) ---- */
+int mcn_act_fwd(int dtype, const void* x, long long n, int act, float alpha, void* y, void* stream);
+int mcn_act_bwd(int dtype, const void* dy, const void* x, long long n, int act, float alpha,
+                void* dx, void* stream);
+/* y = act(a + b)  (stochastic_depth with drop_rate 0 followed by relu) */
+int mcn_add_act_fwd(int dtype, const void* a, const void* b, long long n, int act, float alpha,
+                    void* y, void* stream);
+/* dz = dy*act'(y)  (relu family, from the output) */
+int mcn_add_act_bwd(int dtype, const void* dy, const void* y, long long n, int act, float alpha,
+                    void* dz, void* stream);
+/* a += b */
+int mcn_accumulate(int dtype, void* a, const void* b, long long n, void* stream);
+/* y[n,hw,c] = x[n,hw,c]*m[n,c]; backward gives dx and dm (SE excite) */
+int mcn_scale_bcast_fwd(int dtype, const void* x, const void* m, int N, int HW, int C, void* y,
+                        void* stream);
+int mcn_scale_bcast_bwd(int dtype, const void* dy, const void* x, const void* m, int N, int HW,
+                        int C, void* dx, float* dm, void* stream);
+/* per-channel bias add / bias gradient (tf.nn.bias_add convnet.py:1694) */
+int mcn_bias_add(int dtype, void* y, long long rows, int C, const float* bias, void* stream);
+int mcn_bias_grad(int dtype, const void* dy, long long rows, int C, float* db, void* stream);
+int mcn_cast(int src_dtype, const void* src, int dst_dtype, void* dst, long long n, void* stream);
+/* network input: y = (x - mean)*scale, fp32 NHWC -> compute dtype (convnet.py:452,466,471) */
+int mcn_input_prep(const float* x, long long n, float mean, float scale, int dst_dtype, void* y,
+                   void* stream);
+/* channel concat / split of NHWC tensors (tf.concat axis=-1, deeplabv3plus.py:100,110) */
+int mcn_copy_channels(int dtype, const void* src, long long rows, int Csrc, int src_off, void* dst,
+                      int Cdst, int dst_off, int Ccopy, int accumulate, void* stream);
+/* bilinear resize (tf.image.resize_bilinear, convnet.py:2397). mode: 0 legacy, 1 align_corners,
+ * 2 half_pixel_centers. */
+int mcn_resize_bilinear_fwd(int dtype, const void* x, int N, int H, int W, int C, int Ho, int Wo,
+                            int mode, void* y, void* stream);
+int mcn_resize_bilinear_bwd(int dtype, const void* dy, int N, int H, int W, int C, int Ho, int Wo,
+                            int mode, void* dx, void* stream);
+
+/* ---- losses (convnet.py:594-600, gan.py:134-138) ----
+ * softmax cross-entropy on fp32 logits [rows][C] with int32 labels (-1 = all-zero one-hot row,
+ * convnet.py:448-449).  loss_sum accumulates sum_rows w*valid*CE; dlogits = grad_scale *
+ * w*valid*(softmax - smoothed_onehot).  probs may be NULL. */
+int mcn_softmax_xent(const float* logits, const int32_t* labels, long long rows, int C,
+                     const float* class_w, float label_smoothing, float grad_scale,
+                     float* loss_sum, float* dlogits, float* probs, void* stream);
+int mcn_sigmoid_xent(const float* logits, long long n, float label, float weight, float grad_scale,
+                     float* loss_sum, float* dlogits, int accumulate_grad, void* stream);
+
+/* ---- optimiser: fused multi-tensor update (optimizers.py:149-176, 668-705; EMA
+ * convnet.py:183-184,1401; L2 term convnet.py:563).  One launch updates every tensor in the
+ * table.  Order per element: shadow EMA on the PRE-step value, g += l2*w,
+ * optimiser rule, decoupled weight decay on the post-step value; then bf16 copies refreshed. */
+typedef struct {
+  float* w;            /* fp32 master */
+  const float* g;      /* fp32 gradient (already averaged over ranks) */
+  float* m;            /* momentum / Adam m / RMSProp mom */
+  float* v;            /* Adam v / RMSProp ms (NULL for SGD) */
+  float* ema;          /* EMA shadow (NULL = none) */
+  void* w_bf16;        /* bf16 copy, same layout (NULL = none) */
+  void* w_bf16_t;      /* bf16 [taps][cout][cin] copy (NULL = none) */
+  long long n;         /* elements */
+  int taps, cin, cout; /* for the transposed copy */
+  float l2;            /* L2 factor for this tensor (0 for biases/norm unless bias_norm_decay) */
+  float wd;            /* decoupled weight decay factor (already scaled) */
+} mcn_opt_tensor;
+typedef enum { MCN_OPT_NESTEROV = 0, MCN_OPT_RMSPROP = 1, MCN_OPT_ADAM = 2 } mcn_opt_kind;
+/* table: device array of mcn_opt_tensor; hp (device, 8 floats): lr, momentum(beta1),
+ * beta2/decay, eps, ema_decay_t, adam_lr_t, grad_scale, unused — read on device so a captured
+ * CUDA graph can be replayed with new hyper-parameters. */
+int mcn_opt_step(int kind, const mcn_opt_tensor* table, int ntensors, long long max_n,
+                 const float* hp, void* stream);
+/* EMA only (BN moving statistics shadows). */
+int mcn_ema_update(float* const* shadows, const float* const* values, const long long* sizes,
+                   int ntensors, long long max_n, const float* hp, void* stream);
+
+/* ---- generic helpers ---- */
+int mcn_fill_f32(float* p, long long n, float v, void* stream);
+int mcn_scale_f32(float* p, long long n, float s, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCN_H_ */

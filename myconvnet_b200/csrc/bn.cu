@@ -1,0 +1,474 @@
+// Batch normalisation, forward and backward, NHWC, bandwidth-bound.
+// Replaces tf.nn.fused_batch_norm at reference convnet.py:1883-1896,1916 and the hand-written
+// moving-statistics update at convnet.py:1898-1901; activation (convnet.py:2536-2556) and the
+// residual add (convnet.py:2509-2511) are fused into the same pass.
+//
+// Access pattern: the tensor is walked as a flat array of 16-byte vectors.  The launch makes the
+// total thread count a multiple of (C / vector width), so a thread always lands on the same
+// channel group: its per-channel constants live in registers and every warp reads contiguous
+// 512-byte segments.  Reductions go thread partial (fp32, a few rows) -> shared-memory atomics
+// -> one global atomic per channel per block (fp64 for the forward statistics).
+#include "mcn_common.cuh"
+
+namespace mcn {
+namespace {
+
+constexpr int kUnroll = 4;
+
+struct ChanLaunch {
+  int cv;      // channel vectors per row
+  int block;   // threads per block, multiple of cv
+  int grid;
+};
+
+template <typename T>
+bool plan(long long rows, int C, ChanLaunch* L, int blocks_per_sm) {
+  constexpr int V = Vec16<T>::N;
+  if (C % V != 0) return false;
+  int cv = C / V;
+  if (cv > 512) return false;
+  L->cv = cv;
+  L->block = (512 / cv) * cv;
+  long long nvec = rows * cv;
+  long long want = (nvec + (long long)L->block * kUnroll - 1) / ((long long)L->block * kUnroll);
+  long long cap = (long long)num_sms() * blocks_per_sm;
+  L->grid = (int)std::max<long long>(1, std::min(want, cap));
+  return true;
+}
+
+// ---------------------------------------------------------------- forward statistics
+template <typename T>
+__global__ void __launch_bounds__(512)
+bn_stats_kernel(const T* __restrict__ x, long long nvec, int cv, int C, double* __restrict__ sums) {
+  constexpr int V = Vec16<T>::N;
+  extern __shared__ float sh[];  // [2*C]
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const int cvec = threadIdx.x % cv;
+  float s1[V], s2[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) s1[i] = s2[i] = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; v + (kUnroll - 1) * stride < nvec; v += kUnroll * stride) {
+    Vec16<T> a[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) a[u] = ld_vec_stream(x + (v + u * stride) * V);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        float f = a[u].get(i);
+        s1[i] += f;
+        s2[i] = fmaf(f, f, s2[i]);
+      }
+  }
+  for (; v < nvec; v += stride) {
+    Vec16<T> a = ld_vec_stream(x + v * V);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float f = a.get(i);
+      s1[i] += f;
+      s2[i] = fmaf(f, f, s2[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    atomicAdd(&sh[cvec * V + i], s1[i]);
+    atomicAdd(&sh[C + cvec * V + i], s2[i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&sums[i], (double)sh[i]);
+}
+
+// scalar fallback (C not a multiple of the vector width)
+template <typename T>
+__global__ void bn_stats_scalar_kernel(const T* __restrict__ x, long long rows, int C,
+                                       double* __restrict__ sums) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  long long r0 = rows * blockIdx.y / gridDim.y, r1 = rows * (blockIdx.y + 1) / gridDim.y;
+  float s1 = 0.f, s2 = 0.f;
+  for (long long r = r0; r < r1; ++r) {
+    float f = to_f32(x[r * C + c]);
+    s1 += f;
+    s2 = fmaf(f, f, s2);
+  }
+  atomicAdd(&sums[c], (double)s1);
+  atomicAdd(&sums[C + c], (double)s2);
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, int C, float eps,
+                                   float momentum, float* __restrict__ mean,
+                                   float* __restrict__ invstd, float* __restrict__ moving_mean,
+                                   float* __restrict__ moving_var) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double m = sums[c] / count;
+  double var = sums[C + c] / count - m * m;
+  if (var < 0.0) var = 0.0;
+  mean[c] = (float)m;
+  invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (moving_mean != nullptr) {
+    // tf.nn.fused_batch_norm returns the Bessel-corrected variance; convnet.py:1900-1901
+    double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    moving_mean[c] = momentum * moving_mean[c] + (1.f - momentum) * (float)m;
+    moving_var[c] = momentum * moving_var[c] + (1.f - momentum) * (float)unbiased;
+  }
+}
+
+// ---------------------------------------------------------------- forward apply
+template <typename T, bool kVarInput>
+__global__ void __launch_bounds__(512)
+bn_apply_kernel(const T* __restrict__ x, long long nvec, int cv, const float* __restrict__ mean,
+                const float* __restrict__ invstd_or_var, float eps,
+                const float* __restrict__ gamma, const float* __restrict__ beta,
+                const T* __restrict__ residual, int act, float alpha, T* __restrict__ y) {
+  constexpr int V = Vec16<T>::N;
+  const int c0 = (threadIdx.x % cv) * V;
+  float sc[V], sf[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    float is = kVarInput ? rsqrtf(invstd_or_var[c0 + i] + eps) : invstd_or_var[c0 + i];
+    float g = gamma ? gamma[c0 + i] : 1.f;
+    float b = beta ? beta[c0 + i] : 0.f;
+    sc[i] = g * is;
+    sf[i] = b - mean[c0 + i] * sc[i];
+  }
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
+       v += kUnroll * stride) {
+    Vec16<T> a[kUnroll], r[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      long long vv = v + u * stride;
+      if (vv < nvec) {
+        a[u] = ld_vec_stream(x + vv * V);
+        if (residual) r[u] = ld_vec_stream(residual + vv * V);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      long long vv = v + u * stride;
+      if (vv < nvec) {
+        Vec16<T> o;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          float f = fmaf(a[u].get(i), sc[i], sf[i]);
+          if (residual) f += r[u].get(i);
+          o.set(i, act_fwd(act, f, alpha));
+        }
+        st_vec(y + vv * V, o);
+      }
+    }
+  }
+}
+
+template <typename T, bool kVarInput>
+__global__ void bn_apply_scalar_kernel(const T* __restrict__ x, long long n, int C,
+                                       const float* __restrict__ mean,
+                                       const float* __restrict__ invstd_or_var, float eps,
+                                       const float* __restrict__ gamma,
+                                       const float* __restrict__ beta,
+                                       const T* __restrict__ residual, int act, float alpha,
+                                       T* __restrict__ y) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    float is = kVarInput ? rsqrtf(invstd_or_var[c] + eps) : invstd_or_var[c];
+    float sc = (gamma ? gamma[c] : 1.f) * is;
+    float f = fmaf(to_f32(x[i]), sc, (beta ? beta[c] : 0.f) - mean[c] * sc);
+    if (residual) f += to_f32(residual[i]);
+    y[i] = from_f32<T>(act_fwd(act, f, alpha));
+  }
+}
+
+// ---------------------------------------------------------------- backward
+// dz = dy * act'(.).  With `y` given the derivative comes from the forward output (relu family,
+// also valid with a fused residual); otherwise the pre-activation is rebuilt from x.
+template <typename T>
+__device__ __forceinline__ float dz_of(float dy, float xv, float yv, bool have_y, float sc,
+                                       float sf, int act, float alpha) {
+  if (act == MCN_ACT_NONE) return dy;
+  if (have_y) return dy * act_grad_from_y(act, yv, alpha);
+  return dy * act_grad_from_x(act, fmaf(xv, sc, sf), alpha);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(512)
+bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
+                     long long nvec, int cv, int C, const float* __restrict__ mean,
+                     const float* __restrict__ invstd, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, int act, float alpha,
+                     float* __restrict__ sum_dz, float* __restrict__ sum_dz_xhat) {
+  constexpr int V = Vec16<T>::N;
+  extern __shared__ float sh[];
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const int cvec = threadIdx.x % cv;
+  const int c0 = cvec * V;
+  float mu[V], is[V], sc[V], sf[V], s1[V], s2[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    mu[i] = mean[c0 + i];
+    is[i] = invstd[c0 + i];
+    sc[i] = (gamma ? gamma[c0 + i] : 1.f) * is[i];
+    sf[i] = (beta ? beta[c0 + i] : 0.f) - mu[i] * sc[i];
+    s1[i] = s2[i] = 0.f;
+  }
+  const bool have_y = (y != nullptr);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
+       v += 2 * stride) {
+    Vec16<T> g[2], a[2], o[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      long long vv = v + u * stride;
+      if (vv < nvec) {
+        g[u] = ld_vec_stream(dy + vv * V);
+        a[u] = ld_vec_stream(x + vv * V);
+        if (have_y) o[u] = ld_vec_stream(y + vv * V);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      long long vv = v + u * stride;
+      if (vv < nvec) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          float xv = a[u].get(i);
+          float dz = dz_of<T>(g[u].get(i), xv, have_y ? o[u].get(i) : 0.f, have_y, sc[i], sf[i],
+                              act, alpha);
+          s1[i] += dz;
+          s2[i] = fmaf(dz, (xv - mu[i]) * is[i], s2[i]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    atomicAdd(&sh[c0 + i], s1[i]);
+    atomicAdd(&sh[C + c0 + i], s2[i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(&sum_dz[i], sh[i]);
+    atomicAdd(&sum_dz_xhat[i], sh[C + i]);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(512)
+bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
+                    long long nvec, int cv, const float* __restrict__ mean,
+                    const float* __restrict__ invstd, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, int act, float alpha,
+                    const float* __restrict__ sum_dz, const float* __restrict__ sum_dz_xhat,
+                    float inv_count, T* __restrict__ dx, T* __restrict__ d_residual) {
+  constexpr int V = Vec16<T>::N;
+  const int c0 = (threadIdx.x % cv) * V;
+  float mu[V], is[V], sc[V], sf[V], k1[V], k2[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    mu[i] = mean[c0 + i];
+    is[i] = invstd[c0 + i];
+    sc[i] = (gamma ? gamma[c0 + i] : 1.f) * is[i];
+    sf[i] = (beta ? beta[c0 + i] : 0.f) - mu[i] * sc[i];
+    k1[i] = sum_dz[c0 + i] * inv_count;
+    k2[i] = sum_dz_xhat[c0 + i] * inv_count;
+  }
+  const bool have_y = (y != nullptr);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
+       v += 2 * stride) {
+    Vec16<T> g[2], a[2], o[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      long long vv = v + u * stride;
+      if (vv < nvec) {
+        g[u] = ld_vec_stream(dy + vv * V);
+        a[u] = ld_vec_stream(x + vv * V);
+        if (have_y) o[u] = ld_vec_stream(y + vv * V);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      long long vv = v + u * stride;
+      if (vv < nvec) {
+        Vec16<T> ox, orr;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          float xv = a[u].get(i);
+          float dz = dz_of<T>(g[u].get(i), xv, have_y ? o[u].get(i) : 0.f, have_y, sc[i], sf[i],
+                              act, alpha);
+          float xhat = (xv - mu[i]) * is[i];
+          ox.set(i, sc[i] * (dz - k1[i] - xhat * k2[i]));
+          orr.set(i, dz);
+        }
+        st_vec(dx + vv * V, ox);
+        if (d_residual) st_vec(d_residual + vv * V, orr);
+      }
+    }
+  }
+}
+
+// scalar fallbacks for odd channel counts
+template <typename T>
+__global__ void bn_bwd_reduce_scalar_kernel(const T* dy, const T* x, const T* y, long long rows,
+                                            int C, const float* mean, const float* invstd,
+                                            const float* gamma, const float* beta, int act,
+                                            float alpha, float* sum_dz, float* sum_dz_xhat) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  long long r0 = rows * blockIdx.y / gridDim.y, r1 = rows * (blockIdx.y + 1) / gridDim.y;
+  float is = invstd[c], mu = mean[c];
+  float sc = (gamma ? gamma[c] : 1.f) * is, sf = (beta ? beta[c] : 0.f) - mu * sc;
+  float s1 = 0.f, s2 = 0.f;
+  for (long long r = r0; r < r1; ++r) {
+    float xv = to_f32(x[r * C + c]);
+    float dz = dz_of<T>(to_f32(dy[r * C + c]), xv, y ? to_f32(y[r * C + c]) : 0.f, y != nullptr,
+                        sc, sf, act, alpha);
+    s1 += dz;
+    s2 = fmaf(dz, (xv - mu) * is, s2);
+  }
+  atomicAdd(&sum_dz[c], s1);
+  atomicAdd(&sum_dz_xhat[c], s2);
+}
+template <typename T>
+__global__ void bn_bwd_apply_scalar_kernel(const T* dy, const T* x, const T* y, long long n, int C,
+                                           const float* mean, const float* invstd,
+                                           const float* gamma, const float* beta, int act,
+                                           float alpha, const float* sum_dz,
+                                           const float* sum_dz_xhat, float inv_count, T* dx,
+                                           T* d_residual) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    float is = invstd[c], mu = mean[c];
+    float sc = (gamma ? gamma[c] : 1.f) * is, sf = (beta ? beta[c] : 0.f) - mu * sc;
+    float xv = to_f32(x[i]);
+    float dz = dz_of<T>(to_f32(dy[i]), xv, y ? to_f32(y[i]) : 0.f, y != nullptr, sc, sf, act, alpha);
+    float xhat = (xv - mu) * is;
+    dx[i] = from_f32<T>(sc * (dz - sum_dz[c] * inv_count - xhat * sum_dz_xhat[c] * inv_count));
+    if (d_residual) d_residual[i] = from_f32<T>(dz);
+  }
+}
+
+}  // namespace
+}  // namespace mcn
+
+using namespace mcn;
+
+extern "C" int mcn_bn_stats(int dtype, const void* x, long long rows, int C, double* sums,
+                            void* stream) {
+  MCN_REQUIRE(x && sums && rows > 0 && C > 0, "bn_stats: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MCN_DISPATCH_DTYPE(dtype, T, {
+    ChanLaunch L;
+    if (plan<T>(rows, C, &L, 4)) {
+      bn_stats_kernel<T><<<L.grid, L.block, 2 * C * sizeof(float), st>>>(
+          static_cast<const T*>(x), rows * L.cv, L.cv, C, sums);
+    } else {
+      dim3 grid((C + 127) / 128, (unsigned)std::min<long long>(rows, 4LL * num_sms()));
+      bn_stats_scalar_kernel<T><<<grid, 128, 0, st>>>(static_cast<const T*>(x), rows, C, sums);
+    }
+  });
+  return after_launch("bn_stats");
+}
+
+extern "C" int mcn_bn_finalize(const double* sums, double count, int C, float eps, float momentum,
+                               float* mean, float* invstd, float* moving_mean, float* moving_var,
+                               void* stream) {
+  MCN_REQUIRE(sums && mean && invstd && count > 0, "bn_finalize: bad argument");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      sums, count, C, eps, momentum, mean, invstd, moving_mean, moving_var);
+  return after_launch("bn_finalize");
+}
+
+template <bool kVar>
+static int bn_apply_impl(int dtype, const void* x, long long rows, int C, const float* mean,
+                         const float* is_or_var, float eps, const float* gamma, const float* beta,
+                         const void* residual, int act, float alpha, void* y, void* stream) {
+  MCN_REQUIRE(x && y && mean && is_or_var && rows > 0, "bn_apply: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MCN_DISPATCH_DTYPE(dtype, T, {
+    ChanLaunch L;
+    if (plan<T>(rows, C, &L, 8)) {
+      bn_apply_kernel<T, kVar><<<L.grid, L.block, 0, st>>>(
+          static_cast<const T*>(x), rows * L.cv, L.cv, mean, is_or_var, eps, gamma, beta,
+          static_cast<const T*>(residual), act, alpha, static_cast<T*>(y));
+    } else {
+      long long n = rows * C;
+      int grid = (int)std::min<long long>((n + 255) / 256, 8LL * num_sms());
+      bn_apply_scalar_kernel<T, kVar><<<grid, 256, 0, st>>>(
+          static_cast<const T*>(x), n, C, mean, is_or_var, eps, gamma, beta,
+          static_cast<const T*>(residual), act, alpha, static_cast<T*>(y));
+    }
+  });
+  return after_launch("bn_apply");
+}
+
+extern "C" int mcn_bn_apply(int dtype, const void* x, long long rows, int C, const float* mean,
+                            const float* invstd, const float* gamma, const float* beta,
+                            const void* residual, int act, float act_alpha, void* y,
+                            void* stream) {
+  return bn_apply_impl<false>(dtype, x, rows, C, mean, invstd, 0.f, gamma, beta, residual, act,
+                              act_alpha, y, stream);
+}
+extern "C" int mcn_bn_infer(int dtype, const void* x, long long rows, int C, const float* mean,
+                            const float* var, float eps, const float* gamma, const float* beta,
+                            const void* residual, int act, float act_alpha, void* y,
+                            void* stream) {
+  return bn_apply_impl<true>(dtype, x, rows, C, mean, var, eps, gamma, beta, residual, act,
+                             act_alpha, y, stream);
+}
+
+extern "C" int mcn_bn_bwd_reduce(int dtype, const void* dy, const void* x, const void* y,
+                                 long long rows, int C, const float* mean, const float* invstd,
+                                 const float* gamma, const float* beta, int act, float act_alpha,
+                                 float* sum_dz, float* sum_dz_xhat, void* stream) {
+  MCN_REQUIRE(dy && x && mean && invstd && sum_dz && sum_dz_xhat, "bn_bwd_reduce: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MCN_DISPATCH_DTYPE(dtype, T, {
+    ChanLaunch L;
+    if (plan<T>(rows, C, &L, 4)) {
+      bn_bwd_reduce_kernel<T><<<L.grid, L.block, 2 * C * sizeof(float), st>>>(
+          static_cast<const T*>(dy), static_cast<const T*>(x), static_cast<const T*>(y),
+          rows * L.cv, L.cv, C, mean, invstd, gamma, beta, act, act_alpha, sum_dz, sum_dz_xhat);
+    } else {
+      dim3 grid((C + 127) / 128, (unsigned)std::min<long long>(rows, 4LL * num_sms()));
+      bn_bwd_reduce_scalar_kernel<T><<<grid, 128, 0, st>>>(
+          static_cast<const T*>(dy), static_cast<const T*>(x), static_cast<const T*>(y), rows, C,
+          mean, invstd, gamma, beta, act, act_alpha, sum_dz, sum_dz_xhat);
+    }
+  });
+  return after_launch("bn_bwd_reduce");
+}
+
+extern "C" int mcn_bn_bwd_apply(int dtype, const void* dy, const void* x, const void* y,
+                                long long rows, int C, const float* mean, const float* invstd,
+                                const float* gamma, const float* beta, int act, float act_alpha,
+                                const float* sum_dz, const float* sum_dz_xhat, double count,
+                                void* dx, void* d_residual, void* stream) {
+  MCN_REQUIRE(dy && x && dx && mean && invstd && sum_dz && sum_dz_xhat && count > 0,
+              "bn_bwd_apply: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const float inv_count = (float)(1.0 / count);
+  MCN_DISPATCH_DTYPE(dtype, T, {
+    ChanLaunch L;
+    if (plan<T>(rows, C, &L, 8)) {
+      bn_bwd_apply_kernel<T><<<L.grid, L.block, 0, st>>>(
+          static_cast<const T*>(dy), static_cast<const T*>(x), static_cast<const T*>(y),
+          rows * L.cv, L.cv, mean, invstd, gamma, beta, act, act_alpha, sum_dz, sum_dz_xhat,
+          inv_count, static_cast<T*>(dx), static_cast<T*>(d_residual));
+    } else {
+      long long n = rows * C;
+      int grid = (int)std::min<long long>((n + 255) / 256, 8LL * num_sms());
+      bn_bwd_apply_scalar_kernel<T><<<grid, 256, 0, st>>>(
+          static_cast<const T*>(dy), static_cast<const T*>(x), static_cast<const T*>(y), n, C,
+          mean, invstd, gamma, beta, act, act_alpha, sum_dz, sum_dz_xhat, inv_count,
+          static_cast<T*>(dx), static_cast<T*>(d_residual));
+    }
+  });
+  return after_launch("bn_bwd_apply");
+}

@@ -1,0 +1,873 @@
+// Dense convolution on the 5th-generation tensor cores (sm_100a).
+//
+// Replaces tf.nn.conv2d / Conv2DBackpropInput / Conv2DBackpropFilter / conv2d_transpose / matmul
+// as called from reference convnet.py:1659, :2463, :1743 (see include/mcn.h).
+//
+// Formulation: implicit GEMM, one filter tap at a time.
+//   fprop : Y[pixel, co]  = sum_tap sum_ci X[pixel shifted by tap, ci] * W[tap, co, ci]
+//   dgrad : dX[pixel, ci] = sum_tap sum_co dY[pixel shifted by -tap, co] * W[tap, ci, co]
+//   wgrad : dW[tap, ci, co] = sum_pixel X[pixel shifted by tap, ci] * dY[pixel, co]
+// fprop and dgrad share one kernel (A = activations, K-major; B = weights, K-major);
+// wgrad has its own (both operands MN-major, K = pixels, split-K with fp32 atomics).
+//
+// Data movement: every operand tile is brought in by TMA into 128-byte-swizzled shared memory.
+// The shifted activation window of a tap is either a 4-D TMA *box* (a_mode 0: the tile is a
+// TW x TH x TN block of output pixels, out-of-bounds rows/cols zero-filled = the padding) or
+// a TMA *im2col* load (a_mode 1: the tile is 128 consecutive output pixels in n,h,w order; the
+// hardware walks the window base with the conv stride and the tap offset carries the dilation).
+// MMA: tcgen05.mma cta_group::1, M=128, N=block_n, K=16 per instruction, accumulators in TMEM.
+// Roles per CTA (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
+// warps 2..5 = epilogue (tcgen05.ld -> registers -> global).
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstring>
+
+#include "mcn_common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace mcn {
+namespace {
+
+constexpr int kMaxTaps = 52;
+constexpr int kABytes = 128 * 128;  // one activation tile: 128 rows x 64 bf16
+
+struct TapTab {
+  int brow[kMaxTaps];   // row of this tap's weight slab in the B matrix
+  short dh[kMaxTaps];   // tiled: spatial shift; im2col: tap offset (>= 0)
+  short dw[kMaxTaps];
+  signed char map[kMaxTaps];
+};
+
+struct TileGeom {
+  int a_mode;
+  int tiles_w, tiles_h;     // tiled: tile grid inside (W, H); tiles along N follow
+  int TW, TH, TN, rows_box;  // tiled: box extents, rows_box = TW*TH*TN <= 128
+  int Wo, Ho, Nb;            // logical pixel-space extents
+  int str_w, str_h;          // im2col: traversal stride
+  int low_w, low_h;          // im2col: lower corner (window base of pixel 0)
+  long long m_total;         // Nb*Ho*Wo
+};
+
+struct PixelTile {
+  int w0, h0, n0;   // tiled: box origin; im2col: window base (w,h) and image
+  long long m0;     // im2col: first linear pixel
+};
+
+__device__ __forceinline__ PixelTile decode_tile(const TileGeom& g, int m_t) {
+  PixelTile t;
+  if (g.a_mode == 0) {
+    int wt = m_t % g.tiles_w;
+    int r = m_t / g.tiles_w;
+    int ht = r % g.tiles_h;
+    int nt = r / g.tiles_h;
+    t.w0 = wt * g.TW;
+    t.h0 = ht * g.TH;
+    t.n0 = nt * g.TN;
+    t.m0 = 0;
+  } else {
+    t.m0 = static_cast<long long>(m_t) * 128;
+    int q0 = static_cast<int>(t.m0 % g.Wo);
+    long long r = t.m0 / g.Wo;
+    int p0 = static_cast<int>(r % g.Ho);
+    t.n0 = static_cast<int>(r / g.Ho);
+    t.w0 = q0 * g.str_w + g.low_w;
+    t.h0 = p0 * g.str_h + g.low_h;
+  }
+  return t;
+}
+
+// Row `row` (0..127) of a pixel tile -> (n, p, q) and validity.
+__device__ __forceinline__ bool row_coords(const TileGeom& g, const PixelTile& t, int row, int& n,
+                                           int& p, int& q) {
+  if (g.a_mode == 0) {
+    int wi = row % g.TW;
+    int r = row / g.TW;
+    int hi = r % g.TH;
+    int ni = r / g.TH;
+    q = t.w0 + wi;
+    p = t.h0 + hi;
+    n = t.n0 + ni;
+    return row < g.rows_box && q < g.Wo && p < g.Ho && n < g.Nb;
+  }
+  long long m = t.m0 + row;
+  q = static_cast<int>(m % g.Wo);
+  long long r = m / g.Wo;
+  p = static_cast<int>(r % g.Ho);
+  n = static_cast<int>(r / g.Ho);
+  return m < g.m_total;
+}
+
+// ------------------------------------------------------------------ fprop / dgrad kernel
+struct GemmConvArgs {
+  CUtensorMap mapA[4];
+  CUtensorMap mapB;
+  TileGeom g;
+  int taps, k_chunks, ksteps_last, block_n, n_total, stages, tiles_n, tmem_cols;
+  long long out_sn, out_sh, out_sw;  // element strides of the output pixel grid
+  void* out;
+  const float* bias;
+  int out_f32, vec_ok;
+  TapTab tab;
+};
+
+__global__ void __launch_bounds__(192, 1)
+gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int stages = args.stages;
+  const uint32_t b_bytes = static_cast<uint32_t>(args.block_n) * 128u;
+  const uint32_t stage_bytes = kABytes + b_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(stages) * stage_bytes);
+  uint64_t* empty = full + stages;
+  uint64_t* tmem_full = empty + stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int n_t = blockIdx.x % args.tiles_n;
+  const int m_t = blockIdx.x / args.tiles_n;
+  const PixelTile tile = decode_tile(args.g, m_t);
+  const int total_it = args.taps * args.k_chunks;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 4; ++i) ptx::prefetch_tmap(&args.mapA[i]);
+    ptx::prefetch_tmap(&args.mapB);
+    for (int s = 0; s < stages; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    ptx::mbar_init(tmem_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, static_cast<uint32_t>(args.tmem_cols));
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    if (ptx::elect_one()) {
+      const uint32_t a_tx = (args.g.a_mode == 0) ? static_cast<uint32_t>(args.g.rows_box) * 128u
+                                                 : static_cast<uint32_t>(kABytes);
+      int it = 0;
+      for (int t = 0; t < args.taps; ++t) {
+        for (int kc = 0; kc < args.k_chunks; ++kc, ++it) {
+          const int s = it % stages;
+          const uint32_t ph = static_cast<uint32_t>(it / stages) & 1u;
+          ptx::mbar_wait(&empty[s], ph ^ 1u);
+          ptx::mbar_expect_tx(&full[s], a_tx + b_bytes);
+          uint8_t* sA = smem + static_cast<size_t>(s) * stage_bytes;
+          uint8_t* sB = sA + kABytes;
+          if (args.g.a_mode == 0) {
+            ptx::tma_load_4d(&args.mapA[args.tab.map[t]], &full[s], sA, kc * 64,
+                             tile.w0 + args.tab.dw[t], tile.h0 + args.tab.dh[t], tile.n0);
+          } else {
+            ptx::tma_load_im2col_4d(&args.mapA[0], &full[s], sA, kc * 64, tile.w0, tile.h0,
+                                    tile.n0, static_cast<uint16_t>(args.tab.dw[t]),
+                                    static_cast<uint16_t>(args.tab.dh[t]));
+          }
+          ptx::tma_load_2d(&args.mapB, &full[s], sB, kc * 64,
+                           args.tab.brow[t] + n_t * args.block_n);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    const uint32_t idesc = ptx::make_idesc_bf16(128, args.block_n, 0, 0);
+    int it = 0;
+    for (int t = 0; t < args.taps; ++t) {
+      for (int kc = 0; kc < args.k_chunks; ++kc, ++it) {
+        const int s = it % stages;
+        const uint32_t ph = static_cast<uint32_t>(it / stages) & 1u;
+        ptx::mbar_wait(&full[s], ph);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint32_t a_addr = ptx::smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
+          const uint32_t b_addr = a_addr + kABytes;
+          const int ksteps = (kc == args.k_chunks - 1) ? args.ksteps_last : 4;
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t ad = ptx::make_smem_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t bd = ptx::make_smem_desc(b_addr + k * 32, 16, 1024);
+            ptx::umma_bf16(tmem_base, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty[s]);
+          if (it == total_it - 1) ptx::umma_commit(tmem_full);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ---------------- epilogue: TMEM -> registers -> global ----------------
+    ptx::mbar_wait(tmem_full, 0);
+    ptx::tc_fence_after();
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    const int row = quad * 32 + lane;
+    int n, p, q;
+    const bool valid = row_coords(args.g, tile, row, n, p, q);
+    const long long off = valid ? (n * args.out_sn + p * args.out_sh + q * args.out_sw) : 0;
+    for (int c0 = 0; c0 < args.block_n; c0 += 32) {
+      uint32_t r[32];
+      ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c0, r);
+      ptx::tmem_ld_wait();
+      const int col0 = n_t * args.block_n + c0;
+      if (!valid || col0 >= args.n_total) continue;
+      if (args.bias != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < args.n_total)
+            r[j] = __float_as_uint(__uint_as_float(r[j]) + args.bias[col0 + j]);
+      }
+      if (args.out_f32) {
+        float* o = reinterpret_cast<float*>(args.out) + off + col0;
+        if (args.vec_ok && col0 + 32 <= args.n_total) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<uint4*>(o + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+        } else {
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < args.n_total) o[j] = __uint_as_float(r[j]);
+        }
+      } else {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(args.out) + off + col0;
+        if (args.vec_ok && col0 + 32 <= args.n_total) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(r[j + 2 * e]),
+                                                       __uint_as_float(r[j + 2 * e + 1]));
+              pk[e] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(o + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        } else {
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < args.n_total) o[j] = __float2bfloat16_rn(__uint_as_float(r[j]));
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, static_cast<uint32_t>(args.tmem_cols));
+}
+
+// ------------------------------------------------------------------ wgrad kernel
+struct WgradArgs {
+  CUtensorMap mapX[4];
+  CUtensorMap mapDy;
+  TileGeom g;
+  int taps, stages, block_n, nb_atoms, tmem_cols;
+  int cin, cout;
+  int tiles_mi, tiles_ni, splits, kblocks_total, ksteps;
+  float* dw;
+  TapTab tab;
+};
+
+__global__ void __launch_bounds__(192, 1)
+wgrad_kernel(const __grid_constant__ WgradArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int stages = args.stages;
+  const uint32_t a_bytes = 2u * kABytes;
+  const uint32_t b_bytes = static_cast<uint32_t>(args.nb_atoms) * kABytes;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(stages) * stage_bytes);
+  uint64_t* empty = full + stages;
+  uint64_t* tmem_full = empty + stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  int w = blockIdx.x;
+  const int ni = w % args.tiles_ni;
+  w /= args.tiles_ni;
+  const int mi = w % args.tiles_mi;
+  w /= args.tiles_mi;
+  const int tap = w % args.taps;
+  const int split = w / args.taps;
+  const int kb0 = static_cast<int>(static_cast<long long>(split) * args.kblocks_total / args.splits);
+  const int kb1 =
+      static_cast<int>(static_cast<long long>(split + 1) * args.kblocks_total / args.splits);
+
+  // Rows a tiled box does not cover must read as zero (K padding): clear the stage buffers once.
+  {
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    const int n16 = static_cast<int>(static_cast<size_t>(stages) * stage_bytes / 16);
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+    ptx::fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 4; ++i) ptx::prefetch_tmap(&args.mapX[i]);
+    ptx::prefetch_tmap(&args.mapDy);
+    for (int s = 0; s < stages; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    ptx::mbar_init(tmem_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, static_cast<uint32_t>(args.tmem_cols));
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      const uint32_t rows_bytes =
+          (args.g.a_mode == 0) ? static_cast<uint32_t>(args.g.rows_box) * 128u : kABytes;
+      const uint32_t tx = rows_bytes * static_cast<uint32_t>(2 + args.nb_atoms);
+      for (int kb = kb0, it = 0; kb < kb1; ++kb, ++it) {
+        const int s = it % stages;
+        const uint32_t ph = static_cast<uint32_t>(it / stages) & 1u;
+        ptx::mbar_wait(&empty[s], ph ^ 1u);
+        ptx::mbar_expect_tx(&full[s], tx);
+        uint8_t* sA = smem + static_cast<size_t>(s) * stage_bytes;
+        uint8_t* sB = sA + a_bytes;
+        const PixelTile t = decode_tile(args.g, kb);
+        for (int a = 0; a < 2; ++a) {
+          const int c = mi * 128 + a * 64;
+          if (args.g.a_mode == 0) {
+            ptx::tma_load_4d(&args.mapX[args.tab.map[tap]], &full[s], sA + a * kABytes, c,
+                             t.w0 + args.tab.dw[tap], t.h0 + args.tab.dh[tap], t.n0);
+          } else {
+            ptx::tma_load_im2col_4d(&args.mapX[0], &full[s], sA + a * kABytes, c, t.w0, t.h0, t.n0,
+                                    static_cast<uint16_t>(args.tab.dw[tap]),
+                                    static_cast<uint16_t>(args.tab.dh[tap]));
+          }
+        }
+        for (int j = 0; j < args.nb_atoms; ++j) {
+          const int c = ni * args.block_n + j * 64;
+          if (args.g.a_mode == 0) {
+            ptx::tma_load_4d(&args.mapDy, &full[s], sB + j * kABytes, c, t.w0, t.h0, t.n0);
+          } else {
+            // dy is addressed as a [m_total, Cout] matrix through a (C, M, 1, 1) map
+            ptx::tma_load_4d(&args.mapDy, &full[s], sB + j * kABytes, c,
+                             static_cast<int>(t.m0), 0, 0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = ptx::make_idesc_bf16(128, args.block_n, 1, 1);
+    for (int kb = kb0, it = 0; kb < kb1; ++kb, ++it) {
+      const int s = it % stages;
+      const uint32_t ph = static_cast<uint32_t>(it / stages) & 1u;
+      ptx::mbar_wait(&full[s], ph);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint32_t a_addr = ptx::smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
+        const uint32_t b_addr = a_addr + a_bytes;
+        for (int k = 0; k < args.ksteps; ++k) {
+          // MN-major: 64-channel atoms kABytes apart (LBO), 8-pixel groups 1024 B apart (SBO);
+          // one instruction consumes 16 pixels = 2048 B of each atom.
+          const uint64_t ad = ptx::make_smem_desc(a_addr + k * 2048, kABytes, 1024);
+          const uint64_t bd = ptx::make_smem_desc(b_addr + k * 2048, kABytes, 1024);
+          ptx::umma_bf16(tmem_base, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(&empty[s]);
+        if (kb == kb1 - 1) ptx::umma_commit(tmem_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    ptx::mbar_wait(tmem_full, 0);
+    ptx::tc_fence_after();
+    const int quad = warp & 3;
+    const int ci = mi * 128 + quad * 32 + lane;
+    for (int c0 = 0; c0 < args.block_n; c0 += 32) {
+      uint32_t r[32];
+      ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c0, r);
+      ptx::tmem_ld_wait();
+      if (ci >= args.cin) continue;
+      const int co0 = ni * args.block_n + c0;
+      float* o = args.dw + (static_cast<long long>(tap) * args.cin + ci) * args.cout + co0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (co0 + j < args.cout) atomicAdd(o + j, __uint_as_float(r[j]));
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, static_cast<uint32_t>(args.tmem_cols));
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                   const cuuint64_t*, const cuuint64_t*, const int*, const int*,
+                                   cuuint32_t, cuuint32_t, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+void* driver_symbol(const char* name) {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  return fn;
+}
+
+// bf16 tensor (C innermost) viewed as up to 4 dims; box[0] is always 64 channels (128 B).
+int encode_tiled(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
+                 const uint64_t* strides_bytes, const uint32_t* box) {
+  static EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(driver_symbol("cuTensorMapEncodeTiled"));
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled unavailable");
+    return MCN_ECUDA;
+  }
+  cuuint64_t gd[4];
+  cuuint64_t gs[3];
+  cuuint32_t bx[4];
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    if (i > 0) gs[i - 1] = strides_bytes[i];
+  }
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gd, gs, bx,
+                  es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu %llu box %u %u %u %u",
+              (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+              (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+              box[0], box[1], rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+    return MCN_ECUDA;
+  }
+  return MCN_OK;
+}
+
+int encode_im2col(CUtensorMap* m, const void* base, int C, int W, int H, int N, int low_w,
+                  int low_h, int up_w, int up_h, int str_w, int str_h) {
+  static EncodeIm2colFn fn =
+      reinterpret_cast<EncodeIm2colFn>(driver_symbol("cuTensorMapEncodeIm2col"));
+  if (!fn) {
+    set_error("cuTensorMapEncodeIm2col unavailable");
+    return MCN_ECUDA;
+  }
+  cuuint64_t gd[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t gs[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  int lo[2] = {low_w, low_h};
+  int up[2] = {up_w, up_h};
+  cuuint32_t es[4] = {1, (cuuint32_t)str_w, (cuuint32_t)str_h, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gd, gs, lo, up,
+                  64, 128, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeIm2col failed (%d): C%d W%d H%d N%d lo(%d,%d) up(%d,%d) s(%d,%d)",
+              (int)r, C, W, H, N, low_w, low_h, up_w, up_h, str_w, str_h);
+    return MCN_ECUDA;
+  }
+  return MCN_OK;
+}
+
+// NHWC bf16 tensor -> (C, W, H, N) tiled map with the given box.
+int encode_nhwc(CUtensorMap* m, const void* base, int C, int W, int H, int N, int bw, int bh,
+                int bn) {
+  uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+  uint64_t st[4] = {2, (uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+  uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
+  return encode_tiled(m, base, 4, dims, st, box);
+}
+// [rows, K] bf16 matrix -> 2-D map, box 64 x box_rows.
+int encode_matrix(CUtensorMap* m, const void* base, long long rows, int K, int box_rows) {
+  uint64_t dims[2] = {(uint64_t)K, (uint64_t)rows};
+  uint64_t st[2] = {2, (uint64_t)K * 2};
+  uint32_t box[2] = {64, (uint32_t)box_rows};
+  return encode_tiled(m, base, 2, dims, st, box);
+}
+
+int pick_block_n(int n) {
+  if (n <= 64) return 64;
+  if (n <= 128) return 128;
+  if (n % 256 == 0) return 256;
+  return 128;
+}
+int tmem_cols_for(int block_n) { return block_n <= 64 ? 64 : (block_n <= 128 ? 128 : 256); }
+
+// Pixel-space tiling for the box mode: TW x TH x TN <= 128 output pixels per tile.
+void pick_box(int Wo, int Ho, int Nb, int* TW, int* TH, int* TN) {
+  int tw = std::min(Wo, 128);
+  int th = 1, tn = 1;
+  if (tw == Wo) {
+    int max_th = std::min(Ho, 128 / tw);
+    int best = 1, best_tiles = Ho;
+    for (int c = 1; c <= max_th; ++c) {
+      int tiles = (Ho + c - 1) / c;
+      if (tiles < best_tiles) {
+        best_tiles = tiles;
+        best = c;
+      }
+    }
+    th = best;
+    if (th == Ho) tn = std::max(1, std::min(Nb, 128 / (tw * th)));
+  }
+  *TW = tw;
+  *TH = th;
+  *TN = tn;
+}
+
+struct PixelSpace {   // the pixel grid the GEMM M (fprop/dgrad) or K (wgrad) dimension walks
+  int W, H, N;
+};
+
+void fill_geom_tiled(TileGeom* g, const PixelSpace& ps) {
+  g->a_mode = 0;
+  pick_box(ps.W, ps.H, ps.N, &g->TW, &g->TH, &g->TN);
+  g->rows_box = g->TW * g->TH * g->TN;
+  g->tiles_w = (ps.W + g->TW - 1) / g->TW;
+  g->tiles_h = (ps.H + g->TH - 1) / g->TH;
+  g->Wo = ps.W;
+  g->Ho = ps.H;
+  g->Nb = ps.N;
+  g->str_w = g->str_h = 1;
+  g->low_w = g->low_h = 0;
+  g->m_total = static_cast<long long>(ps.W) * ps.H * ps.N;
+}
+int tiles_m_of(const TileGeom& g) {
+  if (g.a_mode == 0) return g.tiles_w * g.tiles_h * ((g.Nb + g.TN - 1) / g.TN);
+  return static_cast<int>((g.m_total + 127) / 128);
+}
+
+int smem_optin_limit() {
+  static int lim = 0;
+  if (!lim) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (lim <= 0) lim = 227 * 1024;
+  }
+  return lim;
+}
+
+int launch_gemm_conv(GemmConvArgs& a, int tiles_m, cudaStream_t st) {
+  const uint32_t stage_bytes = kABytes + a.block_n * 128;
+  // two CTAs per SM so one tile's epilogue overlaps the other's main loop
+  int stages = std::min(8, static_cast<int>((110 * 1024) / stage_bytes));
+  stages = std::max(2, std::min(stages, a.taps * a.k_chunks));
+  a.stages = stages;
+  a.tmem_cols = tmem_cols_for(a.block_n);
+  size_t smem = static_cast<size_t>(stages) * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
+  static size_t configured = 0;
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(gemm_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             smem_optin_limit()) != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(gemm_conv_kernel) failed");
+      return MCN_ECUDA;
+    }
+    configured = smem_optin_limit();
+  }
+  dim3 grid(static_cast<unsigned>(tiles_m) * a.tiles_n);
+  gemm_conv_kernel<<<grid, 192, smem, st>>>(a);
+  return after_launch("gemm_conv_kernel");
+}
+
+bool tc_shape_ok(const mcn_conv_desc* d) {
+  return d->Cin % 8 == 0 && d->Cout % 8 == 0 && d->kh * d->kw <= kMaxTaps;
+}
+
+}  // namespace
+}  // namespace mcn
+
+using namespace mcn;
+
+extern "C" int mcn_conv2d_fprop_tc(const mcn_conv_desc* d, const void* x, const void* w_ohwi,
+                                   const float* bias, void* y, int y_dtype, int a_mode,
+                                   void* stream) {
+  MCN_REQUIRE(d && x && w_ohwi && y, "fprop_tc: null argument");
+  MCN_REQUIRE(d->Cin % 8 == 0, "fprop_tc: Cin=%d must be a multiple of 8 (16-byte TMA rows)", d->Cin);
+  MCN_REQUIRE(d->kh * d->kw <= kMaxTaps, "fprop_tc: too many taps");
+  const bool pointwise = d->kh == 1 && d->kw == 1 && d->sh == 1 && d->sw == 1;
+  if (a_mode == 1 && (d->Cin % 64 != 0 || pointwise)) a_mode = 0;
+  MCN_REQUIRE(a_mode == 1 || (d->sh == 1 && d->sw == 1) || (d->kh == 1 && d->kw == 1),
+              "fprop_tc: box mode supports stride 1 (or 1x1 kernels) only");
+  GemmConvArgs a;
+  std::memset(&a, 0, sizeof(a));
+  int rc;
+  const int taps = d->kh * d->kw;
+  if (pointwise) {
+    // pure GEMM: pixels form one long row
+    PixelSpace ps{static_cast<int>(std::min<long long>((long long)d->N * d->H * d->W, 1LL << 30)), 1, 1};
+    fill_geom_tiled(&a.g, ps);
+    uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)ps.W, 1, 1};
+    uint64_t stb[4] = {2, (uint64_t)d->Cin * 2, (uint64_t)ps.W * d->Cin * 2,
+                       (uint64_t)ps.W * d->Cin * 2};
+    uint32_t box[4] = {64, (uint32_t)a.g.TW, 1, 1};
+    if ((rc = encode_tiled(&a.mapA[0], x, 4, dims, stb, box))) return rc;
+    a.out_sw = d->Cout;
+    a.out_sh = a.out_sn = 0;
+  } else if (a_mode == 0) {
+    PixelSpace ps{d->Wo, d->Ho, d->N};
+    fill_geom_tiled(&a.g, ps);
+    if (d->sh == 1 && d->sw == 1) {
+      if ((rc = encode_nhwc(&a.mapA[0], x, d->Cin, d->W, d->H, d->N, a.g.TW, a.g.TH, a.g.TN)))
+        return rc;
+    } else {
+      // 1x1 strided: the sampled pixels form a strided view of x
+      uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->Wo, (uint64_t)d->Ho, (uint64_t)d->N};
+      uint64_t stb[4] = {2, (uint64_t)d->sw * d->Cin * 2, (uint64_t)d->sh * d->W * d->Cin * 2,
+                         (uint64_t)d->H * d->W * d->Cin * 2};
+      uint32_t box[4] = {64, (uint32_t)a.g.TW, (uint32_t)a.g.TH, (uint32_t)a.g.TN};
+      if ((rc = encode_tiled(&a.mapA[0], x, 4, dims, stb, box))) return rc;
+    }
+    a.out_sw = d->Cout;
+    a.out_sh = (long long)d->Wo * d->Cout;
+    a.out_sn = (long long)d->Ho * d->Wo * d->Cout;
+  } else {
+    a.g.a_mode = 1;
+    a.g.Wo = d->Wo;
+    a.g.Ho = d->Ho;
+    a.g.Nb = d->N;
+    a.g.m_total = (long long)d->N * d->Ho * d->Wo;
+    a.g.str_w = d->sw;
+    a.g.str_h = d->sh;
+    a.g.low_w = -d->pad_l;
+    a.g.low_h = -d->pad_t;
+    // upper corner chosen so the window base takes exactly Wo (Ho) positions
+    const int up_w = (d->Wo - 1) * d->sw - d->pad_l - (d->W - 1);
+    const int up_h = (d->Ho - 1) * d->sh - d->pad_t - (d->H - 1);
+    if ((rc = encode_im2col(&a.mapA[0], x, d->Cin, d->W, d->H, d->N, a.g.low_w, a.g.low_h, up_w,
+                            up_h, d->sw, d->sh)))
+      return rc;
+    a.out_sw = d->Cout;
+    a.out_sh = (long long)d->Wo * d->Cout;
+    a.out_sn = (long long)d->Ho * d->Wo * d->Cout;
+  }
+  for (int i = 1; i < 4; ++i) a.mapA[i] = a.mapA[0];
+  a.block_n = pick_block_n(d->Cout);
+  a.tiles_n = (d->Cout + a.block_n - 1) / a.block_n;
+  if ((rc = encode_matrix(&a.mapB, w_ohwi, (long long)taps * d->Cout, d->Cin, a.block_n))) return rc;
+  a.taps = taps;
+  a.k_chunks = (d->Cin + 63) / 64;
+  {
+    int rem = d->Cin - (a.k_chunks - 1) * 64;
+    a.ksteps_last = (rem + 15) / 16;
+  }
+  a.n_total = d->Cout;
+  a.out = y;
+  a.out_f32 = (y_dtype == MCN_F32);
+  a.bias = bias;
+  a.vec_ok = (d->Cout % 8 == 0);
+  for (int r = 0; r < d->kh; ++r)
+    for (int s = 0; s < d->kw; ++s) {
+      int t = r * d->kw + s;
+      a.tab.brow[t] = t * d->Cout;
+      a.tab.map[t] = 0;
+      if (a.g.a_mode == 0 && !pointwise) {
+        a.tab.dh[t] = (short)(r * d->dh - d->pad_t);
+        a.tab.dw[t] = (short)(s * d->dw - d->pad_l);
+      } else {
+        a.tab.dh[t] = (short)(r * d->dh);
+        a.tab.dw[t] = (short)(s * d->dw);
+      }
+    }
+  return launch_gemm_conv(a, tiles_m_of(a.g), static_cast<cudaStream_t>(stream));
+}
+
+// dgrad for stride 1: a stride-1 correlation of dy with the taps mirrored.
+//   dx[n,h,w,ci] = sum_{r,s,co} dy[n, h + pad_t - r*dh, w + pad_l - s*dw, co] * W[r,s,ci,co]
+extern "C" int mcn_conv2d_dgrad_tc(const mcn_conv_desc* d, const void* dy, const void* w_hwio,
+                                   void* dx, int dx_dtype, int a_mode, void* stream) {
+  MCN_REQUIRE(d && dy && w_hwio && dx, "dgrad_tc: null argument");
+  MCN_REQUIRE(d->Cout % 8 == 0, "dgrad_tc: Cout=%d must be a multiple of 8", d->Cout);
+  MCN_REQUIRE(d->sh == 1 && d->sw == 1, "dgrad_tc: stride 1 only (strided dgrad is phase-decomposed by the host)");
+  MCN_REQUIRE(d->kh * d->kw <= kMaxTaps, "dgrad_tc: too many taps");
+  const bool pointwise = d->kh == 1 && d->kw == 1;
+  if (a_mode == 1 && (d->Cout % 64 != 0 || pointwise)) a_mode = 0;
+  GemmConvArgs a;
+  std::memset(&a, 0, sizeof(a));
+  int rc;
+  const int taps = d->kh * d->kw;
+  if (pointwise) {
+    PixelSpace ps{static_cast<int>((long long)d->N * d->H * d->W), 1, 1};
+    fill_geom_tiled(&a.g, ps);
+    uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)ps.W, 1, 1};
+    uint64_t stb[4] = {2, (uint64_t)d->Cout * 2, (uint64_t)ps.W * d->Cout * 2,
+                       (uint64_t)ps.W * d->Cout * 2};
+    uint32_t box[4] = {64, (uint32_t)a.g.TW, 1, 1};
+    if ((rc = encode_tiled(&a.mapA[0], dy, 4, dims, stb, box))) return rc;
+    a.out_sw = d->Cin;
+  } else if (a_mode == 0) {
+    PixelSpace ps{d->W, d->H, d->N};
+    fill_geom_tiled(&a.g, ps);
+    if ((rc = encode_nhwc(&a.mapA[0], dy, d->Cout, d->Wo, d->Ho, d->N, a.g.TW, a.g.TH, a.g.TN)))
+      return rc;
+    a.out_sw = d->Cin;
+    a.out_sh = (long long)d->W * d->Cin;
+    a.out_sn = (long long)d->H * d->W * d->Cin;
+  } else {
+    a.g.a_mode = 1;
+    a.g.Wo = d->W;
+    a.g.Ho = d->H;
+    a.g.Nb = d->N;
+    a.g.m_total = (long long)d->N * d->H * d->W;
+    a.g.str_w = a.g.str_h = 1;
+    a.g.low_w = d->pad_l - (d->kw - 1) * d->dw;
+    a.g.low_h = d->pad_t - (d->kh - 1) * d->dh;
+    const int up_w = (d->W - 1) + a.g.low_w - (d->Wo - 1);
+    const int up_h = (d->H - 1) + a.g.low_h - (d->Ho - 1);
+    if ((rc = encode_im2col(&a.mapA[0], dy, d->Cout, d->Wo, d->Ho, d->N, a.g.low_w, a.g.low_h,
+                            up_w, up_h, 1, 1)))
+      return rc;
+    a.out_sw = d->Cin;
+    a.out_sh = (long long)d->W * d->Cin;
+    a.out_sn = (long long)d->H * d->W * d->Cin;
+  }
+  for (int i = 1; i < 4; ++i) a.mapA[i] = a.mapA[0];
+  a.block_n = pick_block_n(d->Cin);
+  a.tiles_n = (d->Cin + a.block_n - 1) / a.block_n;
+  if ((rc = encode_matrix(&a.mapB, w_hwio, (long long)taps * d->Cin, d->Cout, a.block_n))) return rc;
+  a.taps = taps;
+  a.k_chunks = (d->Cout + 63) / 64;
+  {
+    int rem = d->Cout - (a.k_chunks - 1) * 64;
+    a.ksteps_last = (rem + 15) / 16;
+  }
+  a.n_total = d->Cin;
+  a.out = dx;
+  a.out_f32 = (dx_dtype == MCN_F32);
+  a.bias = nullptr;
+  a.vec_ok = (d->Cin % 8 == 0);
+  for (int r = 0; r < d->kh; ++r)
+    for (int s = 0; s < d->kw; ++s) {
+      int t = r * d->kw + s;
+      a.tab.brow[t] = t * d->Cin;
+      a.tab.map[t] = 0;
+      if (a.g.a_mode == 0 && !pointwise) {
+        a.tab.dh[t] = (short)(d->pad_t - r * d->dh);
+        a.tab.dw[t] = (short)(d->pad_l - s * d->dw);
+      } else {
+        a.tab.dh[t] = (short)((d->kh - 1 - r) * d->dh);
+        a.tab.dw[t] = (short)((d->kw - 1 - s) * d->dw);
+      }
+    }
+  return launch_gemm_conv(a, tiles_m_of(a.g), static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mcn_conv2d_wgrad_tc(const mcn_conv_desc* d, const void* x, const void* dy,
+                                   float* dw, int a_mode, void* stream) {
+  MCN_REQUIRE(d && x && dy && dw, "wgrad_tc: null argument");
+  MCN_REQUIRE(d->Cin % 8 == 0 && d->Cout % 8 == 0, "wgrad_tc: channels must be multiples of 8");
+  MCN_REQUIRE(d->kh * d->kw <= kMaxTaps, "wgrad_tc: too many taps");
+  const bool pointwise = d->kh == 1 && d->kw == 1 && d->sh == 1 && d->sw == 1;
+  if (a_mode == 1 && (d->Cin % 64 != 0 || pointwise)) a_mode = 0;
+  MCN_REQUIRE(a_mode == 1 || (d->sh == 1 && d->sw == 1) || (d->kh == 1 && d->kw == 1),
+              "wgrad_tc: box mode supports stride 1 (or 1x1 kernels) only");
+  WgradArgs a;
+  std::memset(&a, 0, sizeof(a));
+  int rc;
+  const int taps = d->kh * d->kw;
+  a.block_n = pick_block_n(d->Cout);
+  if (a.block_n > 128) a.block_n = 128;  // keep a stage at 64 KB
+  a.nb_atoms = a.block_n / 64;
+  if (pointwise) {
+    PixelSpace ps{static_cast<int>((long long)d->N * d->H * d->W), 1, 1};
+    fill_geom_tiled(&a.g, ps);
+    uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)ps.W, 1, 1};
+    uint64_t stb[4] = {2, (uint64_t)d->Cin * 2, (uint64_t)ps.W * d->Cin * 2,
+                       (uint64_t)ps.W * d->Cin * 2};
+    uint32_t box[4] = {64, (uint32_t)a.g.TW, 1, 1};
+    if ((rc = encode_tiled(&a.mapX[0], x, 4, dims, stb, box))) return rc;
+    uint64_t dimsy[4] = {(uint64_t)d->Cout, (uint64_t)ps.W, 1, 1};
+    uint64_t sty[4] = {2, (uint64_t)d->Cout * 2, (uint64_t)ps.W * d->Cout * 2,
+                       (uint64_t)ps.W * d->Cout * 2};
+    if ((rc = encode_tiled(&a.mapDy, dy, 4, dimsy, sty, box))) return rc;
+  } else if (a_mode == 0) {
+    PixelSpace ps{d->Wo, d->Ho, d->N};
+    fill_geom_tiled(&a.g, ps);
+    if (d->sh == 1 && d->sw == 1) {
+      if ((rc = encode_nhwc(&a.mapX[0], x, d->Cin, d->W, d->H, d->N, a.g.TW, a.g.TH, a.g.TN)))
+        return rc;
+    } else {
+      uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->Wo, (uint64_t)d->Ho, (uint64_t)d->N};
+      uint64_t stb[4] = {2, (uint64_t)d->sw * d->Cin * 2, (uint64_t)d->sh * d->W * d->Cin * 2,
+                         (uint64_t)d->H * d->W * d->Cin * 2};
+      uint32_t box[4] = {64, (uint32_t)a.g.TW, (uint32_t)a.g.TH, (uint32_t)a.g.TN};
+      if ((rc = encode_tiled(&a.mapX[0], x, 4, dims, stb, box))) return rc;
+    }
+    if ((rc = encode_nhwc(&a.mapDy, dy, d->Cout, d->Wo, d->Ho, d->N, a.g.TW, a.g.TH, a.g.TN)))
+      return rc;
+  } else {
+    a.g.a_mode = 1;
+    a.g.Wo = d->Wo;
+    a.g.Ho = d->Ho;
+    a.g.Nb = d->N;
+    a.g.m_total = (long long)d->N * d->Ho * d->Wo;
+    a.g.str_w = d->sw;
+    a.g.str_h = d->sh;
+    a.g.low_w = -d->pad_l;
+    a.g.low_h = -d->pad_t;
+    const int up_w = (d->Wo - 1) * d->sw - d->pad_l - (d->W - 1);
+    const int up_h = (d->Ho - 1) * d->sh - d->pad_t - (d->H - 1);
+    if ((rc = encode_im2col(&a.mapX[0], x, d->Cin, d->W, d->H, d->N, a.g.low_w, a.g.low_h, up_w,
+                            up_h, d->sw, d->sh)))
+      return rc;
+    uint64_t dimsy[4] = {(uint64_t)d->Cout, (uint64_t)a.g.m_total, 1, 1};
+    uint64_t sty[4] = {2, (uint64_t)d->Cout * 2, (uint64_t)a.g.m_total * d->Cout * 2,
+                       (uint64_t)a.g.m_total * d->Cout * 2};
+    uint32_t box[4] = {64, 128, 1, 1};
+    if ((rc = encode_tiled(&a.mapDy, dy, 4, dimsy, sty, box))) return rc;
+  }
+  for (int i = 1; i < 4; ++i) a.mapX[i] = a.mapX[0];
+  a.taps = taps;
+  a.cin = d->Cin;
+  a.cout = d->Cout;
+  a.dw = dw;
+  a.tiles_mi = (d->Cin + 127) / 128;
+  a.tiles_ni = (d->Cout + a.block_n - 1) / a.block_n;
+  a.kblocks_total = tiles_m_of(a.g);
+  a.ksteps = (a.g.a_mode == 0) ? (a.g.rows_box + 15) / 16 : 8;
+  {
+    const int base = taps * a.tiles_mi * a.tiles_ni;
+    int want = (2 * num_sms() + base - 1) / base;
+    a.splits = std::max(1, std::min(want, a.kblocks_total));
+  }
+  for (int r = 0; r < d->kh; ++r)
+    for (int s = 0; s < d->kw; ++s) {
+      int t = r * d->kw + s;
+      a.tab.brow[t] = 0;
+      a.tab.map[t] = 0;
+      if (a.g.a_mode == 0 && !pointwise) {
+        a.tab.dh[t] = (short)(r * d->dh - d->pad_t);
+        a.tab.dw[t] = (short)(s * d->dw - d->pad_l);
+      } else {
+        a.tab.dh[t] = (short)(r * d->dh);
+        a.tab.dw[t] = (short)(s * d->dw);
+      }
+    }
+  const uint32_t stage_bytes = (2 + a.nb_atoms) * kABytes;
+  a.stages = std::max(2, std::min(4, (int)((200 * 1024) / stage_bytes)));
+  a.tmem_cols = tmem_cols_for(a.block_n);
+  size_t smem = (size_t)a.stages * stage_bytes + (2 * a.stages + 1) * 8 + 16 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             smem_optin_limit()) != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(wgrad_kernel) failed");
+      return MCN_ECUDA;
+    }
+    configured = true;
+  }
+  dim3 grid((unsigned)(taps * a.tiles_mi * a.tiles_ni * a.splits));
+  wgrad_kernel<<<grid, 192, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  return after_launch("wgrad_kernel");
+}
