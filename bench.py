@@ -1,0 +1,326 @@
+"""Benchmark of the hot path: ResNet-v1.5-50 data-parallel training step on synthetic ImageNet-shaped
+data (BASELINE.json configs[1]: batch 256 per GPU, bf16, synchronised BN across GPUs).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's B200 path
+  python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
+
+One JSON line on stdout (rank 0).  `value` times the step with inputs resident in HBM; `e2e` times
+the same step through the public API with HOST input buffers (pinned) copied in and the loss read
+back every step.  `roofline` describes the kernel class that takes the largest share of the step,
+timed live with CUDA events on the launching stream.  `cpu_baseline` is the CPU restatement of the
+reference's num_gpus=0 path (TensorFlow cannot be installed here: see oracle/tf_ops.py) on a
+bounded sample (batch 32, fp32), timed on this box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODEL = "ResNet-v1.5-50"
+IMG = [224, 224, 3]
+NCLS = 1000
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self.stop_flag = False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------ CPU reference arm
+def cpu_reference_step_rate(steps, warmup, batch=32):
+    """Times the oracle restatement of the reference step (fwd + bwd + Nesterov update, fp32) on
+    the host cores.  Returns (img/s, seconds per step, threads)."""
+    import numpy as np
+    import torch
+    from myconvnet_b200 import convnet as pconv
+    from myconvnet_b200 import loader
+    from myconvnet_b200.engine import draw_initial_value
+    from myconvnet_b200.zoo import resnet50
+    from oracle import ref_convnet
+    from oracle.step import OracleTrainer
+
+    pm, _ = resnet50(IMG, NCLS, batch_size=batch, compute_dtype="f32")
+    rng = np.random.default_rng(0)
+    vals = {v.name: draw_initial_value(v, rng) for v in pm.graph.vars.values()}
+    if loader.reference_root() is not None:
+        om = loader.load_reference_model("models/resnet_v1_5.py", {"convnet": ref_convnet}).ResNet50(IMG, NCLS)
+    else:
+        import types
+        from myconvnet_b200 import zoo
+        om = type("OracleResNet50", (ref_convnet.ConvNet,),
+                  {"_build_model": zoo.ResNet50._build_model, "_bottleneck": zoo.ResNet50._bottleneck,
+                   "channels": zoo.ResNet50.channels, "units": zoo.ResNet50.units,
+                   "strides": zoo.ResNet50.strides})(IMG, NCLS)
+    om.set_variables(vals)
+    tr = OracleTrainer(om)
+    X = rng.uniform(size=[batch] + IMG).astype(np.float32)
+    Y = rng.integers(0, NCLS, size=batch)
+    for _ in range(warmup):
+        tr.step(X, Y)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tr.step(X, Y)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return batch / dt, dt, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    rate, dt, threads = cpu_reference_step_rate(steps, warmup)
+    line = {
+        "impl": "reference", "metric": "train_images_per_sec", "value": rate, "unit": "img/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "%s train step, synthetic 224x224x3" % MODEL,
+                   "sample": "batch 32 per step on the host cores (bounded sample of the batch-256 workload)"},
+        "cpu_baseline": {"value": rate, "unit": "img/s", "cores": threads, "kind": "port",
+                         "sample": "%d steps of batch 32, fp32, torch-CPU restatement of the reference "
+                                   "num_gpus=0 path (TensorFlow unavailable offline)" % steps},
+        "e2e": {"value": rate, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ roofline helpers
+def launch_work(name, args, esz):
+    """Algorithmic (bytes, flops) of one libmcn launch from its resolved argument tuple."""
+    import ctypes
+    if name in ("mcn_conv2d_fprop_tc", "mcn_conv2d_dgrad_tc", "mcn_conv2d_wgrad_tc"):
+        d = args[0]._obj
+        m = d.N * d.Ho * d.Wo
+        flops = 2.0 * m * d.kh * d.kw * d.Cin * d.Cout
+        byt = esz * (d.N * d.H * d.W * d.Cin + m * d.Cout) + esz * d.kh * d.kw * d.Cin * d.Cout
+        return byt, flops
+    if name == "mcn_bn_stats":
+        return args[2] * args[3] * esz, 0.0
+    if name == "mcn_bn_apply":
+        n = args[2] * args[3]
+        return n * esz * (2 + (1 if args[8] else 0)), 0.0
+    if name == "mcn_bn_bwd_reduce":
+        n = args[4] * args[5]
+        return n * esz * (2 + (1 if args[3] else 0)), 0.0
+    if name == "mcn_bn_bwd_apply":
+        n = args[4] * args[5]
+        return n * esz * (3 + (1 if args[3] else 0) + (1 if args[16] else 0)), 0.0
+    return 0.0, 0.0
+
+
+def kernel_class(name, tag):
+    if name == "mcn_conv2d_fprop_tc":
+        return "conv_fprop_tc" if not tag.endswith("/dgrad") else "conv_dgrad_tc"
+    return name.replace("mcn_", "")
+
+
+def profile_step(eng):
+    """Times every launch of one step with CUDA events (eager, serialised on the launching stream).
+    Returns {class: [ms, bytes, flops, launches]}."""
+    import torch
+    from myconvnet_b200 import lib as L
+    st = torch.cuda.current_stream().cuda_stream
+    L.check(eng.lib.mcn_fill_f32(eng._zero_ptr, eng._zero_n, 0.0, st))
+    recs = []
+    for launches in (eng._fwd, eng._bwd):
+        for fn, args, name, tag in launches:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            L.check(fn(*args, st), name)
+            e1.record()
+            recs.append((name, tag, args, e0, e1))
+    torch.cuda.synchronize()
+    esz = 2 if eng.plan.cdt == "bf16" else 4
+    out = {}
+    for name, tag, args, e0, e1 in recs:
+        ms = e0.elapsed_time(e1)
+        byt, fl = launch_work(name, args, esz)
+        c = out.setdefault(kernel_class(name, tag), [0.0, 0.0, 0.0, 0])
+        c[0] += ms
+        c[1] += byt
+        c[2] += fl
+        c[3] += 1
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--profile-json", default=None, help="write the per-kernel-class table here")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    from myconvnet_b200 import lib as L
+    from myconvnet_b200.engine import Engine
+    from myconvnet_b200.zoo import resnet50
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    pg = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        pg = dist.group.WORLD
+    warmup = max(args.warmup, 3)
+    model, model_src = resnet50(IMG, NCLS, batch_size=args.batch, compute_dtype="bf16")
+    eng = Engine(model, optimizer="nesterov", world_size=world, rank=rank, process_group=pg,
+                 use_cuda_graph=(world == 1 and not args.no_graph), seed=0, fetch_pred=False)
+    rng = np.random.default_rng(1234 + rank)
+    X = torch.from_numpy(rng.uniform(size=[args.batch] + IMG).astype(np.float32)).pin_memory()
+    Y = torch.from_numpy(rng.integers(0, NCLS, size=args.batch).astype(np.int32)).pin_memory()
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing
+    eng.load_inputs(X=X, Y=Y)
+    for _ in range(warmup):
+        eng.train_step(fetch_loss=False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.launch_count()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        eng.train_step(fetch_loss=False)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    sampler.stop_flag = True
+    loss = eng.read_loss()
+    eager_launches = eng.launches_per_step()
+    # ---- end-to-end: host buffers in, loss out, every step
+    for _ in range(2):
+        eng.train_step(X, Y, fetch_loss=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.train_step(X, Y, fetch_loss=True)
+    barrier()
+    ms_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms, ms_e2e], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel class (live CUDA-event timing of every launch)
+    hbm_peak, tc_peak, peak_src = measured_peaks()
+    prof = profile_step(eng)
+    prof = profile_step(eng)
+    total_ms = sum(v[0] for v in prof.values())
+    top = max(prof.items(), key=lambda kv: kv[1][0])
+    cname, (cms, cbytes, cflops, cn) = top
+    tensor_bound = cflops > 0 and (cflops / (tc_peak * 1e12)) > (cbytes / (hbm_peak * 1e9))
+    if tensor_bound:
+        ach = cflops / (cms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s", "frac": ach / tc_peak}
+    else:
+        ach = cbytes / (cms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak}
+    roof.update({"kernel": cname, "launches_per_step": cn, "share_of_step": cms / total_ms,
+                 "peak_source": peak_src, "traffic": None,
+                 "note": "aggregate over the class's launches in one step; algorithmic bytes/flops per DESIGN.md"})
+    table = {k: {"ms": v[0], "GB": v[1] / 1e9, "TFLOP": v[2] / 1e12, "launches": v[3],
+                 "GB/s": (v[1] / 1e9) / (v[0] * 1e-3) if v[0] > 0 else 0,
+                 "TFLOP/s": (v[2] / 1e12) / (v[0] * 1e-3) if v[0] > 0 else 0}
+             for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
+    if args.profile_json:
+        os.makedirs(os.path.dirname(args.profile_json) or ".", exist_ok=True)
+        json.dump({"serialized_step_ms": total_ms, "graph_step_ms": ms, "classes": table},
+                  open(args.profile_json, "w"), indent=1)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        rate, dt, threads = cpu_reference_step_rate(steps=2, warmup=1)
+        cpu = {"value": rate, "unit": "img/s", "cores": threads, "kind": "port",
+               "sample": "2 steps of batch 32 fp32 (oracle restatement of the reference num_gpus=0 path; "
+                         "TensorFlow unavailable offline), %.1f s/step" % dt}
+    gb = args.batch * world
+    line = {
+        "metric": "train_images_per_sec", "value": gb / (ms * 1e-3), "unit": "img/s", "n_gpus": world,
+        "steps": args.steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "%s train step (fwd+bwd+Nesterov/L2/EMA update), synthetic 224x224x3, "
+                               "1000 classes, batch %d/GPU, bf16 activations + fp32 master weights, sync-BN"
+                               % (MODEL, args.batch),
+                   "global_batch": gb, "parallelism": "dp%d" % world, "model_source": model_src,
+                   "l2_flush": "not needed: one step touches %.1f GB of HBM per GPU (>> 126 MB L2)"
+                               % (eng.plan.arena_bytes / 1e9),
+                   "cuda_graph": bool(eng.use_cuda_graph and world == 1)},
+        "e2e": {"value": gb / (ms_e2e * 1e-3), "unit": "img/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": int(X.numel() * 4 + Y.numel() * 4 + 64), "d2h_bytes_per_step": 8},
+        "gpu_launches": eager_launches * args.steps,
+        "launches_counted_by_library": L.launch_count() - launches0,
+        "final_loss": loss,
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "clocks": sampler.summary(),
+    }
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

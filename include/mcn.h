@@ -70,7 +70,7 @@ int mcn_conv2d_wgrad_tc(const mcn_conv_desc* d, const void* x, const void* dy, f
 
 /* ---- dense / depthwise convolution, CUDA-core direct path (any dtype, any geometry).
  * Same call sites as above plus tf.nn.depthwise_conv2d (convnet.py:1645).  Weights HWIO
- * (depthwise: [kh][kw][C][mult]) in `wdtype`; wgrad writes fp32 (overwrites). */
+ * (depthwise: [kh][kw][C][mult]) in `wdtype`; wgrad ACCUMULATES into fp32 (zero first). */
 int mcn_conv2d_fprop_direct(const mcn_conv_desc* d, int dtype, const void* x, int wdtype,
                             const void* w, const float* bias, void* y, void* stream);
 int mcn_conv2d_dgrad_direct(const mcn_conv_desc* d, int dtype, const void* dy, int wdtype,
@@ -90,8 +90,6 @@ int mcn_weight_prep(const float* w_hwio_f32, int taps, int cin, int cout, void* 
 /* Explicit im2col for channel counts the TMA path cannot address (Cin % 8 != 0: RGB stems).
  * col: bf16 [N*Ho*Wo][kpad], kpad >= kh*kw*Cin, zero padded. */
 int mcn_im2col(const mcn_conv_desc* d, int dtype, const void* x, void* col, int kpad, void* stream);
-int mcn_col2im(const mcn_conv_desc* d, const void* dcol, int kpad, void* dx, int dx_dtype,
-               void* stream);
 
 /* ---- batch normalisation (tf.nn.fused_batch_norm, convnet.py:1883-1896,1916) ----
  * rows = N*H*W, C channels.
@@ -197,7 +195,8 @@ int mcn_sigmoid_xent(const float* logits, long long n, float label, float weight
  * optimiser rule, decoupled weight decay on the post-step value; then bf16 copies refreshed. */
 typedef struct {
   float* w;            /* fp32 master */
-  const float* g;      /* fp32 gradient (already averaged over ranks) */
+  const float* g;      /* fp32 gradient (already averaged over ranks); NULL = not trainable:
+                          only the EMA shadow and the bf16 copies are refreshed */
   float* m;            /* momentum / Adam m / RMSProp mom */
   float* v;            /* Adam v / RMSProp ms (NULL for SGD) */
   float* ema;          /* EMA shadow (NULL = none) */
@@ -210,13 +209,13 @@ typedef struct {
 } mcn_opt_tensor;
 typedef enum { MCN_OPT_NESTEROV = 0, MCN_OPT_RMSPROP = 1, MCN_OPT_ADAM = 2 } mcn_opt_kind;
 /* table: device array of mcn_opt_tensor; hp (device, 8 floats): lr, momentum(beta1),
- * beta2/decay, eps, ema_decay_t, adam_lr_t, grad_scale, unused — read on device so a captured
- * CUDA graph can be replayed with new hyper-parameters. */
+ * beta2/decay, eps, ema_decay_t, adam_lr_t, grad_scale, weight-decay multiplier — read on device
+ * so a captured CUDA graph can be replayed with new hyper-parameters. */
 int mcn_opt_step(int kind, const mcn_opt_tensor* table, int ntensors, long long max_n,
-                 const float* hp, void* stream);
-/* EMA only (BN moving statistics shadows). */
-int mcn_ema_update(float* const* shadows, const float* const* values, const long long* sizes,
-                   int ntensors, long long max_n, const float* hp, void* stream);
+                 const float* hp, float* l2_loss, void* stream);
+/* out[t][c][r] += in[t][r][c]: gradient of a transposed-conv weight (stored [kh,kw,Cin,Cout],
+ * reference convnet.py:2460-2462) from the wgrad of the underlying conv. */
+int mcn_transpose_add_f32(const float* in, int taps, int rows, int cols, float* out, void* stream);
 
 /* ---- generic helpers ---- */
 int mcn_fill_f32(float* p, long long n, float v, void* stream);

@@ -683,20 +683,44 @@ extern "C" int mcn_conv2d_fprop_tc(const mcn_conv_desc* d, const void* x, const 
   return launch_gemm_conv(a, tiles_m_of(a.g), static_cast<cudaStream_t>(stream));
 }
 
-// dgrad for stride 1: a stride-1 correlation of dy with the taps mirrored.
-//   dx[n,h,w,ci] = sum_{r,s,co} dy[n, h + pad_t - r*dh, w + pad_l - s*dw, co] * W[r,s,ci,co]
-extern "C" int mcn_conv2d_dgrad_tc(const mcn_conv_desc* d, const void* dy, const void* w_hwio,
-                                   void* dx, int dx_dtype, int a_mode, void* stream) {
-  MCN_REQUIRE(d && dy && w_hwio && dx, "dgrad_tc: null argument");
-  MCN_REQUIRE(d->Cout % 8 == 0, "dgrad_tc: Cout=%d must be a multiple of 8", d->Cout);
-  MCN_REQUIRE(d->sh == 1 && d->sw == 1, "dgrad_tc: stride 1 only (strided dgrad is phase-decomposed by the host)");
-  MCN_REQUIRE(d->kh * d->kw <= kMaxTaps, "dgrad_tc: too many taps");
-  const bool pointwise = d->kh == 1 && d->kw == 1;
-  if (a_mode == 1 && (d->Cout % 64 != 0 || pointwise)) a_mode = 0;
+// dgrad.
+//   dx[n,h,w,ci] = sum_{r,s,co} dy[n, (h + pad_t - r*dh)/sh, (w + pad_l - s*dw)/sw, co] * W[r,s,ci,co]
+// over the taps for which the divisions are exact.  For stride 1 this is a correlation of dy with
+// the mirrored taps.  For stride > 1 the input pixels split into sh*sw phases (h % sh, w % sw);
+// each phase is a stride-1 correlation of dy with the subset of taps of matching parity, written
+// to a strided view of dx — one launch per phase, no zero-insertion, no wasted MACs.
+static int dgrad_phase(const mcn_conv_desc* d, const void* dy, const void* w_hwio, void* dx,
+                       int dx_dtype, int a_mode, int ph, int pw, bool* empty, cudaStream_t st) {
   GemmConvArgs a;
   std::memset(&a, 0, sizeof(a));
   int rc;
-  const int taps = d->kh * d->kw;
+  const size_t esz = (dx_dtype == MCN_F32) ? 4 : 2;
+  // pixel grid of this phase
+  const int Ha = (d->H - ph + d->sh - 1) / d->sh;
+  const int Wa = (d->W - pw + d->sw - 1) / d->sw;
+  // taps of matching parity and their dy offsets e (dy row = a + e)
+  int nt = 0, e_h[kMaxTaps], e_w[kMaxTaps], tap_id[kMaxTaps];
+  int min_eh = 1 << 30, min_ew = 1 << 30;
+  for (int r = 0; r < d->kh; ++r) {
+    int th = ph + d->pad_t - r * d->dh;
+    if (((th % d->sh) + d->sh) % d->sh != 0) continue;
+    for (int s = 0; s < d->kw; ++s) {
+      int tw = pw + d->pad_l - s * d->dw;
+      if (((tw % d->sw) + d->sw) % d->sw != 0) continue;
+      // exact division (th, tw are multiples of the stride, possibly negative)
+      e_h[nt] = th / d->sh;
+      e_w[nt] = tw / d->sw;
+      tap_id[nt] = r * d->kw + s;
+      min_eh = std::min(min_eh, e_h[nt]);
+      min_ew = std::min(min_ew, e_w[nt]);
+      ++nt;
+    }
+  }
+  *empty = (nt == 0 || Ha <= 0 || Wa <= 0);
+  if (*empty) return MCN_OK;
+  const bool unit = (d->sh == 1 && d->sw == 1);
+  const bool pointwise = unit && d->kh == 1 && d->kw == 1;
+  if (a_mode == 1 && (d->Cout % 64 != 0 || pointwise)) a_mode = 0;
   if (pointwise) {
     PixelSpace ps{static_cast<int>((long long)d->N * d->H * d->W), 1, 1};
     fill_geom_tiled(&a.g, ps);
@@ -707,60 +731,91 @@ extern "C" int mcn_conv2d_dgrad_tc(const mcn_conv_desc* d, const void* dy, const
     if ((rc = encode_tiled(&a.mapA[0], dy, 4, dims, stb, box))) return rc;
     a.out_sw = d->Cin;
   } else if (a_mode == 0) {
-    PixelSpace ps{d->W, d->H, d->N};
+    PixelSpace ps{Wa, Ha, d->N};
     fill_geom_tiled(&a.g, ps);
     if ((rc = encode_nhwc(&a.mapA[0], dy, d->Cout, d->Wo, d->Ho, d->N, a.g.TW, a.g.TH, a.g.TN)))
       return rc;
-    a.out_sw = d->Cin;
-    a.out_sh = (long long)d->W * d->Cin;
-    a.out_sn = (long long)d->H * d->W * d->Cin;
   } else {
     a.g.a_mode = 1;
-    a.g.Wo = d->W;
-    a.g.Ho = d->H;
+    a.g.Wo = Wa;
+    a.g.Ho = Ha;
     a.g.Nb = d->N;
-    a.g.m_total = (long long)d->N * d->H * d->W;
+    a.g.m_total = (long long)d->N * Ha * Wa;
     a.g.str_w = a.g.str_h = 1;
-    a.g.low_w = d->pad_l - (d->kw - 1) * d->dw;
-    a.g.low_h = d->pad_t - (d->kh - 1) * d->dh;
-    const int up_w = (d->W - 1) + a.g.low_w - (d->Wo - 1);
-    const int up_h = (d->H - 1) + a.g.low_h - (d->Ho - 1);
+    a.g.low_w = min_ew;
+    a.g.low_h = min_eh;
+    const int up_w = (Wa - 1) + a.g.low_w - (d->Wo - 1);
+    const int up_h = (Ha - 1) + a.g.low_h - (d->Ho - 1);
     if ((rc = encode_im2col(&a.mapA[0], dy, d->Cout, d->Wo, d->Ho, d->N, a.g.low_w, a.g.low_h,
                             up_w, up_h, 1, 1)))
       return rc;
-    a.out_sw = d->Cin;
-    a.out_sh = (long long)d->W * d->Cin;
+  }
+  if (!pointwise) {
+    a.out_sw = (long long)d->sw * d->Cin;
+    a.out_sh = (long long)d->sh * d->W * d->Cin;
     a.out_sn = (long long)d->H * d->W * d->Cin;
   }
   for (int i = 1; i < 4; ++i) a.mapA[i] = a.mapA[0];
   a.block_n = pick_block_n(d->Cin);
   a.tiles_n = (d->Cin + a.block_n - 1) / a.block_n;
-  if ((rc = encode_matrix(&a.mapB, w_hwio, (long long)taps * d->Cin, d->Cout, a.block_n))) return rc;
-  a.taps = taps;
+  if ((rc = encode_matrix(&a.mapB, w_hwio, (long long)d->kh * d->kw * d->Cin, d->Cout, a.block_n)))
+    return rc;
+  a.taps = nt;
   a.k_chunks = (d->Cout + 63) / 64;
   {
     int rem = d->Cout - (a.k_chunks - 1) * 64;
     a.ksteps_last = (rem + 15) / 16;
   }
   a.n_total = d->Cin;
-  a.out = dx;
+  a.out = static_cast<uint8_t*>(dx) + ((size_t)ph * d->W + pw) * d->Cin * esz;
   a.out_f32 = (dx_dtype == MCN_F32);
   a.bias = nullptr;
   a.vec_ok = (d->Cin % 8 == 0);
-  for (int r = 0; r < d->kh; ++r)
-    for (int s = 0; s < d->kw; ++s) {
-      int t = r * d->kw + s;
-      a.tab.brow[t] = t * d->Cin;
-      a.tab.map[t] = 0;
-      if (a.g.a_mode == 0 && !pointwise) {
-        a.tab.dh[t] = (short)(d->pad_t - r * d->dh);
-        a.tab.dw[t] = (short)(d->pad_l - s * d->dw);
-      } else {
-        a.tab.dh[t] = (short)((d->kh - 1 - r) * d->dh);
-        a.tab.dw[t] = (short)((d->kw - 1 - s) * d->dw);
-      }
+  for (int t = 0; t < nt; ++t) {
+    a.tab.brow[t] = tap_id[t] * d->Cin;
+    a.tab.map[t] = 0;
+    if (a.g.a_mode == 0 && !pointwise) {
+      a.tab.dh[t] = (short)e_h[t];
+      a.tab.dw[t] = (short)e_w[t];
+    } else {
+      a.tab.dh[t] = (short)(e_h[t] - min_eh);
+      a.tab.dw[t] = (short)(e_w[t] - min_ew);
     }
-  return launch_gemm_conv(a, tiles_m_of(a.g), static_cast<cudaStream_t>(stream));
+  }
+  return launch_gemm_conv(a, tiles_m_of(a.g), st);
+}
+
+extern "C" int mcn_conv2d_dgrad_tc(const mcn_conv_desc* d, const void* dy, const void* w_hwio,
+                                   void* dx, int dx_dtype, int a_mode, void* stream) {
+  MCN_REQUIRE(d && dy && w_hwio && dx, "dgrad_tc: null argument");
+  MCN_REQUIRE(d->Cout % 8 == 0, "dgrad_tc: Cout=%d must be a multiple of 8", d->Cout);
+  MCN_REQUIRE(d->kh * d->kw <= kMaxTaps, "dgrad_tc: too many taps");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t esz = (dx_dtype == MCN_F32) ? 4 : 2;
+  // phases without a contributing tap (e.g. 1x1 stride 2) stay zero
+  bool any_empty = false;
+  for (int ph = 0; ph < d->sh && !any_empty; ++ph)
+    for (int pw = 0; pw < d->sw && !any_empty; ++pw) {
+      bool hit = false;
+      for (int r = 0; r < d->kh && !hit; ++r)
+        for (int s = 0; s < d->kw && !hit; ++s)
+          hit = (((ph + d->pad_t - r * d->dh) % d->sh) == 0) &&
+                (((pw + d->pad_l - s * d->dw) % d->sw) == 0);
+      any_empty = !hit;
+    }
+  if (any_empty) {
+    if (cudaMemsetAsync(dx, 0, (size_t)d->N * d->H * d->W * d->Cin * esz, st) != cudaSuccess) {
+      set_error("dgrad_tc: memset failed");
+      return MCN_ECUDA;
+    }
+  }
+  for (int ph = 0; ph < d->sh; ++ph)
+    for (int pw = 0; pw < d->sw; ++pw) {
+      bool empty = false;
+      int rc = dgrad_phase(d, dy, w_hwio, dx, dx_dtype, a_mode, ph, pw, &empty, st);
+      if (rc) return rc;
+    }
+  return MCN_OK;
 }
 
 extern "C" int mcn_conv2d_wgrad_tc(const mcn_conv_desc* d, const void* x, const void* dy,

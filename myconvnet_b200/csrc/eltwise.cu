@@ -1,0 +1,424 @@
+// Element-wise and data-movement kernels (all bandwidth-bound, 16-byte vectorised where the
+// shape allows).  Replaces the Eigen element-wise ops behind reference convnet.py:2500-2556
+// (activations, stochastic_depth add), :1694 (bias_add), :452/:466/:471 (input zero-centre,
+// scale, cast), efficientnet.py:163 (SE excite), tf.concat (deeplabv3plus.py:100,110) and
+// tf.image.resize_bilinear (convnet.py:2397).
+#include "mcn_common.cuh"
+
+namespace mcn {
+namespace {
+
+inline int grid_for(long long n, int block) {
+  return (int)std::max<long long>(1, std::min<long long>((n + block - 1) / block, 16LL * num_sms()));
+}
+
+// Generic vectorised map over up to two inputs.  F: float(float a, float b).
+template <typename T, bool kTwo, typename F>
+__global__ void map_kernel(const T* __restrict__ a, const T* __restrict__ b, long long n,
+                           T* __restrict__ y, F f) {
+  constexpr int V = Vec16<T>::N;
+  const long long nvec = n / V;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+    Vec16<T> va = ld_vec(a + v * V), vb, o;
+    if (kTwo) vb = ld_vec(b + v * V);
+#pragma unroll
+    for (int i = 0; i < V; ++i) o.set(i, f(va.get(i), kTwo ? vb.get(i) : 0.f));
+    st_vec(y + v * V, o);
+  }
+  // tail
+  for (long long i = nvec * V + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += stride)
+    y[i] = from_f32<T>(f(to_f32(a[i]), kTwo ? to_f32(b[i]) : 0.f));
+}
+
+template <typename T, bool kTwo, typename F>
+int launch_map(const void* a, const void* b, long long n, void* y, cudaStream_t st, F f,
+               const char* what) {
+  constexpr int V = Vec16<T>::N;
+  map_kernel<T, kTwo, F><<<grid_for((n + V - 1) / V, 256), 256, 0, st>>>(
+      static_cast<const T*>(a), static_cast<const T*>(b), n, static_cast<T*>(y), f);
+  return after_launch(what);
+}
+
+struct ActF {
+  int act;
+  float alpha;
+  __device__ float operator()(float a, float) const { return act_fwd(act, a, alpha); }
+};
+struct ActB {  // a = dy, b = x (pre-activation)
+  int act;
+  float alpha;
+  __device__ float operator()(float a, float b) const { return a * act_grad_from_x(act, b, alpha); }
+};
+struct AddActF {
+  int act;
+  float alpha;
+  __device__ float operator()(float a, float b) const { return act_fwd(act, a + b, alpha); }
+};
+struct AddActB {  // a = dy, b = y (output)
+  int act;
+  float alpha;
+  __device__ float operator()(float a, float b) const { return a * act_grad_from_y(act, b, alpha); }
+};
+struct AddF {
+  __device__ float operator()(float a, float b) const { return a + b; }
+};
+
+template <typename T>
+__global__ void scale_bcast_fwd_kernel(const T* __restrict__ x, const T* __restrict__ m, int HW,
+                                       int C, long long total, T* __restrict__ y) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    long long n = i / ((long long)HW * C);
+    y[i] = from_f32<T>(to_f32(x[i]) * to_f32(m[n * C + c]));
+  }
+}
+// dx = dy*m; dm[n,c] = sum_hw dy*x.  One block per (n, 32 channels).
+template <typename T>
+__global__ void scale_bcast_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                       const T* __restrict__ m, int HW, int C,
+                                       T* __restrict__ dx, float* __restrict__ dm) {
+  __shared__ float sh[8][33];
+  int n = blockIdx.y;
+  int c = blockIdx.x * 32 + threadIdx.x;
+  float acc = 0.f;
+  if (c < C) {
+    float mv = to_f32(m[(long long)n * C + c]);
+    for (int i = threadIdx.y; i < HW; i += 8) {
+      long long o = ((long long)n * HW + i) * C + c;
+      float g = to_f32(dy[o]);
+      acc = fmaf(g, to_f32(x[o]), acc);
+      dx[o] = from_f32<T>(g * mv);
+    }
+  }
+  sh[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += sh[j][threadIdx.x];
+    dm[(long long)n * C + c] = s;
+  }
+}
+
+template <typename T>
+__global__ void bias_add_kernel(T* __restrict__ y, long long total, int C,
+                                const float* __restrict__ bias) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x)
+    y[i] = from_f32<T>(to_f32(y[i]) + bias[i % C]);
+}
+// db[c] += sum_rows dy[r, c]; blockDim (32, 8), grid (C/32, row chunks)
+template <typename T>
+__global__ void bias_grad_kernel(const T* __restrict__ dy, long long rows, int C,
+                                 float* __restrict__ db) {
+  __shared__ float sh[8][33];
+  int c = blockIdx.x * 32 + threadIdx.x;
+  long long r0 = rows * blockIdx.y / gridDim.y, r1 = rows * (blockIdx.y + 1) / gridDim.y;
+  float acc = 0.f;
+  if (c < C)
+    for (long long r = r0 + threadIdx.y; r < r1; r += 8) acc += to_f32(dy[r * C + c]);
+  sh[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += sh[j][threadIdx.x];
+    atomicAdd(&db[c], s);
+  }
+}
+
+template <typename TS, typename TD>
+__global__ void cast_kernel(const TS* __restrict__ s, TD* __restrict__ d, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    d[i] = from_f32<TD>(to_f32(s[i]));
+}
+template <typename TD>
+__global__ void input_prep_kernel(const float* __restrict__ x, long long n, float mean, float scale,
+                                  TD* __restrict__ y) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    y[i] = from_f32<TD>((x[i] - mean) * scale);
+}
+
+template <typename T>
+__global__ void copy_channels_kernel(const T* __restrict__ src, long long rows, int Csrc,
+                                     int src_off, T* __restrict__ dst, int Cdst, int dst_off,
+                                     int Ccopy, int accumulate) {
+  const long long total = rows * Ccopy;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % Ccopy);
+    long long r = i / Ccopy;
+    T v = src[r * Csrc + src_off + c];
+    T* d = dst + r * Cdst + dst_off + c;
+    *d = accumulate ? from_f32<T>(to_f32(*d) + to_f32(v)) : v;
+  }
+}
+
+// Bilinear resize source coordinate (TF semantics).
+__device__ __forceinline__ float src_coord(int dst, int in, int out, int mode) {
+  if (mode == 1) return out > 1 ? dst * (float)(in - 1) / (float)(out - 1) : 0.f;
+  if (mode == 2) {
+    float s = ((float)dst + 0.5f) * ((float)in / (float)out) - 0.5f;
+    return s;
+  }
+  return dst * ((float)in / (float)out);
+}
+__device__ __forceinline__ void lerp_idx(int dst, int in, int out, int mode, int* lo, int* hi,
+                                         float* frac) {
+  float s = src_coord(dst, in, out, mode);
+  float fl = floorf(s);
+  *lo = max((int)fl, 0);
+  *hi = min((int)ceilf(s), in - 1);
+  if (mode == 2) {
+    // half-pixel: tf clamps the indices, keeps the fractional part of the unclamped coordinate
+    *lo = min(max((int)fl, 0), in - 1);
+    *hi = min(max((int)fl + 1, 0), in - 1);
+  }
+  *frac = s - fl;
+}
+template <typename T>
+__global__ void resize_fwd_kernel(const T* __restrict__ x, int N, int H, int W, int C, int Ho,
+                                  int Wo, int mode, T* __restrict__ y) {
+  const long long total = (long long)N * Ho * Wo * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    long long r = i / C;
+    int q = (int)(r % Wo);
+    r /= Wo;
+    int p = (int)(r % Ho);
+    int n = (int)(r / Ho);
+    int h0, h1, w0, w1;
+    float fh, fw;
+    lerp_idx(p, H, Ho, mode, &h0, &h1, &fh);
+    lerp_idx(q, W, Wo, mode, &w0, &w1, &fw);
+    const T* b = x + (long long)n * H * W * C + c;
+    float tl = to_f32(b[((long long)h0 * W + w0) * C]), tr = to_f32(b[((long long)h0 * W + w1) * C]);
+    float bl = to_f32(b[((long long)h1 * W + w0) * C]), br = to_f32(b[((long long)h1 * W + w1) * C]);
+    float top = tl + (tr - tl) * fw, bot = bl + (br - bl) * fw;
+    y[i] = from_f32<T>(top + (bot - top) * fh);
+  }
+}
+// backward scatters with fp32 atomics into an fp32 scratch-free path: dx must be fp32-zeroed by
+// the caller when T is float; for bf16 we gather instead (deterministic): each input pixel scans
+// the output rows/cols that can touch it.
+template <typename T>
+__global__ void resize_bwd_kernel(const T* __restrict__ dy, int N, int H, int W, int C, int Ho,
+                                  int Wo, int mode, T* __restrict__ dx) {
+  const long long total = (long long)N * H * W * C;
+  // conservative footprint of one input pixel in output space
+  const int rh = (int)ceilf((float)Ho / (float)max(H - (mode == 1 ? 1 : 0), 1)) + 1;
+  const int rw = (int)ceilf((float)Wo / (float)max(W - (mode == 1 ? 1 : 0), 1)) + 1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    long long r = i / C;
+    int w = (int)(r % W);
+    r /= W;
+    int h = (int)(r % H);
+    int n = (int)(r / H);
+    float sh_ = (mode == 1) ? (H > 1 ? (float)(Ho - 1) / (float)(H - 1) : 0.f) : (float)Ho / (float)H;
+    float sw_ = (mode == 1) ? (W > 1 ? (float)(Wo - 1) / (float)(W - 1) : 0.f) : (float)Wo / (float)W;
+    int pc = (int)(h * sh_), qc = (int)(w * sw_);
+    float acc = 0.f;
+    for (int p = max(pc - rh, 0); p <= min(pc + rh, Ho - 1); ++p) {
+      int h0, h1;
+      float fh;
+      lerp_idx(p, H, Ho, mode, &h0, &h1, &fh);
+      float wh = (h0 == h ? (1.f - fh) : 0.f) + (h1 == h ? fh : 0.f);
+      if (wh == 0.f) continue;
+      for (int q = max(qc - rw, 0); q <= min(qc + rw, Wo - 1); ++q) {
+        int w0, w1;
+        float fw;
+        lerp_idx(q, W, Wo, mode, &w0, &w1, &fw);
+        float ww = (w0 == w ? (1.f - fw) : 0.f) + (w1 == w ? fw : 0.f);
+        if (ww == 0.f) continue;
+        acc = fmaf(wh * ww, to_f32(dy[(((long long)n * Ho + p) * Wo + q) * C + c]), acc);
+      }
+    }
+    dx[i] = from_f32<T>(acc);
+  }
+}
+
+__global__ void fill_kernel(float* p, long long n, float v) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    p[i] = v;
+}
+__global__ void scale_kernel(float* p, long long n, float s) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    p[i] *= s;
+}
+
+}  // namespace
+}  // namespace mcn
+
+using namespace mcn;
+
+extern "C" int mcn_act_fwd(int dtype, const void* x, long long n, int act, float alpha, void* y,
+                           void* stream) {
+  MCN_REQUIRE(x && y && n >= 0, "act_fwd: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MCN_DISPATCH_DTYPE(dtype, T, return (launch_map<T, false>(x, nullptr, n, y, st, ActF{act, alpha}, "act_fwd")));
+  return MCN_OK;
+}
+extern "C" int mcn_act_bwd(int dtype, const void* dy, const void* x, long long n, int act,
+                           float alpha, void* dx, void* stream) {
+  MCN_REQUIRE(dy && x && dx, "act_bwd: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MCN_DISPATCH_DTYPE(dtype, T, return (launch_map<T, true>(dy, x, n, dx, st, ActB{act, alpha}, "act_bwd")));
+  return MCN_OK;
+}
+extern "C" int mcn_add_act_fwd(int dtype, const void* a, const void* b, long long n, int act,
+                               float alpha, void* y, void* stream) {
+  MCN_REQUIRE(a && b && y, "add_act_fwd: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MCN_DISPATCH_DTYPE(dtype, T, return (launch_map<T, true>(a, b, n, y, st, AddActF{act, alpha}, "add_act_fwd")));
+  return MCN_OK;
+}
+extern "C" int mcn_add_act_bwd(int dtype, const void* dy, const void* y, long long n, int act,
+                               float alpha, void* dz, void* stream) {
+  MCN_REQUIRE(dy && y && dz, "add_act_bwd: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MCN_DISPATCH_DTYPE(dtype, T, return (launch_map<T, true>(dy, y, n, dz, st, AddActB{act, alpha}, "add_act_bwd")));
+  return MCN_OK;
+}
+extern "C" int mcn_accumulate(int dtype, void* a, const void* b, long long n, void* stream) {
+  MCN_REQUIRE(a && b, "accumulate: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MCN_DISPATCH_DTYPE(dtype, T, return (launch_map<T, true>(a, b, n, a, st, AddF{}, "accumulate")));
+  return MCN_OK;
+}
+
+extern "C" int mcn_scale_bcast_fwd(int dtype, const void* x, const void* m, int N, int HW, int C,
+                                   void* y, void* stream) {
+  MCN_REQUIRE(x && m && y, "scale_bcast_fwd: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  long long total = (long long)N * HW * C;
+  MCN_DISPATCH_DTYPE(dtype, T, {
+    scale_bcast_fwd_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(
+        static_cast<const T*>(x), static_cast<const T*>(m), HW, C, total, static_cast<T*>(y));
+  });
+  return after_launch("scale_bcast_fwd");
+}
+extern "C" int mcn_scale_bcast_bwd(int dtype, const void* dy, const void* x, const void* m, int N,
+                                   int HW, int C, void* dx, float* dm, void* stream) {
+  MCN_REQUIRE(dy && x && m && dx && dm, "scale_bcast_bwd: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 grid((C + 31) / 32, N), block(32, 8);
+  MCN_DISPATCH_DTYPE(dtype, T, {
+    scale_bcast_bwd_kernel<T><<<grid, block, 0, st>>>(
+        static_cast<const T*>(dy), static_cast<const T*>(x), static_cast<const T*>(m), HW, C,
+        static_cast<T*>(dx), dm);
+  });
+  return after_launch("scale_bcast_bwd");
+}
+
+extern "C" int mcn_bias_add(int dtype, void* y, long long rows, int C, const float* bias,
+                            void* stream) {
+  MCN_REQUIRE(y && bias, "bias_add: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  long long total = rows * C;
+  MCN_DISPATCH_DTYPE(dtype, T, {
+    bias_add_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(static_cast<T*>(y), total, C, bias);
+  });
+  return after_launch("bias_add");
+}
+extern "C" int mcn_bias_grad(int dtype, const void* dy, long long rows, int C, float* db,
+                             void* stream) {
+  MCN_REQUIRE(dy && db, "bias_grad: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int chunks = (int)std::max<long long>(1, std::min<long long>(rows / 64, 2LL * num_sms()));
+  dim3 grid((C + 31) / 32, chunks), block(32, 8);
+  MCN_DISPATCH_DTYPE(dtype, T, {
+    bias_grad_kernel<T><<<grid, block, 0, st>>>(static_cast<const T*>(dy), rows, C, db);
+  });
+  return after_launch("bias_grad");
+}
+
+extern "C" int mcn_cast(int src_dtype, const void* src, int dst_dtype, void* dst, long long n,
+                        void* stream) {
+  MCN_REQUIRE(src && dst, "cast: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int g = grid_for(n, 256);
+  if (src_dtype == MCN_F32 && dst_dtype == MCN_BF16)
+    cast_kernel<float, __nv_bfloat16><<<g, 256, 0, st>>>((const float*)src, (__nv_bfloat16*)dst, n);
+  else if (src_dtype == MCN_BF16 && dst_dtype == MCN_F32)
+    cast_kernel<__nv_bfloat16, float><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, (float*)dst, n);
+  else if (src_dtype == MCN_F32 && dst_dtype == MCN_F32)
+    cast_kernel<float, float><<<g, 256, 0, st>>>((const float*)src, (float*)dst, n);
+  else if (src_dtype == MCN_BF16 && dst_dtype == MCN_BF16)
+    cast_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)src,
+                                                                 (__nv_bfloat16*)dst, n);
+  else {
+    set_error("cast: unsupported dtypes %d -> %d", src_dtype, dst_dtype);
+    return MCN_EINVAL;
+  }
+  return after_launch("cast");
+}
+
+extern "C" int mcn_input_prep(const float* x, long long n, float mean, float scale, int dst_dtype,
+                              void* y, void* stream) {
+  MCN_REQUIRE(x && y, "input_prep: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int g = grid_for(n, 256);
+  if (dst_dtype == MCN_F32)
+    input_prep_kernel<float><<<g, 256, 0, st>>>(x, n, mean, scale, (float*)y);
+  else
+    input_prep_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(x, n, mean, scale, (__nv_bfloat16*)y);
+  return after_launch("input_prep");
+}
+
+extern "C" int mcn_copy_channels(int dtype, const void* src, long long rows, int Csrc, int src_off,
+                                 void* dst, int Cdst, int dst_off, int Ccopy, int accumulate,
+                                 void* stream) {
+  MCN_REQUIRE(src && dst && src_off + Ccopy <= Csrc && dst_off + Ccopy <= Cdst,
+              "copy_channels: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MCN_DISPATCH_DTYPE(dtype, T, {
+    copy_channels_kernel<T><<<grid_for(rows * Ccopy, 256), 256, 0, st>>>(
+        static_cast<const T*>(src), rows, Csrc, src_off, static_cast<T*>(dst), Cdst, dst_off, Ccopy,
+        accumulate);
+  });
+  return after_launch("copy_channels");
+}
+
+extern "C" int mcn_resize_bilinear_fwd(int dtype, const void* x, int N, int H, int W, int C,
+                                       int Ho, int Wo, int mode, void* y, void* stream) {
+  MCN_REQUIRE(x && y && mode >= 0 && mode <= 2, "resize_fwd: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  long long total = (long long)N * Ho * Wo * C;
+  MCN_DISPATCH_DTYPE(dtype, T, {
+    resize_fwd_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const T*>(x), N, H, W, C,
+                                                              Ho, Wo, mode, static_cast<T*>(y));
+  });
+  return after_launch("resize_fwd");
+}
+extern "C" int mcn_resize_bilinear_bwd(int dtype, const void* dy, int N, int H, int W, int C,
+                                       int Ho, int Wo, int mode, void* dx, void* stream) {
+  MCN_REQUIRE(dy && dx && mode >= 0 && mode <= 2, "resize_bwd: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  long long total = (long long)N * H * W * C;
+  MCN_DISPATCH_DTYPE(dtype, T, {
+    resize_bwd_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const T*>(dy), N, H, W,
+                                                              C, Ho, Wo, mode, static_cast<T*>(dx));
+  });
+  return after_launch("resize_bwd");
+}
+
+extern "C" int mcn_fill_f32(float* p, long long n, float v, void* stream) {
+  MCN_REQUIRE(p, "fill: null");
+  fill_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, n, v);
+  return after_launch("fill");
+}
+extern "C" int mcn_scale_f32(float* p, long long n, float s, void* stream) {
+  MCN_REQUIRE(p, "scale: null");
+  scale_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, n, s);
+  return after_launch("scale");
+}

@@ -1,0 +1,151 @@
+// Fused multi-tensor optimiser step.
+// Replaces, in ONE launch over every variable: the EMA shadow update (reference
+// convnet.py:183-184,1401 — applied to the PRE-step value, optimizers.py:159,175), the L2 term of
+// the loss gradient (convnet.py:563), apply_gradients for Nesterov momentum / RMSProp / Adam
+// (optimizers.py:668-705), the decoupled weight decay on the post-step value
+// (optimizers.py:163-172) and the per-use fp32->half cast of the weights (convnet.py:1421), here
+// a bf16 copy in both tensor-core operand layouts.
+#include "mcn_common.cuh"
+
+namespace mcn {
+namespace {
+
+constexpr int kItems = 8;
+constexpr int kBlock = 256;
+
+// hp: [0] lr  [1] momentum|beta1  [2] decay|beta2  [3] eps  [4] ema decay d_t
+//     [5] adam lr_t  [6] gradient scale  [7] weight-decay multiplier
+__global__ void __launch_bounds__(kBlock)
+opt_step_kernel(int kind, const mcn_opt_tensor* __restrict__ table, const float* __restrict__ hp,
+                float* __restrict__ l2_loss) {
+  const mcn_opt_tensor t = table[blockIdx.y];
+  const long long base = (long long)blockIdx.x * (kBlock * kItems);
+  if (base >= t.n) return;
+  const float lr = hp[0], mom = hp[1], b2 = hp[2], eps = hp[3], ema_d = hp[4], adam_lr = hp[5],
+              gscale = hp[6], wd = t.wd * hp[7];
+  float l2_acc = 0.f;  // l2 * sum(w^2)/2 over the PRE-step weights (tf.nn.l2_loss, convnet.py:563)
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) {
+    const long long i = base + k * kBlock + threadIdx.x;
+    if (i >= t.n) continue;
+    float w = t.w[i];
+    l2_acc = fmaf(0.5f * t.l2 * w, w, l2_acc);
+    if (t.ema) {
+      float s = t.ema[i];
+      t.ema[i] = s - (1.f - ema_d) * (s - w);
+    }
+    if (t.g != nullptr) {
+      float g = t.g[i] * gscale + t.l2 * w;
+      if (kind == MCN_OPT_NESTEROV) {
+        float a = mom * t.m[i] + g;
+        t.m[i] = a;
+        w -= lr * (g + mom * a);
+      } else if (kind == MCN_OPT_RMSPROP) {
+        float ms = b2 * t.v[i] + (1.f - b2) * g * g;
+        t.v[i] = ms;
+        float m = mom * t.m[i] + lr * g * rsqrtf(ms + eps);
+        t.m[i] = m;
+        w -= m;
+      } else {
+        float m = mom * t.m[i] + (1.f - mom) * g;
+        float v = b2 * t.v[i] + (1.f - b2) * g * g;
+        t.m[i] = m;
+        t.v[i] = v;
+        w -= adam_lr * m / (sqrtf(v) + eps);
+      }
+      if (wd != 0.f) w -= wd * w;
+      t.w[i] = w;
+    }
+    if (t.w_bf16) reinterpret_cast<__nv_bfloat16*>(t.w_bf16)[i] = __float2bfloat16_rn(w);
+    if (t.w_bf16_t) {
+      // i = (tap*cin + ci)*cout + co  ->  (tap*cout + co)*cin + ci
+      int co = (int)(i % t.cout);
+      long long r = i / t.cout;
+      int ci = (int)(r % t.cin);
+      long long tap = r / t.cin;
+      reinterpret_cast<__nv_bfloat16*>(t.w_bf16_t)[(tap * t.cout + co) * t.cin + ci] =
+          __float2bfloat16_rn(w);
+    }
+  }
+  if (l2_loss != nullptr && t.l2 != 0.f) {
+    l2_acc = warp_sum(l2_acc);
+    if ((threadIdx.x & 31) == 0 && l2_acc != 0.f) atomicAdd(l2_loss, l2_acc);
+  }
+}
+
+// out[t][c][r] += in[t][r][c]   (in: [taps][rows][cols])
+__global__ void transpose_add_kernel(const float* __restrict__ in, int rows, int cols,
+                                     float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int t = blockIdx.z;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const float* src = in + (long long)t * rows * cols;
+  float* dst = out + (long long)t * rows * cols;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    int rr = r0 + r, cc = c0 + threadIdx.x;
+    tile[r][threadIdx.x] = (rr < rows && cc < cols) ? src[(long long)rr * cols + cc] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    int cc = c0 + r, rr = r0 + threadIdx.x;
+    if (rr < rows && cc < cols) dst[(long long)cc * rows + rr] += tile[threadIdx.x][r];
+  }
+}
+
+// Tiled transpose of one weight tensor: fp32 [taps][cin][cout] -> bf16 same + bf16 [taps][cout][cin]
+__global__ void weight_prep_kernel(const float* __restrict__ w, int cin, int cout,
+                                   __nv_bfloat16* __restrict__ o_same,
+                                   __nv_bfloat16* __restrict__ o_t) {
+  __shared__ float tile[32][33];
+  const int tap = blockIdx.z;
+  const int ci0 = blockIdx.y * 32, co0 = blockIdx.x * 32;
+  const float* src = w + (long long)tap * cin * cout;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    int ci = ci0 + r, co = co0 + threadIdx.x;
+    float v = (ci < cin && co < cout) ? src[(long long)ci * cout + co] : 0.f;
+    tile[r][threadIdx.x] = v;
+    if (o_same && ci < cin && co < cout)
+      o_same[(long long)tap * cin * cout + (long long)ci * cout + co] = __float2bfloat16_rn(v);
+  }
+  __syncthreads();
+  if (o_t)
+    for (int r = threadIdx.y; r < 32; r += 8) {
+      int co = co0 + r, ci = ci0 + threadIdx.x;
+      if (ci < cin && co < cout)
+        o_t[(long long)tap * cin * cout + (long long)co * cin + ci] =
+            __float2bfloat16_rn(tile[threadIdx.x][r]);
+    }
+}
+
+}  // namespace
+}  // namespace mcn
+
+using namespace mcn;
+
+extern "C" int mcn_opt_step(int kind, const mcn_opt_tensor* table, int ntensors, long long max_n,
+                            const float* hp, float* l2_loss, void* stream) {
+  MCN_REQUIRE(table && hp && ntensors > 0 && max_n > 0, "opt_step: bad argument");
+  MCN_REQUIRE(kind >= MCN_OPT_NESTEROV && kind <= MCN_OPT_ADAM, "opt_step: unknown optimiser %d", kind);
+  MCN_REQUIRE(ntensors <= 65535, "opt_step: too many tensors");
+  dim3 grid((unsigned)((max_n + kBlock * kItems - 1) / (kBlock * kItems)), (unsigned)ntensors);
+  opt_step_kernel<<<grid, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(kind, table, hp, l2_loss);
+  return after_launch("opt_step");
+}
+
+extern "C" int mcn_weight_prep(const float* w_hwio_f32, int taps, int cin, int cout,
+                               void* w_hwio_bf16, void* w_ohwi_bf16, void* stream) {
+  MCN_REQUIRE(w_hwio_f32 && taps > 0 && cin > 0 && cout > 0, "weight_prep: bad argument");
+  dim3 grid((cout + 31) / 32, (cin + 31) / 32, taps), block(32, 8);
+  weight_prep_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      w_hwio_f32, cin, cout, static_cast<__nv_bfloat16*>(w_hwio_bf16),
+      static_cast<__nv_bfloat16*>(w_ohwi_bf16));
+  return after_launch("weight_prep");
+}
+
+extern "C" int mcn_transpose_add_f32(const float* in, int taps, int rows, int cols, float* out,
+                                     void* stream) {
+  MCN_REQUIRE(in && out && taps > 0 && rows > 0 && cols > 0, "transpose_add: bad argument");
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32, taps), block(32, 8);
+  transpose_add_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(in, rows, cols, out);
+  return after_launch("transpose_add");
+}

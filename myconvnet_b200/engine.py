@@ -1,0 +1,368 @@
+"""Executes a Plan on one B200: arena allocation, variable initialisation, the training step.
+
+Training-step semantics follow the reference (optimizers.py:89-177):
+forward -> backward -> gradient mean over replicas -> [EMA shadows on pre-step values; BN
+moving statistics] -> optimiser update (L2 folded in) -> decoupled weight decay, with
+lr = base_lr * global_batch/256 * multiplier (optimizers.py:46,57).  Replicas are processes
+(one per GPU); the gradient mean is an NCCL all-reduce over flat buckets; BN statistics are
+all-reduced per layer (synchronised BN) instead of the reference's tower-after-tower chain.
+
+torch is used for device memory, streams, CUDA-graph capture and torch.distributed only: every
+arithmetic kernel on the step is a libmcn launch.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import lib as _lib
+from .plan import ConvDesc, Plan, Ptr
+
+OPT_KINDS = {"nesterov": 0, "momentum": 0, "sgd": 0, "rmsprop": 1, "adam": 2}
+
+
+def draw_initial_value(var, rng):
+    """Initial value of a variable in its reference layout."""
+    init = var.init
+    shape = var.shape
+    if init.kind == "constant":
+        return np.full(shape, init.value, dtype=np.float32)
+    if len(shape) >= 2:
+        rf = int(np.prod(shape[:-2]))
+        fan_in, fan_out = shape[-2] * rf, shape[-1] * rf
+    else:
+        fan_in = fan_out = shape[0]
+    fan = {"fan_in": fan_in, "fan_out": fan_out, "fan_avg": 0.5 * (fan_in + fan_out)}[init.mode]
+    scale = init.scale / max(1.0, fan)
+    if init.distribution == "uniform":
+        lim = np.sqrt(3.0 * scale)
+        return rng.uniform(-lim, lim, size=shape).astype(np.float32)
+    std = np.sqrt(scale) / 0.87962566103423978
+    v = rng.standard_normal(size=shape)
+    bad = np.abs(v) > 2.0
+    while bad.any():                      # truncated normal: resample beyond 2 sigma
+        v[bad] = rng.standard_normal(size=int(bad.sum()))
+        bad = np.abs(v) > 2.0
+    return (v * std).astype(np.float32)
+
+
+class Engine(object):
+    def __init__(self, model, optimizer="nesterov", keep=(), seed=0, conv_mode=1, device=None,
+                 world_size=1, rank=0, process_group=None, use_cuda_graph=False,
+                 fetch_pred=True, **kwargs):
+        if not torch.cuda.is_available():
+            raise RuntimeError("myconvnet_b200.Engine needs a CUDA device: there is no CPU execution "
+                               "path (plans can be inspected on CPU through myconvnet_b200.plan.Plan)")
+        self.lib = _lib.load()
+        self.model = model
+        self.graph = model.graph
+        self.kw = dict(model._parameters)
+        self.kw.update(kwargs)
+        self.world = int(world_size)
+        self.rank = int(rank)
+        self.pg = process_group
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.opt_kind = OPT_KINDS[optimizer.lower()]
+        self.plan = Plan(self.graph, world_size=self.world, keep=keep, conv_mode=conv_mode,
+                         fetch_pred=fetch_pred, loss_scale=float(self.kw.get("loss_scaling_factor", 1.0)))
+        p = self.plan
+        self.arena = torch.empty(p.arena_bytes + 1024, dtype=torch.uint8, device=self.device)
+        base = self.arena.data_ptr()
+        self.base = (base + 255) // 256 * 256
+        self._skew = self.base - base
+        self.arena.zero_()
+        self._descs = {}
+        self._resolve()
+        self.global_step = 0
+        self.batch = model._batch_size
+        self.global_batch = self.batch * self.world
+        self.base_lr = float(self.kw.get("base_learning_rate", 0.1))
+        self.momentum = float(self.kw.get("momentum", 0.9))
+        self.ema_decay = float(model.moving_average_decay)
+        self.l2 = float(self.kw.get("l2_reg", 1e-4))
+        self.bias_norm_decay = bool(self.kw.get("bias_norm_decay", False))
+        self.base_wd = float(self.kw.get("base_weight_decay", 0.0)) * self.global_batch / 256
+        self.wd_scheduling = bool(self.kw.get("weight_decay_scheduling", True))
+        if self.kw.get("l1_weight_decay", False) or self.kw.get("huber_decay_delta", None) is not None:
+            raise NotImplementedError("l1 / pseudo-Huber weight decay variants are not supported")
+        if self.kw.get("gradient_threshold", None) is not None:
+            raise NotImplementedError("gradient clipping is not supported yet")
+        self.hp_host = torch.zeros(16, dtype=torch.float32).pin_memory()
+        self.hp_dev = self.view(Ptr(p.b_hp), 16, torch.float32)
+        self._build_opt_table()
+        self.init_variables(seed)
+        self._graph_exec = None
+        self._eager_steps = 0
+        self.use_cuda_graph = use_cuda_graph
+        self._inputs = {name: self.tensor_view(t) for name, t in self.graph.inputs.items()}
+        self._pinned = {}
+
+    # ------------------------------------------------------------------ memory views
+    def addr(self, ptr):
+        return self.base + ptr.buf.offset + ptr.off
+
+    def view(self, ptr, count, dtype):
+        esz = torch.empty(0, dtype=dtype).element_size()
+        start = self._skew + ptr.buf.offset + ptr.off
+        return self.arena[start:start + count * esz].view(dtype)
+
+    def tensor_view(self, t, stored_dtype=None):
+        dt = stored_dtype or self.plan._logits_dtype(t)
+        tdt = {"f32": torch.float32, "bf16": torch.bfloat16, "i32": torch.int32}[dt]
+        return self.view(self.plan.tbuf[t], t.size, tdt).view(*t.shape) if t.shape else \
+            self.view(self.plan.tbuf[t], 1, tdt)
+
+    def fetch(self, t):
+        """Copy a graph tensor's current value to host as float32 numpy."""
+        v = self.tensor_view(t)
+        return v.float().cpu().numpy() if v.dtype != torch.int32 else v.cpu().numpy()
+
+    # ------------------------------------------------------------------ launch resolution
+    def _carg(self, a):
+        if isinstance(a, Ptr):
+            return self.addr(a)
+        if isinstance(a, ConvDesc):
+            k = a.key()
+            if k not in self._descs:
+                self._descs[k] = _lib.ConvDescC(*k)
+            return ctypes.byref(self._descs[k])
+        return a
+
+    def _resolve(self):
+        def conv(launches):
+            out = []
+            for l in launches:
+                fn = getattr(self.lib, l.fn)
+                out.append((fn, tuple(self._carg(a) for a in l.args), l.fn, l.tag))
+            return out
+        self._fwd = conv(self.plan.fwd)
+        self._bwd = conv(self.plan.bwd)
+        # collective points, keyed by launch index
+        self._ar = {"f": {}, "b": {}}
+        for phase, idx, ptr, nbytes, dt in self.plan.allreduce_points:
+            tdt = torch.float64 if dt == "f64" else torch.float32
+            n = nbytes // (8 if dt == "f64" else 4)
+            self._ar[phase].setdefault(idx, []).append(self.view(ptr, n, tdt))
+        z0, z1 = self.plan.region_span["zero"]
+        self._zero_ptr = self.base + z0
+        self._zero_n = (z1 - z0) // 4
+
+    def _run(self, launches, phase, stream):
+        ar = self._ar[phase]
+        check = _lib.check
+        if not ar:
+            for fn, args, name, tag in launches:
+                rc = fn(*args, stream)
+                if rc:
+                    check(rc, name + " [" + tag + "]")
+            return
+        import torch.distributed as dist
+        for i, (fn, args, name, tag) in enumerate(launches):
+            if i in ar:
+                for t in ar[i]:
+                    dist.all_reduce(t, group=self.pg)
+            rc = fn(*args, stream)
+            if rc:
+                check(rc, name + " [" + tag + "]")
+
+    # ------------------------------------------------------------------ variables
+    def _var_view(self, buf, v, n=None):
+        return self.view(Ptr(buf, self.plan.var_off[v] * 4), n or v.storage_size, torch.float32)
+
+    def _to_storage(self, v, value):
+        """reference layout -> device storage layout (im2col-padded stems)."""
+        value = np.asarray(value, dtype=np.float32).reshape(v.shape)
+        if v.storage_shape != v.shape:
+            kpad, co = v.storage_shape
+            flat = value.reshape(-1, co)
+            out = np.zeros((kpad, co), dtype=np.float32)
+            out[:flat.shape[0]] = flat
+            return out
+        return value
+
+    def _from_storage(self, v, arr):
+        arr = np.asarray(arr).reshape(v.storage_shape)
+        if v.storage_shape != v.shape:
+            k = int(np.prod(v.shape[:-1]))
+            return arr[:k].reshape(v.shape).copy()
+        return arr.reshape(v.shape).copy()
+
+    def init_variables(self, seed=0):
+        rng = np.random.default_rng(seed)
+        vals = {v.name: draw_initial_value(v, rng) for v in self.graph.vars.values()}
+        self.set_variables(vals, reset_state=True)
+
+    def set_variables(self, values, reset_state=True):
+        """values: {name: array in reference layout}.  EMA shadows are (re)initialised to the
+        value (tf ExponentialMovingAverage initialises the shadow to the variable)."""
+        p = self.plan
+        for v in p.all_vars:
+            if v.name not in values:
+                continue
+            arr = torch.from_numpy(self._to_storage(v, values[v.name]).reshape(-1)).to(self.device)
+            self._var_view(p.b_param, v).copy_(arr)
+            if reset_state:
+                self._var_view(p.b_ema, v).copy_(arr)
+        if reset_state:
+            self.view(Ptr(p.b_mom), max(p.n_train, 1), torch.float32).zero_()
+            # RMSProp's mean-square accumulator starts at one
+            self.view(Ptr(p.b_v), max(p.n_train, 1), torch.float32).fill_(1.0 if self.opt_kind == 1 else 0.0)
+            self.global_step = 0
+        self.refresh_operand_copies()
+        torch.cuda.synchronize(self.device)
+
+    def refresh_operand_copies(self):
+        """bf16 tensor-core operand copies of the current fp32 master weights."""
+        p = self.plan
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        for v in p.all_vars:
+            if v.needs_bf16 or v.needs_bf16_t:
+                taps, ci, co = v.gemm_dims
+                _lib.check(self.lib.mcn_weight_prep(
+                    self.addr(p.pvar(v)), taps, ci, co,
+                    self.addr(p.pbf16(v)) if v.needs_bf16 else None,
+                    self.addr(p.pbf16t(v)) if v.needs_bf16_t else None, st), "weight_prep")
+
+    def get_variables(self, ema=False):
+        p = self.plan
+        buf = p.b_ema if ema else p.b_param
+        return {v.name: self._from_storage(v, self._var_view(buf, v).cpu().numpy()) for v in p.all_vars}
+
+    def get_gradients(self):
+        p = self.plan
+        return {v.name: self._from_storage(v, self._var_view(p.b_grad, v).cpu().numpy())
+                for v in p.trainable}
+
+    def _build_opt_table(self):
+        p = self.plan
+        n = len(p.all_vars)
+        table = (_lib.OptTensorC * n)()
+        max_n = 1
+        for i, v in enumerate(p.all_vars):
+            e = table[i]
+            off = p.var_off[v] * 4
+            e.w = self.base + p.b_param.offset + off
+            e.ema = self.base + p.b_ema.offset + off
+            if v.trainable:
+                e.g = self.base + p.b_grad.offset + off
+                e.m = self.base + p.b_mom.offset + off
+                e.v = self.base + p.b_v.offset + off
+            e.n = v.storage_size
+            if v.needs_bf16:
+                e.w_bf16 = self.addr(p.pbf16(v))
+            if v.needs_bf16_t:
+                e.w_bf16_t = self.addr(p.pbf16t(v))
+            if v.gemm_dims:
+                e.taps, e.cin, e.cout = v.gemm_dims
+            else:
+                e.taps, e.cin, e.cout = 1, 1, max(v.storage_size, 1)
+            decayed = v.kind == "weight" or (self.bias_norm_decay and v.kind in ("bias", "norm"))
+            e.l2 = self.l2 if (decayed and v.trainable) else 0.0
+            e.wd = self.base_wd if (decayed and v.trainable) else 0.0
+            max_n = max(max_n, v.storage_size)
+        raw = bytes(table)
+        self.opt_table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.device)
+        self.opt_n = n
+        self.opt_max_n = max_n
+
+    # ------------------------------------------------------------------ the step
+    def _set_hyper(self, lr_multiplier):
+        t = self.global_step
+        lr = self.base_lr * self.global_batch / 256.0 * lr_multiplier
+        d_t = min(self.ema_decay, (1.0 + t) / (10.0 + t))
+        b1, b2 = self.momentum, (0.9 if self.opt_kind == 1 else 0.999)
+        adam_lr = lr * np.sqrt(1.0 - b2 ** (t + 1)) / (1.0 - b1 ** (t + 1)) if self.opt_kind == 2 else lr
+        hp = self.hp_host
+        hp[0], hp[1], hp[2], hp[3] = lr, b1, b2, 1e-3
+        hp[4], hp[5] = d_t, adam_lr
+        hp[6] = 1.0 / (self.world * self.plan.loss_scale)
+        hp[7] = lr_multiplier if self.wd_scheduling else 1.0
+        self.hp_dev.copy_(hp, non_blocking=True)
+
+    def load_inputs(self, **arrays):
+        """Host (numpy / pinned torch) -> device input buffers, asynchronously on the current
+        stream.  Returns the bytes copied."""
+        nbytes = 0
+        for name, arr in arrays.items():
+            dst = self._inputs[name]
+            if isinstance(arr, np.ndarray):
+                pin = self._pinned.get(name)
+                if pin is None or pin.shape != dst.shape:
+                    pin = torch.empty(dst.shape, dtype=dst.dtype).pin_memory()
+                    self._pinned[name] = pin
+                pin.copy_(torch.from_numpy(np.ascontiguousarray(arr)).to(dst.dtype).view(dst.shape))
+                arr = pin
+            dst.copy_(arr.view(dst.shape), non_blocking=True)
+            nbytes += dst.numel() * dst.element_size()
+        return nbytes
+
+    def _step_body(self, backward=True, update=True):
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.mcn_fill_f32(self._zero_ptr, self._zero_n, 0.0, st), "zero")
+        self._run(self._fwd, "f", st)
+        if not backward:
+            return
+        self._run(self._bwd, "b", st)
+        if self.world > 1:
+            self._allreduce_grads()
+        if update:
+            p = self.plan
+            _lib.check(self.lib.mcn_opt_step(self.opt_kind, self.opt_table.data_ptr(), self.opt_n,
+                                             self.opt_max_n, self.addr(Ptr(p.b_hp)),
+                                             self.addr(p.loss_slots["l2"]) if "l2" in p.loss_slots else None,
+                                             st), "opt_step")
+
+    def _allreduce_grads(self):
+        import torch.distributed as dist
+        p = self.plan
+        flat = self.view(Ptr(p.b_grad), p.n_train, torch.float32)
+        bucket = int(self.kw.get("bucket_elems", 8 * 1024 * 1024))
+        for s in range(0, p.n_train, bucket):
+            dist.all_reduce(flat[s:min(s + bucket, p.n_train)], group=self.pg)
+
+    def train_step(self, X=None, Y=None, lr_multiplier=1.0, fetch_loss=True, update=True):
+        """One optimisation step.  X: fp32 NHWC images in [0,1]; Y: int32 labels (-1 = none).
+        Returns the reference's loss value (data term + L2 term) when fetch_loss."""
+        if X is not None:
+            self.load_inputs(X=X, Y=Y)
+        self._set_hyper(lr_multiplier)
+        if self.use_cuda_graph and self.world == 1 and update and self._eager_steps >= 1:
+            if self._graph_exec is None:
+                self._capture(update)
+            self._graph_exec.replay()
+        else:
+            # the first step always runs eagerly: lazy driver/attribute initialisation must not
+            # happen inside a stream capture
+            self._step_body(update=update)
+            self._eager_steps += 1
+        if update:
+            self.global_step += 1
+        return self.read_loss() if fetch_loss else None
+
+    def _capture(self, update):
+        # warm-up launch outside capture so lazy CUDA/driver initialisation is done
+        s = torch.cuda.Stream(self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(s):
+            with torch.cuda.graph(g, stream=s):
+                self._step_body(update=update)
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        self._graph_exec = g
+
+    def forward(self, X=None, Y=None):
+        if X is not None:
+            self.load_inputs(X=X, Y=Y)
+        self._step_body(backward=False)
+
+    def read_loss(self):
+        p = self.plan
+        if "loss" not in p.loss_slots:
+            return None
+        v = self.view(p.loss_slots["loss"], 2, torch.float32).cpu().numpy()
+        node = self.graph.losses[0].node
+        data = float(v[0]) / node.attrs["rows"]
+        return data + float(v[1])
+
+    def launches_per_step(self):
+        return 1 + len(self._fwd) + len(self._bwd) + 1

@@ -1,0 +1,108 @@
+"""ctypes binding of libmcn.so (the C ABI declared in include/mcn.h).
+
+There is no fallback: if the library is missing or a symbol cannot be bound, importing code fails
+loudly.  The signature table below is checked against the header by tests/test_abi.py.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmcn.so")
+
+
+class ConvDescC(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in
+                ("N", "H", "W", "Cin", "Cout", "kh", "kw", "sh", "sw", "dh", "dw", "pad_t", "pad_l",
+                 "Ho", "Wo")]
+
+
+class OptTensorC(ctypes.Structure):
+    _fields_ = [("w", ctypes.c_void_p), ("g", ctypes.c_void_p), ("m", ctypes.c_void_p),
+                ("v", ctypes.c_void_p), ("ema", ctypes.c_void_p), ("w_bf16", ctypes.c_void_p),
+                ("w_bf16_t", ctypes.c_void_p), ("n", ctypes.c_longlong), ("taps", ctypes.c_int),
+                ("cin", ctypes.c_int), ("cout", ctypes.c_int), ("l2", ctypes.c_float),
+                ("wd", ctypes.c_float)]
+
+
+_T = {"p": ctypes.c_void_p, "i": ctypes.c_int, "l": ctypes.c_longlong, "f": ctypes.c_float,
+      "d": ctypes.c_double, "D": ctypes.POINTER(ConvDescC)}
+
+# name -> argument codes WITHOUT the trailing stream (every entry ends with a void* stream)
+SIGNATURES = {
+    "mcn_conv2d_fprop_tc": "Dppppii",
+    "mcn_conv2d_dgrad_tc": "Dpppii",
+    "mcn_conv2d_wgrad_tc": "Dpppi",
+    "mcn_conv2d_fprop_direct": "Dipippp",
+    "mcn_conv2d_dgrad_direct": "Dipipp",
+    "mcn_conv2d_wgrad_direct": "Dippp",
+    "mcn_dwconv2d_fwd": "Diipipp",
+    "mcn_dwconv2d_bwd_data": "Diipipp",
+    "mcn_dwconv2d_bwd_filter": "Diippp",
+    "mcn_weight_prep": "piiipp",
+    "mcn_im2col": "Dippi",
+    "mcn_bn_stats": "iplip",
+    "mcn_bn_finalize": "pdiffpppp",
+    "mcn_bn_apply": "iplipppppifp",
+    "mcn_bn_infer": "iplippfpppifp",
+    "mcn_bn_bwd_reduce": "ippplippppifpp",
+    "mcn_bn_bwd_apply": "ippplippppifppdpp",
+    "mcn_maxpool_fwd": "ipiiiiiiiiiiiipp",
+    "mcn_maxpool_bwd": "ippiiiiiiiiiiiip",
+    "mcn_avgpool_fwd": "ipiiiiiiiiiiiip",
+    "mcn_avgpool_bwd": "ipiiiiiiiiiiiip",
+    "mcn_gap_fwd": "ipiiipi",
+    "mcn_gap_bwd": "ipiiiip",
+    "mcn_act_fwd": "iplifp",
+    "mcn_act_bwd": "ipplifp",
+    "mcn_add_act_fwd": "ipplifp",
+    "mcn_add_act_bwd": "ipplifp",
+    "mcn_accumulate": "ippl",
+    "mcn_scale_bcast_fwd": "ippiiip",
+    "mcn_scale_bcast_bwd": "ipppiiipp",
+    "mcn_bias_add": "iplip",
+    "mcn_bias_grad": "iplip",
+    "mcn_cast": "ipipl",
+    "mcn_input_prep": "plffip",
+    "mcn_copy_channels": "ipliipiiii",
+    "mcn_resize_bilinear_fwd": "ipiiiiiiip",
+    "mcn_resize_bilinear_bwd": "ipiiiiiiip",
+    "mcn_softmax_xent": "pplipffppp",
+    "mcn_sigmoid_xent": "plfffppi",
+    "mcn_opt_step": "ipilpp",
+    "mcn_transpose_add_f32": "piiip",
+    "mcn_fill_f32": "plf",
+    "mcn_scale_f32": "plf",
+}
+
+_lib = None
+
+
+def load():
+    """Load libmcn.so and bind every entry point.  Raises if anything is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "libmcn.so not found at %s — build it with `python -m myconvnet_b200.build` "
+            "(there is no CPU fallback)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, codes in SIGNATURES.items():
+        fn = getattr(lib, name)        # AttributeError if the symbol is not exported
+        fn.argtypes = [_T[c] for c in codes] + [ctypes.c_void_p]
+        fn.restype = ctypes.c_int
+    lib.mcn_last_error.restype = ctypes.c_char_p
+    lib.mcn_last_error.argtypes = []
+    lib.mcn_version.restype = ctypes.c_int
+    lib.mcn_launch_count.restype = ctypes.c_longlong
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise RuntimeError("libmcn %s failed (%d): %s" % (what, rc, load().mcn_last_error().decode()))
+
+
+def launch_count():
+    return int(load().mcn_launch_count())

@@ -1,0 +1,958 @@
+"""Lower a recorded layer graph to a fixed launch sequence over one device arena.
+
+Input: graph.Graph built by the ConvNet facade.  Output: a ``Plan`` — buffer table with byte
+offsets into a single arena, forward launches, backward launches (reverse-mode differentiation
+done here, op by op), and the optimiser table.  Everything is decided ahead of time (shapes are
+static, as in the reference's TF graph mode), so a training step is a flat list of C-ABI calls
+that can be captured into a CUDA graph.  Planning runs without a GPU; tests inspect plans on CPU.
+
+Fusion decided here (SURVEY.md 2.2 "new sm_100a kernel" column):
+  conv -> BN -> act                     : BN statistics + one apply pass with the activation
+  conv -> BN -> (+ skip) -> act         : same pass also adds the residual
+  dense -> cast(f32)                    : GEMM epilogue writes fp32 logits
+  softmax-xent forward + gradient (+ softmax probabilities) in one kernel
+"""
+import collections
+import os
+
+import numpy as np
+
+ALIGN = 256
+DT_SIZE = {"f32": 4, "bf16": 2, "i32": 4, "f64": 8, "u8": 1}
+DT_CODE = {"f32": 0, "bf16": 1}
+
+
+class Buf(object):
+    __slots__ = ("name", "nbytes", "offset", "region")
+
+    def __init__(self, name, nbytes, region):
+        self.name = name
+        self.nbytes = int(nbytes)
+        self.offset = None
+        self.region = region
+
+
+class Ptr(object):
+    """Placeholder for arena_base + buf.offset + off, resolved by the engine."""
+    __slots__ = ("buf", "off")
+
+    def __init__(self, buf, off=0):
+        self.buf = buf
+        self.off = int(off)
+
+    def __add__(self, n):
+        return Ptr(self.buf, self.off + int(n))
+
+
+NULL = None
+
+
+class Launch(object):
+    __slots__ = ("fn", "args", "tag")
+
+    def __init__(self, fn, args, tag=""):
+        self.fn = fn
+        self.args = args
+        self.tag = tag
+
+
+class ConvDesc(object):
+    """Mirror of mcn_conv_desc (include/mcn.h)."""
+    FIELDS = ("N", "H", "W", "Cin", "Cout", "kh", "kw", "sh", "sw", "dh", "dw", "pad_t", "pad_l",
+              "Ho", "Wo")
+
+    def __init__(self, **kw):
+        for f in self.FIELDS:
+            setattr(self, f, int(kw[f]))
+
+    def key(self):
+        return tuple(getattr(self, f) for f in self.FIELDS)
+
+
+def _align(n, a=ALIGN):
+    return (n + a - 1) // a * a
+
+
+class TempAllocator(object):
+    """First-fit free-list allocator simulated at plan time for backward temporaries."""
+
+    def __init__(self):
+        self.free = []       # (offset, size)
+        self.top = 0
+        self.peak = 0
+
+    def alloc(self, nbytes):
+        nbytes = _align(nbytes)
+        for i, (off, size) in enumerate(self.free):
+            if size >= nbytes:
+                if size == nbytes:
+                    self.free.pop(i)
+                else:
+                    self.free[i] = (off + nbytes, size - nbytes)
+                return off, nbytes
+        off = self.top
+        self.top += nbytes
+        self.peak = max(self.peak, self.top)
+        return off, nbytes
+
+    def release(self, off, nbytes):
+        self.free.append((off, nbytes))
+        self.free.sort()
+        merged = []
+        for o, s in self.free:
+            if merged and merged[-1][0] + merged[-1][1] == o:
+                merged[-1] = (merged[-1][0], merged[-1][1] + s)
+            else:
+                merged.append((o, s))
+        if merged and merged[-1][0] + merged[-1][1] == self.top:
+            self.top = merged[-1][0]
+            merged.pop()
+        self.free = merged
+
+
+class Plan(object):
+    def __init__(self, graph, world_size=1, keep=(), conv_mode=1, fetch_pred=True,
+                 sync_bn=True, loss_scale=1.0):
+        self.graph = graph
+        self.world = int(world_size)
+        self.keep = set(keep)            # tensors that must stay materialised (parity taps)
+        self.conv_mode = conv_mode       # 1 = im2col TMA, 0 = box TMA
+        self.fetch_pred = fetch_pred
+        self.sync_bn = sync_bn and self.world > 1
+        self.loss_scale = loss_scale
+        self.cdt = graph.compute_dtype
+        self.csz = DT_SIZE[self.cdt]
+        self.ccode = DT_CODE[self.cdt]
+        self.bufs = []
+        self.fwd = []
+        self.bwd = []
+        self.tbuf = {}                   # Tensor -> Ptr
+        self.conv_descs = {}
+        self.bn_layers = []
+        self.allreduce_points = []       # (phase, launch index, Ptr, nbytes, dtype)
+        self.temp = TempAllocator()
+        self.temp_buf = Buf("temp", 0, "temp")
+        self.bufs.append(self.temp_buf)
+        self.loss_slots = {}
+        self._layout_vars()
+        self._fuse()
+        self._emit_forward()
+        self._emit_backward()
+        self.temp_buf.nbytes = self.temp.peak
+        self._assign_offsets()
+
+    # ------------------------------------------------------------------ buffers
+    def new_buf(self, name, nbytes, region="act"):
+        b = Buf(name, max(int(nbytes), 16), region)
+        self.bufs.append(b)
+        return b
+
+    def _assign_offsets(self):
+        order = ["param", "zero", "state", "bf16", "act", "temp"]
+        off = 0
+        self.region_span = {}
+        for region in order:
+            start = off
+            for b in self.bufs:
+                if b.region == region:
+                    b.offset = off
+                    off += _align(b.nbytes)
+            self.region_span[region] = (start, off)
+        self.arena_bytes = off
+
+    # ------------------------------------------------------------------ variables
+    def _layout_vars(self):
+        """All trainable variables contiguous (grads mirror them 1:1 -> flat buckets for the
+        gradient all-reduce), then the non-trainable ones.  Conv weights whose Cin is not a
+        multiple of 8 (RGB stems) are stored as a zero-padded [kpad, Cout] im2col matrix."""
+        g = self.graph
+        self._mark_operand_copies()
+        tr = [v for v in g.vars.values() if v.trainable]
+        nt = [v for v in g.vars.values() if not v.trainable]
+        self.var_off = {}
+        off = 0
+        for v in tr + nt:
+            self.var_off[v] = off
+            off += _align(v.storage_size * 4, 64) // 4   # keep 64-byte alignment per tensor
+        self.n_param = off
+        self.n_train = (self.var_off[nt[0]] if nt else off) if tr else 0
+        self.trainable = tr
+        self.all_vars = tr + nt
+        self.b_param = self.new_buf("params_f32", self.n_param * 4, "param")
+        self.b_ema = self.new_buf("ema_f32", self.n_param * 4, "param")
+        self.b_grad = self.new_buf("grads_f32", max(self.n_train, 1) * 4, "zero")
+        self.b_mom = self.new_buf("opt_m", max(self.n_train, 1) * 4, "state")
+        self.b_v = self.new_buf("opt_v", max(self.n_train, 1) * 4, "state")
+        self.b_hp = self.new_buf("hyper_params", 64, "state")
+        # bf16 operand copies
+        self.bf16_off = {}
+        self.bf16t_off = {}
+        n = 0
+        for v in self.all_vars:
+            if v.needs_bf16:
+                self.bf16_off[v] = n
+                n += _align(v.storage_size * 2, 256)
+            if v.needs_bf16_t:
+                self.bf16t_off[v] = n
+                n += _align(v.storage_size * 2, 256)
+        self.b_bf16 = self.new_buf("weights_bf16", n, "bf16")
+
+    def _mark_operand_copies(self):
+        for node in self.graph.nodes:
+            if node.op in ("conv2d", "dense", "conv2d_transpose") and self.cdt == "bf16":
+                w = node.vars["w"]
+                route = self._conv_route(node)
+                node.attrs["route"] = route
+                if route == "tc":
+                    w.needs_bf16 = w.needs_bf16_t = True
+                    if node.op == "dense":
+                        w.gemm_dims = (1, w.shape[0], w.shape[1])
+                    else:
+                        kh, kw, ci, co = w.shape
+                        w.gemm_dims = (kh * kw, ci, co)
+                elif route == "im2col":
+                    kh, kw, ci, co = w.shape
+                    kpad = _align(kh * kw * ci, 8)
+                    w.storage_shape = (kpad, co)
+                    w.gemm_dims = (1, kpad, co)
+                    w.needs_bf16 = w.needs_bf16_t = True
+                    node.attrs["kpad"] = kpad
+            elif node.op in ("conv2d", "dense", "conv2d_transpose"):
+                node.attrs["route"] = "direct"
+
+    def _conv_route(self, node):
+        """tc: TMA/tcgen05 implicit GEMM; im2col: explicit im2col + tc GEMM (Cin % 8 != 0, fprop
+        and wgrad only); direct: CUDA-core kernel."""
+        w = node.vars["w"]
+        if node.op == "dense":
+            ci, co = w.shape
+            return "tc" if ci % 8 == 0 and co % 8 == 0 else "direct"
+        kh, kw, ci, co = w.shape
+        if node.op == "conv2d_transpose":
+            # runs as dgrad: GEMM K = input channels (ci), N = output channels (co)
+            return "tc" if ci % 8 == 0 and co % 8 == 0 and kh * kw <= 52 else "direct"
+        if ci % 8 == 0 and co % 8 == 0 and kh * kw <= 52:
+            return "tc"
+        if co % 8 == 0 and not self._needs_input_grad(node):
+            return "im2col"
+        return "direct"
+
+    def _needs_input_grad(self, node):
+        return self._tensor_needs_grad(node.inputs[0])
+
+    def _tensor_needs_grad(self, t):
+        cache = self.__dict__.setdefault("_ng_cache", {})
+        if t in cache:
+            return cache[t]
+        n = t.node
+        if n is None or n.op in ("input", "stop_gradient"):
+            r = False
+        else:
+            r = any(v.trainable for v in n.vars.values()) or any(self._tensor_needs_grad(i) for i in n.inputs)
+        cache[t] = r
+        return r
+
+    def pvar(self, v):
+        return Ptr(self.b_param, self.var_off[v] * 4)
+
+    def pgrad(self, v):
+        return Ptr(self.b_grad, self.var_off[v] * 4)
+
+    def pbf16(self, v):
+        return Ptr(self.b_bf16, self.bf16_off[v])
+
+    def pbf16t(self, v):
+        return Ptr(self.b_bf16, self.bf16t_off[v])
+
+    # ------------------------------------------------------------------ fusion
+    def _single_consumer(self, t):
+        return t.consumers[0] if len(t.consumers) == 1 and t not in self.keep else None
+
+    def _fuse(self):
+        for node in self.graph.nodes:
+            node.attrs.setdefault("fused_into", None)
+        for node in self.graph.nodes:
+            if node.op == "bn":
+                node.attrs["residual"] = None
+                node.attrs["final"] = node.outputs[0]
+                cur = node.outputs[0]
+                c = self._single_consumer(cur)
+                if c is not None and c.op == "add":
+                    other = c.inputs[1] if c.inputs[0] is cur else c.inputs[0]
+                    # the residual must already exist when this BN runs
+                    if other.node is not None and other.node.id < node.id and other is not cur:
+                        node.attrs["residual"] = other
+                        c.attrs["fused_into"] = node
+                        cur = c.outputs[0]
+                        node.attrs["final"] = cur
+                        c = self._single_consumer(cur)
+                if c is not None and c.op == "act":
+                    # with a fused residual the derivative must come from the output: relu family
+                    if node.attrs["residual"] is None or c.attrs["act"] in (1, 2, 3):
+                        node.attrs["act"] = c.attrs["act"]
+                        node.attrs["alpha"] = c.attrs["alpha"]
+                        c.attrs["fused_into"] = node
+                        node.attrs["final"] = c.outputs[0]
+            elif node.op == "dense":
+                # dense -> cast(f32): the GEMM epilogue writes fp32 logits.  A softmax consumer
+                # of the pre-cast logits (d['pred']) reads the fp32 values instead.
+                node.attrs["final"] = node.outputs[0]
+                out = node.outputs[0]
+                cons = [c for c in out.consumers if c.op != "softmax"]
+                if len(cons) == 1 and cons[0].op == "cast" and out not in self.keep \
+                        and node.attrs.get("route") == "tc":
+                    cons[0].attrs["fused_into"] = node
+                    node.attrs["final"] = cons[0].outputs[0]
+            elif node.op == "add":
+                node.attrs["act"] = 0
+                node.attrs["alpha"] = 0.0
+                node.attrs["final"] = node.outputs[0]
+        # add -> act for adds that were not absorbed by a BN
+        for node in self.graph.nodes:
+            if node.op == "add" and node.attrs["fused_into"] is None:
+                c = self._single_consumer(node.outputs[0])
+                if c is not None and c.op == "act" and c.attrs["act"] in (1, 2, 3) \
+                        and c.attrs["fused_into"] is None:
+                    node.attrs["act"] = c.attrs["act"]
+                    node.attrs["alpha"] = c.attrs["alpha"]
+                    c.attrs["fused_into"] = node
+                    node.attrs["final"] = c.outputs[0]
+
+    # ------------------------------------------------------------------ helpers
+    def tensor_ptr(self, t):
+        return self.tbuf[t]
+
+    def alloc_act(self, t, dtype=None):
+        dt = dtype or t.dtype
+        b = self.new_buf("act:%s" % t.name, t.size * DT_SIZE[dt], "act")
+        p = Ptr(b)
+        self.tbuf[t] = p
+        return p
+
+    def conv_desc(self, **kw):
+        d = ConvDesc(**kw)
+        return self.conv_descs.setdefault(d.key(), d)
+
+    def L(self, phase, fn, *args, **kw):
+        (self.fwd if phase == "f" else self.bwd).append(Launch(fn, args, kw.get("tag", "")))
+
+    def talloc(self, nbytes):
+        off, size = self.temp.alloc(nbytes)
+        return Ptr(self.temp_buf, off), (off, size)
+
+    def tfree(self, handle):
+        if os.environ.get("MCN_NO_TEMP_REUSE"):   # debugging aid: never recycle temporaries
+            return
+        self.temp.release(*handle)
+
+    # ------------------------------------------------------------------ forward emission
+    def _emit_forward(self):
+        g = self.graph
+        # scratch that must be zero at step start: BN fp64 sums, loss accumulators
+        for node in g.nodes:
+            if node.attrs.get("fused_into") is not None:
+                continue
+            getattr(self, "_f_" + node.op)(node)
+        for node in g.nodes:
+            if node.op == "softmax" and node.attrs.get("standalone"):
+                x = node.inputs[0]
+                src = self.tbuf[x]
+                c = x.shape[-1]
+                if self._logits_dtype(x) != "f32":
+                    raise NotImplementedError("standalone softmax needs fp32 logits")
+                self.L("f", "mcn_softmax_xent", src, NULL, x.size // c, c, NULL, 0.0, 0.0, NULL, NULL,
+                       self.tbuf[node.outputs[0]], tag="softmax")
+
+    def _logits_dtype(self, t):
+        """dtype of the data actually stored for t (a fused dense writes fp32 under a bf16 name)."""
+        n = t.node
+        if n is not None and n.op == "dense" and n.attrs.get("final") is not t:
+            return n.attrs["final"].dtype
+        return t.dtype
+
+    def _f_input(self, node):
+        t = node.outputs[0]
+        self.alloc_act(t)
+
+    def _f_input_prep(self, node):
+        x, y = node.inputs[0], node.outputs[0]
+        py = self.alloc_act(y)
+        self.L("f", "mcn_input_prep", self.tbuf[x], x.size, node.attrs["mean"], node.attrs["scale"],
+               DT_CODE[y.dtype], py, tag="input_prep")
+
+    def _conv_geometry(self, node):
+        x, y = node.inputs[0], node.outputs[0]
+        a = node.attrs
+        n, h, w, ci = x.shape
+        _, ho, wo, co = y.shape
+        return self.conv_desc(N=n, H=h, W=w, Cin=ci, Cout=co, kh=a["k"][0], kw=a["k"][1],
+                              sh=a["s"][0], sw=a["s"][1], dh=a["d"][0], dw=a["d"][1],
+                              pad_t=a["pad"][0], pad_l=a["pad"][1], Ho=ho, Wo=wo)
+
+    def _f_conv2d(self, node):
+        x, y = node.inputs[0], node.outputs[0]
+        w = node.vars["w"]
+        b = node.vars.get("b")
+        d = self._conv_geometry(node)
+        node.attrs["desc"] = d
+        py = self.alloc_act(y)
+        route = node.attrs["route"]
+        pb = self.pvar(b) if b is not None else NULL
+        if route == "tc":
+            self.L("f", "mcn_conv2d_fprop_tc", d, self.tbuf[x], self.pbf16t(w), pb, py, self.ccode,
+                   self.conv_mode, tag=node.scope)
+        elif route == "im2col":
+            kpad = node.attrs["kpad"]
+            m = d.N * d.Ho * d.Wo
+            col = self.new_buf("im2col:%s" % node.scope, m * kpad * 2, "act")
+            node.attrs["col"] = col
+            gd = self.conv_desc(N=1, H=1, W=m, Cin=kpad, Cout=d.Cout, kh=1, kw=1, sh=1, sw=1, dh=1,
+                                dw=1, pad_t=0, pad_l=0, Ho=1, Wo=m)
+            node.attrs["gemm_desc"] = gd
+            self.L("f", "mcn_im2col", d, DT_CODE[x.dtype], self.tbuf[x], Ptr(col), kpad,
+                   tag=node.scope + "/im2col")
+            self.L("f", "mcn_conv2d_fprop_tc", gd, Ptr(col), self.pbf16t(w), pb, py, self.ccode, 0,
+                   tag=node.scope)
+        else:
+            wdt, pw = self._direct_weight(w)
+            self.L("f", "mcn_conv2d_fprop_direct", d, self.ccode, self.tbuf[x], wdt, pw, pb, py,
+                   tag=node.scope)
+
+    def _direct_weight(self, w):
+        return 0, self.pvar(w)   # fp32 master weights
+
+    def _f_dwconv2d(self, node):
+        x, y = node.inputs[0], node.outputs[0]
+        w = node.vars["w"]
+        d = self._conv_geometry(node)
+        # depthwise: desc.Cout is unused by the kernels; keep the input channel count
+        d = self.conv_desc(**dict({f: getattr(d, f) for f in ConvDesc.FIELDS}, Cout=d.Cin))
+        node.attrs["desc"] = d
+        py = self.alloc_act(y)
+        self.L("f", "mcn_dwconv2d_fwd", d, node.attrs["mult"], self.ccode, self.tbuf[x], 0,
+               self.pvar(w), py, tag=node.scope)
+        if "b" in node.vars:
+            self.L("f", "mcn_bias_add", self.ccode, py, y.size // y.shape[-1], y.shape[-1],
+                   self.pvar(node.vars["b"]), tag=node.scope + "/bias")
+
+    def _f_conv2d_transpose(self, node):
+        # forward of conv2d_transpose == dgrad of the conv mapping y-shaped -> x-shaped tensors
+        x, y = node.inputs[0], node.outputs[0]
+        w = node.vars["w"]   # stored [kh,kw,Cin_t,Cout_t] (reference convnet.py:2460)
+        a = node.attrs
+        n, h, wd, ci = x.shape
+        _, ho, wo, co = y.shape
+        # underlying conv: input = y (co channels), output = x (ci channels); its HWIO weight is
+        # [kh,kw,co,ci] = the stored weight with the last two axes swapped, i.e. the stored
+        # layout read as O-H-W-I... handled by passing the "transposed" bf16 copy to dgrad.
+        d = self.conv_desc(N=n, H=ho, W=wo, Cin=co, Cout=ci, kh=a["k"][0], kw=a["k"][1],
+                           sh=a["s"][0], sw=a["s"][1], dh=a["d"][0], dw=a["d"][1],
+                           pad_t=a["pad"][0], pad_l=a["pad"][1], Ho=h, Wo=wd)
+        node.attrs["desc"] = d
+        py = self.alloc_act(y)
+        if node.attrs["route"] == "tc":
+            # dgrad wants W_conv[tap][Cin_conv=co][Cout_conv=ci] = stored[tap][ci][co]^T = bf16_t copy
+            self.L("f", "mcn_conv2d_dgrad_tc", d, self.tbuf[x], self.pbf16t(w), py, self.ccode,
+                   self.conv_mode, tag=node.scope)
+        else:
+            raise NotImplementedError("transposed conv needs channel counts that are multiples of 8 "
+                                      "on the tensor-core path; direct route is lowered in _f_tconv_direct")
+        if "b" in node.vars:
+            self.L("f", "mcn_bias_add", self.ccode, py, y.size // co, co, self.pvar(node.vars["b"]),
+                   tag=node.scope + "/bias")
+
+    def _f_dense(self, node):
+        x = node.inputs[0]
+        y = node.attrs["final"]
+        w = node.vars["w"]
+        b = node.vars.get("b")
+        n, ci = x.shape
+        co = w.shape[1]
+        d = self.conv_desc(N=1, H=1, W=n, Cin=ci, Cout=co, kh=1, kw=1, sh=1, sw=1, dh=1, dw=1,
+                           pad_t=0, pad_l=0, Ho=1, Wo=n)
+        node.attrs["desc"] = d
+        py = self.alloc_act(y)
+        if y is not node.outputs[0]:
+            self.tbuf[node.outputs[0]] = py
+        pb = self.pvar(b) if b is not None else NULL
+        if node.attrs["route"] == "tc":
+            self.L("f", "mcn_conv2d_fprop_tc", d, self.tbuf[x], self.pbf16t(w), pb, py,
+                   DT_CODE[y.dtype], 0, tag=node.scope)
+        else:
+            self.L("f", "mcn_conv2d_fprop_direct", d, self.ccode, self.tbuf[x], 0, self.pvar(w), pb,
+                   py, tag=node.scope)
+
+    def _f_cast(self, node):
+        x, y = node.inputs[0], node.outputs[0]
+        if x.dtype == y.dtype:
+            self.tbuf[y] = self.tbuf[x]
+            return
+        py = self.alloc_act(y)
+        self.L("f", "mcn_cast", DT_CODE[x.dtype], self.tbuf[x], DT_CODE[y.dtype], py, x.size,
+               tag="cast")
+
+    def _f_bn(self, node):
+        x = node.inputs[0]
+        y = node.attrs["final"]
+        c = x.shape[-1]
+        rows = x.size // c
+        v = node.vars
+        sums = self.new_buf("bn_sums:%s" % node.scope, 2 * c * 8, "zero")
+        save = self.new_buf("bn_save:%s" % node.scope, 2 * c * 4, "state")
+        node.attrs["save"] = save
+        node.attrs["rows"] = rows
+        py = self.alloc_act(y)
+        for o in node.outputs:
+            self.tbuf.setdefault(o, py)
+        pg = self.pvar(v["gamma"]) if "gamma" in v else NULL
+        pbeta = self.pvar(v["beta"]) if "beta" in v else NULL
+        res = node.attrs["residual"]
+        pres = self.tbuf[res] if res is not None else NULL
+        self.L("f", "mcn_bn_stats", self.ccode, self.tbuf[x], rows, c, Ptr(sums), tag=node.scope + "/stats")
+        if self.sync_bn:
+            self.allreduce_points.append(("f", len(self.fwd), Ptr(sums), 2 * c * 8, "f64"))
+        upd = node.attrs["update"]
+        self.L("f", "mcn_bn_finalize", Ptr(sums), float(rows * (self.world if self.sync_bn else 1)), c,
+               node.attrs["eps"], node.attrs["momentum"], Ptr(save), Ptr(save, c * 4),
+               self.pvar(v["mu"]) if upd else NULL, self.pvar(v["sigma"]) if upd else NULL,
+               tag=node.scope + "/finalize")
+        self.L("f", "mcn_bn_apply", self.ccode, self.tbuf[x], rows, c, Ptr(save), Ptr(save, c * 4), pg,
+               pbeta, pres, node.attrs["act"], node.attrs["alpha"], py, tag=node.scope + "/apply")
+        self.bn_layers.append(node)
+
+    def _f_act(self, node):
+        x, y = node.inputs[0], node.outputs[0]
+        py = self.alloc_act(y)
+        self.L("f", "mcn_act_fwd", DT_CODE[x.dtype], self.tbuf[x], x.size, node.attrs["act"],
+               node.attrs["alpha"], py, tag="act")
+
+    def _f_add(self, node):
+        a, b = node.inputs
+        y = node.attrs["final"]
+        py = self.alloc_act(y)
+        self.tbuf.setdefault(node.outputs[0], py)
+        self.L("f", "mcn_add_act_fwd", DT_CODE[a.dtype], self.tbuf[a], self.tbuf[b], a.size,
+               node.attrs["act"], node.attrs["alpha"], py, tag="add")
+
+    def _f_scale_bcast(self, node):
+        x, m = node.inputs
+        y = node.outputs[0]
+        n, h, w, c = x.shape
+        py = self.alloc_act(y)
+        self.L("f", "mcn_scale_bcast_fwd", DT_CODE[x.dtype], self.tbuf[x], self.tbuf[m], n, h * w, c,
+               py, tag="se_scale")
+
+    def _f_max_pool(self, node):
+        x, y = node.inputs[0], node.outputs[0]
+        a = node.attrs
+        n, h, w, c = x.shape
+        _, ho, wo, _ = y.shape
+        py = self.alloc_act(y)
+        arg = self.new_buf("argmax:%s" % node.scope, y.size * 4, "act")
+        node.attrs["argmax"] = arg
+        self.L("f", "mcn_maxpool_fwd", DT_CODE[x.dtype], self.tbuf[x], n, h, w, c, a["k"][0], a["k"][1],
+               a["s"][0], a["s"][1], a["pad"][0], a["pad"][1], ho, wo, py, Ptr(arg), tag="max_pool")
+
+    def _f_avg_pool(self, node):
+        x, y = node.inputs[0], node.outputs[0]
+        a = node.attrs
+        n, h, w, c = x.shape
+        _, ho, wo, _ = y.shape
+        py = self.alloc_act(y)
+        self.L("f", "mcn_avgpool_fwd", DT_CODE[x.dtype], self.tbuf[x], n, h, w, c, a["k"][0], a["k"][1],
+               a["s"][0], a["s"][1], a["pad"][0], a["pad"][1], ho, wo, py, tag="avg_pool")
+
+    def _f_gap(self, node):
+        x, y = node.inputs[0], node.outputs[0]
+        n, h, w, c = x.shape
+        py = self.alloc_act(y)
+        self.L("f", "mcn_gap_fwd", DT_CODE[x.dtype], self.tbuf[x], n, h * w, c, py, DT_CODE[y.dtype],
+               tag="gap")
+
+    def _f_concat(self, node):
+        y = node.outputs[0]
+        py = self.alloc_act(y)
+        ctot = y.shape[-1]
+        rows = y.size // ctot
+        off = 0
+        for t in node.inputs:
+            c = t.shape[-1]
+            self.L("f", "mcn_copy_channels", DT_CODE[t.dtype], self.tbuf[t], rows, c, 0, py, ctot, off,
+                   c, 0, tag="concat")
+            off += c
+
+    def _f_reshape(self, node):
+        self.tbuf[node.outputs[0]] = self.tbuf[node.inputs[0]]
+
+    def _f_stop_gradient(self, node):
+        self.tbuf[node.outputs[0]] = self.tbuf[node.inputs[0]]
+
+    def _f_affine(self, node):
+        raise NotImplementedError("scalar affine ops on tensors are not lowered yet")
+
+    def _f_resize_bilinear(self, node):
+        x, y = node.inputs[0], node.outputs[0]
+        n, h, w, c = x.shape
+        _, ho, wo, _ = y.shape
+        py = self.alloc_act(y)
+        self.L("f", "mcn_resize_bilinear_fwd", DT_CODE[x.dtype], self.tbuf[x], n, h, w, c, ho, wo,
+               node.attrs["mode"], py, tag="resize")
+
+    def _f_softmax(self, node):
+        # probabilities come for free from the fused loss kernel when it exists
+        x, y = node.inputs[0], node.outputs[0]
+        b = self.new_buf("probs", x.size * 4, "act")
+        self.tbuf[y] = Ptr(b)
+        node.attrs["standalone"] = True
+
+    def _f_softmax_xent(self, node):
+        logits, labels = node.inputs
+        a = node.attrs
+        c = logits.shape[-1]
+        rows = a["rows"]
+        loss = self.new_buf("loss", 16, "zero")
+        self.loss_slots["loss"] = Ptr(loss)
+        self.loss_slots["l2"] = Ptr(loss, 4)
+        self.tbuf[node.outputs[0]] = Ptr(loss)
+        dlog = self.new_buf("dlogits", logits.size * 4, "act")
+        node.attrs["dlogits"] = dlog
+        probs = NULL
+        src = logits.node.inputs[0] if logits.node is not None and logits.node.op == "cast" else logits
+        for cns in list(logits.consumers) + list(src.consumers):
+            if cns.op == "softmax" and self.fetch_pred:
+                probs = self.tbuf.get(cns.outputs[0])
+                if probs is None:
+                    pb = self.new_buf("probs", logits.size * 4, "act")
+                    probs = Ptr(pb)
+                    self.tbuf[cns.outputs[0]] = probs
+                cns.attrs["standalone"] = False
+        cw = NULL
+        if a["class_weights"] is not None:
+            cwb = self.new_buf("class_weights", c * 4, "state")
+            node.attrs["cw_buf"] = cwb
+            cw = Ptr(cwb)
+        # loss = mean over rows (convnet.py:594); gradient seeded with loss_scale / rows
+        self.L("f", "mcn_softmax_xent", self.tbuf[logits], self.tbuf[labels], rows, c, cw,
+               a["label_smoothing"], self.loss_scale / rows, Ptr(loss), Ptr(dlog), probs,
+               tag="softmax_xent")
+
+    # ------------------------------------------------------------------ backward emission
+    def _emit_backward(self):
+        self.g = {}          # Tensor -> (Ptr, handle or None)
+        g = self.graph
+        for node in reversed(g.nodes):
+            if node.attrs.get("fused_into") is not None:
+                continue
+            fn = getattr(self, "_b_" + node.op, None)
+            if fn is None:
+                continue
+            out = node.attrs.get("final", node.outputs[0] if node.outputs else None)
+            if node.op == "softmax_xent":
+                fn(node)
+                continue
+            if out is None or out not in self.g:
+                continue
+            fn(node, self.g[out][0])
+            self._release_grad(out)
+
+    def _release_grad(self, t):
+        p, h = self.g.pop(t)
+        if h is not None:
+            self.tfree(h)
+
+    def contribute(self, t, nbytes, emit, dtype=None):
+        """Route a gradient contribution for tensor t: the first one writes the gradient buffer,
+        later ones go through a temporary and are accumulated."""
+        if not self._tensor_needs_grad(t):
+            return
+        dt = dtype or t.dtype
+        if t not in self.g:
+            p, h = self.talloc(nbytes)
+            self.g[t] = (p, h)
+            emit(p)
+        else:
+            p, h = self.talloc(nbytes)
+            emit(p)
+            self.L("b", "mcn_accumulate", DT_CODE[dt], self.g[t][0], p, nbytes // DT_SIZE[dt],
+                   tag="grad_accumulate")
+            self.tfree(h)
+
+    def _b_softmax_xent(self, node):
+        logits = node.inputs[0]
+        # the fused kernel already produced dlogits (fp32)
+        self.g[logits] = (Ptr(node.attrs["dlogits"]), None)
+
+    def _b_cast(self, node, gy):
+        x, y = node.inputs[0], node.outputs[0]
+        self.contribute(x, x.size * DT_SIZE[x.dtype],
+                        lambda p: self.L("b", "mcn_cast", DT_CODE[y.dtype], gy, DT_CODE[x.dtype], p,
+                                         x.size, tag="cast_bwd"))
+
+    def _b_dense(self, node, gy):
+        x = node.inputs[0]
+        y = node.attrs["final"]
+        w = node.vars["w"]
+        d = node.attrs["desc"]
+        n, ci = x.shape
+        co = w.shape[1]
+        if "b" in node.vars:
+            self.L("b", "mcn_bias_grad", DT_CODE[y.dtype], gy, n, co, self.pgrad(node.vars["b"]),
+                   tag=node.scope + "/dbias")
+        if node.attrs["route"] == "tc":
+            gyb = gy
+            h = None
+            if y.dtype != "bf16":
+                gyb, h = self.talloc(n * co * 2)
+                self.L("b", "mcn_cast", DT_CODE[y.dtype], gy, 1, gyb, n * co, tag="dlogits_bf16")
+            if w.trainable:
+                self.L("b", "mcn_conv2d_wgrad_tc", d, self.tbuf[x], gyb, self.pgrad(w), 0,
+                       tag=node.scope + "/wgrad")
+            self.contribute(x, x.size * 2,
+                            lambda p: self.L("b", "mcn_conv2d_dgrad_tc", d, gyb, self.pbf16(w), p, 1, 0,
+                                             tag=node.scope + "/dgrad"))
+            if h is not None:
+                self.tfree(h)
+        else:
+            if w.trainable:
+                self.L("b", "mcn_conv2d_wgrad_direct", d, self.ccode, self.tbuf[x], gy, self.pgrad(w),
+                       tag=node.scope + "/wgrad")
+            self.contribute(x, x.size * self.csz,
+                            lambda p: self.L("b", "mcn_conv2d_dgrad_direct", d, self.ccode, gy, 0,
+                                             self.pvar(w), p, tag=node.scope + "/dgrad"))
+
+    def _b_conv2d(self, node, gy):
+        x, y = node.inputs[0], node.outputs[0]
+        w = node.vars["w"]
+        d = node.attrs["desc"]
+        route = node.attrs["route"]
+        if "b" in node.vars:
+            self.L("b", "mcn_bias_grad", self.ccode, gy, y.size // d.Cout, d.Cout,
+                   self.pgrad(node.vars["b"]), tag=node.scope + "/dbias")
+        if route == "tc":
+            if w.trainable:
+                self.L("b", "mcn_conv2d_wgrad_tc", d, self.tbuf[x], gy, self.pgrad(w), self.conv_mode,
+                       tag=node.scope + "/wgrad")
+            self.contribute(x, x.size * 2,
+                            lambda p: self.L("b", "mcn_conv2d_dgrad_tc", d, gy, self.pbf16(w), p, 1,
+                                             self.conv_mode, tag=node.scope + "/dgrad"))
+        elif route == "im2col":
+            if w.trainable:
+                self.L("b", "mcn_conv2d_wgrad_tc", node.attrs["gemm_desc"], Ptr(node.attrs["col"]), gy,
+                       self.pgrad(w), 0, tag=node.scope + "/wgrad")
+        else:
+            if w.trainable:
+                self.L("b", "mcn_conv2d_wgrad_direct", d, self.ccode, self.tbuf[x], gy, self.pgrad(w),
+                       tag=node.scope + "/wgrad")
+            self.contribute(x, x.size * self.csz,
+                            lambda p: self.L("b", "mcn_conv2d_dgrad_direct", d, self.ccode, gy, 0,
+                                             self.pvar(w), p, tag=node.scope + "/dgrad"))
+
+    def _b_dwconv2d(self, node, gy):
+        x, y = node.inputs[0], node.outputs[0]
+        w = node.vars["w"]
+        d = node.attrs["desc"]
+        mult = node.attrs["mult"]
+        if "b" in node.vars:
+            self.L("b", "mcn_bias_grad", self.ccode, gy, y.size // y.shape[-1], y.shape[-1],
+                   self.pgrad(node.vars["b"]), tag=node.scope + "/dbias")
+        if w.trainable:
+            self.L("b", "mcn_dwconv2d_bwd_filter", d, mult, self.ccode, self.tbuf[x], gy, self.pgrad(w),
+                   tag=node.scope + "/dw_wgrad")
+        self.contribute(x, x.size * self.csz,
+                        lambda p: self.L("b", "mcn_dwconv2d_bwd_data", d, mult, self.ccode, gy, 0,
+                                         self.pvar(w), p, tag=node.scope + "/dw_dgrad"))
+
+    def _b_conv2d_transpose(self, node, gy):
+        # y = dgrad_conv(x): dL/dx = fprop_conv(gy); dL/dW_conv[tap][co][ci] = wgrad_conv(a=gy, dy=x)
+        x, y = node.inputs[0], node.outputs[0]
+        w = node.vars["w"]
+        d = node.attrs["desc"]
+        if "b" in node.vars:
+            self.L("b", "mcn_bias_grad", self.ccode, gy, y.size // y.shape[-1], y.shape[-1],
+                   self.pgrad(node.vars["b"]), tag=node.scope + "/dbias")
+        if w.trainable:
+            # wgrad writes [tap][Cin_conv=co][Cout_conv=ci]; the variable is stored [tap][ci][co]
+            tmp, h = self.talloc(w.storage_size * 4)
+            self.L("b", "mcn_fill_f32", tmp, w.storage_size, 0.0, tag="zero")
+            self.L("b", "mcn_conv2d_wgrad_tc", d, gy, self.tbuf[x], tmp, self.conv_mode,
+                   tag=node.scope + "/wgrad")
+            taps, ci, co = w.gemm_dims
+            self.L("b", "mcn_transpose_add_f32", tmp, taps, co, ci, self.pgrad(w), tag="wgrad_T")
+            self.tfree(h)
+        # fprop of the underlying conv needs W_conv as [tap][Cout_conv=ci][Cin_conv=co] = stored layout
+        self.contribute(x, x.size * 2,
+                        lambda p: self.L("b", "mcn_conv2d_fprop_tc", d, gy, self.pbf16(w), NULL, p, 1,
+                                         self.conv_mode, tag=node.scope + "/dgrad"))
+
+    def _b_bn(self, node, gy):
+        x = node.inputs[0]
+        y = node.attrs["final"]
+        c = x.shape[-1]
+        rows = node.attrs["rows"]
+        v = node.vars
+        save = node.attrs["save"]
+        act = node.attrs["act"]
+        res = node.attrs["residual"]
+        pg = self.pvar(v["gamma"]) if "gamma" in v else NULL
+        pbeta = self.pvar(v["beta"]) if "beta" in v else NULL
+        # derivative from the output when a residual was fused (or for relu-family generally it is
+        # cheaper to recompute from x, which is read anyway)
+        py = self.tbuf[y] if (res is not None and act != 0) else NULL
+        # local sums double as dbeta / dgamma; without a trainable beta/gamma they go to scratch
+        scratch = None
+        if "beta" in v and v["beta"].trainable and "gamma" in v and v["gamma"].trainable:
+            s1, s2 = self.pgrad(v["beta"]), self.pgrad(v["gamma"])
+        else:
+            sp, scratch = self.talloc(2 * c * 4)
+            self.L("b", "mcn_fill_f32", sp, 2 * c, 0.0, tag="zero")
+            s1, s2 = sp, sp + c * 4
+        self.L("b", "mcn_bn_bwd_reduce", self.ccode, gy, self.tbuf[x], py, rows, c, Ptr(save),
+               Ptr(save, c * 4), pg, pbeta, act, node.attrs["alpha"], s1, s2, tag=node.scope + "/bwd_reduce")
+        g1, g2, gh = s1, s2, None
+        count = float(rows)
+        if self.sync_bn:
+            gp, gh = self.talloc(2 * c * 4)
+            self.L("b", "mcn_cast", 0, s1, 0, gp, c, tag="syncbn_copy")
+            self.L("b", "mcn_cast", 0, s2, 0, gp + c * 4, c, tag="syncbn_copy")
+            self.allreduce_points.append(("b", len(self.bwd), gp, 2 * c * 4, "f32"))
+            g1, g2 = gp, gp + c * 4
+            count = float(rows * self.world)
+        need_x = self._tensor_needs_grad(x)
+        need_r = res is not None and self._tensor_needs_grad(res)
+        if need_x or need_r:
+            esz = self.csz
+            # residual gradient: first contribution can be written in place by the kernel
+            pres, res_tmp = NULL, None
+            if need_r:
+                if res not in self.g:
+                    p, h = self.talloc(res.size * esz)
+                    self.g[res] = (p, h)
+                    pres = p
+                else:
+                    pres, res_tmp = self.talloc(res.size * esz)
+            if not need_x:
+                dxp, dxh = self.talloc(x.size * esz)
+                self.L("b", "mcn_bn_bwd_apply", self.ccode, gy, self.tbuf[x], py, rows, c, Ptr(save),
+                       Ptr(save, c * 4), pg, pbeta, act, node.attrs["alpha"], g1, g2, count, dxp, pres,
+                       tag=node.scope + "/bwd_apply")
+                self.tfree(dxh)
+            if need_x:
+                def emit(p):
+                    self.L("b", "mcn_bn_bwd_apply", self.ccode, gy, self.tbuf[x], py, rows, c, Ptr(save),
+                           Ptr(save, c * 4), pg, pbeta, act, node.attrs["alpha"], g1, g2, count, p, pres,
+                           tag=node.scope + "/bwd_apply")
+                self.contribute(x, x.size * esz, emit)
+            if res_tmp is not None:
+                self.L("b", "mcn_accumulate", self.ccode, self.g[res][0], pres, res.size,
+                       tag="grad_accumulate")
+                self.tfree(res_tmp)
+        if gh is not None:
+            self.tfree(gh)
+        if scratch is not None:
+            self.tfree(scratch)
+
+    def _b_act(self, node, gy):
+        x = node.inputs[0]
+        self.contribute(x, x.size * DT_SIZE[x.dtype],
+                        lambda p: self.L("b", "mcn_act_bwd", DT_CODE[x.dtype], gy, self.tbuf[x], x.size,
+                                         node.attrs["act"], node.attrs["alpha"], p, tag="act_bwd"))
+
+    def _b_add(self, node, gy):
+        a, b = node.inputs
+        y = node.attrs["final"]
+        esz = DT_SIZE[a.dtype]
+        if node.attrs["act"] != 0:
+            dz, h = self.talloc(a.size * esz)
+            self.L("b", "mcn_add_act_bwd", DT_CODE[a.dtype], gy, self.tbuf[y], a.size, node.attrs["act"],
+                   node.attrs["alpha"], dz, tag="add_act_bwd")
+        else:
+            dz, h = gy, None
+        for t in (a, b):
+            self.contribute(t, t.size * esz,
+                            lambda p: self.L("b", "mcn_cast", DT_CODE[t.dtype], dz, DT_CODE[t.dtype], p,
+                                             t.size, tag="grad_copy"))
+        if h is not None:
+            self.tfree(h)
+
+    def _b_scale_bcast(self, node, gy):
+        x, m = node.inputs
+        n, hh, w, c = x.shape
+        dm32, h32 = self.talloc(n * c * 4)
+        state = {}
+
+        def emit(p):
+            self.L("b", "mcn_scale_bcast_bwd", DT_CODE[x.dtype], gy, self.tbuf[x], self.tbuf[m], n,
+                   hh * w, c, p, dm32, tag="se_scale_bwd")
+            state["done"] = True
+        self.contribute(x, x.size * DT_SIZE[x.dtype], emit)
+        if state.get("done"):
+            self.contribute(m, m.size * DT_SIZE[m.dtype],
+                            lambda p: self.L("b", "mcn_cast", 0, dm32, DT_CODE[m.dtype], p, n * c,
+                                             tag="se_dm_cast"))
+        self.tfree(h32)
+
+    def _b_max_pool(self, node, gy):
+        x, y = node.inputs[0], node.outputs[0]
+        a = node.attrs
+        n, h, w, c = x.shape
+        _, ho, wo, _ = y.shape
+        self.contribute(x, x.size * DT_SIZE[x.dtype],
+                        lambda p: self.L("b", "mcn_maxpool_bwd", DT_CODE[x.dtype], gy, Ptr(a["argmax"]), n,
+                                         h, w, c, a["k"][0], a["k"][1], a["s"][0], a["s"][1], a["pad"][0],
+                                         a["pad"][1], ho, wo, p, tag="max_pool_bwd"))
+
+    def _b_avg_pool(self, node, gy):
+        x, y = node.inputs[0], node.outputs[0]
+        a = node.attrs
+        n, h, w, c = x.shape
+        _, ho, wo, _ = y.shape
+        self.contribute(x, x.size * DT_SIZE[x.dtype],
+                        lambda p: self.L("b", "mcn_avgpool_bwd", DT_CODE[x.dtype], gy, n, h, w, c,
+                                         a["k"][0], a["k"][1], a["s"][0], a["s"][1], a["pad"][0],
+                                         a["pad"][1], ho, wo, p, tag="avg_pool_bwd"))
+
+    def _b_gap(self, node, gy):
+        x, y = node.inputs[0], node.outputs[0]
+        n, h, w, c = x.shape
+        self.contribute(x, x.size * DT_SIZE[x.dtype],
+                        lambda p: self.L("b", "mcn_gap_bwd", DT_CODE[x.dtype], gy, DT_CODE[y.dtype], n,
+                                         h * w, c, p, tag="gap_bwd"))
+
+    def _b_concat(self, node, gy):
+        y = node.outputs[0]
+        ctot = y.shape[-1]
+        rows = y.size // ctot
+        off = 0
+        for t in node.inputs:
+            c = t.shape[-1]
+            o = off
+            self.contribute(t, t.size * DT_SIZE[t.dtype],
+                            lambda p: self.L("b", "mcn_copy_channels", DT_CODE[t.dtype], gy, rows, ctot, o,
+                                             p, c, 0, c, 0, tag="concat_bwd"))
+            off += c
+
+    def _b_reshape(self, node, gy):
+        x = node.inputs[0]
+        if x not in self.g and self._tensor_needs_grad(x):
+            # a reshape is a view: hand the gradient buffer over instead of copying
+            self.g[x] = self.g[node.outputs[0]]
+            self.g[node.outputs[0]] = (gy, None)
+            return
+        self.contribute(x, x.size * DT_SIZE[x.dtype],
+                        lambda p: self.L("b", "mcn_cast", DT_CODE[x.dtype], gy, DT_CODE[x.dtype], p, x.size,
+                                         tag="grad_copy"))
+
+    def _b_resize_bilinear(self, node, gy):
+        x, y = node.inputs[0], node.outputs[0]
+        n, h, w, c = x.shape
+        _, ho, wo, _ = y.shape
+        self.contribute(x, x.size * DT_SIZE[x.dtype],
+                        lambda p: self.L("b", "mcn_resize_bilinear_bwd", DT_CODE[x.dtype], gy, n, h, w, c,
+                                         ho, wo, node.attrs["mode"], p, tag="resize_bwd"))
+
+    # ------------------------------------------------------------------ summaries
+    def launch_histogram(self):
+        h = collections.Counter()
+        for l in self.fwd + self.bwd:
+            h[l.fn] += 1
+        return dict(h)

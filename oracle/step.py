@@ -1,0 +1,74 @@
+"""ORACLE (test infrastructure): one training step with the reference's update semantics.
+
+Restates SURVEY.md 3.2 / reference optimizers.py:89-177 for one tower on CPU:
+  loss -> gradients -> [EMA shadows from PRE-step values with num_updates = global_step before
+  the increment; BN moving statistics assigned] -> apply_gradients -> decoupled weight decay.
+lr = base_lr * batch/256 * multiplier (optimizers.py:46,57).  Data-parallel replicas with
+synchronised BN are numerically one tower at the global batch, which is what this computes.
+"""
+import torch
+
+from . import tf_ops as ops
+
+
+class OracleTrainer(object):
+    def __init__(self, model, optimizer="nesterov", batch_size=None, **kwargs):
+        self.model = model
+        self.kind = optimizer.lower()
+        kw = dict(model._parameters)
+        kw.update(kwargs)
+        self.kw = kw
+        self.batch_size = batch_size
+        self.base_lr = float(kw.get("base_learning_rate", 0.1))
+        self.momentum = float(kw.get("momentum", 0.9))
+        self.base_wd = float(kw.get("base_weight_decay", 0.0))
+        self.wd_sched = bool(kw.get("weight_decay_scheduling", True))
+        self.bias_norm_decay = bool(kw.get("bias_norm_decay", False))
+        self.global_step = 0
+        self.state = {}
+        self.ema = None
+        self.grads = {}
+
+    def step(self, X, Y, lr_multiplier=1.0, update=True):
+        m = self.model
+        batch = self.batch_size or len(X)
+        loss = m.forward(X, Y)
+        if self.ema is None:
+            self.ema = {k: v.detach().clone() for k, v in m.vars.items()}
+        train = [k for k, meta in m.var_meta.items() if meta["trainable"] and meta["kind"] != "stat"]
+        grads = torch.autograd.grad(loss, [m.vars[k] for k in train], allow_unused=True)
+        self.grads = {k: (g if g is not None else torch.zeros_like(m.vars[k])) for k, g in zip(train, grads)}
+        if not update:
+            return float(loss)
+        lr = self.base_lr * batch / 256.0 * lr_multiplier
+        d_t = ops.ema_decay(m.moving_average_decay, self.global_step)
+        with torch.no_grad():
+            # EMA shadows see the pre-step values (control deps optimizers.py:159,175)
+            for k, v in m.vars.items():
+                self.ema[k] = self.ema[k] - (1.0 - d_t) * (self.ema[k] - v)
+            for k, v in m.bn_updates.items():
+                m.vars[k] = v.clone()
+            t = self.global_step + 1
+            for k in train:
+                w, g = m.vars[k].detach(), self.grads[k]
+                st = self.state.setdefault(k, {})
+                if self.kind in ("nesterov", "momentum", "sgd"):
+                    w, st["a"] = ops.nesterov_update(w, g, st.get("a", torch.zeros_like(w)), lr, self.momentum)
+                elif self.kind == "rmsprop":
+                    w, st["ms"], st["mom"] = ops.rmsprop_update(
+                        w, g, st.get("ms", torch.ones_like(w)), st.get("mom", torch.zeros_like(w)), lr,
+                        0.9, self.momentum, 1e-3)
+                elif self.kind == "adam":
+                    w, st["m"], st["v"] = ops.adam_update(
+                        w, g, st.get("m", torch.zeros_like(w)), st.get("v", torch.zeros_like(w)), lr, t,
+                        self.momentum, 0.999, 1e-3)
+                else:
+                    raise ValueError(self.kind)
+                meta = m.var_meta[k]
+                decayed = meta["kind"] == "weight" or (self.bias_norm_decay and meta["kind"] in ("bias", "norm"))
+                if self.base_wd > 0 and decayed:
+                    wd = self.base_wd * batch / 256.0 * (lr_multiplier if self.wd_sched else 1.0)
+                    w = w - wd * w
+                m.vars[k] = w.clone()
+        self.global_step += 1
+        return float(loss)

@@ -1,0 +1,119 @@
+"""GPU parity: the reference's models/resnet_v1_5.py, unchanged, on the B200 engine vs the CPU
+oracle — per-layer activations through the model's own d[...] taps, weight gradients, loss, and a
+short loss curve (SURVEY.md 8c pins 4).
+
+Tolerances (stated, with their reason):
+  fp32 activations  rel-L2 <= 2e-4 per tap, loss 1e-3 relative.
+  fp32 gradients    rel-L2 <= 8e-2 per variable.  A ReLU network's gradient is discontinuous in
+      its pre-activations: two fp32 implementations whose activations agree to 3e-5 still disagree
+      on the sign of a handful of near-zero pre-activations, and each flipped mask bit changes the
+      gradient of a 32-pixel-per-channel layer by ~1 %.  tests/test_oracle.py shows the SAME 1-2 %
+      between the fp32 and fp64 oracle, so this is the floor for any model-level comparison; the
+      kernels themselves are held to 1e-4..1e-5 on gradients in tests/test_gpu_ops.py.
+  bf16 activations  rel-L2 <= 6e-2 up to block_2 and <= 0.35 after (two bf16 pipelines drift apart
+      by an ulp-sized random walk amplified by small-batch BN; the oracle rounds at the same
+      points but accumulates in a different order), loss 3 %, 4-step loss curve 3 %."""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import build_pair, rel_l2, synthetic_batch
+
+pytestmark = pytest.mark.gpu
+
+SHAPE = [64, 64, 3]
+NCLS = 16
+BATCH = 8
+
+
+def _engine(pm, vals, keep=(), **kw):
+    from myconvnet_b200.engine import Engine
+    eng = Engine(pm, keep=keep, **kw)
+    eng.set_variables(vals)
+    return eng
+
+
+@pytest.mark.parametrize("dtype,tol_act,tol_grad", [("f32", 2e-4, 8e-2), ("bf16", 6e-2, None)])
+def test_resnet50_layers_and_grads(have_reference_models, dtype, tol_act, tol_grad):
+    from oracle.step import OracleTrainer
+    pm, om, vals = build_pair("models/resnet_v1_5.py", "ResNet50", SHAPE, NCLS, BATCH, dtype)
+    X, Y = synthetic_batch(BATCH, SHAPE, NCLS)
+    taps = {k: t for k, t in pm.d.items() if hasattr(t, "shape") and k not in ("pred",)}
+    eng = _engine(pm, vals, keep=list(taps.values()))
+    loss_dev = eng.train_step(X, Y, update=False)
+    tr = OracleTrainer(om)
+    tr.step(X, Y, update=False)
+    loss_ref = float(om.data_loss)     # without an optimiser step the device reports the data term
+    bad = []
+    for k, t in taps.items():
+        ref = om.d[k].t.detach().numpy()
+        got = eng.fetch(t)
+        e = rel_l2(got, ref)
+        late = dtype == "bf16" and (k.startswith("block_3") or k.startswith("block_4") or k.startswith("logits"))
+        if e > (0.35 if late else tol_act):
+            bad.append((k, e))
+    assert not bad, "activation mismatches: %s" % bad[:8]
+    assert abs(loss_dev - loss_ref) <= 1e-3 * abs(loss_ref) + (1e-4 if dtype == "f32" else 3e-2)
+    grads = eng.get_gradients()
+    assert all(np.isfinite(g).all() for g in grads.values())
+    if tol_grad is None:
+        return
+    gbad = []
+    for k, g in tr.grads.items():
+        ref = g.numpy()
+        if k.endswith("weights"):
+            ref = ref - 0.0   # oracle grads include the L2 term; device folds it into the optimiser
+            ref = ref - om._parameters.get("l2_reg", 1e-4) * vals[k]
+        e = rel_l2(grads[k], ref)
+        if e > tol_grad and np.linalg.norm(ref) > 1e-6:
+            gbad.append((k, e))
+    assert not gbad, "gradient mismatches: %s" % gbad[:8]
+
+
+@pytest.mark.parametrize("dtype,tol", [("f32", 1e-3), ("bf16", 3e-2)])
+def test_resnet50_fused_loss_curve(have_reference_models, dtype, tol):
+    """Fused plan (BN+ReLU+residual, dense+cast) over several optimiser steps vs the oracle."""
+    from oracle.step import OracleTrainer
+    pm, om, vals = build_pair("models/resnet_v1_5.py", "ResNet50", SHAPE, NCLS, BATCH, dtype,
+                              base_learning_rate=0.05)
+    X, Y = synthetic_batch(BATCH, SHAPE, NCLS)
+    eng = _engine(pm, vals)
+    tr = OracleTrainer(om, base_learning_rate=0.05)
+    dev, ref = [], []
+    for _ in range(4):
+        dev.append(eng.train_step(X, Y))
+        ref.append(tr.step(X, Y))
+    assert np.all(np.isfinite(dev))
+    for a, b in zip(dev, ref):
+        assert abs(a - b) <= tol * abs(b) + tol, (dev, ref)
+    # moving statistics and EMA shadows follow the reference update order
+    v_dev = eng.get_variables()
+    for k in ("block_0/conv_0/bn/mu", "block_0/conv_0/bn/sigma"):
+        assert rel_l2(v_dev[k], om.vars[k].numpy()) < 5 * tol, k
+    e_dev = eng.get_variables(ema=True)
+    k = "block_None/logits/weights"
+    assert rel_l2(e_dev[k], tr.ema[k].numpy()) < 5 * tol
+
+
+def test_maxpool_argmax_bit_exact():
+    """Pooling argmax indices are bit-exact against the oracle's first-max-in-window rule."""
+    import ctypes
+    from myconvnet_b200 import lib as L
+    from oracle import tf_ops
+    lib = L.load()
+    rng = np.random.default_rng(3)
+    # quantised values make ties frequent
+    x = (rng.integers(0, 4, size=(2, 9, 11, 16)).astype(np.float32)) * 0.5
+    xt = torch.from_numpy(x).cuda()
+    for k, s, pad in [(3, 2, "SAME"), (2, 2, "VALID"), (3, 1, "SAME")]:
+        ho, pt, _ = tf_ops.same_pad(9, k, s, 1, pad)
+        wo, pl, _ = tf_ops.same_pad(11, k, s, 1, pad)
+        y = torch.empty(2, ho, wo, 16, device="cuda")
+        am = torch.empty(2, ho, wo, 16, dtype=torch.int32, device="cuda")
+        L.check(lib.mcn_maxpool_fwd(0, xt.data_ptr(), 2, 9, 11, 16, k, k, s, s, pt, pl, ho, wo,
+                                    y.data_ptr(), am.data_ptr(), None))
+        torch.cuda.synchronize()
+        ref_idx = tf_ops.max_pool_argmax(torch.from_numpy(x), [k, k], [s, s], pad).numpy()
+        ref_val = tf_ops.max_pool(torch.from_numpy(x), [k, k], [s, s], pad).numpy()
+        assert np.array_equal(am.cpu().numpy().astype(np.int64), ref_idx)
+        assert np.array_equal(y.cpu().numpy(), ref_val)
