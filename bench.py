@@ -178,14 +178,17 @@ def profile_step(eng):
     torch.cuda.synchronize()
     esz = 2 if eng.plan.cdt == "bf16" else 4
     out = {}
+    detail = []
     for name, tag, args, e0, e1 in recs:
         ms = e0.elapsed_time(e1)
         byt, fl = launch_work(name, args, esz)
+        detail.append((kernel_class(name, tag), tag, ms, byt, fl))
         c = out.setdefault(kernel_class(name, tag), [0.0, 0.0, 0.0, 0])
         c[0] += ms
         c[1] += byt
         c[2] += fl
         c[3] += 1
+    profile_step.detail = detail
     return out
 
 
@@ -290,7 +293,10 @@ def main():
              for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
     if args.profile_json:
         os.makedirs(os.path.dirname(args.profile_json) or ".", exist_ok=True)
-        json.dump({"serialized_step_ms": total_ms, "graph_step_ms": ms, "classes": table},
+        json.dump({"serialized_step_ms": total_ms, "graph_step_ms": ms, "classes": table,
+                   "launches": [{"class": c, "tag": t, "us": m * 1e3, "GB/s": (b / 1e9) / (m * 1e-3) if m > 0 else 0,
+                                 "TFLOP/s": (f / 1e12) / (m * 1e-3) if m > 0 else 0}
+                                for c, t, m, b, f in profile_step.detail]},
                   open(args.profile_json, "w"), indent=1)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

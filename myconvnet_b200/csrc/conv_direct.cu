@@ -209,6 +209,54 @@ __global__ void dwconv_bwd_filter_kernel(mcn_conv_desc d, int mult, const T* __r
 }
 
 // ---------------------------------------------------------------- explicit im2col (bf16 out)
+// Row m of `col` is the receptive field of output pixel m laid out [kh][kw][Cin] and zero-padded
+// to kpad.  With unit dilation along W the kw*Cin elements of one filter row are CONTIGUOUS in
+// the NHWC input, so a thread builds 8 consecutive k (one 16-byte store) from at most two short
+// contiguous runs of the input; only image-border masking is needed.
+template <typename T>
+__global__ void im2col_rows_kernel(mcn_conv_desc d, const T* __restrict__ x,
+                                   __nv_bfloat16* __restrict__ col, int kpad) {
+  const int K = d.kh * d.kw * d.Cin;
+  const int RL = d.kw * d.Cin;        // run length of one filter row
+  const int WL = d.W * d.Cin;         // elements in one input row
+  const int groups = kpad / 8;
+  const long long total = (long long)d.N * d.Ho * d.Wo * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    const long long m = i / groups;
+    const int q = (int)(m % d.Wo);
+    long long rr = m / d.Wo;
+    const int p = (int)(rr % d.Ho);
+    const int n = (int)(rr / d.Ho);
+    const int h0 = p * d.sh - d.pad_t;
+    const int lin0 = (q * d.sw - d.pad_l) * d.Cin;
+    int k = g * 8;
+    int r = k / RL;
+    int rem = k - r * RL;
+    uint32_t pk[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float v = 0.f;
+      if (k < K) {
+        const int h = h0 + r * d.dh;
+        const int lin = lin0 + rem;
+        if (h >= 0 && h < d.H && lin >= 0 && lin < WL)
+          v = to_f32(x[((long long)n * d.H + h) * WL + lin]);
+      }
+      const uint32_t b = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v));
+      pk[e >> 1] |= (e & 1) ? (b << 16) : b;
+      ++k;
+      if (++rem == RL) {
+        rem = 0;
+        ++r;
+      }
+    }
+    *reinterpret_cast<uint4*>(col + m * kpad + g * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
+// general fallback (dilated along W)
 template <typename T>
 __global__ void im2col_kernel(mcn_conv_desc d, const T* __restrict__ x,
                               __nv_bfloat16* __restrict__ col, int kpad) {
@@ -344,10 +392,16 @@ extern "C" int mcn_im2col(const mcn_conv_desc* d, int dtype, const void* x, void
   MCN_REQUIRE(d && x && col && kpad >= d->kh * d->kw * d->Cin && kpad % 8 == 0,
               "im2col: bad argument (kpad must be >= kh*kw*Cin and a multiple of 8)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  long long total = (long long)d->N * d->Ho * d->Wo * kpad;
   MCN_DISPATCH_DTYPE(dtype, T, {
-    im2col_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(*d, static_cast<const T*>(x),
-                                                          static_cast<__nv_bfloat16*>(col), kpad);
+    if (d->dw == 1) {
+      long long total = (long long)d->N * d->Ho * d->Wo * (kpad / 8);
+      im2col_rows_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(
+          *d, static_cast<const T*>(x), static_cast<__nv_bfloat16*>(col), kpad);
+    } else {
+      long long total = (long long)d->N * d->Ho * d->Wo * kpad;
+      im2col_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(*d, static_cast<const T*>(x),
+                                                            static_cast<__nv_bfloat16*>(col), kpad);
+    }
   });
   return after_launch("im2col");
 }

@@ -99,6 +99,55 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ dy, const int32_t* __re
   }
 }
 
+// Vectorised backward: one thread per input pixel x 8-channel (16-byte) vector.
+template <typename T, int V>
+__global__ void maxpool_bwd_vec_kernel(const T* __restrict__ dy, const int32_t* __restrict__ argmax,
+                                       int N, int H, int W, int C, int kh, int kw, int sh, int sw,
+                                       int pad_t, int pad_l, int Ho, int Wo, T* __restrict__ dx) {
+  const int cv = C / V;
+  const long long total = (long long)N * H * W * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % cv) * V;
+    long long r = i / cv;
+    const int w = (int)(r % W);
+    r /= W;
+    const int h = (int)(r % H);
+    const int n = (int)(r / H);
+    const int self = (h * W + w) * C + c0;
+    int p_lo = (h + pad_t - kh + 1 + sh - 1);
+    p_lo = p_lo <= 0 ? 0 : p_lo / sh;
+    const int p_hi = min((h + pad_t) / sh, Ho - 1);
+    int q_lo = (w + pad_l - kw + 1 + sw - 1);
+    q_lo = q_lo <= 0 ? 0 : q_lo / sw;
+    const int q_hi = min((w + pad_l) / sw, Wo - 1);
+    float acc[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[e] = 0.f;
+    for (int p = p_lo; p <= p_hi; ++p)
+      for (int q = q_lo; q <= q_hi; ++q) {
+        const long long o = (((long long)n * Ho + p) * Wo + q) * C + c0;
+        Vec16<T> g = ld_vec(dy + o);
+        int idx[V];
+#pragma unroll
+        for (int e = 0; e < V; e += 4) {
+          int4 a = *reinterpret_cast<const int4*>(argmax + o + e);
+          idx[e] = a.x;
+          idx[e + 1] = a.y;
+          idx[e + 2] = a.z;
+          idx[e + 3] = a.w;
+        }
+#pragma unroll
+        for (int e = 0; e < V; ++e)
+          if (idx[e] == self + e) acc[e] += g.get(e);
+      }
+    Vec16<T> o;
+#pragma unroll
+    for (int e = 0; e < V; ++e) o.set(e, acc[e]);
+    st_vec(dx + (((long long)n * H + h) * W + w) * C + c0, o);
+  }
+}
+
 // Average pooling; SAME divides by the number of in-bounds elements.
 template <typename T>
 __global__ void avgpool_fwd_kernel(const T* __restrict__ x, int N, int H, int W, int C, int kh,
@@ -228,10 +277,18 @@ extern "C" int mcn_maxpool_bwd(int dtype, const void* dy, const int32_t* argmax,
   MCN_REQUIRE(dy && argmax && dx, "maxpool_bwd: null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MCN_DISPATCH_DTYPE(dtype, T, {
-    long long total = (long long)N * H * W * C;
-    maxpool_bwd_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(
-        static_cast<const T*>(dy), argmax, N, H, W, C, kh, kw, sh, sw, pad_t, pad_l, Ho, Wo,
-        static_cast<T*>(dx));
+    constexpr int V = Vec16<T>::N;
+    if (C % V == 0) {
+      long long total = (long long)N * H * W * (C / V);
+      maxpool_bwd_vec_kernel<T, V><<<grid_for(total, 256), 256, 0, st>>>(
+          static_cast<const T*>(dy), argmax, N, H, W, C, kh, kw, sh, sw, pad_t, pad_l, Ho, Wo,
+          static_cast<T*>(dx));
+    } else {
+      long long total = (long long)N * H * W * C;
+      maxpool_bwd_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(
+          static_cast<const T*>(dy), argmax, N, H, W, C, kh, kw, sh, sw, pad_t, pad_l, Ho, Wo,
+          static_cast<T*>(dx));
+    }
   });
   return after_launch("maxpool_bwd");
 }

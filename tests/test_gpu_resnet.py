@@ -70,7 +70,7 @@ def test_resnet50_layers_and_grads(have_reference_models, dtype, tol_act, tol_gr
     assert not gbad, "gradient mismatches: %s" % gbad[:8]
 
 
-@pytest.mark.parametrize("dtype,tol", [("f32", 1e-3), ("bf16", 3e-2)])
+@pytest.mark.parametrize("dtype,tol", [("f32", 5e-3), ("bf16", 3e-2)])
 def test_resnet50_fused_loss_curve(have_reference_models, dtype, tol):
     """Fused plan (BN+ReLU+residual, dense+cast) over several optimiser steps vs the oracle."""
     from oracle.step import OracleTrainer
