@@ -60,11 +60,14 @@ long long mcn_launch_count(void);
  *   w_ohwi : bf16 [kh*kw][Cout][Cin]   (fprop operand; produced by mcn_weight_prep)
  *   w_hwio : bf16 [kh*kw][Cin][Cout]   (dgrad operand; the reference's own layout)
  *   dw     : fp32 [kh*kw][Cin][Cout]   (wgrad ACCUMULATES into it: zero it first)
- * a_mode: 0 = tiled TMA boxes (spatial tiles), 1 = im2col TMA (exact 128-pixel tiles). */
+ * a_mode: 0 = tiled TMA boxes (spatial tiles), 1 = im2col TMA (exact 128-pixel tiles).
+ * accumulate != 0: the epilogue adds into the existing output (y += conv, dx += dgrad) — used for
+ * tensors with several consumers, whose gradient contributions sum (no separate add pass). */
 int mcn_conv2d_fprop_tc(const mcn_conv_desc* d, const void* x, const void* w_ohwi,
-                        const float* bias, void* y, int y_dtype, int a_mode, void* stream);
+                        const float* bias, void* y, int y_dtype, int a_mode, int accumulate,
+                        void* stream);
 int mcn_conv2d_dgrad_tc(const mcn_conv_desc* d, const void* dy, const void* w_hwio, void* dx,
-                        int dx_dtype, int a_mode, void* stream);
+                        int dx_dtype, int a_mode, int accumulate, void* stream);
 int mcn_conv2d_wgrad_tc(const mcn_conv_desc* d, const void* x, const void* dy, float* dw,
                         int a_mode, void* stream);
 

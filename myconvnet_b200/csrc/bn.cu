@@ -36,49 +36,97 @@ bool plan(long long rows, int C, ChanLaunch* L, int blocks_per_sm) {
   return true;
 }
 
-// ---------------------------------------------------------------- forward statistics
+// ---------------------------------------------------------------- reductions over rows
+// Grid = (channel slabs, row chunks).  A slab is up to 16 channel vectors (256 B of a row), so a
+// warp reads two 256-byte row segments per load; a block owns one slab for a contiguous chunk of
+// rows.  Only the blocks of the same slab ever add into the same channel's accumulator, which
+// keeps the number of contended global atomics per address at the row-chunk count (tens), not the
+// whole grid (hundreds) — that contention was the fixed cost of the small late-layer tensors.
+struct SlabLaunch {
+  int cv, slab_v, rowlanes;
+  dim3 grid;
+};
+
 template <typename T>
-__global__ void __launch_bounds__(512)
-bn_stats_kernel(const T* __restrict__ x, long long nvec, int cv, int C, double* __restrict__ sums) {
+bool plan_slab(long long rows, int C, SlabLaunch* L, int blocks_total) {
   constexpr int V = Vec16<T>::N;
-  extern __shared__ float sh[];  // [2*C]
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+  if (C % V != 0) return false;
+  L->cv = C / V;
+  L->slab_v = std::min(L->cv, 16);
+  L->rowlanes = 256 / L->slab_v;
+  int slabs = (L->cv + L->slab_v - 1) / L->slab_v;
+  long long per_block_rows = (long long)L->rowlanes * 8;   // >= 8 rows per thread
+  long long chunks = std::max<long long>(1, std::min<long long>((rows + per_block_rows - 1) / per_block_rows,
+                                                                std::max(1, blocks_total / slabs)));
+  chunks = std::min<long long>(chunks, 65535);
+  L->grid = dim3((unsigned)slabs, (unsigned)chunks);
+  return true;
+}
+
+// Block-level finish shared by the reduction kernels: sh holds [2][rowlanes][slab_v*V] partials.
+template <int V, typename TAcc>
+__device__ __forceinline__ void slab_finish(float* sh, int slab_v, int rowlanes, int slab, int C,
+                                            TAcc* out1, TAcc* out2) {
   __syncthreads();
-  const int cvec = threadIdx.x % cv;
+  const int width = slab_v * V;
+  for (int t = threadIdx.x; t < 2 * width; t += blockDim.x) {
+    const int which = t / width, e = t - which * width;
+    const float* src = sh + (size_t)which * rowlanes * width + e;
+    float acc = 0.f;
+    for (int r = 0; r < rowlanes; ++r) acc += src[(size_t)r * width];
+    const int c = slab * width + e;
+    if (c < C) atomicAdd((which ? out2 : out1) + c, (TAcc)acc);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_stats_kernel(const T* __restrict__ x, long long rows, int C, int slab_v, int rowlanes,
+                double* __restrict__ sums) {
+  constexpr int V = Vec16<T>::N;
+  extern __shared__ float sh[];
+  const int sv = threadIdx.x % slab_v, rl = threadIdx.x / slab_v;
+  const int vec = blockIdx.x * slab_v + sv;
+  const bool active = rl < rowlanes && vec * V < C;
+  const long long r0 = rows * blockIdx.y / gridDim.y, r1 = rows * (blockIdx.y + 1) / gridDim.y;
   float s1[V], s2[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) s1[i] = s2[i] = 0.f;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  for (; v + (kUnroll - 1) * stride < nvec; v += kUnroll * stride) {
-    Vec16<T> a[kUnroll];
+  if (active) {
+    const T* base = x + (long long)vec * V;
+    long long r = r0 + rl;
+    for (; r + (kUnroll - 1) * rowlanes < r1; r += (long long)kUnroll * rowlanes) {
+      Vec16<T> a[kUnroll];
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) a[u] = ld_vec_stream(x + (v + u * stride) * V);
+      for (int u = 0; u < kUnroll; ++u) a[u] = ld_vec_stream(base + (r + (long long)u * rowlanes) * C);
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u)
+      for (int u = 0; u < kUnroll; ++u)
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          float f = a[u].get(i);
+          s1[i] += f;
+          s2[i] = fmaf(f, f, s2[i]);
+        }
+    }
+    for (; r < r1; r += rowlanes) {
+      Vec16<T> a = ld_vec_stream(base + r * C);
 #pragma unroll
       for (int i = 0; i < V; ++i) {
-        float f = a[u].get(i);
+        float f = a.get(i);
         s1[i] += f;
         s2[i] = fmaf(f, f, s2[i]);
       }
-  }
-  for (; v < nvec; v += stride) {
-    Vec16<T> a = ld_vec_stream(x + v * V);
-#pragma unroll
-    for (int i = 0; i < V; ++i) {
-      float f = a.get(i);
-      s1[i] += f;
-      s2[i] = fmaf(f, f, s2[i]);
     }
   }
+  if (rl < rowlanes) {
+    const int width = slab_v * V;
 #pragma unroll
-  for (int i = 0; i < V; ++i) {
-    atomicAdd(&sh[cvec * V + i], s1[i]);
-    atomicAdd(&sh[C + cvec * V + i], s2[i]);
+    for (int i = 0; i < V; ++i) {
+      sh[(size_t)rl * width + sv * V + i] = s1[i];
+      sh[(size_t)(rowlanes + rl) * width + sv * V + i] = s2[i];
+    }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&sums[i], (double)sh[i]);
+  slab_finish<V, double>(sh, slab_v, rowlanes, blockIdx.x, C, sums, sums + C);
 }
 
 // scalar fallback (C not a multiple of the vector width)
@@ -195,66 +243,69 @@ __device__ __forceinline__ float dz_of(float dy, float xv, float yv, bool have_y
 }
 
 template <typename T>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
-                     long long nvec, int cv, int C, const float* __restrict__ mean,
-                     const float* __restrict__ invstd, const float* __restrict__ gamma,
-                     const float* __restrict__ beta, int act, float alpha,
-                     float* __restrict__ sum_dz, float* __restrict__ sum_dz_xhat) {
+                     long long rows, int C, int slab_v, int rowlanes,
+                     const float* __restrict__ mean, const float* __restrict__ invstd,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, int act,
+                     float alpha, float* __restrict__ sum_dz, float* __restrict__ sum_dz_xhat) {
   constexpr int V = Vec16<T>::N;
   extern __shared__ float sh[];
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
-  __syncthreads();
-  const int cvec = threadIdx.x % cv;
-  const int c0 = cvec * V;
-  float mu[V], is[V], sc[V], sf[V], s1[V], s2[V];
+  const int sv = threadIdx.x % slab_v, rl = threadIdx.x / slab_v;
+  const int vec = blockIdx.x * slab_v + sv;
+  const bool active = rl < rowlanes && vec * V < C;
+  const long long r0 = rows * blockIdx.y / gridDim.y, r1 = rows * (blockIdx.y + 1) / gridDim.y;
+  float s1[V], s2[V];
 #pragma unroll
-  for (int i = 0; i < V; ++i) {
-    mu[i] = mean[c0 + i];
-    is[i] = invstd[c0 + i];
-    sc[i] = (gamma ? gamma[c0 + i] : 1.f) * is[i];
-    sf[i] = (beta ? beta[c0 + i] : 0.f) - mu[i] * sc[i];
-    s1[i] = s2[i] = 0.f;
-  }
-  const bool have_y = (y != nullptr);
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
-       v += 2 * stride) {
-    Vec16<T> g[2], a[2], o[2];
+  for (int i = 0; i < V; ++i) s1[i] = s2[i] = 0.f;
+  if (active) {
+    const int c0 = vec * V;
+    float mu[V], is[V], sc[V], sf[V];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      long long vv = v + u * stride;
-      if (vv < nvec) {
-        g[u] = ld_vec_stream(dy + vv * V);
-        a[u] = ld_vec_stream(x + vv * V);
-        if (have_y) o[u] = ld_vec_stream(y + vv * V);
-      }
+    for (int i = 0; i < V; ++i) {
+      mu[i] = mean[c0 + i];
+      is[i] = invstd[c0 + i];
+      sc[i] = (gamma ? gamma[c0 + i] : 1.f) * is[i];
+      sf[i] = (beta ? beta[c0 + i] : 0.f) - mu[i] * sc[i];
     }
+    const bool have_y = (y != nullptr);
+    for (long long r = r0 + rl; r < r1; r += 2LL * rowlanes) {
+      Vec16<T> g[2], a[2], o[2];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      long long vv = v + u * stride;
-      if (vv < nvec) {
+      for (int u = 0; u < 2; ++u) {
+        long long rr = r + (long long)u * rowlanes;
+        if (rr < r1) {
+          long long off = rr * C + c0;
+          g[u] = ld_vec_stream(dy + off);
+          a[u] = ld_vec_stream(x + off);
+          if (have_y) o[u] = ld_vec_stream(y + off);
+        }
+      }
 #pragma unroll
-        for (int i = 0; i < V; ++i) {
-          float xv = a[u].get(i);
-          float dz = dz_of<T>(g[u].get(i), xv, have_y ? o[u].get(i) : 0.f, have_y, sc[i], sf[i],
-                              act, alpha);
-          s1[i] += dz;
-          s2[i] = fmaf(dz, (xv - mu[i]) * is[i], s2[i]);
+      for (int u = 0; u < 2; ++u) {
+        long long rr = r + (long long)u * rowlanes;
+        if (rr < r1) {
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            float xv = a[u].get(i);
+            float dz = dz_of<T>(g[u].get(i), xv, have_y ? o[u].get(i) : 0.f, have_y, sc[i], sf[i],
+                                act, alpha);
+            s1[i] += dz;
+            s2[i] = fmaf(dz, (xv - mu[i]) * is[i], s2[i]);
+          }
         }
       }
     }
   }
+  if (rl < rowlanes) {
+    const int width = slab_v * V;
 #pragma unroll
-  for (int i = 0; i < V; ++i) {
-    atomicAdd(&sh[c0 + i], s1[i]);
-    atomicAdd(&sh[C + c0 + i], s2[i]);
+    for (int i = 0; i < V; ++i) {
+      sh[(size_t)rl * width + sv * V + i] = s1[i];
+      sh[(size_t)(rowlanes + rl) * width + sv * V + i] = s2[i];
+    }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    atomicAdd(&sum_dz[i], sh[i]);
-    atomicAdd(&sum_dz_xhat[i], sh[C + i]);
-  }
+  slab_finish<V, float>(sh, slab_v, rowlanes, blockIdx.x, C, sum_dz, sum_dz_xhat);
 }
 
 template <typename T>
@@ -364,10 +415,11 @@ extern "C" int mcn_bn_stats(int dtype, const void* x, long long rows, int C, dou
   MCN_REQUIRE(x && sums && rows > 0 && C > 0, "bn_stats: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MCN_DISPATCH_DTYPE(dtype, T, {
-    ChanLaunch L;
-    if (plan<T>(rows, C, &L, 4)) {
-      bn_stats_kernel<T><<<L.grid, L.block, 2 * C * sizeof(float), st>>>(
-          static_cast<const T*>(x), rows * L.cv, L.cv, C, sums);
+    SlabLaunch L;
+    if (plan_slab<T>(rows, C, &L, 6 * num_sms())) {
+      size_t smem = 2 * (size_t)L.rowlanes * L.slab_v * Vec16<T>::N * sizeof(float);
+      bn_stats_kernel<T><<<L.grid, 256, smem, st>>>(static_cast<const T*>(x), rows, C, L.slab_v,
+                                                    L.rowlanes, sums);
     } else {
       dim3 grid((C + 127) / 128, (unsigned)std::min<long long>(rows, 4LL * num_sms()));
       bn_stats_scalar_kernel<T><<<grid, 128, 0, st>>>(static_cast<const T*>(x), rows, C, sums);
@@ -430,11 +482,12 @@ extern "C" int mcn_bn_bwd_reduce(int dtype, const void* dy, const void* x, const
   MCN_REQUIRE(dy && x && mean && invstd && sum_dz && sum_dz_xhat, "bn_bwd_reduce: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MCN_DISPATCH_DTYPE(dtype, T, {
-    ChanLaunch L;
-    if (plan<T>(rows, C, &L, 4)) {
-      bn_bwd_reduce_kernel<T><<<L.grid, L.block, 2 * C * sizeof(float), st>>>(
-          static_cast<const T*>(dy), static_cast<const T*>(x), static_cast<const T*>(y),
-          rows * L.cv, L.cv, C, mean, invstd, gamma, beta, act, act_alpha, sum_dz, sum_dz_xhat);
+    SlabLaunch L;
+    if (plan_slab<T>(rows, C, &L, 6 * num_sms())) {
+      size_t smem = 2 * (size_t)L.rowlanes * L.slab_v * Vec16<T>::N * sizeof(float);
+      bn_bwd_reduce_kernel<T><<<L.grid, 256, smem, st>>>(
+          static_cast<const T*>(dy), static_cast<const T*>(x), static_cast<const T*>(y), rows, C,
+          L.slab_v, L.rowlanes, mean, invstd, gamma, beta, act, act_alpha, sum_dz, sum_dz_xhat);
     } else {
       dim3 grid((C + 127) / 128, (unsigned)std::min<long long>(rows, 4LL * num_sms()));
       bn_bwd_reduce_scalar_kernel<T><<<grid, 128, 0, st>>>(

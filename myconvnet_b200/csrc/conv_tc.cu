@@ -107,7 +107,7 @@ struct GemmConvArgs {
   long long out_sn, out_sh, out_sw;  // element strides of the output pixel grid
   void* out;
   const float* bias;
-  int out_f32, vec_ok;
+  int out_f32, vec_ok, accumulate;
   TapTab tab;
 };
 
@@ -204,6 +204,8 @@ gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
     }
   } else {
     // ---------------- epilogue: TMEM -> registers -> global ----------------
+    // Each thread owns one output pixel (row) and walks its channels 64 at a time: 64 bf16 = one
+    // full 128-byte line written with four 32-byte stores (fp32 output: eight).
     ptx::mbar_wait(tmem_full, 0);
     ptx::tc_fence_after();
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
@@ -211,45 +213,69 @@ gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
     int n, p, q;
     const bool valid = row_coords(args.g, tile, row, n, p, q);
     const long long off = valid ? (n * args.out_sn + p * args.out_sh + q * args.out_sw) : 0;
-    for (int c0 = 0; c0 < args.block_n; c0 += 32) {
-      uint32_t r[32];
-      ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c0, r);
+    for (int c0 = 0; c0 < args.block_n; c0 += 64) {
+      uint32_t r[64];
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c0;
+      ptx::tmem_ld_32x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+      ptx::tmem_ld_32x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
       ptx::tmem_ld_wait();
       const int col0 = n_t * args.block_n + c0;
       if (!valid || col0 >= args.n_total) continue;
+      const bool full = args.vec_ok && (col0 + 64 <= args.n_total);
       if (args.bias != nullptr) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (col0 + j < args.n_total)
+        for (int j = 0; j < 64; ++j)
+          if (full || col0 + j < args.n_total)
             r[j] = __float_as_uint(__uint_as_float(r[j]) + args.bias[col0 + j]);
       }
       if (args.out_f32) {
         float* o = reinterpret_cast<float*>(args.out) + off + col0;
-        if (args.vec_ok && col0 + 32 <= args.n_total) {
+        if (full) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<uint4*>(o + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+          for (int j = 0; j < 64; j += 8) {
+            uint32_t v[8];
+            if (args.accumulate) {
+              ptx::ld_global_v8(o + j, v);
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(r[j + e]));
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = r[j + e];
+            }
+            ptx::st_global_v8(o + j, v);
+          }
         } else {
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < args.n_total) o[j] = __uint_as_float(r[j]);
+          for (int j = 0; j < 64; ++j)
+            if (col0 + j < args.n_total)
+              o[j] = __uint_as_float(r[j]) + (args.accumulate ? o[j] : 0.f);
         }
       } else {
         __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(args.out) + off + col0;
-        if (args.vec_ok && col0 + 32 <= args.n_total) {
+        if (full) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint32_t pk[4];
+          for (int j = 0; j < 64; j += 16) {
+            uint32_t v[8];
+            if (args.accumulate) ptx::ld_global_v8(o + j, v);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(r[j + 2 * e]),
-                                                       __uint_as_float(r[j + 2 * e + 1]));
-              pk[e] = *reinterpret_cast<uint32_t*>(&h);
+            for (int e = 0; e < 8; ++e) {
+              float lo = __uint_as_float(r[j + 2 * e]), hi = __uint_as_float(r[j + 2 * e + 1]);
+              if (args.accumulate) {
+                lo += __uint_as_float(v[e] << 16);
+                hi += __uint_as_float(v[e] & 0xFFFF0000u);
+              }
+              __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+              v[e] = *reinterpret_cast<uint32_t*>(&h);
             }
-            *reinterpret_cast<uint4*>(o + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            ptx::st_global_v8(o + j, v);
           }
         } else {
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < args.n_total) o[j] = __float2bfloat16_rn(__uint_as_float(r[j]));
+          for (int j = 0; j < 64; ++j)
+            if (col0 + j < args.n_total) {
+              float f = __uint_as_float(r[j]);
+              if (args.accumulate) f += __bfloat162float(o[j]);
+              o[j] = __float2bfloat16_rn(f);
+            }
         }
       }
     }
@@ -395,9 +421,16 @@ wgrad_kernel(const __grid_constant__ WgradArgs args) {
       if (ci >= args.cin) continue;
       const int co0 = ni * args.block_n + c0;
       float* o = args.dw + (static_cast<long long>(tap) * args.cin + ci) * args.cout + co0;
+      if ((args.cout & 3) == 0 && co0 + 32 <= args.cout) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (co0 + j < args.cout) atomicAdd(o + j, __uint_as_float(r[j]));
+        for (int j = 0; j < 32; j += 4)
+          ptx::red_add_v4(o + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                          __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (co0 + j < args.cout) atomicAdd(o + j, __uint_as_float(r[j]));
+      }
     }
   }
 
@@ -592,7 +625,7 @@ using namespace mcn;
 
 extern "C" int mcn_conv2d_fprop_tc(const mcn_conv_desc* d, const void* x, const void* w_ohwi,
                                    const float* bias, void* y, int y_dtype, int a_mode,
-                                   void* stream) {
+                                   int accumulate, void* stream) {
   MCN_REQUIRE(d && x && w_ohwi && y, "fprop_tc: null argument");
   MCN_REQUIRE(d->Cin % 8 == 0, "fprop_tc: Cin=%d must be a multiple of 8 (16-byte TMA rows)", d->Cin);
   MCN_REQUIRE(d->kh * d->kw <= kMaxTaps, "fprop_tc: too many taps");
@@ -666,7 +699,8 @@ extern "C" int mcn_conv2d_fprop_tc(const mcn_conv_desc* d, const void* x, const 
   a.out = y;
   a.out_f32 = (y_dtype == MCN_F32);
   a.bias = bias;
-  a.vec_ok = (d->Cout % 8 == 0);
+  a.vec_ok = (d->Cout % 16 == 0) && (reinterpret_cast<uintptr_t>(y) % 32 == 0);
+  a.accumulate = accumulate;
   for (int r = 0; r < d->kh; ++r)
     for (int s = 0; s < d->kw; ++s) {
       int t = r * d->kw + s;
@@ -690,7 +724,8 @@ extern "C" int mcn_conv2d_fprop_tc(const mcn_conv_desc* d, const void* x, const 
 // each phase is a stride-1 correlation of dy with the subset of taps of matching parity, written
 // to a strided view of dx — one launch per phase, no zero-insertion, no wasted MACs.
 static int dgrad_phase(const mcn_conv_desc* d, const void* dy, const void* w_hwio, void* dx,
-                       int dx_dtype, int a_mode, int ph, int pw, bool* empty, cudaStream_t st) {
+                       int dx_dtype, int a_mode, int accumulate, int ph, int pw, bool* empty,
+                       cudaStream_t st) {
   GemmConvArgs a;
   std::memset(&a, 0, sizeof(a));
   int rc;
@@ -770,7 +805,8 @@ static int dgrad_phase(const mcn_conv_desc* d, const void* dy, const void* w_hwi
   a.out = static_cast<uint8_t*>(dx) + ((size_t)ph * d->W + pw) * d->Cin * esz;
   a.out_f32 = (dx_dtype == MCN_F32);
   a.bias = nullptr;
-  a.vec_ok = (d->Cin % 8 == 0);
+  a.vec_ok = (d->Cin % 16 == 0) && (reinterpret_cast<uintptr_t>(a.out) % 32 == 0);
+  a.accumulate = accumulate;
   for (int t = 0; t < nt; ++t) {
     a.tab.brow[t] = tap_id[t] * d->Cin;
     a.tab.map[t] = 0;
@@ -786,7 +822,8 @@ static int dgrad_phase(const mcn_conv_desc* d, const void* dy, const void* w_hwi
 }
 
 extern "C" int mcn_conv2d_dgrad_tc(const mcn_conv_desc* d, const void* dy, const void* w_hwio,
-                                   void* dx, int dx_dtype, int a_mode, void* stream) {
+                                   void* dx, int dx_dtype, int a_mode, int accumulate,
+                                   void* stream) {
   MCN_REQUIRE(d && dy && w_hwio && dx, "dgrad_tc: null argument");
   MCN_REQUIRE(d->Cout % 8 == 0, "dgrad_tc: Cout=%d must be a multiple of 8", d->Cout);
   MCN_REQUIRE(d->kh * d->kw <= kMaxTaps, "dgrad_tc: too many taps");
@@ -803,7 +840,7 @@ extern "C" int mcn_conv2d_dgrad_tc(const mcn_conv_desc* d, const void* dy, const
                 (((pw + d->pad_l - s * d->dw) % d->sw) == 0);
       any_empty = !hit;
     }
-  if (any_empty) {
+  if (any_empty && !accumulate) {
     if (cudaMemsetAsync(dx, 0, (size_t)d->N * d->H * d->W * d->Cin * esz, st) != cudaSuccess) {
       set_error("dgrad_tc: memset failed");
       return MCN_ECUDA;
@@ -812,7 +849,7 @@ extern "C" int mcn_conv2d_dgrad_tc(const mcn_conv_desc* d, const void* dy, const
   for (int ph = 0; ph < d->sh; ++ph)
     for (int pw = 0; pw < d->sw; ++pw) {
       bool empty = false;
-      int rc = dgrad_phase(d, dy, w_hwio, dx, dx_dtype, a_mode, ph, pw, &empty, st);
+      int rc = dgrad_phase(d, dy, w_hwio, dx, dx_dtype, a_mode, accumulate, ph, pw, &empty, st);
       if (rc) return rc;
     }
   return MCN_OK;

@@ -29,8 +29,8 @@ _T = {"p": ctypes.c_void_p, "i": ctypes.c_int, "l": ctypes.c_longlong, "f": ctyp
 
 # name -> argument codes WITHOUT the trailing stream (every entry ends with a void* stream)
 SIGNATURES = {
-    "mcn_conv2d_fprop_tc": "Dppppii",
-    "mcn_conv2d_dgrad_tc": "Dpppii",
+    "mcn_conv2d_fprop_tc": "Dppppiii",
+    "mcn_conv2d_dgrad_tc": "Dpppiii",
     "mcn_conv2d_wgrad_tc": "Dpppi",
     "mcn_conv2d_fprop_direct": "Dipippp",
     "mcn_conv2d_dgrad_direct": "Dipipp",

@@ -400,7 +400,7 @@ class Plan(object):
         pb = self.pvar(b) if b is not None else NULL
         if route == "tc":
             self.L("f", "mcn_conv2d_fprop_tc", d, self.tbuf[x], self.pbf16t(w), pb, py, self.ccode,
-                   self.conv_mode, tag=node.scope)
+                   self.conv_mode, 0, tag=node.scope)
         elif route == "im2col":
             kpad = node.attrs["kpad"]
             m = d.N * d.Ho * d.Wo
@@ -411,7 +411,7 @@ class Plan(object):
             node.attrs["gemm_desc"] = gd
             self.L("f", "mcn_im2col", d, DT_CODE[x.dtype], self.tbuf[x], Ptr(col), kpad,
                    tag=node.scope + "/im2col")
-            self.L("f", "mcn_conv2d_fprop_tc", gd, Ptr(col), self.pbf16t(w), pb, py, self.ccode, 0,
+            self.L("f", "mcn_conv2d_fprop_tc", gd, Ptr(col), self.pbf16t(w), pb, py, self.ccode, 0, 0,
                    tag=node.scope)
         else:
             wdt, pw = self._direct_weight(w)
@@ -453,7 +453,7 @@ class Plan(object):
         if node.attrs["route"] == "tc":
             # dgrad wants W_conv[tap][Cin_conv=co][Cout_conv=ci] = stored[tap][ci][co]^T = bf16_t copy
             self.L("f", "mcn_conv2d_dgrad_tc", d, self.tbuf[x], self.pbf16t(w), py, self.ccode,
-                   self.conv_mode, tag=node.scope)
+                   self.conv_mode, 0, tag=node.scope)
         else:
             raise NotImplementedError("transposed conv needs channel counts that are multiples of 8 "
                                       "on the tensor-core path; direct route is lowered in _f_tconv_direct")
@@ -477,7 +477,7 @@ class Plan(object):
         pb = self.pvar(b) if b is not None else NULL
         if node.attrs["route"] == "tc":
             self.L("f", "mcn_conv2d_fprop_tc", d, self.tbuf[x], self.pbf16t(w), pb, py,
-                   DT_CODE[y.dtype], 0, tag=node.scope)
+                   DT_CODE[y.dtype], 0, 0, tag=node.scope)
         else:
             self.L("f", "mcn_conv2d_fprop_direct", d, self.ccode, self.tbuf[x], 0, self.pvar(w), pb,
                    py, tag=node.scope)
@@ -660,9 +660,10 @@ class Plan(object):
         if h is not None:
             self.tfree(h)
 
-    def contribute(self, t, nbytes, emit, dtype=None):
-        """Route a gradient contribution for tensor t: the first one writes the gradient buffer,
-        later ones go through a temporary and are accumulated."""
+    def contribute(self, t, nbytes, emit, dtype=None, emit_acc=None):
+        """Route a gradient contribution for tensor t: the first one writes the gradient buffer;
+        later ones are added in the producing kernel's epilogue when it can (emit_acc), else go
+        through a temporary and a separate accumulate pass."""
         if not self._tensor_needs_grad(t):
             return
         dt = dtype or t.dtype
@@ -670,6 +671,8 @@ class Plan(object):
             p, h = self.talloc(nbytes)
             self.g[t] = (p, h)
             emit(p)
+        elif emit_acc is not None:
+            emit_acc(self.g[t][0])
         else:
             p, h = self.talloc(nbytes)
             emit(p)
@@ -708,8 +711,10 @@ class Plan(object):
                 self.L("b", "mcn_conv2d_wgrad_tc", d, self.tbuf[x], gyb, self.pgrad(w), 0,
                        tag=node.scope + "/wgrad")
             self.contribute(x, x.size * 2,
-                            lambda p: self.L("b", "mcn_conv2d_dgrad_tc", d, gyb, self.pbf16(w), p, 1, 0,
-                                             tag=node.scope + "/dgrad"))
+                            lambda p: self.L("b", "mcn_conv2d_dgrad_tc", d, gyb, self.pbf16(w), p, 1, 0, 0,
+                                             tag=node.scope + "/dgrad"),
+                            emit_acc=lambda p: self.L("b", "mcn_conv2d_dgrad_tc", d, gyb, self.pbf16(w), p,
+                                                      1, 0, 1, tag=node.scope + "/dgrad+"))
             if h is not None:
                 self.tfree(h)
         else:
@@ -734,7 +739,9 @@ class Plan(object):
                        tag=node.scope + "/wgrad")
             self.contribute(x, x.size * 2,
                             lambda p: self.L("b", "mcn_conv2d_dgrad_tc", d, gy, self.pbf16(w), p, 1,
-                                             self.conv_mode, tag=node.scope + "/dgrad"))
+                                             self.conv_mode, 0, tag=node.scope + "/dgrad"),
+                            emit_acc=lambda p: self.L("b", "mcn_conv2d_dgrad_tc", d, gy, self.pbf16(w), p, 1,
+                                                      self.conv_mode, 1, tag=node.scope + "/dgrad+"))
         elif route == "im2col":
             if w.trainable:
                 self.L("b", "mcn_conv2d_wgrad_tc", node.attrs["gemm_desc"], Ptr(node.attrs["col"]), gy,
@@ -782,7 +789,9 @@ class Plan(object):
         # fprop of the underlying conv needs W_conv as [tap][Cout_conv=ci][Cin_conv=co] = stored layout
         self.contribute(x, x.size * 2,
                         lambda p: self.L("b", "mcn_conv2d_fprop_tc", d, gy, self.pbf16(w), NULL, p, 1,
-                                         self.conv_mode, tag=node.scope + "/dgrad"))
+                                         self.conv_mode, 0, tag=node.scope + "/dgrad"),
+                        emit_acc=lambda p: self.L("b", "mcn_conv2d_fprop_tc", d, gy, self.pbf16(w), NULL, p,
+                                                  1, self.conv_mode, 1, tag=node.scope + "/dgrad+"))
 
     def _b_bn(self, node, gy):
         x = node.inputs[0]

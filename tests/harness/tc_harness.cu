@@ -146,8 +146,8 @@ int main(int argc, char** argv) {
   auto run = [&]() -> int {
     if (c.op == 0)
       return mcn_conv2d_fprop_tc(&d, dx_, dw2, c.bias ? dbias : nullptr, dout,
-                                 c.out_f32 ? MCN_F32 : MCN_BF16, c.a_mode, 0);
-    if (c.op == 1) return mcn_conv2d_dgrad_tc(&d, dy_, dw1, dout, MCN_BF16, c.a_mode, 0);
+                                 c.out_f32 ? MCN_F32 : MCN_BF16, c.a_mode, 0, 0);
+    if (c.op == 1) return mcn_conv2d_dgrad_tc(&d, dy_, dw1, dout, MCN_BF16, c.a_mode, 0, 0);
     return mcn_conv2d_wgrad_tc(&d, dx_, dy_, (float*)dout, c.a_mode, 0);
   };
   int rc = run();

@@ -116,19 +116,28 @@ def test_conv_tensor_core(L, case, mode):
     w_ohwi = torch.empty(k * k, co, ci, device="cuda", dtype=torch.bfloat16)
     L.check(lib.mcn_weight_prep(wd.data_ptr(), k * k, ci, co, w_hwio.data_ptr(), w_ohwi.data_ptr(), None))
     y = torch.empty(n, ho, wo, co, device="cuda", dtype=torch.bfloat16)
-    L.check(lib.mcn_conv2d_fprop_tc(d, xd.data_ptr(), w_ohwi.data_ptr(), None, y.data_ptr(), 1, mode, None))
+    L.check(lib.mcn_conv2d_fprop_tc(d, xd.data_ptr(), w_ohwi.data_ptr(), None, y.data_ptr(), 1, mode, 0, None))
     dx = torch.full((n, h, w, ci), 7.0, device="cuda", dtype=torch.bfloat16)
-    L.check(lib.mcn_conv2d_dgrad_tc(d, dyd.data_ptr(), w_hwio.data_ptr(), dx.data_ptr(), 1, mode, None))
+    L.check(lib.mcn_conv2d_dgrad_tc(d, dyd.data_ptr(), w_hwio.data_ptr(), dx.data_ptr(), 1, mode, 0, None))
+    # accumulate-in-epilogue variants: out += op(.)
+    base = torch.tensor(r(rng.standard_normal((n, h, w, ci)).astype(np.float32)))
+    dx2 = base.cuda().bfloat16()
+    L.check(lib.mcn_conv2d_dgrad_tc(d, dyd.data_ptr(), w_hwio.data_ptr(), dx2.data_ptr(), 1, mode, 1, None))
+    ybase = torch.tensor(r(rng.standard_normal((n, ho, wo, co)).astype(np.float32)))
+    y2 = ybase.cuda().bfloat16()
+    L.check(lib.mcn_conv2d_fprop_tc(d, xd.data_ptr(), w_ohwi.data_ptr(), None, y2.data_ptr(), 1, mode, 1, None))
     dw = torch.zeros(k, k, ci, co, device="cuda")
     L.check(lib.mcn_conv2d_wgrad_tc(d, xd.data_ptr(), dyd.data_ptr(), dw.data_ptr(), mode, None))
     torch.cuda.synchronize()
     assert rel_l2(y.float().cpu(), yref.detach()) < 6e-3
     assert rel_l2(dx.float().cpu(), xt.grad) < 6e-3
     assert rel_l2(dw.cpu(), wtt.grad) < 1e-4
+    assert rel_l2(dx2.float().cpu(), xt.grad + base) < 6e-3
+    assert rel_l2(y2.float().cpu(), yref.detach() + ybase) < 6e-3
 
 
 @pytest.mark.parametrize("code", [0, 1])
-@pytest.mark.parametrize("C", [64, 24, 20])
+@pytest.mark.parametrize("C", [64, 24, 20, 320])
 @pytest.mark.parametrize("variant", ["plain", "relu", "relu_res", "swish", "res_noact"])
 def test_batch_norm(L, code, C, variant):
     lib = L.load()
