@@ -22,13 +22,14 @@ struct ChanLaunch {
 };
 
 template <typename T>
-bool plan(long long rows, int C, ChanLaunch* L, int blocks_per_sm) {
+bool plan(long long rows, int C, ChanLaunch* L, int blocks_per_sm, int max_block = 512) {
   constexpr int V = Vec16<T>::N;
   if (C % V != 0) return false;
   int cv = C / V;
   if (cv > 512) return false;
+  if (cv > max_block) max_block = 512;
   L->cv = cv;
-  L->block = (512 / cv) * cv;
+  L->block = (max_block / cv) * cv;
   long long nvec = rows * cv;
   long long want = (nvec + (long long)L->block * kUnroll - 1) / ((long long)L->block * kUnroll);
   long long cap = (long long)num_sms() * blocks_per_sm;
@@ -243,7 +244,7 @@ __device__ __forceinline__ float dz_of(float dy, float xv, float yv, bool have_y
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
                      long long rows, int C, int slab_v, int rowlanes,
                      const float* __restrict__ mean, const float* __restrict__ invstd,
@@ -260,13 +261,11 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T*
   for (int i = 0; i < V; ++i) s1[i] = s2[i] = 0.f;
   if (active) {
     const int c0 = vec * V;
-    float mu[V], is[V], sc[V], sf[V];
+    float sc[V], sf[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-      mu[i] = mean[c0 + i];
-      is[i] = invstd[c0 + i];
-      sc[i] = (gamma ? gamma[c0 + i] : 1.f) * is[i];
-      sf[i] = (beta ? beta[c0 + i] : 0.f) - mu[i] * sc[i];
+      sc[i] = (gamma ? gamma[c0 + i] : 1.f) * invstd[c0 + i];
+      sf[i] = (beta ? beta[c0 + i] : 0.f) - mean[c0 + i] * sc[i];
     }
     const bool have_y = (y != nullptr);
     for (long long r = r0 + rl; r < r1; r += 2LL * rowlanes) {
@@ -291,11 +290,14 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T*
             float dz = dz_of<T>(g[u].get(i), xv, have_y ? o[u].get(i) : 0.f, have_y, sc[i], sf[i],
                                 act, alpha);
             s1[i] += dz;
-            s2[i] = fmaf(dz, (xv - mu[i]) * is[i], s2[i]);
+            s2[i] = fmaf(dz, xv, s2[i]);          // sum dz*x; turned into sum dz*xhat below
           }
         }
       }
     }
+    // sum dz*xhat = invstd * (sum dz*x - mean * sum dz)
+#pragma unroll
+    for (int i = 0; i < V; ++i) s2[i] = invstd[c0 + i] * (s2[i] - mean[c0 + i] * s1[i]);
   }
   if (rl < rowlanes) {
     const int width = slab_v * V;
@@ -318,15 +320,16 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
                     float inv_count, T* __restrict__ dx, T* __restrict__ d_residual) {
   constexpr int V = Vec16<T>::N;
   const int c0 = (threadIdx.x % cv) * V;
-  float mu[V], is[V], sc[V], sf[V], k1[V], k2[V];
+  // dx = sc*(dz - k1 - xhat*k2) with xhat = (x-mu)*is  ==  A*dz + B*x + Cc
+  float A[V], B[V], Cc[V], sf[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) {
-    mu[i] = mean[c0 + i];
-    is[i] = invstd[c0 + i];
-    sc[i] = (gamma ? gamma[c0 + i] : 1.f) * is[i];
-    sf[i] = (beta ? beta[c0 + i] : 0.f) - mu[i] * sc[i];
-    k1[i] = sum_dz[c0 + i] * inv_count;
-    k2[i] = sum_dz_xhat[c0 + i] * inv_count;
+    const float mu = mean[c0 + i], is = invstd[c0 + i];
+    const float k1 = sum_dz[c0 + i] * inv_count, k2 = sum_dz_xhat[c0 + i] * inv_count;
+    A[i] = (gamma ? gamma[c0 + i] : 1.f) * is;
+    sf[i] = (beta ? beta[c0 + i] : 0.f) - mu * A[i];
+    B[i] = -A[i] * k2 * is;
+    Cc[i] = A[i] * (k2 * mu * is - k1);
   }
   const bool have_y = (y != nullptr);
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -350,10 +353,9 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
 #pragma unroll
         for (int i = 0; i < V; ++i) {
           float xv = a[u].get(i);
-          float dz = dz_of<T>(g[u].get(i), xv, have_y ? o[u].get(i) : 0.f, have_y, sc[i], sf[i],
+          float dz = dz_of<T>(g[u].get(i), xv, have_y ? o[u].get(i) : 0.f, have_y, A[i], sf[i],
                               act, alpha);
-          float xhat = (xv - mu[i]) * is[i];
-          ox.set(i, sc[i] * (dz - k1[i] - xhat * k2[i]));
+          ox.set(i, fmaf(A[i], dz, fmaf(B[i], xv, Cc[i])));
           orr.set(i, dz);
         }
         st_vec(dx + vv * V, ox);
@@ -509,7 +511,7 @@ extern "C" int mcn_bn_bwd_apply(int dtype, const void* dy, const void* x, const 
   const float inv_count = (float)(1.0 / count);
   MCN_DISPATCH_DTYPE(dtype, T, {
     ChanLaunch L;
-    if (plan<T>(rows, C, &L, 8)) {
+    if (plan<T>(rows, C, &L, 12, 256)) {
       bn_bwd_apply_kernel<T><<<L.grid, L.block, 0, st>>>(
           static_cast<const T*>(dy), static_cast<const T*>(x), static_cast<const T*>(y),
           rows * L.cv, L.cv, mean, invstd, gamma, beta, act, act_alpha, sum_dz, sum_dz_xhat,

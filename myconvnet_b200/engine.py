@@ -313,12 +313,10 @@ class Engine(object):
                                              st), "opt_step")
 
     def _allreduce_grads(self):
-        import torch.distributed as dist
+        from .dist import allreduce_sum_flat
         p = self.plan
         flat = self.view(Ptr(p.b_grad), p.n_train, torch.float32)
-        bucket = int(self.kw.get("bucket_elems", 8 * 1024 * 1024))
-        for s in range(0, p.n_train, bucket):
-            dist.all_reduce(flat[s:min(s + bucket, p.n_train)], group=self.pg)
+        allreduce_sum_flat(flat, int(self.kw.get("bucket_elems", 8 * 1024 * 1024)), group=self.pg)
 
     def train_step(self, X=None, Y=None, lr_multiplier=1.0, fetch_loss=True, update=True):
         """One optimisation step.  X: fp32 NHWC images in [0,1]; Y: int32 labels (-1 = none).

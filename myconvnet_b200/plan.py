@@ -270,9 +270,10 @@ class Plan(object):
 
     def _fuse(self):
         for node in self.graph.nodes:
-            node.attrs.setdefault("fused_into", None)
+            node.attrs["fused_into"] = None          # a graph may be planned more than once
         for node in self.graph.nodes:
             if node.op == "bn":
+                node.attrs["act"], node.attrs["alpha"] = 0, 0.0
                 node.attrs["residual"] = None
                 node.attrs["final"] = node.outputs[0]
                 cur = node.outputs[0]

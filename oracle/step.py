@@ -39,7 +39,7 @@ class OracleTrainer(object):
         grads = torch.autograd.grad(loss, [m.vars[k] for k in train], allow_unused=True)
         self.grads = {k: (g if g is not None else torch.zeros_like(m.vars[k])) for k, g in zip(train, grads)}
         if not update:
-            return float(loss)
+            return float(loss.detach())
         lr = self.base_lr * batch / 256.0 * lr_multiplier
         d_t = ops.ema_decay(m.moving_average_decay, self.global_step)
         with torch.no_grad():
@@ -71,4 +71,4 @@ class OracleTrainer(object):
                     w = w - wd * w
                 m.vars[k] = w.clone()
         self.global_step += 1
-        return float(loss)
+        return float(loss.detach())

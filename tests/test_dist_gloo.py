@@ -1,0 +1,54 @@
+"""world_size-2 gloo tests (CPU) of the data-parallel host logic: bucketed gradient averaging
+equals the reference's concat+reduce_mean over towers (optimizers.py:137-138), and summed per-rank
+BN statistics reproduce the single-tower statistics at the global batch (synchronised BN)."""
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from myconvnet_b200.dist import allreduce_stats, allreduce_sum_flat, bucket_ranges
+    from oracle import tf_ops
+    rng = np.random.default_rng(100 + rank)
+    n = 10007
+    g = torch.tensor(rng.standard_normal(n).astype(np.float32))
+    mine = g.clone()
+    nb = allreduce_sum_flat(g, 1024)
+    g /= world
+    # BN statistics of this rank's shard of a global batch
+    full = np.random.default_rng(7).standard_normal((8, 3, 3, 5)).astype(np.float64)
+    shard = torch.tensor(full[rank * 4:(rank + 1) * 4])
+    st = torch.cat([shard.reshape(-1, 5).sum(0), (shard.reshape(-1, 5) ** 2).sum(0)])
+    allreduce_stats(st)
+    cnt = full.size // 5
+    mean = st[:5] / cnt
+    var = st[5:] / cnt - mean ** 2
+    _, m_ref, v_ref = tf_ops.fused_batch_norm_train(torch.tensor(full), None, None, 1e-3)
+    q.put((rank, mine.numpy(), g.numpy(), nb, float((mean - m_ref).abs().max()),
+           float((var * cnt / (cnt - 1) - v_ref).abs().max()), bucket_ranges(n, 1024)[-1]))
+    dist.destroy_process_group()
+
+
+def test_bucketed_gradient_mean_and_sync_bn_statistics():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() % 200)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    expect = np.mean(np.stack([r[1] for r in res]), axis=0)          # concat + reduce_mean over towers
+    for r in res:
+        assert np.allclose(r[2], expect, atol=1e-6)
+        assert r[3] == 10 and r[4] < 1e-12 and r[5] < 1e-12
+        assert r[6] == (9216, 10007)

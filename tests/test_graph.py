@@ -1,0 +1,112 @@
+"""Host logic without a GPU: the reference model files build unchanged on the facade, the
+structure KATs of SURVEY.md 8c hold, and the planner fuses / differentiates as designed."""
+import numpy as np
+import pytest
+
+from myconvnet_b200 import convnet, loader
+from myconvnet_b200.plan import Plan
+
+
+@pytest.fixture(scope="module")
+def r50(have_reference_models):
+    mod = loader.load_reference_model("models/resnet_v1_5.py", {"convnet": convnet})
+    return mod.ResNet50([224, 224, 3], 1000, batch_size=256, compute_dtype="bf16")
+
+
+def test_resnet50_structure_kats(r50):
+    g = r50.graph
+    assert r50.params == 25557032                       # reference's own parameter counter
+    convs = [n for n in g.nodes if n.op == "conv2d"]
+    bns = [n for n in g.nodes if n.op == "bn"]
+    assert len(convs) == 53 and len(bns) == 53
+    macs = sum(n.outputs[0].shape[1] * n.outputs[0].shape[2] * int(np.prod(n.vars["w"].shape)) for n in convs)
+    macs += 2048 * 1000
+    assert macs == 4089184256                           # fwd MAC/img
+    assert len(g.vars) == 267 and sum(v.trainable for v in g.vars.values()) == 161
+    names = set(g.vars)
+    for k in ("block_0/conv_0/weights", "block_0/conv_0/bn/mu", "block_1/res_0/conv_skip/bn/gamma",
+              "block_4/res_2/conv_2/bn/sigma", "block_None/logits/weights", "block_None/logits/biases"):
+        assert k in names, k
+    # TF SAME asymmetry on the strided layers
+    stem = convs[0]
+    assert stem.attrs["pad"] == (2, 2) and stem.outputs[0].shape == (256, 112, 112, 64)
+    s2 = [n for n in convs if n.attrs["s"] == [2, 2] and n.attrs["k"] == [3, 3]]
+    assert all(n.attrs["pad"] == (0, 0) for n in s2) and len(s2) == 3
+    assert r50.block_list == (None, 0, 1, 2, 3, 4) and r50.num_blocks == 5
+
+
+def test_native_builder_matches_reference_graph(r50):
+    from myconvnet_b200 import zoo
+    m = zoo.ResNet50([224, 224, 3], 1000, batch_size=256, compute_dtype="bf16")
+    a = [(n.op, tuple(o.shape for o in n.outputs), tuple(sorted(v.name for v in n.vars.values()))) for n in m.graph.nodes]
+    b = [(n.op, tuple(o.shape for o in n.outputs), tuple(sorted(v.name for v in n.vars.values()))) for n in r50.graph.nodes]
+    assert a == b
+    assert set(m.d) == set(r50.d)
+
+
+def test_plan_fusion_and_launch_counts(r50):
+    p = Plan(r50.graph)
+    h = p.launch_histogram()
+    assert h["mcn_conv2d_fprop_tc"] == 54 and h["mcn_conv2d_wgrad_tc"] == 54      # 53 convs + dense
+    assert h["mcn_conv2d_dgrad_tc"] == 53                                        # no dgrad into the images
+    assert h["mcn_bn_apply"] == 53 and "mcn_act_fwd" not in h and "mcn_add_act_fwd" not in h
+    assert "mcn_accumulate" not in h                    # multi-consumer gradients add in the dgrad epilogue
+    fused = [n for n in r50.graph.nodes if n.op == "bn"]
+    assert sum(n.attrs["residual"] is not None for n in fused) == 16
+    assert sum(n.attrs["act"] == 1 for n in fused) == 49
+    # arena fits comfortably in 180 GB and regions do not overlap
+    spans = sorted(p.region_span.values())
+    assert all(spans[i][1] <= spans[i + 1][0] for i in range(len(spans) - 1))
+    assert p.arena_bytes < 40e9
+    offs = sorted((b.offset, b.offset + b.nbytes) for b in p.bufs if b.region != "temp")
+    assert all(offs[i][1] <= offs[i + 1][0] for i in range(len(offs) - 1))
+    # stem: RGB input goes through explicit im2col with a zero-padded K
+    stem = [n for n in r50.graph.nodes if n.op == "conv2d"][0]
+    assert stem.attrs["route"] == "im2col" and stem.attrs["kpad"] == 152
+    assert stem.vars["w"].storage_shape == (152, 64)
+
+
+def test_plan_keeps_taps_unfused(r50):
+    taps = [t for k, t in r50.d.items() if k.endswith("/bn")]
+    p = Plan(r50.graph, keep=taps)
+    assert p.launch_histogram().get("mcn_act_fwd", 0) > 0
+    for t in taps:
+        assert t in p.tbuf
+
+
+def test_sync_bn_plan_has_collective_points(r50):
+    p = Plan(r50.graph, world_size=8)
+    assert len([a for a in p.allreduce_points if a[0] == "f"]) == 53
+    assert len([a for a in p.allreduce_points if a[0] == "b"]) == 53
+
+
+def test_fp32_config_uses_exact_path(have_reference_models):
+    mod = loader.load_reference_model("models/resnet_v1_5.py", {"convnet": convnet})
+    m = mod.ResNet50([224, 224, 3], 1000, batch_size=32)        # BASELINE config 1: fp32, batch 32
+    h = Plan(m.graph).launch_histogram()
+    assert "mcn_conv2d_fprop_tc" not in h and h["mcn_conv2d_fprop_direct"] == 54
+
+
+def test_facade_errors_mirror_reference():
+    m = convnet.ConvNet([8, 8, 3], 4, auto_build=False, batch_size=2)
+    x = m.graph.placeholder("x", (2, 8, 8, 4), "f32")
+    with pytest.raises(ValueError):
+        m.pooling_layer(x, 2, 2, pooling_type="median")           # convnet.py:1470
+    with pytest.raises(ValueError):
+        m.normalization(x, norm_type="layer")                     # convnet.py:1776
+    with pytest.raises(ValueError):
+        m.activation(x, activation_type="gelu")                   # convnet.py:2533
+    with pytest.raises(ValueError):
+        m.upsampling_2d_layer(x, upsampling_method="bicubic")     # convnet.py:2400
+    with pytest.raises(NotImplementedError):
+        convnet.ConvNet([8, 8, 3], 4, channel_first=True, batch_size=2)
+    assert m.relu(x).shape == (2, 8, 8, 4) and m.activation(x, None) is x
+
+
+def test_engine_refuses_to_run_without_cuda(r50):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from myconvnet_b200.engine import Engine
+    with pytest.raises(RuntimeError, match="no CPU execution"):
+        Engine(r50)
