@@ -103,7 +103,7 @@ struct GemmConvArgs {
   CUtensorMap mapA[4];
   CUtensorMap mapB;
   TileGeom g;
-  int taps, k_chunks, ksteps_last, block_n, n_total, stages, tiles_n, tmem_cols;
+  int taps, k_chunks, ksteps_last, block_n, n_total, stages, tiles_n, tmem_cols, total_tiles;
   long long out_sn, out_sh, out_sw;  // element strides of the output pixel grid
   void* out;
   const float* bias;
@@ -111,6 +111,10 @@ struct GemmConvArgs {
   TapTab tab;
 };
 
+// Persistent: one CTA per SM walks tiles (tile = blockIdx.x + i*gridDim.x).  The shared-memory
+// ring and its phases run across tile boundaries, so the producer prefetches the next tile while
+// the MMA warp finishes the current one; the accumulator is double-buffered in TMEM so the
+// epilogue of tile i overlaps the MMAs of tile i+1.
 __global__ void __launch_bounds__(192, 1)
 gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
   extern __shared__ uint8_t smem_raw[];
@@ -123,13 +127,12 @@ gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
   const uint32_t stage_bytes = kABytes + b_bytes;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(stages) * stage_bytes);
   uint64_t* empty = full + stages;
-  uint64_t* tmem_full = empty + stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tmem_full = empty + stages;     // [2]
+  uint64_t* tmem_empty = tmem_full + 2;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-  const int n_t = blockIdx.x % args.tiles_n;
-  const int m_t = blockIdx.x / args.tiles_n;
-  const PixelTile tile = decode_tile(args.g, m_t);
-  const int total_it = args.taps * args.k_chunks;
+  const int total_tiles = args.total_tiles;
+  const int k_iters = args.taps * args.k_chunks;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) ptx::prefetch_tmap(&args.mapA[i]);
@@ -138,7 +141,10 @@ gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
       ptx::mbar_init(&full[s], 1);
       ptx::mbar_init(&empty[s], 1);
     }
-    ptx::mbar_init(tmem_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&tmem_full[b], 1);
+      ptx::mbar_init(&tmem_empty[b], 4);   // one arrival per epilogue warp
+    }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -156,126 +162,166 @@ gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
       const uint32_t a_tx = (args.g.a_mode == 0) ? static_cast<uint32_t>(args.g.rows_box) * 128u
                                                  : static_cast<uint32_t>(kABytes);
       int it = 0;
-      for (int t = 0; t < args.taps; ++t) {
-        for (int kc = 0; kc < args.k_chunks; ++kc, ++it) {
-          const int s = it % stages;
-          const uint32_t ph = static_cast<uint32_t>(it / stages) & 1u;
-          ptx::mbar_wait(&empty[s], ph ^ 1u);
-          ptx::mbar_expect_tx(&full[s], a_tx + b_bytes);
-          uint8_t* sA = smem + static_cast<size_t>(s) * stage_bytes;
-          uint8_t* sB = sA + kABytes;
-          if (args.g.a_mode == 0) {
-            ptx::tma_load_4d(&args.mapA[args.tab.map[t]], &full[s], sA, kc * 64,
-                             tile.w0 + args.tab.dw[t], tile.h0 + args.tab.dh[t], tile.n0);
-          } else {
-            ptx::tma_load_im2col_4d(&args.mapA[0], &full[s], sA, kc * 64, tile.w0, tile.h0,
-                                    tile.n0, static_cast<uint16_t>(args.tab.dw[t]),
-                                    static_cast<uint16_t>(args.tab.dh[t]));
+      for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x) {
+        const int n_t = tile_id % args.tiles_n;
+        const PixelTile tile = decode_tile(args.g, tile_id / args.tiles_n);
+        for (int t = 0; t < args.taps; ++t) {
+          for (int kc = 0; kc < args.k_chunks; ++kc, ++it) {
+            const int s = it % stages;
+            const uint32_t ph = static_cast<uint32_t>(it / stages) & 1u;
+            ptx::mbar_wait(&empty[s], ph ^ 1u);
+            ptx::mbar_expect_tx(&full[s], a_tx + b_bytes);
+            uint8_t* sA = smem + static_cast<size_t>(s) * stage_bytes;
+            uint8_t* sB = sA + kABytes;
+            if (args.g.a_mode == 0) {
+              ptx::tma_load_4d(&args.mapA[args.tab.map[t]], &full[s], sA, kc * 64,
+                               tile.w0 + args.tab.dw[t], tile.h0 + args.tab.dh[t], tile.n0);
+            } else {
+              ptx::tma_load_im2col_4d(&args.mapA[0], &full[s], sA, kc * 64, tile.w0, tile.h0,
+                                      tile.n0, static_cast<uint16_t>(args.tab.dw[t]),
+                                      static_cast<uint16_t>(args.tab.dh[t]));
+            }
+            ptx::tma_load_2d(&args.mapB, &full[s], sB, kc * 64,
+                             args.tab.brow[t] + n_t * args.block_n);
           }
-          ptx::tma_load_2d(&args.mapB, &full[s], sB, kc * 64,
-                           args.tab.brow[t] + n_t * args.block_n);
         }
       }
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
     const uint32_t idesc = ptx::make_idesc_bf16(128, args.block_n, 0, 0);
-    int it = 0;
-    for (int t = 0; t < args.taps; ++t) {
-      for (int kc = 0; kc < args.k_chunks; ++kc, ++it) {
-        const int s = it % stages;
-        const uint32_t ph = static_cast<uint32_t>(it / stages) & 1u;
-        ptx::mbar_wait(&full[s], ph);
-        ptx::tc_fence_after();
-        if (ptx::elect_one()) {
-          const uint32_t a_addr = ptx::smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
-          const uint32_t b_addr = a_addr + kABytes;
-          const int ksteps = (kc == args.k_chunks - 1) ? args.ksteps_last : 4;
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t ad = ptx::make_smem_desc(a_addr + k * 32, 16, 1024);
-            const uint64_t bd = ptx::make_smem_desc(b_addr + k * 32, 16, 1024);
-            ptx::umma_bf16(tmem_base, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+    int it = 0, lt = 0;
+    for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x, ++lt) {
+      const int buf = lt & 1;
+      const uint32_t tph = static_cast<uint32_t>(lt >> 1) & 1u;
+      ptx::mbar_wait(&tmem_empty[buf], tph ^ 1u);   // epilogue has drained this accumulator
+      ptx::tc_fence_after();
+      const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * args.block_n);
+      int kit = 0;
+      for (int t = 0; t < args.taps; ++t) {
+        for (int kc = 0; kc < args.k_chunks; ++kc, ++it, ++kit) {
+          const int s = it % stages;
+          const uint32_t ph = static_cast<uint32_t>(it / stages) & 1u;
+          ptx::mbar_wait(&full[s], ph);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            const uint32_t a_addr = ptx::smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
+            const uint32_t b_addr = a_addr + kABytes;
+            const int ksteps = (kc == args.k_chunks - 1) ? args.ksteps_last : 4;
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t ad = ptx::make_smem_desc(a_addr + k * 32, 16, 1024);
+              const uint64_t bd = ptx::make_smem_desc(b_addr + k * 32, 16, 1024);
+              ptx::umma_bf16(tmem_d, ad, bd, idesc, (kit | k) != 0 ? 1u : 0u);
+            }
+            ptx::umma_commit(&empty[s]);
+            if (kit == k_iters - 1) ptx::umma_commit(&tmem_full[buf]);
           }
-          ptx::umma_commit(&empty[s]);
-          if (it == total_it - 1) ptx::umma_commit(tmem_full);
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
   } else {
     // ---------------- epilogue: TMEM -> registers -> global ----------------
     // Each thread owns one output pixel (row) and walks its channels 64 at a time: 64 bf16 = one
     // full 128-byte line written with four 32-byte stores (fp32 output: eight).
-    ptx::mbar_wait(tmem_full, 0);
-    ptx::tc_fence_after();
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;
-    int n, p, q;
-    const bool valid = row_coords(args.g, tile, row, n, p, q);
-    const long long off = valid ? (n * args.out_sn + p * args.out_sh + q * args.out_sw) : 0;
-    for (int c0 = 0; c0 < args.block_n; c0 += 64) {
-      uint32_t r[64];
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c0;
-      ptx::tmem_ld_32x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
-      ptx::tmem_ld_32x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
-      ptx::tmem_ld_wait();
-      const int col0 = n_t * args.block_n + c0;
-      if (!valid || col0 >= args.n_total) continue;
-      const bool full = args.vec_ok && (col0 + 64 <= args.n_total);
-      if (args.bias != nullptr) {
+    int lt = 0;
+    for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x, ++lt) {
+      const int buf = lt & 1;
+      const uint32_t tph = static_cast<uint32_t>(lt >> 1) & 1u;
+      const int n_t = tile_id % args.tiles_n;
+      const PixelTile tile = decode_tile(args.g, tile_id / args.tiles_n);
+      int n, p, q;
+      const bool valid = row_coords(args.g, tile, row, n, p, q);
+      const long long off = valid ? (n * args.out_sn + p * args.out_sh + q * args.out_sw) : 0;
+      // bf16 accumulate (dx += dgrad): the previous values of a 64-channel chunk are fetched
+      // with four back-to-back 32-byte loads one chunk AHEAD (the first one before the
+      // accumulator is even ready), so the global-load latency hides behind the MMAs.
+      const bool acc_bf16 = args.accumulate && !args.out_f32 && args.vec_ok;
+      uint32_t old[32];
+      __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(args.out) + off;
+      auto prefetch_old = [&](int c0) {
+        const int col0 = n_t * args.block_n + c0;
+        if (valid && col0 + 64 <= args.n_total) {
 #pragma unroll
-        for (int j = 0; j < 64; ++j)
-          if (full || col0 + j < args.n_total)
-            r[j] = __float_as_uint(__uint_as_float(r[j]) + args.bias[col0 + j]);
-      }
-      if (args.out_f32) {
-        float* o = reinterpret_cast<float*>(args.out) + off + col0;
-        if (full) {
+          for (int j = 0; j < 4; ++j)
+            ptx::ld_global_v8(obase + col0 + j * 16, *reinterpret_cast<uint32_t(*)[8]>(&old[j * 8]));
+        }
+      };
+      if (acc_bf16) prefetch_old(0);
+      ptx::mbar_wait(&tmem_full[buf], tph);
+      ptx::tc_fence_after();
+      for (int c0 = 0; c0 < args.block_n; c0 += 64) {
+        uint32_t r[64];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                               static_cast<uint32_t>(buf * args.block_n + c0);
+        ptx::tmem_ld_32x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+        ptx::tmem_ld_32x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+        ptx::tmem_ld_wait();
+        if (c0 + 64 >= args.block_n) {
+          // last read of this accumulator: hand the TMEM buffer back before the stores drain
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tmem_empty[buf]);
+        }
+        const int col0 = n_t * args.block_n + c0;
+        const bool fullw = args.vec_ok && (col0 + 64 <= args.n_total);
+        if (!valid || col0 >= args.n_total) continue;
+        if (args.bias != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 64; j += 8) {
-            uint32_t v[8];
-            if (args.accumulate) {
-              ptx::ld_global_v8(o + j, v);
+          for (int j = 0; j < 64; ++j)
+            if (fullw || col0 + j < args.n_total)
+              r[j] = __float_as_uint(__uint_as_float(r[j]) + args.bias[col0 + j]);
+        }
+        if (args.out_f32) {
+          float* o = reinterpret_cast<float*>(args.out) + off + col0;
+          if (fullw) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e)
-                v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(r[j + e]));
-            } else {
+            for (int j = 0; j < 64; j += 8) {
+              uint32_t v[8];
+              if (args.accumulate) {
+                ptx::ld_global_v8(o + j, v);
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = r[j + e];
+                for (int e = 0; e < 8; ++e)
+                  v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(r[j + e]));
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = r[j + e];
+              }
+              ptx::st_global_v8(o + j, v);
             }
-            ptx::st_global_v8(o + j, v);
+          } else {
+            for (int j = 0; j < 64; ++j)
+              if (col0 + j < args.n_total)
+                o[j] = __uint_as_float(r[j]) + (args.accumulate ? o[j] : 0.f);
           }
         } else {
-          for (int j = 0; j < 64; ++j)
-            if (col0 + j < args.n_total)
-              o[j] = __uint_as_float(r[j]) + (args.accumulate ? o[j] : 0.f);
-        }
-      } else {
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(args.out) + off + col0;
-        if (full) {
+          __nv_bfloat16* o = obase + col0;
+          if (fullw) {
+            uint32_t v[32];
 #pragma unroll
-          for (int j = 0; j < 64; j += 16) {
-            uint32_t v[8];
-            if (args.accumulate) ptx::ld_global_v8(o + j, v);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              float lo = __uint_as_float(r[j + 2 * e]), hi = __uint_as_float(r[j + 2 * e + 1]);
-              if (args.accumulate) {
-                lo += __uint_as_float(v[e] << 16);
-                hi += __uint_as_float(v[e] & 0xFFFF0000u);
+            for (int e = 0; e < 32; ++e) {
+              float lo = __uint_as_float(r[2 * e]), hi = __uint_as_float(r[2 * e + 1]);
+              if (acc_bf16) {
+                lo += __uint_as_float(old[e] << 16);
+                hi += __uint_as_float(old[e] & 0xFFFF0000u);
               }
               __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
               v[e] = *reinterpret_cast<uint32_t*>(&h);
             }
-            ptx::st_global_v8(o + j, v);
+            if (acc_bf16 && c0 + 64 < args.block_n) prefetch_old(c0 + 64);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              ptx::st_global_v8(o + j * 16, *reinterpret_cast<uint32_t(*)[8]>(&v[j * 8]));
+          } else {
+            for (int j = 0; j < 64; ++j)
+              if (col0 + j < args.n_total) {
+                float f = __uint_as_float(r[j]);
+                if (args.accumulate) f += __bfloat162float(o[j]);
+                o[j] = __float2bfloat16_rn(f);
+              }
           }
-        } else {
-          for (int j = 0; j < 64; ++j)
-            if (col0 + j < args.n_total) {
-              float f = __uint_as_float(r[j]);
-              if (args.accumulate) f += __bfloat162float(o[j]);
-              o[j] = __float2bfloat16_rn(f);
-            }
         }
       }
     }
@@ -594,22 +640,23 @@ int smem_optin_limit() {
 
 int launch_gemm_conv(GemmConvArgs& a, int tiles_m, cudaStream_t st) {
   const uint32_t stage_bytes = kABytes + a.block_n * 128;
-  // two CTAs per SM so one tile's epilogue overlaps the other's main loop
-  int stages = std::min(8, static_cast<int>((110 * 1024) / stage_bytes));
-  stages = std::max(2, std::min(stages, a.taps * a.k_chunks));
+  // one persistent CTA per SM: the whole shared memory is the TMA ring
+  int stages = std::min(8, static_cast<int>((200 * 1024) / stage_bytes));
+  stages = std::max(2, stages);
   a.stages = stages;
-  a.tmem_cols = tmem_cols_for(a.block_n);
-  size_t smem = static_cast<size_t>(stages) * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
-  static size_t configured = 0;
-  if (smem > configured) {
+  a.tmem_cols = 2 * tmem_cols_for(a.block_n);   // double-buffered accumulator
+  a.total_tiles = tiles_m * a.tiles_n;
+  size_t smem = static_cast<size_t>(stages) * stage_bytes + (2 * stages + 4) * 8 + 16 + 1024;
+  static bool configured = false;
+  if (!configured) {
     if (cudaFuncSetAttribute(gemm_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              smem_optin_limit()) != cudaSuccess) {
       set_error("cudaFuncSetAttribute(gemm_conv_kernel) failed");
       return MCN_ECUDA;
     }
-    configured = smem_optin_limit();
+    configured = true;
   }
-  dim3 grid(static_cast<unsigned>(tiles_m) * a.tiles_n);
+  dim3 grid(static_cast<unsigned>(std::min(a.total_tiles, num_sms())));
   gemm_conv_kernel<<<grid, 192, smem, st>>>(a);
   return after_launch("gemm_conv_kernel");
 }
