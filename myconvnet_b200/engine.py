@@ -283,8 +283,12 @@ class Engine(object):
         """Host (numpy / pinned torch) -> device input buffers, asynchronously on the current
         stream.  Returns the bytes copied."""
         nbytes = 0
+        off = int(getattr(self.model, "label_offset", 0))
         for name, arr in arrays.items():
             dst = self._inputs[name]
+            if name == "Y" and off:
+                # task bases that take labels with 0 = ignore (segnet.py:50) store class-1 on device
+                arr = (np.asarray(arr) if isinstance(arr, np.ndarray) else arr.numpy()).astype(np.int64) - off
             if isinstance(arr, np.ndarray):
                 pin = self._pinned.get(name)
                 if pin is None or pin.shape != dst.shape:

@@ -1,0 +1,81 @@
+"""GPU parity of the other north-star model files, loaded UNCHANGED: EfficientNet-B0 (depthwise
+conv, SE, swish) and DeepLabv3+ on the dilated ResNet (atrous conv, ASPP concat, bilinear
+upsampling, per-pixel loss).  fp32 path: tight activation/loss check; bf16 path: tensor-core
+kernels, loss and loss curve within 3 %.  See tests/test_gpu_resnet.py for the tolerance rationale."""
+import numpy as np
+import pytest
+
+from myconvnet_b200 import loader
+from myconvnet_b200.engine import draw_initial_value
+from tests.util import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(rel_path, cls, shape, ncls, batch, dtype, oracle_facade, **kw):
+    pm = getattr(loader.load_reference_model(rel_path, loader.product_facade()), cls)(
+        shape, ncls, batch_size=batch, compute_dtype=dtype, **kw)
+    rng = np.random.default_rng(0)
+    vals = {v.name: draw_initial_value(v, rng) for v in pm.graph.vars.values()}
+    for k in vals:
+        if k.endswith("gamma") and not vals[k].any():
+            vals[k] = np.full_like(vals[k], 0.5)
+    om = getattr(loader.load_reference_model(rel_path, oracle_facade), cls)(
+        shape, ncls, oracle_round_bf16=(dtype == "bf16"), **kw)
+    om.set_variables(vals)
+    return pm, om, vals
+
+
+def _oracle_facade():
+    from oracle import ref_convnet, ref_segnet
+    return {"convnet": ref_convnet, "segmentation.segnet": ref_segnet}
+
+
+def _check(pm, om, vals, X, Y, dtype, steps=3):
+    from myconvnet_b200.engine import Engine
+    from oracle.step import OracleTrainer
+    taps = {k: t for k, t in pm.d.items() if hasattr(t, "shape") and k != "pred"}
+    eng = Engine(pm, keep=list(taps.values()))
+    eng.set_variables(vals)
+    loss_dev = eng.train_step(X, Y, update=False)
+    tr = OracleTrainer(om, batch_size=len(X))
+    tr.step(X, Y, update=False)
+    assert abs(loss_dev - float(om.data_loss)) <= (1e-3 if dtype == "f32" else 3e-2) * abs(float(om.data_loss)) + 1e-4
+    if dtype == "f32":
+        bad = [(k, rel_l2(eng.fetch(t), om.d[k].t.detach().numpy())) for k, t in taps.items()
+               if om.d.get(k) is not None]
+        bad = [b for b in bad if b[1] > 5e-4]
+        assert not bad, bad[:6]
+    grads = eng.get_gradients()
+    assert all(np.isfinite(g).all() for g in grads.values())
+    # fused plan over a few optimiser steps
+    eng2 = Engine(pm)
+    eng2.set_variables(vals)
+    tr2 = OracleTrainer(om, batch_size=len(X))
+    om.set_variables(vals)
+    tol = 1e-2 if dtype == "f32" else 4e-2
+    for _ in range(steps):
+        a, b = eng2.train_step(X, Y), tr2.step(X, Y)
+        assert np.isfinite(a) and abs(a - b) <= tol * abs(b) + tol, (a, b)
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_efficientnet_b0(have_reference_models, dtype):
+    shape, ncls, batch = [64, 64, 3], 10, 8
+    pm, om, vals = _pair("models/efficientnet.py", "EfficientNetB0", shape, ncls, batch, dtype,
+                         _oracle_facade(), base_learning_rate=0.05)
+    rng = np.random.default_rng(1)
+    X = rng.uniform(size=[batch] + shape).astype(np.float32)
+    Y = rng.integers(0, ncls, size=batch).astype(np.int32)
+    _check(pm, om, vals, X, Y, dtype)
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_deeplabv3plus(have_reference_models, dtype):
+    shape, ncls, batch = [64, 64, 3], 5, 2
+    pm, om, vals = _pair("models/deeplabv3plus.py", "DeepLabV3PlusResNet", shape, ncls, batch, dtype,
+                         _oracle_facade(), base_learning_rate=0.05)
+    rng = np.random.default_rng(2)
+    X = rng.uniform(size=[batch] + shape).astype(np.float32)
+    Y = rng.integers(0, ncls + 1, size=[batch] + shape[:2]).astype(np.int32)    # 0 = ignore
+    _check(pm, om, vals, X, Y, dtype, steps=2)
