@@ -79,7 +79,8 @@ class Engine(object):
         self.base_lr = float(self.kw.get("base_learning_rate", 0.1))
         self.momentum = float(self.kw.get("momentum", 0.9))
         self.ema_decay = float(model.moving_average_decay)
-        self.l2 = float(self.kw.get("l2_reg", 1e-4))
+        # GAN losses carry no L2 term (gan.py overrides _build_loss)
+        self.l2 = float(self.kw.get("l2_reg", 1e-4)) if getattr(model, "uses_l2", True) else 0.0
         self.bias_norm_decay = bool(self.kw.get("bias_norm_decay", False))
         self.base_wd = float(self.kw.get("base_weight_decay", 0.0)) * self.global_batch / 256
         self.wd_scheduling = bool(self.kw.get("weight_decay_scheduling", True))
@@ -361,8 +362,12 @@ class Engine(object):
         p = self.plan
         if "loss" not in p.loss_slots:
             return None
-        v = self.view(p.loss_slots["loss"], 2, torch.float32).cpu().numpy()
         node = self.graph.losses[0].node
+        if "loss_g" in p.loss_slots:
+            v = self.view(p.loss_slots["loss"], 3, torch.float32).cpu().numpy()
+            self.last_losses = (float(v[0]) / node.attrs["rows"], float(v[1]) / node.attrs["rows"])
+            return self.last_losses[0]
+        v = self.view(p.loss_slots["loss"], 2, torch.float32).cpu().numpy()
         data = float(v[0]) / node.attrs["rows"]
         return data + float(v[1])
 

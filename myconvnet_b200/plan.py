@@ -203,7 +203,7 @@ class Plan(object):
                 w = node.vars["w"]
                 route = self._conv_route(node)
                 node.attrs["route"] = route
-                if route == "tc":
+                if route in ("tc", "mixed"):
                     w.needs_bf16 = w.needs_bf16_t = True
                     if node.op == "dense":
                         w.gemm_dims = (1, w.shape[0], w.shape[1])
@@ -229,26 +229,37 @@ class Plan(object):
             return "tc" if ci % 8 == 0 and co % 8 == 0 else "direct"
         kh, kw, ci, co = w.shape
         if node.op == "conv2d_transpose":
-            # runs as dgrad: GEMM K = input channels (ci), N = output channels (co)
-            return "tc" if ci % 8 == 0 and co % 8 == 0 and kh * kw <= 52 else "direct"
+            # runs as dgrad: GEMM K = input channels (ci), N = output channels (co, masked if odd);
+            # "mixed": forward on tcgen05, backward on the CUDA-core kernels (co % 8 != 0: RGB out)
+            if ci % 8 == 0 and kh * kw <= 52:
+                return "tc" if co % 8 == 0 else "mixed"
+            return "direct"
         if ci % 8 == 0 and co % 8 == 0 and kh * kw <= 52:
             return "tc"
-        if co % 8 == 0 and not self._needs_input_grad(node):
+        if co % 8 == 0 and kh * kw <= 52:
             return "im2col"
         return "direct"
 
     def _needs_input_grad(self, node):
         return self._tensor_needs_grad(node.inputs[0])
 
+    def _var_trains(self, v):
+        """Is v updated by the backward pass being emitted?  (GANs run one pass per loss, each
+        with its own variable subset, optimizers_gan.py:56-58.)"""
+        ps = self.__dict__.get("cur_pass")
+        return v.trainable and (ps is None or ps["train"] is None or v in ps["train"])
+
     def _tensor_needs_grad(self, t):
         cache = self.__dict__.setdefault("_ng_cache", {})
         if t in cache:
             return cache[t]
         n = t.node
-        if n is None or n.op in ("input", "stop_gradient"):
+        ps = self.__dict__.get("cur_pass")
+        if n is None or n.op in ("input", "stop_gradient") or (ps is not None and t in ps["stop"]):
             r = False
         else:
-            r = any(v.trainable for v in n.vars.values()) or any(self._tensor_needs_grad(i) for i in n.inputs)
+            r = any(self._var_trains(v) for v in n.vars.values()) or \
+                any(self._tensor_needs_grad(i) for i in n.inputs)
         cache[t] = r
         return r
 
@@ -451,13 +462,21 @@ class Plan(object):
                            pad_t=a["pad"][0], pad_l=a["pad"][1], Ho=h, Wo=wd)
         node.attrs["desc"] = d
         py = self.alloc_act(y)
-        if node.attrs["route"] == "tc":
+        if node.attrs["route"] in ("tc", "mixed"):
             # dgrad wants W_conv[tap][Cin_conv=co][Cout_conv=ci] = stored[tap][ci][co]^T = bf16_t copy
             self.L("f", "mcn_conv2d_dgrad_tc", d, self.tbuf[x], self.pbf16t(w), py, self.ccode,
                    self.conv_mode, 0, tag=node.scope)
         else:
-            raise NotImplementedError("transposed conv needs channel counts that are multiples of 8 "
-                                      "on the tensor-core path; direct route is lowered in _f_tconv_direct")
+            # exact / odd-channel path on CUDA cores: the underlying conv's HWIO weight
+            # [tap][co][ci] is rebuilt from the stored [tap][ci][co] master every step (tiny)
+            kh, kw, ci_t, co_t = w.shape
+            wT = self.new_buf("tconv_wT:%s" % node.scope, w.size * 4, "act")
+            node.attrs["wT"] = wT
+            self.L("f", "mcn_fill_f32", Ptr(wT), w.size, 0.0, tag="zero")
+            self.L("f", "mcn_transpose_add_f32", self.pvar(w), kh * kw, ci_t, co_t, Ptr(wT),
+                   tag=node.scope + "/wT")
+            self.L("f", "mcn_conv2d_dgrad_direct", d, self.ccode, self.tbuf[x], 0, Ptr(wT), py,
+                   tag=node.scope)
         if "b" in node.vars:
             self.L("f", "mcn_bias_add", self.ccode, py, y.size // co, co, self.pvar(node.vars["b"]),
                    tag=node.scope + "/bias")
@@ -637,24 +656,82 @@ class Plan(object):
                a["label_smoothing"], self.loss_scale / rows, Ptr(loss), Ptr(dlog), probs,
                tag="softmax_xent")
 
+    def _f_gan_loss(self, node):
+        lr_, lf_ = node.inputs
+        a = node.attrs
+        n = a["rows"]
+        loss = self.new_buf("gan_loss", 16, "zero")
+        self.loss_slots["loss"] = Ptr(loss)
+        self.loss_slots["loss_g"] = Ptr(loss, 4)
+        self.loss_slots["l2"] = Ptr(loss, 8)
+        self.tbuf[node.outputs[0]] = Ptr(loss)
+        self.tbuf[node.outputs[1]] = Ptr(loss, 4)
+        bufs = [self.new_buf("dlogits_%s" % k, n * 4, "act") for k in ("real", "fake_d", "fake_g")]
+        a["dlogits"] = bufs
+        w0, w1 = a["w"]
+        ls = a["label_smoothing"]
+        gs = self.loss_scale / n
+        # loss_d = mean(w1*sigCE(1-ls, D(x)) + w0*sigCE(0, D(G(z)))); loss_g = mean(w0*sigCE(1-ls, D(G(z))))
+        self.L("f", "mcn_sigmoid_xent", self.tbuf[lr_], n, 1.0 - ls, w1, gs, Ptr(loss), Ptr(bufs[0]), 0,
+               tag="gan_loss/real")
+        self.L("f", "mcn_sigmoid_xent", self.tbuf[lf_], n, 0.0, w0, gs, Ptr(loss), Ptr(bufs[1]), 0,
+               tag="gan_loss/fake_d")
+        self.L("f", "mcn_sigmoid_xent", self.tbuf[lf_], n, 1.0 - ls, w0, gs * a["generator_scaling_factor"],
+               Ptr(loss, 4), Ptr(bufs[2]), 0, tag="gan_loss/fake_g")
+
+    def _b_gan_loss(self, node):
+        lr_, lf_ = node.inputs
+        b = node.attrs["dlogits"]
+        if self.cur_pass["id"] == 0:
+            self.g[lr_] = (Ptr(b[0]), None)
+            self.g[lf_] = (Ptr(b[1]), None)
+        else:
+            self.g[lf_] = (Ptr(b[2]), None)
+
     # ------------------------------------------------------------------ backward emission
+    def _backward_passes(self):
+        gl = [n for n in self.graph.nodes if n.op == "gan_loss"]
+        if not gl:
+            return [{"id": 0, "train": None, "stop": set()}]
+        model_vars = list(self.graph.vars.values())
+        node = gl[0]
+        g_blocks = node.attrs["g_blocks"]
+        vd = set(v for v in model_vars if v.block not in g_blocks)
+        vg = set(v for v in model_vars if v.block in g_blocks)
+        return [{"id": 0, "train": vd, "stop": {node.attrs["generate"]}},
+                {"id": 1, "train": vg, "stop": set()}]
+
     def _emit_backward(self):
-        self.g = {}          # Tensor -> (Ptr, handle or None)
         g = self.graph
-        for node in reversed(g.nodes):
-            if node.attrs.get("fused_into") is not None:
-                continue
-            fn = getattr(self, "_b_" + node.op, None)
-            if fn is None:
-                continue
-            out = node.attrs.get("final", node.outputs[0] if node.outputs else None)
-            if node.op == "softmax_xent":
-                fn(node)
-                continue
-            if out is None or out not in self.g:
-                continue
-            fn(node, self.g[out][0])
-            self._release_grad(out)
+        uses = collections.Counter()
+        for node in g.nodes:
+            if node.op == "bn":
+                for k in ("gamma", "beta"):
+                    if k in node.vars:
+                        uses[node.vars[k]] += 1
+        self._bn_var_uses = uses
+        for ps in self._backward_passes():
+            self.cur_pass = ps
+            self._ng_cache = {}
+            self.g = {}          # Tensor -> (Ptr, handle or None)
+            for node in reversed(g.nodes):
+                if node.attrs.get("fused_into") is not None:
+                    continue
+                fn = getattr(self, "_b_" + node.op, None)
+                if fn is None:
+                    continue
+                if node.op in ("softmax_xent", "gan_loss"):
+                    fn(node)
+                    continue
+                out = node.attrs.get("final", node.outputs[0] if node.outputs else None)
+                if out is None or out not in self.g:
+                    continue
+                fn(node, self.g[out][0])
+                self._release_grad(out)
+            for t in list(self.g):
+                self._release_grad(t)
+        self.cur_pass = None
+        self._ng_cache = {}
 
     def _release_grad(self, t):
         p, h = self.g.pop(t)
@@ -699,7 +776,7 @@ class Plan(object):
         d = node.attrs["desc"]
         n, ci = x.shape
         co = w.shape[1]
-        if "b" in node.vars:
+        if "b" in node.vars and self._var_trains(node.vars["b"]):
             self.L("b", "mcn_bias_grad", DT_CODE[y.dtype], gy, n, co, self.pgrad(node.vars["b"]),
                    tag=node.scope + "/dbias")
         if node.attrs["route"] == "tc":
@@ -708,7 +785,7 @@ class Plan(object):
             if y.dtype != "bf16":
                 gyb, h = self.talloc(n * co * 2)
                 self.L("b", "mcn_cast", DT_CODE[y.dtype], gy, 1, gyb, n * co, tag="dlogits_bf16")
-            if w.trainable:
+            if self._var_trains(w):
                 self.L("b", "mcn_conv2d_wgrad_tc", d, self.tbuf[x], gyb, self.pgrad(w), 0,
                        tag=node.scope + "/wgrad")
             self.contribute(x, x.size * 2,
@@ -719,7 +796,7 @@ class Plan(object):
             if h is not None:
                 self.tfree(h)
         else:
-            if w.trainable:
+            if self._var_trains(w):
                 self.L("b", "mcn_conv2d_wgrad_direct", d, self.ccode, self.tbuf[x], gy, self.pgrad(w),
                        tag=node.scope + "/wgrad")
             self.contribute(x, x.size * self.csz,
@@ -731,11 +808,11 @@ class Plan(object):
         w = node.vars["w"]
         d = node.attrs["desc"]
         route = node.attrs["route"]
-        if "b" in node.vars:
+        if "b" in node.vars and self._var_trains(node.vars["b"]):
             self.L("b", "mcn_bias_grad", self.ccode, gy, y.size // d.Cout, d.Cout,
                    self.pgrad(node.vars["b"]), tag=node.scope + "/dbias")
         if route == "tc":
-            if w.trainable:
+            if self._var_trains(w):
                 self.L("b", "mcn_conv2d_wgrad_tc", d, self.tbuf[x], gy, self.pgrad(w), self.conv_mode,
                        tag=node.scope + "/wgrad")
             self.contribute(x, x.size * 2,
@@ -744,11 +821,17 @@ class Plan(object):
                             emit_acc=lambda p: self.L("b", "mcn_conv2d_dgrad_tc", d, gy, self.pbf16(w), p, 1,
                                                       self.conv_mode, 1, tag=node.scope + "/dgrad+"))
         elif route == "im2col":
-            if w.trainable:
+            if self._var_trains(w):
                 self.L("b", "mcn_conv2d_wgrad_tc", node.attrs["gemm_desc"], Ptr(node.attrs["col"]), gy,
                        self.pgrad(w), 0, tag=node.scope + "/wgrad")
+            # the padded [kpad, Cout] storage is [tap][Cin][Cout] for its first rows = dgrad's B operand
+            self.contribute(x, x.size * 2,
+                            lambda p: self.L("b", "mcn_conv2d_dgrad_tc", d, gy, self.pbf16(w), p, 1,
+                                             self.conv_mode, 0, tag=node.scope + "/dgrad"),
+                            emit_acc=lambda p: self.L("b", "mcn_conv2d_dgrad_tc", d, gy, self.pbf16(w), p, 1,
+                                                      self.conv_mode, 1, tag=node.scope + "/dgrad+"))
         else:
-            if w.trainable:
+            if self._var_trains(w):
                 self.L("b", "mcn_conv2d_wgrad_direct", d, self.ccode, self.tbuf[x], gy, self.pgrad(w),
                        tag=node.scope + "/wgrad")
             self.contribute(x, x.size * self.csz,
@@ -760,10 +843,10 @@ class Plan(object):
         w = node.vars["w"]
         d = node.attrs["desc"]
         mult = node.attrs["mult"]
-        if "b" in node.vars:
+        if "b" in node.vars and self._var_trains(node.vars["b"]):
             self.L("b", "mcn_bias_grad", self.ccode, gy, y.size // y.shape[-1], y.shape[-1],
                    self.pgrad(node.vars["b"]), tag=node.scope + "/dbias")
-        if w.trainable:
+        if self._var_trains(w):
             self.L("b", "mcn_dwconv2d_bwd_filter", d, mult, self.ccode, self.tbuf[x], gy, self.pgrad(w),
                    tag=node.scope + "/dw_wgrad")
         self.contribute(x, x.size * self.csz,
@@ -775,18 +858,37 @@ class Plan(object):
         x, y = node.inputs[0], node.outputs[0]
         w = node.vars["w"]
         d = node.attrs["desc"]
-        if "b" in node.vars:
+        if "b" in node.vars and self._var_trains(node.vars["b"]):
             self.L("b", "mcn_bias_grad", self.ccode, gy, y.size // y.shape[-1], y.shape[-1],
                    self.pgrad(node.vars["b"]), tag=node.scope + "/dbias")
-        if w.trainable:
+        mixed = node.attrs["route"] in ("mixed", "direct")
+        if node.attrs["route"] == "direct":
+            kh, kw, ci_t, co_t = w.shape
+            w.gemm_dims = (kh * kw, ci_t, co_t)
+        if self._var_trains(w):
             # wgrad writes [tap][Cin_conv=co][Cout_conv=ci]; the variable is stored [tap][ci][co]
             tmp, h = self.talloc(w.storage_size * 4)
             self.L("b", "mcn_fill_f32", tmp, w.storage_size, 0.0, tag="zero")
-            self.L("b", "mcn_conv2d_wgrad_tc", d, gy, self.tbuf[x], tmp, self.conv_mode,
-                   tag=node.scope + "/wgrad")
+            if mixed:
+                self.L("b", "mcn_conv2d_wgrad_direct", d, self.ccode, gy, self.tbuf[x], tmp,
+                       tag=node.scope + "/wgrad")
+            else:
+                self.L("b", "mcn_conv2d_wgrad_tc", d, gy, self.tbuf[x], tmp, self.conv_mode,
+                       tag=node.scope + "/wgrad")
             taps, ci, co = w.gemm_dims
             self.L("b", "mcn_transpose_add_f32", tmp, taps, co, ci, self.pgrad(w), tag="wgrad_T")
             self.tfree(h)
+        if mixed:
+            # conv HWIO [tap][Cin_conv=co][Cout_conv=ci] is the transposed bf16 copy
+            if node.attrs["route"] == "direct":
+                self.contribute(x, x.size * self.csz,
+                                lambda p: self.L("b", "mcn_conv2d_fprop_direct", d, self.ccode, gy, 0,
+                                                 Ptr(node.attrs["wT"]), NULL, p, tag=node.scope + "/dgrad"))
+            else:
+                self.contribute(x, x.size * 2,
+                                lambda p: self.L("b", "mcn_conv2d_fprop_direct", d, self.ccode, gy, 1,
+                                                 self.pbf16t(w), NULL, p, tag=node.scope + "/dgrad"))
+            return
         # fprop of the underlying conv needs W_conv as [tap][Cout_conv=ci][Cin_conv=co] = stored layout
         self.contribute(x, x.size * 2,
                         lambda p: self.L("b", "mcn_conv2d_fprop_tc", d, gy, self.pbf16(w), NULL, p, 1,
@@ -810,9 +912,14 @@ class Plan(object):
         py = self.tbuf[y] if (res is not None and act != 0) else NULL
         # local sums double as dbeta / dgamma; without a trainable beta/gamma they go to scratch
         scratch = None
-        if "beta" in v and v["beta"].trainable and "gamma" in v and v["gamma"].trainable:
+        direct = ("beta" in v and self._var_trains(v["beta"]) and "gamma" in v
+                  and self._var_trains(v["gamma"]) and self._bn_var_uses[v["beta"]] == 1
+                  and self._bn_var_uses[v["gamma"]] == 1)
+        if direct:
             s1, s2 = self.pgrad(v["beta"]), self.pgrad(v["gamma"])
         else:
+            # variables shared by several BN nodes (D(real)/D(fake)) or not trained in this pass:
+            # this node's own sums go to scratch and are added to the gradients afterwards
             sp, scratch = self.talloc(2 * c * 4)
             self.L("b", "mcn_fill_f32", sp, 2 * c, 0.0, tag="zero")
             s1, s2 = sp, sp + c * 4
@@ -859,6 +966,10 @@ class Plan(object):
         if gh is not None:
             self.tfree(gh)
         if scratch is not None:
+            if "beta" in v and self._var_trains(v["beta"]):
+                self.L("b", "mcn_accumulate", 0, self.pgrad(v["beta"]), s1, c, tag="dbeta+=")
+            if "gamma" in v and self._var_trains(v["gamma"]):
+                self.L("b", "mcn_accumulate", 0, self.pgrad(v["gamma"]), s2, c, tag="dgamma+=")
             self.tfree(scratch)
 
     def _b_act(self, node, gy):

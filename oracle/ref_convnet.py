@@ -191,7 +191,9 @@ class ConvNet(object):
         if full not in self.var_meta:
             self.var_meta[full] = dict(kind=kind, trainable=trainable, block=self._curr_block,
                                        init=init, shape=tuple(int(s) for s in shape))
-            self.add_to_collection("block_{}/variables".format(self._curr_block), full)
+        coll = "block_{}/variables".format(self.var_meta[full]["block"])
+        if full not in self.collections.get(coll, ()):
+            self.add_to_collection(coll, full)
         if full not in self.vars:
             raise KeyError("oracle variable %s has no value: call set_variables first" % full)
         return self.vars[full]
@@ -213,6 +215,7 @@ class ConvNet(object):
         """X: float [N,H,W,C] in [0,1]; Y: int labels.  Returns the loss; fills self.d."""
         tf.reset_scopes()
         self._block_list = []
+        self.collections = {}       # every forward is a fresh build (block registry included)
         self.bn_updates = {}
         for name, t in self.vars.items():
             t.requires_grad_(self.var_meta.get(name, {}).get("trainable", True)
@@ -344,8 +347,10 @@ class ConvNet(object):
             y, bm, bv = ops.fused_batch_norm_train(x.t, gamma, beta, epsilon)
             if update:
                 m = self.batch_norm_decay
-                self.bn_updates[sc + "/mu"] = (m * mu + (1 - m) * bm).detach()
-                self.bn_updates[sc + "/sigma"] = (m * sigma + (1 - m) * bv).detach()
+                mu_prev = self.bn_updates.get(sc + "/mu", mu)
+                sigma_prev = self.bn_updates.get(sc + "/sigma", sigma)
+                self.bn_updates[sc + "/mu"] = (m * mu_prev + (1 - m) * bm).detach()
+                self.bn_updates[sc + "/sigma"] = (m * sigma_prev + (1 - m) * bv).detach()
         return OTensor(y)   # rounding happens after the fused activation/residual, as on device
 
     def upsampling_2d_layer(self, x, scale=2, out_shape=None, align_corners=False,

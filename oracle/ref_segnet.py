@@ -14,6 +14,7 @@ class SegNet(ConvNet):
     def forward(self, X, Y):
         tf.reset_scopes()
         self._block_list = []
+        self.collections = {}
         self.bn_updates = {}
         for name, t in self.vars.items():
             t.requires_grad_(self.var_meta.get(name, {}).get("trainable", True)

@@ -35,8 +35,23 @@ class OracleTrainer(object):
         loss = m.forward(X, Y)
         if self.ema is None:
             self.ema = {k: v.detach().clone() for k, v in m.vars.items()}
-        train = [k for k, meta in m.var_meta.items() if meta["trainable"] and meta["kind"] != "stat"]
-        grads = torch.autograd.grad(loss, [m.vars[k] for k in train], allow_unused=True)
+        if isinstance(loss, tuple):
+            # GAN: d(loss_d)/d(theta_D) and d(gsf*loss_g)/d(theta_G) from the same forward
+            # (optimizers_gan.py:56-58)
+            loss_d, loss_g = loss
+            vd, vg = m.variable_split()
+            td = [k for k in vd if m.var_meta[k]["trainable"] and m.var_meta[k]["kind"] != "stat"]
+            tg = [k for k in vg if m.var_meta[k]["trainable"] and m.var_meta[k]["kind"] != "stat"]
+            gsf = float(self.kw.get("generator_scaling_factor", 1.0))
+            gd = torch.autograd.grad(loss_d, [m.vars[k] for k in td], allow_unused=True, retain_graph=True)
+            gg = torch.autograd.grad(loss_g * gsf, [m.vars[k] for k in tg], allow_unused=True)
+            train = td + tg
+            grads = list(gd) + list(gg)
+            self.last_losses = (float(loss_d.detach()), float(loss_g.detach()))
+            loss = loss_d
+        else:
+            train = [k for k, meta in m.var_meta.items() if meta["trainable"] and meta["kind"] != "stat"]
+            grads = torch.autograd.grad(loss, [m.vars[k] for k in train], allow_unused=True)
         self.grads = {k: (g if g is not None else torch.zeros_like(m.vars[k])) for k, g in zip(train, grads)}
         if not update:
             return float(loss.detach())

@@ -79,3 +79,43 @@ def test_deeplabv3plus(have_reference_models, dtype):
     X = rng.uniform(size=[batch] + shape).astype(np.float32)
     Y = rng.integers(0, ncls + 1, size=[batch] + shape[:2]).astype(np.int32)    # 0 = ignore
     _check(pm, om, vals, X, Y, dtype, steps=2)
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_dcgan_simultaneous_update(have_reference_models, dtype):
+    """models/dcgan.py unchanged: D(real)/G/D(fake) with shared D variables, two losses, D and G
+    gradients from the same forward, one Adam update (optimizers_gan.py:56-58,110-120)."""
+    from myconvnet_b200.engine import Engine
+    from oracle import ref_convnet, ref_gan
+    from oracle.step import OracleTrainer
+    shape, latent, batch = [64, 64, 3], 100, 8
+    kw = dict(base_learning_rate=5e-4 * 32, momentum=0.5, generator_scaling_factor=2.0, label_smoothing=0.1)
+    facade = {"convnet": ref_convnet, "generative.gan": ref_gan}
+    pm, om, vals = _pair("models/dcgan.py", "DCGAN", shape, latent, batch, dtype, facade, **kw)
+    rng = np.random.default_rng(3)
+    X = rng.uniform(size=[batch] + shape).astype(np.float32)
+    Z = rng.uniform(-1, 1, size=(batch, latent)).astype(np.float32)
+    assert pm.generate.shape == (batch, 64, 64, 3)           # 4x4 seed (SURVEY Appendix D.1)
+    eng = Engine(pm, optimizer="adam", keep=[pm.generate, pm.logits_real, pm.logits_fake])
+    eng.set_variables(vals)
+    tr = OracleTrainer(om, optimizer="adam", batch_size=batch)
+    tol = 2e-3 if dtype == "f32" else 5e-2
+    # gradients of both passes on the first (identical-weights) step
+    eng.train_step(X, Z, update=False)
+    tr.step(X, Z, update=False)
+    assert rel_l2(eng.fetch(pm.generate), om.d["generate"].t.detach().numpy()) < (1e-4 if dtype == "f32" else 3e-2)
+    ld, lg = eng.last_losses
+    assert abs(ld - tr.last_losses[0]) < tol * abs(tr.last_losses[0]) + tol
+    assert abs(lg - tr.last_losses[1]) < tol * abs(tr.last_losses[1]) + tol
+    if dtype == "f32":
+        grads = eng.get_gradients()
+        errs = {k: rel_l2(grads[k], g.numpy()) for k, g in tr.grads.items() if float(g.norm()) > 1e-7}
+        worst = sorted(errs.items(), key=lambda kv: -kv[1])[:5]
+        assert worst[0][1] < 8e-2, worst       # LeakyReLU/ReLU kink sensitivity, see test_gpu_resnet
+    for _ in range(3):
+        eng.train_step(X, Z)
+        tr.step(X, Z)
+        ld, lg = eng.last_losses
+        assert np.isfinite(ld) and np.isfinite(lg)
+        assert abs(ld - tr.last_losses[0]) < 3 * tol * abs(tr.last_losses[0]) + 3 * tol, (ld, tr.last_losses)
+        assert abs(lg - tr.last_losses[1]) < 3 * tol * abs(tr.last_losses[1]) + 3 * tol, (lg, tr.last_losses)
