@@ -224,7 +224,7 @@ def main():
     warmup = max(args.warmup, 3)
     model, model_src = resnet50(IMG, NCLS, batch_size=args.batch, compute_dtype="bf16")
     eng = Engine(model, optimizer="nesterov", world_size=world, rank=rank, process_group=pg,
-                 use_cuda_graph=(world == 1 and not args.no_graph), seed=0, fetch_pred=False)
+                 use_cuda_graph=(not args.no_graph), seed=0, fetch_pred=False)
     rng = np.random.default_rng(1234 + rank)
     X = torch.from_numpy(rng.uniform(size=[args.batch] + IMG).astype(np.float32)).pin_memory()
     Y = torch.from_numpy(rng.integers(0, NCLS, size=args.batch).astype(np.int32)).pin_memory()
@@ -268,6 +268,10 @@ def main():
         t = torch.tensor([ms, ms_e2e], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(t[0]), float(t[1])
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     # ---- roofline of the dominant kernel class (live CUDA-event timing of every launch)
@@ -315,7 +319,7 @@ def main():
                    "global_batch": gb, "parallelism": "dp%d" % world, "model_source": model_src,
                    "l2_flush": "not needed: one step touches %.1f GB of HBM per GPU (>> 126 MB L2)"
                                % (eng.plan.arena_bytes / 1e9),
-                   "cuda_graph": bool(eng.use_cuda_graph and world == 1)},
+                   "cuda_graph": bool(eng.use_cuda_graph)},
         "e2e": {"value": gb / (ms_e2e * 1e-3), "unit": "img/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(X.numel() * 4 + Y.numel() * 4 + 64), "d2h_bytes_per_step": 8},
         "gpu_launches": eager_launches * args.steps,

@@ -329,7 +329,7 @@ class Engine(object):
         if X is not None:
             self.load_inputs(X=X, Y=Y)
         self._set_hyper(lr_multiplier)
-        if self.use_cuda_graph and self.world == 1 and update and self._eager_steps >= 1:
+        if self.use_cuda_graph and update and self._eager_steps >= 1:
             if self._graph_exec is None:
                 self._capture(update)
             self._graph_exec.replay()
