@@ -202,6 +202,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--profile-json", default=None, help="write the per-kernel-class table here")
+    ap.add_argument("--conv-mode", type=int, default=None, help="0 box, 1 im2col, 2 halo where eligible")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -224,7 +225,8 @@ def main():
     warmup = max(args.warmup, 3)
     model, model_src = resnet50(IMG, NCLS, batch_size=args.batch, compute_dtype="bf16")
     eng = Engine(model, optimizer="nesterov", world_size=world, rank=rank, process_group=pg,
-                 use_cuda_graph=(not args.no_graph), seed=0, fetch_pred=False)
+                 use_cuda_graph=(not args.no_graph), seed=0, fetch_pred=False,
+                 **({"conv_mode": args.conv_mode} if args.conv_mode is not None else {}))
     rng = np.random.default_rng(1234 + rank)
     X = torch.from_numpy(rng.uniform(size=[args.batch] + IMG).astype(np.float32)).pin_memory()
     Y = torch.from_numpy(rng.integers(0, NCLS, size=args.batch).astype(np.int32)).pin_memory()

@@ -418,7 +418,7 @@ extern "C" int mcn_bn_stats(int dtype, const void* x, long long rows, int C, dou
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MCN_DISPATCH_DTYPE(dtype, T, {
     SlabLaunch L;
-    if (plan_slab<T>(rows, C, &L, 6 * num_sms())) {
+    if (plan_slab<T>(rows, C, &L, 3 * num_sms())) {
       size_t smem = 2 * (size_t)L.rowlanes * L.slab_v * Vec16<T>::N * sizeof(float);
       bn_stats_kernel<T><<<L.grid, 256, smem, st>>>(static_cast<const T*>(x), rows, C, L.slab_v,
                                                     L.rowlanes, sums);
@@ -447,7 +447,7 @@ static int bn_apply_impl(int dtype, const void* x, long long rows, int C, const 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MCN_DISPATCH_DTYPE(dtype, T, {
     ChanLaunch L;
-    if (plan<T>(rows, C, &L, 8)) {
+    if (plan<T>(rows, C, &L, 2)) {
       bn_apply_kernel<T, kVar><<<L.grid, L.block, 0, st>>>(
           static_cast<const T*>(x), rows * L.cv, L.cv, mean, is_or_var, eps, gamma, beta,
           static_cast<const T*>(residual), act, alpha, static_cast<T*>(y));
@@ -485,7 +485,7 @@ extern "C" int mcn_bn_bwd_reduce(int dtype, const void* dy, const void* x, const
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MCN_DISPATCH_DTYPE(dtype, T, {
     SlabLaunch L;
-    if (plan_slab<T>(rows, C, &L, 6 * num_sms())) {
+    if (plan_slab<T>(rows, C, &L, 3 * num_sms())) {
       size_t smem = 2 * (size_t)L.rowlanes * L.slab_v * Vec16<T>::N * sizeof(float);
       bn_bwd_reduce_kernel<T><<<L.grid, 256, smem, st>>>(
           static_cast<const T*>(dy), static_cast<const T*>(x), static_cast<const T*>(y), rows, C,
@@ -511,7 +511,7 @@ extern "C" int mcn_bn_bwd_apply(int dtype, const void* dy, const void* x, const 
   const float inv_count = (float)(1.0 / count);
   MCN_DISPATCH_DTYPE(dtype, T, {
     ChanLaunch L;
-    if (plan<T>(rows, C, &L, 12, 256)) {
+    if (plan<T>(rows, C, &L, 3, 256)) {
       bn_bwd_apply_kernel<T><<<L.grid, L.block, 0, st>>>(
           static_cast<const T*>(dy), static_cast<const T*>(x), static_cast<const T*>(y),
           rows * L.cv, L.cv, mean, invstd, gamma, beta, act, act_alpha, sum_dz, sum_dz_xhat,

@@ -21,6 +21,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "mcn_common.cuh"
@@ -98,16 +99,123 @@ __device__ __forceinline__ bool row_coords(const TileGeom& g, const PixelTile& t
   return m < g.m_total;
 }
 
+// ------------------------------------------------------------------ shared epilogue
+struct EpiArgs {
+  void* out;
+  const float* bias;
+  int out_f32, vec_ok, accumulate, block_n, n_total;
+  int debug;   // bit0: skip stores, bit1: skip MMA issue, bit2: skip TMEM loads (timing experiments)
+};
+
+// One output tile: wait for the accumulator, TMEM -> registers -> global.  Each thread owns one
+// output pixel (row) and walks its channels 64 at a time: 64 bf16 = one full 128-byte line written
+// with four 32-byte stores (fp32 output: eight).  The TMEM buffer is handed back to the MMA warp
+// right after the last tcgen05.ld, before the stores drain.
+__device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t tmem_acc, int quad, int lane,
+                                              bool valid, long long off, int n_t,
+                                              uint64_t* tmem_full_bar, uint32_t tph,
+                                              uint64_t* tmem_empty_bar) {
+      // bf16 accumulate (dx += dgrad): the previous values of a 64-channel chunk are fetched
+  // with four back-to-back 32-byte loads one chunk AHEAD (the first one before the
+  // accumulator is even ready), so the global-load latency hides behind the MMAs.
+  const bool acc_bf16 = e.accumulate && !e.out_f32 && e.vec_ok;
+  uint32_t old[32];
+  __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(e.out) + off;
+  auto prefetch_old = [&](int c0) {
+    const int col0 = n_t * e.block_n + c0;
+    if (valid && col0 + 64 <= e.n_total) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        ptx::ld_global_v8(obase + col0 + j * 16, *reinterpret_cast<uint32_t(*)[8]>(&old[j * 8]));
+    }
+  };
+  if (acc_bf16) prefetch_old(0);
+  ptx::mbar_wait(tmem_full_bar, tph);
+  ptx::tc_fence_after();
+  for (int c0 = 0; c0 < e.block_n; c0 += 64) {
+    uint32_t r[64];
+    const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quad * 32) << 16) +
+                           static_cast<uint32_t>(c0);
+    if (!(e.debug & 4)) {
+      ptx::tmem_ld_32x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+      ptx::tmem_ld_32x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+      ptx::tmem_ld_wait();
+    }
+    if (c0 + 64 >= e.block_n) {
+      // last read of this accumulator: hand the TMEM buffer back before the stores drain
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tmem_empty_bar);
+    }
+    const int col0 = n_t * e.block_n + c0;
+    const bool fullw = e.vec_ok && (col0 + 64 <= e.n_total);
+    if (!valid || col0 >= e.n_total || (e.debug & 1)) continue;
+    if (e.bias != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j)
+        if (fullw || col0 + j < e.n_total)
+          r[j] = __float_as_uint(__uint_as_float(r[j]) + e.bias[col0 + j]);
+    }
+    if (e.out_f32) {
+      float* o = reinterpret_cast<float*>(e.out) + off + col0;
+      if (fullw) {
+#pragma unroll
+        for (int j = 0; j < 64; j += 8) {
+          uint32_t v[8];
+          if (e.accumulate) {
+            ptx::ld_global_v8(o + j, v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(r[j + e]));
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = r[j + e];
+          }
+          ptx::st_global_v8(o + j, v);
+        }
+      } else {
+        for (int j = 0; j < 64; ++j)
+          if (col0 + j < e.n_total)
+            o[j] = __uint_as_float(r[j]) + (e.accumulate ? o[j] : 0.f);
+      }
+    } else {
+      __nv_bfloat16* o = obase + col0;
+      if (fullw) {
+        uint32_t v[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          float lo = __uint_as_float(r[2 * e]), hi = __uint_as_float(r[2 * e + 1]);
+          if (acc_bf16) {
+            lo += __uint_as_float(old[e] << 16);
+            hi += __uint_as_float(old[e] & 0xFFFF0000u);
+          }
+          __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+          v[e] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        if (acc_bf16 && c0 + 64 < e.block_n) prefetch_old(c0 + 64);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          ptx::st_global_v8(o + j * 16, *reinterpret_cast<uint32_t(*)[8]>(&v[j * 8]));
+      } else {
+        for (int j = 0; j < 64; ++j)
+          if (col0 + j < e.n_total) {
+            float f = __uint_as_float(r[j]);
+            if (e.accumulate) f += __bfloat162float(o[j]);
+            o[j] = __float2bfloat16_rn(f);
+          }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ fprop / dgrad kernel
 struct GemmConvArgs {
   CUtensorMap mapA[4];
   CUtensorMap mapB;
   TileGeom g;
-  int taps, k_chunks, ksteps_last, block_n, n_total, stages, tiles_n, tmem_cols, total_tiles;
+  int taps, k_chunks, ksteps_last, block_n, stages, tiles_n, tmem_cols, total_tiles;
   long long out_sn, out_sh, out_sw;  // element strides of the output pixel grid
-  void* out;
-  const float* bias;
-  int out_f32, vec_ok, accumulate;
+  EpiArgs e;
   TapTab tab;
 };
 
@@ -235,95 +343,198 @@ gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
       int n, p, q;
       const bool valid = row_coords(args.g, tile, row, n, p, q);
       const long long off = valid ? (n * args.out_sn + p * args.out_sh + q * args.out_sw) : 0;
-      // bf16 accumulate (dx += dgrad): the previous values of a 64-channel chunk are fetched
-      // with four back-to-back 32-byte loads one chunk AHEAD (the first one before the
-      // accumulator is even ready), so the global-load latency hides behind the MMAs.
-      const bool acc_bf16 = args.accumulate && !args.out_f32 && args.vec_ok;
-      uint32_t old[32];
-      __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(args.out) + off;
-      auto prefetch_old = [&](int c0) {
-        const int col0 = n_t * args.block_n + c0;
-        if (valid && col0 + 64 <= args.n_total) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            ptx::ld_global_v8(obase + col0 + j * 16, *reinterpret_cast<uint32_t(*)[8]>(&old[j * 8]));
-        }
-      };
-      if (acc_bf16) prefetch_old(0);
-      ptx::mbar_wait(&tmem_full[buf], tph);
-      ptx::tc_fence_after();
-      for (int c0 = 0; c0 < args.block_n; c0 += 64) {
-        uint32_t r[64];
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
-                               static_cast<uint32_t>(buf * args.block_n + c0);
-        ptx::tmem_ld_32x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
-        ptx::tmem_ld_32x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
-        ptx::tmem_ld_wait();
-        if (c0 + 64 >= args.block_n) {
-          // last read of this accumulator: hand the TMEM buffer back before the stores drain
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&tmem_empty[buf]);
-        }
-        const int col0 = n_t * args.block_n + c0;
-        const bool fullw = args.vec_ok && (col0 + 64 <= args.n_total);
-        if (!valid || col0 >= args.n_total) continue;
-        if (args.bias != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 64; ++j)
-            if (fullw || col0 + j < args.n_total)
-              r[j] = __float_as_uint(__uint_as_float(r[j]) + args.bias[col0 + j]);
-        }
-        if (args.out_f32) {
-          float* o = reinterpret_cast<float*>(args.out) + off + col0;
-          if (fullw) {
-#pragma unroll
-            for (int j = 0; j < 64; j += 8) {
-              uint32_t v[8];
-              if (args.accumulate) {
-                ptx::ld_global_v8(o + j, v);
-#pragma unroll
-                for (int e = 0; e < 8; ++e)
-                  v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(r[j + e]));
-              } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = r[j + e];
-              }
-              ptx::st_global_v8(o + j, v);
-            }
-          } else {
-            for (int j = 0; j < 64; ++j)
-              if (col0 + j < args.n_total)
-                o[j] = __uint_as_float(r[j]) + (args.accumulate ? o[j] : 0.f);
-          }
-        } else {
-          __nv_bfloat16* o = obase + col0;
-          if (fullw) {
-            uint32_t v[32];
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              float lo = __uint_as_float(r[2 * e]), hi = __uint_as_float(r[2 * e + 1]);
-              if (acc_bf16) {
-                lo += __uint_as_float(old[e] << 16);
-                hi += __uint_as_float(old[e] & 0xFFFF0000u);
-              }
-              __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-              v[e] = *reinterpret_cast<uint32_t*>(&h);
-            }
-            if (acc_bf16 && c0 + 64 < args.block_n) prefetch_old(c0 + 64);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              ptx::st_global_v8(o + j * 16, *reinterpret_cast<uint32_t(*)[8]>(&v[j * 8]));
-          } else {
-            for (int j = 0; j < 64; ++j)
-              if (col0 + j < args.n_total) {
-                float f = __uint_as_float(r[j]);
-                if (args.accumulate) f += __bfloat162float(o[j]);
-                o[j] = __float2bfloat16_rn(f);
-              }
-          }
+      epilogue_tile(args.e, tmem_base + static_cast<uint32_t>(buf * args.e.block_n), quad, lane, valid,
+                    off, n_t, &tmem_full[buf], tph, &tmem_empty[buf]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, static_cast<uint32_t>(args.tmem_cols));
+}
+
+// ------------------------------------------------------------------ halo kernel (k x k, stride 1)
+// For stride-1 k x k convolutions the im2col feed re-reads every input pixel kh*kw times from L2.
+// Here an output tile is 16 rows x 8 columns of one image and its INPUT halo
+// ((16+(kh-1)dh) x (8+(kw-1)dw) pixels x 64 channels) is brought in by ONE TMA box per channel
+// chunk; each filter tap is then just a different start address into the same shared-memory
+// tile: 8 consecutive pixels of an output row are 8 consecutive 128-byte rows (one swizzle
+// group) and successive output rows are SBO = halo_width*128 bytes apart.  Activation traffic
+// drops from kh*kw x to ~1.4 x; weight tiles stream through their own ring (or stay resident for
+// the whole persistent CTA when all taps fit: the 64->64 3x3 layers).
+struct HaloArgs {
+  CUtensorMap mapA;
+  CUtensorMap mapB;
+  EpiArgs e;
+  int taps, k_chunks, tiles_n, tmem_cols, total_tiles;
+  int tiles_w, tiles_h;
+  int Wo, Ho, Nb;
+  int hwb, hhb;          // halo box extent in pixels
+  int org_w, org_h;      // input coordinate of the halo origin relative to the tile origin
+  int a_stages, b_stages, halo_stride, b_stationary, use_base_offset;
+  long long out_sn, out_sh, out_sw;
+  int brow[kMaxTaps];
+  short toff[kMaxTaps];  // halo row (pixel) offset of each tap
+};
+
+__global__ void __launch_bounds__(224, 1)
+halo_conv_kernel(const __grid_constant__ HaloArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t b_bytes = static_cast<uint32_t>(args.e.block_n) * 128u;
+  const int nb_slots = args.b_stationary ? args.taps * args.k_chunks : args.b_stages;
+  uint8_t* smemA = smem;
+  uint8_t* smemB = smem + static_cast<size_t>(args.a_stages) * args.halo_stride;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smemB + static_cast<size_t>(nb_slots) * b_bytes);
+  uint64_t* full_a = bars;
+  uint64_t* empty_a = full_a + args.a_stages;
+  uint64_t* full_b = empty_a + args.a_stages;      // [b_stages] (stationary: [0] only)
+  uint64_t* empty_b = full_b + args.b_stages;
+  uint64_t* tmem_full = empty_b + args.b_stages;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  const int total_tiles = args.total_tiles;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&args.mapA);
+    ptx::prefetch_tmap(&args.mapB);
+    for (int s = 0; s < args.a_stages; ++s) {
+      ptx::mbar_init(&full_a[s], 1);
+      ptx::mbar_init(&empty_a[s], 1);
+    }
+    for (int s = 0; s < args.b_stages; ++s) {
+      ptx::mbar_init(&full_b[s], 1);
+      ptx::mbar_init(&empty_b[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&tmem_full[b], 1);
+      ptx::mbar_init(&tmem_empty[b], 4);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, static_cast<uint32_t>(args.tmem_cols));
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int tiles_per_img = args.tiles_w * args.tiles_h;
+
+  if (warp == 0) {
+    // ---------------- activation (halo) producer ----------------
+    if (ptx::elect_one()) {
+      const uint32_t a_tx = static_cast<uint32_t>(args.hwb * args.hhb) * 128u;
+      int ita = 0;
+      for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x) {
+        const int m = tile_id / args.tiles_n;
+        const int n = m / tiles_per_img;
+        const int r = m - n * tiles_per_img;
+        const int h0 = (r / args.tiles_w) * 16, w0 = (r % args.tiles_w) * 8;
+        for (int kc = 0; kc < args.k_chunks; ++kc, ++ita) {
+          const int s = ita % args.a_stages;
+          const uint32_t ph = static_cast<uint32_t>(ita / args.a_stages) & 1u;
+          ptx::mbar_wait(&empty_a[s], ph ^ 1u);
+          ptx::mbar_expect_tx(&full_a[s], a_tx);
+          ptx::tma_load_4d(&args.mapA, &full_a[s], smemA + static_cast<size_t>(s) * args.halo_stride,
+                           kc * 64, w0 + args.org_w, h0 + args.org_h, n);
         }
       }
+    }
+  } else if (warp == 2) {
+    // ---------------- weight producer ----------------
+    if (ptx::elect_one()) {
+      if (args.b_stationary) {
+        // every (k-chunk, tap) weight tile fits: load once, keep for all tiles of this CTA
+        const int n_t = blockIdx.x % args.tiles_n;   // tiles_n == 1 in this mode
+        ptx::mbar_expect_tx(&full_b[0], static_cast<uint32_t>(nb_slots) * b_bytes);
+        for (int kc = 0; kc < args.k_chunks; ++kc)
+          for (int t = 0; t < args.taps; ++t)
+            ptx::tma_load_2d(&args.mapB, &full_b[0],
+                             smemB + static_cast<size_t>(kc * args.taps + t) * b_bytes, kc * 64,
+                             args.brow[t] + n_t * args.e.block_n);
+      } else {
+        int itb = 0;
+        for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x) {
+          const int n_t = tile_id % args.tiles_n;
+          for (int kc = 0; kc < args.k_chunks; ++kc)
+            for (int t = 0; t < args.taps; ++t, ++itb) {
+              const int s = itb % args.b_stages;
+              const uint32_t ph = static_cast<uint32_t>(itb / args.b_stages) & 1u;
+              ptx::mbar_wait(&empty_b[s], ph ^ 1u);
+              ptx::mbar_expect_tx(&full_b[s], b_bytes);
+              ptx::tma_load_2d(&args.mapB, &full_b[s], smemB + static_cast<size_t>(s) * b_bytes,
+                               kc * 64, args.brow[t] + n_t * args.e.block_n);
+            }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    const uint32_t idesc = ptx::make_idesc_bf16(128, args.e.block_n, 0, 0);
+    const uint32_t sbo = static_cast<uint32_t>(args.hwb) * 128u;
+    int ita = 0, itb = 0, lt = 0;
+    if (args.b_stationary) ptx::mbar_wait(&full_b[0], 0);
+    for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x, ++lt) {
+      const int buf = lt & 1;
+      const uint32_t tph = static_cast<uint32_t>(lt >> 1) & 1u;
+      ptx::mbar_wait(&tmem_empty[buf], tph ^ 1u);
+      ptx::tc_fence_after();
+      const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * args.e.block_n);
+      int kit = 0;
+      for (int kc = 0; kc < args.k_chunks; ++kc, ++ita) {
+        const int sa = ita % args.a_stages;
+        ptx::mbar_wait(&full_a[sa], static_cast<uint32_t>(ita / args.a_stages) & 1u);
+        ptx::tc_fence_after();
+        const uint32_t a_base = ptx::smem_u32(smemA + static_cast<size_t>(sa) * args.halo_stride);
+        for (int t = 0; t < args.taps; ++t, ++itb, ++kit) {
+          int sb;
+          if (args.b_stationary) {
+            sb = kc * args.taps + t;
+          } else {
+            sb = itb % args.b_stages;
+            ptx::mbar_wait(&full_b[sb], static_cast<uint32_t>(itb / args.b_stages) & 1u);
+            ptx::tc_fence_after();
+          }
+          if (ptx::elect_one()) {
+            const uint32_t a_addr = a_base + static_cast<uint32_t>(args.toff[t]) * 128u;
+            const uint32_t b_addr = ptx::smem_u32(smemB + static_cast<size_t>(sb) * b_bytes);
+            const uint32_t bo = args.use_base_offset ? ((a_addr >> 7) & 7u) : 0u;
+            for (int k = 0; k < ((args.e.debug & 2) ? 0 : 4); ++k) {
+              const uint64_t ad = ptx::make_smem_desc(a_addr + k * 32, 16, sbo, bo);
+              const uint64_t bd = ptx::make_smem_desc(b_addr + k * 32, 16, 1024);
+              ptx::umma_bf16(tmem_d, ad, bd, idesc, (kit | k) != 0 ? 1u : 0u);
+            }
+            if (!args.b_stationary) ptx::umma_commit(&empty_b[sb]);
+            if (t == args.taps - 1) ptx::umma_commit(&empty_a[sa]);
+            if (kc == args.k_chunks - 1 && t == args.taps - 1) ptx::umma_commit(&tmem_full[buf]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ---------------- epilogue (warps 3..6) ----------------
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    int lt = 0;
+    for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x, ++lt) {
+      const int buf = lt & 1;
+      const uint32_t tph = static_cast<uint32_t>(lt >> 1) & 1u;
+      const int n_t = tile_id % args.tiles_n;
+      const int m = tile_id / args.tiles_n;
+      const int n = m / tiles_per_img;
+      const int r = m - n * tiles_per_img;
+      const int p = (r / args.tiles_w) * 16 + (row >> 3);
+      const int q = (r % args.tiles_w) * 8 + (row & 7);
+      const bool valid = p < args.Ho && q < args.Wo;
+      const long long off = valid ? (n * args.out_sn + p * args.out_sh + q * args.out_sw) : 0;
+      epilogue_tile(args.e, tmem_base + static_cast<uint32_t>(buf * args.e.block_n), quad, lane, valid,
+                    off, n_t, &tmem_full[buf], tph, &tmem_empty[buf]);
     }
   }
 
@@ -639,6 +850,7 @@ int smem_optin_limit() {
 }
 
 int launch_gemm_conv(GemmConvArgs& a, int tiles_m, cudaStream_t st) {
+  a.e.block_n = a.block_n;
   const uint32_t stage_bytes = kABytes + a.block_n * 128;
   // one persistent CTA per SM: the whole shared memory is the TMA ring
   int stages = std::min(8, static_cast<int>((200 * 1024) / stage_bytes));
@@ -661,6 +873,97 @@ int launch_gemm_conv(GemmConvArgs& a, int tiles_m, cudaStream_t st) {
   return after_launch("gemm_conv_kernel");
 }
 
+// Halo mode (a_mode 2): stride-1 k x k convolution whose spatial size makes 16x8 tiles efficient.
+// `flip` selects the dgrad tap order (correlation with mirrored taps).
+bool halo_eligible(int cin, int kh, int kw, int sh, int sw, int dh, int dw, int Ho, int Wo) {
+  if (sh != 1 || sw != 1 || (kh == 1 && kw == 1) || cin % 64 != 0 || kh * kw > kMaxTaps) return false;
+  const int hwb = 8 + (kw - 1) * dw, hhb = 16 + (kh - 1) * dh;
+  if (hwb > 256 || hhb > 256 || hwb * hhb * 128 > 40 * 1024) return false;
+  // tile efficiency: fraction of the 16x8 tiles that is real output.  Measured on B200
+  // (profiles/r01_halo_vs_im2col.txt): the halo feed wins on the large maps (56x56: 187 -> 144 us)
+  // and loses below ~48x48, where the im2col feed's exact 128-pixel tiles matter more.
+  const double eff = (double)(Ho * Wo) / ((double)((Ho + 15) / 16 * 16) * ((Wo + 7) / 8 * 8));
+  return eff >= 0.85 && Ho * Wo >= 48 * 48;
+}
+
+int launch_halo(const void* in, int C_in, int W_in, int H_in, int N, const void* wmat, int taps_rows,
+                int n_total, int kh, int kw, int dh, int dw, int org_h, int org_w, bool flip,
+                int Ho, int Wo, void* out, int out_f32, const float* bias, int accumulate,
+                cudaStream_t st) {
+  HaloArgs a;
+  std::memset(&a, 0, sizeof(a));
+  int rc;
+  a.hwb = 8 + (kw - 1) * dw;
+  a.hhb = 16 + (kh - 1) * dh;
+  if ((rc = encode_nhwc(&a.mapA, in, C_in, W_in, H_in, N, a.hwb, a.hhb, 1))) return rc;
+  a.e.block_n = pick_block_n(n_total);
+  a.tiles_n = (n_total + a.e.block_n - 1) / a.e.block_n;
+  a.taps = kh * kw;
+  a.k_chunks = C_in / 64;
+  if ((rc = encode_matrix(&a.mapB, wmat, (long long)a.taps * taps_rows, C_in, a.e.block_n))) return rc;
+  a.e.n_total = n_total;
+  a.e.out = out;
+  a.e.out_f32 = out_f32;
+  a.e.bias = bias;
+  a.e.accumulate = accumulate;
+  a.e.vec_ok = (n_total % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 32 == 0);
+  a.Wo = Wo;
+  a.Ho = Ho;
+  a.Nb = N;
+  a.tiles_w = (Wo + 7) / 8;
+  a.tiles_h = (Ho + 15) / 16;
+  a.org_w = org_w;
+  a.org_h = org_h;
+  a.out_sw = n_total;
+  a.out_sh = (long long)Wo * n_total;
+  a.out_sn = (long long)Ho * Wo * n_total;
+  for (int r = 0; r < kh; ++r)
+    for (int s2 = 0; s2 < kw; ++s2) {
+      const int t = r * kw + s2;
+      a.brow[t] = t * taps_rows;
+      const int rr = flip ? (kh - 1 - r) : r, ss = flip ? (kw - 1 - s2) : s2;
+      a.toff[t] = (short)(rr * dh * a.hwb + ss * dw);
+    }
+  const uint32_t b_bytes = a.e.block_n * 128;
+  a.halo_stride = ((a.hwb * a.hhb * 128) + 1023) / 1024 * 1024;
+  const long long b_all = (long long)a.taps * a.k_chunks * b_bytes;
+  a.b_stationary = (a.tiles_n == 1 && b_all <= 100 * 1024) ? 1 : 0;
+  a.a_stages = 3;
+  const long long budget = 200 * 1024 - (long long)a.a_stages * a.halo_stride;
+  if (a.b_stationary) {
+    a.b_stages = 1;
+  } else {
+    a.b_stages = (int)std::max<long long>(2, std::min<long long>(8, budget / b_bytes));
+  }
+  static int use_bo = -1;
+  if (use_bo < 0) {
+    const char* e = getenv("MCN_HALO_BASE_OFFSET");
+    use_bo = (e && e[0] == '1') ? 1 : 0;
+  }
+  a.use_base_offset = use_bo;
+  {
+    const char* e = getenv("MCN_DEBUG_SKIP");
+    a.e.debug = e ? atoi(e) : 0;
+  }
+  a.tmem_cols = 2 * tmem_cols_for(a.e.block_n);
+  a.total_tiles = a.tiles_w * a.tiles_h * N * a.tiles_n;
+  const int nb_slots = a.b_stationary ? a.taps * a.k_chunks : a.b_stages;
+  size_t smem = (size_t)a.a_stages * a.halo_stride + (size_t)nb_slots * b_bytes +
+                (2 * a.a_stages + 2 * a.b_stages + 4) * 8 + 16 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(halo_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             smem_optin_limit()) != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(halo_conv_kernel) failed");
+      return MCN_ECUDA;
+    }
+    configured = true;
+  }
+  dim3 grid((unsigned)std::min(a.total_tiles, num_sms()));
+  halo_conv_kernel<<<grid, 224, smem, st>>>(a);
+  return after_launch("halo_conv_kernel");
+}
+
 bool tc_shape_ok(const mcn_conv_desc* d) {
   return d->Cin % 8 == 0 && d->Cout % 8 == 0 && d->kh * d->kw <= kMaxTaps;
 }
@@ -677,6 +980,13 @@ extern "C" int mcn_conv2d_fprop_tc(const mcn_conv_desc* d, const void* x, const 
   MCN_REQUIRE(d->Cin % 8 == 0, "fprop_tc: Cin=%d must be a multiple of 8 (16-byte TMA rows)", d->Cin);
   MCN_REQUIRE(d->kh * d->kw <= kMaxTaps, "fprop_tc: too many taps");
   const bool pointwise = d->kh == 1 && d->kw == 1 && d->sh == 1 && d->sw == 1;
+  if (a_mode == 2) {
+    if (halo_eligible(d->Cin, d->kh, d->kw, d->sh, d->sw, d->dh, d->dw, d->Ho, d->Wo))
+      return launch_halo(x, d->Cin, d->W, d->H, d->N, w_ohwi, d->Cout, d->Cout, d->kh, d->kw, d->dh,
+                         d->dw, -d->pad_t, -d->pad_l, false, d->Ho, d->Wo, y, y_dtype == MCN_F32, bias,
+                         accumulate, static_cast<cudaStream_t>(stream));
+    a_mode = 1;
+  }
   if (a_mode == 1 && (d->Cin % 64 != 0 || pointwise)) a_mode = 0;
   MCN_REQUIRE(a_mode == 1 || (d->sh == 1 && d->sw == 1) || (d->kh == 1 && d->kw == 1),
               "fprop_tc: box mode supports stride 1 (or 1x1 kernels) only");
@@ -742,12 +1052,12 @@ extern "C" int mcn_conv2d_fprop_tc(const mcn_conv_desc* d, const void* x, const 
     int rem = d->Cin - (a.k_chunks - 1) * 64;
     a.ksteps_last = (rem + 15) / 16;
   }
-  a.n_total = d->Cout;
-  a.out = y;
-  a.out_f32 = (y_dtype == MCN_F32);
-  a.bias = bias;
-  a.vec_ok = (d->Cout % 16 == 0) && (reinterpret_cast<uintptr_t>(y) % 32 == 0);
-  a.accumulate = accumulate;
+  a.e.n_total = d->Cout;
+  a.e.out = y;
+  a.e.out_f32 = (y_dtype == MCN_F32);
+  a.e.bias = bias;
+  a.e.vec_ok = (d->Cout % 16 == 0) && (reinterpret_cast<uintptr_t>(y) % 32 == 0);
+  a.e.accumulate = accumulate;
   for (int r = 0; r < d->kh; ++r)
     for (int s = 0; s < d->kw; ++s) {
       int t = r * d->kw + s;
@@ -848,12 +1158,12 @@ static int dgrad_phase(const mcn_conv_desc* d, const void* dy, const void* w_hwi
     int rem = d->Cout - (a.k_chunks - 1) * 64;
     a.ksteps_last = (rem + 15) / 16;
   }
-  a.n_total = d->Cin;
-  a.out = static_cast<uint8_t*>(dx) + ((size_t)ph * d->W + pw) * d->Cin * esz;
-  a.out_f32 = (dx_dtype == MCN_F32);
-  a.bias = nullptr;
-  a.vec_ok = (d->Cin % 16 == 0) && (reinterpret_cast<uintptr_t>(a.out) % 32 == 0);
-  a.accumulate = accumulate;
+  a.e.n_total = d->Cin;
+  a.e.out = static_cast<uint8_t*>(dx) + ((size_t)ph * d->W + pw) * d->Cin * esz;
+  a.e.out_f32 = (dx_dtype == MCN_F32);
+  a.e.bias = nullptr;
+  a.e.vec_ok = (d->Cin % 16 == 0) && (reinterpret_cast<uintptr_t>(a.e.out) % 32 == 0);
+  a.e.accumulate = accumulate;
   for (int t = 0; t < nt; ++t) {
     a.tab.brow[t] = tap_id[t] * d->Cin;
     a.tab.map[t] = 0;
@@ -876,6 +1186,14 @@ extern "C" int mcn_conv2d_dgrad_tc(const mcn_conv_desc* d, const void* dy, const
   MCN_REQUIRE(d->kh * d->kw <= kMaxTaps, "dgrad_tc: too many taps");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t esz = (dx_dtype == MCN_F32) ? 4 : 2;
+  if (a_mode == 2) {
+    // stride-1 dgrad = correlation of dy with the mirrored taps; halo origin pad - (k-1)*d
+    if (halo_eligible(d->Cout, d->kh, d->kw, d->sh, d->sw, d->dh, d->dw, d->H, d->W))
+      return launch_halo(dy, d->Cout, d->Wo, d->Ho, d->N, w_hwio, d->Cin, d->Cin, d->kh, d->kw, d->dh,
+                         d->dw, d->pad_t - (d->kh - 1) * d->dh, d->pad_l - (d->kw - 1) * d->dw, true,
+                         d->H, d->W, dx, dx_dtype == MCN_F32, nullptr, accumulate, st);
+    a_mode = 1;
+  }
   // phases without a contributing tap (e.g. 1x1 stride 2) stay zero
   bool any_empty = false;
   for (int ph = 0; ph < d->sh && !any_empty; ++ph)
@@ -906,6 +1224,7 @@ extern "C" int mcn_conv2d_wgrad_tc(const mcn_conv_desc* d, const void* x, const 
                                    float* dw, int a_mode, void* stream) {
   MCN_REQUIRE(d && x && dy && dw, "wgrad_tc: null argument");
   MCN_REQUIRE(d->Cin % 8 == 0 && d->Cout % 8 == 0, "wgrad_tc: channels must be multiples of 8");
+  if (a_mode == 2) a_mode = 1;   // no halo variant of wgrad yet
   MCN_REQUIRE(d->kh * d->kw <= kMaxTaps, "wgrad_tc: too many taps");
   const bool pointwise = d->kh == 1 && d->kw == 1 && d->sh == 1 && d->sw == 1;
   if (a_mode == 1 && (d->Cin % 64 != 0 || pointwise)) a_mode = 0;

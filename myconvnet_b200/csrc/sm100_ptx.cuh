@@ -173,8 +173,8 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 //   K-major  operand: rows (M/N) at 128 B pitch, 8-row groups at SBO; LBO unused (encoded 1).
 //   MN-major operand: 64-element MN atoms at LBO, 8-row K groups at SBO.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes,
-                                                   uint32_t sbo_bytes) {
-  uint64_t d = 0;
+                                                   uint32_t sbo_bytes, uint32_t base_offset = 0) {
+  uint64_t d = static_cast<uint64_t>(base_offset & 7u) << 49;
   d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;

@@ -47,7 +47,7 @@ def draw_initial_value(var, rng):
 
 
 class Engine(object):
-    def __init__(self, model, optimizer="nesterov", keep=(), seed=0, conv_mode=1, device=None,
+    def __init__(self, model, optimizer="nesterov", keep=(), seed=0, conv_mode=2, device=None,
                  world_size=1, rank=0, process_group=None, use_cuda_graph=False,
                  fetch_pred=True, **kwargs):
         if not torch.cuda.is_available():

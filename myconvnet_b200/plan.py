@@ -111,12 +111,12 @@ class TempAllocator(object):
 
 
 class Plan(object):
-    def __init__(self, graph, world_size=1, keep=(), conv_mode=1, fetch_pred=True,
+    def __init__(self, graph, world_size=1, keep=(), conv_mode=2, fetch_pred=True,
                  sync_bn=True, loss_scale=1.0):
         self.graph = graph
         self.world = int(world_size)
         self.keep = set(keep)            # tensors that must stay materialised (parity taps)
-        self.conv_mode = conv_mode       # 1 = im2col TMA, 0 = box TMA
+        self.conv_mode = conv_mode       # 2 = halo tiles where they pay off else im2col TMA, 1 = im2col, 0 = box
         self.fetch_pred = fetch_pred
         self.sync_bn = sync_bn and self.world > 1
         self.loss_scale = loss_scale

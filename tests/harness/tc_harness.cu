@@ -82,6 +82,20 @@ static std::vector<Case> cases() {
   c.push_back({"wgrad 3x3 s1 im2col", 2, 2, 14, 14, 64, 64, 3, 1, 1, 1, 1, 0, 0, 0});
   c.push_back({"wgrad 3x3 s2 im2col", 2, 2, 28, 28, 64, 128, 3, 2, 1, 1, 1, 0, 0, 0});
   c.push_back({"wgrad 1x1 s2 box", 2, 2, 28, 28, 64, 128, 1, 2, 1, 0, 1, 0, 0, 0});
+  // halo mode (a_mode 2): one TMA box per input halo tile, taps = start offsets into it
+  c.push_back({"fprop 3x3 s1 halo 56x56 64->64 (W resident)", 0, 2, 56, 56, 64, 64, 3, 1, 1, 2, 1, 0, 0, 0});
+  c.push_back({"fprop 3x3 s1 halo 28x28 128->128", 0, 2, 28, 28, 128, 128, 3, 1, 1, 2, 1, 1, 0, 0});
+  c.push_back({"fprop 3x3 s1 halo 30x20 64->256 ragged", 0, 2, 30, 20, 64, 256, 3, 1, 1, 2, 1, 0, 0, 0});
+  c.push_back({"fprop 3x3 d2 halo 32x32 64->64", 0, 1, 32, 32, 64, 64, 3, 1, 2, 2, 1, 0, 0, 0});
+  c.push_back({"fprop 5x5 s1 halo 32x32 64->128", 0, 1, 32, 32, 64, 128, 5, 1, 1, 2, 1, 0, 0, 0});
+  c.push_back({"fprop 3x3 VALID halo 34x34 64->64", 0, 1, 34, 34, 64, 64, 3, 1, 1, 2, 0, 0, 0, 0});
+  c.push_back({"dgrad 3x3 s1 halo 56x56 64<-64", 1, 2, 56, 56, 64, 64, 3, 1, 1, 2, 1, 0, 0, 0});
+  c.push_back({"dgrad 3x3 s1 halo 28x28 128<-128", 1, 2, 28, 28, 128, 128, 3, 1, 1, 2, 1, 0, 0, 0});
+  c.push_back({"dgrad 5x5 s1 halo 32x32 64<-128", 1, 1, 32, 32, 64, 128, 5, 1, 1, 2, 1, 0, 0, 0});
+  c.push_back({"T fprop 3x3 56x56 64->64 b64 halo", 0, 64, 56, 56, 64, 64, 3, 1, 1, 2, 1, 0, 0, 20});
+  c.push_back({"T fprop 3x3 28x28 128->128 b64 halo", 0, 64, 28, 28, 128, 128, 3, 1, 1, 2, 1, 0, 0, 20});
+  c.push_back({"T fprop 3x3 28x28 128->128 b64 im2col", 0, 64, 28, 28, 128, 128, 3, 1, 1, 1, 1, 0, 0, 20});
+  c.push_back({"T dgrad 3x3 56x56 64<-64 b64 halo", 1, 64, 56, 56, 64, 64, 3, 1, 1, 2, 1, 0, 0, 20});
   // timing cases (ResNet-50 shapes at batch 64)
   c.push_back({"T fprop 1x1 56x56 256->64 b64", 0, 64, 56, 56, 256, 64, 1, 1, 1, 0, 1, 0, 0, 20});
   c.push_back({"T fprop 1x1 14x14 1024->256 b64", 0, 64, 14, 14, 1024, 256, 1, 1, 1, 0, 1, 0, 0, 20});
