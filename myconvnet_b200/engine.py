@@ -138,6 +138,7 @@ class Engine(object):
             return out
         self._fwd = conv(self.plan.fwd)
         self._bwd = conv(self.plan.bwd)
+        self._inf = conv(self.plan.inf)
         # collective points, keyed by launch index
         self._ar = {"f": {}, "b": {}}
         for phase, idx, ptr, nbytes, dt in self.plan.allreduce_points:
@@ -212,17 +213,35 @@ class Engine(object):
         self.refresh_operand_copies()
         torch.cuda.synchronize(self.device)
 
-    def refresh_operand_copies(self):
-        """bf16 tensor-core operand copies of the current fp32 master weights."""
+    def refresh_operand_copies(self, ema=False):
+        """bf16 tensor-core operand copies of the fp32 master weights (or of their EMA shadows)."""
         p = self.plan
         st = torch.cuda.current_stream(self.device).cuda_stream
-        for v in p.all_vars:
-            if v.needs_bf16 or v.needs_bf16_t:
-                taps, ci, co = v.gemm_dims
-                _lib.check(self.lib.mcn_weight_prep(
-                    self.addr(p.pvar(v)), taps, ci, co,
-                    self.addr(p.pbf16(v)) if v.needs_bf16 else None,
-                    self.addr(p.pbf16t(v)) if v.needs_bf16_t else None, st), "weight_prep")
+        p.phase = "infer" if ema else "train"
+        try:
+            for v in p.all_vars:
+                if v.needs_bf16 or v.needs_bf16_t:
+                    taps, ci, co = v.gemm_dims
+                    _lib.check(self.lib.mcn_weight_prep(
+                        self.addr(p.pvar(v)), taps, ci, co,
+                        self.addr(p.pbf16(v)) if v.needs_bf16 else None,
+                        self.addr(p.pbf16t(v)) if v.needs_bf16_t else None, st), "weight_prep")
+        finally:
+            p.phase = "train"
+
+    def predict(self, X, fetch="pred"):
+        """Inference as the reference's ConvNet.predict (convnet.py:609-665): is_train=False, so
+        every variable is replaced by its EMA shadow (convnet.py:1406) and batch-norm uses the
+        (shadowed) moving statistics.  Returns the model's `pred` tensor as float32 numpy."""
+        self.load_inputs(X=X)
+        self.refresh_operand_copies(ema=True)
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        for fn, args, name, tag in self._inf:
+            rc = fn(*args, st)
+            if rc:
+                _lib.check(rc, name + " [" + tag + "]")
+        t = getattr(self.model, fetch) if isinstance(fetch, str) else fetch
+        return self.fetch(t)
 
     def get_variables(self, ema=False):
         p = self.plan

@@ -126,6 +126,9 @@ class Plan(object):
         self.bufs = []
         self.fwd = []
         self.bwd = []
+        self.inf = []                    # inference (is_train=False) launches: EMA weights, BN moving stats
+        self.phase = "train"
+        self._node_bufs = {}             # (node id, key) -> Buf: per-PLAN cache (a graph may be re-planned)
         self.tbuf = {}                   # Tensor -> Ptr
         self.conv_descs = {}
         self.bn_layers = []
@@ -138,10 +141,18 @@ class Plan(object):
         self._fuse()
         self._emit_forward()
         self._emit_backward()
+        self._emit_inference()
         self.temp_buf.nbytes = self.temp.peak
         self._assign_offsets()
 
     # ------------------------------------------------------------------ buffers
+    def node_buf(self, node, key, name, nbytes, region="act"):
+        """Buffer owned by a node, created once per plan (training and inference lists share it)."""
+        k = (node.id, key)
+        if k not in self._node_bufs:
+            self._node_bufs[k] = self.new_buf(name, nbytes, region)
+        return self._node_bufs[k]
+
     def new_buf(self, name, nbytes, region="act"):
         b = Buf(name, max(int(nbytes), 16), region)
         self.bufs.append(b)
@@ -196,6 +207,7 @@ class Plan(object):
                 self.bf16t_off[v] = n
                 n += _align(v.storage_size * 2, 256)
         self.b_bf16 = self.new_buf("weights_bf16", n, "bf16")
+        self.b_bf16_ema = self.new_buf("weights_bf16_ema", n, "bf16")
 
     def _mark_operand_copies(self):
         for node in self.graph.nodes:
@@ -264,16 +276,18 @@ class Plan(object):
         return r
 
     def pvar(self, v):
-        return Ptr(self.b_param, self.var_off[v] * 4)
+        # inference reads the EMA shadows of every variable (tf.cond(is_train, v, v_ema),
+        # reference convnet.py:1406,1872-1876)
+        return Ptr(self.b_ema if self.phase == "infer" else self.b_param, self.var_off[v] * 4)
 
     def pgrad(self, v):
         return Ptr(self.b_grad, self.var_off[v] * 4)
 
     def pbf16(self, v):
-        return Ptr(self.b_bf16, self.bf16_off[v])
+        return Ptr(self.b_bf16_ema if self.phase == "infer" else self.b_bf16, self.bf16_off[v])
 
     def pbf16t(self, v):
-        return Ptr(self.b_bf16, self.bf16t_off[v])
+        return Ptr(self.b_bf16_ema if self.phase == "infer" else self.b_bf16, self.bf16t_off[v])
 
     # ------------------------------------------------------------------ fusion
     def _single_consumer(self, t):
@@ -335,6 +349,8 @@ class Plan(object):
         return self.tbuf[t]
 
     def alloc_act(self, t, dtype=None):
+        if t in self.tbuf:              # inference reuses the training forward's buffers
+            return self.tbuf[t]
         dt = dtype or t.dtype
         b = self.new_buf("act:%s" % t.name, t.size * DT_SIZE[dt], "act")
         p = Ptr(b)
@@ -346,6 +362,9 @@ class Plan(object):
         return self.conv_descs.setdefault(d.key(), d)
 
     def L(self, phase, fn, *args, **kw):
+        if self.phase == "infer":
+            self.inf.append(Launch(fn, args, kw.get("tag", "")))
+            return
         (self.fwd if phase == "f" else self.bwd).append(Launch(fn, args, kw.get("tag", "")))
 
     def talloc(self, nbytes):
@@ -358,6 +377,12 @@ class Plan(object):
         self.temp.release(*handle)
 
     # ------------------------------------------------------------------ forward emission
+    def _emit_inference(self):
+        """Forward-only launch list for is_train=False (reference predict(), convnet.py:609-665)."""
+        self.phase = "infer"
+        self._emit_forward()
+        self.phase = "train"
+
     def _emit_forward(self):
         g = self.graph
         # scratch that must be zero at step start: BN fp64 sums, loss accumulators
@@ -371,7 +396,15 @@ class Plan(object):
                 src = self.tbuf[x]
                 c = x.shape[-1]
                 if self._logits_dtype(x) != "f32":
-                    raise NotImplementedError("standalone softmax needs fp32 logits")
+                    # use the fp32 copy the loss reads when there is one, else make one
+                    f32 = [cn.outputs[0] for cn in x.consumers
+                           if cn.op == "cast" and cn.outputs[0].dtype == "f32" and cn.outputs[0] in self.tbuf]
+                    if f32:
+                        src = self.tbuf[f32[0]]
+                    else:
+                        b = self.node_buf(node, "f32_copy", "softmax_in_f32", x.size * 4)
+                        src = Ptr(b)
+                        self.L("f", "mcn_cast", DT_CODE[x.dtype], self.tbuf[x], 0, src, x.size, tag="softmax_cast")
                 self.L("f", "mcn_softmax_xent", src, NULL, x.size // c, c, NULL, 0.0, 0.0, NULL, NULL,
                        self.tbuf[node.outputs[0]], tag="softmax")
 
@@ -416,7 +449,7 @@ class Plan(object):
         elif route == "im2col":
             kpad = node.attrs["kpad"]
             m = d.N * d.Ho * d.Wo
-            col = self.new_buf("im2col:%s" % node.scope, m * kpad * 2, "act")
+            col = self.node_buf(node, "col", "im2col:%s" % node.scope, m * kpad * 2)
             node.attrs["col"] = col
             gd = self.conv_desc(N=1, H=1, W=m, Cin=kpad, Cout=d.Cout, kh=1, kw=1, sh=1, sw=1, dh=1,
                                 dw=1, pad_t=0, pad_l=0, Ho=1, Wo=m)
@@ -470,7 +503,7 @@ class Plan(object):
             # exact / odd-channel path on CUDA cores: the underlying conv's HWIO weight
             # [tap][co][ci] is rebuilt from the stored [tap][ci][co] master every step (tiny)
             kh, kw, ci_t, co_t = w.shape
-            wT = self.new_buf("tconv_wT:%s" % node.scope, w.size * 4, "act")
+            wT = self.node_buf(node, "wT", "tconv_wT:%s" % node.scope, w.size * 4)
             node.attrs["wT"] = wT
             self.L("f", "mcn_fill_f32", Ptr(wT), w.size, 0.0, tag="zero")
             self.L("f", "mcn_transpose_add_f32", self.pvar(w), kh * kw, ci_t, co_t, Ptr(wT),
@@ -517,6 +550,18 @@ class Plan(object):
         c = x.shape[-1]
         rows = x.size // c
         v = node.vars
+        if self.phase == "infer":
+            py = self.alloc_act(y)
+            for o in node.outputs:
+                self.tbuf.setdefault(o, py)
+            res = node.attrs["residual"]
+            self.L("f", "mcn_bn_infer", self.ccode, self.tbuf[x], rows, c, self.pvar(v["mu"]),
+                   self.pvar(v["sigma"]), node.attrs["eps"],
+                   self.pvar(v["gamma"]) if "gamma" in v else NULL,
+                   self.pvar(v["beta"]) if "beta" in v else NULL,
+                   self.tbuf[res] if res is not None else NULL, node.attrs["act"], node.attrs["alpha"], py,
+                   tag=node.scope + "/infer")
+            return
         sums = self.new_buf("bn_sums:%s" % node.scope, 2 * c * 8, "zero")
         save = self.new_buf("bn_save:%s" % node.scope, 2 * c * 4, "state")
         node.attrs["save"] = save
@@ -568,7 +613,7 @@ class Plan(object):
         n, h, w, c = x.shape
         _, ho, wo, _ = y.shape
         py = self.alloc_act(y)
-        arg = self.new_buf("argmax:%s" % node.scope, y.size * 4, "act")
+        arg = self.node_buf(node, "argmax", "argmax:%s" % node.scope, y.size * 4)
         node.attrs["argmax"] = arg
         self.L("f", "mcn_maxpool_fwd", DT_CODE[x.dtype], self.tbuf[x], n, h, w, c, a["k"][0], a["k"][1],
                a["s"][0], a["s"][1], a["pad"][0], a["pad"][1], ho, wo, py, Ptr(arg), tag="max_pool")
@@ -621,8 +666,9 @@ class Plan(object):
     def _f_softmax(self, node):
         # probabilities come for free from the fused loss kernel when it exists
         x, y = node.inputs[0], node.outputs[0]
-        b = self.new_buf("probs", x.size * 4, "act")
-        self.tbuf[y] = Ptr(b)
+        if y not in self.tbuf:
+            b = self.new_buf("probs", x.size * 4, "act")
+            self.tbuf[y] = Ptr(b)
         node.attrs["standalone"] = True
 
     def _f_softmax_xent(self, node):
@@ -630,6 +676,8 @@ class Plan(object):
         a = node.attrs
         c = logits.shape[-1]
         rows = a["rows"]
+        if self.phase == "infer":
+            return          # predictions come from the softmax node (emitted stand-alone below)
         loss = self.new_buf("loss", 16, "zero")
         self.loss_slots["loss"] = Ptr(loss)
         self.loss_slots["l2"] = Ptr(loss, 4)
@@ -657,6 +705,8 @@ class Plan(object):
                tag="softmax_xent")
 
     def _f_gan_loss(self, node):
+        if self.phase == "infer":
+            return
         lr_, lf_ = node.inputs
         a = node.attrs
         n = a["rows"]

@@ -344,6 +344,9 @@ class ConvNet(object):
             gamma = self._get_var("gamma", [c], tf.zeros_initializer() if zero_scale_init else tf.ones_initializer(),
                                   "norm", trainable=trainable) if scale else None
             beta = self._get_var("beta", [c], tf.zeros_initializer(), "norm", trainable=trainable) if shift else None
+            if not getattr(self, "is_train", True):
+                # is_train=False: moving statistics (their EMA shadows, loaded by the trainer)
+                return OTensor(ops.fused_batch_norm_infer(x.t, gamma, beta, mu, sigma, epsilon))
             y, bm, bv = ops.fused_batch_norm_train(x.t, gamma, beta, epsilon)
             if update:
                 m = self.batch_norm_decay

@@ -87,3 +87,19 @@ class OracleTrainer(object):
                 m.vars[k] = w.clone()
         self.global_step += 1
         return float(loss.detach())
+
+    def predict(self, X, Y=None):
+        """reference ConvNet.predict: is_train=False -> EMA shadows of all variables, BN inference."""
+        m = self.model
+        saved = dict(m.vars)
+        ema = self.ema if self.ema is not None else saved
+        try:
+            m.vars = {k: ema[k].detach().clone() for k in saved}
+            m.is_train = False
+            import numpy as np
+            with torch.no_grad():
+                m.forward(X, Y if Y is not None else np.zeros(len(X), dtype=np.int64))
+            return m.pred.detach().numpy()
+        finally:
+            m.vars = saved
+            m.is_train = True

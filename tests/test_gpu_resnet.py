@@ -95,6 +95,28 @@ def test_resnet50_fused_loss_curve(have_reference_models, dtype, tol):
     assert rel_l2(e_dev[k], tr.ema[k].numpy()) < 5 * tol
 
 
+def test_predict_uses_ema_shadows_and_moving_statistics(have_reference_models):
+    """ConvNet.predict semantics (reference convnet.py:609-665, 1406, 1872-1876): after a few
+    training steps the inference pass runs on the EMA shadows with BN in inference mode."""
+    from oracle.step import OracleTrainer
+    pm, om, vals = build_pair("models/resnet_v1_5.py", "ResNet50", SHAPE, NCLS, BATCH, "f32",
+                              base_learning_rate=0.05)
+    X, Y = synthetic_batch(BATCH, SHAPE, NCLS)
+    eng = _engine(pm, vals)
+    tr = OracleTrainer(om, base_learning_rate=0.05)
+    for _ in range(3):
+        eng.train_step(X, Y)
+        tr.step(X, Y)
+    p_dev = eng.predict(X)
+    p_ref = tr.predict(X, Y)
+    assert p_dev.shape == p_ref.shape == (BATCH, NCLS)
+    assert np.allclose(p_dev.sum(-1), 1.0, atol=1e-4)
+    assert rel_l2(p_dev, p_ref) < 2e-2
+    # and it differs from a training-mode forward (batch statistics, raw weights)
+    eng.forward(X, Y)
+    assert rel_l2(eng.fetch(pm.pred), p_dev) > 1e-3
+
+
 def test_maxpool_argmax_bit_exact():
     """Pooling argmax indices are bit-exact against the oracle's first-max-in-window rule."""
     import ctypes
