@@ -21,6 +21,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+T0 = time.time()
 
 MODEL = "ResNet-v1.5-50"
 IMG = [224, 224, 3]
@@ -203,6 +204,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--profile-json", default=None, help="write the per-kernel-class table here")
     ap.add_argument("--conv-mode", type=int, default=None, help="0 box, 1 im2col, 2 halo where eligible")
+    ap.add_argument("--stall-timeout", type=int, default=120,
+                    help="abort if no benchmark stage completes within this many seconds")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -216,13 +219,47 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    def stage(msg):
+        sys.stderr.write("[bench rank %d %.1fs] %s\n" % (rank, time.time() - T0, msg))
+        sys.stderr.flush()
+
+    # A collective that never completes must not hang the driver: a watchdog ends the process
+    # with a diagnostic if no stage is reached for --stall-timeout seconds.
+    last_progress = [time.time()]
+
+    def watchdog():
+        while True:
+            time.sleep(5)
+            if time.time() - last_progress[0] > args.stall_timeout:
+                sys.stderr.write("[bench rank %d] no progress for %ds: aborting\n" % (rank, args.stall_timeout))
+                sys.stderr.flush()
+                os._exit(3)
+    threading.Thread(target=watchdog, daemon=True).start()
+    _stage = stage
+
+    def stage(msg):  # noqa: F811
+        last_progress[0] = time.time()
+        _stage(msg)
+
     torch.cuda.set_device(local)
     pg = None
     if world > 1:
+        import datetime
+        # NVLS (in-switch multicast) needs a healthy fabric-manager/IMEX setup; the plain NVLink
+        # ring/tree paths do not.  Opt in with MCN_NCCL_NVLS=1.
+        if os.environ.get("MCN_NCCL_NVLS", "0") != "1":
+            os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        stage("init_process_group(nccl), world %d" % world)
+        dist.init_process_group("nccl", timeout=datetime.timedelta(seconds=args.stall_timeout))
         pg = dist.group.WORLD
+        t = torch.ones(1, device="cuda")
+        dist.all_reduce(t)
+        torch.cuda.synchronize()
+        stage("first all-reduce done (%d)" % int(t.item()))
     warmup = max(args.warmup, 3)
+    stage("building model and engine")
     model, model_src = resnet50(IMG, NCLS, batch_size=args.batch, compute_dtype="bf16")
     eng = Engine(model, optimizer="nesterov", world_size=world, rank=rank, process_group=pg,
                  use_cuda_graph=(not args.no_graph), seed=0, fetch_pred=False,
@@ -238,9 +275,12 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident timing
+    stage("warm-up (%d steps; step 2 captures the CUDA graph)" % warmup)
     eng.load_inputs(X=X, Y=Y)
-    for _ in range(warmup):
+    for i in range(warmup):
         eng.train_step(fetch_loss=False)
+        torch.cuda.synchronize()
+        stage("warm-up step %d done" % i)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -253,6 +293,7 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1) / args.steps
+    stage("timed region done: %.2f ms/step" % ms)
     sampler.stop_flag = True
     loss = eng.read_loss()
     eager_launches = eng.launches_per_step()
@@ -265,17 +306,21 @@ def main():
         eng.train_step(X, Y, fetch_loss=True)
     barrier()
     ms_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
+    stage("end-to-end region done: %.2f ms/step" % ms_e2e)
     if world > 1:
         import torch.distributed as dist
         t = torch.tensor([ms, ms_e2e], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(t[0]), float(t[1])
     if world > 1:
-        import torch.distributed as dist
-        dist.barrier()
-        dist.destroy_process_group()
+        # Tearing the NCCL communicator down while captured graphs still reference it can block;
+        # peers leave right after the last collective and rank 0 exits with os._exit below.
+        torch.cuda.synchronize()
+        stage("collectives done")
     if rank != 0:
-        return
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     # ---- roofline of the dominant kernel class (live CUDA-event timing of every launch)
     hbm_peak, tc_peak, peak_src = measured_peaks()
     prof = profile_step(eng)
@@ -332,6 +377,10 @@ def main():
         "clocks": sampler.summary(),
     }
     print(json.dumps(line))
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world > 1:
+        os._exit(0)
 
 
 if __name__ == "__main__":
