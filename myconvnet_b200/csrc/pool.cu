@@ -58,10 +58,20 @@ __global__ void maxpool_fwd_kernel(const T* __restrict__ x, int N, int H, int W,
       }
     }
     long long o = (((long long)n * Ho + p) * Wo + q) * C + c0;
+    if (V == 1) {
+      y[o] = from_f32<T>(best[0]);
+      if (argmax) argmax[o] = bidx[0];
+    } else {
+      // one 16-byte store for the values, 16-byte stores for the indices
+      Vec16<T> ov;
 #pragma unroll
-    for (int e = 0; e < V; ++e) {
-      y[o + e] = from_f32<T>(best[e]);
-      if (argmax) argmax[o + e] = bidx[e];
+      for (int e = 0; e < V; ++e) ov.set(e, best[e]);
+      st_vec(y + o, ov);
+      if (argmax) {
+#pragma unroll
+        for (int e = 0; e < V; e += 4)
+          *reinterpret_cast<int4*>(argmax + o + e) = make_int4(bidx[e], bidx[e + 1], bidx[e + 2], bidx[e + 3]);
+      }
     }
   }
 }

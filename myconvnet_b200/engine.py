@@ -320,6 +320,45 @@ class Engine(object):
             nbytes += dst.numel() * dst.element_size()
         return nbytes
 
+    def prefetch_inputs(self, **arrays):
+        """Start copying the NEXT step's host batch (pinned memory) into device staging buffers on a
+        side stream, so the PCIe transfer overlaps the current step's kernels.  The following
+        train_step(prefetched=True) moves staging -> input buffers with a device-to-device copy."""
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(self.device)
+            self._staging = {n: torch.empty_like(t) for n, t in self._inputs.items()}
+            self._staged = torch.cuda.Event()
+            self._consumed = None
+        if self._consumed is not None:
+            self._copy_stream.wait_event(self._consumed)     # staging is free again
+        off = int(getattr(self.model, "label_offset", 0))
+        nbytes = 0
+        with torch.cuda.stream(self._copy_stream):
+            for name, arr in arrays.items():
+                dst = self._staging[name]
+                if isinstance(arr, np.ndarray) or (name == "Y" and off):
+                    a = np.asarray(arr) if isinstance(arr, np.ndarray) else arr.numpy()
+                    if name == "Y" and off:
+                        a = a.astype(np.int64) - off
+                    pin = self._pinned.get(name)
+                    if pin is None or pin.shape != dst.shape:
+                        pin = torch.empty(dst.shape, dtype=dst.dtype).pin_memory()
+                        self._pinned[name] = pin
+                    pin.copy_(torch.from_numpy(np.ascontiguousarray(a)).to(dst.dtype).view(dst.shape))
+                    arr = pin
+                dst.copy_(arr.view(dst.shape), non_blocking=True)
+                nbytes += dst.numel() * dst.element_size()
+            self._staged.record(self._copy_stream)
+        return nbytes
+
+    def _consume_prefetched(self):
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(self._staged)
+        for name, dst in self._inputs.items():
+            dst.copy_(self._staging[name], non_blocking=True)
+        self._consumed = torch.cuda.Event()
+        self._consumed.record(cur)
+
     def _step_body(self, backward=True, update=True):
         st = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(self.lib.mcn_fill_f32(self._zero_ptr, self._zero_n, 0.0, st), "zero")
@@ -342,10 +381,14 @@ class Engine(object):
         flat = self.view(Ptr(p.b_grad), p.n_train, torch.float32)
         allreduce_sum_flat(flat, int(self.kw.get("bucket_elems", 8 * 1024 * 1024)), group=self.pg)
 
-    def train_step(self, X=None, Y=None, lr_multiplier=1.0, fetch_loss=True, update=True):
+    def train_step(self, X=None, Y=None, lr_multiplier=1.0, fetch_loss=True, update=True,
+                   prefetched=False):
         """One optimisation step.  X: fp32 NHWC images in [0,1]; Y: int32 labels (-1 = none).
-        Returns the reference's loss value (data term + L2 term) when fetch_loss."""
-        if X is not None:
+        Returns the reference's loss value (data term + L2 term) when fetch_loss.
+        prefetched=True consumes the batch uploaded by prefetch_inputs()."""
+        if prefetched:
+            self._consume_prefetched()
+        elif X is not None:
             self.load_inputs(X=X, Y=Y)
         self._set_hyper(lr_multiplier)
         if self.use_cuda_graph and update and self._eager_steps >= 1:

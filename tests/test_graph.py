@@ -110,3 +110,44 @@ def test_engine_refuses_to_run_without_cuda(r50):
     from myconvnet_b200.engine import Engine
     with pytest.raises(RuntimeError, match="no CPU execution"):
         Engine(r50)
+
+
+def test_other_north_star_models_build_and_plan(have_reference_models):
+    """efficientnet.py, deeplabv3plus.py and dcgan.py import unchanged and lower to launch lists."""
+    fac = loader.product_facade()
+    b0 = loader.load_reference_model("models/efficientnet.py", fac).EfficientNetB0(
+        [224, 224, 3], 1000, batch_size=8, compute_dtype="bf16")
+    assert b0.params == 5288548                       # 5.25 M non-BN + BN gamma/beta (SURVEY B.2)
+    h = Plan(b0.graph).launch_histogram()
+    assert h["mcn_dwconv2d_fwd"] == 16 and h["mcn_scale_bcast_fwd"] == 16 and h["mcn_bn_apply"] == 49
+    assert "block_1/mbconv_0/se_mask/conv_0/biases" in b0.graph.vars
+    dl = loader.load_reference_model("models/deeplabv3plus.py", fac).DeepLabV3PlusResNet(
+        [512, 512, 3], 21, batch_size=2, compute_dtype="bf16")
+    dil = sorted({tuple(n.attrs["d"]) for n in dl.graph.nodes if n.op == "conv2d"})
+    assert (6, 6) in dil and (12, 12) in dil and (18, 18) in dil and (2, 2) in dil and (8, 8) in dil
+    assert dl.logits.shape == (2, 512, 512, 21) and dl.Y.shape == (2, 512, 512)
+    hp = Plan(dl.graph).launch_histogram()
+    assert hp["mcn_resize_bilinear_fwd"] == 2 and hp["mcn_copy_channels"] > 0
+    gan = loader.load_reference_model("models/dcgan.py", fac).DCGAN(
+        [64, 64, 3], 100, batch_size=128, compute_dtype="bf16")
+    assert gan.generate.shape == (128, 64, 64, 3)       # 4x4 seed: SURVEY Appendix D.1
+    vd, vg = gan.gan_variable_split()
+    assert {v.name.split("/")[0] for v in vd} == {"block_0", "block_1", "block_2", "block_3", "block_None"}
+    assert {v.name.split("/")[0] for v in vg} == {"block_%d" % i for i in range(4, 9)}
+    p = Plan(gan.graph)
+    assert p.launch_histogram()["mcn_sigmoid_xent"] == 3
+    # D convolutions are differentiated twice (real + fake) for D's loss, and a third time without
+    # weight gradients for G's loss
+    tags = [l.tag for l in p.bwd]
+    assert sum(t.endswith("discriminator_unit/conv_0/wgrad") for t in tags) == 8
+
+
+def test_inference_plan_uses_ema_and_moving_statistics(r50):
+    p = Plan(r50.graph)
+    names = [l.fn for l in p.inf]
+    assert names.count("mcn_bn_infer") == 53 and "mcn_bn_stats" not in names
+    assert names.count("mcn_conv2d_fprop_tc") == 54
+    # every weight operand of the inference list comes from the EMA copies
+    ema_ptrs = [a for l in p.inf for a in l.args if hasattr(a, "buf") and a.buf in (p.b_ema, p.b_bf16_ema)]
+    raw_ptrs = [a for l in p.inf for a in l.args if hasattr(a, "buf") and a.buf in (p.b_param, p.b_bf16)]
+    assert ema_ptrs and not raw_ptrs
