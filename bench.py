@@ -135,7 +135,8 @@ def run_reference(args):
 def launch_work(name, args, esz):
     """Algorithmic (bytes, flops) of one libmcn launch from its resolved argument tuple."""
     import ctypes
-    if name in ("mcn_conv2d_fprop_tc", "mcn_conv2d_dgrad_tc", "mcn_conv2d_wgrad_tc"):
+    if name in ("mcn_conv2d_fprop_tc", "mcn_conv2d_fprop_tc_stats", "mcn_conv2d_dgrad_tc",
+                "mcn_conv2d_wgrad_tc"):
         d = args[0]._obj
         m = d.N * d.Ho * d.Wo
         flops = 2.0 * m * d.kh * d.kw * d.Cin * d.Cout
@@ -146,6 +147,9 @@ def launch_work(name, args, esz):
     if name == "mcn_bn_apply":
         n = args[2] * args[3]
         return n * esz * (2 + (1 if args[8] else 0)), 0.0
+    if name == "mcn_bn_apply_stats":
+        n = args[2] * args[3]
+        return n * esz * (2 + (1 if args[10] else 0)), 0.0
     if name == "mcn_bn_bwd_reduce":
         n = args[4] * args[5]
         return n * esz * (2 + (1 if args[3] else 0)), 0.0
@@ -156,8 +160,10 @@ def launch_work(name, args, esz):
 
 
 def kernel_class(name, tag):
-    if name == "mcn_conv2d_fprop_tc":
+    if name in ("mcn_conv2d_fprop_tc", "mcn_conv2d_fprop_tc_stats"):
         return "conv_fprop_tc" if not tag.endswith("/dgrad") else "conv_dgrad_tc"
+    if name == "mcn_bn_apply_stats":
+        return "bn_apply"
     return name.replace("mcn_", "")
 
 

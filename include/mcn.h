@@ -66,6 +66,13 @@ long long mcn_launch_count(void);
 int mcn_conv2d_fprop_tc(const mcn_conv_desc* d, const void* x, const void* w_ohwi,
                         const float* bias, void* y, int y_dtype, int a_mode, int accumulate,
                         void* stream);
+/* conv -> batch-norm fusion: same as mcn_conv2d_fprop_tc with a bf16 output, and the epilogue also
+ * ACCUMULATES the per-channel statistics of the stored output into bn_sums (fp64 [2*Cout]:
+ * sum y | sum y^2; zero first) — the statistics half of tf.nn.fused_batch_norm
+ * (convnet.py:1883) without a second pass over y.  Needs Cout % 64 == 0. */
+int mcn_conv2d_fprop_tc_stats(const mcn_conv_desc* d, const void* x, const void* w_ohwi,
+                              const float* bias, void* y, int a_mode, double* bn_sums,
+                              void* stream);
 int mcn_conv2d_dgrad_tc(const mcn_conv_desc* d, const void* dy, const void* w_hwio, void* dx,
                         int dx_dtype, int a_mode, int accumulate, void* stream);
 int mcn_conv2d_wgrad_tc(const mcn_conv_desc* d, const void* x, const void* dy, float* dw,
@@ -110,6 +117,14 @@ int mcn_bn_finalize(const double* sums, double count, int C, float eps, float mo
 int mcn_bn_apply(int dtype, const void* x, long long rows, int C, const float* mean,
                  const float* invstd, const float* gamma, const float* beta, const void* residual,
                  int act, float act_alpha, void* y, void* stream);
+/* finalize + apply in one launch: every thread derives mean / invstd of its channels from the
+ * (all-reduced) fp64 sums; block 0 also stores them for the backward pass (save_mean,
+ * save_invstd) and performs the moving-statistics update (moving_* may be NULL). */
+int mcn_bn_apply_stats(int dtype, const void* x, long long rows, int C, const double* sums,
+                       double count, float eps, float momentum, const float* gamma,
+                       const float* beta, const void* residual, int act, float act_alpha, void* y,
+                       float* save_mean, float* save_invstd, float* moving_mean,
+                       float* moving_var, void* stream);
 /* inference mode: y = act(gamma*(x-mean)/sqrt(var+eps)+beta [+ residual]) */
 int mcn_bn_infer(int dtype, const void* x, long long rows, int C, const float* mean,
                  const float* var, float eps, const float* gamma, const float* beta,

@@ -8,12 +8,34 @@
 // channel group: its per-channel constants live in registers and every warp reads contiguous
 // 512-byte segments.  Reductions go thread partial (fp32, a few rows) -> shared-memory atomics
 // -> one global atomic per channel per block (fp64 for the forward statistics).
+#include <cstdlib>
+
 #include "mcn_common.cuh"
 
 namespace mcn {
 namespace {
 
 constexpr int kUnroll = 4;
+
+// MCN_BN_RUNS=0 selects the grid-stride kernels everywhere (A/B switch)
+// the run-based backward-apply kernel measured slower than the grid-stride one in the training
+// step (three read streams): off unless MCN_BN_BWD_RUNS=1
+inline bool bn_bwd_use_runs() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MCN_BN_BWD_RUNS");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v != 0;
+}
+inline bool bn_use_runs() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MCN_BN_RUNS");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
 
 struct ChanLaunch {
   int cv;      // channel vectors per row
@@ -167,23 +189,78 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
 }
 
 // ---------------------------------------------------------------- forward apply
-template <typename T, bool kVarInput>
-__global__ void __launch_bounds__(512)
+// Per-channel scale/shift of a thread's V channels are held in registers; the tensor is then
+// streamed once.  Three sources for the normalisation constants:
+//   kMode 0: saved mean / invstd            (mcn_bn_apply)
+//   kMode 1: moving mean / variance + eps   (mcn_bn_infer)
+//   kMode 2: the fp64 sums [sum x | sum x^2] of this step (mcn_bn_apply_stats): every thread
+//            finalises its own channels (mean, biased variance; the cancellation-prone
+//            E[x^2] - mean^2 stays in fp64), and block 0 also writes the saved mean / invstd for
+//            the backward pass and the reference's moving-statistics update
+//            (convnet.py:1898-1901, Bessel-corrected variance) — no separate finalize launch.
+struct BnSumsArgs {
+  const double* sums;
+  double inv_count, bessel;
+  float eps, momentum;
+  float* save_mean;
+  float* save_invstd;
+  float* moving_mean;
+  float* moving_var;
+};
+
+template <int V, int kMode>
+__device__ __forceinline__ void bn_apply_coefs(int c0, int C, int cv, const float* __restrict__ mean,
+                                               const float* __restrict__ invstd_or_var, float eps,
+                                               const float* __restrict__ gamma,
+                                               const float* __restrict__ beta, const BnSumsArgs& fs,
+                                               float* sc, float* sf) {
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    float mu, is;
+    if (kMode == 2) {
+      const double m = fs.sums[c0 + i] * fs.inv_count;
+      double var = fs.sums[C + c0 + i] * fs.inv_count - m * m;
+      if (var < 0.0) var = 0.0;
+      mu = static_cast<float>(m);
+      // 1/sqrt(var + eps) correctly rounded from the fp64 variance (as bn_finalize_kernel does) at
+      // the cost of four fp64 operations: fp32 seed, one Newton step in fp64 (error ~1e-14).  A ReLU
+      // network amplifies even 1-ulp differences of invstd into mask flips, so this matters for
+      // step-to-step reproducibility against the oracle.
+      const double ve = var + static_cast<double>(fs.eps);
+      double yd = static_cast<double>(rsqrtf(static_cast<float>(ve)));
+      yd = yd * (1.5 - 0.5 * ve * yd * yd);
+      is = static_cast<float>(yd);
+      if (blockIdx.x == 0 && threadIdx.x < cv) {
+        fs.save_mean[c0 + i] = mu;
+        fs.save_invstd[c0 + i] = is;
+        if (fs.moving_mean != nullptr) {
+          const float unbiased = static_cast<float>(var * fs.bessel);
+          fs.moving_mean[c0 + i] = fs.momentum * fs.moving_mean[c0 + i] + (1.f - fs.momentum) * mu;
+          fs.moving_var[c0 + i] = fs.momentum * fs.moving_var[c0 + i] + (1.f - fs.momentum) * unbiased;
+        }
+      }
+    } else {
+      mu = mean[c0 + i];
+      is = (kMode == 1) ? rsqrtf(invstd_or_var[c0 + i] + eps) : invstd_or_var[c0 + i];
+    }
+    const float g = gamma ? gamma[c0 + i] : 1.f;
+    const float b = beta ? beta[c0 + i] : 0.f;
+    sc[i] = g * is;
+    sf[i] = b - mu * sc[i];
+  }
+}
+
+template <typename T, int kMode>
+__global__ void __launch_bounds__(512, 2)   // two blocks per SM: the fp64 finalize must not cost occupancy
 bn_apply_kernel(const T* __restrict__ x, long long nvec, int cv, const float* __restrict__ mean,
                 const float* __restrict__ invstd_or_var, float eps,
                 const float* __restrict__ gamma, const float* __restrict__ beta,
-                const T* __restrict__ residual, int act, float alpha, T* __restrict__ y) {
+                const T* __restrict__ residual, int act, float alpha, T* __restrict__ y,
+                BnSumsArgs fs) {
   constexpr int V = Vec16<T>::N;
   const int c0 = (threadIdx.x % cv) * V;
   float sc[V], sf[V];
-#pragma unroll
-  for (int i = 0; i < V; ++i) {
-    float is = kVarInput ? rsqrtf(invstd_or_var[c0 + i] + eps) : invstd_or_var[c0 + i];
-    float g = gamma ? gamma[c0 + i] : 1.f;
-    float b = beta ? beta[c0 + i] : 0.f;
-    sc[i] = g * is;
-    sf[i] = b - mean[c0 + i] * sc[i];
-  }
+  bn_apply_coefs<V, kMode>(c0, cv * V, cv, mean, invstd_or_var, eps, gamma, beta, fs, sc, sf);
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
        v += kUnroll * stride) {
@@ -205,6 +282,54 @@ bn_apply_kernel(const T* __restrict__ x, long long nvec, int cv, const float* __
         for (int i = 0; i < V; ++i) {
           float f = fmaf(a[u].get(i), sc[i], sf[i]);
           if (residual) f += r[u].get(i);
+          o.set(i, act_fwd(act, f, alpha));
+        }
+        st_vec(y + vv * V, o);
+      }
+    }
+  }
+}
+
+// Non-persistent variant ("runs"): a block of 256 threads owns contiguous runs of 256*U vectors
+// (32 KB of bf16 at U = 8) and issues all U loads of a run before touching the data — measured
+// 10-15 % faster than the grid-stride walk on 25-411 MB tensors (profiles/r01_stream_sweep.txt).
+// Needs 256 % cv == 0 so that a thread keeps its channel group from run to run.  The loads of the
+// first run are in flight while the per-channel constants are derived.
+template <typename T, int kMode, int U, bool kRes>
+__global__ void __launch_bounds__(256)
+bn_apply_runs_kernel(const T* __restrict__ x, long long nvec, int cv, const float* __restrict__ mean,
+                     const float* __restrict__ invstd_or_var, float eps,
+                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                     const T* __restrict__ residual, int act, float alpha, T* __restrict__ y,
+                     BnSumsArgs fs, int runs_per_block) {
+  constexpr int V = Vec16<T>::N;
+  const int c0 = (threadIdx.x % cv) * V;
+  long long v = (long long)blockIdx.x * runs_per_block * (256 * U) + threadIdx.x;
+  Vec16<T> a[U], r[U];
+  auto load = [&](long long vbase) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long vv = vbase + u * 256;
+      if (vv < nvec) {
+        a[u] = ld_vec_stream(x + vv * V);
+        if (kRes) r[u] = ld_vec_stream(residual + vv * V);
+      }
+    }
+  };
+  load(v);
+  float sc[V], sf[V];
+  bn_apply_coefs<V, kMode>(c0, cv * V, cv, mean, invstd_or_var, eps, gamma, beta, fs, sc, sf);
+  for (int run = 0; run < runs_per_block; ++run, v += 256 * U) {
+    if (run > 0) load(v);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long vv = v + u * 256;
+      if (vv < nvec) {
+        Vec16<T> o;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          float f = fmaf(a[u].get(i), sc[i], sf[i]);
+          if (kRes) f += r[u].get(i);
           o.set(i, act_fwd(act, f, alpha));
         }
         st_vec(y + vv * V, o);
@@ -365,6 +490,65 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
   }
 }
 
+// Run-based variant of the backward apply pass (see bn_apply_runs_kernel): 256 threads own
+// contiguous runs of 256*U vectors, all loads of a run are issued before any arithmetic.
+template <typename T, int U, bool kHaveY, bool kRes>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_runs_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
+                         long long nvec, int cv, const float* __restrict__ mean,
+                         const float* __restrict__ invstd, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, int act, float alpha,
+                         const float* __restrict__ sum_dz, const float* __restrict__ sum_dz_xhat,
+                         float inv_count, T* __restrict__ dx, T* __restrict__ d_residual,
+                         int runs_per_block) {
+  constexpr int V = Vec16<T>::N;
+  const int c0 = (threadIdx.x % cv) * V;
+  long long v = (long long)blockIdx.x * runs_per_block * (256 * U) + threadIdx.x;
+  Vec16<T> g[U], a[U], o[U];
+  auto load = [&](long long vbase) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long vv = vbase + u * 256;
+      if (vv < nvec) {
+        g[u] = ld_vec_stream(dy + vv * V);
+        a[u] = ld_vec_stream(x + vv * V);
+        if (kHaveY) o[u] = ld_vec_stream(y + vv * V);
+      }
+    }
+  };
+  load(v);
+  float A[V], B[V], Cc[V], sf[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const float mu = mean[c0 + i], is = invstd[c0 + i];
+    const float k1 = sum_dz[c0 + i] * inv_count, k2 = sum_dz_xhat[c0 + i] * inv_count;
+    A[i] = (gamma ? gamma[c0 + i] : 1.f) * is;
+    sf[i] = (beta ? beta[c0 + i] : 0.f) - mu * A[i];
+    B[i] = -A[i] * k2 * is;
+    Cc[i] = A[i] * (k2 * mu * is - k1);
+  }
+  for (int run = 0; run < runs_per_block; ++run, v += 256 * U) {
+    if (run > 0) load(v);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long vv = v + u * 256;
+      if (vv < nvec) {
+        Vec16<T> ox, orr;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          const float xv = a[u].get(i);
+          const float dz = dz_of<T>(g[u].get(i), xv, kHaveY ? o[u].get(i) : 0.f, kHaveY, A[i], sf[i],
+                                    act, alpha);
+          ox.set(i, fmaf(A[i], dz, fmaf(B[i], xv, Cc[i])));
+          if (kRes) orr.set(i, dz);
+        }
+        st_vec(dx + vv * V, ox);
+        if (kRes) st_vec(d_residual + vv * V, orr);
+      }
+    }
+  }
+}
+
 // scalar fallbacks for odd channel counts
 template <typename T>
 __global__ void bn_bwd_reduce_scalar_kernel(const T* dy, const T* x, const T* y, long long rows,
@@ -439,22 +623,52 @@ extern "C" int mcn_bn_finalize(const double* sums, double count, int C, float ep
   return after_launch("bn_finalize");
 }
 
-template <bool kVar>
+template <int kMode>
 static int bn_apply_impl(int dtype, const void* x, long long rows, int C, const float* mean,
                          const float* is_or_var, float eps, const float* gamma, const float* beta,
-                         const void* residual, int act, float alpha, void* y, void* stream) {
-  MCN_REQUIRE(x && y && mean && is_or_var && rows > 0, "bn_apply: bad argument");
+                         const void* residual, int act, float alpha, void* y, const BnSumsArgs& fs,
+                         void* stream) {
+  MCN_REQUIRE(x && y && rows > 0, "bn_apply: bad argument");
+  MCN_REQUIRE(kMode == 2 || (mean && is_or_var), "bn_apply: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MCN_DISPATCH_DTYPE(dtype, T, {
     ChanLaunch L;
-    if (plan<T>(rows, C, &L, 2)) {
-      bn_apply_kernel<T, kVar><<<L.grid, L.block, 0, st>>>(
+    constexpr int V = Vec16<T>::N;
+    const int cvr = (C % V == 0) ? C / V : 0;
+    // measured in the training step (profiles/r01_bn_runs_ab.txt): the run-based kernel wins for
+    // the single-stream case (170 -> 140 us on 411 MB) and loses once a residual stream is added
+    if (cvr > 0 && cvr <= 256 && 256 % cvr == 0 && bn_use_runs() && residual == nullptr) {
+      const long long nvec = rows * cvr;
+      const bool res = residual != nullptr;
+      const int U = res ? 4 : 8;
+      const long long runs = (nvec + 256LL * U - 1) / (256LL * U);
+      // several runs per block amortise the constants' derivation once the grid is >= 4 waves
+      int rpb = (int)std::max<long long>(1, std::min<long long>(8, runs / (4LL * 3 * num_sms())));
+      const unsigned grid = (unsigned)((runs + rpb - 1) / rpb);
+      if (res)
+        bn_apply_runs_kernel<T, kMode, 4, true><<<grid, 256, 0, st>>>(
+            static_cast<const T*>(x), nvec, cvr, mean, is_or_var, eps, gamma, beta,
+            static_cast<const T*>(residual), act, alpha, static_cast<T*>(y), fs, rpb);
+      else
+        bn_apply_runs_kernel<T, kMode, 8, false><<<grid, 256, 0, st>>>(
+            static_cast<const T*>(x), nvec, cvr, mean, is_or_var, eps, gamma, beta, nullptr, act, alpha,
+            static_cast<T*>(y), fs, rpb);
+    } else if (plan<T>(rows, C, &L, 2)) {
+      bn_apply_kernel<T, kMode><<<L.grid, L.block, 0, st>>>(
           static_cast<const T*>(x), rows * L.cv, L.cv, mean, is_or_var, eps, gamma, beta,
-          static_cast<const T*>(residual), act, alpha, static_cast<T*>(y));
+          static_cast<const T*>(residual), act, alpha, static_cast<T*>(y), fs);
     } else {
+      // odd channel counts: finalize as its own launch, then the scalar kernel
+      if (kMode == 2) {
+        bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(fs.sums, 1.0 / fs.inv_count, C, fs.eps,
+                                                            fs.momentum, fs.save_mean, fs.save_invstd,
+                                                            fs.moving_mean, fs.moving_var);
+        mean = fs.save_mean;
+        is_or_var = fs.save_invstd;
+      }
       long long n = rows * C;
       int grid = (int)std::min<long long>((n + 255) / 256, 8LL * num_sms());
-      bn_apply_scalar_kernel<T, kVar><<<grid, 256, 0, st>>>(
+      bn_apply_scalar_kernel<T, kMode == 1><<<grid, 256, 0, st>>>(
           static_cast<const T*>(x), n, C, mean, is_or_var, eps, gamma, beta,
           static_cast<const T*>(residual), act, alpha, static_cast<T*>(y));
     }
@@ -466,15 +680,35 @@ extern "C" int mcn_bn_apply(int dtype, const void* x, long long rows, int C, con
                             const float* invstd, const float* gamma, const float* beta,
                             const void* residual, int act, float act_alpha, void* y,
                             void* stream) {
-  return bn_apply_impl<false>(dtype, x, rows, C, mean, invstd, 0.f, gamma, beta, residual, act,
-                              act_alpha, y, stream);
+  return bn_apply_impl<0>(dtype, x, rows, C, mean, invstd, 0.f, gamma, beta, residual, act,
+                          act_alpha, y, BnSumsArgs{}, stream);
 }
 extern "C" int mcn_bn_infer(int dtype, const void* x, long long rows, int C, const float* mean,
                             const float* var, float eps, const float* gamma, const float* beta,
                             const void* residual, int act, float act_alpha, void* y,
                             void* stream) {
-  return bn_apply_impl<true>(dtype, x, rows, C, mean, var, eps, gamma, beta, residual, act,
-                             act_alpha, y, stream);
+  return bn_apply_impl<1>(dtype, x, rows, C, mean, var, eps, gamma, beta, residual, act,
+                          act_alpha, y, BnSumsArgs{}, stream);
+}
+extern "C" int mcn_bn_apply_stats(int dtype, const void* x, long long rows, int C,
+                                  const double* sums, double count, float eps, float momentum,
+                                  const float* gamma, const float* beta, const void* residual,
+                                  int act, float act_alpha, void* y, float* save_mean,
+                                  float* save_invstd, float* moving_mean, float* moving_var,
+                                  void* stream) {
+  MCN_REQUIRE(sums && save_mean && save_invstd && count > 0, "bn_apply_stats: bad argument");
+  BnSumsArgs fs;
+  fs.sums = sums;
+  fs.inv_count = 1.0 / count;
+  fs.bessel = count > 1.0 ? count / (count - 1.0) : 1.0;
+  fs.eps = eps;
+  fs.momentum = momentum;
+  fs.save_mean = save_mean;
+  fs.save_invstd = save_invstd;
+  fs.moving_mean = moving_mean;
+  fs.moving_var = moving_var;
+  return bn_apply_impl<2>(dtype, x, rows, C, nullptr, nullptr, eps, gamma, beta, residual, act,
+                          act_alpha, y, fs, stream);
 }
 
 extern "C" int mcn_bn_bwd_reduce(int dtype, const void* dy, const void* x, const void* y,
@@ -500,6 +734,31 @@ extern "C" int mcn_bn_bwd_reduce(int dtype, const void* dy, const void* x, const
   return after_launch("bn_bwd_reduce");
 }
 
+template <typename T>
+static void launch_bwd_apply_runs(unsigned grid, cudaStream_t st, const void* dy, const void* x,
+                                  const void* y, long long nvec, int cv, const float* mean,
+                                  const float* invstd, const float* gamma, const float* beta, int act,
+                                  float alpha, const float* sum_dz, const float* sum_dz_xhat,
+                                  float inv_count, void* dx, void* d_residual, int rpb) {
+  const T* pdy = static_cast<const T*>(dy);
+  const T* px = static_cast<const T*>(x);
+  const T* py = static_cast<const T*>(y);
+  T* pdx = static_cast<T*>(dx);
+  T* pdr = static_cast<T*>(d_residual);
+  if (y != nullptr && d_residual != nullptr)
+    bn_bwd_apply_runs_kernel<T, 4, true, true><<<grid, 256, 0, st>>>(
+        pdy, px, py, nvec, cv, mean, invstd, gamma, beta, act, alpha, sum_dz, sum_dz_xhat, inv_count, pdx, pdr, rpb);
+  else if (y != nullptr)
+    bn_bwd_apply_runs_kernel<T, 4, true, false><<<grid, 256, 0, st>>>(
+        pdy, px, py, nvec, cv, mean, invstd, gamma, beta, act, alpha, sum_dz, sum_dz_xhat, inv_count, pdx, pdr, rpb);
+  else if (d_residual != nullptr)
+    bn_bwd_apply_runs_kernel<T, 4, false, true><<<grid, 256, 0, st>>>(
+        pdy, px, py, nvec, cv, mean, invstd, gamma, beta, act, alpha, sum_dz, sum_dz_xhat, inv_count, pdx, pdr, rpb);
+  else
+    bn_bwd_apply_runs_kernel<T, 4, false, false><<<grid, 256, 0, st>>>(
+        pdy, px, py, nvec, cv, mean, invstd, gamma, beta, act, alpha, sum_dz, sum_dz_xhat, inv_count, pdx, pdr, rpb);
+}
+
 extern "C" int mcn_bn_bwd_apply(int dtype, const void* dy, const void* x, const void* y,
                                 long long rows, int C, const float* mean, const float* invstd,
                                 const float* gamma, const float* beta, int act, float act_alpha,
@@ -511,7 +770,17 @@ extern "C" int mcn_bn_bwd_apply(int dtype, const void* dy, const void* x, const 
   const float inv_count = (float)(1.0 / count);
   MCN_DISPATCH_DTYPE(dtype, T, {
     ChanLaunch L;
-    if (plan<T>(rows, C, &L, 3, 256)) {
+    constexpr int V = Vec16<T>::N;
+    const int cvr = (C % V == 0) ? C / V : 0;
+    if (cvr > 0 && cvr <= 256 && 256 % cvr == 0 && bn_bwd_use_runs()) {
+      const long long nvec = rows * cvr;
+      constexpr int U = 4;
+      const long long runs = (nvec + 256LL * U - 1) / (256LL * U);
+      int rpb = (int)std::max<long long>(1, std::min<long long>(8, runs / (4LL * 2 * num_sms())));
+      const unsigned grid = (unsigned)((runs + rpb - 1) / rpb);
+      launch_bwd_apply_runs<T>(grid, st, dy, x, y, nvec, cvr, mean, invstd, gamma, beta, act, act_alpha,
+                               sum_dz, sum_dz_xhat, inv_count, dx, d_residual, rpb);
+    } else if (plan<T>(rows, C, &L, 3, 256)) {
       bn_bwd_apply_kernel<T><<<L.grid, L.block, 0, st>>>(
           static_cast<const T*>(dy), static_cast<const T*>(x), static_cast<const T*>(y),
           rows * L.cv, L.cv, mean, invstd, gamma, beta, act, act_alpha, sum_dz, sum_dz_xhat,

@@ -103,9 +103,49 @@ __device__ __forceinline__ bool row_coords(const TileGeom& g, const PixelTile& t
 struct EpiArgs {
   void* out;
   const float* bias;
+  double* stats;   // fused batch-norm statistics: [2*n_total] fp64 (sum y, sum y^2), or nullptr
   int out_f32, vec_ok, accumulate, block_n, n_total;
   int debug;   // bit0: skip stores, bit1: skip MMA issue, bit2: skip TMEM loads (timing experiments)
 };
+
+// Fused BN statistics (conv -> BN): the epilogue already holds every output element in
+// registers, so the per-channel sum and sum of squares of the STORED (bf16-rounded) values are
+// taken there and the separate statistics pass over y disappears.  A thread owns one pixel row,
+// a channel's values are spread over the lanes: each epilogue warp parks its 32 rows x 64 packed
+// bf16 channels in a private shared-memory tile (row pitch 36 words: conflict-free 16-byte row
+// stores and conflict-free column reads), lane L then sums channels 2L and 2L+1 down the 32
+// rows.  Partial sums go to a per-WARP shared accumulator (one n-tile wide, plain read-modify-
+// write: no shared-memory float atomics, which are CAS loops) and are flushed with fp64 global
+// atomics only when the persistent CTA moves to another n-tile or finishes.
+constexpr int kStatRowWords = 36;
+constexpr int kStatStageWords = 4 * 32 * kStatRowWords;          // four epilogue warps
+constexpr int kStatAccWarp = 2 * 256;                            // [sum | sum sq] x block_n <= 256
+constexpr int kStatAccFloats = 4 * kStatAccWarp;                 // one slice per epilogue warp
+constexpr int kStatSmemBytes = kStatStageWords * 4 + kStatAccFloats * 4;
+constexpr int kBarRegionBytes = 256;                             // mbarriers + tmem slot
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// et: index of the thread among the 128 epilogue threads
+__device__ __forceinline__ void stats_flush(const EpiArgs& e, float* acc, int n_t, int et) {
+  epi_bar_sync();   // every warp's shared-memory atomics of the finished tiles have landed
+  for (int c = et; c < e.block_n; c += 128) {
+    const int col = n_t * e.block_n + c;
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      s1 += acc[w * kStatAccWarp + c];
+      s2 += acc[w * kStatAccWarp + 256 + c];
+      acc[w * kStatAccWarp + c] = 0.f;
+      acc[w * kStatAccWarp + 256 + c] = 0.f;
+    }
+    if (col < e.n_total) {
+      atomicAdd(e.stats + col, static_cast<double>(s1));
+      atomicAdd(e.stats + e.n_total + col, static_cast<double>(s2));
+    }
+  }
+  epi_bar_sync();
+}
 
 // One output tile: wait for the accumulator, TMEM -> registers -> global.  Each thread owns one
 // output pixel (row) and walks its channels 64 at a time: 64 bf16 = one full 128-byte line written
@@ -114,7 +154,8 @@ struct EpiArgs {
 __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t tmem_acc, int quad, int lane,
                                               bool valid, long long off, int n_t,
                                               uint64_t* tmem_full_bar, uint32_t tph,
-                                              uint64_t* tmem_empty_bar) {
+                                              uint64_t* tmem_empty_bar, uint32_t* stat_stage,
+                                              float* stat_acc) {
       // bf16 accumulate (dx += dgrad): the previous values of a 64-channel chunk are fetched
   // with four back-to-back 32-byte loads one chunk AHEAD (the first one before the
   // accumulator is even ready), so the global-load latency hides behind the MMAs.
@@ -149,7 +190,9 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t tmem_ac
     }
     const int col0 = n_t * e.block_n + c0;
     const bool fullw = e.vec_ok && (col0 + 64 <= e.n_total);
-    if (!valid || col0 >= e.n_total || (e.debug & 1)) continue;
+    if (col0 >= e.n_total) continue;                               // warp-uniform
+    const bool do_store = valid && !(e.debug & 1);
+    if (e.stats == nullptr && !do_store) continue;                 // statistics need every lane
     if (e.bias != nullptr) {
 #pragma unroll
       for (int j = 0; j < 64; ++j)
@@ -157,6 +200,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t tmem_ac
           r[j] = __float_as_uint(__uint_as_float(r[j]) + e.bias[col0 + j]);
     }
     if (e.out_f32) {
+      if (!do_store) continue;
       float* o = reinterpret_cast<float*>(e.out) + off + col0;
       if (fullw) {
 #pragma unroll
@@ -165,11 +209,11 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t tmem_ac
           if (e.accumulate) {
             ptx::ld_global_v8(o + j, v);
 #pragma unroll
-            for (int e = 0; e < 8; ++e)
-              v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(r[j + e]));
+            for (int i = 0; i < 8; ++i)
+              v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(r[j + i]));
           } else {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = r[j + e];
+            for (int i = 0; i < 8; ++i) v[i] = r[j + i];
           }
           ptx::st_global_v8(o + j, v);
         }
@@ -183,20 +227,52 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t tmem_ac
       if (fullw) {
         uint32_t v[32];
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          float lo = __uint_as_float(r[2 * e]), hi = __uint_as_float(r[2 * e + 1]);
+        for (int i = 0; i < 32; ++i) {
+          float lo = __uint_as_float(r[2 * i]), hi = __uint_as_float(r[2 * i + 1]);
           if (acc_bf16) {
-            lo += __uint_as_float(old[e] << 16);
-            hi += __uint_as_float(old[e] & 0xFFFF0000u);
+            lo += __uint_as_float(old[i] << 16);
+            hi += __uint_as_float(old[i] & 0xFFFF0000u);
           }
           __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-          v[e] = *reinterpret_cast<uint32_t*>(&h);
+          v[i] = *reinterpret_cast<uint32_t*>(&h);
         }
         if (acc_bf16 && c0 + 64 < e.block_n) prefetch_old(c0 + 64);
+        if (do_store) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          ptx::st_global_v8(o + j * 16, *reinterpret_cast<uint32_t(*)[8]>(&v[j * 8]));
-      } else {
+          for (int j = 0; j < 4; ++j)
+            ptx::st_global_v8(o + j * 16, *reinterpret_cast<uint32_t(*)[8]>(&v[j * 8]));
+        }
+        if (e.stats != nullptr) {
+          uint32_t* mine = stat_stage + lane * kStatRowWords;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(mine + 4 * j) =
+                valid ? make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3])
+                      : make_uint4(0u, 0u, 0u, 0u);
+          __syncwarp();
+          float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+#pragma unroll
+          for (int r = 0; r < 32; ++r) {
+            const uint32_t w = stat_stage[r * kStatRowWords + lane];
+            const float lo = __uint_as_float(w << 16), hi = __uint_as_float(w & 0xFFFF0000u);
+            s1a += lo;
+            s1b += hi;
+            s2a = fmaf(lo, lo, s2a);
+            s2b = fmaf(hi, hi, s2b);
+          }
+          __syncwarp();
+          // this warp's own slice, this lane's own two channels: plain read-modify-write
+          float2* a1 = reinterpret_cast<float2*>(stat_acc + c0 + 2 * lane);
+          float2* a2 = reinterpret_cast<float2*>(stat_acc + 256 + c0 + 2 * lane);
+          float2 t1 = *a1, t2 = *a2;
+          t1.x += s1a;
+          t1.y += s1b;
+          t2.x += s2a;
+          t2.y += s2b;
+          *a1 = t1;
+          *a2 = t2;
+        }
+      } else if (do_store) {
         for (int j = 0; j < 64; ++j)
           if (col0 + j < e.n_total) {
             float f = __uint_as_float(r[j]);
@@ -334,18 +410,34 @@ gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
     // full 128-byte line written with four 32-byte stores (fp32 output: eight).
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;
-    int lt = 0;
+    uint32_t* stat_stage = reinterpret_cast<uint32_t*>(smem + static_cast<size_t>(stages) * stage_bytes +
+                                                       kBarRegionBytes);
+    float* stat_acc_all = reinterpret_cast<float*>(stat_stage + kStatStageWords);
+    float* stat_acc = stat_acc_all + quad * kStatAccWarp;
+    stat_stage += quad * 32 * kStatRowWords;
+    const bool stats = args.e.stats != nullptr;
+    if (stats) {
+      for (int i = row; i < kStatAccFloats; i += 128) stat_acc_all[i] = 0.f;
+      epi_bar_sync();
+    }
+    int lt = 0, cur_nt = -1;
     for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x, ++lt) {
       const int buf = lt & 1;
       const uint32_t tph = static_cast<uint32_t>(lt >> 1) & 1u;
       const int n_t = tile_id % args.tiles_n;
+      if (stats && (n_t != cur_nt || (lt & 7) == 0)) {
+        // also every 8 tiles: bounds the length of the fp32 partial sums (accuracy of sum x^2)
+        if (cur_nt >= 0) stats_flush(args.e, stat_acc_all, cur_nt, row);
+        cur_nt = n_t;
+      }
       const PixelTile tile = decode_tile(args.g, tile_id / args.tiles_n);
       int n, p, q;
       const bool valid = row_coords(args.g, tile, row, n, p, q);
       const long long off = valid ? (n * args.out_sn + p * args.out_sh + q * args.out_sw) : 0;
       epilogue_tile(args.e, tmem_base + static_cast<uint32_t>(buf * args.e.block_n), quad, lane, valid,
-                    off, n_t, &tmem_full[buf], tph, &tmem_empty[buf]);
+                    off, n_t, &tmem_full[buf], tph, &tmem_empty[buf], stat_stage, stat_acc);
     }
+    if (stats && cur_nt >= 0) stats_flush(args.e, stat_acc_all, cur_nt, row);
   }
 
   ptx::tc_fence_before();
@@ -521,11 +613,25 @@ halo_conv_kernel(const __grid_constant__ HaloArgs args) {
     // ---------------- epilogue (warps 3..6) ----------------
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
-    int lt = 0;
+    uint32_t* stat_stage = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + kBarRegionBytes);
+    float* stat_acc_all = reinterpret_cast<float*>(stat_stage + kStatStageWords);
+    float* stat_acc = stat_acc_all + quad * kStatAccWarp;
+    stat_stage += quad * 32 * kStatRowWords;
+    const bool stats = args.e.stats != nullptr;
+    if (stats) {
+      for (int i = row; i < kStatAccFloats; i += 128) stat_acc_all[i] = 0.f;
+      epi_bar_sync();
+    }
+    int lt = 0, cur_nt = -1;
     for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x, ++lt) {
       const int buf = lt & 1;
       const uint32_t tph = static_cast<uint32_t>(lt >> 1) & 1u;
       const int n_t = tile_id % args.tiles_n;
+      if (stats && (n_t != cur_nt || (lt & 7) == 0)) {
+        // also every 8 tiles: bounds the length of the fp32 partial sums (accuracy of sum x^2)
+        if (cur_nt >= 0) stats_flush(args.e, stat_acc_all, cur_nt, row);
+        cur_nt = n_t;
+      }
       const int m = tile_id / args.tiles_n;
       const int n = m / tiles_per_img;
       const int r = m - n * tiles_per_img;
@@ -534,8 +640,9 @@ halo_conv_kernel(const __grid_constant__ HaloArgs args) {
       const bool valid = p < args.Ho && q < args.Wo;
       const long long off = valid ? (n * args.out_sn + p * args.out_sh + q * args.out_sw) : 0;
       epilogue_tile(args.e, tmem_base + static_cast<uint32_t>(buf * args.e.block_n), quad, lane, valid,
-                    off, n_t, &tmem_full[buf], tph, &tmem_empty[buf]);
+                    off, n_t, &tmem_full[buf], tph, &tmem_empty[buf], stat_stage, stat_acc);
     }
+    if (stats && cur_nt >= 0) stats_flush(args.e, stat_acc_all, cur_nt, row);
   }
 
   ptx::tc_fence_before();
@@ -687,6 +794,169 @@ wgrad_kernel(const __grid_constant__ WgradArgs args) {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           if (co0 + j < args.cout) atomicAdd(o + j, __uint_as_float(r[j]));
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, static_cast<uint32_t>(args.tmem_cols));
+}
+
+// ------------------------------------------------------------------ wgrad, halo feed (k x k, stride 1)
+// The tap-at-a-time wgrad above re-reads the dy tile for every tap and the x tile for every
+// output-channel tile: with 128 x 128 output tiles it moves 64 KB of operands per 128^3 MACs
+// and is bound by the L2 -> shared-memory rate, not by the tensor pipe.  Here a pixel tile is
+// 16 rows x 8 columns of one image (as in halo_conv_kernel): its INPUT halo and its dy tile are
+// loaded ONCE and every filter tap of the group is a different start address into the halo
+// (MN-major operand: 8 consecutive pixels = 8 consecutive 128-byte rows = one swizzle group,
+// the next output row is SBO = halo_width*128 bytes further).  Each tap owns a TMEM
+// accumulator; a CTA keeps all of them for its whole range of pixel tiles (split-K over the
+// pixels) and adds them into dw with fp32 red.global at the end.
+//   pair mode  (Cin == 64): all taps in one CTA; two taps share one M=128 instruction, the
+//               second tap being the "next 64-channel atom" at LBO = its byte distance in the halo.
+//   group mode (Cin >= 128): one kernel row (kw taps) per CTA, M = 128 input channels held in two
+//               halo boxes LBO apart.
+constexpr int kWhMaxGroups = 8;
+constexpr int kWhMaxAcc = 8;
+struct WgradHaloArgs {
+  CUtensorMap mapX;    // box (64 ch, hwb, box_h, 1)
+  CUtensorMap mapDy;   // box (64 ch, 8, 16, 1)
+  float* dw;
+  int n_acc, block_n, nb_atoms, a_atoms, a_box_bytes, a_stride, stages, tmem_cols;
+  int hwb, tiles_w, tiles_h, tiles_total, units_ci, units_co, groups, splits;
+  int cin, cout, ci_tile, org_w;
+  int org_h[kWhMaxGroups];
+  int aoff[kWhMaxGroups][kWhMaxAcc];   // byte offset of the accumulator's (first) tap in the halo
+  int lbo[kWhMaxGroups][kWhMaxAcc];    // byte distance to the operand's second 64-row atom
+  short tap_lo[kWhMaxGroups][kWhMaxAcc];  // tap written by accumulator rows 0..63 (-1: discard)
+  short tap_hi[kWhMaxGroups][kWhMaxAcc];  // tap of rows 64..127 (-2: same tap, channels + 64)
+};
+
+__global__ void __launch_bounds__(192, 1)
+wgrad_halo_kernel(const __grid_constant__ WgradHaloArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int stages = args.stages;
+  const uint32_t a_bytes = static_cast<uint32_t>(args.a_atoms) * args.a_stride;
+  const uint32_t b_bytes = static_cast<uint32_t>(args.nb_atoms) * kABytes;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(stages) * stage_bytes);
+  uint64_t* empty = full + stages;
+  uint64_t* tmem_full = empty + stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  int w = blockIdx.x;
+  const int split = w % args.splits;
+  w /= args.splits;
+  const int g = w % args.groups;
+  w /= args.groups;
+  const int co_t = w % args.units_co;
+  const int ci_t = w / args.units_co;
+  const int t0 = static_cast<int>(static_cast<long long>(split) * args.tiles_total / args.splits);
+  const int t1 = static_cast<int>(static_cast<long long>(split + 1) * args.tiles_total / args.splits);
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&args.mapX);
+    ptx::prefetch_tmap(&args.mapDy);
+    for (int s = 0; s < stages; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    ptx::mbar_init(tmem_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, static_cast<uint32_t>(args.tmem_cols));
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int tiles_per_img = args.tiles_w * args.tiles_h;
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      const uint32_t tx = static_cast<uint32_t>(args.a_atoms) * args.a_box_bytes + b_bytes;
+      for (int t = t0, it = 0; t < t1; ++t, ++it) {
+        const int s = it % stages;
+        const uint32_t ph = static_cast<uint32_t>(it / stages) & 1u;
+        ptx::mbar_wait(&empty[s], ph ^ 1u);
+        ptx::mbar_expect_tx(&full[s], tx);
+        uint8_t* sA = smem + static_cast<size_t>(s) * stage_bytes;
+        uint8_t* sB = sA + a_bytes;
+        const int n = t / tiles_per_img;
+        const int r = t - n * tiles_per_img;
+        const int h0 = (r / args.tiles_w) * 16, w0 = (r % args.tiles_w) * 8;
+        for (int a = 0; a < args.a_atoms; ++a)
+          ptx::tma_load_4d(&args.mapX, &full[s], sA + static_cast<size_t>(a) * args.a_stride,
+                           ci_t * args.ci_tile + a * 64, w0 + args.org_w, h0 + args.org_h[g], n);
+        for (int j = 0; j < args.nb_atoms; ++j)
+          ptx::tma_load_4d(&args.mapDy, &full[s], sB + static_cast<size_t>(j) * kABytes,
+                           co_t * args.block_n + j * 64, w0, h0, n);
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = ptx::make_idesc_bf16(128, args.block_n, 1, 1);
+    const uint32_t row_pitch = static_cast<uint32_t>(args.hwb) * 128u;   // one output row further
+    for (int t = t0, it = 0; t < t1; ++t, ++it) {
+      const int s = it % stages;
+      const uint32_t ph = static_cast<uint32_t>(it / stages) & 1u;
+      ptx::mbar_wait(&full[s], ph);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint32_t a_addr = ptx::smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
+        const uint32_t b_addr = a_addr + a_bytes;
+        for (int acc = 0; acc < args.n_acc; ++acc) {
+          const uint32_t a0 = a_addr + static_cast<uint32_t>(args.aoff[g][acc]);
+          const uint32_t lbo = static_cast<uint32_t>(args.lbo[g][acc]);
+          const uint32_t td = tmem_base + static_cast<uint32_t>(acc * args.block_n);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            // K = 16 pixels = output rows 2j and 2j+1 of the tile (8 pixels each)
+            const uint64_t ad = ptx::make_smem_desc(a0 + j * 2 * row_pitch, lbo, row_pitch);
+            const uint64_t bd = ptx::make_smem_desc(b_addr + j * 2048, kABytes, 1024);
+            ptx::umma_bf16(td, ad, bd, idesc, (it | j) != 0 ? 1u : 0u);
+          }
+        }
+        ptx::umma_commit(&empty[s]);
+        if (t == t1 - 1) ptx::umma_commit(tmem_full);
+      }
+      __syncwarp();
+    }
+  } else if (t1 > t0) {
+    ptx::mbar_wait(tmem_full, 0);
+    ptx::tc_fence_after();
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    for (int acc = 0; acc < args.n_acc; ++acc) {
+      const int tlo = args.tap_lo[g][acc], thi = args.tap_hi[g][acc];
+      int tap, ci;
+      if (thi == -2) {
+        tap = tlo;
+        ci = ci_t * args.ci_tile + row;
+      } else {
+        tap = row < 64 ? tlo : thi;
+        ci = ci_t * args.ci_tile + (row & 63);
+      }
+      const bool ok = tap >= 0 && ci < args.cin;
+      for (int c0 = 0; c0 < args.block_n; c0 += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                               static_cast<uint32_t>(acc * args.block_n + c0), r);
+        ptx::tmem_ld_wait();
+        if (!ok) continue;
+        const int co0 = co_t * args.block_n + c0;
+        if (co0 >= args.cout) continue;
+        float* o = args.dw + (static_cast<long long>(tap) * args.cin + ci) * args.cout + co0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          ptx::red_add_v4(o + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                          __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
       }
     }
   }
@@ -858,7 +1128,8 @@ int launch_gemm_conv(GemmConvArgs& a, int tiles_m, cudaStream_t st) {
   a.stages = stages;
   a.tmem_cols = 2 * tmem_cols_for(a.block_n);   // double-buffered accumulator
   a.total_tiles = tiles_m * a.tiles_n;
-  size_t smem = static_cast<size_t>(stages) * stage_bytes + (2 * stages + 4) * 8 + 16 + 1024;
+  size_t smem = static_cast<size_t>(stages) * stage_bytes + kBarRegionBytes +
+                (a.e.stats ? kStatSmemBytes : 0) + 1024;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(gemm_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -889,9 +1160,10 @@ bool halo_eligible(int cin, int kh, int kw, int sh, int sw, int dh, int dw, int 
 int launch_halo(const void* in, int C_in, int W_in, int H_in, int N, const void* wmat, int taps_rows,
                 int n_total, int kh, int kw, int dh, int dw, int org_h, int org_w, bool flip,
                 int Ho, int Wo, void* out, int out_f32, const float* bias, int accumulate,
-                cudaStream_t st) {
+                double* stats, cudaStream_t st) {
   HaloArgs a;
   std::memset(&a, 0, sizeof(a));
+  a.e.stats = stats;
   int rc;
   a.hwb = 8 + (kw - 1) * dw;
   a.hhb = 16 + (kh - 1) * dh;
@@ -929,7 +1201,7 @@ int launch_halo(const void* in, int C_in, int W_in, int H_in, int N, const void*
   const long long b_all = (long long)a.taps * a.k_chunks * b_bytes;
   a.b_stationary = (a.tiles_n == 1 && b_all <= 100 * 1024) ? 1 : 0;
   a.a_stages = 3;
-  const long long budget = 200 * 1024 - (long long)a.a_stages * a.halo_stride;
+  const long long budget = (stats ? 192 : 200) * 1024 - (long long)a.a_stages * a.halo_stride;
   if (a.b_stationary) {
     a.b_stages = 1;
   } else {
@@ -948,8 +1220,8 @@ int launch_halo(const void* in, int C_in, int W_in, int H_in, int N, const void*
   a.tmem_cols = 2 * tmem_cols_for(a.e.block_n);
   a.total_tiles = a.tiles_w * a.tiles_h * N * a.tiles_n;
   const int nb_slots = a.b_stationary ? a.taps * a.k_chunks : a.b_stages;
-  size_t smem = (size_t)a.a_stages * a.halo_stride + (size_t)nb_slots * b_bytes +
-                (2 * a.a_stages + 2 * a.b_stages + 4) * 8 + 16 + 1024;
+  size_t smem = (size_t)a.a_stages * a.halo_stride + (size_t)nb_slots * b_bytes + kBarRegionBytes +
+                (a.e.stats ? kStatSmemBytes : 0) + 1024;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(halo_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -973,10 +1245,16 @@ bool tc_shape_ok(const mcn_conv_desc* d) {
 
 using namespace mcn;
 
-extern "C" int mcn_conv2d_fprop_tc(const mcn_conv_desc* d, const void* x, const void* w_ohwi,
-                                   const float* bias, void* y, int y_dtype, int a_mode,
-                                   int accumulate, void* stream) {
+static int fprop_tc_impl(const mcn_conv_desc* d, const void* x, const void* w_ohwi,
+                         const float* bias, void* y, int y_dtype, int a_mode, int accumulate,
+                         double* bn_sums, void* stream) {
   MCN_REQUIRE(d && x && w_ohwi && y, "fprop_tc: null argument");
+  if (bn_sums != nullptr) {
+    MCN_REQUIRE(y_dtype == MCN_BF16 && !accumulate && d->Cout % 64 == 0 &&
+                    reinterpret_cast<uintptr_t>(y) % 32 == 0,
+                "fprop_tc: fused BN statistics need a bf16, 32-byte aligned, non-accumulating output "
+                "with Cout %% 64 == 0 (Cout=%d)", d->Cout);
+  }
   MCN_REQUIRE(d->Cin % 8 == 0, "fprop_tc: Cin=%d must be a multiple of 8 (16-byte TMA rows)", d->Cin);
   MCN_REQUIRE(d->kh * d->kw <= kMaxTaps, "fprop_tc: too many taps");
   const bool pointwise = d->kh == 1 && d->kw == 1 && d->sh == 1 && d->sw == 1;
@@ -984,7 +1262,7 @@ extern "C" int mcn_conv2d_fprop_tc(const mcn_conv_desc* d, const void* x, const 
     if (halo_eligible(d->Cin, d->kh, d->kw, d->sh, d->sw, d->dh, d->dw, d->Ho, d->Wo))
       return launch_halo(x, d->Cin, d->W, d->H, d->N, w_ohwi, d->Cout, d->Cout, d->kh, d->kw, d->dh,
                          d->dw, -d->pad_t, -d->pad_l, false, d->Ho, d->Wo, y, y_dtype == MCN_F32, bias,
-                         accumulate, static_cast<cudaStream_t>(stream));
+                         accumulate, bn_sums, static_cast<cudaStream_t>(stream));
     a_mode = 1;
   }
   if (a_mode == 1 && (d->Cin % 64 != 0 || pointwise)) a_mode = 0;
@@ -1054,6 +1332,7 @@ extern "C" int mcn_conv2d_fprop_tc(const mcn_conv_desc* d, const void* x, const 
   }
   a.e.n_total = d->Cout;
   a.e.out = y;
+  a.e.stats = bn_sums;
   a.e.out_f32 = (y_dtype == MCN_F32);
   a.e.bias = bias;
   a.e.vec_ok = (d->Cout % 16 == 0) && (reinterpret_cast<uintptr_t>(y) % 32 == 0);
@@ -1072,6 +1351,18 @@ extern "C" int mcn_conv2d_fprop_tc(const mcn_conv_desc* d, const void* x, const 
       }
     }
   return launch_gemm_conv(a, tiles_m_of(a.g), static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mcn_conv2d_fprop_tc(const mcn_conv_desc* d, const void* x, const void* w_ohwi,
+                                   const float* bias, void* y, int y_dtype, int a_mode,
+                                   int accumulate, void* stream) {
+  return fprop_tc_impl(d, x, w_ohwi, bias, y, y_dtype, a_mode, accumulate, nullptr, stream);
+}
+extern "C" int mcn_conv2d_fprop_tc_stats(const mcn_conv_desc* d, const void* x, const void* w_ohwi,
+                                         const float* bias, void* y, int a_mode, double* bn_sums,
+                                         void* stream) {
+  MCN_REQUIRE(bn_sums != nullptr, "fprop_tc_stats: bn_sums is null");
+  return fprop_tc_impl(d, x, w_ohwi, bias, y, MCN_BF16, a_mode, 0, bn_sums, stream);
 }
 
 // dgrad.
@@ -1191,7 +1482,7 @@ extern "C" int mcn_conv2d_dgrad_tc(const mcn_conv_desc* d, const void* dy, const
     if (halo_eligible(d->Cout, d->kh, d->kw, d->sh, d->sw, d->dh, d->dw, d->H, d->W))
       return launch_halo(dy, d->Cout, d->Wo, d->Ho, d->N, w_hwio, d->Cin, d->Cin, d->kh, d->kw, d->dh,
                          d->dw, d->pad_t - (d->kh - 1) * d->dh, d->pad_l - (d->kw - 1) * d->dw, true,
-                         d->H, d->W, dx, dx_dtype == MCN_F32, nullptr, accumulate, st);
+                         d->H, d->W, dx, dx_dtype == MCN_F32, nullptr, accumulate, nullptr, st);
     a_mode = 1;
   }
   // phases without a contributing tap (e.g. 1x1 stride 2) stay zero
@@ -1220,11 +1511,123 @@ extern "C" int mcn_conv2d_dgrad_tc(const mcn_conv_desc* d, const void* dy, const
   return MCN_OK;
 }
 
+// Halo wgrad: returns 1 when the geometry is eligible and the launch was issued, 0 when the
+// caller should use the tap-at-a-time kernel, negative on error.
+static int try_wgrad_halo(const mcn_conv_desc* d, const void* x, const void* dy, float* dw,
+                          cudaStream_t st) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("MCN_WGRAD_HALO");
+    enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!enabled) return 0;
+  if (d->sh != 1 || d->sw != 1 || (d->kh == 1 && d->kw == 1)) return 0;
+  if (d->Cin % 64 != 0 || d->Cout % 64 != 0) return 0;
+  if (d->kh > kWhMaxGroups || d->kw > kWhMaxAcc) return 0;
+  const int taps = d->kh * d->kw;
+  WgradHaloArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.hwb = 8 + (d->kw - 1) * d->dw;
+  const bool pair = d->Cin == 64 && taps >= 2 && ((taps + 1) / 2) <= kWhMaxAcc &&
+                    ((taps + 1) / 2) * 64 <= 512;
+  int box_h;
+  if (pair) {
+    a.groups = 1;
+    box_h = 16 + (d->kh - 1) * d->dh;
+    a.block_n = 64;
+    a.n_acc = (taps + 1) / 2;
+    a.a_atoms = 1;
+    a.ci_tile = 64;
+  } else {
+    if (d->Cin < 128) return 0;
+    a.groups = d->kh;
+    box_h = 16;
+    a.block_n = (d->kw * 128 <= 512 && d->Cout % 128 == 0) ? 128 : 64;
+    if (d->kw * a.block_n > 512) return 0;
+    a.n_acc = d->kw;
+    a.a_atoms = 2;
+    a.ci_tile = 128;
+  }
+  if (a.hwb > 256 || box_h > 256) return 0;
+  a.a_box_bytes = a.hwb * box_h * 128;
+  if (a.a_box_bytes > 48 * 1024) return 0;
+  a.a_stride = (a.a_box_bytes + 1023) / 1024 * 1024;
+  a.tiles_w = (d->Wo + 7) / 8;
+  a.tiles_h = (d->Ho + 15) / 16;
+  const double eff = (double)(d->Ho * d->Wo) / ((double)a.tiles_h * 16 * a.tiles_w * 8);
+  if (eff < 0.7) return 0;
+  a.nb_atoms = a.block_n / 64;
+  const uint32_t stage_bytes = a.a_atoms * a.a_stride + a.nb_atoms * kABytes;
+  a.stages = std::min(4, (int)((216 * 1024) / stage_bytes));
+  if (a.stages < 2) return 0;
+  int cols = a.n_acc * a.block_n;
+  a.tmem_cols = 32;
+  while (a.tmem_cols < cols) a.tmem_cols *= 2;
+  a.tiles_total = d->N * a.tiles_w * a.tiles_h;
+  a.units_ci = (d->Cin + a.ci_tile - 1) / a.ci_tile;
+  a.units_co = (d->Cout + a.block_n - 1) / a.block_n;
+  const int units = a.units_ci * a.units_co * a.groups;
+  a.splits = std::max(1, std::min(a.tiles_total, num_sms() / units));
+  a.cin = d->Cin;
+  a.cout = d->Cout;
+  a.dw = dw;
+  a.org_w = -d->pad_l;
+  auto off = [&](int r, int s2) { return (r * d->dh * a.hwb + s2 * d->dw) * 128; };
+  if (pair) {
+    a.org_h[0] = -d->pad_t;
+    for (int i = 0; i < a.n_acc; ++i) {
+      int lo = 2 * i, hi = 2 * i + 1;
+      bool discard_lo = false;
+      if (hi >= taps) {   // odd tap count: the last tap rides in the upper half next to its predecessor
+        hi = taps - 1;
+        lo = taps - 2;
+        discard_lo = true;
+      }
+      a.aoff[0][i] = off(lo / d->kw, lo % d->kw);
+      a.lbo[0][i] = off(hi / d->kw, hi % d->kw) - a.aoff[0][i];
+      a.tap_lo[0][i] = (short)(discard_lo ? -1 : lo);
+      a.tap_hi[0][i] = (short)hi;
+      if (a.lbo[0][i] <= 0) return 0;
+    }
+  } else {
+    for (int r = 0; r < d->kh; ++r) {
+      a.org_h[r] = -d->pad_t + r * d->dh;
+      for (int s2 = 0; s2 < d->kw; ++s2) {
+        a.aoff[r][s2] = s2 * d->dw * 128;
+        a.lbo[r][s2] = a.a_stride;
+        a.tap_lo[r][s2] = (short)(r * d->kw + s2);
+        a.tap_hi[r][s2] = -2;
+      }
+    }
+  }
+  int rc;
+  if ((rc = encode_nhwc(&a.mapX, x, d->Cin, d->W, d->H, d->N, a.hwb, box_h, 1))) return rc;
+  if ((rc = encode_nhwc(&a.mapDy, dy, d->Cout, d->Wo, d->Ho, d->N, 8, 16, 1))) return rc;
+  size_t smem = (size_t)a.stages * stage_bytes + kBarRegionBytes + 1024;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             smem_optin_limit()) != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(wgrad_halo_kernel) failed");
+      return MCN_ECUDA;
+    }
+    configured = true;
+  }
+  dim3 grid((unsigned)(units * a.splits));
+  wgrad_halo_kernel<<<grid, 192, smem, st>>>(a);
+  rc = after_launch("wgrad_halo_kernel");
+  return rc ? rc : 1;
+}
+
 extern "C" int mcn_conv2d_wgrad_tc(const mcn_conv_desc* d, const void* x, const void* dy,
                                    float* dw, int a_mode, void* stream) {
   MCN_REQUIRE(d && x && dy && dw, "wgrad_tc: null argument");
   MCN_REQUIRE(d->Cin % 8 == 0 && d->Cout % 8 == 0, "wgrad_tc: channels must be multiples of 8");
-  if (a_mode == 2) a_mode = 1;   // no halo variant of wgrad yet
+  if (a_mode == 2) {
+    int rc = try_wgrad_halo(d, x, dy, dw, static_cast<cudaStream_t>(stream));
+    if (rc != 0) return rc < 0 ? rc : MCN_OK;
+    a_mode = 1;   // not eligible: tap-at-a-time kernel with the im2col feed
+  }
   MCN_REQUIRE(d->kh * d->kw <= kMaxTaps, "wgrad_tc: too many taps");
   const bool pointwise = d->kh == 1 && d->kw == 1 && d->sh == 1 && d->sw == 1;
   if (a_mode == 1 && (d->Cin % 64 != 0 || pointwise)) a_mode = 0;

@@ -30,6 +30,7 @@ _T = {"p": ctypes.c_void_p, "i": ctypes.c_int, "l": ctypes.c_longlong, "f": ctyp
 # name -> argument codes WITHOUT the trailing stream (every entry ends with a void* stream)
 SIGNATURES = {
     "mcn_conv2d_fprop_tc": "Dppppiii",
+    "mcn_conv2d_fprop_tc_stats": "Dppppip",
     "mcn_conv2d_dgrad_tc": "Dpppiii",
     "mcn_conv2d_wgrad_tc": "Dpppi",
     "mcn_conv2d_fprop_direct": "Dipippp",
@@ -43,6 +44,7 @@ SIGNATURES = {
     "mcn_bn_stats": "iplip",
     "mcn_bn_finalize": "pdiffpppp",
     "mcn_bn_apply": "iplipppppifp",
+    "mcn_bn_apply_stats": "iplipdffpppifppppp",
     "mcn_bn_infer": "iplippfpppifp",
     "mcn_bn_bwd_reduce": "ippplippppifpp",
     "mcn_bn_bwd_apply": "ippplippppifppdpp",

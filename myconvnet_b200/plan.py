@@ -112,8 +112,11 @@ class TempAllocator(object):
 
 class Plan(object):
     def __init__(self, graph, world_size=1, keep=(), conv_mode=2, fetch_pred=True,
-                 sync_bn=True, loss_scale=1.0):
+                 sync_bn=True, loss_scale=1.0, fuse_bn_stats=None):
         self.graph = graph
+        if fuse_bn_stats is None:
+            fuse_bn_stats = os.environ.get("MCN_FUSE_BN_STATS", "1") != "0"
+        self.fuse_bn_stats = bool(fuse_bn_stats)
         self.world = int(world_size)
         self.keep = set(keep)            # tensors that must stay materialised (parity taps)
         self.conv_mode = conv_mode       # 2 = halo tiles where they pay off else im2col TMA, 1 = im2col, 0 = box
@@ -296,8 +299,19 @@ class Plan(object):
     def _fuse(self):
         for node in self.graph.nodes:
             node.attrs["fused_into"] = None          # a graph may be planned more than once
+            node.attrs["bn_stats_node"] = None
         for node in self.graph.nodes:
             if node.op == "bn":
+                # conv -> BN: the statistics are taken in the tensor-core conv's epilogue
+                prod = node.inputs[0].node
+                node.attrs["stats_in_conv"] = False
+                if (self.fuse_bn_stats and self.cdt == "bf16" and prod is not None
+                        and prod.op == "conv2d" and prod.attrs.get("route") in ("tc", "im2col")
+                        and prod.attrs["bn_stats_node"] is None
+                        and node.inputs[0].shape[-1] % 64 == 0
+                        and self._stats_fusion_pays(prod)):
+                    prod.attrs["bn_stats_node"] = node
+                    node.attrs["stats_in_conv"] = True
                 node.attrs["act"], node.attrs["alpha"] = 0, 0.0
                 node.attrs["residual"] = None
                 node.attrs["final"] = node.outputs[0]
@@ -443,9 +457,15 @@ class Plan(object):
         py = self.alloc_act(y)
         route = node.attrs["route"]
         pb = self.pvar(b) if b is not None else NULL
+        bn = node.attrs.get("bn_stats_node") if self.phase == "train" else None
+        psums = Ptr(self._bn_sums_buf(bn)) if bn is not None else None
         if route == "tc":
-            self.L("f", "mcn_conv2d_fprop_tc", d, self.tbuf[x], self.pbf16t(w), pb, py, self.ccode,
-                   self.conv_mode, 0, tag=node.scope)
+            if bn is not None:
+                self.L("f", "mcn_conv2d_fprop_tc_stats", d, self.tbuf[x], self.pbf16t(w), pb, py,
+                       self.conv_mode, psums, tag=node.scope)
+            else:
+                self.L("f", "mcn_conv2d_fprop_tc", d, self.tbuf[x], self.pbf16t(w), pb, py, self.ccode,
+                       self.conv_mode, 0, tag=node.scope)
         elif route == "im2col":
             kpad = node.attrs["kpad"]
             m = d.N * d.Ho * d.Wo
@@ -456,12 +476,30 @@ class Plan(object):
             node.attrs["gemm_desc"] = gd
             self.L("f", "mcn_im2col", d, DT_CODE[x.dtype], self.tbuf[x], Ptr(col), kpad,
                    tag=node.scope + "/im2col")
-            self.L("f", "mcn_conv2d_fprop_tc", gd, Ptr(col), self.pbf16t(w), pb, py, self.ccode, 0, 0,
-                   tag=node.scope)
+            if bn is not None:
+                self.L("f", "mcn_conv2d_fprop_tc_stats", gd, Ptr(col), self.pbf16t(w), pb, py, 0, psums,
+                       tag=node.scope)
+            else:
+                self.L("f", "mcn_conv2d_fprop_tc", gd, Ptr(col), self.pbf16t(w), pb, py, self.ccode, 0, 0,
+                       tag=node.scope)
         else:
             wdt, pw = self._direct_weight(w)
             self.L("f", "mcn_conv2d_fprop_direct", d, self.ccode, self.tbuf[x], wdt, pw, pb, py,
                    tag=node.scope)
+
+    @staticmethod
+    def _stats_fusion_pays(conv):
+        """The epilogue statistics cost ~0.5-1.4k cycles per 128x64 output chunk.  That hides behind
+        the MMAs when the reduction is deep (K = kh*kw*Cin) and shows when the conv is epilogue /
+        store bound (1x1 expansions with small K).  Rule fitted on the per-layer A/B profile of
+        ResNet-50 at batch 256 (profiles/r01_fused_stats_ab.txt)."""
+        kh, kw, ci, co = conv.vars["w"].shape
+        k = kh * kw * ci
+        return k >= 512 or (k >= 128 and co <= 64)
+
+    def _bn_sums_buf(self, bn_node):
+        c = bn_node.inputs[0].shape[-1]
+        return self.node_buf(bn_node, "sums", "bn_sums:%s" % bn_node.scope, 2 * c * 8, "zero")
 
     def _direct_weight(self, w):
         return 0, self.pvar(w)   # fp32 master weights
@@ -562,7 +600,7 @@ class Plan(object):
                    self.tbuf[res] if res is not None else NULL, node.attrs["act"], node.attrs["alpha"], py,
                    tag=node.scope + "/infer")
             return
-        sums = self.new_buf("bn_sums:%s" % node.scope, 2 * c * 8, "zero")
+        sums = self._bn_sums_buf(node)
         save = self.new_buf("bn_save:%s" % node.scope, 2 * c * 4, "state")
         node.attrs["save"] = save
         node.attrs["rows"] = rows
@@ -573,16 +611,26 @@ class Plan(object):
         pbeta = self.pvar(v["beta"]) if "beta" in v else NULL
         res = node.attrs["residual"]
         pres = self.tbuf[res] if res is not None else NULL
-        self.L("f", "mcn_bn_stats", self.ccode, self.tbuf[x], rows, c, Ptr(sums), tag=node.scope + "/stats")
+        if not node.attrs.get("stats_in_conv"):
+            self.L("f", "mcn_bn_stats", self.ccode, self.tbuf[x], rows, c, Ptr(sums), tag=node.scope + "/stats")
         if self.sync_bn:
             self.allreduce_points.append(("f", len(self.fwd), Ptr(sums), 2 * c * 8, "f64"))
         upd = node.attrs["update"]
-        self.L("f", "mcn_bn_finalize", Ptr(sums), float(rows * (self.world if self.sync_bn else 1)), c,
-               node.attrs["eps"], node.attrs["momentum"], Ptr(save), Ptr(save, c * 4),
+        if os.environ.get("MCN_BN_FOLD_FINALIZE", "1") == "0":     # A/B switch: separate finalize launch
+            self.L("f", "mcn_bn_finalize", Ptr(sums), float(rows * (self.world if self.sync_bn else 1)), c,
+                   node.attrs["eps"], node.attrs["momentum"], Ptr(save), Ptr(save, c * 4),
+                   self.pvar(v["mu"]) if upd else NULL, self.pvar(v["sigma"]) if upd else NULL,
+                   tag=node.scope + "/finalize")
+            self.L("f", "mcn_bn_apply", self.ccode, self.tbuf[x], rows, c, Ptr(save), Ptr(save, c * 4), pg,
+                   pbeta, pres, node.attrs["act"], node.attrs["alpha"], py, tag=node.scope + "/apply")
+            self.bn_layers.append(node)
+            return
+        # finalize (mean / invstd / moving statistics) happens in the apply kernel's prologue
+        self.L("f", "mcn_bn_apply_stats", self.ccode, self.tbuf[x], rows, c, Ptr(sums),
+               float(rows * (self.world if self.sync_bn else 1)), node.attrs["eps"], node.attrs["momentum"],
+               pg, pbeta, pres, node.attrs["act"], node.attrs["alpha"], py, Ptr(save), Ptr(save, c * 4),
                self.pvar(v["mu"]) if upd else NULL, self.pvar(v["sigma"]) if upd else NULL,
-               tag=node.scope + "/finalize")
-        self.L("f", "mcn_bn_apply", self.ccode, self.tbuf[x], rows, c, Ptr(save), Ptr(save, c * 4), pg,
-               pbeta, pres, node.attrs["act"], node.attrs["alpha"], py, tag=node.scope + "/apply")
+               tag=node.scope + "/apply")
         self.bn_layers.append(node)
 
     def _f_act(self, node):

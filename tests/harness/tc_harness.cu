@@ -105,6 +105,19 @@ static std::vector<Case> cases() {
   c.push_back({"T dgrad 3x3 14x14 256->256 b64 im2col", 1, 64, 14, 14, 256, 256, 3, 1, 1, 1, 1, 0, 0, 20});
   c.push_back({"T wgrad 3x3 14x14 256->256 b64 im2col", 2, 64, 14, 14, 256, 256, 3, 1, 1, 1, 1, 0, 0, 20});
   c.push_back({"T wgrad 1x1 56x56 64->256 b64", 2, 64, 56, 56, 64, 256, 1, 1, 1, 0, 1, 0, 0, 20});
+  // halo wgrad (a_mode 2): pair mode (Cin 64) and group mode (Cin >= 128)
+  c.push_back({"wgrad 3x3 halo pair 56x56 64->64", 2, 2, 56, 56, 64, 64, 3, 1, 1, 2, 1, 0, 0, 0});
+  c.push_back({"wgrad 3x3 halo pair 30x20 64->128 ragged", 2, 3, 30, 20, 64, 128, 3, 1, 1, 2, 1, 0, 0, 0});
+  c.push_back({"wgrad 3x3 halo pair d2 32x32 64->64", 2, 1, 32, 32, 64, 64, 3, 1, 2, 2, 1, 0, 0, 0});
+  c.push_back({"wgrad 3x3 halo group 28x28 128->128", 2, 2, 28, 28, 128, 128, 3, 1, 1, 2, 1, 0, 0, 0});
+  c.push_back({"wgrad 3x3 halo group 14x14 256->256", 2, 3, 14, 14, 256, 256, 3, 1, 1, 2, 1, 0, 0, 0});
+  c.push_back({"wgrad 3x3 halo group 30x20 192->64 ragged", 2, 2, 30, 20, 192, 64, 3, 1, 1, 2, 1, 0, 0, 0});
+  c.push_back({"wgrad 3x3 halo group VALID 34x34 128->128", 2, 1, 34, 34, 128, 128, 3, 1, 1, 2, 0, 0, 0, 0});
+  c.push_back({"T wgrad 3x3 56x56 64->64 b64 halo", 2, 64, 56, 56, 64, 64, 3, 1, 1, 2, 1, 0, 0, 20});
+  c.push_back({"T wgrad 3x3 56x56 64->64 b64 im2col", 2, 64, 56, 56, 64, 64, 3, 1, 1, 1, 1, 0, 0, 20});
+  c.push_back({"T wgrad 3x3 28x28 128->128 b64 halo", 2, 64, 28, 28, 128, 128, 3, 1, 1, 2, 1, 0, 0, 20});
+  c.push_back({"T wgrad 3x3 28x28 128->128 b64 im2col", 2, 64, 28, 28, 128, 128, 3, 1, 1, 1, 1, 0, 0, 20});
+  c.push_back({"T wgrad 3x3 14x14 256->256 b64 halo", 2, 64, 14, 14, 256, 256, 3, 1, 1, 2, 1, 0, 0, 20});
   return c;
 }
 

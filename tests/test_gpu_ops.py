@@ -136,6 +136,107 @@ def test_conv_tensor_core(L, case, mode):
     assert rel_l2(y2.float().cpu(), yref.detach() + ybase) < 6e-3
 
 
+STATS_CASES = [
+    # n, h, w, ci, co, k, stride, mode  (mode 2 = halo tiles where eligible)
+    (2, 14, 14, 64, 64, 3, 1, 1),
+    (3, 16, 16, 128, 256, 1, 1, 0),      # block_n 256
+    (2, 28, 28, 64, 128, 3, 2, 1),
+    (1, 56, 56, 64, 64, 3, 1, 2),        # halo kernel, weight-stationary
+    (1, 62, 54, 64, 192, 3, 1, 2),       # halo kernel with ragged tiles; Cout 192 = 2 n-tiles of 128
+    (5, 7, 7, 128, 512, 1, 1, 0),        # box tiles merged over the batch, rows of padding in the last tile
+    (2, 12, 12, 64, 2048, 1, 1, 0),      # 8 n-tiles: per-CTA accumulator flushes between tiles
+]
+
+
+@pytest.mark.parametrize("case", STATS_CASES)
+@pytest.mark.parametrize("bias", [False, True])
+def test_conv_fused_bn_statistics(L, case, bias):
+    """mcn_conv2d_fprop_tc_stats: same y as the plain kernel, and sums = per-channel sum / sum of
+    squares of the STORED bf16 output (what the separate mcn_bn_stats pass would have read)."""
+    n, h, w, ci, co, k, s, mode = case
+    rng = np.random.default_rng(3)
+    r = lambda a: torch.tensor(a).bfloat16().float().numpy()
+    x = r(rng.standard_normal((n, h, w, ci)).astype(np.float32) + 0.3)
+    wt = r((rng.standard_normal((k, k, ci, co)) * 0.1).astype(np.float32))
+    b = rng.standard_normal(co).astype(np.float32) if bias else None
+    d, ho, wo = desc_for(L, x.shape, wt.shape, s, 1, "SAME")
+    lib = L.load()
+    xd, wd = dev(x, torch.bfloat16), dev(wt)
+    bd = dev(b) if bias else None
+    w_hwio = torch.empty(k * k, ci, co, device="cuda", dtype=torch.bfloat16)
+    w_ohwi = torch.empty(k * k, co, ci, device="cuda", dtype=torch.bfloat16)
+    L.check(lib.mcn_weight_prep(wd.data_ptr(), k * k, ci, co, w_hwio.data_ptr(), w_ohwi.data_ptr(), None))
+    y0 = torch.empty(n, ho, wo, co, device="cuda", dtype=torch.bfloat16)
+    y1 = torch.full_like(y0, 3.0)
+    bp = bd.data_ptr() if bias else None
+    L.check(lib.mcn_conv2d_fprop_tc(d, xd.data_ptr(), w_ohwi.data_ptr(), bp, y0.data_ptr(), 1, mode, 0, None))
+    sums = torch.zeros(2 * co, dtype=torch.float64, device="cuda")
+    L.check(lib.mcn_conv2d_fprop_tc_stats(d, xd.data_ptr(), w_ohwi.data_ptr(), bp, y1.data_ptr(), mode,
+                                          sums.data_ptr(), None))
+    ref = torch.zeros(2 * co, dtype=torch.float64, device="cuda")
+    L.check(lib.mcn_bn_stats(1, y0.data_ptr(), n * ho * wo, co, ref.data_ptr(), None))
+    torch.cuda.synchronize()
+    assert torch.equal(y0, y1)                                   # bit-identical output
+    yf = y0.double().reshape(-1, co)
+    exact = torch.cat([yf.sum(0), (yf * yf).sum(0)]).cpu().numpy()
+    scale = np.concatenate([np.abs(yf.cpu().numpy()).sum(0), (yf * yf).sum(0).cpu().numpy()]) + 1e-30
+    assert np.max(np.abs(sums.cpu().numpy() - exact) / scale) < 2e-6      # fp32 partials, fp64 totals
+    assert np.max(np.abs(ref.cpu().numpy() - exact) / scale) < 2e-6
+    # the oracle's convolution agrees with the stored output
+    yref = tf_ops.conv2d(torch.tensor(x), torch.tensor(wt), (s, s), "SAME", (1, 1))
+    if bias:
+        yref = yref + torch.tensor(b)
+    assert rel_l2(y1.float().cpu(), yref) < 6e-3
+
+
+@pytest.mark.parametrize("code", [0, 1])
+@pytest.mark.parametrize("C", [64, 20, 320])
+@pytest.mark.parametrize("use_res", [False, True])
+def test_bn_apply_from_sums_matches_finalize_then_apply(L, code, C, use_res):
+    """mcn_bn_apply_stats == mcn_bn_finalize + mcn_bn_apply (saved statistics, moving statistics,
+    output), and agrees with the oracle's fused_batch_norm."""
+    lib = L.load()
+    rng = np.random.default_rng(4)
+    rows, eps, mom = 3 * 9 * 11, 1e-3, 0.9
+    dt = tdt(code)
+    q = (lambda a: torch.tensor(a).to(dt).float().numpy())
+    x = q((rng.standard_normal((rows, C)) * 2 + 0.7).astype(np.float32))
+    res = q(rng.standard_normal((rows, C)).astype(np.float32))
+    gamma = rng.uniform(0.5, 1.5, C).astype(np.float32)
+    beta = rng.standard_normal(C).astype(np.float32)
+    mm = rng.standard_normal(C).astype(np.float32)
+    mv = rng.uniform(0.5, 2, C).astype(np.float32)
+    xd, rd, gd, bd = dev(x, dt), dev(res, dt), dev(gamma), dev(beta)
+    sums = torch.zeros(2 * C, dtype=torch.float64, device="cuda")
+    L.check(lib.mcn_bn_stats(code, xd.data_ptr(), rows, C, sums.data_ptr(), None))
+    outs = []
+    for fused in (False, True):
+        mmd, mvd = dev(mm), dev(mv)
+        save = torch.zeros(2 * C, device="cuda")
+        y = torch.empty_like(xd)
+        rp = rd.data_ptr() if use_res else None
+        if fused:
+            L.check(lib.mcn_bn_apply_stats(code, xd.data_ptr(), rows, C, sums.data_ptr(), float(rows), eps, mom,
+                                           gd.data_ptr(), bd.data_ptr(), rp, 1, 0.0, y.data_ptr(),
+                                           save.data_ptr(), save.data_ptr() + 4 * C, mmd.data_ptr(),
+                                           mvd.data_ptr(), None))
+        else:
+            L.check(lib.mcn_bn_finalize(sums.data_ptr(), float(rows), C, eps, mom, save.data_ptr(),
+                                        save.data_ptr() + 4 * C, mmd.data_ptr(), mvd.data_ptr(), None))
+            L.check(lib.mcn_bn_apply(code, xd.data_ptr(), rows, C, save.data_ptr(), save.data_ptr() + 4 * C,
+                                     gd.data_ptr(), bd.data_ptr(), rp, 1, 0.0, y.data_ptr(), None))
+        torch.cuda.synchronize()
+        outs.append((y.float().cpu().numpy(), save.cpu().numpy(), mmd.cpu().numpy(), mvd.cpu().numpy()))
+    (y0, s0, m0, v0), (y1, s1, m1, v1) = outs
+    assert rel_l2(s1, s0) < 1e-6 and rel_l2(m1, m0) < 1e-6 and rel_l2(v1, v0) < 1e-6
+    assert rel_l2(y1, y0) < (1e-6 if code == 0 else 2e-3)
+    yb, bm, bv = tf_ops.fused_batch_norm_train(torch.tensor(x), torch.tensor(gamma), torch.tensor(beta), eps)
+    yref = torch.relu(yb + torch.tensor(res) if use_res else yb)
+    assert rel_l2(y1, yref) < (2e-5 if code == 0 else 8e-3)
+    assert rel_l2(s1[:C], bm) < 1e-5
+    assert rel_l2(v1, mom * mv + (1 - mom) * bv.numpy()) < 1e-5
+
+
 @pytest.mark.parametrize("code", [0, 1])
 @pytest.mark.parametrize("C", [64, 24, 20, 320])
 @pytest.mark.parametrize("variant", ["plain", "relu", "relu_res", "swish", "res_noact"])

@@ -47,9 +47,17 @@ def test_native_builder_matches_reference_graph(r50):
 def test_plan_fusion_and_launch_counts(r50):
     p = Plan(r50.graph)
     h = p.launch_histogram()
-    assert h["mcn_conv2d_fprop_tc"] == 54 and h["mcn_conv2d_wgrad_tc"] == 54      # 53 convs + dense
+    # convs with a deep reduction take the BN statistics in their epilogue (33 of the 53 that feed a
+    # BN); the store-bound 1x1 expansions keep the separate statistics pass; finalize is gone
+    assert h["mcn_conv2d_fprop_tc_stats"] + h["mcn_conv2d_fprop_tc"] == 54
+    assert h["mcn_conv2d_fprop_tc_stats"] + h["mcn_bn_stats"] == 53
+    assert h["mcn_conv2d_fprop_tc_stats"] >= 30 and "mcn_bn_finalize" not in h
+    assert h["mcn_conv2d_wgrad_tc"] == 54
     assert h["mcn_conv2d_dgrad_tc"] == 53                                        # no dgrad into the images
-    assert h["mcn_bn_apply"] == 53 and "mcn_act_fwd" not in h and "mcn_add_act_fwd" not in h
+    assert h["mcn_bn_apply_stats"] == 53 and "mcn_act_fwd" not in h and "mcn_add_act_fwd" not in h
+    # the unfused plan keeps the separate statistics pass
+    hu = Plan(r50.graph, fuse_bn_stats=False).launch_histogram()
+    assert hu["mcn_conv2d_fprop_tc"] == 54 and hu["mcn_bn_stats"] == 53 and hu["mcn_bn_apply_stats"] == 53
     assert "mcn_accumulate" not in h                    # multi-consumer gradients add in the dgrad epilogue
     fused = [n for n in r50.graph.nodes if n.op == "bn"]
     assert sum(n.attrs["residual"] is not None for n in fused) == 16
@@ -119,7 +127,8 @@ def test_other_north_star_models_build_and_plan(have_reference_models):
         [224, 224, 3], 1000, batch_size=8, compute_dtype="bf16")
     assert b0.params == 5288548                       # 5.25 M non-BN + BN gamma/beta
     h = Plan(b0.graph).launch_histogram()
-    assert h["mcn_dwconv2d_fwd"] == 16 and h["mcn_scale_bcast_fwd"] == 16 and h["mcn_bn_apply"] == 49
+    assert h["mcn_dwconv2d_fwd"] == 16 and h["mcn_scale_bcast_fwd"] == 16 and h["mcn_bn_apply_stats"] == 49
+    assert h["mcn_bn_stats"] >= 16                      # depthwise outputs keep the separate statistics pass
     assert "block_1/mbconv_0/se_mask/conv_0/biases" in b0.graph.vars
     dl = loader.load_reference_model("models/deeplabv3plus.py", fac).DeepLabV3PlusResNet(
         [512, 512, 3], 21, batch_size=2, compute_dtype="bf16")
@@ -146,7 +155,7 @@ def test_inference_plan_uses_ema_and_moving_statistics(r50):
     p = Plan(r50.graph)
     names = [l.fn for l in p.inf]
     assert names.count("mcn_bn_infer") == 53 and "mcn_bn_stats" not in names
-    assert names.count("mcn_conv2d_fprop_tc") == 54
+    assert names.count("mcn_conv2d_fprop_tc") == 54 and "mcn_conv2d_fprop_tc_stats" not in names
     # every weight operand of the inference list comes from the EMA copies
     ema_ptrs = [a for l in p.inf for a in l.args if hasattr(a, "buf") and a.buf in (p.b_ema, p.b_bf16_ema)]
     raw_ptrs = [a for l in p.inf for a in l.args if hasattr(a, "buf") and a.buf in (p.b_param, p.b_bf16)]
