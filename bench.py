@@ -142,6 +142,12 @@ def launch_work(name, args, esz):
         flops = 2.0 * m * d.kh * d.kw * d.Cin * d.Cout
         byt = esz * (d.N * d.H * d.W * d.Cin + m * d.Cout) + esz * d.kh * d.kw * d.Cin * d.Cout
         return byt, flops
+    if name in ("mcn_stem_conv_fprop", "mcn_stem_conv_wgrad"):
+        d = args[0]._obj
+        m = d.N * d.Ho * d.Wo
+        flops = 2.0 * m * d.kh * d.kw * 3 * d.Cout            # the real taps / channels
+        byt = esz * (d.N * d.H * d.W * 4 + m * d.Cout)
+        return byt, flops
     if name == "mcn_bn_stats":
         return args[2] * args[3] * esz, 0.0
     if name == "mcn_bn_apply":
@@ -378,7 +384,13 @@ def main():
                    "global_batch": gb, "parallelism": "dp%d" % world, "model_source": model_src,
                    "l2_flush": "not needed: one step touches %.1f GB of HBM per GPU (>> 126 MB L2)"
                                % (eng.plan.arena_bytes / 1e9),
-                   "cuda_graph": bool(eng.use_cuda_graph)},
+                   "cuda_graph": bool(eng.use_cuda_graph),
+                   "sync_bn_exchange": ("none (1 GPU)" if world == 1 else
+                                        "one-shot all-reduce kernel over NVLink peer memory (csrc/comm.cu)"
+                                        if eng._peer is not None else "ncclAllReduce per layer"),
+                   "grad_allreduce": ("none (1 GPU)" if world == 1 else
+                                      "NCCL, %d buckets started during backward + %d after"
+                                      % (sum(len(v) for v in eng._bucket_ready.values()), len(eng._bucket_tail)))},
         "e2e": {"value": gb / (ms_e2e * 1e-3), "unit": "img/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(X.numel() * 4 + Y.numel() * 4 + 64), "d2h_bytes_per_step": 8},
         "gpu_launches": eager_launches * args.steps,

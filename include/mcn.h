@@ -94,6 +94,23 @@ int mcn_dwconv2d_bwd_data(const mcn_conv_desc* d, int mult, int dtype, const voi
 int mcn_dwconv2d_bwd_filter(const mcn_conv_desc* d, int mult, int dtype, const void* x,
                             const void* dy, float* dw, void* stream);
 
+/* ---- stem convolution: k x k (3 or 7), stride 2 along W, on an RGB image stored with FOUR
+ * channels (8-byte pixels, 4th = 0; mcn_pad_rgb4).  Same call site as mcn_conv2d_fprop_tc
+ * (tf.nn.conv2d, convnet.py:1659) for the first layer of resnet_v1_5.py:43 / efficientnet.py:62,
+ * without an im2col matrix: the GEMM A tile is gathered from the image with 16-byte cp.async
+ * copies.  d->Cin must be 4.  The weight is stored as [Kpad][Cout] with row
+ * k = (r*(kw+1) + s)*4 + c  (tap s = kw and channel c = 3 are zero), Kpad = mcn_stem_conv_kpad(d):
+ *   w_okp : bf16 [Cout][Kpad]   (fprop operand = mcn_weight_prep's transposed copy)
+ *   dw    : fp32 [Kpad][Cout]   (wgrad ACCUMULATES; rows of the zero tap are left untouched)
+ * bn_sums (may be NULL): fused batch-norm statistics as in mcn_conv2d_fprop_tc_stats. */
+int mcn_stem_conv_kpad(const mcn_conv_desc* d);   /* 0 when the geometry is not supported */
+int mcn_stem_conv_fprop(const mcn_conv_desc* d, const void* x4, const void* w_okp, const float* bias,
+                        void* y, double* bn_sums, void* stream);
+int mcn_stem_conv_wgrad(const mcn_conv_desc* d, const void* x4, const void* dy, float* dw,
+                        void* stream);
+/* bf16 [pixels][3] -> bf16 [pixels][4] (4th channel zero) */
+int mcn_pad_rgb4(const void* x_bf16, long long pixels, void* y_bf16, void* stream);
+
 /* fp32 master weight [taps][Cin][Cout] -> bf16 copies in both operand layouts. */
 int mcn_weight_prep(const float* w_hwio_f32, int taps, int cin, int cout, void* w_hwio_bf16,
                     void* w_ohwi_bf16, void* stream);
@@ -234,6 +251,21 @@ int mcn_opt_step(int kind, const mcn_opt_tensor* table, int ntensors, long long 
 /* out[t][c][r] += in[t][r][c]: gradient of a transposed-conv weight (stored [kh,kw,Cin,Cout],
  * reference convnet.py:2460-2462) from the wgrad of the underlying conv. */
 int mcn_transpose_add_f32(const float* in, int taps, int rows, int cols, float* out, void* stream);
+
+/* ---- multi-GPU: one-shot all-reduce (sum) of a small vector over peer-mapped memory ----
+ * Replaces, for synchronised batch-norm, the reference's tower-after-tower statistics chain
+ * (convnet.py:1898-1914) and the per-layer ncclAllReduce: every rank writes its vector into a
+ * mailbox slot in every peer's memory over NVLink, raises a flag, waits for all flags and sums the
+ * slots in rank order (bit-identical on all ranks).
+ *   peers    : DEVICE array [world] of the peer-mapped base address of every rank's symmetric region
+ *   mail_off : byte offset of this collective point's mailbox ([world][n0+n1] elements) in a region
+ *   flag_off : byte offset of its flag row ([world] uint64, zero-initialised)
+ *   counter  : local device uint64 sequence number of this collective point (starts at 0)
+ *   src0/src1: local source segments (n0, n1 elements; src1 may be NULL when n1 == 0)
+ *   dst      : local destination, n0+n1 elements (may alias src0) */
+int mcn_peer_allreduce(const unsigned long long* peers, long long mail_off, long long flag_off,
+                       unsigned long long* counter, int is_f64, const void* src0, int n0,
+                       const void* src1, int n1, void* dst, int rank, int world, void* stream);
 
 /* ---- generic helpers ---- */
 int mcn_fill_f32(float* p, long long n, float v, void* stream);

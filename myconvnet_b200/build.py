@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmcn.so")
 SOURCES = ["runtime.cu", "conv_tc.cu", "conv_direct.cu", "bn.cu", "pool.cu", "eltwise.cu",
-           "loss.cu", "opt.cu"]
+           "loss.cu", "opt.cu", "comm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--use_fast_math", "-Xcompiler", "-fPIC"]
 

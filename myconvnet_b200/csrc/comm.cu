@@ -1,0 +1,104 @@
+// One-shot all-reduce of small vectors over peer-mapped device memory (NVLink / NVSwitch).
+//
+// Synchronised batch-norm exchanges 2*C numbers per layer and direction (106 exchanges in a
+// ResNet-50 step) on the critical path of the step; an NCCL all-reduce costs ~25-30 us each
+// (launch + its own cross-GPU handshake), i.e. ~3 ms of a 26 ms step at 8 GPUs.  Here every rank
+// WRITES its vector straight into a mailbox slot in every peer's memory, raises a flag there, waits
+// for the flags of all peers in its own memory and sums the mailbox in rank order (so all ranks
+// get bit-identical results).  One tiny kernel, no library call, capturable in a CUDA graph.
+// Replaces the reference's tower-after-tower statistics chain (convnet.py:1898-1914).
+//
+// Memory: a symmetric region per rank (torch.distributed._symmetric_memory; `peers` holds the
+// peer-mapped base address of every rank's region).  Each collective point of the step owns a
+// mailbox [world][n] and a flag row [world] inside it, and a local sequence counter.  A mailbox is
+// reused one step later; every rank passes at least one other collective point in between, which
+// orders the reuse after the previous read (a rank cannot raise its next flag before it has left
+// this kernel).
+#include "mcn_common.cuh"
+
+namespace mcn {
+namespace {
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+template <typename T>
+__device__ __forceinline__ T ld_sys(const T* p) {
+  return *reinterpret_cast<const volatile T*>(p);   // bypasses L1: the data was written by a peer
+}
+
+template <typename T>
+__global__ void __launch_bounds__(512)
+peer_allreduce_kernel(const unsigned long long* __restrict__ peers, long long mail_off,
+                      long long flag_off, unsigned long long* counter, const T* __restrict__ src0,
+                      int n0, const T* __restrict__ src1, int n1, T* __restrict__ dst, int rank,
+                      int world) {
+  __shared__ unsigned long long seq_s;
+  const int n = n0 + n1;
+  if (threadIdx.x == 0) {
+    seq_s = *counter + 1;
+    *counter = seq_s;
+  }
+  __syncthreads();
+  const unsigned long long seq = seq_s;
+  // 1. push my vector into slot [rank] of every rank's mailbox (my own included)
+  for (int p = 0; p < world; ++p) {
+    T* slot = reinterpret_cast<T*>(peers[p] + mail_off) + static_cast<size_t>(rank) * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) slot[i] = i < n0 ? src0[i] : src1[i - n0];
+  }
+  __threadfence_system();
+  __syncthreads();
+  // 2. raise my flag at every rank, 3. wait for everyone's flag here
+  if (threadIdx.x < world) {
+    st_release_sys(reinterpret_cast<unsigned long long*>(peers[threadIdx.x] + flag_off) + rank, seq);
+    const unsigned long long* mine =
+        reinterpret_cast<const unsigned long long*>(peers[rank] + flag_off) + threadIdx.x;
+    unsigned long long spins = 0;
+    while (ld_acquire_sys(mine) < seq) {
+      if (++spins > (1ull << 31)) {   // a missing peer becomes a launch failure, not a hang
+        printf("mcn: peer all-reduce timeout rank=%d waiting for rank=%d seq=%llu\n", rank,
+               (int)threadIdx.x, seq);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+  // 4. sum the mailbox in rank order
+  const T* box = reinterpret_cast<const T*>(peers[rank] + mail_off);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    T acc = ld_sys(box + i);
+    for (int q = 1; q < world; ++q) acc += ld_sys(box + static_cast<size_t>(q) * n + i);
+    dst[i] = acc;
+  }
+}
+
+}  // namespace
+}  // namespace mcn
+
+using namespace mcn;
+
+extern "C" int mcn_peer_allreduce(const unsigned long long* peers, long long mail_off,
+                                  long long flag_off, unsigned long long* counter, int is_f64,
+                                  const void* src0, int n0, const void* src1, int n1, void* dst,
+                                  int rank, int world, void* stream) {
+  MCN_REQUIRE(peers && counter && src0 && dst && n0 > 0 && n1 >= 0 && (n1 == 0 || src1) &&
+                  world >= 1 && world <= 64 && rank >= 0 && rank < world,
+              "peer_allreduce: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (is_f64)
+    peer_allreduce_kernel<double><<<1, 512, 0, st>>>(peers, mail_off, flag_off, counter,
+                                                     static_cast<const double*>(src0), n0,
+                                                     static_cast<const double*>(src1), n1,
+                                                     static_cast<double*>(dst), rank, world);
+  else
+    peer_allreduce_kernel<float><<<1, 512, 0, st>>>(peers, mail_off, flag_off, counter,
+                                                    static_cast<const float*>(src0), n0,
+                                                    static_cast<const float*>(src1), n1,
+                                                    static_cast<float*>(dst), rank, world);
+  return after_launch("peer_allreduce");
+}

@@ -966,6 +966,347 @@ wgrad_halo_kernel(const __grid_constant__ WgradHaloArgs args) {
   if (warp == 1) ptx::tmem_dealloc(tmem_base, static_cast<uint32_t>(args.tmem_cols));
 }
 
+// ------------------------------------------------------------------ stem convolution (RGB input)
+// A k x k stride-2 convolution on a 3-channel image cannot be fed by TMA (6-byte pixels), and an
+// explicit im2col matrix costs ~1 GB of HBM writes + two reads per step at batch 256.  Here the
+// image is stored with 4 channels (8-byte pixels, 4th = 0) and the filter row is widened to an
+// even tap count kwp = kw + 1 (the extra tap has a zero weight): with stride 2 and an even left
+// pad the kwp*8 bytes of one filter row of one output pixel then start on a 16-byte boundary, so
+// the GEMM A tile is gathered straight from the image with 16-byte cp.async copies into the
+// 128-byte-swizzled K-major layout tcgen05 expects.  K index = (r*kwp + s)*4 + c.
+//   fprop: M = 128 pixels, N = Cout, K = kh*kwp*4 (224 for 7x7), weights resident in shared memory.
+//   wgrad: the same tile read as an MN-major operand (rows = pixels = K), dy tiles by TMA,
+//          one TMEM accumulator per 128 k-rows, split-K over pixel tiles, fp32 red.global at the end.
+struct StemArgs {
+  CUtensorMap mapW;     // fprop: [Cout][Kpad] bf16, box 64 x Cout;  wgrad: dy [M][Cout], box 64 x 128
+  const __nv_bfloat16* x4;
+  EpiArgs e;            // fprop output / statistics
+  float* dw;            // wgrad output [Kpad][Cout]
+  int H, W, Ho, Wo, N, sh, pad_t, pad_l, kh, kw;
+  int epr, cpr, rpc, kc, kc_alloc, ksteps_last, kp;   // elements / 16-byte chunks per filter row, rows per 128-byte line
+  int stages, tmem_cols, total_tiles, cout, nb_atoms, splits;
+  long long m_total;
+};
+
+constexpr int kStemProducers = 128;
+
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, bool valid) {
+  const uint32_t n = valid ? 16u : 0u;   // src-size 0: the 16 bytes are zero-filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// One producer thread gathers the receptive field of pixel `m` (row `t` of the tile) into stage `sA`.
+// The filter size is a template parameter: with one warp per scheduler the gather is bound by
+// the latency of its own address arithmetic, so everything that can fold to a constant must
+// (a generic version with run-time kh / kw spent ~8k cycles per tile, mostly in integer divisions).
+template <int KH, int KW>
+__device__ __forceinline__ void stem_gather(const StemArgs& a, uint8_t* sA, int t, uint32_t m) {
+  constexpr int EPR = (KW + 1) * 4, CPR = EPR / 8, RPC = 64 / EPR;
+  const bool live = m < static_cast<uint32_t>(a.m_total);
+  uint32_t q = 0, p = 0, n = 0;
+  if (live) {
+    const uint32_t wo = static_cast<uint32_t>(a.Wo), ho = static_cast<uint32_t>(a.Ho);
+    q = m % wo;
+    const uint32_t r = m / wo;
+    p = r % ho;
+    n = r / ho;
+  }
+  const int w0 = static_cast<int>(q) * 2 - a.pad_l;                      // even: 16-byte aligned pixel pair
+  const int h0 = static_cast<int>(p) * a.sh - a.pad_t;
+  const __nv_bfloat16* img = a.x4 + static_cast<long long>(n) * a.H * a.W * 4;
+  const uint32_t row_base = ptx::smem_u32(sA) + static_cast<uint32_t>(t) * 128u;
+  const uint32_t sw = static_cast<uint32_t>(t & 7);
+  bool wok[CPR];
+#pragma unroll
+  for (int j = 0; j < CPR; ++j) wok[j] = (w0 + 2 * j >= 0) && (w0 + 2 * j + 1 < a.W);
+#pragma unroll
+  for (int r = 0; r < KH; ++r) {
+    const int h = h0 + r;
+    const bool hin = live && h >= 0 && h < a.H;
+    const __nv_bfloat16* src = img + ((hin ? h : 0) * a.W + w0) * 4;
+    const uint32_t chunk_base = row_base + static_cast<uint32_t>(r / RPC) * kABytes;
+#pragma unroll
+    for (int j = 0; j < CPR; ++j) {
+      const bool ok = hin && wok[j];
+      cp_async_16(chunk_base + ((static_cast<uint32_t>((r % RPC) * CPR + j) ^ sw) << 4),
+                  ok ? src + 8 * j : a.x4, ok);
+    }
+  }
+}
+// run-time dispatch on the two supported filter sizes (uniform across the block)
+__device__ __forceinline__ void stem_gather_any(const StemArgs& a, uint8_t* sA, int t, uint32_t m) {
+  if (a.kw == 7) stem_gather<7, 7>(a, sA, t, m);
+  else stem_gather<3, 3>(a, sA, t, m);
+}
+
+// Roles (288 threads): warps 0-3 gather A tiles (cp.async, two stages in flight), warp 4 loads the
+// weights once and issues the MMAs, warps 5-8 run the shared epilogue (incl. fused BN statistics).
+__global__ void __launch_bounds__(288, 1)
+stem_fprop_kernel(const __grid_constant__ StemArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int stages = args.stages;
+  const uint32_t a_stage = static_cast<uint32_t>(args.kc_alloc) * kABytes;
+  const uint32_t b_chunk = static_cast<uint32_t>(args.e.block_n) * 128u;
+  uint8_t* smemB = smem + static_cast<size_t>(stages) * a_stage;
+  uint8_t* tail = smemB + static_cast<size_t>(args.kc) * b_chunk;
+  uint64_t* full = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty = full + stages;
+  uint64_t* wbar = empty + stages;
+  uint64_t* tmem_full = wbar + 1;     // [2]
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  const int total_tiles = args.total_tiles;
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tmap(&args.mapW);
+    for (int s = 0; s < stages; ++s) {
+      ptx::mbar_init(&full[s], kStemProducers);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    ptx::mbar_init(wbar, 1);
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&tmem_full[b], 1);
+      ptx::mbar_init(&tmem_empty[b], 4);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 4) {
+    ptx::tmem_alloc(tmem_slot, static_cast<uint32_t>(args.tmem_cols));
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ---------------- gather producers ----------------
+    const int t = threadIdx.x;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int s = it % stages;
+      ptx::mbar_wait(&empty[s], (static_cast<uint32_t>(it / stages) & 1u) ^ 1u);
+      stem_gather_any(args, smem + static_cast<size_t>(s) * a_stage, t, static_cast<uint32_t>(tile) * 128u + t);
+      cp_async_commit();
+      if (it > 0) {
+        cp_async_wait<1>();               // the previous tile's copies have landed
+        ptx::fence_proxy_async();         // generic-proxy writes -> visible to the tensor core
+        ptx::mbar_arrive(&full[(it - 1) % stages]);
+      }
+    }
+    if (it > 0) {
+      cp_async_wait<0>();
+      ptx::fence_proxy_async();
+      ptx::mbar_arrive(&full[(it - 1) % stages]);
+    }
+  } else if (warp == 4) {
+    // ---------------- weights + MMA issuer ----------------
+    if (ptx::elect_one()) {
+      ptx::mbar_expect_tx(wbar, static_cast<uint32_t>(args.kc) * b_chunk);
+      for (int kc = 0; kc < args.kc; ++kc)
+        ptx::tma_load_2d(&args.mapW, wbar, smemB + static_cast<size_t>(kc) * b_chunk, kc * 64, 0);
+    }
+    __syncwarp();
+    ptx::mbar_wait(wbar, 0);
+    const uint32_t idesc = ptx::make_idesc_bf16(128, args.e.block_n, 0, 0);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int s = it % stages;
+      const int buf = it & 1;
+      ptx::mbar_wait(&tmem_empty[buf], (static_cast<uint32_t>(it >> 1) & 1u) ^ 1u);
+      ptx::mbar_wait(&full[s], static_cast<uint32_t>(it / stages) & 1u);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint32_t a_addr = ptx::smem_u32(smem + static_cast<size_t>(s) * a_stage);
+        const uint32_t b_addr = ptx::smem_u32(smemB);
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * args.e.block_n);
+        for (int kc = 0; kc < args.kc; ++kc) {
+          const int ksteps = (kc == args.kc - 1) ? args.ksteps_last : 4;
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t ad = ptx::make_smem_desc(a_addr + kc * kABytes + k * 32, 16, 1024);
+            const uint64_t bd = ptx::make_smem_desc(b_addr + kc * b_chunk + k * 32, 16, 1024);
+            ptx::umma_bf16(tmem_d, ad, bd, idesc, (kc | k) != 0 ? 1u : 0u);
+          }
+        }
+        ptx::umma_commit(&empty[s]);
+        ptx::umma_commit(&tmem_full[buf]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---------------- epilogue (warps 5..8) ----------------
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    uint32_t* stat_stage = reinterpret_cast<uint32_t*>(tail + kBarRegionBytes);
+    float* stat_acc_all = reinterpret_cast<float*>(stat_stage + kStatStageWords);
+    float* stat_acc = stat_acc_all + quad * kStatAccWarp;
+    stat_stage += quad * 32 * kStatRowWords;
+    const bool stats = args.e.stats != nullptr;
+    if (stats) {
+      for (int i = row; i < kStatAccFloats; i += 128) stat_acc_all[i] = 0.f;
+      epi_bar_sync();
+    }
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      if (stats && it > 0 && (it & 7) == 0) stats_flush(args.e, stat_acc_all, 0, row);
+      const long long m = static_cast<long long>(tile) * 128 + row;
+      const bool valid = m < args.m_total;
+      epilogue_tile(args.e, tmem_base + static_cast<uint32_t>(buf * args.e.block_n), quad, lane, valid,
+                    valid ? m * args.cout : 0, 0, &tmem_full[buf], static_cast<uint32_t>(it >> 1) & 1u,
+                    &tmem_empty[buf], stat_stage, stat_acc);
+    }
+    if (stats && it > 0) stats_flush(args.e, stat_acc_all, 0, row);
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 4) ptx::tmem_dealloc(tmem_base, static_cast<uint32_t>(args.tmem_cols));
+}
+
+// wgrad: warps 0-3 gather, warp 4 loads dy tiles by TMA and issues the MMAs, warps 5-8 write dw.
+__global__ void __launch_bounds__(288, 1)
+stem_wgrad_kernel(const __grid_constant__ StemArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int stages = args.stages;
+  const uint32_t a_stage = static_cast<uint32_t>(args.kc_alloc) * kABytes;
+  const uint32_t b_stage = static_cast<uint32_t>(args.nb_atoms) * kABytes;
+  const uint32_t stage_bytes = a_stage + b_stage;
+  uint8_t* tail = smem + static_cast<size_t>(stages) * stage_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(tail);      // producers' gather
+  uint64_t* fullb = full + stages;                         // dy TMA
+  uint64_t* empty = fullb + stages;
+  uint64_t* tmem_full = empty + stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  const int split = blockIdx.x;
+  const int t0 = static_cast<int>(static_cast<long long>(split) * args.total_tiles / args.splits);
+  const int t1 = static_cast<int>(static_cast<long long>(split + 1) * args.total_tiles / args.splits);
+
+  // k-chunks the gather never writes (padding up to a multiple of 128 k-rows) must read as zero
+  for (int s = 0; s < stages; ++s) {
+    uint4* z = reinterpret_cast<uint4*>(smem + static_cast<size_t>(s) * stage_bytes +
+                                        static_cast<size_t>(args.kc) * kABytes);
+    const int n16 = (args.kc_alloc - args.kc) * kABytes / 16;
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  ptx::fence_proxy_async();
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tmap(&args.mapW);
+    for (int s = 0; s < stages; ++s) {
+      ptx::mbar_init(&full[s], kStemProducers);
+      ptx::mbar_init(&fullb[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    ptx::mbar_init(tmem_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 4) {
+    ptx::tmem_alloc(tmem_slot, static_cast<uint32_t>(args.tmem_cols));
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int m_tiles = args.kc_alloc / 2;     // accumulators of 128 k-rows
+
+  if (warp < 4) {
+    const int t = threadIdx.x;
+    int it = 0;
+    for (int tile = t0; tile < t1; ++tile, ++it) {
+      const int s = it % stages;
+      ptx::mbar_wait(&empty[s], (static_cast<uint32_t>(it / stages) & 1u) ^ 1u);
+      stem_gather_any(args, smem + static_cast<size_t>(s) * stage_bytes, t, static_cast<uint32_t>(tile) * 128u + t);
+      cp_async_commit();
+      if (it > 0) {
+        cp_async_wait<1>();
+        ptx::fence_proxy_async();
+        ptx::mbar_arrive(&full[(it - 1) % stages]);
+      }
+    }
+    if (it > 0) {
+      cp_async_wait<0>();
+      ptx::fence_proxy_async();
+      ptx::mbar_arrive(&full[(it - 1) % stages]);
+    }
+  } else if (warp == 4) {
+    const uint32_t idesc = ptx::make_idesc_bf16(128, args.e.block_n, 1, 1);
+    // dy loads run one stage ahead of the MMAs: issue for tile i+1 before consuming tile i
+    auto issue_dy = [&](int tile, int it) {
+      const int s = it % stages;
+      ptx::mbar_wait(&empty[s], (static_cast<uint32_t>(it / stages) & 1u) ^ 1u);
+      ptx::mbar_expect_tx(&fullb[s], b_stage);
+      uint8_t* sB = smem + static_cast<size_t>(s) * stage_bytes + a_stage;
+      for (int j = 0; j < args.nb_atoms; ++j)
+        ptx::tma_load_2d(&args.mapW, &fullb[s], sB + static_cast<size_t>(j) * kABytes, j * 64, tile * 128);
+    };
+    const bool leader = ptx::elect_one();
+    if (leader && t0 < t1) issue_dy(t0, 0);
+    __syncwarp();
+    int it = 0;
+    for (int tile = t0; tile < t1; ++tile, ++it) {
+      const int s = it % stages;
+      const uint32_t ph = static_cast<uint32_t>(it / stages) & 1u;
+      if (leader && tile + 1 < t1 && stages > 1) issue_dy(tile + 1, it + 1);
+      __syncwarp();
+      ptx::mbar_wait(&full[s], ph);
+      ptx::mbar_wait(&fullb[s], ph);
+      ptx::tc_fence_after();
+      if (leader) {
+        const uint32_t a_addr = ptx::smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
+        const uint32_t b_addr = a_addr + a_stage;
+        for (int mt = 0; mt < m_tiles; ++mt)
+          for (int k = 0; k < 8; ++k) {
+            const uint64_t ad = ptx::make_smem_desc(a_addr + mt * 2 * kABytes + k * 2048, kABytes, 1024);
+            const uint64_t bd = ptx::make_smem_desc(b_addr + k * 2048, kABytes, 1024);
+            ptx::umma_bf16(tmem_base + static_cast<uint32_t>(mt * args.e.block_n), ad, bd, idesc,
+                           (it | k) != 0 ? 1u : 0u);
+          }
+        ptx::umma_commit(&empty[s]);
+        if (tile == t1 - 1) ptx::umma_commit(tmem_full);
+      }
+      __syncwarp();
+    }
+  } else if (t1 > t0) {
+    ptx::mbar_wait(tmem_full, 0);
+    ptx::tc_fence_after();
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    for (int mt = 0; mt < m_tiles; ++mt) {
+      const int k = mt * 128 + row;
+      const int s2 = (k % args.epr) >> 2;          // tap within the (widened) filter row
+      const bool ok = k < args.kp && s2 < args.kw;    // the widening tap carries a zero weight: no gradient
+      for (int c0 = 0; c0 < args.e.block_n; c0 += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                               static_cast<uint32_t>(mt * args.e.block_n + c0), r);
+        ptx::tmem_ld_wait();
+        if (!ok || c0 >= args.cout) continue;
+        float* o = args.dw + static_cast<long long>(k) * args.cout + c0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          ptx::red_add_v4(o + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                          __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 4) ptx::tmem_dealloc(tmem_base, static_cast<uint32_t>(args.tmem_cols));
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -1731,4 +2072,116 @@ extern "C" int mcn_conv2d_wgrad_tc(const mcn_conv_desc* d, const void* x, const 
   dim3 grid((unsigned)(taps * a.tiles_mi * a.tiles_ni * a.splits));
   wgrad_kernel<<<grid, 192, smem, static_cast<cudaStream_t>(stream)>>>(a);
   return after_launch("wgrad_kernel");
+}
+
+// ------------------------------------------------------------------ stem convolution: host side
+namespace {
+// Fills the geometry fields of StemArgs; returns false when the convolution is not a "stem" the
+// gather kernels handle (see the comment above StemArgs).
+bool stem_geometry(const mcn_conv_desc* d, StemArgs* a) {
+  if (d->Cin != 4 || d->sw != 2 || d->dw != 1 || d->dh != 1 || (d->pad_l & 1) || (d->W & 1)) return false;
+  if (!((d->kw == 3 && d->kh == 3) || (d->kw == 7 && d->kh == 7))) return false;   // instantiated filter sizes
+  if (static_cast<long long>(d->N) * d->Ho * d->Wo >= (1LL << 31) - 256) return false;
+  if (static_cast<long long>(d->H) * d->W * 4 >= (1LL << 31)) return false;
+  if (d->Cout % 16 != 0 || d->Cout > 256) return false;
+  a->H = d->H; a->W = d->W; a->Ho = d->Ho; a->Wo = d->Wo; a->N = d->N;
+  a->sh = d->sh; a->pad_t = d->pad_t; a->pad_l = d->pad_l; a->kh = d->kh; a->kw = d->kw;
+  a->epr = (d->kw + 1) * 4;
+  a->cpr = a->epr / 8;
+  a->rpc = 64 / a->epr;
+  a->kc = (d->kh + a->rpc - 1) / a->rpc;
+  a->kc_alloc = (a->kc + 1) / 2 * 2;
+  a->kp = d->kh * a->epr;
+  a->ksteps_last = (a->kp - (a->kc - 1) * 64 + 15) / 16;
+  a->cout = d->Cout;
+  a->m_total = static_cast<long long>(d->N) * d->Ho * d->Wo;
+  a->total_tiles = static_cast<int>((a->m_total + 127) / 128);
+  return true;
+}
+}  // namespace
+
+extern "C" int mcn_stem_conv_kpad(const mcn_conv_desc* d) {
+  StemArgs a;
+  std::memset(&a, 0, sizeof(a));
+  if (!d || !stem_geometry(d, &a)) return 0;
+  return a.kc_alloc * 64;
+}
+
+extern "C" int mcn_stem_conv_fprop(const mcn_conv_desc* d, const void* x4, const void* w_okp,
+                                   const float* bias, void* y, double* bn_sums, void* stream) {
+  MCN_REQUIRE(d && x4 && w_okp && y, "stem_conv_fprop: null argument");
+  StemArgs a;
+  std::memset(&a, 0, sizeof(a));
+  MCN_REQUIRE(stem_geometry(d, &a), "stem_conv_fprop: geometry not supported (needs Cin=4 padded input, "
+              "stride-2 3x3/7x7, even W and left pad, Cout %% 16 == 0)");
+  MCN_REQUIRE(bn_sums == nullptr || d->Cout % 64 == 0, "stem_conv_fprop: fused statistics need Cout %% 64 == 0");
+  MCN_REQUIRE(reinterpret_cast<uintptr_t>(x4) % 16 == 0 && reinterpret_cast<uintptr_t>(y) % 32 == 0,
+              "stem_conv_fprop: misaligned tensor");
+  a.x4 = static_cast<const __nv_bfloat16*>(x4);
+  const int kpad = a.kc_alloc * 64;
+  int rc;
+  if ((rc = encode_matrix(&a.mapW, w_okp, d->Cout, kpad, d->Cout))) return rc;
+  a.e.block_n = d->Cout;
+  a.e.n_total = d->Cout;
+  a.e.out = y;
+  a.e.bias = bias;
+  a.e.stats = bn_sums;
+  a.e.out_f32 = 0;
+  a.e.accumulate = 0;
+  a.e.vec_ok = (d->Cout % 16 == 0);
+  a.nb_atoms = 0;
+  const size_t a_stage = static_cast<size_t>(a.kc_alloc) * kABytes;
+  const size_t fixed = static_cast<size_t>(a.kc) * d->Cout * 128 + kBarRegionBytes +
+                       (bn_sums ? kStatSmemBytes : 0) + 1024;
+  a.stages = static_cast<int>(std::min<size_t>(3, (static_cast<size_t>(smem_optin_limit()) - fixed) / a_stage));
+  MCN_REQUIRE(a.stages >= 2, "stem_conv_fprop: shared memory budget too small");
+  a.tmem_cols = 2 * tmem_cols_for(d->Cout);
+  const size_t smem = a.stages * a_stage + fixed;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(stem_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             smem_optin_limit()) != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(stem_fprop_kernel) failed");
+      return MCN_ECUDA;
+    }
+    configured = true;
+  }
+  dim3 grid(static_cast<unsigned>(std::min(a.total_tiles, num_sms())));
+  stem_fprop_kernel<<<grid, 288, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  return after_launch("stem_fprop_kernel");
+}
+
+extern "C" int mcn_stem_conv_wgrad(const mcn_conv_desc* d, const void* x4, const void* dy, float* dw,
+                                   void* stream) {
+  MCN_REQUIRE(d && x4 && dy && dw, "stem_conv_wgrad: null argument");
+  StemArgs a;
+  std::memset(&a, 0, sizeof(a));
+  MCN_REQUIRE(stem_geometry(d, &a) && d->Cout % 64 == 0,
+              "stem_conv_wgrad: geometry not supported (see mcn_stem_conv_fprop; Cout %% 64 == 0)");
+  a.x4 = static_cast<const __nv_bfloat16*>(x4);
+  a.dw = dw;
+  int rc;
+  if ((rc = encode_matrix(&a.mapW, dy, a.m_total, d->Cout, 128))) return rc;
+  a.e.block_n = d->Cout;
+  a.nb_atoms = d->Cout / 64;
+  const size_t stage_bytes = static_cast<size_t>(a.kc_alloc + a.nb_atoms) * kABytes;
+  a.stages = static_cast<int>(std::min<size_t>(3, (static_cast<size_t>(smem_optin_limit()) - kBarRegionBytes - 1024) / stage_bytes));
+  MCN_REQUIRE(a.stages >= 2, "stem_conv_wgrad: shared memory budget too small");
+  int cols = (a.kc_alloc / 2) * d->Cout;
+  MCN_REQUIRE(cols <= 512, "stem_conv_wgrad: too many accumulator columns");
+  a.tmem_cols = 32;
+  while (a.tmem_cols < cols) a.tmem_cols *= 2;
+  a.splits = std::max(1, std::min(a.total_tiles, num_sms()));
+  const size_t smem = a.stages * stage_bytes + kBarRegionBytes + 1024;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(stem_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             smem_optin_limit()) != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(stem_wgrad_kernel) failed");
+      return MCN_ECUDA;
+    }
+    configured = true;
+  }
+  stem_wgrad_kernel<<<a.splits, 288, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  return after_launch("stem_wgrad_kernel");
 }

@@ -375,6 +375,51 @@ extern "C" int mcn_input_prep(const float* x, long long n, float mean, float sca
   return after_launch("input_prep");
 }
 
+// RGB -> 4-channel pixels (the stem convolution's input format): 4 pixels per thread, 24 bytes in
+// (three aligned 8-byte loads), 32 bytes out; the 4th channel is written as zero.
+__global__ void pad3to4_kernel(const uint2* __restrict__ x, long long quads, uint4* __restrict__ y) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < quads;
+       i += (long long)gridDim.x * blockDim.x) {
+    const uint2 a = x[3 * i], b = x[3 * i + 1], c = x[3 * i + 2];
+    // elements (16-bit): a.x = p0c0 p0c1 | a.y = p0c2 p1c0 | b.x = p1c1 p1c2 | b.y = p2c0 p2c1 | c.x = p2c2 p3c0 | c.y = p3c1 p3c2
+    uint4 o0, o1;
+    o0.x = a.x;
+    o0.y = a.y & 0xFFFFu;
+    o0.z = (a.y >> 16) | (b.x << 16);
+    o0.w = b.x >> 16;
+    o1.x = b.y;
+    o1.y = c.x & 0xFFFFu;
+    o1.z = (c.x >> 16) | (c.y << 16);
+    o1.w = c.y >> 16;
+    y[2 * i] = o0;
+    y[2 * i + 1] = o1;
+  }
+}
+__global__ void pad3to4_tail_kernel(const __nv_bfloat16* __restrict__ x, long long p0, long long p1,
+                                    __nv_bfloat16* __restrict__ y) {
+  for (long long p = p0 + blockIdx.x * blockDim.x + threadIdx.x; p < p1; p += (long long)gridDim.x * blockDim.x) {
+    y[4 * p] = x[3 * p];
+    y[4 * p + 1] = x[3 * p + 1];
+    y[4 * p + 2] = x[3 * p + 2];
+    y[4 * p + 3] = __float2bfloat16_rn(0.f);
+  }
+}
+
+extern "C" int mcn_pad_rgb4(const void* x_bf16, long long pixels, void* y_bf16, void* stream) {
+  MCN_REQUIRE(x_bf16 && y_bf16 && pixels >= 0, "pad_rgb4: bad argument");
+  MCN_REQUIRE(reinterpret_cast<uintptr_t>(x_bf16) % 8 == 0 && reinterpret_cast<uintptr_t>(y_bf16) % 16 == 0,
+              "pad_rgb4: misaligned tensor");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long quads = pixels / 4;
+  if (quads > 0)
+    pad3to4_kernel<<<grid_for(quads, 256), 256, 0, st>>>(static_cast<const uint2*>(x_bf16), quads,
+                                                         static_cast<uint4*>(y_bf16));
+  if (quads * 4 < pixels)
+    pad3to4_tail_kernel<<<1, 32, 0, st>>>(static_cast<const __nv_bfloat16*>(x_bf16), quads * 4, pixels,
+                                          static_cast<__nv_bfloat16*>(y_bf16));
+  return after_launch("pad_rgb4");
+}
+
 extern "C" int mcn_copy_channels(int dtype, const void* src, long long rows, int Csrc, int src_off,
                                  void* dst, int Cdst, int dst_off, int Ccopy, int accumulate,
                                  void* stream) {

@@ -11,6 +11,8 @@ torch is used for device memory, streams, CUDA-graph capture and torch.distribut
 arithmetic kernel on the step is a libmcn launch.
 """
 import ctypes
+import os
+import sys
 
 import numpy as np
 import torch
@@ -97,6 +99,12 @@ class Engine(object):
         self.use_cuda_graph = use_cuda_graph
         self._inputs = {name: self.tensor_view(t) for name, t in self.graph.inputs.items()}
         self._pinned = {}
+        self._works = []
+        self._bucket_ready = {}
+        self._peer = None
+        if self.world > 1:
+            self._setup_grad_buckets()
+            self._setup_peer_comm()
 
     # ------------------------------------------------------------------ memory views
     def addr(self, ptr):
@@ -141,10 +149,10 @@ class Engine(object):
         self._inf = conv(self.plan.inf)
         # collective points, keyed by launch index
         self._ar = {"f": {}, "b": {}}
-        for phase, idx, ptr, nbytes, dt in self.plan.allreduce_points:
+        for k, (phase, idx, ptr, nbytes, dt) in enumerate(self.plan.allreduce_points):
             tdt = torch.float64 if dt == "f64" else torch.float32
             n = nbytes // (8 if dt == "f64" else 4)
-            self._ar[phase].setdefault(idx, []).append(self.view(ptr, n, tdt))
+            self._ar[phase].setdefault(idx, []).append((self.view(ptr, n, tdt), k))
         z0, z1 = self.plan.region_span["zero"]
         self._zero_ptr = self.base + z0
         self._zero_n = (z1 - z0) // 4
@@ -152,20 +160,78 @@ class Engine(object):
     def _run(self, launches, phase, stream):
         ar = self._ar[phase]
         check = _lib.check
-        if not ar:
+        ready = self._bucket_ready if phase == "b" else {}
+        if not ar and not ready:
             for fn, args, name, tag in launches:
                 rc = fn(*args, stream)
                 if rc:
                     check(rc, name + " [" + tag + "]")
             return
         import torch.distributed as dist
+        peer = self._peer
         for i, (fn, args, name, tag) in enumerate(launches):
             if i in ar:
-                for t in ar[i]:
-                    dist.all_reduce(t, group=self.pg)
+                for t, k in ar[i]:
+                    if peer is not None:
+                        # one-shot exchange over NVLink peer memory (csrc/comm.cu)
+                        p = t.data_ptr()
+                        check(self.lib.mcn_peer_allreduce(
+                            peer["peers"], peer["mail"][k], peer["flag"][k], peer["ctr"] + 8 * k,
+                            1 if t.dtype == torch.float64 else 0, p, t.numel(), None, 0, p, self.rank,
+                            self.world, stream), "peer_allreduce")
+                    else:
+                        dist.all_reduce(t, group=self.pg)
             rc = fn(*args, stream)
             if rc:
                 check(rc, name + " [" + tag + "]")
+            if i in ready:
+                # every gradient of these buckets is final: exchange them while backward continues
+                for s0, e0 in ready[i]:
+                    self._works.append(dist.all_reduce(self._flat_grads[s0:e0], op=dist.ReduceOp.SUM,
+                                                       group=self.pg, async_op=True))
+
+    # ------------------------------------------------------------------ multi-GPU set-up
+    def _setup_grad_buckets(self):
+        p = self.plan
+        self._flat_grads = self.view(Ptr(p.b_grad), p.n_train, torch.float32)
+        self._bucket_ready = {}
+        self._bucket_tail = []
+        overlap = os.environ.get("MCN_OVERLAP_GRADS", "1") != "0"
+        for s0, e0, r in p.grad_bucket_schedule(int(self.kw.get("bucket_elems", 4 * 1024 * 1024))):
+            if overlap and r >= 0:
+                self._bucket_ready.setdefault(r, []).append((s0, e0))
+            else:
+                self._bucket_tail.append((s0, e0))
+
+    def _setup_peer_comm(self):
+        """Symmetric-memory mailboxes for the synchronised-BN exchanges (mcn_peer_allreduce).  Falls
+        back to NCCL all-reduces when peer mapping is not available (MCN_PEER_ALLREDUCE=0 forces it)."""
+        pts = self.plan.allreduce_points
+        if not pts or os.environ.get("MCN_PEER_ALLREDUCE", "1") == "0":
+            return
+        import torch.distributed as dist
+        try:
+            import torch.distributed._symmetric_memory as symm
+            mail, off = [], 0
+            for _, _, _, nbytes, _ in pts:
+                mail.append(off)
+                off += (self.world * nbytes + 255) // 256 * 256
+            flag = [off + 512 * k for k in range(len(pts))]       # [world] uint64 per point, world <= 64
+            off += 512 * len(pts)
+            buf = symm.empty(off, dtype=torch.uint8, device=self.device)
+            buf.zero_()
+            torch.cuda.synchronize(self.device)
+            group = self.pg if self.pg is not None else dist.group.WORLD
+            hdl = symm.rendezvous(buf, group)
+            ctr = torch.zeros(len(pts), dtype=torch.int64, device=self.device)
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=group)                          # every region is zeroed before any push
+            self._peer = {"buf": buf, "hdl": hdl, "ctr_t": ctr, "ctr": ctr.data_ptr(),
+                          "peers": int(hdl.buffer_ptrs_dev), "mail": mail, "flag": flag}
+        except Exception as e:                                     # noqa: BLE001
+            sys.stderr.write("[myconvnet_b200] peer-memory all-reduce unavailable (%s: %s); "
+                             "using NCCL for the BN statistics\n" % (type(e).__name__, e))
+            self._peer = None
 
     # ------------------------------------------------------------------ variables
     def _var_view(self, buf, v, n=None):
@@ -178,13 +244,20 @@ class Engine(object):
             kpad, co = v.storage_shape
             flat = value.reshape(-1, co)
             out = np.zeros((kpad, co), dtype=np.float32)
-            out[:flat.shape[0]] = flat
+            rows = getattr(v, "storage_rows", None)
+            if rows is not None:
+                out[rows] = flat            # gather-stem layout: widened filter rows, 4-channel pixels
+            else:
+                out[:flat.shape[0]] = flat
             return out
         return value
 
     def _from_storage(self, v, arr):
         arr = np.asarray(arr).reshape(v.storage_shape)
         if v.storage_shape != v.shape:
+            rows = getattr(v, "storage_rows", None)
+            if rows is not None:
+                return arr[rows].reshape(v.shape).copy()
             k = int(np.prod(v.shape[:-1]))
             return arr[:k].reshape(v.shape).copy()
         return arr.reshape(v.shape).copy()
@@ -376,10 +449,15 @@ class Engine(object):
                                              st), "opt_step")
 
     def _allreduce_grads(self):
-        from .dist import allreduce_sum_flat
-        p = self.plan
-        flat = self.view(Ptr(p.b_grad), p.n_train, torch.float32)
-        allreduce_sum_flat(flat, int(self.kw.get("bucket_elems", 8 * 1024 * 1024)), group=self.pg)
+        """Buckets whose gradients were final early are already in flight (started from _run);
+        start the rest and wait for all of them before the optimiser reads the buffer."""
+        import torch.distributed as dist
+        for s0, e0 in self._bucket_tail[::-1]:
+            self._works.append(dist.all_reduce(self._flat_grads[s0:e0], op=dist.ReduceOp.SUM,
+                                               group=self.pg, async_op=True))
+        for w in self._works:
+            w.wait()
+        self._works = []
 
     def train_step(self, X=None, Y=None, lr_multiplier=1.0, fetch_loss=True, update=True,
                    prefetched=False):

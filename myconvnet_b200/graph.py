@@ -50,6 +50,7 @@ class Var(object):
         self.needs_bf16 = False         # tensor-core operand copies wanted
         self.needs_bf16_t = False
         self.gemm_dims = None           # (taps, cin, cout) of the storage layout
+        self.storage_rows = None        # storage row of each logical leading index (gather-stem layout)
 
     @property
     def size(self):

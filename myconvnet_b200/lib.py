@@ -39,6 +39,9 @@ SIGNATURES = {
     "mcn_dwconv2d_fwd": "Diipipp",
     "mcn_dwconv2d_bwd_data": "Diipipp",
     "mcn_dwconv2d_bwd_filter": "Diippp",
+    "mcn_stem_conv_fprop": "Dppppp",
+    "mcn_stem_conv_wgrad": "Dppp",
+    "mcn_pad_rgb4": "plp",
     "mcn_weight_prep": "piiipp",
     "mcn_im2col": "Dippi",
     "mcn_bn_stats": "iplip",
@@ -72,6 +75,7 @@ SIGNATURES = {
     "mcn_sigmoid_xent": "plfffppi",
     "mcn_opt_step": "ipilpp",
     "mcn_transpose_add_f32": "piiip",
+    "mcn_peer_allreduce": "pllpipipipii",
     "mcn_fill_f32": "plf",
     "mcn_scale_f32": "plf",
 }
@@ -97,6 +101,8 @@ def load():
     lib.mcn_last_error.argtypes = []
     lib.mcn_version.restype = ctypes.c_int
     lib.mcn_launch_count.restype = ctypes.c_longlong
+    lib.mcn_stem_conv_kpad.restype = ctypes.c_int
+    lib.mcn_stem_conv_kpad.argtypes = [ctypes.POINTER(ConvDescC)]
     _lib = lib
     return lib
 

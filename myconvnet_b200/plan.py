@@ -229,8 +229,17 @@ class Plan(object):
                     kh, kw, ci, co = w.shape
                     kpad = _align(kh * kw * ci, 8)
                     w.storage_shape = (kpad, co)
+                    w.storage_rows = None
                     w.gemm_dims = (1, kpad, co)
                     w.needs_bf16 = w.needs_bf16_t = True
+                    node.attrs["kpad"] = kpad
+                elif route == "stem":
+                    kh, kw, ci, co = w.shape
+                    kpad, rows = self._stem_geometry(node)
+                    w.storage_shape = (kpad, co)
+                    w.storage_rows = rows           # storage row of every reference [r, s, c]
+                    w.gemm_dims = (1, kpad, co)
+                    w.needs_bf16_t = True           # [Cout][Kpad]: the fprop operand
                     node.attrs["kpad"] = kpad
             elif node.op in ("conv2d", "dense", "conv2d_transpose"):
                 node.attrs["route"] = "direct"
@@ -251,9 +260,42 @@ class Plan(object):
             return "direct"
         if ci % 8 == 0 and co % 8 == 0 and kh * kw <= 52:
             return "tc"
+        if self._stem_geometry(node) is not None:
+            return "stem"
         if co % 8 == 0 and kh * kw <= 52:
             return "im2col"
         return "direct"
+
+    @staticmethod
+    def stem_kpad(kh, kw):
+        """Rows of the stem weight storage [Kpad][Cout]: k = (r*(kw+1) + s)*4 + c, padded to a
+        multiple of 128 (mirrors mcn_stem_conv_kpad in csrc/conv_tc.cu)."""
+        epr = (kw + 1) * 4
+        rpc = 64 // epr
+        kc = (kh + rpc - 1) // rpc
+        return (kc + 1) // 2 * 2 * 64
+
+    def _stem_geometry(self, node):
+        """RGB stems the gather kernels handle (mcn_stem_conv_fprop): 3x3 / 7x7, stride 2 along W,
+        unit dilation, even image width and left pad, Cout % 64 == 0, fed by the network input
+        (no gradient into the image).  Returns (kpad, row index of every [r, s, c]) or None."""
+        if os.environ.get("MCN_STEM_GATHER", "1") == "0" or node.op != "conv2d":
+            return None
+        w = node.vars["w"]
+        kh, kw, ci, co = w.shape
+        a = node.attrs
+        x = node.inputs[0]
+        if ci != 3 or (kh, kw) not in ((3, 3), (7, 7)) or co % 64 != 0 or co > 256:
+            return None
+        if a["s"][1] != 2 or tuple(a["d"]) != (1, 1) or a["pad"][1] % 2 or x.shape[2] % 2:
+            return None
+        if x.node is not None and x.node.op not in ("input", "input_prep"):
+            return None
+        if x.size % 4:       # mcn_pad_rgb4 works on whole quads of pixels plus a scalar tail: any size is fine
+            pass
+        rows = np.array([(r * (kw + 1) + s2) * 4 + c for r in range(kh) for s2 in range(kw) for c in range(ci)],
+                        dtype=np.int64)
+        return self.stem_kpad(kh, kw), rows
 
     def _needs_input_grad(self, node):
         return self._tensor_needs_grad(node.inputs[0])
@@ -306,7 +348,7 @@ class Plan(object):
                 prod = node.inputs[0].node
                 node.attrs["stats_in_conv"] = False
                 if (self.fuse_bn_stats and self.cdt == "bf16" and prod is not None
-                        and prod.op == "conv2d" and prod.attrs.get("route") in ("tc", "im2col")
+                        and prod.op == "conv2d" and prod.attrs.get("route") in ("tc", "im2col", "stem")
                         and prod.attrs["bn_stats_node"] is None
                         and node.inputs[0].shape[-1] % 64 == 0
                         and self._stats_fusion_pays(prod)):
@@ -466,6 +508,15 @@ class Plan(object):
             else:
                 self.L("f", "mcn_conv2d_fprop_tc", d, self.tbuf[x], self.pbf16t(w), pb, py, self.ccode,
                        self.conv_mode, 0, tag=node.scope)
+        elif route == "stem":
+            # 4-channel copy of the image, then the gather convolution (no im2col matrix)
+            x4 = self.node_buf(node, "x4", "rgb4:%s" % node.scope, d.N * d.H * d.W * 4 * 2)
+            node.attrs["x4"] = x4
+            d4 = self.conv_desc(**dict({f: getattr(d, f) for f in ConvDesc.FIELDS}, Cin=4))
+            node.attrs["desc4"] = d4
+            self.L("f", "mcn_pad_rgb4", self.tbuf[x], d.N * d.H * d.W, Ptr(x4), tag=node.scope + "/rgb4")
+            self.L("f", "mcn_stem_conv_fprop", d4, Ptr(x4), self.pbf16t(w), pb, py,
+                   psums if bn is not None else NULL, tag=node.scope)
         elif route == "im2col":
             kpad = node.attrs["kpad"]
             m = d.N * d.Ho * d.Wo
@@ -918,6 +969,11 @@ class Plan(object):
                                              self.conv_mode, 0, tag=node.scope + "/dgrad"),
                             emit_acc=lambda p: self.L("b", "mcn_conv2d_dgrad_tc", d, gy, self.pbf16(w), p, 1,
                                                       self.conv_mode, 1, tag=node.scope + "/dgrad+"))
+        elif route == "stem":
+            if self._var_trains(w):
+                self.L("b", "mcn_stem_conv_wgrad", node.attrs["desc4"], Ptr(node.attrs["x4"]), gy,
+                       self.pgrad(w), tag=node.scope + "/wgrad")
+            assert not self._needs_input_grad(node), "stem route is only chosen for network inputs"
         elif route == "im2col":
             if self._var_trains(w):
                 self.L("b", "mcn_conv2d_wgrad_tc", node.attrs["gemm_desc"], Ptr(node.attrs["col"]), gy,
@@ -1168,6 +1224,37 @@ class Plan(object):
         self.contribute(x, x.size * DT_SIZE[x.dtype],
                         lambda p: self.L("b", "mcn_resize_bilinear_bwd", DT_CODE[x.dtype], gy, n, h, w, c,
                                          ho, wo, node.attrs["mode"], p, tag="resize_bwd"))
+
+    # ------------------------------------------------------------------ gradient buckets
+    def grad_bucket_schedule(self, bucket_elems):
+        """Slices of the flat gradient buffer and, for each, the index of the LAST backward launch
+        that writes into it: [(start_elem, end_elem, ready_idx)], ready_idx = -1 when no launch
+        does.  The engine starts a bucket's all-reduce right after launch `ready_idx`, so the
+        exchange of the last layers' gradients overlaps the rest of the backward pass (replaces
+        the reference's gather-everything-then-average, optimizers.py:117-147)."""
+        import bisect
+        from .dist import bucket_ranges
+        starts = [self.var_off[v] for v in self.trainable]
+        ends = [self.var_off[v] + v.storage_size for v in self.trainable]
+        last = [-1] * len(starts)
+        for li, l in enumerate(self.bwd):
+            for a in l.args:
+                if isinstance(a, Ptr) and a.buf is self.b_grad:
+                    e = a.off // 4
+                    vi = bisect.bisect_right(starts, e) - 1
+                    if 0 <= vi < len(starts) and e < ends[vi]:
+                        last[vi] = max(last[vi], li)
+        out = []
+        for s0, e0 in bucket_ranges(self.n_train, bucket_elems):
+            lo = max(0, bisect.bisect_right(starts, s0) - 1)
+            ready = -1
+            for vi in range(lo, len(starts)):
+                if starts[vi] >= e0:
+                    break
+                if ends[vi] > s0:
+                    ready = max(ready, last[vi])
+            out.append((s0, e0, ready))
+        return out
 
     # ------------------------------------------------------------------ summaries
     def launch_histogram(self):

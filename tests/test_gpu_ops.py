@@ -189,6 +189,66 @@ def test_conv_fused_bn_statistics(L, case, bias):
     assert rel_l2(y1.float().cpu(), yref) < 6e-3
 
 
+STEM_CASES = [
+    # n, h, w, k, stride_h, cout
+    (2, 64, 64, 7, 2, 64),
+    (3, 30, 34, 3, 2, 64),
+    (1, 224, 224, 7, 2, 64),
+    (5, 17, 22, 7, 2, 128),       # odd height, ragged last tile, two dy atoms
+]
+
+
+@pytest.mark.parametrize("case", STEM_CASES)
+def test_stem_gather_convolution(L, case):
+    """mcn_pad_rgb4 + mcn_stem_conv_fprop / _wgrad (RGB stem without an im2col matrix) vs the
+    oracle's conv2d and its autograd weight gradient; fused BN statistics checked as well."""
+    from myconvnet_b200.plan import Plan
+    n, h, w, k, st, co = case
+    rng = np.random.default_rng(5)
+    r = lambda a: torch.tensor(a).bfloat16().float().numpy()
+    x = r(rng.standard_normal((n, h, w, 3)).astype(np.float32))
+    wt = r((rng.standard_normal((k, k, 3, co)) * 0.1).astype(np.float32))
+    b = rng.standard_normal(co).astype(np.float32)
+    d, ho, wo = desc_for(L, x.shape, wt.shape, st, 1, "SAME")
+    d4 = L.ConvDescC(n, h, w, 4, co, k, k, st, st, 1, 1, d.pad_t, d.pad_l, ho, wo)
+    lib = L.load()
+    kpad = lib.mcn_stem_conv_kpad(d4)
+    assert kpad == Plan.stem_kpad(k, k) and kpad > 0
+    rows = np.array([(rr * (k + 1) + ss) * 4 + c for rr in range(k) for ss in range(k) for c in range(3)])
+    wst = np.zeros((kpad, co), np.float32)
+    wst[rows] = wt.reshape(-1, co)
+    dy = r(rng.standard_normal((n, ho, wo, co)).astype(np.float32))
+    xt = torch.tensor(x)
+    wtt = torch.tensor(wt, requires_grad=True)
+    yref = tf_ops.conv2d(xt, wtt, (st, st), "SAME", (1, 1)) + torch.tensor(b)
+    yref.backward(torch.tensor(dy))
+    xd, dyd, wd, bd = dev(x, torch.bfloat16), dev(dy, torch.bfloat16), dev(wst), dev(b)
+    x4 = torch.full((n, h, w, 4), 9.0, device="cuda", dtype=torch.bfloat16)
+    L.check(lib.mcn_pad_rgb4(xd.data_ptr(), n * h * w, x4.data_ptr(), None))
+    w_t = torch.empty(co, kpad, device="cuda", dtype=torch.bfloat16)
+    L.check(lib.mcn_weight_prep(wd.data_ptr(), 1, kpad, co, None, w_t.data_ptr(), None))
+    y = torch.empty(n, ho, wo, co, device="cuda", dtype=torch.bfloat16)
+    sums = torch.zeros(2 * co, dtype=torch.float64, device="cuda")
+    L.check(lib.mcn_stem_conv_fprop(d4, x4.data_ptr(), w_t.data_ptr(), bd.data_ptr(), y.data_ptr(),
+                                    sums.data_ptr(), None))
+    y2 = torch.empty_like(y)
+    L.check(lib.mcn_stem_conv_fprop(d4, x4.data_ptr(), w_t.data_ptr(), bd.data_ptr(), y2.data_ptr(), None, None))
+    dw = torch.zeros(kpad, co, device="cuda")
+    L.check(lib.mcn_stem_conv_wgrad(d4, x4.data_ptr(), dyd.data_ptr(), dw.data_ptr(), None))
+    torch.cuda.synchronize()
+    assert torch.equal(x4[..., :3], xd) and float(x4[..., 3].abs().max()) == 0.0
+    assert rel_l2(y.float().cpu(), yref.detach()) < 6e-3
+    assert torch.equal(y, y2)
+    yf = y.double().reshape(-1, co)
+    exact = torch.cat([yf.sum(0), (yf * yf).sum(0)]).cpu().numpy()
+    scale = np.concatenate([np.abs(yf.cpu().numpy()).sum(0), (yf * yf).sum(0).cpu().numpy()]) + 1e-30
+    assert np.max(np.abs(sums.cpu().numpy() - exact) / scale) < 2e-6
+    dwh = dw.cpu().numpy()
+    assert rel_l2(dwh[rows].reshape(k, k, 3, co), wtt.grad) < 1e-4
+    other = np.setdiff1d(np.arange(kpad), rows)
+    assert np.all(dwh[other] == 0.0)          # widening tap / 4th channel / padding rows carry no gradient
+
+
 @pytest.mark.parametrize("code", [0, 1])
 @pytest.mark.parametrize("C", [64, 20, 320])
 @pytest.mark.parametrize("use_res", [False, True])

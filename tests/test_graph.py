@@ -47,17 +47,18 @@ def test_native_builder_matches_reference_graph(r50):
 def test_plan_fusion_and_launch_counts(r50):
     p = Plan(r50.graph)
     h = p.launch_histogram()
-    # convs with a deep reduction take the BN statistics in their epilogue (33 of the 53 that feed a
-    # BN); the store-bound 1x1 expansions keep the separate statistics pass; finalize is gone
-    assert h["mcn_conv2d_fprop_tc_stats"] + h["mcn_conv2d_fprop_tc"] == 54
-    assert h["mcn_conv2d_fprop_tc_stats"] + h["mcn_bn_stats"] == 53
+    # convs with a deep reduction take the BN statistics in their epilogue; the store-bound 1x1
+    # expansions keep the separate statistics pass; finalize is folded into the apply kernel
+    assert h["mcn_stem_conv_fprop"] == 1 and h["mcn_stem_conv_wgrad"] == 1 and h["mcn_pad_rgb4"] == 1
+    assert h["mcn_conv2d_fprop_tc_stats"] + h["mcn_conv2d_fprop_tc"] == 53          # 52 convs + dense
+    assert h["mcn_conv2d_fprop_tc_stats"] + 1 + h["mcn_bn_stats"] == 53             # +1: the stem fuses too
     assert h["mcn_conv2d_fprop_tc_stats"] >= 30 and "mcn_bn_finalize" not in h
-    assert h["mcn_conv2d_wgrad_tc"] == 54
+    assert h["mcn_conv2d_wgrad_tc"] == 53
     assert h["mcn_conv2d_dgrad_tc"] == 53                                        # no dgrad into the images
     assert h["mcn_bn_apply_stats"] == 53 and "mcn_act_fwd" not in h and "mcn_add_act_fwd" not in h
     # the unfused plan keeps the separate statistics pass
     hu = Plan(r50.graph, fuse_bn_stats=False).launch_histogram()
-    assert hu["mcn_conv2d_fprop_tc"] == 54 and hu["mcn_bn_stats"] == 53 and hu["mcn_bn_apply_stats"] == 53
+    assert hu["mcn_conv2d_fprop_tc"] == 53 and hu["mcn_bn_stats"] == 53 and hu["mcn_bn_apply_stats"] == 53
     assert "mcn_accumulate" not in h                    # multi-consumer gradients add in the dgrad epilogue
     fused = [n for n in r50.graph.nodes if n.op == "bn"]
     assert sum(n.attrs["residual"] is not None for n in fused) == 16
@@ -68,10 +69,23 @@ def test_plan_fusion_and_launch_counts(r50):
     assert p.arena_bytes < 40e9
     offs = sorted((b.offset, b.offset + b.nbytes) for b in p.bufs if b.region != "temp")
     assert all(offs[i][1] <= offs[i + 1][0] for i in range(len(offs) - 1))
-    # stem: RGB input goes through explicit im2col with a zero-padded K
+    # stem: the RGB input is gathered from a 4-channel copy of the image; the weight is stored
+    # [Kpad=256][64] with row (r*8 + s)*4 + c (8th tap and 4th channel zero)
     stem = [n for n in r50.graph.nodes if n.op == "conv2d"][0]
-    assert stem.attrs["route"] == "im2col" and stem.attrs["kpad"] == 152
-    assert stem.vars["w"].storage_shape == (152, 64)
+    assert stem.attrs["route"] == "stem" and stem.attrs["kpad"] == 256
+    w = stem.vars["w"]
+    assert w.storage_shape == (256, 64) and len(w.storage_rows) == 147
+    assert w.storage_rows[3] == 4 and w.storage_rows[21] == 32 and w.storage_rows.max() == 6 * 32 + 6 * 4 + 2
+    # with the gather stem disabled the explicit im2col route is used (K padded to 152)
+    import os
+    os.environ["MCN_STEM_GATHER"] = "0"
+    try:
+        p2 = Plan(r50.graph)
+        assert stem.attrs["route"] == "im2col" and stem.attrs["kpad"] == 152
+        assert stem.vars["w"].storage_shape == (152, 64) and p2.launch_histogram()["mcn_im2col"] == 1
+    finally:
+        del os.environ["MCN_STEM_GATHER"]
+        Plan(r50.graph)          # restore the default layout on the shared fixture
 
 
 def test_plan_keeps_taps_unfused(r50):
@@ -86,6 +100,27 @@ def test_sync_bn_plan_has_collective_points(r50):
     p = Plan(r50.graph, world_size=8)
     assert len([a for a in p.allreduce_points if a[0] == "f"]) == 53
     assert len([a for a in p.allreduce_points if a[0] == "b"]) == 53
+
+
+def test_gradient_buckets_become_ready_in_reverse_layer_order(r50):
+    """The flat gradient buffer mirrors the variable order (stem first), backward runs last layer
+    first: bucket k's all-reduce can start after launch ready[k], long before backward ends."""
+    p = Plan(r50.graph, world_size=8)
+    sched = p.grad_bucket_schedule(4 * 1024 * 1024)
+    assert sched[0][0] == 0 and sched[-1][1] == p.n_train
+    assert all(a[1] == b[0] for a, b in zip(sched, sched[1:]))
+    ready = [r for _, _, r in sched]
+    assert ready == sorted(ready, reverse=True) and ready[-1] < 10 and ready[0] == len(p.bwd) - 1
+    # the dense layer's gradients (last bucket) come from the first few backward launches
+    tags = [p.bwd[i].tag for i in range(ready[-1] + 1)]
+    assert any("logits" in t for t in tags)
+    # every launch that writes into the gradient buffer is at or before its bucket's ready index
+    for li, l in enumerate(p.bwd):
+        for a in l.args:
+            if hasattr(a, "buf") and a.buf is p.b_grad:
+                e = a.off // 4
+                r = [rd for s0, e0, rd in sched if s0 <= e < e0][0]
+                assert li <= r, (li, r, l.tag)
 
 
 def test_fp32_config_uses_exact_path(have_reference_models):
@@ -155,7 +190,8 @@ def test_inference_plan_uses_ema_and_moving_statistics(r50):
     p = Plan(r50.graph)
     names = [l.fn for l in p.inf]
     assert names.count("mcn_bn_infer") == 53 and "mcn_bn_stats" not in names
-    assert names.count("mcn_conv2d_fprop_tc") == 54 and "mcn_conv2d_fprop_tc_stats" not in names
+    assert names.count("mcn_conv2d_fprop_tc") == 53 and names.count("mcn_stem_conv_fprop") == 1
+    assert "mcn_conv2d_fprop_tc_stats" not in names
     # every weight operand of the inference list comes from the EMA copies
     ema_ptrs = [a for l in p.inf for a in l.args if hasattr(a, "buf") and a.buf in (p.b_ema, p.b_bf16_ema)]
     raw_ptrs = [a for l in p.inf for a in l.args if hasattr(a, "buf") and a.buf in (p.b_param, p.b_bf16)]
