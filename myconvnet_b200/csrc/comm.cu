@@ -60,7 +60,7 @@ peer_allreduce_kernel(const unsigned long long* __restrict__ peers, long long ma
         reinterpret_cast<const unsigned long long*>(peers[rank] + flag_off) + threadIdx.x;
     unsigned long long spins = 0;
     while (ld_acquire_sys(mine) < seq) {
-      if (++spins > (1ull << 31)) {   // a missing peer becomes a launch failure, not a hang
+      if (++spins > (1ull << 25)) {   // ~20 s: a missing peer becomes a launch failure, not a hang
         printf("mcn: peer all-reduce timeout rank=%d waiting for rank=%d seq=%llu\n", rank,
                (int)threadIdx.x, seq);
         __trap();

@@ -121,7 +121,8 @@ constexpr int kStatRowWords = 36;
 constexpr int kStatStageWords = 4 * 32 * kStatRowWords;          // four epilogue warps
 constexpr int kStatAccWarp = 2 * 256;                            // [sum | sum sq] x block_n <= 256
 constexpr int kStatAccFloats = 4 * kStatAccWarp;                 // one slice per epilogue warp
-constexpr int kStatSmemBytes = kStatStageWords * 4 + kStatAccFloats * 4;
+constexpr int kEpiStageBytes = kStatStageWords * 4;              // always: the store path stages through it
+constexpr int kStatAccBytes = kStatAccFloats * 4;                // only with fused statistics
 constexpr int kBarRegionBytes = 256;                             // mbarriers + tmem slot
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
@@ -147,6 +148,11 @@ __device__ __forceinline__ void stats_flush(const EpiArgs& e, float* acc, int n_
   epi_bar_sync();
 }
 
+// (A shared-memory staged, fully coalesced write-out was tried in round 1 and measured SLOWER on
+// the store-heavy 1x1 convolutions (24.8 vs 24.5 ms/step): ncu shows the epilogue warps bound by
+// their own instruction stream (~1500 instructions per 128x256 tile at one warp per scheduler,
+// 5.8 cycles per issued instruction), not by LSU wavefronts, so adding instructions loses.  The
+// lever is more epilogue warps per TMEM quadrant / fewer instructions per element.)
 // One output tile: wait for the accumulator, TMEM -> registers -> global.  Each thread owns one
 // output pixel (row) and walks its channels 64 at a time: 64 bf16 = one full 128-byte line written
 // with four 32-byte stores (fp32 output: eight).  The TMEM buffer is handed back to the MMA warp
@@ -290,6 +296,7 @@ struct GemmConvArgs {
   CUtensorMap mapB;
   TileGeom g;
   int taps, k_chunks, ksteps_last, block_n, stages, tiles_n, tmem_cols, total_tiles;
+  int b_stationary;   // the CTA's whole weight slab (all taps / k-chunks of its n-tile) stays in smem
   long long out_sn, out_sh, out_sw;  // element strides of the output pixel grid
   EpiArgs e;
   TapTab tab;
@@ -308,15 +315,22 @@ gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
   const int lane = threadIdx.x & 31;
   const int stages = args.stages;
   const uint32_t b_bytes = static_cast<uint32_t>(args.block_n) * 128u;
-  const uint32_t stage_bytes = kABytes + b_bytes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(stages) * stage_bytes);
+  // Weight-stationary mode: small weight slabs (1x1 convs) are loaded ONCE per CTA behind the
+  // activation ring instead of once per tile — for K = 64, N = 256 the weights were two thirds of
+  // the shared-memory fill traffic.  Needs a constant n-tile per CTA (gridDim % tiles_n == 0).
+  const bool bstat = args.b_stationary != 0;
+  const uint32_t stage_bytes = bstat ? kABytes : kABytes + b_bytes;
+  const int k_iters = args.taps * args.k_chunks;
+  uint8_t* smemBs = smem + static_cast<size_t>(stages) * stage_bytes;
+  uint8_t* tail = smemBs + (bstat ? static_cast<size_t>(k_iters) * b_bytes : 0);
+  uint64_t* full = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty = full + stages;
   uint64_t* tmem_full = empty + stages;     // [2]
   uint64_t* tmem_empty = tmem_full + 2;     // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* bstat_bar = tmem_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bstat_bar + 1);
 
   const int total_tiles = args.total_tiles;
-  const int k_iters = args.taps * args.k_chunks;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) ptx::prefetch_tmap(&args.mapA[i]);
@@ -329,6 +343,7 @@ gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
       ptx::mbar_init(&tmem_full[b], 1);
       ptx::mbar_init(&tmem_empty[b], 4);   // one arrival per epilogue warp
     }
+    ptx::mbar_init(bstat_bar, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -345,6 +360,15 @@ gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
     if (ptx::elect_one()) {
       const uint32_t a_tx = (args.g.a_mode == 0) ? static_cast<uint32_t>(args.g.rows_box) * 128u
                                                  : static_cast<uint32_t>(kABytes);
+      if (bstat) {
+        const int n_t = blockIdx.x % args.tiles_n;
+        ptx::mbar_expect_tx(bstat_bar, static_cast<uint32_t>(k_iters) * b_bytes);
+        for (int t = 0; t < args.taps; ++t)
+          for (int kc = 0; kc < args.k_chunks; ++kc)
+            ptx::tma_load_2d(&args.mapB, bstat_bar,
+                             smemBs + static_cast<size_t>(t * args.k_chunks + kc) * b_bytes, kc * 64,
+                             args.tab.brow[t] + n_t * args.block_n);
+      }
       int it = 0;
       for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x) {
         const int n_t = tile_id % args.tiles_n;
@@ -354,7 +378,7 @@ gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
             const int s = it % stages;
             const uint32_t ph = static_cast<uint32_t>(it / stages) & 1u;
             ptx::mbar_wait(&empty[s], ph ^ 1u);
-            ptx::mbar_expect_tx(&full[s], a_tx + b_bytes);
+            ptx::mbar_expect_tx(&full[s], bstat ? a_tx : a_tx + b_bytes);
             uint8_t* sA = smem + static_cast<size_t>(s) * stage_bytes;
             uint8_t* sB = sA + kABytes;
             if (args.g.a_mode == 0) {
@@ -365,8 +389,9 @@ gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
                                       tile.n0, static_cast<uint16_t>(args.tab.dw[t]),
                                       static_cast<uint16_t>(args.tab.dh[t]));
             }
-            ptx::tma_load_2d(&args.mapB, &full[s], sB, kc * 64,
-                             args.tab.brow[t] + n_t * args.block_n);
+            if (!bstat)
+              ptx::tma_load_2d(&args.mapB, &full[s], sB, kc * 64,
+                               args.tab.brow[t] + n_t * args.block_n);
           }
         }
       }
@@ -374,6 +399,7 @@ gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
     const uint32_t idesc = ptx::make_idesc_bf16(128, args.block_n, 0, 0);
+    if (bstat) ptx::mbar_wait(bstat_bar, 0);
     int it = 0, lt = 0;
     for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x, ++lt) {
       const int buf = lt & 1;
@@ -390,8 +416,9 @@ gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
             const uint32_t a_addr = ptx::smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
-            const uint32_t b_addr = a_addr + kABytes;
-            const int ksteps = (kc == args.k_chunks - 1) ? args.ksteps_last : 4;
+            const uint32_t b_addr = bstat ? ptx::smem_u32(smemBs) + static_cast<uint32_t>(kit) * b_bytes
+                                          : a_addr + kABytes;
+            const int ksteps = (args.e.debug & 2) ? 0 : ((kc == args.k_chunks - 1) ? args.ksteps_last : 4);
             for (int k = 0; k < ksteps; ++k) {
               const uint64_t ad = ptx::make_smem_desc(a_addr + k * 32, 16, 1024);
               const uint64_t bd = ptx::make_smem_desc(b_addr + k * 32, 16, 1024);
@@ -410,8 +437,7 @@ gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
     // full 128-byte line written with four 32-byte stores (fp32 output: eight).
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;
-    uint32_t* stat_stage = reinterpret_cast<uint32_t*>(smem + static_cast<size_t>(stages) * stage_bytes +
-                                                       kBarRegionBytes);
+    uint32_t* stat_stage = reinterpret_cast<uint32_t*>(tail + kBarRegionBytes);
     float* stat_acc_all = reinterpret_cast<float*>(stat_stage + kStatStageWords);
     float* stat_acc = stat_acc_all + quad * kStatAccWarp;
     stat_stage += quad * 32 * kStatRowWords;
@@ -1462,15 +1488,36 @@ int smem_optin_limit() {
 
 int launch_gemm_conv(GemmConvArgs& a, int tiles_m, cudaStream_t st) {
   a.e.block_n = a.block_n;
-  const uint32_t stage_bytes = kABytes + a.block_n * 128;
+  a.total_tiles = tiles_m * a.tiles_n;
+  {
+    static int dbg = -1;      // timing experiments: MCN_DEBUG_SKIP bit0 no stores, bit2 no TMEM loads
+    if (dbg < 0) {
+      const char* e = getenv("MCN_DEBUG_SKIP");
+      dbg = e ? atoi(e) : 0;
+    }
+    a.e.debug = dbg;
+  }
+  const int grid_n = std::min(a.total_tiles, num_sms());
+  // weight-stationary when the CTA's weight slab is small and it sees one n-tile only
+  static int ws_enabled = -1;
+  if (ws_enabled < 0) {
+    const char* e = getenv("MCN_WEIGHT_STATIONARY");
+    ws_enabled = (e && e[0] == '0') ? 0 : ((e && e[0] == '2') ? 2 : 1);   // 2: also for tiny grids (tests)
+  }
+  const size_t b_slab = static_cast<size_t>(a.taps) * a.k_chunks * a.block_n * 128;
+  a.b_stationary = (ws_enabled && b_slab <= 128 * 1024 && grid_n % a.tiles_n == 0 &&
+                    (a.total_tiles >= 2 * grid_n || ws_enabled == 2)) ? 1 : 0;
+  const uint32_t stage_bytes = a.b_stationary ? kABytes : kABytes + a.block_n * 128;
   // one persistent CTA per SM: the whole shared memory is the TMA ring
-  int stages = std::min(8, static_cast<int>((200 * 1024) / stage_bytes));
+  const size_t fixed = kBarRegionBytes + (a.e.stats ? kEpiStageBytes + kStatAccBytes : 0) + 1024 +
+                       (a.b_stationary ? b_slab : 0);
+  const size_t ring_budget = std::min<size_t>(200 * 1024, static_cast<size_t>(smem_optin_limit()) - fixed);
+  int stages = std::min(8, static_cast<int>(ring_budget / stage_bytes));
   stages = std::max(2, stages);
   a.stages = stages;
   a.tmem_cols = 2 * tmem_cols_for(a.block_n);   // double-buffered accumulator
-  a.total_tiles = tiles_m * a.tiles_n;
-  size_t smem = static_cast<size_t>(stages) * stage_bytes + kBarRegionBytes +
-                (a.e.stats ? kStatSmemBytes : 0) + 1024;
+  size_t smem = static_cast<size_t>(stages) * stage_bytes + (a.b_stationary ? b_slab : 0) +
+                kBarRegionBytes + (a.e.stats ? kEpiStageBytes + kStatAccBytes : 0) + 1024;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(gemm_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1480,7 +1527,7 @@ int launch_gemm_conv(GemmConvArgs& a, int tiles_m, cudaStream_t st) {
     }
     configured = true;
   }
-  dim3 grid(static_cast<unsigned>(std::min(a.total_tiles, num_sms())));
+  dim3 grid(static_cast<unsigned>(grid_n));
   gemm_conv_kernel<<<grid, 192, smem, st>>>(a);
   return after_launch("gemm_conv_kernel");
 }
@@ -1562,7 +1609,7 @@ int launch_halo(const void* in, int C_in, int W_in, int H_in, int N, const void*
   a.total_tiles = a.tiles_w * a.tiles_h * N * a.tiles_n;
   const int nb_slots = a.b_stationary ? a.taps * a.k_chunks : a.b_stages;
   size_t smem = (size_t)a.a_stages * a.halo_stride + (size_t)nb_slots * b_bytes + kBarRegionBytes +
-                (a.e.stats ? kStatSmemBytes : 0) + 1024;
+                (a.e.stats ? kEpiStageBytes + kStatAccBytes : 0) + 1024;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(halo_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -2132,7 +2179,7 @@ extern "C" int mcn_stem_conv_fprop(const mcn_conv_desc* d, const void* x4, const
   a.nb_atoms = 0;
   const size_t a_stage = static_cast<size_t>(a.kc_alloc) * kABytes;
   const size_t fixed = static_cast<size_t>(a.kc) * d->Cout * 128 + kBarRegionBytes +
-                       (bn_sums ? kStatSmemBytes : 0) + 1024;
+                       (bn_sums ? kEpiStageBytes + kStatAccBytes : 0) + 1024;
   a.stages = static_cast<int>(std::min<size_t>(3, (static_cast<size_t>(smem_optin_limit()) - fixed) / a_stage));
   MCN_REQUIRE(a.stages >= 2, "stem_conv_fprop: shared memory budget too small");
   a.tmem_cols = 2 * tmem_cols_for(d->Cout);

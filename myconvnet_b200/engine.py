@@ -149,10 +149,14 @@ class Engine(object):
         self._inf = conv(self.plan.inf)
         # collective points, keyed by launch index
         self._ar = {"f": {}, "b": {}}
-        for k, (phase, idx, ptr, nbytes, dt) in enumerate(self.plan.allreduce_points):
+        for k, (phase, idx, ptr, nbytes, dt, srcs) in enumerate(self.plan.allreduce_points):
             tdt = torch.float64 if dt == "f64" else torch.float32
             n = nbytes // (8 if dt == "f64" else 4)
-            self._ar[phase].setdefault(idx, []).append((self.view(ptr, n, tdt), k))
+            seg = None
+            if srcs is not None:
+                s0, n0, s1, n1 = srcs
+                seg = (self.view(s0, n0, tdt), self.view(s1, n1, tdt))
+            self._ar[phase].setdefault(idx, []).append((self.view(ptr, n, tdt), k, seg))
         z0, z1 = self.plan.region_span["zero"]
         self._zero_ptr = self.base + z0
         self._zero_n = (z1 - z0) // 4
@@ -171,15 +175,21 @@ class Engine(object):
         peer = self._peer
         for i, (fn, args, name, tag) in enumerate(launches):
             if i in ar:
-                for t, k in ar[i]:
+                for t, k, seg in ar[i]:
                     if peer is not None:
                         # one-shot exchange over NVLink peer memory (csrc/comm.cu)
-                        p = t.data_ptr()
+                        if seg is None:
+                            a0, n0, a1, n1 = t.data_ptr(), t.numel(), None, 0
+                        else:
+                            a0, n0, a1, n1 = seg[0].data_ptr(), seg[0].numel(), seg[1].data_ptr(), seg[1].numel()
                         check(self.lib.mcn_peer_allreduce(
                             peer["peers"], peer["mail"][k], peer["flag"][k], peer["ctr"] + 8 * k,
-                            1 if t.dtype == torch.float64 else 0, p, t.numel(), None, 0, p, self.rank,
+                            1 if t.dtype == torch.float64 else 0, a0, n0, a1, n1, t.data_ptr(), self.rank,
                             self.world, stream), "peer_allreduce")
                     else:
+                        if seg is not None:
+                            t[:seg[0].numel()].copy_(seg[0])
+                            t[seg[0].numel():].copy_(seg[1])
                         dist.all_reduce(t, group=self.pg)
             rc = fn(*args, stream)
             if rc:
@@ -213,7 +223,7 @@ class Engine(object):
         try:
             import torch.distributed._symmetric_memory as symm
             mail, off = [], 0
-            for _, _, _, nbytes, _ in pts:
+            for _, _, _, nbytes, _, _ in pts:
                 mail.append(off)
                 off += (self.world * nbytes + 255) // 256 * 256
             flag = [off + 512 * k for k in range(len(pts))]       # [world] uint64 per point, world <= 64

@@ -135,7 +135,7 @@ class Plan(object):
         self.tbuf = {}                   # Tensor -> Ptr
         self.conv_descs = {}
         self.bn_layers = []
-        self.allreduce_points = []       # (phase, launch index, Ptr, nbytes, dtype)
+        self.allreduce_points = []       # (phase, launch index, dst Ptr, nbytes, dtype, (src0, n0, src1, n1) | None = in place)
         self.temp = TempAllocator()
         self.temp_buf = Buf("temp", 0, "temp")
         self.bufs.append(self.temp_buf)
@@ -665,7 +665,7 @@ class Plan(object):
         if not node.attrs.get("stats_in_conv"):
             self.L("f", "mcn_bn_stats", self.ccode, self.tbuf[x], rows, c, Ptr(sums), tag=node.scope + "/stats")
         if self.sync_bn:
-            self.allreduce_points.append(("f", len(self.fwd), Ptr(sums), 2 * c * 8, "f64"))
+            self.allreduce_points.append(("f", len(self.fwd), Ptr(sums), 2 * c * 8, "f64", None))
         upd = node.attrs["update"]
         if os.environ.get("MCN_BN_FOLD_FINALIZE", "1") == "0":     # A/B switch: separate finalize launch
             self.L("f", "mcn_bn_finalize", Ptr(sums), float(rows * (self.world if self.sync_bn else 1)), c,
@@ -1082,10 +1082,11 @@ class Plan(object):
         g1, g2, gh = s1, s2, None
         count = float(rows)
         if self.sync_bn:
+            # global sums go to a scratch vector: the LOCAL sums stay in place as dbeta / dgamma
+            # (they are averaged over ranks with the other gradients).  The exchange gathers its
+            # two source segments itself (mcn_peer_allreduce src0/src1), no staging copies.
             gp, gh = self.talloc(2 * c * 4)
-            self.L("b", "mcn_cast", 0, s1, 0, gp, c, tag="syncbn_copy")
-            self.L("b", "mcn_cast", 0, s2, 0, gp + c * 4, c, tag="syncbn_copy")
-            self.allreduce_points.append(("b", len(self.bwd), gp, 2 * c * 4, "f32"))
+            self.allreduce_points.append(("b", len(self.bwd), gp, 2 * c * 4, "f32", (s1, c, s2, c)))
             g1, g2 = gp, gp + c * 4
             count = float(rows * self.world)
         need_x = self._tensor_needs_grad(x)

@@ -118,6 +118,14 @@ static std::vector<Case> cases() {
   c.push_back({"T wgrad 3x3 28x28 128->128 b64 halo", 2, 64, 28, 28, 128, 128, 3, 1, 1, 2, 1, 0, 0, 20});
   c.push_back({"T wgrad 3x3 28x28 128->128 b64 im2col", 2, 64, 28, 28, 128, 128, 3, 1, 1, 1, 1, 0, 0, 20});
   c.push_back({"T wgrad 3x3 14x14 256->256 b64 halo", 2, 64, 14, 14, 256, 256, 3, 1, 1, 2, 1, 0, 0, 20});
+  // weight-stationary mode of the GEMM kernel needs >= 2 tiles per SM: larger batches
+  c.push_back({"fprop 1x1 56x56 64->256 N16 (W stationary)", 0, 16, 56, 56, 64, 256, 1, 1, 1, 0, 1, 1, 0, 0});
+  c.push_back({"dgrad 1x1 56x56 256<-64 N16 (W stationary)", 1, 16, 56, 56, 256, 64, 1, 1, 1, 0, 1, 0, 0, 0});
+  c.push_back({"fprop 1x1 28x28 128->512 N64 (2 n-tiles)", 0, 64, 28, 28, 128, 512, 1, 1, 1, 0, 1, 0, 0, 0});
+  c.push_back({"T fprop 1x1 56x56 64->256 b64", 0, 64, 56, 56, 64, 256, 1, 1, 1, 0, 1, 0, 0, 20});
+  c.push_back({"T dgrad 1x1 56x56 256<-64 b64", 1, 64, 56, 56, 256, 64, 1, 1, 1, 0, 1, 0, 0, 20});
+  c.push_back({"T fprop 1x1 28x28 128->512 b64", 0, 64, 28, 28, 128, 512, 1, 1, 1, 0, 1, 0, 0, 20});
+  c.push_back({"T fprop 1x1 28x28 512->128 b64", 0, 64, 28, 28, 512, 128, 1, 1, 1, 0, 1, 0, 0, 20});
   return c;
 }
 
