@@ -179,6 +179,7 @@ def profile_step(eng):
     import torch
     from myconvnet_b200 import lib as L
     st = torch.cuda.current_stream().cuda_stream
+    torch.cuda.nvtx.range_push("mcn_profiled_step")      # ncu --nvtx --nvtx-include "mcn_profiled_step/"
     L.check(eng.lib.mcn_fill_f32(eng._zero_ptr, eng._zero_n, 0.0, st))
     recs = []
     for launches in (eng._fwd, eng._bwd):
@@ -189,6 +190,7 @@ def profile_step(eng):
             e1.record()
             recs.append((name, tag, args, e0, e1))
     torch.cuda.synchronize()
+    torch.cuda.nvtx.range_pop()
     esz = 2 if eng.plan.cdt == "bf16" else 4
     out = {}
     detail = []
@@ -356,8 +358,16 @@ def main():
     else:
         ach = cbytes / (cms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak}
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel class, from the
+        # committed ncu capture of the same command (scripts/ncu_profile.sh)
+        t = json.load(open(tpath)).get("classes", {}).get(cname)
+        if t:
+            traffic = t["dram_bytes_per_launch"]
     roof.update({"kernel": cname, "launches_per_step": cn, "share_of_step": cms / total_ms,
-                 "peak_source": peak_src, "traffic": None,
+                 "peak_source": peak_src, "traffic": traffic,
                  "note": "aggregate over the class's launches in one step; algorithmic bytes/flops per DESIGN.md"})
     table = {k: {"ms": v[0], "GB": v[1] / 1e9, "TFLOP": v[2] / 1e12, "launches": v[3],
                  "GB/s": (v[1] / 1e9) / (v[0] * 1e-3) if v[0] > 0 else 0,

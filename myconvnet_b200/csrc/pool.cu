@@ -115,15 +115,16 @@ __global__ void maxpool_bwd_vec_kernel(const T* __restrict__ dy, const int32_t* 
                                        int N, int H, int W, int C, int kh, int kw, int sh, int sw,
                                        int pad_t, int pad_l, int Ho, int Wo, T* __restrict__ dx) {
   const int cv = C / V;
-  const long long total = (long long)N * H * W * cv;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % cv) * V;
-    long long r = i / cv;
-    const int w = (int)(r % W);
-    r /= W;
-    const int h = (int)(r % H);
-    const int n = (int)(r / H);
+  // 32-bit index arithmetic (the host falls back to the scalar kernel beyond 2^31 vectors): the
+  // 64-bit divisions were a third of this kernel's instructions
+  const uint32_t total = (uint32_t)N * H * W * cv;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % (uint32_t)cv) * V;
+    uint32_t r = i / (uint32_t)cv;
+    const int w = (int)(r % (uint32_t)W);
+    r /= (uint32_t)W;
+    const int h = (int)(r % (uint32_t)H);
+    const int n = (int)(r / (uint32_t)H);
     const int self = (h * W + w) * C + c0;
     int p_lo = (h + pad_t - kh + 1 + sh - 1);
     p_lo = p_lo <= 0 ? 0 : p_lo / sh;
@@ -288,7 +289,8 @@ extern "C" int mcn_maxpool_bwd(int dtype, const void* dy, const int32_t* argmax,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MCN_DISPATCH_DTYPE(dtype, T, {
     constexpr int V = Vec16<T>::N;
-    if (C % V == 0) {
+    if (C % V == 0 && (long long)N * H * W * (C / V) < (1LL << 31) - (1 << 24) &&
+        (long long)N * Ho * Wo * C < (1LL << 62)) {
       long long total = (long long)N * H * W * (C / V);
       maxpool_bwd_vec_kernel<T, V><<<grid_for(total, 256), 256, 0, st>>>(
           static_cast<const T*>(dy), argmax, N, H, W, C, kh, kw, sh, sw, pad_t, pad_l, Ho, Wo,

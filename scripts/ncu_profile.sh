@@ -1,14 +1,17 @@
 #!/bin/bash
-# Round profile: (1) launch list of one eager bench step, (2) --set full on a handful of launches
-# of the heaviest kernels, exported to CSV on the box (the .ncu-rep itself is too large to bring
-# back).  Each ncu pass only after the identical plain command exited 0 (B200_PROFILING.md).
+# Round profile of one eager training step (the NVTX range "mcn_profiled_step" in bench.py):
+#  (1) launch list with duration and DRAM bytes of EVERY launch of the step,
+#  (2) --set full on the first launches of each heavy kernel, exported to CSV on the box.
+# Each ncu pass only after the identical plain command exited 0 (B200_PROFILING.md).
 mkdir -p gpurun_out/ncu
 CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph"
-$CMD > gpurun_out/ncu/plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -s 1830 -c 460 --csv \
-    --log-file gpurun_out/ncu/launches.csv $CMD > gpurun_out/ncu/ncu1.log 2>&1
-$CMD > gpurun_out/ncu/plain2.log 2>&1 &&
-ncu --set full --clock-control none -k regex:"wgrad_kernel|gemm_conv_kernel|bn_bwd_apply_kernel|bn_bwd_reduce_kernel|bn_apply_kernel|bn_stats_kernel" \
-    -s 1000 -c 14 -o /tmp/prof_full $CMD > gpurun_out/ncu/ncu2.log 2>&1
+$CMD > gpurun_out/ncu/plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/ncu/plain.log; exit 1; }
+ncu --nvtx --nvtx-include "mcn_profiled_step/" --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
+    --clock-control none -c 348 --csv --log-file gpurun_out/ncu/launches.csv $CMD > gpurun_out/ncu/ncu1.log 2>&1
+echo "launch list rc=$? lines=$(wc -l < gpurun_out/ncu/launches.csv)"
+ncu --nvtx --nvtx-include "mcn_profiled_step/" --set full --clock-control none \
+    -k regex:"gemm_conv_kernel|halo_conv_kernel|wgrad_halo_kernel|wgrad_kernel|stem_fprop_kernel|stem_wgrad_kernel|bn_bwd_apply_kernel|bn_bwd_reduce_kernel|bn_apply_runs_kernel|bn_apply_kernel" \
+    -s 4 -c 26 -o /tmp/prof_full $CMD > gpurun_out/ncu/ncu2.log 2>&1
+echo "full set rc=$?"
 ncu -i /tmp/prof_full.ncu-rep --page raw --csv > gpurun_out/ncu/full_raw.csv 2> gpurun_out/ncu/export.log
-ls -la /tmp/prof_full.ncu-rep gpurun_out/ncu/
+ls -la /tmp/prof_full.ncu-rep gpurun_out/ncu/ | tail -8
