@@ -4,10 +4,10 @@
 #  (2) --set full on the first launches of each heavy kernel, exported to CSV on the box.
 # Each ncu pass only after the identical plain command exited 0 (B200_PROFILING.md).
 mkdir -p gpurun_out/ncu
-CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph"
+CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph --stall-timeout 100000"
 $CMD > gpurun_out/ncu/plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/ncu/plain.log; exit 1; }
 ncu --nvtx --nvtx-include "mcn_profiled_step/" --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
-    --clock-control none -c 348 --csv --log-file gpurun_out/ncu/launches.csv $CMD > gpurun_out/ncu/ncu1.log 2>&1
+    --clock-control none -c 400 --csv --log-file gpurun_out/ncu/launches.csv $CMD > gpurun_out/ncu/ncu1.log 2>&1
 echo "launch list rc=$? lines=$(wc -l < gpurun_out/ncu/launches.csv)"
 ncu --nvtx --nvtx-include "mcn_profiled_step/" --set full --clock-control none \
     -k regex:"gemm_conv_kernel|halo_conv_kernel|wgrad_halo_kernel|wgrad_kernel|stem_fprop_kernel|stem_wgrad_kernel|bn_bwd_apply_kernel|bn_bwd_reduce_kernel|bn_apply_runs_kernel|bn_apply_kernel" \
