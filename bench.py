@@ -262,9 +262,9 @@ def main():
         import datetime
         # NVLS (in-switch multicast) needs a healthy fabric-manager/IMEX setup; the plain NVLink
         # ring/tree paths do not.  Opt in with MCN_NCCL_NVLS=1.
-        # NCCL_DEBUG=VERSION makes NCCL print its version banner on STDOUT, next to the JSON line
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL prints its version banner (NCCL_DEBUG >= VERSION) on STDOUT, next to the JSON line:
+        # send NCCL's own log to stderr instead
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         if os.environ.get("MCN_NCCL_NVLS", "0") != "1":
             os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
         import torch.distributed as dist
