@@ -99,7 +99,6 @@ class Engine(object):
         self.use_cuda_graph = use_cuda_graph
         self._inputs = {name: self.tensor_view(t) for name, t in self.graph.inputs.items()}
         self._pinned = {}
-        self._works = []
         self._bucket_ready = {}
         self._peer = None
         if self.world > 1:
@@ -196,22 +195,18 @@ class Engine(object):
                 check(rc, name + " [" + tag + "]")
             if i in ready:
                 # every gradient of these buckets is final: exchange them while backward continues
-                for s0, e0 in ready[i]:
-                    self._works.append(dist.all_reduce(self._flat_grads[s0:e0], op=dist.ReduceOp.SUM,
-                                                       group=self.pg, async_op=True))
+                self._buckets.after_launch(i)
 
     # ------------------------------------------------------------------ multi-GPU set-up
     def _setup_grad_buckets(self):
+        from .dist import BucketOverlap
         p = self.plan
         self._flat_grads = self.view(Ptr(p.b_grad), p.n_train, torch.float32)
-        self._bucket_ready = {}
-        self._bucket_tail = []
-        overlap = os.environ.get("MCN_OVERLAP_GRADS", "1") != "0"
-        for s0, e0, r in p.grad_bucket_schedule(int(self.kw.get("bucket_elems", 4 * 1024 * 1024))):
-            if overlap and r >= 0:
-                self._bucket_ready.setdefault(r, []).append((s0, e0))
-            else:
-                self._bucket_tail.append((s0, e0))
+        self._buckets = BucketOverlap(
+            self._flat_grads, p.grad_bucket_schedule(int(self.kw.get("bucket_elems", 4 * 1024 * 1024))),
+            group=self.pg, overlap=os.environ.get("MCN_OVERLAP_GRADS", "1") != "0")
+        self._bucket_ready = self._buckets.ready
+        self._bucket_tail = self._buckets.tail
 
     def _setup_peer_comm(self):
         """Symmetric-memory mailboxes for the synchronised-BN exchanges (mcn_peer_allreduce).  Falls
@@ -461,13 +456,7 @@ class Engine(object):
     def _allreduce_grads(self):
         """Buckets whose gradients were final early are already in flight (started from _run);
         start the rest and wait for all of them before the optimiser reads the buffer."""
-        import torch.distributed as dist
-        for s0, e0 in self._bucket_tail[::-1]:
-            self._works.append(dist.all_reduce(self._flat_grads[s0:e0], op=dist.ReduceOp.SUM,
-                                               group=self.pg, async_op=True))
-        for w in self._works:
-            w.wait()
-        self._works = []
+        self._buckets.finish()
 
     def train_step(self, X=None, Y=None, lr_multiplier=1.0, fetch_loss=True, update=True,
                    prefetched=False):

@@ -30,6 +30,28 @@ def _worker(rank, world, port, q):
     mean = st[:5] / cnt
     var = st[5:] / cnt - mean ** 2
     _, m_ref, v_ref = tf_ops.fused_batch_norm_train(torch.tensor(full), None, None, 1e-3)
+    # gradient buckets started DURING a (simulated) backward pass: slices become final in reverse
+    # order, each bucket's all-reduce starts right after the launch that completes it
+    from myconvnet_b200.dist import BucketOverlap
+    flat = torch.zeros(5000)
+    sched = [(0, 2048, 9), (2048, 4096, 5), (4096, 5000, 1)]          # (start, end, ready launch)
+    writes = {1: (4096, 5000), 3: (3000, 4096), 5: (2048, 3000), 7: (1000, 2048), 9: (0, 1000)}
+    started = []
+    for overlap in (True, False):
+        flat.zero_()
+        bo = BucketOverlap(flat, sched, overlap=overlap)
+        for launch in range(10):
+            if launch in writes:
+                a, b = writes[launch]
+                flat[a:b] = torch.arange(a, b, dtype=torch.float32) * (rank + 1)
+            before = len(bo.works)
+            bo.after_launch(launch)
+            started.append((overlap, launch, len(bo.works) - before))
+        nfin = bo.finish()
+        expect = torch.arange(5000, dtype=torch.float32) * sum(r + 1 for r in range(world))
+        assert torch.equal(flat, expect), "bucket overlap (overlap=%s) wrong sum" % overlap
+        assert nfin == 3 and bo.n_overlapped == (3 if overlap else 0)
+    assert [x for x in started if x[0] and x[2]] == [(True, 1, 1), (True, 5, 1), (True, 9, 1)]
     q.put((rank, mine.numpy(), g.numpy(), nb, float((mean - m_ref).abs().max()),
            float((var * cnt / (cnt - 1) - v_ref).abs().max()), bucket_ranges(n, 1024)[-1]))
     dist.destroy_process_group()
