@@ -106,6 +106,40 @@ def test_resnet50_fused_loss_curve(have_reference_models, dtype, tol):
     assert rel_l2(e_dev[k], tr.ema[k].numpy()) < 5 * tol
 
 
+def test_trainer_drives_the_engine_with_the_reference_schedule(have_reference_models):
+    """Step driver: Trainer feeds shuffled in-memory batches and the warm-up /
+    cosine multiplier of the reference loop (optimizers.py:608-632) to the device engine; the
+    oracle trainer stepped with the same batches and multipliers gives the same losses."""
+    from myconvnet_b200.trainer import Trainer
+    from oracle import schedule
+    from oracle.step import OracleTrainer
+    pm, om, vals = build_pair("models/resnet_v1_5.py", "ResNet50", SHAPE, NCLS, BATCH, "f32",
+                              base_learning_rate=0.05)
+    rng = np.random.default_rng(11)
+    n = 3 * BATCH + 3                                   # 4 steps per epoch, the 4th (partial) is skipped
+    X = rng.uniform(size=[n] + SHAPE).astype(np.float32)
+    Y = rng.integers(0, NCLS, size=n).astype(np.int32)
+    eng = _engine(pm, vals)
+    seen = []
+    orig = eng.train_step
+
+    def spy(Xb, Yb, lr_multiplier=1.0, fetch_loss=True):
+        seen.append((Xb.copy(), Yb.copy(), lr_multiplier))
+        return orig(Xb, Yb, lr_multiplier=lr_multiplier, fetch_loss=fetch_loss)
+    eng.train_step = spy
+    tr = Trainer(eng, n, num_epochs=2, seed=3, learning_warmup_epochs=0.5,
+                 learning_rate_decay_method="cosine", learning_rate_decay_params=(0,))
+    dev = tr.fit(X, Y, num_steps=5)
+    want = schedule.multipliers(n, BATCH, 2, 0.5, "cosine", (0,))
+    assert tr.steps_per_epoch == 4 and len(dev) == 4 and tr.curr_step == 5          # step 3 had no full batch
+    assert np.allclose([m for _, _, m in seen], [want[0], want[1], want[2], want[4]], rtol=1e-12)
+    ot = OracleTrainer(om, base_learning_rate=0.05)
+    ref = [ot.step(xb, yb, lr_multiplier=m) for xb, yb, m in seen]
+    for k, (a, b) in enumerate(zip(dev, ref)):
+        band = 5e-3 * (1 + k)
+        assert abs(a - b) <= band * abs(b) + band, (k, dev, ref)
+
+
 def test_predict_uses_ema_shadows_and_moving_statistics(have_reference_models):
     """ConvNet.predict semantics (reference convnet.py:609-665, 1406, 1872-1876): after a few
     training steps the inference pass runs on the EMA shadows with BN in inference mode."""
