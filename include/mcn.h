@@ -243,11 +243,16 @@ typedef struct {
   float wd;            /* decoupled weight decay factor (already scaled) */
 } mcn_opt_tensor;
 typedef enum { MCN_OPT_NESTEROV = 0, MCN_OPT_RMSPROP = 1, MCN_OPT_ADAM = 2 } mcn_opt_kind;
-/* table: device array of mcn_opt_tensor; hp (device, 8 floats): lr, momentum(beta1),
- * beta2/decay, eps, ema_decay_t, adam_lr_t, grad_scale, weight-decay multiplier — read on device
+/* table: device array of mcn_opt_tensor; hp (device, 9 floats): lr, momentum(beta1),
+ * beta2/decay, eps, ema_decay_t, adam_lr_t, grad_scale, weight-decay multiplier, clip threshold — read on device
  * so a captured CUDA graph can be replayed with new hyper-parameters. */
 int mcn_opt_step(int kind, const mcn_opt_tensor* table, int ntensors, long long max_n,
-                 const float* hp, float* l2_loss, void* stream);
+                 const float* hp, float* l2_loss, const float* grad_sqnorm, void* stream);
+/* Gradient clipping (tf.clip_by_global_norm, optimizers.py:112-113): out += sum over all trainable
+ * tensors of (g*hp[6] + l2*w)^2 (zero `out` first).  Passing it to mcn_opt_step as grad_sqnorm
+ * scales every gradient by hp[8] / max(sqrt(*grad_sqnorm), hp[8]); NULL = no clipping. */
+int mcn_grad_sqnorm(const mcn_opt_tensor* table, int ntensors, long long max_n, const float* hp,
+                    float* out, void* stream);
 /* out[t][c][r] += in[t][r][c]: gradient of a transposed-conv weight (stored [kh,kw,Cin,Cout],
  * reference convnet.py:2460-2462) from the wgrad of the underlying conv. */
 int mcn_transpose_add_f32(const float* in, int taps, int rows, int cols, float* out, void* stream);

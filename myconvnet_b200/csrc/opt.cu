@@ -13,16 +13,52 @@ namespace {
 constexpr int kItems = 8;
 constexpr int kBlock = 256;
 
+// Squared global norm of the full gradient (data term averaged over ranks + L2 term), the
+// quantity tf.clip_by_global_norm needs (reference optimizers.py:112-113).  Same grid as the step.
+__global__ void __launch_bounds__(kBlock)
+grad_sqnorm_kernel(const mcn_opt_tensor* __restrict__ table, const float* __restrict__ hp,
+                   float* __restrict__ out) {
+  const mcn_opt_tensor t = table[blockIdx.y];
+  const long long base = (long long)blockIdx.x * (kBlock * kItems);
+  if (base >= t.n || t.g == nullptr) return;
+  const float gscale = hp[6];
+  float acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) {
+    const long long i = base + k * kBlock + threadIdx.x;
+    if (i < t.n) {
+      const float g = t.g[i] * gscale + t.l2 * t.w[i];
+      acc = fmaf(g, g, acc);
+    }
+  }
+  __shared__ float part[kBlock / 32];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kBlock / 32; ++w) s += part[w];
+    if (s != 0.f) atomicAdd(out, s);
+  }
+}
+
 // hp: [0] lr  [1] momentum|beta1  [2] decay|beta2  [3] eps  [4] ema decay d_t
-//     [5] adam lr_t  [6] gradient scale  [7] weight-decay multiplier
+//     [5] adam lr_t  [6] gradient scale  [7] weight-decay multiplier  [8] clip threshold
 __global__ void __launch_bounds__(kBlock)
 opt_step_kernel(int kind, const mcn_opt_tensor* __restrict__ table, const float* __restrict__ hp,
-                float* __restrict__ l2_loss) {
+                float* __restrict__ l2_loss, const float* __restrict__ grad_sqnorm) {
   const mcn_opt_tensor t = table[blockIdx.y];
   const long long base = (long long)blockIdx.x * (kBlock * kItems);
   if (base >= t.n) return;
   const float lr = hp[0], mom = hp[1], b2 = hp[2], eps = hp[3], ema_d = hp[4], adam_lr = hp[5],
               gscale = hp[6], wd = t.wd * hp[7];
+  // tf.clip_by_global_norm: g * clip / max(global_norm, clip)
+  float clip = 1.f;
+  if (grad_sqnorm != nullptr) {
+    const float thr = hp[8];
+    clip = thr / fmaxf(sqrtf(*grad_sqnorm), thr);
+  }
   float l2_acc = 0.f;  // l2 * sum(w^2)/2 over the PRE-step weights (tf.nn.l2_loss, convnet.py:563)
 #pragma unroll
   for (int k = 0; k < kItems; ++k) {
@@ -35,7 +71,7 @@ opt_step_kernel(int kind, const mcn_opt_tensor* __restrict__ table, const float*
       t.ema[i] = s - (1.f - ema_d) * (s - w);
     }
     if (t.g != nullptr) {
-      float g = t.g[i] * gscale + t.l2 * w;
+      float g = (t.g[i] * gscale + t.l2 * w) * clip;
       if (kind == MCN_OPT_NESTEROV) {
         float a = mom * t.m[i] + g;
         t.m[i] = a;
@@ -123,13 +159,23 @@ __global__ void weight_prep_kernel(const float* __restrict__ w, int cin, int cou
 using namespace mcn;
 
 extern "C" int mcn_opt_step(int kind, const mcn_opt_tensor* table, int ntensors, long long max_n,
-                            const float* hp, float* l2_loss, void* stream) {
+                            const float* hp, float* l2_loss, const float* grad_sqnorm, void* stream) {
   MCN_REQUIRE(table && hp && ntensors > 0 && max_n > 0, "opt_step: bad argument");
   MCN_REQUIRE(kind >= MCN_OPT_NESTEROV && kind <= MCN_OPT_ADAM, "opt_step: unknown optimiser %d", kind);
   MCN_REQUIRE(ntensors <= 65535, "opt_step: too many tensors");
   dim3 grid((unsigned)((max_n + kBlock * kItems - 1) / (kBlock * kItems)), (unsigned)ntensors);
-  opt_step_kernel<<<grid, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(kind, table, hp, l2_loss);
+  opt_step_kernel<<<grid, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(kind, table, hp, l2_loss,
+                                                                         grad_sqnorm);
   return after_launch("opt_step");
+}
+
+extern "C" int mcn_grad_sqnorm(const mcn_opt_tensor* table, int ntensors, long long max_n,
+                               const float* hp, float* out, void* stream) {
+  MCN_REQUIRE(table && hp && out && ntensors > 0 && max_n > 0, "grad_sqnorm: bad argument");
+  MCN_REQUIRE(ntensors <= 65535, "grad_sqnorm: too many tensors");
+  dim3 grid((unsigned)((max_n + kBlock * kItems - 1) / (kBlock * kItems)), (unsigned)ntensors);
+  grad_sqnorm_kernel<<<grid, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(table, hp, out);
+  return after_launch("grad_sqnorm");
 }
 
 extern "C" int mcn_weight_prep(const float* w_hwio_f32, int taps, int cin, int cout,

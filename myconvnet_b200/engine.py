@@ -88,8 +88,10 @@ class Engine(object):
         self.wd_scheduling = bool(self.kw.get("weight_decay_scheduling", True))
         if self.kw.get("l1_weight_decay", False) or self.kw.get("huber_decay_delta", None) is not None:
             raise NotImplementedError("l1 / pseudo-Huber weight decay variants are not supported")
-        if self.kw.get("gradient_threshold", None) is not None:
-            raise NotImplementedError("gradient clipping is not supported yet")
+        # tf.clip_by_global_norm on the gradient of the full loss (optimizers.py:112-113); with
+        # several GPUs it is applied to the rank-averaged gradient (one tower at the global batch)
+        gt = self.kw.get("gradient_threshold", None)
+        self.grad_threshold = None if gt is None else float(gt)
         self.hp_host = torch.zeros(16, dtype=torch.float32).pin_memory()
         self.hp_dev = self.view(Ptr(p.b_hp), 16, torch.float32)
         self._build_opt_table()
@@ -375,6 +377,7 @@ class Engine(object):
         hp[4], hp[5] = d_t, adam_lr
         hp[6] = 1.0 / (self.world * self.plan.loss_scale)
         hp[7] = lr_multiplier if self.wd_scheduling else 1.0
+        hp[8] = self.grad_threshold if self.grad_threshold is not None else 0.0
         self.hp_dev.copy_(hp, non_blocking=True)
 
     def load_inputs(self, **arrays):
@@ -448,10 +451,15 @@ class Engine(object):
             self._allreduce_grads()
         if update:
             p = self.plan
+            gnorm = None
+            if self.grad_threshold is not None:
+                gnorm = self.addr(Ptr(p.b_gnorm))
+                _lib.check(self.lib.mcn_grad_sqnorm(self.opt_table.data_ptr(), self.opt_n, self.opt_max_n,
+                                                    self.addr(Ptr(p.b_hp)), gnorm, st), "grad_sqnorm")
             _lib.check(self.lib.mcn_opt_step(self.opt_kind, self.opt_table.data_ptr(), self.opt_n,
                                              self.opt_max_n, self.addr(Ptr(p.b_hp)),
                                              self.addr(p.loss_slots["l2"]) if "l2" in p.loss_slots else None,
-                                             st), "opt_step")
+                                             gnorm, st), "opt_step")
 
     def _allreduce_grads(self):
         """Buckets whose gradients were final early are already in flight (started from _run);

@@ -73,7 +73,8 @@ SIGNATURES = {
     "mcn_resize_bilinear_bwd": "ipiiiiiiip",
     "mcn_softmax_xent": "pplipffppp",
     "mcn_sigmoid_xent": "plfffppi",
-    "mcn_opt_step": "ipilpp",
+    "mcn_opt_step": "ipilppp",
+    "mcn_grad_sqnorm": "pilpp",
     "mcn_transpose_add_f32": "piiip",
     "mcn_peer_allreduce": "pllpipipipii",
     "mcn_fill_f32": "plf",

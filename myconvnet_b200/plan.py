@@ -198,6 +198,7 @@ class Plan(object):
         self.b_mom = self.new_buf("opt_m", max(self.n_train, 1) * 4, "state")
         self.b_v = self.new_buf("opt_v", max(self.n_train, 1) * 4, "state")
         self.b_hp = self.new_buf("hyper_params", 64, "state")
+        self.b_gnorm = self.new_buf("grad_sqnorm", 16, "zero")      # squared global gradient norm (clipping)
         # bf16 operand copies
         self.bf16_off = {}
         self.bf16t_off = {}

@@ -53,6 +53,13 @@ class OracleTrainer(object):
             train = [k for k, meta in m.var_meta.items() if meta["trainable"] and meta["kind"] != "stat"]
             grads = torch.autograd.grad(loss, [m.vars[k] for k in train], allow_unused=True)
         self.grads = {k: (g if g is not None else torch.zeros_like(m.vars[k])) for k, g in zip(train, grads)}
+        thr = self.kw.get("gradient_threshold", None)
+        if thr is not None:
+            # tf.clip_by_global_norm (optimizers.py:112-113): g * clip / max(global_norm, clip)
+            gn = torch.sqrt(sum((g.double() ** 2).sum() for g in self.grads.values()))
+            self.grad_norm = float(gn)
+            scale = float(thr) / max(float(gn), float(thr))
+            self.grads = {k: g * scale for k, g in self.grads.items()}
         if not update:
             return float(loss.detach())
         lr = self.base_lr * batch / 256.0 * lr_multiplier

@@ -140,6 +140,35 @@ def test_trainer_drives_the_engine_with_the_reference_schedule(have_reference_mo
         assert abs(a - b) <= band * abs(b) + band, (k, dev, ref)
 
 
+def test_gradient_clipping_matches_clip_by_global_norm(have_reference_models):
+    """gradient_threshold (optimizers.py:112-113, tf.clip_by_global_norm on the gradient of the full
+    loss incl. the L2 term): the device step (mcn_grad_sqnorm + clip factor inside mcn_opt_step)
+    moves the weights like the oracle's clipped step — and half as far as an unclipped one."""
+    from oracle.step import OracleTrainer
+    pm, om, vals = build_pair("models/resnet_v1_5.py", "ResNet50", SHAPE, NCLS, BATCH, "f32",
+                              base_learning_rate=0.05)
+    X, Y = synthetic_batch(BATCH, SHAPE, NCLS)
+    probe = OracleTrainer(om, base_learning_rate=0.05, gradient_threshold=1e12)
+    probe.step(X, Y, update=False)
+    thr = 0.5 * probe.grad_norm                          # the clip halves every gradient
+    assert thr > 0
+    key = "block_2/res_1/conv_1/weights"
+    w0 = vals[key].astype(np.float64)
+    deltas = {}
+    for name, t in (("clipped", thr), ("free", None)):
+        eng = _engine(pm, vals, gradient_threshold=t)
+        eng.train_step(X, Y)
+        deltas[name] = eng.get_variables()[key].astype(np.float64) - w0
+    om.set_variables(vals)
+    ot = OracleTrainer(om, base_learning_rate=0.05, gradient_threshold=thr)
+    ot.step(X, Y)
+    d_ref = om.vars[key].detach().numpy().astype(np.float64) - w0
+    assert rel_l2(deltas["clipped"], d_ref) < 0.1                  # ReLU-kink floor of model-level gradients
+    ratio = np.linalg.norm(deltas["clipped"]) / np.linalg.norm(deltas["free"])
+    assert 0.49 < ratio < 0.51, ratio
+    assert abs(np.linalg.norm(deltas["clipped"]) / np.linalg.norm(d_ref) - 1.0) < 0.02
+
+
 def test_predict_uses_ema_shadows_and_moving_statistics(have_reference_models):
     """ConvNet.predict semantics (reference convnet.py:609-665, 1406, 1872-1876): after a few
     training steps the inference pass runs on the EMA shadows with BN in inference mode."""
