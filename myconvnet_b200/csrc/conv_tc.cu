@@ -161,7 +161,9 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t tmem_ac
                                               bool valid, long long off, int n_t,
                                               uint64_t* tmem_full_bar, uint32_t tph,
                                               uint64_t* tmem_empty_bar, uint32_t* stat_stage,
-                                              float* stat_acc) {
+                                              float* stat_acc, int chunk_first = 0, int chunk_step = 64) {
+  // chunk_first / chunk_step: with two epilogue warps per TMEM lane quadrant (MCN_EPI_WARPS=8) the
+  // pair splits the 64-channel chunks of a tile between them (first = 0 or 64, step = 128).
       // bf16 accumulate (dx += dgrad): the previous values of a 64-channel chunk are fetched
   // with four back-to-back 32-byte loads one chunk AHEAD (the first one before the
   // accumulator is even ready), so the global-load latency hides behind the MMAs.
@@ -176,10 +178,16 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t tmem_ac
         ptx::ld_global_v8(obase + col0 + j * 16, *reinterpret_cast<uint32_t(*)[8]>(&old[j * 8]));
     }
   };
-  if (acc_bf16) prefetch_old(0);
+  if (acc_bf16 && chunk_first < e.block_n) prefetch_old(chunk_first);
   ptx::mbar_wait(tmem_full_bar, tph);
   ptx::tc_fence_after();
-  for (int c0 = 0; c0 < e.block_n; c0 += 64) {
+  if (chunk_first >= e.block_n) {
+    // nothing to drain for this warp (narrow tile): it still takes part in the hand-back count
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(tmem_empty_bar);
+    return;
+  }
+  for (int c0 = chunk_first; c0 < e.block_n; c0 += chunk_step) {
     uint32_t r[64];
     const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quad * 32) << 16) +
                            static_cast<uint32_t>(c0);
@@ -188,7 +196,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t tmem_ac
       ptx::tmem_ld_32x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
       ptx::tmem_ld_wait();
     }
-    if (c0 + 64 >= e.block_n) {
+    if (c0 + chunk_step >= e.block_n) {
       // last read of this accumulator: hand the TMEM buffer back before the stores drain
       ptx::tc_fence_before();
       __syncwarp();
@@ -242,7 +250,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t tmem_ac
           __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
           v[i] = *reinterpret_cast<uint32_t*>(&h);
         }
-        if (acc_bf16 && c0 + 64 < e.block_n) prefetch_old(c0 + 64);
+        if (acc_bf16 && c0 + chunk_step < e.block_n) prefetch_old(c0 + chunk_step);
         if (do_store) {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -306,7 +314,8 @@ struct GemmConvArgs {
 // ring and its phases run across tile boundaries, so the producer prefetches the next tile while
 // the MMA warp finishes the current one; the accumulator is double-buffered in TMEM so the
 // epilogue of tile i overlaps the MMAs of tile i+1.
-__global__ void __launch_bounds__(192, 1)
+template <int kEpiWarps>
+__global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1)
 gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
@@ -341,7 +350,7 @@ gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&tmem_full[b], 1);
-      ptx::mbar_init(&tmem_empty[b], 4);   // one arrival per epilogue warp
+      ptx::mbar_init(&tmem_empty[b], (blockDim.x >> 5) - 2);   // one arrival per epilogue warp (4 or 8)
     }
     ptx::mbar_init(bstat_bar, 1);
     ptx::fence_barrier_init();
@@ -437,6 +446,10 @@ gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
     // full 128-byte line written with four 32-byte stores (fp32 output: eight).
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;
+    // 8 epilogue warps (never together with fused statistics): warps w and w+4 share a quadrant
+    // and take alternate 64-channel chunks
+    const int epi_pairs = ((blockDim.x >> 5) - 2) >> 2;            // 1 or 2
+    const int chunk_first = ((warp - 2) >> 2) * 64, chunk_step = 64 * epi_pairs;
     uint32_t* stat_stage = reinterpret_cast<uint32_t*>(tail + kBarRegionBytes);
     float* stat_acc_all = reinterpret_cast<float*>(stat_stage + kStatStageWords);
     float* stat_acc = stat_acc_all + quad * kStatAccWarp;
@@ -461,7 +474,8 @@ gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
       const bool valid = row_coords(args.g, tile, row, n, p, q);
       const long long off = valid ? (n * args.out_sn + p * args.out_sh + q * args.out_sw) : 0;
       epilogue_tile(args.e, tmem_base + static_cast<uint32_t>(buf * args.e.block_n), quad, lane, valid,
-                    off, n_t, &tmem_full[buf], tph, &tmem_empty[buf], stat_stage, stat_acc);
+                    off, n_t, &tmem_full[buf], tph, &tmem_empty[buf], stat_stage, stat_acc, chunk_first,
+                    chunk_step);
     }
     if (stats && cur_nt >= 0) stats_flush(args.e, stat_acc_all, cur_nt, row);
   }
@@ -1520,15 +1534,29 @@ int launch_gemm_conv(GemmConvArgs& a, int tiles_m, cudaStream_t st) {
                 kBarRegionBytes + (a.e.stats ? kEpiStageBytes + kStatAccBytes : 0) + 1024;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(gemm_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(gemm_conv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             smem_optin_limit()) != cudaSuccess ||
+        cudaFuncSetAttribute(gemm_conv_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              smem_optin_limit()) != cudaSuccess) {
       set_error("cudaFuncSetAttribute(gemm_conv_kernel) failed");
       return MCN_ECUDA;
     }
     configured = true;
   }
+  // MCN_EPI_WARPS=8 (experimental, default 4): two epilogue warps per TMEM quadrant for tiles of at
+  // least two 64-channel chunks — the store-heavy 1x1 convolutions are bound by the epilogue warps'
+  // instruction issue (profiles/r01_epilogue_knockout.txt).  Not combined with fused statistics.
+  static int epi_warps = 0;
+  if (!epi_warps) {
+    const char* e = getenv("MCN_EPI_WARPS");
+    epi_warps = (e && atoi(e) == 8) ? 8 : 4;
+  }
+  const int threads = (epi_warps == 8 && a.e.stats == nullptr && a.block_n >= 128) ? 320 : 192;
   dim3 grid(static_cast<unsigned>(grid_n));
-  gemm_conv_kernel<<<grid, 192, smem, st>>>(a);
+  if (threads == 320)
+    gemm_conv_kernel<8><<<grid, 320, smem, st>>>(a);
+  else
+    gemm_conv_kernel<4><<<grid, 192, smem, st>>>(a);
   return after_launch("gemm_conv_kernel");
 }
 
