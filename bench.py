@@ -78,7 +78,6 @@ def cpu_reference_step_rate(steps, warmup, batch=32):
     the host cores.  Returns (img/s, seconds per step, threads)."""
     import numpy as np
     import torch
-    from myconvnet_b200 import convnet as pconv
     from myconvnet_b200 import loader
     from myconvnet_b200.engine import draw_initial_value
     from myconvnet_b200.zoo import resnet50
@@ -91,7 +90,6 @@ def cpu_reference_step_rate(steps, warmup, batch=32):
     if loader.reference_root() is not None:
         om = loader.load_reference_model("models/resnet_v1_5.py", {"convnet": ref_convnet}).ResNet50(IMG, NCLS)
     else:
-        import types
         from myconvnet_b200 import zoo
         om = type("OracleResNet50", (ref_convnet.ConvNet,),
                   {"_build_model": zoo.ResNet50._build_model, "_bottleneck": zoo.ResNet50._bottleneck,
@@ -134,7 +132,6 @@ def run_reference(args):
 # ------------------------------------------------------------------ roofline helpers
 def launch_work(name, args, esz):
     """Algorithmic (bytes, flops) of one libmcn launch from its resolved argument tuple."""
-    import ctypes
     if name in ("mcn_conv2d_fprop_tc", "mcn_conv2d_fprop_tc_stats", "mcn_conv2d_dgrad_tc",
                 "mcn_conv2d_wgrad_tc"):
         d = args[0]._obj

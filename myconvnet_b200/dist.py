@@ -5,7 +5,6 @@ on the parameter device) and its tower-after-tower BN moving-statistics chain
 (convnet.py:1898-1914).  One process per GPU; NCCL over NVLink on the device, gloo in CPU tests.
 The flat gradient buffer mirrors the parameter layout, so a bucket is a slice — no packing copy.
 """
-import torch
 import torch.distributed as dist
 
 
