@@ -328,6 +328,25 @@ class Engine(object):
         buf = p.b_ema if ema else p.b_param
         return {v.name: self._from_storage(v, self._var_view(buf, v).cpu().numpy()) for v in p.all_vars}
 
+    def save_checkpoint(self, path, naming="reference"):
+        """Variables and EMA shadows under the reference's names (checkpoint.py); .npz."""
+        from . import checkpoint
+        checkpoint.save_npz(path, self.get_variables(), self.get_variables(ema=True), naming=naming)
+
+    def load_checkpoint(self, path, naming="reference", prefer_ema=False):
+        """Loads what matches by name and shape; returns the names that were not found.  The EMA
+        shadows restart from the loaded values unless the file carries its own."""
+        from . import checkpoint
+        expected = {v.name: v.shape for v in self.plan.all_vars}
+        var, ema = checkpoint.load_npz(path, expected=expected, naming=naming, prefer_ema=prefer_ema)
+        self.set_variables(var, reset_state=True)
+        p = self.plan
+        for v in p.all_vars:
+            if v.name in ema:
+                arr = torch.from_numpy(self._to_storage(v, ema[v.name]).reshape(-1)).to(self.device)
+                self._var_view(p.b_ema, v).copy_(arr)
+        return sorted(set(expected) - set(var))
+
     def get_gradients(self):
         p = self.plan
         return {v.name: self._from_storage(v, self._var_view(p.b_grad, v).cpu().numpy())
