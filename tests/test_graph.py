@@ -196,3 +196,34 @@ def test_inference_plan_uses_ema_and_moving_statistics(r50):
     ema_ptrs = [a for l in p.inf for a in l.args if hasattr(a, "buf") and a.buf in (p.b_ema, p.b_bf16_ema)]
     raw_ptrs = [a for l in p.inf for a in l.args if hasattr(a, "buf") and a.buf in (p.b_param, p.b_bf16)]
     assert ema_ptrs and not raw_ptrs
+
+
+def test_every_launch_pointer_lies_inside_its_buffer(r50):
+    """Structural check of the planned launch lists (train, backward, inference): every pointer
+    argument addresses a byte inside the buffer it names, buffers of the arena do not overlap, and
+    every fused-statistics conv writes into the sums buffer of the BN that reads it."""
+    from myconvnet_b200.plan import Ptr
+    for world in (1, 8):
+        p = Plan(r50.graph, world_size=world)
+        for l in p.fwd + p.bwd + p.inf:
+            for a in l.args:
+                if isinstance(a, Ptr):
+                    assert 0 <= a.off < max(a.buf.nbytes, 1), (l.fn, l.tag, a.buf.name, a.off, a.buf.nbytes)
+                    assert a.buf.offset is not None and a.buf.offset % 256 == 0
+        spans = sorted((b.offset, b.offset + b.nbytes, b.name) for b in p.bufs if b.nbytes > 0)
+        assert all(spans[i][1] <= spans[i + 1][0] for i in range(len(spans) - 1))
+        sums_of_apply = {}
+        for l in p.fwd:
+            if l.fn == "mcn_bn_apply_stats":
+                sums_of_apply[l.tag.rsplit("/bn/", 1)[0]] = l.args[4].buf
+        fused = [l for l in p.fwd if l.fn in ("mcn_conv2d_fprop_tc_stats", "mcn_stem_conv_fprop")]
+        assert len(fused) == 36
+        for l in fused:
+            sums = l.args[6] if l.fn == "mcn_conv2d_fprop_tc_stats" else l.args[5]
+            assert sums.buf is sums_of_apply[l.tag] and sums.buf.region == "zero"
+        # synchronised BN: one exchange before every apply and one before every backward apply
+        if world > 1:
+            for phase, idx, ptr, nbytes, dt, srcs in p.allreduce_points:
+                nxt = (p.fwd if phase == "f" else p.bwd)[idx]
+                assert nxt.fn == ("mcn_bn_apply_stats" if phase == "f" else "mcn_bn_bwd_apply"), nxt.fn
+                assert any(isinstance(a, Ptr) and a.buf is ptr.buf and a.off == ptr.off for a in nxt.args)
