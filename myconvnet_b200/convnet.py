@@ -541,7 +541,9 @@ class ConvNet(object):
                 node.vars['beta'] = beta
         return node.outputs[0]
 
-    def group_norm(self, *args, **kwargs):
+    def group_norm(self, x, num_groups=32, scale=True, shift=True, zero_scale_init=False, epsilon=1e-3,
+                   scope='gn'):
+        # signature of reference convnet.py:1928; the kernels are a "next" row
         raise NotImplementedError('group_norm is not supported yet (SURVEY 8f-3)')
 
     # ------------------------------------------------------------------ resize
