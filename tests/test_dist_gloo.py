@@ -52,6 +52,63 @@ def _worker(rank, world, port, q):
         assert torch.equal(flat, expect), "bucket overlap (overlap=%s) wrong sum" % overlap
         assert nfin == 3 and bo.n_overlapped == (3 if overlap else 0)
     assert [x for x in started if x[0] and x[2]] == [(True, 1, 1), (True, 5, 1), (True, 9, 1)]
+    # the ENGINE's own multi-GPU glue (Engine._setup_grad_buckets / _run / _allreduce_grads) driven
+    # over a real plan with no-op launches: every trainable gradient ends up summed over the ranks
+    from myconvnet_b200.engine import Engine
+    from myconvnet_b200.plan import Plan
+    from myconvnet_b200.zoo import ResNet50
+    pm = ResNet50([32, 32, 3], 10, batch_size=2, compute_dtype="bf16")
+
+    class FakeEngine(object):
+        pass
+    fe = FakeEngine()
+    fe.plan = Plan(pm.graph, world_size=world)
+    fe.kw, fe.pg, fe.world, fe.rank = {"bucket_elems": 1 << 20}, None, world, rank
+    flat_store = torch.full((fe.plan.n_train,), float(rank + 1))
+    fe.view = lambda ptr, n, dt: flat_store[:n]
+    fe._ar, fe._peer = {"f": {}, "b": {}}, None
+    Engine._setup_grad_buckets(fe)
+    assert len(fe._bucket_ready) >= 3 and not fe._bucket_tail
+    launches = [((lambda *a: 0), (), l.fn, l.tag) for l in fe.plan.bwd]
+    Engine._run(fe, launches, "b", None)
+    assert len(fe._buckets.works) == sum(len(v) for v in fe._bucket_ready.values())
+    Engine._allreduce_grads(fe)
+    assert torch.equal(flat_store, torch.full_like(flat_store, float(sum(r + 1 for r in range(world)))))
+    # synchronised-BN exchange points through the same _run loop, NCCL/gloo fallback branch (no peer
+    # mapping on CPU): forward sums in place, backward gathers its two source segments first
+    store = {}
+
+    def view(ptr, count, dt):
+        key = (id(ptr.buf), ptr.off, count, dt)
+        if key not in store:
+            store[key] = torch.full((count,), float(rank + 1), dtype=dt)
+        return store[key]
+    fe.view = view
+    fe._ar = {"f": {}, "b": {}}
+    for k, (phase, idx, ptr, nbytes, dt, srcs) in enumerate(fe.plan.allreduce_points):
+        tdt = torch.float64 if dt == "f64" else torch.float32
+        cnt_k = nbytes // (8 if dt == "f64" else 4)
+        seg = None if srcs is None else (view(srcs[0], srcs[1], tdt), view(srcs[2], srcs[3], tdt))
+        if seg is not None:
+            seg[1].mul_(10.0)                     # make the two segments distinguishable
+        fe._ar[phase].setdefault(idx, []).append((view(ptr, cnt_k, tdt), k, seg))
+    fe._bucket_ready = {}
+    Engine._run(fe, [((lambda *a: 0), (), l.fn, l.tag) for l in fe.plan.fwd], "f", None)
+    Engine._run(fe, [((lambda *a: 0), (), l.fn, l.tag) for l in fe.plan.bwd], "b", None)
+    tot = float(sum(r + 1 for r in range(world)))
+    n_f = n_b = 0
+    for phase in ("f", "b"):
+        for lst in fe._ar[phase].values():
+            for t, k, seg in lst:
+                if seg is None:
+                    assert torch.equal(t, torch.full_like(t, tot))
+                    n_f += 1
+                else:
+                    c = seg[0].numel()
+                    assert torch.equal(t[:c], torch.full_like(t[:c], tot))
+                    assert torch.equal(t[c:], torch.full_like(t[c:], 10.0 * tot))
+                    n_b += 1
+    assert n_f == 53 and n_b == 53
     q.put((rank, mine.numpy(), g.numpy(), nb, float((mean - m_ref).abs().max()),
            float((var * cnt / (cnt - 1) - v_ref).abs().max()), bucket_ranges(n, 1024)[-1]))
     dist.destroy_process_group()
