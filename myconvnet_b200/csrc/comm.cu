@@ -1,8 +1,8 @@
 // One-shot all-reduce of small vectors over peer-mapped device memory (NVLink / NVSwitch).
 //
 // Synchronised batch-norm exchanges 2*C numbers per layer and direction (106 exchanges in a
-// ResNet-50 step) on the critical path of the step; an NCCL all-reduce costs ~25-30 us each
-// (launch + its own cross-GPU handshake), i.e. ~3 ms of a 26 ms step at 8 GPUs.  Here every rank
+// ResNet-50 step) on the critical path of the step; with one ncclAllReduce each, 8 GPUs ran at
+// 30.8 ms per step against 27.3 ms on one GPU at the start of round 1.  Here every rank
 // WRITES its vector straight into a mailbox slot in every peer's memory, raises a flag there, waits
 // for the flags of all peers in its own memory and sums the mailbox in rank order (so all ranks
 // get bit-identical results).  One tiny kernel, no library call, capturable in a CUDA graph.
