@@ -53,6 +53,25 @@ int mcn_version(void);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 long long mcn_launch_count(void);
 
+/* ---- determinism: workspace and exact accumulators --------------------------------------
+ * No entry point of this library uses floating-point atomics: every cross-block reduction is
+ * either summed in a fixed order (split-K slices of the wgrad kernels) or accumulated in an
+ * EXACT fixed-point accumulator ("xsum": three int64 limbs per sum, limb k of element i of an
+ * n-element array at limbs[k*n + i]; value = l0*2^-80 + l1*2^-40 + l2), so two runs of the same
+ * call give bit-identical results (the reference's TF ops are deterministic per tower).
+ * The reductions need scratch memory: ONE device buffer per device, registered here, zero-filled
+ * by the caller before the first use (every launch leaves it zeroed again).  Launches that share
+ * it must be stream-ordered, as with a cuBLAS handle.  Calls that need it fail with MCN_EINVAL
+ * when none is registered.  Size: mcn_workspace_min_bytes() plus, for the tensor-core / direct
+ * wgrad kernels, one fp32 dw-sized slice per split (mcn_conv2d_wgrad_workspace_bytes gives the
+ * preferred size for one convolution; less means fewer splits, never a different result class). */
+int mcn_set_workspace(void* device_ptr, long long bytes);
+long long mcn_workspace_min_bytes(void);
+long long mcn_conv2d_wgrad_workspace_bytes(const mcn_conv_desc* d, int a_mode, int stem);
+/* xsum limbs [3][n] -> out_f32[n] and/or out_f64[n] (either may be NULL); accumulate != 0 adds. */
+int mcn_xsum_decode(const long long* limbs, int n, float* out_f32, double* out_f64,
+                    int accumulate, void* stream);
+
 /* ---- dense convolution, tensor-core path (tcgen05/TMEM + TMA), bf16 in / fp32 accumulate.
  * Replaces tf.nn.conv2d (convnet.py:1659), its autodiff Conv2DBackpropInput/Filter,
  * tf.nn.conv2d_transpose (convnet.py:2463, = dgrad) and tf.matmul (convnet.py:1743,1755; a
@@ -217,12 +236,13 @@ int mcn_resize_bilinear_bwd(int dtype, const void* dy, int N, int H, int W, int 
 /* ---- losses (convnet.py:594-600, gan.py:134-138) ----
  * softmax cross-entropy on fp32 logits [rows][C] with int32 labels (-1 = all-zero one-hot row,
  * convnet.py:448-449).  loss_sum accumulates sum_rows w*valid*CE; dlogits = grad_scale *
- * w*valid*(softmax - smoothed_onehot).  probs may be NULL. */
+ * w*valid*(softmax - smoothed_onehot).  probs may be NULL.  loss_xs: one xsum accumulator
+ * (3 int64, zero first; decode on the host or with mcn_xsum_decode). */
 int mcn_softmax_xent(const float* logits, const int32_t* labels, long long rows, int C,
                      const float* class_w, float label_smoothing, float grad_scale,
-                     float* loss_sum, float* dlogits, float* probs, void* stream);
+                     long long* loss_xs, float* dlogits, float* probs, void* stream);
 int mcn_sigmoid_xent(const float* logits, long long n, float label, float weight, float grad_scale,
-                     float* loss_sum, float* dlogits, int accumulate_grad, void* stream);
+                     long long* loss_xs, float* dlogits, int accumulate_grad, void* stream);
 
 /* ---- optimiser: fused multi-tensor update (optimizers.py:149-176, 668-705; EMA
  * convnet.py:183-184,1401; L2 term convnet.py:563).  One launch updates every tensor in the
@@ -247,12 +267,14 @@ typedef enum { MCN_OPT_NESTEROV = 0, MCN_OPT_RMSPROP = 1, MCN_OPT_ADAM = 2 } mcn
  * beta2/decay, eps, ema_decay_t, adam_lr_t, grad_scale, weight-decay multiplier, clip threshold — read on device
  * so a captured CUDA graph can be replayed with new hyper-parameters. */
 int mcn_opt_step(int kind, const mcn_opt_tensor* table, int ntensors, long long max_n,
-                 const float* hp, float* l2_loss, const float* grad_sqnorm, void* stream);
-/* Gradient clipping (tf.clip_by_global_norm, optimizers.py:112-113): out += sum over all trainable
- * tensors of (g*hp[6] + l2*w)^2 (zero `out` first).  Passing it to mcn_opt_step as grad_sqnorm
- * scales every gradient by hp[8] / max(sqrt(*grad_sqnorm), hp[8]); NULL = no clipping. */
+                 const float* hp, long long* l2_loss_xs, const long long* grad_sqnorm_xs,
+                 void* stream);
+/* Gradient clipping (tf.clip_by_global_norm, optimizers.py:112-113): out_xs (one xsum accumulator,
+ * zero first) += sum over all trainable tensors of (g*hp[6] + l2*w)^2.  Passing it to mcn_opt_step
+ * as grad_sqnorm_xs scales every gradient by hp[8] / max(sqrt(sum), hp[8]); NULL = no clipping.
+ * l2_loss_xs (may be NULL): xsum accumulator receiving sum_t l2_t * |w_t|^2 / 2 (pre-step). */
 int mcn_grad_sqnorm(const mcn_opt_tensor* table, int ntensors, long long max_n, const float* hp,
-                    float* out, void* stream);
+                    long long* out_xs, void* stream);
 /* out[t][c][r] += in[t][r][c]: gradient of a transposed-conv weight (stored [kh,kw,Cin,Cout],
  * reference convnet.py:2460-2462) from the wgrad of the underlying conv. */
 int mcn_transpose_add_f32(const float* in, int taps, int rows, int cols, float* out, void* stream);

@@ -76,15 +76,28 @@ def split(flat):
     return var, ema
 
 
-def save_npz(path, variables, ema=None, naming="reference", depth=50):
+EXTRA_PREFIX = "__state__/"      # optimiser slots, global_step: kept apart from the variables
+
+
+def save_npz(path, variables, ema=None, naming="reference", depth=50, extra=None):
     """naming='reference' keeps the reference's names; 'slim' writes the TF-slim ResNet-v1 keys
-    (variables without a slim counterpart are kept under their own name)."""
+    (variables without a slim counterpart are kept under their own name).  `extra`: optimiser
+    slots (`<var>/Momentum`, ...), `global_step` — what tf.train.Saver would also have saved."""
     flat = flatten(variables, ema)
     if naming == "slim":
         flat = {(slim_resnet_v1_name(k, depth) or k): v for k, v in flat.items()}
     elif naming != "reference":
         raise ValueError("naming must be 'reference' or 'slim'")
+    for k, v in (extra or {}).items():
+        flat[EXTRA_PREFIX + k] = np.asarray(v)
     np.savez(path, **{k.replace("/", "|"): v for k, v in flat.items()})    # '/' is not a valid zip member name on every OS
+
+
+def load_extra(path):
+    """The `extra` dict of save_npz ({} for files without one)."""
+    with np.load(path) as z:
+        return {k.replace("|", "/")[len(EXTRA_PREFIX):]: z[k] for k in z.files
+                if k.replace("|", "/").startswith(EXTRA_PREFIX)}
 
 
 def load_npz(path, expected=None, naming="reference", depth=50, prefer_ema=False):
@@ -95,6 +108,7 @@ def load_npz(path, expected=None, naming="reference", depth=50, prefer_ema=False
     (load_moving_average=True there)."""
     with np.load(path) as z:
         flat = {k.replace("|", "/"): z[k] for k in z.files}
+    flat = {k: v for k, v in flat.items() if not k.startswith(EXTRA_PREFIX)}
     if expected is None:
         return split(flat)
     var, ema = {}, {}

@@ -6,11 +6,13 @@
 // Access pattern: the tensor is walked as a flat array of 16-byte vectors.  The launch makes the
 // total thread count a multiple of (C / vector width), so a thread always lands on the same
 // channel group: its per-channel constants live in registers and every warp reads contiguous
-// 512-byte segments.  Reductions go thread partial (fp32, a few rows) -> shared-memory atomics
-// -> one global atomic per channel per block (fp64 for the forward statistics).
+// 512-byte segments.  Reductions go thread partial (fp32, a few rows) -> shared memory -> one
+// add per channel per block into the exact fixed-point accumulator of xsum.cuh (order-
+// independent, so the step is bit-reproducible); the last block decodes it into the output.
 #include <cstdlib>
 
 #include "mcn_common.cuh"
+#include "xsum.cuh"
 
 namespace mcn {
 namespace {
@@ -86,10 +88,32 @@ bool plan_slab(long long rows, int C, SlabLaunch* L, int blocks_total) {
   return true;
 }
 
+// Last block of a channel group (ticket counter per group): limbs [3][2C] -> out1[c] += sum 0,
+// out2[c] += sum 1 for the group's channels [c0, c1), limbs and counter cleared for the next
+// launch.  All limb loads are issued before anything is consumed (one L2 round trip).
+template <typename TAcc>
+__device__ __forceinline__ void xs_decode_pair(const XsScratch& xsc, int group, int C, int c0, int c1,
+                                               TAcc* __restrict__ out1, TAcc* __restrict__ out2) {
+  const int nthreads = blockDim.x * blockDim.y;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int w = c1 - c0;
+  for (int i = tid; i < 2 * w; i += nthreads) {
+    const int which = i >= w ? 1 : 0;
+    const int c = c0 + i - which * w;
+    TAcc* o = which ? out2 + c : out1 + c;
+    const TAcc prev = *o;
+    const double v = xs::read_clear(xsc.limbs, 2 * C, which * C + c);
+    *o = static_cast<TAcc>(static_cast<double>(prev) + v);
+  }
+  if (tid == 0) xs::release(xsc.counter + group);
+}
+
 // Block-level finish shared by the reduction kernels: sh holds [2][rowlanes][slab_v*V] partials.
+// Only the blocks of one slab (blockIdx.x) add into the same channels, so the ticket is per slab:
+// the last block of a slab decodes just that slab's channels — no grid-wide serial tail.
 template <int V, typename TAcc>
 __device__ __forceinline__ void slab_finish(float* sh, int slab_v, int rowlanes, int slab, int C,
-                                            TAcc* out1, TAcc* out2) {
+                                            TAcc* out1, TAcc* out2, const XsScratch& xsc) {
   __syncthreads();
   const int width = slab_v * V;
   for (int t = threadIdx.x; t < 2 * width; t += blockDim.x) {
@@ -98,14 +122,16 @@ __device__ __forceinline__ void slab_finish(float* sh, int slab_v, int rowlanes,
     float acc = 0.f;
     for (int r = 0; r < rowlanes; ++r) acc += src[(size_t)r * width];
     const int c = slab * width + e;
-    if (c < C) atomicAdd((which ? out2 : out1) + c, (TAcc)acc);
+    if (c < C) xs::add(xsc.limbs, 2 * C, which * C + c, acc);
   }
+  if (xs::block_is_last(xsc.counter + slab, gridDim.y))
+    xs_decode_pair<TAcc>(xsc, slab, C, slab * width, min(C, (slab + 1) * width), out1, out2);
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256)
 bn_stats_kernel(const T* __restrict__ x, long long rows, int C, int slab_v, int rowlanes,
-                double* __restrict__ sums) {
+                double* __restrict__ sums, XsScratch xsc) {
   constexpr int V = Vec16<T>::N;
   extern __shared__ float sh[];
   const int sv = threadIdx.x % slab_v, rl = threadIdx.x / slab_v;
@@ -149,24 +175,28 @@ bn_stats_kernel(const T* __restrict__ x, long long rows, int C, int slab_v, int 
       sh[(size_t)(rowlanes + rl) * width + sv * V + i] = s2[i];
     }
   }
-  slab_finish<V, double>(sh, slab_v, rowlanes, blockIdx.x, C, sums, sums + C);
+  slab_finish<V, double>(sh, slab_v, rowlanes, blockIdx.x, C, sums, sums + C, xsc);
 }
 
 // scalar fallback (C not a multiple of the vector width)
 template <typename T>
 __global__ void bn_stats_scalar_kernel(const T* __restrict__ x, long long rows, int C,
-                                       double* __restrict__ sums) {
+                                       double* __restrict__ sums, XsScratch xsc) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  long long r0 = rows * blockIdx.y / gridDim.y, r1 = rows * (blockIdx.y + 1) / gridDim.y;
-  float s1 = 0.f, s2 = 0.f;
-  for (long long r = r0; r < r1; ++r) {
-    float f = to_f32(x[r * C + c]);
-    s1 += f;
-    s2 = fmaf(f, f, s2);
+  if (c < C) {
+    long long r0 = rows * blockIdx.y / gridDim.y, r1 = rows * (blockIdx.y + 1) / gridDim.y;
+    float s1 = 0.f, s2 = 0.f;
+    for (long long r = r0; r < r1; ++r) {
+      float f = to_f32(x[r * C + c]);
+      s1 += f;
+      s2 = fmaf(f, f, s2);
+    }
+    xs::add(xsc.limbs, 2 * C, c, s1);
+    xs::add(xsc.limbs, 2 * C, C + c, s2);
   }
-  atomicAdd(&sums[c], (double)s1);
-  atomicAdd(&sums[C + c], (double)s2);
+  if (xs::block_is_last(xsc.counter + blockIdx.x, gridDim.y))
+    xs_decode_pair<double>(xsc, blockIdx.x, C, blockIdx.x * blockDim.x, min(C, (int)((blockIdx.x + 1) * blockDim.x)),
+                           sums, sums + C);
 }
 
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, int C, float eps,
@@ -374,7 +404,8 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T*
                      long long rows, int C, int slab_v, int rowlanes,
                      const float* __restrict__ mean, const float* __restrict__ invstd,
                      const float* __restrict__ gamma, const float* __restrict__ beta, int act,
-                     float alpha, float* __restrict__ sum_dz, float* __restrict__ sum_dz_xhat) {
+                     float alpha, float* __restrict__ sum_dz, float* __restrict__ sum_dz_xhat,
+                     XsScratch xsc) {
   constexpr int V = Vec16<T>::N;
   extern __shared__ float sh[];
   const int sv = threadIdx.x % slab_v, rl = threadIdx.x / slab_v;
@@ -432,7 +463,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T*
       sh[(size_t)(rowlanes + rl) * width + sv * V + i] = s2[i];
     }
   }
-  slab_finish<V, float>(sh, slab_v, rowlanes, blockIdx.x, C, sum_dz, sum_dz_xhat);
+  slab_finish<V, float>(sh, slab_v, rowlanes, blockIdx.x, C, sum_dz, sum_dz_xhat, xsc);
 }
 
 template <typename T>
@@ -554,22 +585,27 @@ template <typename T>
 __global__ void bn_bwd_reduce_scalar_kernel(const T* dy, const T* x, const T* y, long long rows,
                                             int C, const float* mean, const float* invstd,
                                             const float* gamma, const float* beta, int act,
-                                            float alpha, float* sum_dz, float* sum_dz_xhat) {
+                                            float alpha, float* sum_dz, float* sum_dz_xhat,
+                                            XsScratch xsc) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  long long r0 = rows * blockIdx.y / gridDim.y, r1 = rows * (blockIdx.y + 1) / gridDim.y;
-  float is = invstd[c], mu = mean[c];
-  float sc = (gamma ? gamma[c] : 1.f) * is, sf = (beta ? beta[c] : 0.f) - mu * sc;
-  float s1 = 0.f, s2 = 0.f;
-  for (long long r = r0; r < r1; ++r) {
-    float xv = to_f32(x[r * C + c]);
-    float dz = dz_of<T>(to_f32(dy[r * C + c]), xv, y ? to_f32(y[r * C + c]) : 0.f, y != nullptr,
-                        sc, sf, act, alpha);
-    s1 += dz;
-    s2 = fmaf(dz, (xv - mu) * is, s2);
+  if (c < C) {
+    long long r0 = rows * blockIdx.y / gridDim.y, r1 = rows * (blockIdx.y + 1) / gridDim.y;
+    float is = invstd[c], mu = mean[c];
+    float sc = (gamma ? gamma[c] : 1.f) * is, sf = (beta ? beta[c] : 0.f) - mu * sc;
+    float s1 = 0.f, s2 = 0.f;
+    for (long long r = r0; r < r1; ++r) {
+      float xv = to_f32(x[r * C + c]);
+      float dz = dz_of<T>(to_f32(dy[r * C + c]), xv, y ? to_f32(y[r * C + c]) : 0.f, y != nullptr,
+                          sc, sf, act, alpha);
+      s1 += dz;
+      s2 = fmaf(dz, (xv - mu) * is, s2);
+    }
+    xs::add(xsc.limbs, 2 * C, c, s1);
+    xs::add(xsc.limbs, 2 * C, C + c, s2);
   }
-  atomicAdd(&sum_dz[c], s1);
-  atomicAdd(&sum_dz_xhat[c], s2);
+  if (xs::block_is_last(xsc.counter + blockIdx.x, gridDim.y))
+    xs_decode_pair<float>(xsc, blockIdx.x, C, blockIdx.x * blockDim.x, min(C, (int)((blockIdx.x + 1) * blockDim.x)),
+                          sum_dz, sum_dz_xhat);
 }
 template <typename T>
 __global__ void bn_bwd_apply_scalar_kernel(const T* dy, const T* x, const T* y, long long n, int C,
@@ -600,15 +636,18 @@ extern "C" int mcn_bn_stats(int dtype, const void* x, long long rows, int C, dou
                             void* stream) {
   MCN_REQUIRE(x && sums && rows > 0 && C > 0, "bn_stats: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const XsScratch xsc = xs_scratch(2 * C, "bn_stats");
+  if (xsc.limbs == nullptr) return MCN_EINVAL;
   MCN_DISPATCH_DTYPE(dtype, T, {
     SlabLaunch L;
     if (plan_slab<T>(rows, C, &L, 3 * num_sms())) {
       size_t smem = 2 * (size_t)L.rowlanes * L.slab_v * Vec16<T>::N * sizeof(float);
       bn_stats_kernel<T><<<L.grid, 256, smem, st>>>(static_cast<const T*>(x), rows, C, L.slab_v,
-                                                    L.rowlanes, sums);
+                                                    L.rowlanes, sums, xsc);
     } else {
+      MCN_REQUIRE((C + 127) / 128 <= kWsCounters, "bn_stats: too many channels (%d)", C);
       dim3 grid((C + 127) / 128, (unsigned)std::min<long long>(rows, 4LL * num_sms()));
-      bn_stats_scalar_kernel<T><<<grid, 128, 0, st>>>(static_cast<const T*>(x), rows, C, sums);
+      bn_stats_scalar_kernel<T><<<grid, 128, 0, st>>>(static_cast<const T*>(x), rows, C, sums, xsc);
     }
   });
   return after_launch("bn_stats");
@@ -717,18 +756,21 @@ extern "C" int mcn_bn_bwd_reduce(int dtype, const void* dy, const void* x, const
                                  float* sum_dz, float* sum_dz_xhat, void* stream) {
   MCN_REQUIRE(dy && x && mean && invstd && sum_dz && sum_dz_xhat, "bn_bwd_reduce: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const XsScratch xsc = xs_scratch(2 * C, "bn_bwd_reduce");
+  if (xsc.limbs == nullptr) return MCN_EINVAL;
   MCN_DISPATCH_DTYPE(dtype, T, {
     SlabLaunch L;
     if (plan_slab<T>(rows, C, &L, 3 * num_sms())) {
       size_t smem = 2 * (size_t)L.rowlanes * L.slab_v * Vec16<T>::N * sizeof(float);
       bn_bwd_reduce_kernel<T><<<L.grid, 256, smem, st>>>(
           static_cast<const T*>(dy), static_cast<const T*>(x), static_cast<const T*>(y), rows, C,
-          L.slab_v, L.rowlanes, mean, invstd, gamma, beta, act, act_alpha, sum_dz, sum_dz_xhat);
+          L.slab_v, L.rowlanes, mean, invstd, gamma, beta, act, act_alpha, sum_dz, sum_dz_xhat, xsc);
     } else {
+      MCN_REQUIRE((C + 127) / 128 <= kWsCounters, "bn_bwd_reduce: too many channels (%d)", C);
       dim3 grid((C + 127) / 128, (unsigned)std::min<long long>(rows, 4LL * num_sms()));
       bn_bwd_reduce_scalar_kernel<T><<<grid, 128, 0, st>>>(
           static_cast<const T*>(dy), static_cast<const T*>(x), static_cast<const T*>(y), rows, C,
-          mean, invstd, gamma, beta, act, act_alpha, sum_dz, sum_dz_xhat);
+          mean, invstd, gamma, beta, act, act_alpha, sum_dz, sum_dz_xhat, xsc);
     }
   });
   return after_launch("bn_bwd_reduce");

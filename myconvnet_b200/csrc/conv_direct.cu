@@ -4,6 +4,7 @@
 // 3-channel stems.  Dense call sites: convnet.py:1659 and its autodiff, :2463.
 // Depthwise is bandwidth-bound: threads run along the channel axis so every access is coalesced.
 #include "mcn_common.cuh"
+#include "xsum.cuh"
 
 namespace mcn {
 namespace {
@@ -84,10 +85,12 @@ __global__ void conv_dgrad_direct_kernel(mcn_conv_desc d, const T* __restrict__ 
   }
 }
 
-// dW[tap,ci,co] += sum over a chunk of pixels; threads along co (coalesced dy reads).
+// dW[tap,ci,co] over a chunk of pixels; threads along co (coalesced dy reads).  Each pixel chunk
+// writes its own slice (slice_stride elements apart); splitk_reduce adds the slices in order.
 template <typename T>
 __global__ void conv_wgrad_direct_kernel(mcn_conv_desc d, const T* __restrict__ x,
-                                         const T* __restrict__ dy, float* __restrict__ dw) {
+                                         const T* __restrict__ dy, float* __restrict__ dw,
+                                         long long slice_stride) {
   // grid.x: (tap*Cin + ci) * ceil(Cout/blockDim.x) ; grid.y: pixel chunks
   const int cob = (d.Cout + blockDim.x - 1) / blockDim.x;
   const int co = (blockIdx.x % cob) * blockDim.x + threadIdx.x;
@@ -109,7 +112,7 @@ __global__ void conv_wgrad_direct_kernel(mcn_conv_desc d, const T* __restrict__ 
     float xv = to_f32(x[(((long long)n * d.H + h) * d.W + ww) * d.Cin + ci]);
     acc = fmaf(xv, to_f32(dy[m * d.Cout + co]), acc);
   }
-  atomicAdd(&dw[((long long)tap * d.Cin + ci) * d.Cout + co], acc);
+  dw[blockIdx.y * slice_stride + ((long long)tap * d.Cin + ci) * d.Cout + co] = acc;
 }
 
 // ---------------------------------------------------------------- depthwise
@@ -176,7 +179,8 @@ __global__ void dwconv_bwd_data_kernel(mcn_conv_desc d, int mult, const T* __res
 // blockDim (32 channels, 8 pixel lanes); grid (ceil(Co/32), taps, pixel chunks)
 template <typename T>
 __global__ void dwconv_bwd_filter_kernel(mcn_conv_desc d, int mult, const T* __restrict__ x,
-                                         const T* __restrict__ dy, float* __restrict__ dw) {
+                                         const T* __restrict__ dy, float* __restrict__ dw,
+                                         long long slice_stride) {
   __shared__ float sh[8][33];
   const int Co = d.Cin * mult;
   const int oc = blockIdx.x * 32 + threadIdx.x;
@@ -204,7 +208,7 @@ __global__ void dwconv_bwd_filter_kernel(mcn_conv_desc d, int mult, const T* __r
     float s = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) s += sh[j][threadIdx.x];
-    atomicAdd(&dw[(long long)tap * Co + oc], s);  // [tap][c][m] == [tap][oc]
+    dw[blockIdx.z * slice_stride + (long long)tap * Co + oc] = s;  // [tap][c][m] == [tap][oc]
   }
 }
 
@@ -340,12 +344,24 @@ extern "C" int mcn_conv2d_wgrad_direct(const mcn_conv_desc* d, int dtype, const 
   const long long pixels = (long long)d->N * d->Ho * d->Wo;
   long long chunks = std::max<long long>(1, std::min<long long>(pixels / 256, (8LL * num_sms() + gx - 1) / gx));
   chunks = std::min<long long>(chunks, 65535);
+  // deterministic: one workspace slice per pixel chunk, summed in chunk order afterwards
+  const long long n = (long long)d->kh * d->kw * d->Cin * d->Cout;
+  const long long stride = (n + 63) / 64 * 64;
+  const Workspace w = current_workspace();
+  MCN_REQUIRE(w.base != nullptr, "wgrad_direct: no workspace registered (mcn_set_workspace)");
+  const long long cap = (w.bytes - kWsSplitOff) / (stride * 4);
+  MCN_REQUIRE(cap >= 1, "wgrad_direct: workspace too small (%lld bytes, one slice needs %lld)",
+              w.bytes, kWsSplitOff + stride * 4);
+  chunks = std::min(chunks, cap);
+  float* slices = reinterpret_cast<float*>(w.base + kWsSplitOff);
   dim3 grid((unsigned)gx, (unsigned)chunks);
   MCN_DISPATCH_DTYPE(dtype, T, {
     conv_wgrad_direct_kernel<T><<<grid, block, 0, st>>>(*d, static_cast<const T*>(x),
-                                                        static_cast<const T*>(dy), dw);
+                                                        static_cast<const T*>(dy), slices, stride);
   });
-  return after_launch("conv_wgrad_direct");
+  int rc = after_launch("conv_wgrad_direct");
+  if (rc) return rc;
+  return launch_splitk_reduce(slices, stride, (int)chunks, n, dw, st);
 }
 
 extern "C" int mcn_dwconv2d_fwd(const mcn_conv_desc* d, int mult, int dtype, const void* x,
@@ -379,12 +395,22 @@ extern "C" int mcn_dwconv2d_bwd_filter(const mcn_conv_desc* d, int mult, int dty
   const long long gx = (Co + 31) / 32, taps = (long long)d->kh * d->kw;
   long long chunks = std::max<long long>(1, std::min<long long>(pixels / 64, (8LL * num_sms() + gx * taps - 1) / (gx * taps)));
   chunks = std::min<long long>(chunks, 65535);
+  const long long n = taps * Co;
+  const long long stride = (n + 63) / 64 * 64;
+  const Workspace w = current_workspace();
+  MCN_REQUIRE(w.base != nullptr, "dwconv_bwd_filter: no workspace registered (mcn_set_workspace)");
+  const long long cap = (w.bytes - kWsSplitOff) / (stride * 4);
+  MCN_REQUIRE(cap >= 1, "dwconv_bwd_filter: workspace too small");
+  chunks = std::min(chunks, cap);
+  float* slices = reinterpret_cast<float*>(w.base + kWsSplitOff);
   dim3 grid((unsigned)gx, (unsigned)taps, (unsigned)chunks), block(32, 8);
   MCN_DISPATCH_DTYPE(dtype, T, {
     dwconv_bwd_filter_kernel<T><<<grid, block, 0, st>>>(*d, mult, static_cast<const T*>(x),
-                                                        static_cast<const T*>(dy), dw);
+                                                        static_cast<const T*>(dy), slices, stride);
   });
-  return after_launch("dwconv_bwd_filter");
+  int rc = after_launch("dwconv_bwd_filter");
+  if (rc) return rc;
+  return launch_splitk_reduce(slices, stride, (int)chunks, n, dw, st);
 }
 
 extern "C" int mcn_im2col(const mcn_conv_desc* d, int dtype, const void* x, void* col, int kpad,

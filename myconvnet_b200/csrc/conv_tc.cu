@@ -26,6 +26,7 @@
 
 #include "mcn_common.cuh"
 #include "sm100_ptx.cuh"
+#include "xsum.cuh"
 
 namespace mcn {
 namespace {
@@ -104,6 +105,9 @@ struct EpiArgs {
   void* out;
   const float* bias;
   double* stats;   // fused batch-norm statistics: [2*n_total] fp64 (sum y, sum y^2), or nullptr
+  long long* xs;   // exact accumulator limbs [3][2*n_total] in the workspace (xsum.cuh)
+  unsigned int* xs_counter;   // one tile counter per n-tile
+  int tiles_m;     // tiles per n-tile
   int out_f32, vec_ok, accumulate, block_n, n_total;
   int debug;   // bit0: skip stores, bit1: skip MMA issue, bit2: skip TMEM loads (timing experiments)
 };
@@ -115,8 +119,10 @@ struct EpiArgs {
 // bf16 channels in a private shared-memory tile (row pitch 36 words: conflict-free 16-byte row
 // stores and conflict-free column reads), lane L then sums channels 2L and 2L+1 down the 32
 // rows.  Partial sums go to a per-WARP shared accumulator (one n-tile wide, plain read-modify-
-// write: no shared-memory float atomics, which are CAS loops) and are flushed with fp64 global
-// atomics only when the persistent CTA moves to another n-tile or finishes.
+// write: no shared-memory float atomics, which are CAS loops) and are flushed into the exact
+// fixed-point accumulator of xsum.cuh (integer atomics: the result does not depend on the order
+// in which CTAs arrive) only when the persistent CTA moves to another n-tile or finishes; the
+// flush that completes an n-tile decodes its limbs into the caller's fp64 sums (stats_flush).
 constexpr int kStatRowWords = 36;
 constexpr int kStatStageWords = 4 * 32 * kStatRowWords;          // four epilogue warps
 constexpr int kStatAccWarp = 2 * 256;                            // [sum | sum sq] x block_n <= 256
@@ -127,9 +133,14 @@ constexpr int kBarRegionBytes = 256;                             // mbarriers + 
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-// et: index of the thread among the 128 epilogue threads
-__device__ __forceinline__ void stats_flush(const EpiArgs& e, float* acc, int n_t, int et) {
-  epi_bar_sync();   // every warp's shared-memory atomics of the finished tiles have landed
+// et: index of the thread among the 128 epilogue threads; `pending` = tiles of n-tile n_t whose
+// sums this flush carries.  The ticket counter of an n-tile counts TILES: the flush that
+// completes the n-tile's tiles_m tiles decodes just that n-tile's channels into the caller's fp64
+// sums and clears limbs and counter — no grid-wide serial tail, and the workspace is zero again
+// when the kernel ends.  `flag` is a shared-memory word visible to all epilogue threads.
+__device__ __forceinline__ void stats_flush(const EpiArgs& e, float* acc, int n_t, int et, int pending,
+                                            int* flag) {
+  epi_bar_sync();   // every warp's shared-memory sums of the finished tiles have landed
   for (int c = et; c < e.block_n; c += 128) {
     const int col = n_t * e.block_n + c;
     float s1 = 0.f, s2 = 0.f;
@@ -141,9 +152,28 @@ __device__ __forceinline__ void stats_flush(const EpiArgs& e, float* acc, int n_
       acc[w * kStatAccWarp + 256 + c] = 0.f;
     }
     if (col < e.n_total) {
-      atomicAdd(e.stats + col, static_cast<double>(s1));
-      atomicAdd(e.stats + e.n_total + col, static_cast<double>(s2));
+      xs::add(e.xs, 2 * e.n_total, col, s1);
+      xs::add(e.xs, 2 * e.n_total, e.n_total + col, s2);
     }
+  }
+  __threadfence();   // the adds are ordered before the ticket
+  epi_bar_sync();
+  if (et == 0) {
+    const unsigned int old = atomicAdd(e.xs_counter + n_t, static_cast<unsigned int>(pending));
+    __threadfence();
+    *flag = (old + static_cast<unsigned int>(pending) == static_cast<unsigned int>(e.tiles_m)) ? 1 : 0;
+  }
+  epi_bar_sync();
+  if (*flag) {
+    const int c0 = n_t * e.block_n;
+    const int w = min(e.n_total - c0, e.block_n);
+    for (int i = et; i < 2 * w; i += 128) {
+      const int which = i >= w ? 1 : 0;
+      const int idx = which * e.n_total + c0 + i - which * w;
+      const double prev = e.stats[idx];
+      e.stats[idx] = prev + xs::read_clear(e.xs, 2 * e.n_total, idx);
+    }
+    if (et == 0) xs::release(e.xs_counter + n_t);
   }
   epi_bar_sync();
 }
@@ -459,16 +489,19 @@ gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
       for (int i = row; i < kStatAccFloats; i += 128) stat_acc_all[i] = 0.f;
       epi_bar_sync();
     }
-    int lt = 0, cur_nt = -1;
+    int* stat_flag = reinterpret_cast<int*>(tail + kBarRegionBytes - 16);
+    int lt = 0, cur_nt = -1, pending = 0;
     for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x, ++lt) {
       const int buf = lt & 1;
       const uint32_t tph = static_cast<uint32_t>(lt >> 1) & 1u;
       const int n_t = tile_id % args.tiles_n;
-      if (stats && (n_t != cur_nt || (lt & 7) == 0)) {
+      if (stats && (n_t != cur_nt || pending == 8)) {
         // also every 8 tiles: bounds the length of the fp32 partial sums (accuracy of sum x^2)
-        if (cur_nt >= 0) stats_flush(args.e, stat_acc_all, cur_nt, row);
+        if (cur_nt >= 0) stats_flush(args.e, stat_acc_all, cur_nt, row, pending, stat_flag);
         cur_nt = n_t;
+        pending = 0;
       }
+      ++pending;
       const PixelTile tile = decode_tile(args.g, tile_id / args.tiles_n);
       int n, p, q;
       const bool valid = row_coords(args.g, tile, row, n, p, q);
@@ -477,7 +510,7 @@ gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
                     off, n_t, &tmem_full[buf], tph, &tmem_empty[buf], stat_stage, stat_acc, chunk_first,
                     chunk_step);
     }
-    if (stats && cur_nt >= 0) stats_flush(args.e, stat_acc_all, cur_nt, row);
+    if (stats && cur_nt >= 0) stats_flush(args.e, stat_acc_all, cur_nt, row, pending, stat_flag);
   }
 
   ptx::tc_fence_before();
@@ -662,16 +695,19 @@ halo_conv_kernel(const __grid_constant__ HaloArgs args) {
       for (int i = row; i < kStatAccFloats; i += 128) stat_acc_all[i] = 0.f;
       epi_bar_sync();
     }
-    int lt = 0, cur_nt = -1;
+    int* stat_flag = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(bars) + kBarRegionBytes - 16);
+    int lt = 0, cur_nt = -1, pending = 0;
     for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x, ++lt) {
       const int buf = lt & 1;
       const uint32_t tph = static_cast<uint32_t>(lt >> 1) & 1u;
       const int n_t = tile_id % args.tiles_n;
-      if (stats && (n_t != cur_nt || (lt & 7) == 0)) {
+      if (stats && (n_t != cur_nt || pending == 8)) {
         // also every 8 tiles: bounds the length of the fp32 partial sums (accuracy of sum x^2)
-        if (cur_nt >= 0) stats_flush(args.e, stat_acc_all, cur_nt, row);
+        if (cur_nt >= 0) stats_flush(args.e, stat_acc_all, cur_nt, row, pending, stat_flag);
         cur_nt = n_t;
+        pending = 0;
       }
+      ++pending;
       const int m = tile_id / args.tiles_n;
       const int n = m / tiles_per_img;
       const int r = m - n * tiles_per_img;
@@ -682,7 +718,7 @@ halo_conv_kernel(const __grid_constant__ HaloArgs args) {
       epilogue_tile(args.e, tmem_base + static_cast<uint32_t>(buf * args.e.block_n), quad, lane, valid,
                     off, n_t, &tmem_full[buf], tph, &tmem_empty[buf], stat_stage, stat_acc);
     }
-    if (stats && cur_nt >= 0) stats_flush(args.e, stat_acc_all, cur_nt, row);
+    if (stats && cur_nt >= 0) stats_flush(args.e, stat_acc_all, cur_nt, row, pending, stat_flag);
   }
 
   ptx::tc_fence_before();
@@ -698,9 +734,39 @@ struct WgradArgs {
   int taps, stages, block_n, nb_atoms, tmem_cols;
   int cin, cout;
   int tiles_mi, tiles_ni, splits, kblocks_total, ksteps;
-  float* dw;
+  float* dw;          // split-K partial slices (deterministic) or the gradient itself (atomics)
+  long long ws_stride;  // elements between the slices of consecutive splits; 0 = fp32 atomics into
+                        // dw; -1 = K is not split: every element has one owner, added in place
   TapTab tab;
 };
+
+// A thread's 32 consecutive output channels of one dw row: plain 16-byte stores into this
+// split's private slice (summed later in split order by splitk_reduce), or, in the legacy
+// MCN_WGRAD_ATOMICS=1 mode, fp32 reductions straight into the gradient.
+__device__ __forceinline__ void wgrad_out32(float* o, const uint32_t (&r)[32], bool atomics,
+                                            bool owner_rmw = false) {
+  if (owner_rmw) {
+    // un-split K: this thread is the only writer of these elements in the whole grid
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      float4 v = *reinterpret_cast<float4*>(o + j);
+      v.x += __uint_as_float(r[j]);
+      v.y += __uint_as_float(r[j + 1]);
+      v.z += __uint_as_float(r[j + 2]);
+      v.w += __uint_as_float(r[j + 3]);
+      *reinterpret_cast<float4*>(o + j) = v;
+    }
+  } else if (atomics) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4)
+      ptx::red_add_v4(o + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                      __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4)
+      *reinterpret_cast<uint4*>(o + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+  }
+}
 
 __global__ void __launch_bounds__(192, 1)
 wgrad_kernel(const __grid_constant__ WgradArgs args) {
@@ -824,16 +890,20 @@ wgrad_kernel(const __grid_constant__ WgradArgs args) {
       ptx::tmem_ld_wait();
       if (ci >= args.cin) continue;
       const int co0 = ni * args.block_n + c0;
-      float* o = args.dw + (static_cast<long long>(tap) * args.cin + ci) * args.cout + co0;
+      const bool atomics = args.ws_stride == 0;
+      const bool rmw = args.ws_stride < 0;      // splits == 1: add straight into the gradient
+      float* o = args.dw + (rmw ? 0 : static_cast<long long>(split) * args.ws_stride) +
+                 (static_cast<long long>(tap) * args.cin + ci) * args.cout + co0;
       if ((args.cout & 3) == 0 && co0 + 32 <= args.cout) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          ptx::red_add_v4(o + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                          __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        wgrad_out32(o, r, atomics, rmw);
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (co0 + j < args.cout) atomicAdd(o + j, __uint_as_float(r[j]));
+          if (co0 + j < args.cout) {
+            if (atomics) atomicAdd(o + j, __uint_as_float(r[j]));
+            else if (rmw) o[j] += __uint_as_float(r[j]);
+            else o[j] = __uint_as_float(r[j]);
+          }
       }
     }
   }
@@ -862,7 +932,8 @@ constexpr int kWhMaxAcc = 8;
 struct WgradHaloArgs {
   CUtensorMap mapX;    // box (64 ch, hwb, box_h, 1)
   CUtensorMap mapDy;   // box (64 ch, 8, 16, 1)
-  float* dw;
+  float* dw;           // split-K slices (ws_stride > 0) or the gradient (atomics)
+  long long ws_stride;
   int n_acc, block_n, nb_atoms, a_atoms, a_box_bytes, a_stride, stages, tmem_cols;
   int hwb, tiles_w, tiles_h, tiles_total, units_ci, units_co, groups, splits;
   int cin, cout, ci_tile, org_w;
@@ -992,11 +1063,9 @@ wgrad_halo_kernel(const __grid_constant__ WgradHaloArgs args) {
         if (!ok) continue;
         const int co0 = co_t * args.block_n + c0;
         if (co0 >= args.cout) continue;
-        float* o = args.dw + (static_cast<long long>(tap) * args.cin + ci) * args.cout + co0;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          ptx::red_add_v4(o + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                          __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        float* o = args.dw + static_cast<long long>(split) * args.ws_stride +
+                   (static_cast<long long>(tap) * args.cin + ci) * args.cout + co0;
+        wgrad_out32(o, r, args.ws_stride == 0);
       }
     }
   }
@@ -1021,7 +1090,8 @@ struct StemArgs {
   CUtensorMap mapW;     // fprop: [Cout][Kpad] bf16, box 64 x Cout;  wgrad: dy [M][Cout], box 64 x 128
   const __nv_bfloat16* x4;
   EpiArgs e;            // fprop output / statistics
-  float* dw;            // wgrad output [Kpad][Cout]
+  float* dw;            // wgrad output [Kpad][Cout]: split-K slices (ws_stride > 0) or the gradient
+  long long ws_stride;
   int H, W, Ho, Wo, N, sh, pad_t, pad_l, kh, kw;
   int epr, cpr, rpc, kc, kc_alloc, ksteps_last, kp;   // elements / 16-byte chunks per filter row, rows per 128-byte line
   int stages, tmem_cols, total_tiles, cout, nb_atoms, splits;
@@ -1193,17 +1263,22 @@ stem_fprop_kernel(const __grid_constant__ StemArgs args) {
       for (int i = row; i < kStatAccFloats; i += 128) stat_acc_all[i] = 0.f;
       epi_bar_sync();
     }
-    int it = 0;
+    int* stat_flag = reinterpret_cast<int*>(tail + kBarRegionBytes - 16);
+    int it = 0, pending = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
-      if (stats && it > 0 && (it & 7) == 0) stats_flush(args.e, stat_acc_all, 0, row);
+      if (stats && pending == 8) {
+        stats_flush(args.e, stat_acc_all, 0, row, pending, stat_flag);
+        pending = 0;
+      }
+      ++pending;
       const long long m = static_cast<long long>(tile) * 128 + row;
       const bool valid = m < args.m_total;
       epilogue_tile(args.e, tmem_base + static_cast<uint32_t>(buf * args.e.block_n), quad, lane, valid,
                     valid ? m * args.cout : 0, 0, &tmem_full[buf], static_cast<uint32_t>(it >> 1) & 1u,
                     &tmem_empty[buf], stat_stage, stat_acc);
     }
-    if (stats && it > 0) stats_flush(args.e, stat_acc_all, 0, row);
+    if (stats && pending > 0) stats_flush(args.e, stat_acc_all, 0, row, pending, stat_flag);
   }
 
   ptx::tc_fence_before();
@@ -1332,12 +1407,18 @@ stem_wgrad_kernel(const __grid_constant__ StemArgs args) {
         ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                                static_cast<uint32_t>(mt * args.e.block_n + c0), r);
         ptx::tmem_ld_wait();
-        if (!ok || c0 >= args.cout) continue;
-        float* o = args.dw + static_cast<long long>(k) * args.cout + c0;
+        if (c0 >= args.cout) continue;
+        const bool atomics = args.ws_stride == 0;
+        if (!ok) {
+          // rows of the widening tap / K padding carry no gradient: the slice still needs defined
+          // values there because splitk_reduce sums whole slices
+          if (atomics) continue;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          ptx::red_add_v4(o + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                          __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          for (int j = 0; j < 32; ++j) r[j] = 0u;
+        }
+        float* o = args.dw + static_cast<long long>(split) * args.ws_stride +
+                   static_cast<long long>(k) * args.cout + c0;
+        wgrad_out32(o, r, atomics);
       }
     }
   }
@@ -1500,9 +1581,76 @@ int smem_optin_limit() {
   return lim;
 }
 
+// Fused statistics go through the workspace's exact accumulator (xsum.cuh).
+int attach_xs(EpiArgs* e, int tiles_m, int tiles_n) {
+  e->xs = nullptr;
+  e->xs_counter = nullptr;
+  e->tiles_m = tiles_m;
+  if (e->stats == nullptr) return MCN_OK;
+  if (tiles_n > kWsCounters) {
+    set_error("conv fused statistics: too many n-tiles (%d)", tiles_n);
+    return MCN_EINVAL;
+  }
+  const XsScratch sc = xs_scratch(2 * e->n_total, "conv fused statistics");
+  if (sc.limbs == nullptr) return MCN_EINVAL;
+  e->xs = sc.limbs;
+  e->xs_counter = sc.counter;
+  return MCN_OK;
+}
+
+// Deterministic split-K: every split writes its partial dw into a private slice of the workspace
+// and splitk_reduce sums the slices in split order.  MCN_WGRAD_ATOMICS=1 selects the old fp32
+// atomics (A/B timing only; run-to-run results then differ in the low bits).
+bool wgrad_atomics() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MCN_WGRAD_ATOMICS");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v != 0;
+}
+struct SplitPlan {
+  float* base;         // first slice (nullptr in query / atomics mode)
+  long long stride;    // elements per slice
+  int splits;
+};
+// n: elements of dw; want: preferred split count.  query != nullptr: only report the bytes wanted.
+int plan_splits(long long n, int want, SplitPlan* sp, long long* query, const char* who) {
+  sp->stride = (n + 63) / 64 * 64;
+  sp->splits = want;
+  sp->base = nullptr;
+  if (query != nullptr) {
+    *query = kWsSplitOff + static_cast<long long>(want) * sp->stride * 4;
+    return MCN_OK;
+  }
+  if (wgrad_atomics()) {
+    sp->stride = 0;
+    return MCN_OK;
+  }
+  const Workspace w = current_workspace();
+  if (w.base == nullptr) {
+    set_error("%s: no workspace registered for this device (mcn_set_workspace)", who);
+    return MCN_EINVAL;
+  }
+  const long long cap = (w.bytes - kWsSplitOff) / (sp->stride * 4);
+  if (cap < 1) {
+    set_error("%s: workspace too small: %lld bytes, one split needs %lld", who, w.bytes,
+              kWsSplitOff + sp->stride * 4);
+    return MCN_EINVAL;
+  }
+  sp->splits = static_cast<int>(std::min<long long>(want, cap));
+  sp->base = reinterpret_cast<float*>(w.base + kWsSplitOff);
+  return MCN_OK;
+}
+
 int launch_gemm_conv(GemmConvArgs& a, int tiles_m, cudaStream_t st) {
   a.e.block_n = a.block_n;
   a.total_tiles = tiles_m * a.tiles_n;
+  {
+    const int rc = attach_xs(&a.e, tiles_m, a.tiles_n);
+    if (rc) return rc;
+  }
+#ifdef MCN_ENABLE_DEBUG_SKIP
   {
     static int dbg = -1;      // timing experiments: MCN_DEBUG_SKIP bit0 no stores, bit2 no TMEM loads
     if (dbg < 0) {
@@ -1511,6 +1659,9 @@ int launch_gemm_conv(GemmConvArgs& a, int tiles_m, cudaStream_t st) {
     }
     a.e.debug = dbg;
   }
+#else
+  a.e.debug = 0;
+#endif
   const int grid_n = std::min(a.total_tiles, num_sms());
   // weight-stationary when the CTA's weight slab is small and it sees one n-tile only
   static int ws_enabled = -1;
@@ -1629,10 +1780,14 @@ int launch_halo(const void* in, int C_in, int W_in, int H_in, int N, const void*
     use_bo = (e && e[0] == '1') ? 1 : 0;
   }
   a.use_base_offset = use_bo;
+#ifdef MCN_ENABLE_DEBUG_SKIP
   {
     const char* e = getenv("MCN_DEBUG_SKIP");
     a.e.debug = e ? atoi(e) : 0;
   }
+#else
+  a.e.debug = 0;
+#endif
   a.tmem_cols = 2 * tmem_cols_for(a.e.block_n);
   a.total_tiles = a.tiles_w * a.tiles_h * N * a.tiles_n;
   const int nb_slots = a.b_stationary ? a.taps * a.k_chunks : a.b_stages;
@@ -1647,6 +1802,7 @@ int launch_halo(const void* in, int C_in, int W_in, int H_in, int N, const void*
     }
     configured = true;
   }
+  if ((rc = attach_xs(&a.e, a.total_tiles / a.tiles_n, a.tiles_n))) return rc;
   dim3 grid((unsigned)std::min(a.total_tiles, num_sms()));
   halo_conv_kernel<<<grid, 224, smem, st>>>(a);
   return after_launch("halo_conv_kernel");
@@ -1930,7 +2086,7 @@ extern "C" int mcn_conv2d_dgrad_tc(const mcn_conv_desc* d, const void* dy, const
 // Halo wgrad: returns 1 when the geometry is eligible and the launch was issued, 0 when the
 // caller should use the tap-at-a-time kernel, negative on error.
 static int try_wgrad_halo(const mcn_conv_desc* d, const void* x, const void* dy, float* dw,
-                          cudaStream_t st) {
+                          cudaStream_t st, long long* query) {
   static int enabled = -1;
   if (enabled < 0) {
     const char* e = getenv("MCN_WGRAD_HALO");
@@ -1986,7 +2142,16 @@ static int try_wgrad_halo(const mcn_conv_desc* d, const void* x, const void* dy,
   a.splits = std::max(1, std::min(a.tiles_total, num_sms() / units));
   a.cin = d->Cin;
   a.cout = d->Cout;
-  a.dw = dw;
+  const long long dw_elems = (long long)taps * d->Cin * d->Cout;
+  SplitPlan sp;
+  {
+    const int prc = plan_splits(dw_elems, a.splits, &sp, query, "wgrad_tc (halo)");
+    if (prc) return prc;
+    if (query != nullptr) return 1;
+  }
+  a.splits = sp.splits;
+  a.ws_stride = sp.stride;
+  a.dw = sp.stride ? sp.base : dw;
   a.org_w = -d->pad_l;
   auto off = [&](int r, int s2) { return (r * d->dh * a.hwb + s2 * d->dw) * 128; };
   if (pair) {
@@ -2032,15 +2197,17 @@ static int try_wgrad_halo(const mcn_conv_desc* d, const void* x, const void* dy,
   dim3 grid((unsigned)(units * a.splits));
   wgrad_halo_kernel<<<grid, 192, smem, st>>>(a);
   rc = after_launch("wgrad_halo_kernel");
-  return rc ? rc : 1;
+  if (rc) return rc;
+  if (sp.stride && (rc = launch_splitk_reduce(sp.base, sp.stride, a.splits, dw_elems, dw, st))) return rc;
+  return 1;
 }
 
-extern "C" int mcn_conv2d_wgrad_tc(const mcn_conv_desc* d, const void* x, const void* dy,
-                                   float* dw, int a_mode, void* stream) {
-  MCN_REQUIRE(d && x && dy && dw, "wgrad_tc: null argument");
+static int wgrad_tc_impl(const mcn_conv_desc* d, const void* x, const void* dy, float* dw,
+                         int a_mode, void* stream, long long* query) {
+  MCN_REQUIRE(d && (query || (x && dy && dw)), "wgrad_tc: null argument");
   MCN_REQUIRE(d->Cin % 8 == 0 && d->Cout % 8 == 0, "wgrad_tc: channels must be multiples of 8");
   if (a_mode == 2) {
-    int rc = try_wgrad_halo(d, x, dy, dw, static_cast<cudaStream_t>(stream));
+    int rc = try_wgrad_halo(d, x, dy, dw, static_cast<cudaStream_t>(stream), query);
     if (rc != 0) return rc < 0 ? rc : MCN_OK;
     a_mode = 1;   // not eligible: tap-at-a-time kernel with the im2col feed
   }
@@ -2063,25 +2230,25 @@ extern "C" int mcn_conv2d_wgrad_tc(const mcn_conv_desc* d, const void* x, const 
     uint64_t stb[4] = {2, (uint64_t)d->Cin * 2, (uint64_t)ps.W * d->Cin * 2,
                        (uint64_t)ps.W * d->Cin * 2};
     uint32_t box[4] = {64, (uint32_t)a.g.TW, 1, 1};
-    if ((rc = encode_tiled(&a.mapX[0], x, 4, dims, stb, box))) return rc;
+    if (!query && (rc = encode_tiled(&a.mapX[0], x, 4, dims, stb, box))) return rc;
     uint64_t dimsy[4] = {(uint64_t)d->Cout, (uint64_t)ps.W, 1, 1};
     uint64_t sty[4] = {2, (uint64_t)d->Cout * 2, (uint64_t)ps.W * d->Cout * 2,
                        (uint64_t)ps.W * d->Cout * 2};
-    if ((rc = encode_tiled(&a.mapDy, dy, 4, dimsy, sty, box))) return rc;
+    if (!query && (rc = encode_tiled(&a.mapDy, dy, 4, dimsy, sty, box))) return rc;
   } else if (a_mode == 0) {
     PixelSpace ps{d->Wo, d->Ho, d->N};
     fill_geom_tiled(&a.g, ps);
     if (d->sh == 1 && d->sw == 1) {
-      if ((rc = encode_nhwc(&a.mapX[0], x, d->Cin, d->W, d->H, d->N, a.g.TW, a.g.TH, a.g.TN)))
+      if (!query && (rc = encode_nhwc(&a.mapX[0], x, d->Cin, d->W, d->H, d->N, a.g.TW, a.g.TH, a.g.TN)))
         return rc;
     } else {
       uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->Wo, (uint64_t)d->Ho, (uint64_t)d->N};
       uint64_t stb[4] = {2, (uint64_t)d->sw * d->Cin * 2, (uint64_t)d->sh * d->W * d->Cin * 2,
                          (uint64_t)d->H * d->W * d->Cin * 2};
       uint32_t box[4] = {64, (uint32_t)a.g.TW, (uint32_t)a.g.TH, (uint32_t)a.g.TN};
-      if ((rc = encode_tiled(&a.mapX[0], x, 4, dims, stb, box))) return rc;
+      if (!query && (rc = encode_tiled(&a.mapX[0], x, 4, dims, stb, box))) return rc;
     }
-    if ((rc = encode_nhwc(&a.mapDy, dy, d->Cout, d->Wo, d->Ho, d->N, a.g.TW, a.g.TH, a.g.TN)))
+    if (!query && (rc = encode_nhwc(&a.mapDy, dy, d->Cout, d->Wo, d->Ho, d->N, a.g.TW, a.g.TH, a.g.TN)))
       return rc;
   } else {
     a.g.a_mode = 1;
@@ -2095,20 +2262,19 @@ extern "C" int mcn_conv2d_wgrad_tc(const mcn_conv_desc* d, const void* x, const 
     a.g.low_h = -d->pad_t;
     const int up_w = (d->Wo - 1) * d->sw - d->pad_l - (d->W - 1);
     const int up_h = (d->Ho - 1) * d->sh - d->pad_t - (d->H - 1);
-    if ((rc = encode_im2col(&a.mapX[0], x, d->Cin, d->W, d->H, d->N, a.g.low_w, a.g.low_h, up_w,
+    if (!query && (rc = encode_im2col(&a.mapX[0], x, d->Cin, d->W, d->H, d->N, a.g.low_w, a.g.low_h, up_w,
                             up_h, d->sw, d->sh)))
       return rc;
     uint64_t dimsy[4] = {(uint64_t)d->Cout, (uint64_t)a.g.m_total, 1, 1};
     uint64_t sty[4] = {2, (uint64_t)d->Cout * 2, (uint64_t)a.g.m_total * d->Cout * 2,
                        (uint64_t)a.g.m_total * d->Cout * 2};
     uint32_t box[4] = {64, 128, 1, 1};
-    if ((rc = encode_tiled(&a.mapDy, dy, 4, dimsy, sty, box))) return rc;
+    if (!query && (rc = encode_tiled(&a.mapDy, dy, 4, dimsy, sty, box))) return rc;
   }
   for (int i = 1; i < 4; ++i) a.mapX[i] = a.mapX[0];
   a.taps = taps;
   a.cin = d->Cin;
   a.cout = d->Cout;
-  a.dw = dw;
   a.tiles_mi = (d->Cin + 127) / 128;
   a.tiles_ni = (d->Cout + a.block_n - 1) / a.block_n;
   a.kblocks_total = tiles_m_of(a.g);
@@ -2116,7 +2282,29 @@ extern "C" int mcn_conv2d_wgrad_tc(const mcn_conv_desc* d, const void* x, const 
   {
     const int base = taps * a.tiles_mi * a.tiles_ni;
     int want = (2 * num_sms() + base - 1) / base;
+    // one CTA per SM is resident at a time, so a grid that already fills 3/4 of the SMs gains
+    // nothing from splitting K — and an un-split K needs no slices and no second pass
+    if (4 * base >= 3 * num_sms()) want = 1;
     a.splits = std::max(1, std::min(want, a.kblocks_total));
+  }
+  const long long dw_elems = (long long)taps * d->Cin * d->Cout;
+  SplitPlan sp;
+  sp.base = nullptr;
+  sp.stride = 0;
+  sp.splits = 1;
+  if (a.splits == 1 && !wgrad_atomics()) {
+    if (query != nullptr) {
+      *query = kWsMinBytes;
+      return MCN_OK;
+    }
+    a.ws_stride = -1;
+    a.dw = dw;
+  } else {
+    if ((rc = plan_splits(dw_elems, a.splits, &sp, query, "wgrad_tc"))) return rc;
+    if (query != nullptr) return MCN_OK;
+    a.splits = sp.splits;
+    a.ws_stride = sp.stride;
+    a.dw = sp.stride ? sp.base : dw;
   }
   for (int r = 0; r < d->kh; ++r)
     for (int s = 0; s < d->kw; ++s) {
@@ -2146,8 +2334,17 @@ extern "C" int mcn_conv2d_wgrad_tc(const mcn_conv_desc* d, const void* x, const 
   }
   dim3 grid((unsigned)(taps * a.tiles_mi * a.tiles_ni * a.splits));
   wgrad_kernel<<<grid, 192, smem, static_cast<cudaStream_t>(stream)>>>(a);
-  return after_launch("wgrad_kernel");
+  if ((rc = after_launch("wgrad_kernel"))) return rc;
+  if (sp.stride)
+    return launch_splitk_reduce(sp.base, sp.stride, a.splits, dw_elems, dw, static_cast<cudaStream_t>(stream));
+  return MCN_OK;
 }
+
+extern "C" int mcn_conv2d_wgrad_tc(const mcn_conv_desc* d, const void* x, const void* dy,
+                                   float* dw, int a_mode, void* stream) {
+  return wgrad_tc_impl(d, x, dy, dw, a_mode, stream, nullptr);
+}
+
 
 // ------------------------------------------------------------------ stem convolution: host side
 namespace {
@@ -2221,21 +2418,29 @@ extern "C" int mcn_stem_conv_fprop(const mcn_conv_desc* d, const void* x4, const
     }
     configured = true;
   }
+  if ((rc = attach_xs(&a.e, a.total_tiles, 1))) return rc;
   dim3 grid(static_cast<unsigned>(std::min(a.total_tiles, num_sms())));
   stem_fprop_kernel<<<grid, 288, smem, static_cast<cudaStream_t>(stream)>>>(a);
   return after_launch("stem_fprop_kernel");
 }
 
-extern "C" int mcn_stem_conv_wgrad(const mcn_conv_desc* d, const void* x4, const void* dy, float* dw,
-                                   void* stream) {
-  MCN_REQUIRE(d && x4 && dy && dw, "stem_conv_wgrad: null argument");
+static int stem_wgrad_impl(const mcn_conv_desc* d, const void* x4, const void* dy, float* dw,
+                           void* stream, long long* query) {
+  MCN_REQUIRE(d && (query || (x4 && dy && dw)), "stem_conv_wgrad: null argument");
   StemArgs a;
   std::memset(&a, 0, sizeof(a));
   MCN_REQUIRE(stem_geometry(d, &a) && d->Cout % 64 == 0,
               "stem_conv_wgrad: geometry not supported (see mcn_stem_conv_fprop; Cout %% 64 == 0)");
   a.x4 = static_cast<const __nv_bfloat16*>(x4);
-  a.dw = dw;
   int rc;
+  a.splits = std::max(1, std::min(a.total_tiles, num_sms()));
+  const long long dw_elems = (long long)a.kc_alloc * 64 * d->Cout;
+  SplitPlan sp;
+  if ((rc = plan_splits(dw_elems, a.splits, &sp, query, "stem_conv_wgrad"))) return rc;
+  if (query != nullptr) return MCN_OK;
+  a.splits = sp.splits;
+  a.ws_stride = sp.stride;
+  a.dw = sp.stride ? sp.base : dw;
   if ((rc = encode_matrix(&a.mapW, dy, a.m_total, d->Cout, 128))) return rc;
   a.e.block_n = d->Cout;
   a.nb_atoms = d->Cout / 64;
@@ -2246,7 +2451,6 @@ extern "C" int mcn_stem_conv_wgrad(const mcn_conv_desc* d, const void* x4, const
   MCN_REQUIRE(cols <= 512, "stem_conv_wgrad: too many accumulator columns");
   a.tmem_cols = 32;
   while (a.tmem_cols < cols) a.tmem_cols *= 2;
-  a.splits = std::max(1, std::min(a.total_tiles, num_sms()));
   const size_t smem = a.stages * stage_bytes + kBarRegionBytes + 1024;
   static bool configured = false;
   if (!configured) {
@@ -2258,5 +2462,23 @@ extern "C" int mcn_stem_conv_wgrad(const mcn_conv_desc* d, const void* x4, const
     configured = true;
   }
   stem_wgrad_kernel<<<a.splits, 288, smem, static_cast<cudaStream_t>(stream)>>>(a);
-  return after_launch("stem_wgrad_kernel");
+  if ((rc = after_launch("stem_wgrad_kernel"))) return rc;
+  if (sp.stride)
+    return launch_splitk_reduce(sp.base, sp.stride, a.splits, dw_elems, dw, static_cast<cudaStream_t>(stream));
+  return MCN_OK;
+}
+
+extern "C" int mcn_stem_conv_wgrad(const mcn_conv_desc* d, const void* x4, const void* dy, float* dw,
+                                   void* stream) {
+  return stem_wgrad_impl(d, x4, dy, dw, stream, nullptr);
+}
+
+// Bytes of workspace (mcn_set_workspace) the wgrad of this convolution would like: the fixed
+// reduction area plus one dw-sized fp32 slice per split.  stem != 0: mcn_stem_conv_wgrad geometry.
+// A smaller workspace still works (fewer splits) down to one slice.
+extern "C" long long mcn_conv2d_wgrad_workspace_bytes(const mcn_conv_desc* d, int a_mode, int stem) {
+  long long q = 0;
+  const int rc = stem ? stem_wgrad_impl(d, nullptr, nullptr, nullptr, nullptr, &q)
+                      : wgrad_tc_impl(d, nullptr, nullptr, nullptr, a_mode, nullptr, &q);
+  return rc ? static_cast<long long>(rc) : q;
 }

@@ -4,6 +4,7 @@
 // scale, cast), efficientnet.py:163 (SE excite), tf.concat (deeplabv3plus.py:100,110) and
 // tf.image.resize_bilinear (convnet.py:2397).
 #include "mcn_common.cuh"
+#include "xsum.cuh"
 
 namespace mcn {
 namespace {
@@ -113,7 +114,7 @@ __global__ void bias_add_kernel(T* __restrict__ y, long long total, int C,
 // db[c] += sum_rows dy[r, c]; blockDim (32, 8), grid (C/32, row chunks)
 template <typename T>
 __global__ void bias_grad_kernel(const T* __restrict__ dy, long long rows, int C,
-                                 float* __restrict__ db) {
+                                 float* __restrict__ db, XsScratch xsc) {
   __shared__ float sh[8][33];
   int c = blockIdx.x * 32 + threadIdx.x;
   long long r0 = rows * blockIdx.y / gridDim.y, r1 = rows * (blockIdx.y + 1) / gridDim.y;
@@ -126,7 +127,14 @@ __global__ void bias_grad_kernel(const T* __restrict__ dy, long long rows, int C
     float s = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) s += sh[j][threadIdx.x];
-    atomicAdd(&db[c], s);
+    xs::add(xsc.limbs, C, c, s);
+  }
+  // exact accumulation + decode by the last block: the gradient does not depend on block order
+  if (xs::block_is_last(xsc.counter, gridDim.x * gridDim.y)) {
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    for (int i = tid; i < C; i += 256)
+      db[i] = static_cast<float>(static_cast<double>(db[i]) + xs::read_clear(xsc.limbs, C, i));
+    if (tid == 0) xs::release(xsc.counter);
   }
 }
 
@@ -334,10 +342,12 @@ extern "C" int mcn_bias_grad(int dtype, const void* dy, long long rows, int C, f
                              void* stream) {
   MCN_REQUIRE(dy && db, "bias_grad: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const XsScratch xsc = xs_scratch(C, "bias_grad");
+  if (xsc.limbs == nullptr) return MCN_EINVAL;
   int chunks = (int)std::max<long long>(1, std::min<long long>(rows / 64, 2LL * num_sms()));
   dim3 grid((C + 31) / 32, chunks), block(32, 8);
   MCN_DISPATCH_DTYPE(dtype, T, {
-    bias_grad_kernel<T><<<grid, block, 0, st>>>(static_cast<const T*>(dy), rows, C, db);
+    bias_grad_kernel<T><<<grid, block, 0, st>>>(static_cast<const T*>(dy), rows, C, db, xsc);
   });
   return after_launch("bias_grad");
 }

@@ -5,6 +5,7 @@
 #include <cfloat>
 
 #include "mcn_common.cuh"
+#include "xsum.cuh"
 
 namespace mcn {
 namespace {
@@ -14,7 +15,7 @@ namespace {
 __global__ void softmax_xent_kernel(const float* __restrict__ logits,
                                     const int32_t* __restrict__ labels, long long rows, int C,
                                     const float* __restrict__ class_w, float ls, float grad_scale,
-                                    float* __restrict__ loss_sum, float* __restrict__ dlogits,
+                                    long long* __restrict__ loss_xs, float* __restrict__ dlogits,
                                     float* __restrict__ probs) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
@@ -54,12 +55,12 @@ __global__ void softmax_xent_kernel(const float* __restrict__ logits,
       }
     }
   }
-  if (loss_sum && lane == 0 && block_loss != 0.f) atomicAdd(loss_sum, block_loss);
+  if (loss_xs && lane == 0) xs::add(loss_xs, 1, 0, block_loss);
 }
 
 // loss = max(x,0) - x*z + log1p(exp(-|x|));  d/dx = sigmoid(x) - z
 __global__ void sigmoid_xent_kernel(const float* __restrict__ logits, long long n, float label,
-                                    float weight, float grad_scale, float* __restrict__ loss_sum,
+                                    float weight, float grad_scale, long long* __restrict__ loss_xs,
                                     float* __restrict__ dlogits, int accumulate) {
   float acc = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -72,7 +73,7 @@ __global__ void sigmoid_xent_kernel(const float* __restrict__ logits, long long 
     }
   }
   acc = warp_sum(acc);
-  if (loss_sum && (threadIdx.x & 31) == 0 && acc != 0.f) atomicAdd(loss_sum, acc);
+  if (loss_xs && (threadIdx.x & 31) == 0) xs::add(loss_xs, 1, 0, acc);
 }
 
 }  // namespace
@@ -82,21 +83,21 @@ using namespace mcn;
 
 extern "C" int mcn_softmax_xent(const float* logits, const int32_t* labels, long long rows, int C,
                                 const float* class_w, float label_smoothing, float grad_scale,
-                                float* loss_sum, float* dlogits, float* probs, void* stream) {
+                                long long* loss_xs, float* dlogits, float* probs, void* stream) {
   MCN_REQUIRE(logits && rows > 0 && C > 0, "softmax_xent: bad argument");
   const int wpb = 8;
   int grid = (int)std::max<long long>(1, std::min<long long>((rows + wpb - 1) / wpb, 8LL * num_sms()));
   softmax_xent_kernel<<<grid, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      logits, labels, rows, C, class_w, label_smoothing, grad_scale, loss_sum, dlogits, probs);
+      logits, labels, rows, C, class_w, label_smoothing, grad_scale, loss_xs, dlogits, probs);
   return after_launch("softmax_xent");
 }
 
 extern "C" int mcn_sigmoid_xent(const float* logits, long long n, float label, float weight,
-                                float grad_scale, float* loss_sum, float* dlogits,
+                                float grad_scale, long long* loss_xs, float* dlogits,
                                 int accumulate_grad, void* stream) {
   MCN_REQUIRE(logits && n > 0, "sigmoid_xent: bad argument");
   int grid = (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, 4LL * num_sms()));
   sigmoid_xent_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      logits, n, label, weight, grad_scale, loss_sum, dlogits, accumulate_grad);
+      logits, n, label, weight, grad_scale, loss_xs, dlogits, accumulate_grad);
   return after_launch("sigmoid_xent");
 }

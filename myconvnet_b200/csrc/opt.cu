@@ -6,6 +6,7 @@
 // (optimizers.py:163-172) and the per-use fp32->half cast of the weights (convnet.py:1421), here
 // a bf16 copy in both tensor-core operand layouts.
 #include "mcn_common.cuh"
+#include "xsum.cuh"
 
 namespace mcn {
 namespace {
@@ -17,7 +18,7 @@ constexpr int kBlock = 256;
 // quantity tf.clip_by_global_norm needs (reference optimizers.py:112-113).  Same grid as the step.
 __global__ void __launch_bounds__(kBlock)
 grad_sqnorm_kernel(const mcn_opt_tensor* __restrict__ table, const float* __restrict__ hp,
-                   float* __restrict__ out) {
+                   long long* __restrict__ out_xs) {
   const mcn_opt_tensor t = table[blockIdx.y];
   const long long base = (long long)blockIdx.x * (kBlock * kItems);
   if (base >= t.n || t.g == nullptr) return;
@@ -39,7 +40,7 @@ grad_sqnorm_kernel(const mcn_opt_tensor* __restrict__ table, const float* __rest
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < kBlock / 32; ++w) s += part[w];
-    if (s != 0.f) atomicAdd(out, s);
+    xs::add(out_xs, 1, 0, s);
   }
 }
 
@@ -47,7 +48,7 @@ grad_sqnorm_kernel(const mcn_opt_tensor* __restrict__ table, const float* __rest
 //     [5] adam lr_t  [6] gradient scale  [7] weight-decay multiplier  [8] clip threshold
 __global__ void __launch_bounds__(kBlock)
 opt_step_kernel(int kind, const mcn_opt_tensor* __restrict__ table, const float* __restrict__ hp,
-                float* __restrict__ l2_loss, const float* __restrict__ grad_sqnorm) {
+                long long* __restrict__ l2_xs, const long long* __restrict__ grad_sqnorm_xs) {
   const mcn_opt_tensor t = table[blockIdx.y];
   const long long base = (long long)blockIdx.x * (kBlock * kItems);
   if (base >= t.n) return;
@@ -55,9 +56,9 @@ opt_step_kernel(int kind, const mcn_opt_tensor* __restrict__ table, const float*
               gscale = hp[6], wd = t.wd * hp[7];
   // tf.clip_by_global_norm: g * clip / max(global_norm, clip)
   float clip = 1.f;
-  if (grad_sqnorm != nullptr) {
+  if (grad_sqnorm_xs != nullptr) {
     const float thr = hp[8];
-    clip = thr / fmaxf(sqrtf(*grad_sqnorm), thr);
+    clip = thr / fmaxf(static_cast<float>(sqrt(xs::read(grad_sqnorm_xs, 1, 0))), thr);
   }
   float l2_acc = 0.f;  // l2 * sum(w^2)/2 over the PRE-step weights (tf.nn.l2_loss, convnet.py:563)
 #pragma unroll
@@ -103,9 +104,9 @@ opt_step_kernel(int kind, const mcn_opt_tensor* __restrict__ table, const float*
           __float2bfloat16_rn(w);
     }
   }
-  if (l2_loss != nullptr && t.l2 != 0.f) {
+  if (l2_xs != nullptr && t.l2 != 0.f) {
     l2_acc = warp_sum(l2_acc);
-    if ((threadIdx.x & 31) == 0 && l2_acc != 0.f) atomicAdd(l2_loss, l2_acc);
+    if ((threadIdx.x & 31) == 0) xs::add(l2_xs, 1, 0, l2_acc);
   }
 }
 
@@ -159,22 +160,23 @@ __global__ void weight_prep_kernel(const float* __restrict__ w, int cin, int cou
 using namespace mcn;
 
 extern "C" int mcn_opt_step(int kind, const mcn_opt_tensor* table, int ntensors, long long max_n,
-                            const float* hp, float* l2_loss, const float* grad_sqnorm, void* stream) {
+                            const float* hp, long long* l2_xs, const long long* grad_sqnorm_xs,
+                            void* stream) {
   MCN_REQUIRE(table && hp && ntensors > 0 && max_n > 0, "opt_step: bad argument");
   MCN_REQUIRE(kind >= MCN_OPT_NESTEROV && kind <= MCN_OPT_ADAM, "opt_step: unknown optimiser %d", kind);
   MCN_REQUIRE(ntensors <= 65535, "opt_step: too many tensors");
   dim3 grid((unsigned)((max_n + kBlock * kItems - 1) / (kBlock * kItems)), (unsigned)ntensors);
-  opt_step_kernel<<<grid, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(kind, table, hp, l2_loss,
-                                                                         grad_sqnorm);
+  opt_step_kernel<<<grid, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(kind, table, hp, l2_xs,
+                                                                         grad_sqnorm_xs);
   return after_launch("opt_step");
 }
 
 extern "C" int mcn_grad_sqnorm(const mcn_opt_tensor* table, int ntensors, long long max_n,
-                               const float* hp, float* out, void* stream) {
-  MCN_REQUIRE(table && hp && out && ntensors > 0 && max_n > 0, "grad_sqnorm: bad argument");
+                               const float* hp, long long* out_xs, void* stream) {
+  MCN_REQUIRE(table && hp && out_xs && ntensors > 0 && max_n > 0, "grad_sqnorm: bad argument");
   MCN_REQUIRE(ntensors <= 65535, "grad_sqnorm: too many tensors");
   dim3 grid((unsigned)((max_n + kBlock * kItems - 1) / (kBlock * kItems)), (unsigned)ntensors);
-  grad_sqnorm_kernel<<<grid, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(table, hp, out);
+  grad_sqnorm_kernel<<<grid, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(table, hp, out_xs);
   return after_launch("grad_sqnorm");
 }
 

@@ -94,6 +94,7 @@ class Engine(object):
         self.grad_threshold = None if gt is None else float(gt)
         self.hp_host = torch.zeros(16, dtype=torch.float32).pin_memory()
         self.hp_dev = self.view(Ptr(p.b_hp), 16, torch.float32)
+        self._ws = _lib.ensure_workspace(self._workspace_bytes(), self.device)
         self._build_opt_table()
         self.init_variables(seed)
         self._graph_exec = None
@@ -106,6 +107,22 @@ class Engine(object):
         if self.world > 1:
             self._setup_grad_buckets()
             self._setup_peer_comm()
+
+    def _workspace_bytes(self):
+        """Reduction workspace (include/mcn.h, mcn_set_workspace): the fixed limb area plus the
+        split-K slices the largest wgrad of this plan would like."""
+        need = int(self.lib.mcn_workspace_min_bytes())
+        cap = 1 << 30
+        for l in self.plan.bwd:
+            if l.fn == "mcn_conv2d_wgrad_tc":
+                need = max(need, int(self.lib.mcn_conv2d_wgrad_workspace_bytes(self._carg(l.args[0]), l.args[4], 0)))
+            elif l.fn == "mcn_stem_conv_wgrad":
+                need = max(need, int(self.lib.mcn_conv2d_wgrad_workspace_bytes(self._carg(l.args[0]), 0, 1)))
+            elif l.fn in ("mcn_conv2d_wgrad_direct", "mcn_dwconv2d_bwd_filter"):
+                d = l.args[0]
+                n = d.kh * d.kw * d.Cin * (l.args[1] if l.fn == "mcn_dwconv2d_bwd_filter" else d.Cout)
+                need = max(need, int(self.lib.mcn_workspace_min_bytes()) + min(64 * n * 4 + 4096, cap))
+        return min(need, int(self.lib.mcn_workspace_min_bytes()) + cap)
 
     # ------------------------------------------------------------------ memory views
     def addr(self, ptr):
@@ -315,6 +332,7 @@ class Engine(object):
         (shadowed) moving statistics.  Returns the model's `pred` tensor as float32 numpy."""
         self.load_inputs(X=X)
         self.refresh_operand_copies(ema=True)
+        _lib.use_workspace(self._ws)
         st = torch.cuda.current_stream(self.device).cuda_stream
         for fn, args, name, tag in self._inf:
             rc = fn(*args, st)
@@ -328,23 +346,74 @@ class Engine(object):
         buf = p.b_ema if ema else p.b_param
         return {v.name: self._from_storage(v, self._var_view(buf, v).cpu().numpy()) for v in p.all_vars}
 
-    def save_checkpoint(self, path, naming="reference"):
-        """Variables and EMA shadows under the reference's names (checkpoint.py); .npz."""
-        from . import checkpoint
-        checkpoint.save_npz(path, self.get_variables(), self.get_variables(ema=True), naming=naming)
+    # TF slot names of the three optimisers (tf.train.MomentumOptimizer / RMSPropOptimizer /
+    # AdamOptimizer), as tf.train.Saver writes them next to the variables (optimizers.py:312)
+    SLOT_NAMES = {0: ("Momentum", None), 1: ("RMSProp_1", "RMSProp"), 2: ("Adam", "Adam_1")}
 
-    def load_checkpoint(self, path, naming="reference", prefer_ema=False):
+    def get_optimizer_state(self):
+        """{<var>/<slot>: array in reference layout} for the optimiser slots (momentum / RMSProp
+        mean-square + momentum / Adam moments)."""
+        p = self.plan
+        m_name, v_name = self.SLOT_NAMES[self.opt_kind]
+        out = {}
+        for v in p.trainable:
+            out[v.name + "/" + m_name] = self._from_storage(v, self._var_view(p.b_mom, v).cpu().numpy())
+            if v_name is not None:
+                out[v.name + "/" + v_name] = self._from_storage(v, self._var_view(p.b_v, v).cpu().numpy())
+        return out
+
+    def set_optimizer_state(self, state, global_step=None):
+        """Inverse of get_optimizer_state; slots that are not in `state` keep their value."""
+        p = self.plan
+        m_name, v_name = self.SLOT_NAMES[self.opt_kind]
+        for v in p.trainable:
+            for buf, slot in ((p.b_mom, m_name), (p.b_v, v_name)):
+                key = None if slot is None else v.name + "/" + slot
+                if key is not None and key in state:
+                    arr = torch.from_numpy(self._to_storage(v, state[key]).reshape(-1)).to(self.device)
+                    self._var_view(buf, v).copy_(arr)
+        if global_step is not None:
+            self.global_step = int(global_step)
+        torch.cuda.synchronize(self.device)
+
+    def set_ema(self, values):
+        """EMA shadows from {name: array in reference layout}."""
+        p = self.plan
+        for v in p.all_vars:
+            if v.name in values:
+                arr = torch.from_numpy(self._to_storage(v, values[v.name]).reshape(-1)).to(self.device)
+                self._var_view(p.b_ema, v).copy_(arr)
+        torch.cuda.synchronize(self.device)
+
+    def save_checkpoint(self, path, naming="reference", trainer=None):
+        """Everything tf.train.Saver keeps for a resumable run (reference optimizers.py:312 saves all
+        global variables): the variables and their EMA shadows under the reference's names
+        (checkpoint.py), the optimiser slots under TF's slot names, global_step and, when a
+        Trainer is passed, its step counter; .npz."""
+        from . import checkpoint
+        extra = dict(self.get_optimizer_state())
+        extra["global_step"] = np.asarray(self.global_step, dtype=np.int64)
+        if trainer is not None:
+            extra["trainer/curr_step"] = np.asarray(trainer.curr_step, dtype=np.int64)
+        checkpoint.save_npz(path, self.get_variables(), self.get_variables(ema=True), naming=naming,
+                            extra=extra)
+
+    def load_checkpoint(self, path, naming="reference", prefer_ema=False, resume=True, trainer=None):
         """Loads what matches by name and shape; returns the names that were not found.  The EMA
-        shadows restart from the loaded values unless the file carries its own."""
+        shadows restart from the loaded values unless the file carries its own.  resume=True also
+        restores optimiser slots and global_step when the file has them (a run continues where it
+        stopped: EMA warm-up, Adam bias correction and momentum are not reset); resume=False is a
+        transfer-style load that starts the optimiser from scratch."""
         from . import checkpoint
         expected = {v.name: v.shape for v in self.plan.all_vars}
         var, ema = checkpoint.load_npz(path, expected=expected, naming=naming, prefer_ema=prefer_ema)
         self.set_variables(var, reset_state=True)
-        p = self.plan
-        for v in p.all_vars:
-            if v.name in ema:
-                arr = torch.from_numpy(self._to_storage(v, ema[v.name]).reshape(-1)).to(self.device)
-                self._var_view(p.b_ema, v).copy_(arr)
+        self.set_ema(ema)
+        if resume:
+            extra = checkpoint.load_extra(path)
+            self.set_optimizer_state(extra, global_step=extra.get("global_step"))
+            if trainer is not None and "trainer/curr_step" in extra:
+                trainer.curr_step = int(extra["trainer/curr_step"])
         return sorted(set(expected) - set(var))
 
     def get_gradients(self):
@@ -461,6 +530,7 @@ class Engine(object):
 
     def _step_body(self, backward=True, update=True):
         st = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.use_workspace(self._ws)
         _lib.check(self.lib.mcn_fill_f32(self._zero_ptr, self._zero_n, 0.0, st), "zero")
         self._run(self._fwd, "f", st)
         if not backward:
@@ -529,13 +599,15 @@ class Engine(object):
         if "loss" not in p.loss_slots:
             return None
         node = self.graph.losses[0].node
+        # the slots are exact fixed-point accumulators (xsum limbs), decoded on the host
         if "loss_g" in p.loss_slots:
-            v = self.view(p.loss_slots["loss"], 3, torch.float32).cpu().numpy()
-            self.last_losses = (float(v[0]) / node.attrs["rows"], float(v[1]) / node.attrs["rows"])
+            v = self.view(p.loss_slots["loss"], 9, torch.int64).cpu().numpy().reshape(3, 3)
+            d, g = _lib.xsum_value(v[0]), _lib.xsum_value(v[1])
+            self.last_losses = (d / node.attrs["rows"], g / node.attrs["rows"])
             return self.last_losses[0]
-        v = self.view(p.loss_slots["loss"], 2, torch.float32).cpu().numpy()
-        data = float(v[0]) / node.attrs["rows"]
-        return data + float(v[1])
+        v = self.view(p.loss_slots["loss"], 6, torch.int64).cpu().numpy().reshape(2, 3)
+        data = _lib.xsum_value(v[0]) / node.attrs["rows"]
+        return data + _lib.xsum_value(v[1])
 
     def launches_per_step(self):
         return 1 + len(self._fwd) + len(self._bwd) + 1

@@ -77,6 +77,7 @@ SIGNATURES = {
     "mcn_grad_sqnorm": "pilpp",
     "mcn_transpose_add_f32": "piiip",
     "mcn_peer_allreduce": "pllpipipipii",
+    "mcn_xsum_decode": "pippi",
     "mcn_fill_f32": "plf",
     "mcn_scale_f32": "plf",
 }
@@ -104,6 +105,12 @@ def load():
     lib.mcn_launch_count.restype = ctypes.c_longlong
     lib.mcn_stem_conv_kpad.restype = ctypes.c_int
     lib.mcn_stem_conv_kpad.argtypes = [ctypes.POINTER(ConvDescC)]
+    lib.mcn_set_workspace.restype = ctypes.c_int
+    lib.mcn_set_workspace.argtypes = [ctypes.c_void_p, ctypes.c_longlong]
+    lib.mcn_workspace_min_bytes.restype = ctypes.c_longlong
+    lib.mcn_workspace_min_bytes.argtypes = []
+    lib.mcn_conv2d_wgrad_workspace_bytes.restype = ctypes.c_longlong
+    lib.mcn_conv2d_wgrad_workspace_bytes.argtypes = [ctypes.POINTER(ConvDescC), ctypes.c_int, ctypes.c_int]
     _lib = lib
     return lib
 
@@ -115,3 +122,42 @@ def check(rc, what=""):
 
 def launch_count():
     return int(load().mcn_launch_count())
+
+
+def xsum_value(limbs):
+    """Host decode of xsum accumulators (include/mcn.h): limbs is an int64 array [3][n] (or [3]);
+    exact Python-integer arithmetic, returned as float(s)."""
+    import numpy as np
+    a = np.asarray(limbs, dtype=np.int64).reshape(3, -1)
+    out = [float((int(l0) + (int(l1) << 40) + (int(l2) << 80)) / (1 << 80)) if abs(int(l2)) < (1 << 61)
+           else float("nan") for l0, l1, l2 in zip(a[0], a[1], a[2])]
+    return out[0] if len(out) == 1 else np.array(out)
+
+
+_workspaces = {}      # device index -> list of workspace tensors, newest last (none is ever freed:
+                      # captured CUDA graphs keep raw pointers into the one they were recorded with)
+
+
+def ensure_workspace(nbytes=0, device=None):
+    """Allocate (once per device, growing on demand), zero and register the reduction workspace
+    every deterministic kernel needs (mcn_set_workspace).  Returns the torch tensor holding it.
+    One workspace per device is shared by everything in the process that runs on the current
+    stream (launches sharing it must be stream-ordered)."""
+    import torch
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    lib = load()
+    need = max(int(nbytes), int(lib.mcn_workspace_min_bytes()))
+    held = _workspaces.setdefault(dev.index, [])
+    if not held or held[-1].numel() < need + 256:
+        torch.cuda.synchronize(dev)
+        held.append(torch.zeros(need + 256, dtype=torch.uint8, device=dev))
+    use_workspace(held[-1])
+    return held[-1]
+
+
+def use_workspace(t):
+    """Register an existing (zeroed) uint8 tensor as the current device's workspace."""
+    import torch
+    base = (t.data_ptr() + 255) // 256 * 256
+    with torch.cuda.device(t.device):
+        check(load().mcn_set_workspace(base, t.numel() - (base - t.data_ptr())), "set_workspace")

@@ -198,7 +198,7 @@ class Plan(object):
         self.b_mom = self.new_buf("opt_m", max(self.n_train, 1) * 4, "state")
         self.b_v = self.new_buf("opt_v", max(self.n_train, 1) * 4, "state")
         self.b_hp = self.new_buf("hyper_params", 64, "state")
-        self.b_gnorm = self.new_buf("grad_sqnorm", 16, "zero")      # squared global gradient norm (clipping)
+        self.b_gnorm = self.new_buf("grad_sqnorm", 32, "zero")      # xsum accumulator: squared global gradient norm (clipping)
         # bf16 operand copies
         self.bf16_off = {}
         self.bf16t_off = {}
@@ -778,9 +778,10 @@ class Plan(object):
         rows = a["rows"]
         if self.phase == "infer":
             return          # predictions come from the softmax node (emitted stand-alone below)
-        loss = self.new_buf("loss", 16, "zero")
+        # loss accumulators are exact fixed-point sums (xsum: 3 int64 limbs each, include/mcn.h)
+        loss = self.new_buf("loss", 2 * 24, "zero")
         self.loss_slots["loss"] = Ptr(loss)
-        self.loss_slots["l2"] = Ptr(loss, 4)
+        self.loss_slots["l2"] = Ptr(loss, 24)
         self.tbuf[node.outputs[0]] = Ptr(loss)
         dlog = self.new_buf("dlogits", logits.size * 4, "act")
         node.attrs["dlogits"] = dlog
@@ -810,12 +811,12 @@ class Plan(object):
         lr_, lf_ = node.inputs
         a = node.attrs
         n = a["rows"]
-        loss = self.new_buf("gan_loss", 16, "zero")
+        loss = self.new_buf("gan_loss", 3 * 24, "zero")
         self.loss_slots["loss"] = Ptr(loss)
-        self.loss_slots["loss_g"] = Ptr(loss, 4)
-        self.loss_slots["l2"] = Ptr(loss, 8)
+        self.loss_slots["loss_g"] = Ptr(loss, 24)
+        self.loss_slots["l2"] = Ptr(loss, 48)
         self.tbuf[node.outputs[0]] = Ptr(loss)
-        self.tbuf[node.outputs[1]] = Ptr(loss, 4)
+        self.tbuf[node.outputs[1]] = Ptr(loss, 24)
         bufs = [self.new_buf("dlogits_%s" % k, n * 4, "act") for k in ("real", "fake_d", "fake_g")]
         a["dlogits"] = bufs
         w0, w1 = a["w"]
@@ -827,7 +828,7 @@ class Plan(object):
         self.L("f", "mcn_sigmoid_xent", self.tbuf[lf_], n, 0.0, w0, gs, Ptr(loss), Ptr(bufs[1]), 0,
                tag="gan_loss/fake_d")
         self.L("f", "mcn_sigmoid_xent", self.tbuf[lf_], n, 1.0 - ls, w0, gs * a["generator_scaling_factor"],
-               Ptr(loss, 4), Ptr(bufs[2]), 0, tag="gan_loss/fake_g")
+               Ptr(loss, 24), Ptr(bufs[2]), 0, tag="gan_loss/fake_g")
 
     def _b_gan_loss(self, node):
         lr_, lf_ = node.inputs

@@ -57,7 +57,9 @@ def test_ctypes_table_matches_header(built_lib):
         got = "".join(code_of(a) for a in args[:-1])
         assert got == codes, "%s: header %s vs lib.py %s" % (name, got, codes)
     missing = set(decls) - set(lib.SIGNATURES) - {"mcn_last_error", "mcn_version", "mcn_launch_count",
-                                                        "mcn_stem_conv_kpad"}
+                                                        "mcn_stem_conv_kpad", "mcn_set_workspace",
+                                                        "mcn_workspace_min_bytes",
+                                                        "mcn_conv2d_wgrad_workspace_bytes"}
     assert not missing, missing
     L = lib.load()
     assert L.mcn_version() >= 100
