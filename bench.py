@@ -27,6 +27,71 @@ MODEL = "ResNet-v1.5-50"
 IMG = [224, 224, 3]
 NCLS = 1000
 
+# BASELINE.json configs.  The default ("r50") is configs[1], the one the headline metric is quoted
+# on; the others are measured with --config and recorded under profiles/ (same JSON schema).
+CONFIGS = {
+    "r50": "ResNet-v1.5-50, synthetic 224x224x3, 1000 classes, batch 256/GPU, bf16 (BASELINE configs[1])",
+    "r50_fp32_b32": "ResNet-v1.5-50, synthetic 224x224x3, batch 32, fp32 (GPU leg of BASELINE configs[0])",
+    "effnet_b0": "EfficientNet-B0, synthetic 224x224x3, 1000 classes, batch 256/GPU, bf16 (BASELINE configs[2])",
+    "deeplab_r50_512": "DeepLabv3+ on dilated ResNet-v1.5-50 (OS16), synthetic 512x512x3, 21 classes, "
+                       "batch 16/GPU, bf16 (BASELINE configs[3])",
+    "dcgan_64": "DCGAN 64x64x3, latent 100, batch 128, bf16, D and G updated from one forward "
+                "(BASELINE configs[4]; reference semantics, optimizers_gan.py:56-58)",
+}
+
+
+def build_workload(args, np, torch):
+    """(model, source, X, Y, optimizer, dtype, description) of the selected BASELINE config."""
+    from myconvnet_b200 import loader
+    from myconvnet_b200.zoo import resnet50
+    cfg = args.config
+    rng = np.random.default_rng(1234 + int(os.environ.get("RANK", "0")))
+    u8 = lambda shape: torch.from_numpy(rng.integers(0, 256, size=shape, dtype=np.uint8)).pin_memory()  # noqa: E731
+    if cfg in ("r50", "r50_fp32_b32"):
+        dt = "bf16" if cfg == "r50" else "f32"
+        batch = args.batch or (256 if cfg == "r50" else 32)
+        # images cross the host boundary as raw uint8 NHWC (what an image data set holds); the device
+        # prologue divides by 255, zero-centres, scales and casts (mcn_input_prep, convnet.py:449-471)
+        model, src = resnet50(IMG, NCLS, batch_size=batch, compute_dtype=dt, input_dtype="u8")
+        X = u8([batch] + IMG)
+        Y = torch.from_numpy(rng.integers(0, NCLS, size=batch).astype(np.int32)).pin_memory()
+        return model, src, X, Y, "nesterov", dt, batch
+    if loader.reference_root() is None:
+        raise RuntimeError("config %s needs the reference model files (scripts/stage_reference.py)" % cfg)
+    fac = loader.product_facade()
+    if cfg == "effnet_b0":
+        batch = args.batch or 256
+        mod = loader.load_reference_model("models/efficientnet.py", fac)
+        model = mod.EfficientNetB0(IMG, NCLS, batch_size=batch, compute_dtype="bf16", input_dtype="u8")
+        X = u8([batch] + IMG)
+        Y = torch.from_numpy(rng.integers(0, NCLS, size=batch).astype(np.int32)).pin_memory()
+        return model, "reference models/efficientnet.py (unchanged)", X, Y, "rmsprop", "bf16", batch
+    if cfg == "deeplab_r50_512":
+        batch = args.batch or 16
+        mod = loader.load_reference_model("models/deeplabv3plus.py", fac)
+
+        class DeepLabV3PlusResNet50(mod.DeepLabV3PlusResNet):
+            # the file hard-imports ResNet101OS16; the BASELINE config names the ResNet-50 depth
+            # (res_units of resnet_v1_5_dilated.py:10 with the OS16 strides of :157-162)
+            def _init_params(self, **kwargs):
+                mod.DeepLabV3PlusResNet._init_params(self, **kwargs)
+                self.res_units = [None, 3, 4, 6, 3]
+        shape = [512, 512, 3]
+        model = DeepLabV3PlusResNet50(shape, 21, batch_size=batch, compute_dtype="bf16", input_dtype="u8")
+        X = u8([batch] + shape)
+        Y = torch.from_numpy(rng.integers(0, 22, size=[batch, 512, 512]).astype(np.int32)).pin_memory()
+        return model, "reference models/deeplabv3plus.py (unchanged; ResNet-50 depth)", X, Y, "nesterov", "bf16", batch
+    if cfg == "dcgan_64":
+        batch = args.batch or 128
+        mod = loader.load_reference_model("models/dcgan.py", fac)
+        shape = [64, 64, 3]
+        model = mod.DCGAN(shape, 100, batch_size=batch, compute_dtype="bf16", input_dtype="u8",
+                          base_learning_rate=5e-4, momentum=0.5, generator_scaling_factor=2.0)
+        X = u8([batch] + shape)
+        Y = torch.from_numpy(rng.uniform(-1, 1, size=(batch, 100)).astype(np.float32)).pin_memory()
+        return model, "reference models/dcgan.py (unchanged)", X, Y, "adam", "bf16", batch
+    raise ValueError("unknown --config %s (one of %s)" % (cfg, ", ".join(CONFIGS)))
+
 
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -210,7 +275,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: the config's)")
+    ap.add_argument("--config", default="r50", choices=sorted(CONFIGS), help="BASELINE config to run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--profile-json", default=None, help="write the per-kernel-class table here")
@@ -225,7 +291,6 @@ def main():
     import torch
     from myconvnet_b200 import lib as L
     from myconvnet_b200.engine import Engine
-    from myconvnet_b200.zoo import resnet50
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -274,13 +339,10 @@ def main():
         stage("first all-reduce done (%d)" % int(t.item()))
     warmup = max(args.warmup, 3)
     stage("building model and engine")
-    model, model_src = resnet50(IMG, NCLS, batch_size=args.batch, compute_dtype="bf16")
-    eng = Engine(model, optimizer="nesterov", world_size=world, rank=rank, process_group=pg,
+    model, model_src, X, Y, optimizer, cdt, args.batch = build_workload(args, np, torch)
+    eng = Engine(model, optimizer=optimizer, world_size=world, rank=rank, process_group=pg,
                  use_cuda_graph=(not args.no_graph), seed=0, fetch_pred=False,
                  **({"conv_mode": args.conv_mode} if args.conv_mode is not None else {}))
-    rng = np.random.default_rng(1234 + rank)
-    X = torch.from_numpy(rng.uniform(size=[args.batch] + IMG).astype(np.float32)).pin_memory()
-    Y = torch.from_numpy(rng.integers(0, NCLS, size=args.batch).astype(np.int32)).pin_memory()
 
     def barrier():
         if world > 1:
@@ -387,11 +449,12 @@ def main():
     line = {
         "metric": "train_images_per_sec", "value": gb / (ms * 1e-3), "unit": "img/s", "n_gpus": world,
         "steps": args.steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "%s train step (fwd+bwd+Nesterov/L2/EMA update), synthetic 224x224x3, "
-                               "1000 classes, batch %d/GPU, bf16 activations + fp32 master weights, sync-BN"
-                               % (MODEL, args.batch),
+        "scaling": "weak", "vs_baseline": None, "dtype": cdt, "data": "synthetic",
+        "config": {"workload": "%s: one training step (forward + backward + %s update with L2 / EMA), "
+                               "fp32 master weights, sync-BN across GPUs" % (CONFIGS[args.config], optimizer),
+                   "name": args.config,
                    "global_batch": gb, "parallelism": "dp%d" % world, "model_source": model_src,
+                   "input": "uint8 NHWC images from pinned host memory, normalised on the device",
                    "l2_flush": "not needed: one step touches %.1f GB of HBM per GPU (>> 126 MB L2)"
                                % (eng.plan.arena_bytes / 1e9),
                    "cuda_graph": bool(eng.use_cuda_graph),
@@ -402,7 +465,8 @@ def main():
                                       "NCCL, %d buckets started during backward + %d after"
                                       % (sum(len(v) for v in eng._bucket_ready.values()), len(eng._bucket_tail)))},
         "e2e": {"value": gb / (ms_e2e * 1e-3), "unit": "img/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": int(X.numel() * 4 + Y.numel() * 4 + 64), "d2h_bytes_per_step": 8},
+                "h2d_bytes_per_step": int(X.numel() * X.element_size() + Y.numel() * Y.element_size() + 64),
+                "d2h_bytes_per_step": 48},
         "gpu_launches": eager_launches * args.steps,
         "launches_counted_by_library": L.launch_count() - launches0,
         "final_loss": loss,

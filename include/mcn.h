@@ -25,7 +25,7 @@ extern "C" {
 #endif
 
 typedef enum { MCN_OK = 0, MCN_EINVAL = -1, MCN_ECUDA = -2, MCN_EUNSUPPORTED = -3 } mcn_status;
-typedef enum { MCN_F32 = 0, MCN_BF16 = 1 } mcn_dtype;
+typedef enum { MCN_F32 = 0, MCN_BF16 = 1, MCN_U8 = 2 } mcn_dtype;   /* U8: network input images only */
 typedef enum {
   MCN_ACT_NONE = 0,
   MCN_ACT_RELU = 1,
@@ -150,6 +150,11 @@ int mcn_bn_stats(int dtype, const void* x, long long rows, int C, double* sums, 
 int mcn_bn_finalize(const double* sums, double count, int C, float eps, float momentum,
                     float* mean, float* invstd, float* moving_mean, float* moving_var,
                     void* stream);
+/* frozen BN (update off, convnet.py:1916-1924): mean = moving_mean, invstd = 1/sqrt(moving_var+eps);
+ * mcn_bn_apply then normalises with them, the backward pass is mcn_bn_bwd_reduce (dgamma, dbeta)
+ * + mcn_bn_bwd_apply with ZERO sums (dx = dz*gamma*invstd: no batch-statistics terms). */
+int mcn_bn_frozen_stats(const float* moving_mean, const float* moving_var, int C, float eps,
+                        float* mean, float* invstd, void* stream);
 int mcn_bn_apply(int dtype, const void* x, long long rows, int C, const float* mean,
                  const float* invstd, const float* gamma, const float* beta, const void* residual,
                  int act, float act_alpha, void* y, void* stream);
@@ -191,6 +196,17 @@ int mcn_maxpool_fwd(int dtype, const void* x, int N, int H, int W, int C, int kh
 int mcn_maxpool_bwd(int dtype, const void* dy, const int32_t* argmax, int N, int H, int W, int C,
                     int kh, int kw, int sh, int sw, int pad_t, int pad_l, int Ho, int Wo, void* dx,
                     void* stream);
+/* compact form used by the training step: the winner is stored as its TAP index a*kw + b inside the
+ * window (one byte instead of four: the int32 argmax is twice the size of a bf16 tensor); same
+ * tie rule.  mcn_maxpool_tap_to_argmax expands it to the TF index above, bit for bit.
+ * Needs kh*kw <= 255 and C a multiple of the 16-byte vector (8 bf16 / 4 fp32). */
+int mcn_maxpool_fwd_tap(int dtype, const void* x, int N, int H, int W, int C, int kh, int kw, int sh,
+                        int sw, int pad_t, int pad_l, int Ho, int Wo, void* y, uint8_t* tap, void* stream);
+int mcn_maxpool_bwd_tap(int dtype, const void* dy, const uint8_t* tap, int N, int H, int W, int C, int kh,
+                        int kw, int sh, int sw, int pad_t, int pad_l, int Ho, int Wo, void* dx,
+                        void* stream);
+int mcn_maxpool_tap_to_argmax(const uint8_t* tap, int N, int H, int W, int C, int kh, int kw, int sh,
+                              int sw, int pad_t, int pad_l, int Ho, int Wo, int32_t* argmax, void* stream);
 int mcn_avgpool_fwd(int dtype, const void* x, int N, int H, int W, int C, int kh, int kw, int sh,
                     int sw, int pad_t, int pad_l, int Ho, int Wo, void* y, void* stream);
 int mcn_avgpool_bwd(int dtype, const void* dy, int N, int H, int W, int C, int kh, int kw, int sh,
@@ -220,9 +236,11 @@ int mcn_scale_bcast_bwd(int dtype, const void* dy, const void* x, const void* m,
 int mcn_bias_add(int dtype, void* y, long long rows, int C, const float* bias, void* stream);
 int mcn_bias_grad(int dtype, const void* dy, long long rows, int C, float* db, void* stream);
 int mcn_cast(int src_dtype, const void* src, int dst_dtype, void* dst, long long n, void* stream);
-/* network input: y = (x - mean)*scale, fp32 NHWC -> compute dtype (convnet.py:452,466,471) */
-int mcn_input_prep(const float* x, long long n, float mean, float scale, int dst_dtype, void* y,
-                   void* stream);
+/* network input prologue (convnet.py:449-471): x is [N,Hi,Wi,C] fp32 in [0,1] (MCN_F32) or raw uint8
+ * (MCN_U8: divided by 255 first); centre crop to [N,H,W,C] with offsets (Hi-H)//2, (Wi-W)//2
+ * (center_crop, convnet.py:1137-1149), y = (x - mean)*scale, cast to the compute dtype. */
+int mcn_input_prep(const void* x, int src_dtype, int N, int Hi, int Wi, int H, int W, int C,
+                   float mean, float scale, int dst_dtype, void* y, void* stream);
 /* channel concat / split of NHWC tensors (tf.concat axis=-1, deeplabv3plus.py:100,110) */
 int mcn_copy_channels(int dtype, const void* src, long long rows, int Csrc, int src_off, void* dst,
                       int Cdst, int dst_off, int Ccopy, int accumulate, void* stream);
@@ -233,13 +251,42 @@ int mcn_resize_bilinear_fwd(int dtype, const void* x, int N, int H, int W, int C
 int mcn_resize_bilinear_bwd(int dtype, const void* dy, int N, int H, int W, int C, int Ho, int Wo,
                             int mode, void* dx, void* stream);
 
+/* nearest-neighbour resize (tf.image.resize_nearest_neighbor, convnet.py:2393-2395); modes as above:
+ * 0 src = floor(dst*in/out), 1 src = round(dst*(in-1)/(out-1)), 2 src = floor((dst+0.5)*in/out). */
+int mcn_resize_nearest_fwd(int dtype, const void* x, int N, int H, int W, int C, int Ho, int Wo,
+                           int mode, void* y, void* stream);
+int mcn_resize_nearest_bwd(int dtype, const void* dy, int N, int H, int W, int C, int Ho, int Wo,
+                           int mode, void* dx, void* stream);
+
+/* ---- random train-time ops.  Keep decisions are a pure function of (seed, step, layer, element):
+ * Philox4x32-10 with counter (idx_lo, idx_hi, step, 0) and key (seed, layer); u = (bits>>8)*2^-24;
+ * keep <=> u >= rate; kept values are scaled by 1/(1-rate).  seed and step are read on the device
+ * from hp (the optimiser's hyper-parameter vector: uint32 at float slots 12 and 13), so a replayed
+ * CUDA graph draws new masks every step and the backward pass recomputes them.
+ * dropout: tf.nn.dropout(x, rate) (resnet_v1_5.py:75, efficientnet.py:117); element i uses output
+ *          i%4 of counter i/4; the same call with dy in place of x is the backward pass.
+ * sd_add : ConvNet.stochastic_depth (convnet.py:2500-2512): y = act(a*survived[n] + b) with
+ *          survived[n] = (u_n >= rate)/(1-rate) per sample (counter = n, output 0);
+ *          backward: dz = dy*act'(y), da = dz*survived[n], db = dz (either may be NULL). */
+int mcn_dropout(int dtype, const void* x, long long n, float rate, const float* hp, int layer, void* y,
+                void* stream);
+int mcn_sd_add_fwd(int dtype, const void* a, const void* b, int N, long long per_sample, float rate,
+                   const float* hp, int layer, int act, float alpha, void* y, void* stream);
+int mcn_sd_add_bwd(int dtype, const void* dy, const void* y, int N, long long per_sample, float rate,
+                   const float* hp, int layer, int act, float alpha, void* da, void* db, void* stream);
+
 /* ---- losses (convnet.py:594-600, gan.py:134-138) ----
  * softmax cross-entropy on fp32 logits [rows][C] with int32 labels (-1 = all-zero one-hot row,
  * convnet.py:448-449).  loss_sum accumulates sum_rows w*valid*CE; dlogits = grad_scale *
  * w*valid*(softmax - smoothed_onehot).  probs may be NULL.  loss_xs: one xsum accumulator
- * (3 int64, zero first; decode on the host or with mcn_xsum_decode). */
+ * (3 int64, zero first; decode on the host or with mcn_xsum_decode).
+ * label_smoothing: targets onehot*(1-ls) + ls/C (convnet.py:603-607) or, with seg_h/seg_w > 0 (rows
+ * are the pixels of [N,seg_h,seg_w] label maps), onehot*(1-ls) + ls*avg5x5(onehot)
+ * (segmentation/segnet.py:116-121).  focal_gamma > 0: CE *= (1-p_true)^gamma; sigmoid_focal_alpha
+ * > 0: CE *= stop_gradient(1-sigmoid(alpha*(p_true-0.5)))/(1-sigmoid(-alpha/2)) (convnet.py:580-592). */
 int mcn_softmax_xent(const float* logits, const int32_t* labels, long long rows, int C,
-                     const float* class_w, float label_smoothing, float grad_scale,
+                     const float* class_w, float label_smoothing, float focal_gamma,
+                     float sigmoid_focal_alpha, int seg_h, int seg_w, float grad_scale,
                      long long* loss_xs, float* dlogits, float* probs, void* stream);
 int mcn_sigmoid_xent(const float* logits, long long n, float label, float weight, float grad_scale,
                      long long* loss_xs, float* dlogits, int accumulate_grad, void* stream);
@@ -261,11 +308,14 @@ typedef struct {
   int taps, cin, cout; /* for the transposed copy */
   float l2;            /* L2 factor for this tensor (0 for biases/norm unless bias_norm_decay) */
   float wd;            /* decoupled weight decay factor (already scaled) */
+  float l1;            /* L1 factor (convnet.py:555-558): g += l1*sign(w), loss += l1*sum|w| */
 } mcn_opt_tensor;
 typedef enum { MCN_OPT_NESTEROV = 0, MCN_OPT_RMSPROP = 1, MCN_OPT_ADAM = 2 } mcn_opt_kind;
-/* table: device array of mcn_opt_tensor; hp (device, 9 floats): lr, momentum(beta1),
- * beta2/decay, eps, ema_decay_t, adam_lr_t, grad_scale, weight-decay multiplier, clip threshold — read on device
- * so a captured CUDA graph can be replayed with new hyper-parameters. */
+/* table: device array of mcn_opt_tensor; hp (device, 11 floats): lr, momentum(beta1),
+ * beta2/decay, eps, ema_decay_t, adam_lr_t, grad_scale, weight-decay multiplier, clip threshold,
+ * weight-decay form (0 = wd*w, 1 = wd*sign(w), 2 = pseudo-Huber wd*w/sqrt(1+(w/delta)^2);
+ * optimizers.py:163-172), Huber delta — read on device so a captured CUDA graph can be replayed
+ * with new hyper-parameters. */
 int mcn_opt_step(int kind, const mcn_opt_tensor* table, int ntensors, long long max_n,
                  const float* hp, long long* l2_loss_xs, const long long* grad_sqnorm_xs,
                  void* stream);

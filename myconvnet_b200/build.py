@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmcn.so")
 SOURCES = ["runtime.cu", "conv_tc.cu", "conv_direct.cu", "bn.cu", "pool.cu", "eltwise.cu",
-           "loss.cu", "opt.cu", "comm.cu"]
+           "loss.cu", "opt.cu", "comm.cu", "dropout.cu", "dwconv.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 # Approximate division / sqrt and flush-to-zero only where they cannot reach the fp32 parity of the
@@ -20,7 +20,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 # bn.cu keeps it too: its cancellation-prone maths (mean / variance / invstd) is explicit fp64, and
 # without fast-math the runtime-selected activation (tanhf, precise division) doubles the register
 # count of the streaming kernels (measured: bn_apply 142 -> 293 us on a 411 MB tensor).
-FAST_MATH = {"conv_tc.cu", "conv_direct.cu", "pool.cu", "eltwise.cu", "dwconv.cu", "bn.cu"}
+FAST_MATH = {"conv_tc.cu", "conv_direct.cu", "pool.cu", "eltwise.cu", "dwconv.cu", "bn.cu", "dropout.cu"}
 
 
 def _stale():

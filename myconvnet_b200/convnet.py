@@ -133,7 +133,16 @@ class ConvNet(object):
         h, w, c = self.input_size
         if kwargs_get(self._parameters, 'zero_pad_ratio', 0.0) != 0.0:
             raise NotImplementedError('zero_pad_ratio != 0 is not supported (input pipeline is out of scope)')
-        x_in = self.graph.placeholder('X', (n, h, w, c), 'f32')
+        # images of the data set may be larger than the network input: centre crop (no augmentation),
+        # reference convnet.py:453-456,1137-1149.  `input_dtype='u8'` takes raw uint8 images (they are
+        # divided by 255 on the device) — a quarter of the host->device bytes of fp32 batches.
+        hi, wi = kwargs_get(self._parameters, 'image_size', (h, w, c))[:2]
+        if hi < h or wi < w:
+            raise ValueError('image_size %s is smaller than the network input %s' % ((hi, wi), (h, w)))
+        in_dt = kwargs_get(self._parameters, 'input_dtype', 'f32')
+        if in_dt not in ('f32', 'u8'):
+            raise ValueError("input_dtype must be 'f32' or 'u8'")
+        x_in = self.graph.placeholder('X', (n, int(hi), int(wi), c), in_dt)
         node = self.graph._add('input_prep', [x_in], [(n, h, w, c)], [self._dtype],
                                {'mean': self.image_mean, 'scale': self.scale_factor})
         return x_in, node.outputs[0]
@@ -167,21 +176,28 @@ class ConvNet(object):
         l1_factor = kwargs.get('l1_reg', 0e-8)
         l2_factor = kwargs.get('l2_reg', 1e-4)
         ls_factor = kwargs.get('label_smoothing', 0.0)
-        if l1_factor > 0.0:
-            raise NotImplementedError('l1_reg is not supported')
-        if kwargs.get('focal_loss_factor', 0.0) > 0.0 or kwargs.get('sigmoid_focal_loss_factor', 0.0) > 0.0:
-            raise NotImplementedError('focal losses are not supported')
         w = self.loss_weights
         w = None if w is None else np.array(w, dtype=np.float32)
         logits = self.logits
         rows = int(np.prod(logits.shape[:-1]))
+        # the smoothing rule is the task base's _label_smoothing (convnet.py:603-607 uniform;
+        # segmentation/segnet.py:116-121 5x5 spatial average of the one-hot map)
+        seg_hw = self._label_smoothing_map() if ls_factor > 0.0 else None
         node = self.graph._add('softmax_xent', [logits, self.Y], [()], ['f32'],
                                {'class_weights': w, 'label_smoothing': float(ls_factor),
-                                'rows': rows, 'l2': float(l2_factor),
+                                'seg_hw': seg_hw,
+                                'focal_gamma': float(kwargs.get('focal_loss_factor', 0.0)),
+                                'sigmoid_focal_alpha': float(kwargs.get('sigmoid_focal_loss_factor', 0.0)),
+                                'rows': rows, 'l2': float(l2_factor), 'l1': float(l1_factor),
                                 'bias_norm_decay': bool(kwargs.get('bias_norm_decay', False))})
         loss = node.outputs[0]
         self.graph.losses.append(loss)
         return loss
+
+    def _label_smoothing_map(self):
+        """None: labels*(1-ls) + ls/num_classes (convnet.py:603-607).  Task bases whose smoothing is
+        spatial return the (H, W) of their label maps."""
+        return None
 
     # ------------------------------------------------------------------ properties
     @property
@@ -563,13 +579,23 @@ class ConvNet(object):
                                    {'mode': mode}, tf.current_scope() + '/' + name)
             return node.outputs[0]
         elif upsampling_method.lower() in ('nearest', 'nearest_neighbor'):
-            raise NotImplementedError('nearest-neighbour upsampling is not supported yet')
+            node = self.graph._add('resize_nearest', [x],
+                                   [(x.shape[0], out_shape[0], out_shape[1], x.shape[3])], [x.dtype],
+                                   {'mode': mode}, tf.current_scope() + '/' + name)
+            return node.outputs[0]
         raise ValueError('Upsampling method of {} is not supported'.format(upsampling_method))
 
     # ------------------------------------------------------------------ residual / activations
     def stochastic_depth(self, x, skip, drop_rate=0.0, name='drop'):
+        # x*survived + skip with a per-sample Bernoulli keep (reference convnet.py:2500-2512); the
+        # keep mask is drawn on the device (csrc/dropout.cu), inference adds the branches unchanged
         if drop_rate > 0.0:
-            raise NotImplementedError('stochastic depth with drop_rate > 0 is not supported yet')
+            if x.shape != skip.shape:
+                raise ValueError('stochastic_depth: shape mismatch %s vs %s' % (x.shape, skip.shape))
+            node = self.graph._add('sd_add', [x, skip], [x.shape], [x.dtype],
+                                   {'rate': float(drop_rate), 'layer': self.graph.next_random_layer()},
+                                   tf.current_scope() + '/' + name)
+            return node.outputs[0]
         return x + skip
 
     def activation(self, x, activation_type='relu', params=None):

@@ -30,6 +30,15 @@ inline bool bn_bwd_use_runs() {
   }
   return v != 0;
 }
+// rows (reduce) / vectors (apply) in flight per thread of the backward kernels: MCN_BN_BWD_UNROLL=2|4
+inline int bn_bwd_unroll() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MCN_BN_BWD_UNROLL");
+    v = (e && e[0] == '4') ? 4 : 2;   // measured: 4 spills and costs occupancy (25.6 -> 28.1 ms/step)
+  }
+  return v;
+}
 inline bool bn_use_runs() {
   static int v = -1;
   if (v < 0) {
@@ -218,6 +227,19 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
   }
 }
 
+// Frozen batch-norm (update off: blocks outside blocks_to_train or update_batch_norm=False): the
+// reference normalises with the STORED moving statistics even while training
+// (fused_batch_norm(is_training=False), convnet.py:1916-1924).  This fills the saved mean / invstd
+// the apply and backward kernels read, so both passes use the same constants.
+__global__ void bn_frozen_stats_kernel(const float* __restrict__ moving_mean,
+                                       const float* __restrict__ moving_var, int C, float eps,
+                                       float* __restrict__ mean, float* __restrict__ invstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  mean[c] = moving_mean[c];
+  invstd[c] = static_cast<float>(1.0 / sqrt(static_cast<double>(moving_var[c]) + static_cast<double>(eps)));
+}
+
 // ---------------------------------------------------------------- forward apply
 // Per-channel scale/shift of a thread's V channels are held in registers; the tensor is then
 // streamed once.  Three sources for the normalisation constants:
@@ -398,8 +420,11 @@ __device__ __forceinline__ float dz_of(float dy, float xv, float yv, bool have_y
   return dy * act_grad_from_x(act, fmaf(xv, sc, sf), alpha);
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256, 3)
+// U rows per thread are in flight at once (U*2 or U*3 16-byte loads): at 768 threads per SM two rows
+// keep ~49 KB in flight, about what 6.5 TB/s x ~1 us of loaded latency needs per SM and no more
+// (measured 0.65 of the copy peak); four rows double that.
+template <typename T, int U, bool kHaveY>
+__global__ void __launch_bounds__(256, (U > 2 && kHaveY) ? 2 : 3)
 bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
                      long long rows, int C, int slab_v, int rowlanes,
                      const float* __restrict__ mean, const float* __restrict__ invstd,
@@ -423,11 +448,11 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T*
       sc[i] = (gamma ? gamma[c0 + i] : 1.f) * invstd[c0 + i];
       sf[i] = (beta ? beta[c0 + i] : 0.f) - mean[c0 + i] * sc[i];
     }
-    const bool have_y = (y != nullptr);
-    for (long long r = r0 + rl; r < r1; r += 2LL * rowlanes) {
-      Vec16<T> g[2], a[2], o[2];
+    constexpr bool have_y = kHaveY;
+    for (long long r = r0 + rl; r < r1; r += (long long)U * rowlanes) {
+      Vec16<T> g[U], a[U], o[kHaveY ? U : 1];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < U; ++u) {
         long long rr = r + (long long)u * rowlanes;
         if (rr < r1) {
           long long off = rr * C + c0;
@@ -437,13 +462,13 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T*
         }
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < U; ++u) {
         long long rr = r + (long long)u * rowlanes;
         if (rr < r1) {
 #pragma unroll
           for (int i = 0; i < V; ++i) {
             float xv = a[u].get(i);
-            float dz = dz_of<T>(g[u].get(i), xv, have_y ? o[u].get(i) : 0.f, have_y, sc[i], sf[i],
+            float dz = dz_of<T>(g[u].get(i), xv, have_y ? o[kHaveY ? u : 0].get(i) : 0.f, have_y, sc[i], sf[i],
                                 act, alpha);
             s1[i] += dz;
             s2[i] = fmaf(dz, xv, s2[i]);          // sum dz*x; turned into sum dz*xhat below
@@ -466,7 +491,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T*
   slab_finish<V, float>(sh, slab_v, rowlanes, blockIdx.x, C, sum_dz, sum_dz_xhat, xsc);
 }
 
-template <typename T>
+template <typename T, int U>
 __global__ void __launch_bounds__(512)
 bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
                     long long nvec, int cv, const float* __restrict__ mean,
@@ -490,10 +515,10 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
   const bool have_y = (y != nullptr);
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
-       v += 2 * stride) {
-    Vec16<T> g[2], a[2], o[2];
+       v += U * stride) {
+    Vec16<T> g[U], a[U], o[U];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < U; ++u) {
       long long vv = v + u * stride;
       if (vv < nvec) {
         g[u] = ld_vec_stream(dy + vv * V);
@@ -502,7 +527,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
       }
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < U; ++u) {
       long long vv = v + u * stride;
       if (vv < nvec) {
         Vec16<T> ox, orr;
@@ -653,6 +678,14 @@ extern "C" int mcn_bn_stats(int dtype, const void* x, long long rows, int C, dou
   return after_launch("bn_stats");
 }
 
+extern "C" int mcn_bn_frozen_stats(const float* moving_mean, const float* moving_var, int C, float eps,
+                                   float* mean, float* invstd, void* stream) {
+  MCN_REQUIRE(moving_mean && moving_var && mean && invstd && C > 0, "bn_frozen_stats: bad argument");
+  bn_frozen_stats_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      moving_mean, moving_var, C, eps, mean, invstd);
+  return after_launch("bn_frozen_stats");
+}
+
 extern "C" int mcn_bn_finalize(const double* sums, double count, int C, float eps, float momentum,
                                float* mean, float* invstd, float* moving_mean, float* moving_var,
                                void* stream) {
@@ -750,6 +783,29 @@ extern "C" int mcn_bn_apply_stats(int dtype, const void* x, long long rows, int 
                           act_alpha, y, fs, stream);
 }
 
+template <typename T>
+static void launch_bn_bwd_reduce(const SlabLaunch& L, size_t smem, cudaStream_t st, const void* dy, const void* x,
+                                 const void* y, long long rows, int C, const float* mean, const float* invstd,
+                                 const float* gamma, const float* beta, int act, float alpha, float* sum_dz,
+                                 float* sum_dz_xhat, const XsScratch& xsc) {
+  const T* pdy = static_cast<const T*>(dy);
+  const T* px = static_cast<const T*>(x);
+  const T* py = static_cast<const T*>(y);
+  const bool four = bn_bwd_unroll() == 4;
+  if (four && y != nullptr)
+    bn_bwd_reduce_kernel<T, 4, true><<<L.grid, 256, smem, st>>>(pdy, px, py, rows, C, L.slab_v, L.rowlanes, mean, invstd,
+                                                               gamma, beta, act, alpha, sum_dz, sum_dz_xhat, xsc);
+  else if (four)
+    bn_bwd_reduce_kernel<T, 4, false><<<L.grid, 256, smem, st>>>(pdy, px, py, rows, C, L.slab_v, L.rowlanes, mean, invstd,
+                                                                gamma, beta, act, alpha, sum_dz, sum_dz_xhat, xsc);
+  else if (y != nullptr)
+    bn_bwd_reduce_kernel<T, 2, true><<<L.grid, 256, smem, st>>>(pdy, px, py, rows, C, L.slab_v, L.rowlanes, mean, invstd,
+                                                               gamma, beta, act, alpha, sum_dz, sum_dz_xhat, xsc);
+  else
+    bn_bwd_reduce_kernel<T, 2, false><<<L.grid, 256, smem, st>>>(pdy, px, py, rows, C, L.slab_v, L.rowlanes, mean, invstd,
+                                                                gamma, beta, act, alpha, sum_dz, sum_dz_xhat, xsc);
+}
+
 extern "C" int mcn_bn_bwd_reduce(int dtype, const void* dy, const void* x, const void* y,
                                  long long rows, int C, const float* mean, const float* invstd,
                                  const float* gamma, const float* beta, int act, float act_alpha,
@@ -762,9 +818,8 @@ extern "C" int mcn_bn_bwd_reduce(int dtype, const void* dy, const void* x, const
     SlabLaunch L;
     if (plan_slab<T>(rows, C, &L, 3 * num_sms())) {
       size_t smem = 2 * (size_t)L.rowlanes * L.slab_v * Vec16<T>::N * sizeof(float);
-      bn_bwd_reduce_kernel<T><<<L.grid, 256, smem, st>>>(
-          static_cast<const T*>(dy), static_cast<const T*>(x), static_cast<const T*>(y), rows, C,
-          L.slab_v, L.rowlanes, mean, invstd, gamma, beta, act, act_alpha, sum_dz, sum_dz_xhat, xsc);
+      launch_bn_bwd_reduce<T>(L, smem, st, dy, x, y, rows, C, mean, invstd, gamma, beta, act, act_alpha,
+                              sum_dz, sum_dz_xhat, xsc);
     } else {
       MCN_REQUIRE((C + 127) / 128 <= kWsCounters, "bn_bwd_reduce: too many channels (%d)", C);
       dim3 grid((C + 127) / 128, (unsigned)std::min<long long>(rows, 4LL * num_sms()));
@@ -823,10 +878,16 @@ extern "C" int mcn_bn_bwd_apply(int dtype, const void* dy, const void* x, const 
       launch_bwd_apply_runs<T>(grid, st, dy, x, y, nvec, cvr, mean, invstd, gamma, beta, act, act_alpha,
                                sum_dz, sum_dz_xhat, inv_count, dx, d_residual, rpb);
     } else if (plan<T>(rows, C, &L, 3, 256)) {
-      bn_bwd_apply_kernel<T><<<L.grid, L.block, 0, st>>>(
-          static_cast<const T*>(dy), static_cast<const T*>(x), static_cast<const T*>(y),
-          rows * L.cv, L.cv, mean, invstd, gamma, beta, act, act_alpha, sum_dz, sum_dz_xhat,
-          inv_count, static_cast<T*>(dx), static_cast<T*>(d_residual));
+      if (bn_bwd_unroll() == 4)
+        bn_bwd_apply_kernel<T, 4><<<L.grid, L.block, 0, st>>>(
+            static_cast<const T*>(dy), static_cast<const T*>(x), static_cast<const T*>(y),
+            rows * L.cv, L.cv, mean, invstd, gamma, beta, act, act_alpha, sum_dz, sum_dz_xhat,
+            inv_count, static_cast<T*>(dx), static_cast<T*>(d_residual));
+      else
+        bn_bwd_apply_kernel<T, 2><<<L.grid, L.block, 0, st>>>(
+            static_cast<const T*>(dy), static_cast<const T*>(x), static_cast<const T*>(y),
+            rows * L.cv, L.cv, mean, invstd, gamma, beta, act, act_alpha, sum_dz, sum_dz_xhat,
+            inv_count, static_cast<T*>(dx), static_cast<T*>(d_residual));
     } else {
       long long n = rows * C;
       int grid = (int)std::min<long long>((n + 255) / 256, 8LL * num_sms());

@@ -3,11 +3,28 @@
 // (tf.nn.depthwise_conv2d, reference convnet.py:1645) and the explicit im2col used by the
 // 3-channel stems.  Dense call sites: convnet.py:1659 and its autodiff, :2463.
 // Depthwise is bandwidth-bound: threads run along the channel axis so every access is coalesced.
+#include <cstdlib>
+
 #include "mcn_common.cuh"
 #include "xsum.cuh"
 
 namespace mcn {
+// specialised depthwise kernels (dwconv.cu): multiplier 1, 3x3 / 5x5, stride 1 / 2, vector-aligned C
+bool dw_fast_eligible(const mcn_conv_desc* d, int mult, int dtype, int wdtype);
+int dw_fast_fwd(const mcn_conv_desc* d, int dtype, const void* x, const float* w, void* y, cudaStream_t st);
+int dw_fast_bwd_data(const mcn_conv_desc* d, int dtype, const void* dy, const float* w, void* dx, cudaStream_t st);
+int dw_fast_bwd_filter(const mcn_conv_desc* d, int dtype, const void* x, const void* dy, float* dw, cudaStream_t st);
+
 namespace {
+
+inline bool dw_fast_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MCN_DW_FAST");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
 
 inline int grid_for(long long n, int block) {
   return (int)std::max<long long>(1, std::min<long long>((n + block - 1) / block, 32LL * num_sms()));
@@ -113,6 +130,205 @@ __global__ void conv_wgrad_direct_kernel(mcn_conv_desc d, const T* __restrict__ 
     acc = fmaf(xv, to_f32(dy[m * d.Cout + co]), acc);
   }
   dw[blockIdx.y * slice_stride + ((long long)tap * d.Cin + ci) * d.Cout + co] = acc;
+}
+
+// ---------------------------------------------------------------- tiled implicit GEMM (CUDA cores)
+// The three kernels above walk one output element per thread; fine for a handful of tiny layers,
+// 1.1 s per step for the fp32 ResNet-50 of BASELINE config 1 and 34 ms for one 256->21 logits wgrad
+// of DeepLab.  This is the classic shared-memory tiled GEMM on the FP32 pipe (exact fp32 FMA: the
+// fp32 config stays a true fp32 path, no TF32), with the convolution's gather folded into the tile
+// loads.  C[M x Nn] = A[M x K] * B[K x Nn]:
+//   fprop: M = pixels of y,  Nn = Cout, K = taps*Cin ; A = x gathered, B = w[k][co]
+//   dgrad: M = pixels of dx, Nn = Cin,  K = taps*Cout; A = dy gathered (exact stride divisions), B = w
+//   wgrad: M = taps*Cin,     Nn = Cout, K = pixels   ; A = x gathered, B = dy; K is split over
+//          gridDim.z chunks, each writing its own slice (summed in order by splitk_reduce).
+// 256 threads, BM = 64 rows x BN = 16*TN columns x BK = 16; a thread owns a 4 x TN micro-tile.
+constexpr int kIgBM = 64, kIgBK = 16;
+enum { kIgFprop = 0, kIgDgrad = 1, kIgWgrad = 2 };
+
+template <typename T, typename TW, int MODE, int TN>
+__global__ void __launch_bounds__(256)
+igemm_kernel(mcn_conv_desc d, const T* __restrict__ a_src, const void* __restrict__ b_src,
+             const float* __restrict__ bias, void* __restrict__ out, long long slice_stride) {
+  constexpr int BN = 16 * TN;
+  __shared__ float As[kIgBK][kIgBM + 4];
+  __shared__ float Bs[kIgBK][BN + 4];
+  const int taps = d.kh * d.kw;
+  const long long pix_out = (long long)d.N * d.Ho * d.Wo, pix_in = (long long)d.N * d.H * d.W;
+  const long long M = MODE == kIgFprop ? pix_out : (MODE == kIgDgrad ? pix_in : (long long)taps * d.Cin);
+  const int Nn = MODE == kIgDgrad ? d.Cin : d.Cout;
+  const long long Kall = MODE == kIgFprop ? (long long)taps * d.Cin
+                                          : (MODE == kIgDgrad ? (long long)taps * d.Cout : pix_out);
+  const long long k_begin = MODE == kIgWgrad ? Kall * blockIdx.z / gridDim.z : 0;
+  const long long k_end = MODE == kIgWgrad ? Kall * (blockIdx.z + 1) / gridDim.z : Kall;
+  const long long m0 = (long long)blockIdx.x * kIgBM;
+  const int n0 = blockIdx.y * BN;
+  const int t = threadIdx.x;
+  const int tx = t % 16, ty = t / 16;
+  // ---- A-tile load pattern: the memory-contiguous index varies fastest across threads
+  constexpr bool kAlongK = MODE != kIgWgrad;          // fprop/dgrad: k = channels contiguous
+  const int a_k = kAlongK ? t % kIgBK : t / kIgBM;    // + 4*i for wgrad
+  const int a_m = kAlongK ? t / kIgBK : t % kIgBM;    // + 16*i for fprop/dgrad
+  // per-thread decode of the rows it loads (constant over the K loop)
+  int r_n[4], r_h[4], r_w[4];
+  bool r_ok[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long m = m0 + (kAlongK ? a_m + 16 * i : a_m);
+    r_ok[i] = m < M;
+    r_n[i] = r_h[i] = r_w[i] = 0;
+    if (!r_ok[i]) continue;
+    if (MODE == kIgFprop) {
+      const int q = (int)(m % d.Wo);
+      const long long r = m / d.Wo;
+      r_h[i] = (int)(r % d.Ho) * d.sh - d.pad_t;
+      r_w[i] = q * d.sw - d.pad_l;
+      r_n[i] = (int)(r / d.Ho);
+    } else if (MODE == kIgDgrad) {
+      const int w = (int)(m % d.W);
+      const long long r = m / d.W;
+      r_h[i] = (int)(r % d.H) + d.pad_t;
+      r_w[i] = w + d.pad_l;
+      r_n[i] = (int)(r / d.H);
+    } else {   // wgrad: one row per thread: (tap, ci)
+      const int tap = (int)(m / d.Cin);
+      r_n[i] = (int)(m % d.Cin);                       // ci
+      r_h[i] = (tap / d.kw) * d.dh - d.pad_t;          // tap offset
+      r_w[i] = (tap % d.kw) * d.dw - d.pad_l;
+    }
+  }
+  // ---- B-tile load pattern
+  constexpr bool kBAlongN = MODE != kIgDgrad;         // fprop: w[k][co]; wgrad: dy[pix][co]
+  const int b_n = kBAlongN ? t % BN : t / kIgBK;      // dgrad: + 16*i
+  const int b_k = kBAlongN ? t / BN : t % kIgBK;      // fprop/wgrad: + (256/BN)*i
+  constexpr int kBRep = (kIgBK * BN) / 256;           // elements per thread (4 for BN 64, 1 for BN 16)
+  float acc[4][TN];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  for (long long k0 = k_begin; k0 < k_end; k0 += kIgBK) {
+    // ---- A tile
+    if (kAlongK) {
+      const long long k = k0 + a_k;
+      const bool kok = k < k_end;
+      const int cdim = MODE == kIgFprop ? d.Cin : d.Cout;
+      const int tap = kok ? (int)(k / cdim) : 0, c = kok ? (int)(k % cdim) : 0;
+      const int ta = tap / d.kw, tb = tap % d.kw;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float v = 0.f;
+        if (kok && r_ok[i]) {
+          if (MODE == kIgFprop) {
+            const int h = r_h[i] + ta * d.dh, w = r_w[i] + tb * d.dw;
+            if (h >= 0 && h < d.H && w >= 0 && w < d.W)
+              v = to_f32(a_src[(((long long)r_n[i] * d.H + h) * d.W + w) * d.Cin + c]);
+          } else {
+            const int hp = r_h[i] - ta * d.dh, wq = r_w[i] - tb * d.dw;
+            if (hp >= 0 && wq >= 0 && hp % d.sh == 0 && wq % d.sw == 0) {
+              const int p = hp / d.sh, q = wq / d.sw;
+              if (p < d.Ho && q < d.Wo)
+                v = to_f32(a_src[(((long long)r_n[i] * d.Ho + p) * d.Wo + q) * d.Cout + c]);
+            }
+          }
+        }
+        As[a_k][a_m + 16 * i] = v;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const long long k = k0 + a_k + 4 * i;          // output pixel
+        float v = 0.f;
+        if (k < k_end && r_ok[0]) {
+          const int q = (int)(k % d.Wo);
+          const long long r = k / d.Wo;
+          const int p = (int)(r % d.Ho);
+          const int n = (int)(r / d.Ho);
+          const int h = p * d.sh + r_h[0], w = q * d.sw + r_w[0];
+          if (h >= 0 && h < d.H && w >= 0 && w < d.W)
+            v = to_f32(a_src[(((long long)n * d.H + h) * d.W + w) * d.Cin + r_n[0]]);
+        }
+        As[a_k + 4 * i][a_m] = v;
+      }
+    }
+    // ---- B tile
+#pragma unroll
+    for (int i = 0; i < kBRep; ++i) {
+      float v = 0.f;
+      if (kBAlongN) {
+        const long long k = k0 + b_k + (256 / BN) * i;
+        const int n = n0 + b_n;
+        if (k < k_end && n < Nn) {
+          if (MODE == kIgFprop) v = to_f32(static_cast<const TW*>(b_src)[k * d.Cout + n]);
+          else v = to_f32(static_cast<const T*>(b_src)[k * d.Cout + n]);
+        }
+        Bs[b_k + (256 / BN) * i][b_n] = v;
+      } else {
+        const long long k = k0 + b_k;                  // (tap, co)
+        const int n = n0 + b_n + 16 * i;               // ci
+        if (k < k_end && n < Nn) {
+          const int tap = (int)(k / d.Cout), co = (int)(k % d.Cout);
+          v = to_f32(static_cast<const TW*>(b_src)[((long long)tap * d.Cin + n) * d.Cout + co]);
+        }
+        if (b_n + 16 * i < BN) Bs[b_k][b_n + 16 * i] = v;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kIgBK; ++kk) {
+      float av[4], bv[TN];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) bv[j] = Bs[kk][tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  // ---- epilogue
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + tx * TN + j;
+      if (n >= Nn) continue;
+      if (MODE == kIgWgrad)
+        static_cast<float*>(out)[(long long)blockIdx.z * slice_stride + m * d.Cout + n] = acc[i][j];
+      else
+        static_cast<T*>(out)[m * Nn + n] = from_f32<T>(acc[i][j] + (MODE == kIgFprop && bias ? bias[n] : 0.f));
+    }
+  }
+}
+
+template <typename T, typename TW, int MODE>
+void launch_igemm(const mcn_conv_desc* d, const void* a, const void* b, const float* bias, void* out,
+                  long long slice_stride, int zchunks, cudaStream_t st) {
+  const int taps = d->kh * d->kw;
+  const long long M = MODE == kIgFprop ? (long long)d->N * d->Ho * d->Wo
+                                       : (MODE == kIgDgrad ? (long long)d->N * d->H * d->W : (long long)taps * d->Cin);
+  const int Nn = MODE == kIgDgrad ? d->Cin : d->Cout;
+  if (Nn <= 16) {
+    dim3 grid((unsigned)((M + kIgBM - 1) / kIgBM), (unsigned)((Nn + 15) / 16), (unsigned)zchunks);
+    igemm_kernel<T, TW, MODE, 1><<<grid, 256, 0, st>>>(*d, static_cast<const T*>(a), b, bias, out, slice_stride);
+  } else {
+    dim3 grid((unsigned)((M + kIgBM - 1) / kIgBM), (unsigned)((Nn + 63) / 64), (unsigned)zchunks);
+    igemm_kernel<T, TW, MODE, 4><<<grid, 256, 0, st>>>(*d, static_cast<const T*>(a), b, bias, out, slice_stride);
+  }
+}
+
+inline bool igemm_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MCN_DIRECT_IGEMM");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
 }
 
 // ---------------------------------------------------------------- depthwise
@@ -308,6 +524,11 @@ extern "C" int mcn_conv2d_fprop_direct(const mcn_conv_desc* d, int dtype, const 
                                        void* stream) {
   MCN_REQUIRE(d && x && w && y, "fprop_direct: null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (igemm_enabled() && d->Cout >= 8) {
+    MCN_DISPATCH_DTYPE(dtype, T, MCN_DISPATCH_W(wdtype, TW,
+                                                (launch_igemm<T, TW, kIgFprop>(d, x, w, bias, y, 0, 1, st))));
+    return after_launch("conv_fprop_direct");
+  }
   MCN_DISPATCH_DTYPE(dtype, T, MCN_DISPATCH_W(wdtype, TW, {
     if (d->Cout % 4 == 0) {
       long long total = (long long)d->N * d->Ho * d->Wo * (d->Cout / 4);
@@ -326,6 +547,11 @@ extern "C" int mcn_conv2d_dgrad_direct(const mcn_conv_desc* d, int dtype, const 
                                        int wdtype, const void* w, void* dx, void* stream) {
   MCN_REQUIRE(d && dy && w && dx, "dgrad_direct: null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (igemm_enabled() && d->Cin >= 8) {
+    MCN_DISPATCH_DTYPE(dtype, T, MCN_DISPATCH_W(wdtype, TW,
+                                                (launch_igemm<T, TW, kIgDgrad>(d, dy, w, nullptr, dx, 0, 1, st))));
+    return after_launch("conv_dgrad_direct");
+  }
   long long total = (long long)d->N * d->H * d->W * d->Cin;
   MCN_DISPATCH_DTYPE(dtype, T, MCN_DISPATCH_W(wdtype, TW, {
     conv_dgrad_direct_kernel<T, TW><<<grid_for(total, 128), 128, 0, st>>>(
@@ -354,6 +580,16 @@ extern "C" int mcn_conv2d_wgrad_direct(const mcn_conv_desc* d, int dtype, const 
               w.bytes, kWsSplitOff + stride * 4);
   chunks = std::min(chunks, cap);
   float* slices = reinterpret_cast<float*>(w.base + kWsSplitOff);
+  if (igemm_enabled()) {
+    // tiled implicit GEMM: enough K chunks to fill the GPU about twice
+    const long long tiles = ((long long)d->kh * d->kw * d->Cin + kIgBM - 1) / kIgBM * ((d->Cout + 63) / 64);
+    long long z = std::max<long long>(1, std::min<long long>((2LL * num_sms() + tiles - 1) / tiles, pixels / 256 + 1));
+    z = std::min(z, std::min<long long>(cap, 65535));
+    MCN_DISPATCH_DTYPE(dtype, T, (launch_igemm<T, float, kIgWgrad>(d, x, dy, nullptr, slices, stride, (int)z, st)));
+    int rc0 = after_launch("conv_wgrad_direct");
+    if (rc0) return rc0;
+    return launch_splitk_reduce(slices, stride, (int)z, n, dw, st);
+  }
   dim3 grid((unsigned)gx, (unsigned)chunks);
   MCN_DISPATCH_DTYPE(dtype, T, {
     conv_wgrad_direct_kernel<T><<<grid, block, 0, st>>>(*d, static_cast<const T*>(x),
@@ -368,6 +604,8 @@ extern "C" int mcn_dwconv2d_fwd(const mcn_conv_desc* d, int mult, int dtype, con
                                 int wdtype, const void* w, void* y, void* stream) {
   MCN_REQUIRE(d && x && w && y && mult >= 1, "dwconv_fwd: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dw_fast_enabled() && dw_fast_eligible(d, mult, dtype, wdtype))
+    return dw_fast_fwd(d, dtype, x, static_cast<const float*>(w), y, st);
   long long total = (long long)d->N * d->Ho * d->Wo * d->Cin * mult;
   MCN_DISPATCH_DTYPE(dtype, T, MCN_DISPATCH_W(wdtype, TW, {
     dwconv_fwd_kernel<T, TW><<<grid_for(total, 256), 256, 0, st>>>(
@@ -379,6 +617,8 @@ extern "C" int mcn_dwconv2d_bwd_data(const mcn_conv_desc* d, int mult, int dtype
                                      int wdtype, const void* w, void* dx, void* stream) {
   MCN_REQUIRE(d && dy && w && dx && mult >= 1, "dwconv_bwd_data: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dw_fast_enabled() && dw_fast_eligible(d, mult, dtype, wdtype))
+    return dw_fast_bwd_data(d, dtype, dy, static_cast<const float*>(w), dx, st);
   long long total = (long long)d->N * d->H * d->W * d->Cin;
   MCN_DISPATCH_DTYPE(dtype, T, MCN_DISPATCH_W(wdtype, TW, {
     dwconv_bwd_data_kernel<T, TW><<<grid_for(total, 256), 256, 0, st>>>(
@@ -390,6 +630,8 @@ extern "C" int mcn_dwconv2d_bwd_filter(const mcn_conv_desc* d, int mult, int dty
                                        const void* dy, float* dw, void* stream) {
   MCN_REQUIRE(d && x && dy && dw && mult >= 1, "dwconv_bwd_filter: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dw_fast_enabled() && dw_fast_eligible(d, mult, dtype, MCN_F32))
+    return dw_fast_bwd_filter(d, dtype, x, dy, dw, st);
   const int Co = d->Cin * mult;
   const long long pixels = (long long)d->N * d->Ho * d->Wo;
   const long long gx = (Co + 31) / 32, taps = (long long)d->kh * d->kw;

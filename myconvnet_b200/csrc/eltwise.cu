@@ -144,12 +144,27 @@ __global__ void cast_kernel(const TS* __restrict__ s, TD* __restrict__ d, long l
        i += (long long)gridDim.x * blockDim.x)
     d[i] = from_f32<TD>(to_f32(s[i]));
 }
-template <typename TD>
-__global__ void input_prep_kernel(const float* __restrict__ x, long long n, float mean, float scale,
-                                  TD* __restrict__ y) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x)
-    y[i] = from_f32<TD>((x[i] - mean) * scale);
+// Network input prologue (reference convnet.py:449-471): images arrive as fp32 in [0,1] or as raw
+// uint8 (then /255 first), [N, Hi, Wi, C]; centre crop to [N, H, W, C] with offsets (Hi-H)//2,
+// (Wi-W)//2 (convnet.py:1137-1149; a no-op when the sizes agree), zero-centre, scale, cast.
+template <typename TS, typename TD>
+__global__ void input_prep_kernel(const TS* __restrict__ x, int N, int Hi, int Wi, int H, int W, int C,
+                                  float mean, float scale, TD* __restrict__ y) {
+  const int oh = (Hi - H) / 2, ow = (Wi - W) / 2;
+  const long long row = (long long)W * C;
+  const long long total = (long long)N * H * row;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / row;              // n*H + h
+    const long long e = i - r * row;
+    const int h = static_cast<int>(r % H);
+    const long long n = r / H;
+    const long long src = ((n * Hi + h + oh) * Wi + ow) * C + e;
+    float v;
+    if (sizeof(TS) == 1) v = static_cast<float>(x[src]) * (1.f / 255.f);
+    else v = static_cast<float>(x[src]);
+    y[i] = from_f32<TD>((v - mean) * scale);
+  }
 }
 
 template <typename T>
@@ -373,15 +388,54 @@ extern "C" int mcn_cast(int src_dtype, const void* src, int dst_dtype, void* dst
   return after_launch("cast");
 }
 
-extern "C" int mcn_input_prep(const float* x, long long n, float mean, float scale, int dst_dtype,
-                              void* y, void* stream) {
-  MCN_REQUIRE(x && y, "input_prep: bad argument");
+// No crop: a flat element-wise map, 16 input elements per thread (one 16-byte load of uint8).
+template <typename TD>
+__global__ void input_prep_u8_flat_kernel(const uint4* __restrict__ x, long long n16, float mean, float scale,
+                                          TD* __restrict__ y) {
+  const float k = scale * (1.f / 255.f), b = -mean * scale;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16;
+       i += (long long)gridDim.x * blockDim.x) {
+    const uint4 v = x[i];
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    Vec16<TD> o[16 / Vec16<TD>::N];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int idx = j * 4 + e;
+        o[idx / Vec16<TD>::N].set(idx % Vec16<TD>::N,
+                                  fmaf(static_cast<float>((w[j] >> (8 * e)) & 255u), k, b));
+      }
+#pragma unroll
+    for (int q = 0; q < 16 / Vec16<TD>::N; ++q) st_vec(y + i * 16 + q * Vec16<TD>::N, o[q]);
+  }
+}
+
+extern "C" int mcn_input_prep(const void* x, int src_dtype, int N, int Hi, int Wi, int H, int W, int C,
+                              float mean, float scale, int dst_dtype, void* y, void* stream) {
+  MCN_REQUIRE(x && y && N > 0 && H > 0 && W > 0 && C > 0 && Hi >= H && Wi >= W, "input_prep: bad argument");
+  MCN_REQUIRE(src_dtype == MCN_F32 || src_dtype == MCN_U8, "input_prep: images are fp32 or uint8");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int g = grid_for(n, 256);
-  if (dst_dtype == MCN_F32)
-    input_prep_kernel<float><<<g, 256, 0, st>>>(x, n, mean, scale, (float*)y);
-  else
-    input_prep_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(x, n, mean, scale, (__nv_bfloat16*)y);
+  const long long n = (long long)N * H * W * C;
+  const int g = grid_for(n, 256);
+  if (src_dtype == MCN_F32) {
+    if (dst_dtype == MCN_F32)
+      input_prep_kernel<float, float><<<g, 256, 0, st>>>((const float*)x, N, Hi, Wi, H, W, C, mean, scale, (float*)y);
+    else
+      input_prep_kernel<float, __nv_bfloat16><<<g, 256, 0, st>>>((const float*)x, N, Hi, Wi, H, W, C, mean, scale,
+                                                               (__nv_bfloat16*)y);
+  } else if (Hi == H && Wi == W && n % 16 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0 &&
+             reinterpret_cast<uintptr_t>(y) % 16 == 0 && dst_dtype == MCN_BF16) {
+    input_prep_u8_flat_kernel<__nv_bfloat16><<<grid_for(n / 16, 256), 256, 0, st>>>(
+        (const uint4*)x, n / 16, mean, scale, (__nv_bfloat16*)y);
+  } else {
+    if (dst_dtype == MCN_F32)
+      input_prep_kernel<uint8_t, float><<<g, 256, 0, st>>>((const uint8_t*)x, N, Hi, Wi, H, W, C, mean, scale,
+                                                         (float*)y);
+    else
+      input_prep_kernel<uint8_t, __nv_bfloat16><<<g, 256, 0, st>>>((const uint8_t*)x, N, Hi, Wi, H, W, C, mean,
+                                                                 scale, (__nv_bfloat16*)y);
+  }
   return after_launch("input_prep");
 }
 

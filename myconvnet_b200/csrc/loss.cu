@@ -12,9 +12,47 @@ namespace {
 
 // One warp per row.  labels[r] < 0 (or >= C) is the reference's all-zero one-hot row: the row is
 // invalid, its loss and gradient are zero (convnet.py:448-449, 567-573).
+//
+// Targets t_c (convnet.py:574-577, 603-607; segmentation/segnet.py:116-121):
+//   seg_h == 0 : t = onehot*(1-ls) + ls/C                          (classification)
+//   seg_h  > 0 : t = onehot*(1-ls) + ls*avg5x5(onehot)             (rows are pixels of [N,seg_h,seg_w]
+//                maps; tf.nn.avg_pool2d SAME divides by the in-bounds window size, ignored pixels
+//                are zero rows of the one-hot map) — computed on the fly from the label map.
+// CE = -sum_c t_c log p_c = lse*sum(t) - sum_c t_c z_c (targets need not sum to one).
+// Focal variants (convnet.py:580-592), p_y = softmax probability of the TRUE class:
+//   focal_gamma > 0 : CE *= (1 - p_y)^gamma                         (differentiated through)
+//   sig_alpha   > 0 : CE *= stop_gradient(1 - sigmoid(alpha*(p_y - 0.5))) / (1 - sigmoid(-alpha/2))
+struct XentOpts {
+  float ls, focal_gamma, sig_alpha;
+  int seg_h, seg_w;
+};
+
+__device__ __forceinline__ float xent_target(const XentOpts& o, const int32_t* __restrict__ labels,
+                                             long long r, int y, int c, int C) {
+  const float hot = (c == y) ? 1.f - o.ls : 0.f;
+  if (o.ls <= 0.f) return hot;
+  if (o.seg_h == 0) return hot + o.ls / static_cast<float>(C);
+  const int w = static_cast<int>(r % o.seg_w);
+  const long long q = r / o.seg_w;
+  const int h = static_cast<int>(q % o.seg_h);
+  const long long img = (q / o.seg_h) * o.seg_h * o.seg_w;
+  int cnt = 0, nvalid = 0;
+  for (int dy = -2; dy <= 2; ++dy) {
+    const int hh = h + dy;
+    if (hh < 0 || hh >= o.seg_h) continue;
+    for (int dx = -2; dx <= 2; ++dx) {
+      const int ww = w + dx;
+      if (ww < 0 || ww >= o.seg_w) continue;
+      ++nvalid;
+      cnt += (labels[img + static_cast<long long>(hh) * o.seg_w + ww] == c) ? 1 : 0;
+    }
+  }
+  return hot + o.ls * static_cast<float>(cnt) / static_cast<float>(nvalid);
+}
+
 __global__ void softmax_xent_kernel(const float* __restrict__ logits,
                                     const int32_t* __restrict__ labels, long long rows, int C,
-                                    const float* __restrict__ class_w, float ls, float grad_scale,
+                                    const float* __restrict__ class_w, XentOpts o, float grad_scale,
                                     long long* __restrict__ loss_xs, float* __restrict__ dlogits,
                                     float* __restrict__ probs) {
   const int lane = threadIdx.x & 31;
@@ -26,7 +64,7 @@ __global__ void softmax_xent_kernel(const float* __restrict__ logits,
     float mx = -FLT_MAX;
     for (int c = lane; c < C; c += 32) mx = fmaxf(mx, z[c]);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    for (int s = 16; s > 0; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
     float se = 0.f;
     for (int c = lane; c < C; c += 32) se += __expf(z[c] - mx);
     se = warp_sum(se);
@@ -34,24 +72,46 @@ __global__ void softmax_xent_kernel(const float* __restrict__ logits,
     const int y = labels ? labels[r] : -1;
     const bool valid = (y >= 0 && y < C);
     const float w = valid ? (class_w ? class_w[y] : 1.f) : 0.f;
-    // smoothed target t_c = onehot*(1-ls) + ls/C  (convnet.py:606); sum_c t_c = 1
-    // CE = -sum_c t_c (z_c - lse) = lse - (1-ls) z_y - (ls/C) sum_c z_c
-    float sz = 0.f;
-    if (ls > 0.f) {
-      for (int c = lane; c < C; c += 32) sz += z[c];
-      sz = warp_sum(sz);
-    }
-    if (valid && lane == 0) {
-      float ce = lse - (1.f - ls) * z[y] - (ls > 0.f ? ls / (float)C * sz : 0.f);
-      block_loss += w * ce;
-    }
     const float inv_se = 1.f / se;
+    float ce = 0.f, st = 1.f, f_mul = 1.f, df = 0.f, s_mul = 1.f, py = 0.f;
+    if (valid) {
+      // sum_c t_c and sum_c t_c z_c
+      float a = 0.f, b = 0.f;
+      if (o.ls > 0.f) {
+        for (int c = lane; c < C; c += 32) {
+          const float t = xent_target(o, labels, r, y, c, C);
+          a += t;
+          b = fmaf(t, z[c], b);
+        }
+        a = warp_sum(a);
+        b = warp_sum(b);
+      } else {
+        a = 1.f;
+        b = z[y];
+      }
+      st = a;
+      ce = lse * a - b;
+      py = __expf(z[y] - mx) * inv_se;
+      if (o.focal_gamma > 0.f) {
+        const float om = fmaxf(1.f - py, 1e-12f);
+        f_mul = __powf(om, o.focal_gamma);
+        df = -o.focal_gamma * __powf(om, o.focal_gamma - 1.f) * py;      // dF/dz_c = df * ((c==y) - p_c)
+      }
+      if (o.sig_alpha > 0.f)
+        s_mul = (1.f - 1.f / (1.f + __expf(-o.sig_alpha * (py - 0.5f)))) /
+                (1.f - 1.f / (1.f + __expf(0.5f * o.sig_alpha)));
+      if (lane == 0) block_loss += w * ce * f_mul * s_mul;
+    }
     for (int c = lane; c < C; c += 32) {
-      float p = __expf(z[c] - mx) * inv_se;
+      const float p = __expf(z[c] - mx) * inv_se;
       if (probs) probs[r * C + c] = p;
       if (dlogits) {
-        float t = (c == y ? 1.f - ls : 0.f) + ls / (float)C;
-        dlogits[r * C + c] = grad_scale * w * (p - t);
+        float g = 0.f;
+        if (valid) {
+          const float t = xent_target(o, labels, r, y, c, C);
+          g = f_mul * (p * st - t) + ce * df * ((c == y ? 1.f : 0.f) - p);
+        }
+        dlogits[r * C + c] = grad_scale * w * s_mul * g;
       }
     }
   }
@@ -82,13 +142,17 @@ __global__ void sigmoid_xent_kernel(const float* __restrict__ logits, long long 
 using namespace mcn;
 
 extern "C" int mcn_softmax_xent(const float* logits, const int32_t* labels, long long rows, int C,
-                                const float* class_w, float label_smoothing, float grad_scale,
+                                const float* class_w, float label_smoothing, float focal_gamma,
+                                float sigmoid_focal_alpha, int seg_h, int seg_w, float grad_scale,
                                 long long* loss_xs, float* dlogits, float* probs, void* stream) {
   MCN_REQUIRE(logits && rows > 0 && C > 0, "softmax_xent: bad argument");
+  MCN_REQUIRE(seg_h >= 0 && seg_w >= 0 && (seg_h == 0 || (seg_w > 0 && rows % ((long long)seg_h * seg_w) == 0)),
+              "softmax_xent: rows must be whole [seg_h, seg_w] label maps");
+  XentOpts o{label_smoothing, focal_gamma, sigmoid_focal_alpha, seg_h, seg_w};
   const int wpb = 8;
   int grid = (int)std::max<long long>(1, std::min<long long>((rows + wpb - 1) / wpb, 8LL * num_sms()));
   softmax_xent_kernel<<<grid, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      logits, labels, rows, C, class_w, label_smoothing, grad_scale, loss_xs, dlogits, probs);
+      logits, labels, rows, C, class_w, o, grad_scale, loss_xs, dlogits, probs);
   return after_launch("softmax_xent");
 }
 

@@ -28,7 +28,8 @@ grad_sqnorm_kernel(const mcn_opt_tensor* __restrict__ table, const float* __rest
   for (int k = 0; k < kItems; ++k) {
     const long long i = base + k * kBlock + threadIdx.x;
     if (i < t.n) {
-      const float g = t.g[i] * gscale + t.l2 * t.w[i];
+      const float wv = t.w[i];
+      const float g = t.g[i] * gscale + t.l2 * wv + t.l1 * (wv > 0.f ? 1.f : (wv < 0.f ? -1.f : 0.f));
       acc = fmaf(g, g, acc);
     }
   }
@@ -46,6 +47,8 @@ grad_sqnorm_kernel(const mcn_opt_tensor* __restrict__ table, const float* __rest
 
 // hp: [0] lr  [1] momentum|beta1  [2] decay|beta2  [3] eps  [4] ema decay d_t
 //     [5] adam lr_t  [6] gradient scale  [7] weight-decay multiplier  [8] clip threshold
+//     [9] decoupled weight-decay form: 0 = w -= wd*w, 1 = w -= wd*sign(w) (l1_weight_decay),
+//         2 = w -= wd*w/sqrt(1+(w/delta)^2) (pseudo-Huber, optimizers.py:165-171)  [10] Huber delta
 __global__ void __launch_bounds__(kBlock)
 opt_step_kernel(int kind, const mcn_opt_tensor* __restrict__ table, const float* __restrict__ hp,
                 long long* __restrict__ l2_xs, const long long* __restrict__ grad_sqnorm_xs) {
@@ -54,25 +57,29 @@ opt_step_kernel(int kind, const mcn_opt_tensor* __restrict__ table, const float*
   if (base >= t.n) return;
   const float lr = hp[0], mom = hp[1], b2 = hp[2], eps = hp[3], ema_d = hp[4], adam_lr = hp[5],
               gscale = hp[6], wd = t.wd * hp[7];
+  const int wd_form = static_cast<int>(hp[9]);
+  const float huber_delta = hp[10];
   // tf.clip_by_global_norm: g * clip / max(global_norm, clip)
   float clip = 1.f;
   if (grad_sqnorm_xs != nullptr) {
     const float thr = hp[8];
     clip = thr / fmaxf(static_cast<float>(sqrt(xs::read(grad_sqnorm_xs, 1, 0))), thr);
   }
-  float l2_acc = 0.f;  // l2 * sum(w^2)/2 over the PRE-step weights (tf.nn.l2_loss, convnet.py:563)
+  // regularisation loss over the PRE-step weights: l2 * sum(w^2)/2 (tf.nn.l2_loss, convnet.py:563)
+  // + l1 * sum|w| (convnet.py:557)
+  float l2_acc = 0.f;
 #pragma unroll
   for (int k = 0; k < kItems; ++k) {
     const long long i = base + k * kBlock + threadIdx.x;
     if (i >= t.n) continue;
     float w = t.w[i];
-    l2_acc = fmaf(0.5f * t.l2 * w, w, l2_acc);
+    l2_acc = fmaf(0.5f * t.l2 * w, w, l2_acc) + t.l1 * fabsf(w);
     if (t.ema) {
       float s = t.ema[i];
       t.ema[i] = s - (1.f - ema_d) * (s - w);
     }
     if (t.g != nullptr) {
-      float g = (t.g[i] * gscale + t.l2 * w) * clip;
+      float g = (t.g[i] * gscale + t.l2 * w + t.l1 * (w > 0.f ? 1.f : (w < 0.f ? -1.f : 0.f))) * clip;
       if (kind == MCN_OPT_NESTEROV) {
         float a = mom * t.m[i] + g;
         t.m[i] = a;
@@ -90,7 +97,11 @@ opt_step_kernel(int kind, const mcn_opt_tensor* __restrict__ table, const float*
         t.v[i] = v;
         w -= adam_lr * m / (sqrtf(v) + eps);
       }
-      if (wd != 0.f) w -= wd * w;
+      if (wd != 0.f) {
+        if (wd_form == 1) w -= wd * (w > 0.f ? 1.f : (w < 0.f ? -1.f : 0.f));
+        else if (wd_form == 2) w -= wd * w / sqrtf(1.f + (w / huber_delta) * (w / huber_delta));
+        else w -= wd * w;
+      }
       t.w[i] = w;
     }
     if (t.w_bf16) reinterpret_cast<__nv_bfloat16*>(t.w_bf16)[i] = __float2bfloat16_rn(w);
@@ -104,7 +115,7 @@ opt_step_kernel(int kind, const mcn_opt_tensor* __restrict__ table, const float*
           __float2bfloat16_rn(w);
     }
   }
-  if (l2_xs != nullptr && t.l2 != 0.f) {
+  if (l2_xs != nullptr && (t.l2 != 0.f || t.l1 != 0.f)) {
     l2_acc = warp_sum(l2_acc);
     if ((threadIdx.x & 31) == 0) xs::add(l2_xs, 1, 0, l2_acc);
   }

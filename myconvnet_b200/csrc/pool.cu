@@ -159,6 +159,187 @@ __global__ void maxpool_bwd_vec_kernel(const T* __restrict__ dy, const int32_t* 
   }
 }
 
+// ---- compact-argmax max pooling (what the training step uses).
+// The int32 TF-style argmax above costs 4 bytes per output element — twice the bf16 tensor itself
+// (ResNet-50 stem pool at batch 256: 205 MB of 719 MB).  The winning position is one of kh*kw <= 255
+// taps of the window, so the step stores the TAP index a*kw + b as one byte (51 MB); the TF index is
+// (p*sh + a - pad_t)*W + (q*sw + b - pad_l))*C + c, recoverable exactly (maxpool_tap_to_argmax).
+// K / S > 0 are compile-time square kernel / stride (3/2, 2/2, 3/1: every window load is issued
+// before the first compare); K == 0 is the run-time general case.
+template <typename T, int V, int K, int S>
+__global__ void __launch_bounds__(256)
+maxpool_fwd_tap_kernel(const T* __restrict__ x, int N, int H, int W, int C, int kh_, int kw_, int sh_, int sw_,
+                       int pad_t, int pad_l, int Ho, int Wo, T* __restrict__ y, uint8_t* __restrict__ tap) {
+  const int kh = K ? K : kh_, kw = K ? K : kw_, sh = S ? S : sh_, sw = S ? S : sw_;
+  const int cv = C / V;
+  const uint32_t total = (uint32_t)N * Ho * Wo * cv;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % (uint32_t)cv) * V;
+    uint32_t r = i / (uint32_t)cv;
+    const int q = (int)(r % (uint32_t)Wo);
+    r /= (uint32_t)Wo;
+    const int p = (int)(r % (uint32_t)Ho);
+    const int n = (int)(r / (uint32_t)Ho);
+    const int h0 = p * sh - pad_t, w0 = q * sw - pad_l;
+    const T* img = x + (long long)n * H * W * C + c0;
+    float best[V];
+    int bt[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      best[e] = -FLT_MAX;
+      bt[e] = -1;
+    }
+    if (K > 0) {
+      constexpr int KK = K ? K * K : 1;
+      Vec16<T> t[KK];
+      bool ok[KK];
+#pragma unroll
+      for (int a = 0; a < K; ++a)
+#pragma unroll
+        for (int b = 0; b < K; ++b) {
+          const int h = h0 + a, w = w0 + b;
+          ok[a * K + b] = h >= 0 && h < H && w >= 0 && w < W;
+          if (ok[a * K + b]) t[a * K + b] = ld_vec_stream(img + ((long long)h * W + w) * C);
+        }
+#pragma unroll
+      for (int k = 0; k < K * K; ++k)
+        if (ok[k]) {
+#pragma unroll
+          for (int e = 0; e < V; ++e) {
+            const float v = t[k].get(e);
+            if (v > best[e] || bt[e] < 0) {
+              best[e] = v;
+              bt[e] = k;
+            }
+          }
+        }
+    } else {
+      for (int a = 0; a < kh; ++a) {
+        const int h = h0 + a;
+        if (h < 0 || h >= H) continue;
+        for (int b = 0; b < kw; ++b) {
+          const int w = w0 + b;
+          if (w < 0 || w >= W) continue;
+          const Vec16<T> t = ld_vec(img + ((long long)h * W + w) * C);
+#pragma unroll
+          for (int e = 0; e < V; ++e) {
+            const float v = t.get(e);
+            if (v > best[e] || bt[e] < 0) {
+              best[e] = v;
+              bt[e] = a * kw + b;
+            }
+          }
+        }
+      }
+    }
+    const long long o = (((long long)n * Ho + p) * Wo + q) * C + c0;
+    Vec16<T> ov;
+#pragma unroll
+    for (int e = 0; e < V; ++e) ov.set(e, best[e]);
+    st_vec(y + o, ov);
+    uint32_t pk[V / 4];
+#pragma unroll
+    for (int e = 0; e < V; e += 4)
+      pk[e / 4] = (uint32_t)(bt[e] & 255) | ((uint32_t)(bt[e + 1] & 255) << 8) |
+                  ((uint32_t)(bt[e + 2] & 255) << 16) | ((uint32_t)(bt[e + 3] & 255) << 24);
+    if (V == 8) *reinterpret_cast<uint2*>(tap + o) = make_uint2(pk[0], pk[1]);
+    else *reinterpret_cast<uint32_t*>(tap + o) = pk[0];
+  }
+}
+
+// Backward, gather form: an input pixel (h, w) lies in window p at tap row a = h + pad_t - p*sh;
+// it receives dy[p, q] when the stored tap equals (a, b).  One thread per input pixel x 16-byte
+// channel vector; with K, S known every candidate window's dy / tap load is issued first.
+template <typename T, int V, int K, int S>
+__global__ void __launch_bounds__(256)
+maxpool_bwd_tap_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ tap, int N, int H, int W, int C,
+                       int kh_, int kw_, int sh_, int sw_, int pad_t, int pad_l, int Ho, int Wo,
+                       T* __restrict__ dx) {
+  const int kh = K ? K : kh_, kw = K ? K : kw_, sh = S ? S : sh_, sw = S ? S : sw_;
+  constexpr int MAXW = K ? (K + S - 1) / S : 1;      // windows covering a pixel along one axis
+  const int cv = C / V;
+  const uint32_t total = (uint32_t)N * H * W * cv;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % (uint32_t)cv) * V;
+    uint32_t r = i / (uint32_t)cv;
+    const int w = (int)(r % (uint32_t)W);
+    r /= (uint32_t)W;
+    const int h = (int)(r % (uint32_t)H);
+    const int n = (int)(r / (uint32_t)H);
+    const int p_hi = (h + pad_t) / sh, q_hi = (w + pad_l) / sw;      // window with the smallest tap row/col
+    float acc[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[e] = 0.f;
+    const T* gimg = dy + (long long)n * Ho * Wo * C + c0;
+    const uint8_t* timg = tap + (long long)n * Ho * Wo * C + c0;
+    if (K > 0) {
+      Vec16<T> g[MAXW * MAXW];
+      uint2 tp[MAXW * MAXW];
+      int want[MAXW * MAXW];
+#pragma unroll
+      for (int j = 0; j < MAXW; ++j)
+#pragma unroll
+        for (int k = 0; k < MAXW; ++k) {
+          const int p = p_hi - j, q = q_hi - k;
+          const int a = h + pad_t - p * S, b = w + pad_l - q * S;
+          const bool ok = p >= 0 && p < Ho && q >= 0 && q < Wo && a < K && b < K;
+          want[j * MAXW + k] = ok ? a * K + b : -1;
+          if (ok) {
+            const long long o = ((long long)p * Wo + q) * C;
+            g[j * MAXW + k] = ld_vec_stream(gimg + o);
+            if (V == 8) tp[j * MAXW + k] = *reinterpret_cast<const uint2*>(timg + o);
+            else tp[j * MAXW + k] = make_uint2(*reinterpret_cast<const uint32_t*>(timg + o), 0u);
+          }
+        }
+      // ascending (p, q): the summation order of the int32-argmax kernel, so both agree bit for bit
+#pragma unroll
+      for (int m = MAXW * MAXW - 1; m >= 0; --m)
+        if (want[m] >= 0) {
+#pragma unroll
+          for (int e = 0; e < V; ++e) {
+            const uint32_t word = e < 4 ? tp[m].x : tp[m].y;
+            if ((int)((word >> (8 * (e & 3))) & 255u) == want[m]) acc[e] += g[m].get(e);
+          }
+        }
+    } else {
+      int p_lo = h + pad_t - kh + 1 + sh - 1;
+      p_lo = p_lo <= 0 ? 0 : p_lo / sh;
+      int q_lo = w + pad_l - kw + 1 + sw - 1;
+      q_lo = q_lo <= 0 ? 0 : q_lo / sw;
+      for (int p = p_lo; p <= min(p_hi, Ho - 1); ++p) {
+        const int a = h + pad_t - p * sh;
+        for (int q = q_lo; q <= min(q_hi, Wo - 1); ++q) {
+          const int want = a * kw + (w + pad_l - q * sw);
+          const long long o = ((long long)p * Wo + q) * C;
+          const Vec16<T> g = ld_vec(gimg + o);
+#pragma unroll
+          for (int e = 0; e < V; ++e)
+            if ((int)timg[o + e] == want) acc[e] += g.get(e);
+        }
+      }
+    }
+    Vec16<T> ov;
+#pragma unroll
+    for (int e = 0; e < V; ++e) ov.set(e, acc[e]);
+    st_vec(dx + (((long long)n * H + h) * W + w) * C + c0, ov);
+  }
+}
+
+__global__ void maxpool_tap_to_argmax_kernel(const uint8_t* __restrict__ tap, long long total, int W, int C,
+                                             int kw, int sh, int sw, int pad_t, int pad_l, int Ho, int Wo,
+                                             int32_t* __restrict__ argmax) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long r = i / C;
+    const int q = (int)(r % Wo);
+    r /= Wo;
+    const int p = (int)(r % Ho);
+    const int t = tap[i];
+    argmax[i] = ((p * sh + t / kw - pad_t) * W + (q * sw + t % kw - pad_l)) * C + c;
+  }
+}
+
 // Average pooling; SAME divides by the number of in-bounds elements.
 template <typename T>
 __global__ void avgpool_fwd_kernel(const T* __restrict__ x, int N, int H, int W, int C, int kh,
@@ -303,6 +484,67 @@ extern "C" int mcn_maxpool_bwd(int dtype, const void* dy, const int32_t* argmax,
     }
   });
   return after_launch("maxpool_bwd");
+}
+
+template <typename T, int V>
+static void launch_maxpool_tap(bool fwd, const void* in, const uint8_t* tap_in, int N, int H, int W, int C, int kh,
+                               int kw, int sh, int sw, int pad_t, int pad_l, int Ho, int Wo, void* out,
+                               uint8_t* tap_out, cudaStream_t st) {
+  const long long total = fwd ? (long long)N * Ho * Wo * (C / V) : (long long)N * H * W * (C / V);
+  const int grid = (int)std::max<long long>(1, (total + 255) / 256);
+#define MCN_POOL_CASE(KK, SS)                                                                        \
+  if (fwd)                                                                                           \
+    maxpool_fwd_tap_kernel<T, V, KK, SS><<<grid, 256, 0, st>>>(static_cast<const T*>(in), N, H, W, C, kh, kw, sh, \
+                                                             sw, pad_t, pad_l, Ho, Wo, static_cast<T*>(out), tap_out); \
+  else                                                                                               \
+    maxpool_bwd_tap_kernel<T, V, KK, SS><<<grid, 256, 0, st>>>(static_cast<const T*>(in), tap_in, N, H, W, C, kh, \
+                                                             kw, sh, sw, pad_t, pad_l, Ho, Wo, static_cast<T*>(out))
+  const bool sq = kh == kw && sh == sw;
+  if (sq && kh == 3 && sh == 2) { MCN_POOL_CASE(3, 2); }
+  else if (sq && kh == 2 && sh == 2) { MCN_POOL_CASE(2, 2); }
+  else if (sq && kh == 3 && sh == 1) { MCN_POOL_CASE(3, 1); }
+  else { MCN_POOL_CASE(0, 0); }
+#undef MCN_POOL_CASE
+}
+
+static int maxpool_tap_impl(bool fwd, int dtype, const void* in, const uint8_t* tap_in, int N, int H, int W, int C,
+                            int kh, int kw, int sh, int sw, int pad_t, int pad_l, int Ho, int Wo, void* out,
+                            uint8_t* tap_out, void* stream) {
+  MCN_REQUIRE(kh * kw <= 255, "maxpool (tap form): window of %d x %d taps does not fit a byte", kh, kw);
+  MCN_REQUIRE((long long)N * H * W * C < (1LL << 31) * 4 && (long long)N * H * W * (C / 4) < (1LL << 32) - (1 << 24),
+              "maxpool (tap form): tensor too large for 32-bit vector indexing");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MCN_DISPATCH_DTYPE(dtype, T, {
+    constexpr int V = Vec16<T>::N;
+    MCN_REQUIRE(C % V == 0, "maxpool (tap form): C=%d must be a multiple of %d", C, V);
+    launch_maxpool_tap<T, V>(fwd, in, tap_in, N, H, W, C, kh, kw, sh, sw, pad_t, pad_l, Ho, Wo, out, tap_out, st);
+  });
+  return after_launch(fwd ? "maxpool_fwd_tap" : "maxpool_bwd_tap");
+}
+
+extern "C" int mcn_maxpool_fwd_tap(int dtype, const void* x, int N, int H, int W, int C, int kh, int kw, int sh,
+                                   int sw, int pad_t, int pad_l, int Ho, int Wo, void* y, uint8_t* tap,
+                                   void* stream) {
+  MCN_REQUIRE(x && y && tap, "maxpool_fwd_tap: null argument");
+  return maxpool_tap_impl(true, dtype, x, nullptr, N, H, W, C, kh, kw, sh, sw, pad_t, pad_l, Ho, Wo, y, tap, stream);
+}
+extern "C" int mcn_maxpool_bwd_tap(int dtype, const void* dy, const uint8_t* tap, int N, int H, int W, int C,
+                                   int kh, int kw, int sh, int sw, int pad_t, int pad_l, int Ho, int Wo,
+                                   void* dx, void* stream) {
+  MCN_REQUIRE(dy && dx && tap, "maxpool_bwd_tap: null argument");
+  return maxpool_tap_impl(false, dtype, dy, tap, N, H, W, C, kh, kw, sh, sw, pad_t, pad_l, Ho, Wo, dx, nullptr,
+                          stream);
+}
+extern "C" int mcn_maxpool_tap_to_argmax(const uint8_t* tap, int N, int H, int W, int C, int kh, int kw, int sh,
+                                         int sw, int pad_t, int pad_l, int Ho, int Wo, int32_t* argmax,
+                                         void* stream) {
+  MCN_REQUIRE(tap && argmax && kw > 0, "maxpool_tap_to_argmax: bad argument");
+  (void)H;
+  (void)kh;
+  const long long total = (long long)N * Ho * Wo * C;
+  maxpool_tap_to_argmax_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      tap, total, W, C, kw, sh, sw, pad_t, pad_l, Ho, Wo, argmax);
+  return after_launch("maxpool_tap_to_argmax");
 }
 
 extern "C" int mcn_avgpool_fwd(int dtype, const void* x, int N, int H, int W, int C, int kh,

@@ -86,13 +86,16 @@ class Engine(object):
         self.bias_norm_decay = bool(self.kw.get("bias_norm_decay", False))
         self.base_wd = float(self.kw.get("base_weight_decay", 0.0)) * self.global_batch / 256
         self.wd_scheduling = bool(self.kw.get("weight_decay_scheduling", True))
-        if self.kw.get("l1_weight_decay", False) or self.kw.get("huber_decay_delta", None) is not None:
-            raise NotImplementedError("l1 / pseudo-Huber weight decay variants are not supported")
+        # decoupled weight-decay form (optimizers.py:163-172): w -= wd*w | wd*sign(w) | pseudo-Huber
+        self.huber_delta = self.kw.get("huber_decay_delta", None)
+        self.wd_form = 2 if self.huber_delta is not None else (1 if self.kw.get("l1_weight_decay", False) else 0)
+        self.l1 = float(self.kw.get("l1_reg", 0.0)) if getattr(model, "uses_l2", True) else 0.0
         # tf.clip_by_global_norm on the gradient of the full loss (optimizers.py:112-113); with
         # several GPUs it is applied to the rank-averaged gradient (one tower at the global batch)
         gt = self.kw.get("gradient_threshold", None)
         self.grad_threshold = None if gt is None else float(gt)
-        self.hp_host = torch.zeros(16, dtype=torch.float32).pin_memory()
+        self.random_seed = int(self.kw.get("random_seed", seed))
+        self._pin_rings = {}
         self.hp_dev = self.view(Ptr(p.b_hp), 16, torch.float32)
         self._ws = _lib.ensure_workspace(self._workspace_bytes(), self.device)
         self._build_opt_table()
@@ -135,7 +138,7 @@ class Engine(object):
 
     def tensor_view(self, t, stored_dtype=None):
         dt = stored_dtype or self.plan._logits_dtype(t)
-        tdt = {"f32": torch.float32, "bf16": torch.bfloat16, "i32": torch.int32}[dt]
+        tdt = {"f32": torch.float32, "bf16": torch.bfloat16, "i32": torch.int32, "u8": torch.uint8}[dt]
         return self.view(self.plan.tbuf[t], t.size, tdt).view(*t.shape) if t.shape else \
             self.view(self.plan.tbuf[t], 1, tdt)
 
@@ -341,6 +344,22 @@ class Engine(object):
         t = getattr(self.model, fetch) if isinstance(fetch, str) else fetch
         return self.fetch(t)
 
+    def maxpool_argmax(self, node):
+        """TF-convention argmax (h*W + w)*C + c of a max_pool node of the last forward pass, int32
+        numpy [N,Ho,Wo,C] (tf.nn.max_pool_with_argmax without the batch term)."""
+        x, y = node.inputs[0], node.outputs[0]
+        a = node.attrs
+        n, h, w, c = x.shape
+        _, ho, wo, _ = y.shape
+        if not a.get("tap_form"):
+            return self.view(Ptr(a["argmax"]), y.size, torch.int32).cpu().numpy().reshape(y.shape)
+        out = torch.empty(y.size, dtype=torch.int32, device=self.device)
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.mcn_maxpool_tap_to_argmax(self.addr(Ptr(a["argmax"])), n, h, w, c, a["k"][0], a["k"][1],
+                                                      a["s"][0], a["s"][1], a["pad"][0], a["pad"][1], ho, wo,
+                                                      out.data_ptr(), st), "maxpool_tap_to_argmax")
+        return out.cpu().numpy().reshape(y.shape)
+
     def get_variables(self, ema=False):
         p = self.plan
         buf = p.b_ema if ema else p.b_param
@@ -445,7 +464,11 @@ class Engine(object):
             else:
                 e.taps, e.cin, e.cout = 1, 1, max(v.storage_size, 1)
             decayed = v.kind == "weight" or (self.bias_norm_decay and v.kind in ("bias", "norm"))
-            e.l2 = self.l2 if (decayed and v.trainable) else 0.0
+            # the regularisation LOSS sums over every weight variable, frozen ones included
+            # (convnet.py:535-563 takes the whole 'weight_variables' collection); gradients and the
+            # decoupled decay only touch trainable ones (g == NULL skips both in the kernel)
+            e.l2 = self.l2 if decayed else 0.0
+            e.l1 = self.l1 if decayed else 0.0
             e.wd = self.base_wd if (decayed and v.trainable) else 0.0
             max_n = max(max_n, v.storage_size)
         raw = bytes(table)
@@ -460,13 +483,45 @@ class Engine(object):
         d_t = min(self.ema_decay, (1.0 + t) / (10.0 + t))
         b1, b2 = self.momentum, (0.9 if self.opt_kind == 1 else 0.999)
         adam_lr = lr * np.sqrt(1.0 - b2 ** (t + 1)) / (1.0 - b1 ** (t + 1)) if self.opt_kind == 2 else lr
-        hp = self.hp_host
+        hp = self._pinned_slot("hp", (16,), torch.float32, slots=4)
+        hp.zero_()
         hp[0], hp[1], hp[2], hp[3] = lr, b1, b2, 1e-3
         hp[4], hp[5] = d_t, adam_lr
         hp[6] = 1.0 / (self.world * self.plan.loss_scale)
         hp[7] = lr_multiplier if self.wd_scheduling else 1.0
         hp[8] = self.grad_threshold if self.grad_threshold is not None else 0.0
+        hp[9] = float(self.wd_form)
+        hp[10] = float(self.huber_delta) if self.huber_delta is not None else 1.0
+        # seed / step of the random train-time ops (dropout, stochastic depth): uint32 bit patterns
+        hpi = hp.view(torch.int32)
+        hpi[12] = int(np.int32(np.uint32(self.random_seed & 0xFFFFFFFF)))
+        hpi[13] = int(np.int32(np.uint32(t & 0xFFFFFFFF)))
         self.hp_dev.copy_(hp, non_blocking=True)
+        self._pinned_done("hp")
+
+    def _pinned_slot(self, key, shape, dtype, slots=2):
+        """Pinned host staging buffer for an asynchronous H2D copy.  A slot is only rewritten after
+        the copy that last read it has completed (event recorded by _pinned_done): with
+        fetch_loss=False or CUDA-graph replay the host runs ahead of the GPU, and rewriting a
+        buffer an earlier copy_(non_blocking=True) is still reading would hand step N the
+        hyper-parameters or batch of step N+k."""
+        ring = self._pin_rings.setdefault(key, {"bufs": [], "events": [], "next": 0})
+        if not ring["bufs"] or tuple(ring["bufs"][0].shape) != tuple(shape) or ring["bufs"][0].dtype != dtype:
+            ring["bufs"] = [torch.empty(tuple(shape), dtype=dtype).pin_memory() for _ in range(slots)]
+            ring["events"] = [None] * slots
+            ring["next"] = 0
+        i = ring["next"]
+        ring["next"] = (i + 1) % len(ring["bufs"])
+        if ring["events"][i] is not None:
+            ring["events"][i].synchronize()
+        ring["cur"] = i
+        return ring["bufs"][i]
+
+    def _pinned_done(self, key, stream=None):
+        ring = self._pin_rings[key]
+        ev = torch.cuda.Event()
+        ev.record(stream if stream is not None else torch.cuda.current_stream(self.device))
+        ring["events"][ring["cur"]] = ev
 
     def load_inputs(self, **arrays):
         """Host (numpy / pinned torch) -> device input buffers, asynchronously on the current
@@ -477,15 +532,17 @@ class Engine(object):
             dst = self._inputs[name]
             if name == "Y" and off:
                 # task bases that take labels with 0 = ignore (segnet.py:50) store class-1 on device
-                arr = (np.asarray(arr) if isinstance(arr, np.ndarray) else arr.numpy()).astype(np.int64) - off
-            if isinstance(arr, np.ndarray):
-                pin = self._pinned.get(name)
-                if pin is None or pin.shape != dst.shape:
-                    pin = torch.empty(dst.shape, dtype=dst.dtype).pin_memory()
-                    self._pinned[name] = pin
+                arr = (np.asarray(arr) if isinstance(arr, np.ndarray) else arr.numpy()).astype(np.int32) - np.int32(off)
+            if dst.dtype == torch.uint8 and (arr.dtype != np.uint8 if isinstance(arr, np.ndarray) else arr.dtype != torch.uint8):
+                raise TypeError("this model was built with input_dtype='u8': pass raw uint8 images")
+            staged = isinstance(arr, np.ndarray)
+            if staged:
+                pin = self._pinned_slot("in:" + name, dst.shape, dst.dtype)
                 pin.copy_(torch.from_numpy(np.ascontiguousarray(arr)).to(dst.dtype).view(dst.shape))
                 arr = pin
             dst.copy_(arr.view(dst.shape), non_blocking=True)
+            if staged:
+                self._pinned_done("in:" + name)
             nbytes += dst.numel() * dst.element_size()
         return nbytes
 
@@ -508,14 +565,14 @@ class Engine(object):
                 if isinstance(arr, np.ndarray) or (name == "Y" and off):
                     a = np.asarray(arr) if isinstance(arr, np.ndarray) else arr.numpy()
                     if name == "Y" and off:
-                        a = a.astype(np.int64) - off
-                    pin = self._pinned.get(name)
-                    if pin is None or pin.shape != dst.shape:
-                        pin = torch.empty(dst.shape, dtype=dst.dtype).pin_memory()
-                        self._pinned[name] = pin
+                        a = a.astype(np.int32) - np.int32(off)
+                    pin = self._pinned_slot("pre:" + name, dst.shape, dst.dtype)
                     pin.copy_(torch.from_numpy(np.ascontiguousarray(a)).to(dst.dtype).view(dst.shape))
                     arr = pin
-                dst.copy_(arr.view(dst.shape), non_blocking=True)
+                    dst.copy_(arr.view(dst.shape), non_blocking=True)
+                    self._pinned_done("pre:" + name, self._copy_stream)
+                else:
+                    dst.copy_(arr.view(dst.shape), non_blocking=True)
                 nbytes += dst.numel() * dst.element_size()
             self._staged.record(self._copy_stream)
         return nbytes

@@ -130,7 +130,10 @@ class Tensor(object):
         rate = float(rate)
         if rate == 0.0:
             return self  # tf.nn.dropout(rate=0) is the identity
-        raise NotImplementedError("dropout with rate > 0 is not implemented in this backend yet")
+        if not 0.0 < rate < 1.0:
+            raise ValueError("dropout rate must be in [0, 1)")
+        return self.graph._add("dropout", [self], [self.shape], [self.dtype],
+                               {"rate": rate, "layer": self.graph.next_random_layer()}).outputs[0]
 
 
 class Node(object):
@@ -160,6 +163,11 @@ class Graph(object):
         self.losses = []                # scalar loss tensors (node op 'softmax_xent' ...)
         self.flops = 0
         self.collections = collections.defaultdict(list)
+
+    def next_random_layer(self):
+        """Id of a random op (dropout / stochastic depth): part of its Philox key."""
+        self.random_layers = getattr(self, "random_layers", 0) + 1
+        return self.random_layers
 
     # ---- construction helpers
     def _add(self, op, inputs, out_shapes, out_dtypes, attrs=None, scope=""):

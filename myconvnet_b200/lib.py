@@ -21,7 +21,7 @@ class OptTensorC(ctypes.Structure):
                 ("v", ctypes.c_void_p), ("ema", ctypes.c_void_p), ("w_bf16", ctypes.c_void_p),
                 ("w_bf16_t", ctypes.c_void_p), ("n", ctypes.c_longlong), ("taps", ctypes.c_int),
                 ("cin", ctypes.c_int), ("cout", ctypes.c_int), ("l2", ctypes.c_float),
-                ("wd", ctypes.c_float)]
+                ("wd", ctypes.c_float), ("l1", ctypes.c_float)]
 
 
 _T = {"p": ctypes.c_void_p, "i": ctypes.c_int, "l": ctypes.c_longlong, "f": ctypes.c_float,
@@ -46,6 +46,7 @@ SIGNATURES = {
     "mcn_im2col": "Dippi",
     "mcn_bn_stats": "iplip",
     "mcn_bn_finalize": "pdiffpppp",
+    "mcn_bn_frozen_stats": "ppifpp",
     "mcn_bn_apply": "iplipppppifp",
     "mcn_bn_apply_stats": "iplipdffpppifppppp",
     "mcn_bn_infer": "iplippfpppifp",
@@ -53,6 +54,9 @@ SIGNATURES = {
     "mcn_bn_bwd_apply": "ippplippppifppdpp",
     "mcn_maxpool_fwd": "ipiiiiiiiiiiiipp",
     "mcn_maxpool_bwd": "ippiiiiiiiiiiiip",
+    "mcn_maxpool_fwd_tap": "ipiiiiiiiiiiiipp",
+    "mcn_maxpool_bwd_tap": "ippiiiiiiiiiiiip",
+    "mcn_maxpool_tap_to_argmax": "piiiiiiiiiiiip",
     "mcn_avgpool_fwd": "ipiiiiiiiiiiiip",
     "mcn_avgpool_bwd": "ipiiiiiiiiiiiip",
     "mcn_gap_fwd": "ipiiipi",
@@ -67,11 +71,16 @@ SIGNATURES = {
     "mcn_bias_add": "iplip",
     "mcn_bias_grad": "iplip",
     "mcn_cast": "ipipl",
-    "mcn_input_prep": "plffip",
+    "mcn_input_prep": "piiiiiiiffip",
     "mcn_copy_channels": "ipliipiiii",
     "mcn_resize_bilinear_fwd": "ipiiiiiiip",
     "mcn_resize_bilinear_bwd": "ipiiiiiiip",
-    "mcn_softmax_xent": "pplipffppp",
+    "mcn_resize_nearest_fwd": "ipiiiiiiip",
+    "mcn_resize_nearest_bwd": "ipiiiiiiip",
+    "mcn_dropout": "iplfpip",
+    "mcn_sd_add_fwd": "ippilfpiifp",
+    "mcn_sd_add_bwd": "ippilfpiifpp",
+    "mcn_softmax_xent": "pplipfffiifppp",
     "mcn_sigmoid_xent": "plfffppi",
     "mcn_opt_step": "ipilppp",
     "mcn_grad_sqnorm": "pilpp",

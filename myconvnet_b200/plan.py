@@ -19,7 +19,7 @@ import numpy as np
 
 ALIGN = 256
 DT_SIZE = {"f32": 4, "bf16": 2, "i32": 4, "f64": 8, "u8": 1}
-DT_CODE = {"f32": 0, "bf16": 1}
+DT_CODE = {"f32": 0, "bf16": 1, "u8": 2}
 
 
 class Buf(object):
@@ -349,6 +349,7 @@ class Plan(object):
                 prod = node.inputs[0].node
                 node.attrs["stats_in_conv"] = False
                 if (self.fuse_bn_stats and self.cdt == "bf16" and prod is not None
+                        and node.attrs["update"]
                         and prod.op == "conv2d" and prod.attrs.get("route") in ("tc", "im2col", "stem")
                         and prod.attrs["bn_stats_node"] is None
                         and node.inputs[0].shape[-1] % 64 == 0
@@ -386,13 +387,13 @@ class Plan(object):
                         and node.attrs.get("route") == "tc":
                     cons[0].attrs["fused_into"] = node
                     node.attrs["final"] = cons[0].outputs[0]
-            elif node.op == "add":
+            elif node.op in ("add", "sd_add"):
                 node.attrs["act"] = 0
                 node.attrs["alpha"] = 0.0
                 node.attrs["final"] = node.outputs[0]
         # add -> act for adds that were not absorbed by a BN
         for node in self.graph.nodes:
-            if node.op == "add" and node.attrs["fused_into"] is None:
+            if node.op in ("add", "sd_add") and node.attrs["fused_into"] is None:
                 c = self._single_consumer(node.outputs[0])
                 if c is not None and c.op == "act" and c.attrs["act"] in (1, 2, 3) \
                         and c.attrs["fused_into"] is None:
@@ -462,8 +463,8 @@ class Plan(object):
                         b = self.node_buf(node, "f32_copy", "softmax_in_f32", x.size * 4)
                         src = Ptr(b)
                         self.L("f", "mcn_cast", DT_CODE[x.dtype], self.tbuf[x], 0, src, x.size, tag="softmax_cast")
-                self.L("f", "mcn_softmax_xent", src, NULL, x.size // c, c, NULL, 0.0, 0.0, NULL, NULL,
-                       self.tbuf[node.outputs[0]], tag="softmax")
+                self.L("f", "mcn_softmax_xent", src, NULL, x.size // c, c, NULL, 0.0, 0.0, 0.0, 0, 0, 0.0,
+                       NULL, NULL, self.tbuf[node.outputs[0]], tag="softmax")
 
     def _logits_dtype(self, t):
         """dtype of the data actually stored for t (a fused dense writes fp32 under a bf16 name)."""
@@ -479,8 +480,10 @@ class Plan(object):
     def _f_input_prep(self, node):
         x, y = node.inputs[0], node.outputs[0]
         py = self.alloc_act(y)
-        self.L("f", "mcn_input_prep", self.tbuf[x], x.size, node.attrs["mean"], node.attrs["scale"],
-               DT_CODE[y.dtype], py, tag="input_prep")
+        n, hi, wi, c = x.shape
+        _, h, w, _ = y.shape
+        self.L("f", "mcn_input_prep", self.tbuf[x], DT_CODE[x.dtype], n, hi, wi, h, w, c, node.attrs["mean"],
+               node.attrs["scale"], DT_CODE[y.dtype], py, tag="input_prep")
 
     def _conv_geometry(self, node):
         x, y = node.inputs[0], node.outputs[0]
@@ -663,6 +666,15 @@ class Plan(object):
         pbeta = self.pvar(v["beta"]) if "beta" in v else NULL
         res = node.attrs["residual"]
         pres = self.tbuf[res] if res is not None else NULL
+        if not node.attrs["update"]:
+            # frozen layer: normalise with the stored moving statistics (reference
+            # convnet.py:1916-1924, fused_batch_norm(is_training=False) in the training graph)
+            self.L("f", "mcn_bn_frozen_stats", self.pvar(v["mu"]), self.pvar(v["sigma"]), c, node.attrs["eps"],
+                   Ptr(save), Ptr(save, c * 4), tag=node.scope + "/frozen_stats")
+            self.L("f", "mcn_bn_apply", self.ccode, self.tbuf[x], rows, c, Ptr(save), Ptr(save, c * 4), pg,
+                   pbeta, pres, node.attrs["act"], node.attrs["alpha"], py, tag=node.scope + "/apply")
+            self.bn_layers.append(node)
+            return
         if not node.attrs.get("stats_in_conv"):
             self.L("f", "mcn_bn_stats", self.ccode, self.tbuf[x], rows, c, Ptr(sums), tag=node.scope + "/stats")
         if self.sync_bn:
@@ -699,6 +711,73 @@ class Plan(object):
         self.L("f", "mcn_add_act_fwd", DT_CODE[a.dtype], self.tbuf[a], self.tbuf[b], a.size,
                node.attrs["act"], node.attrs["alpha"], py, tag="add")
 
+    def _f_sd_add(self, node):
+        # stochastic depth (convnet.py:2500-2512): train y = act(a*survived[n] + b); inference a + b
+        a, b = node.inputs
+        y = node.attrs["final"]
+        py = self.alloc_act(y)
+        self.tbuf.setdefault(node.outputs[0], py)
+        if self.phase == "infer":
+            self.L("f", "mcn_add_act_fwd", DT_CODE[a.dtype], self.tbuf[a], self.tbuf[b], a.size,
+                   node.attrs["act"], node.attrs["alpha"], py, tag="add")
+            return
+        n = a.shape[0]
+        self.L("f", "mcn_sd_add_fwd", DT_CODE[a.dtype], self.tbuf[a], self.tbuf[b], n, a.size // n,
+               node.attrs["rate"], Ptr(self.b_hp), node.attrs["layer"], node.attrs["act"],
+               node.attrs["alpha"], py, tag=node.scope)
+
+    def _b_sd_add(self, node, gy):
+        a, b = node.inputs
+        y = node.attrs["final"]
+        esz = DT_SIZE[a.dtype]
+        n = a.shape[0]
+        need_a, need_b = self._tensor_needs_grad(a), self._tensor_needs_grad(b)
+        pa, ha = self.talloc(a.size * esz) if need_a else (NULL, None)
+        pb, hb = self.talloc(b.size * esz) if need_b else (NULL, None)
+        if need_a or need_b:
+            self.L("b", "mcn_sd_add_bwd", DT_CODE[a.dtype], gy, self.tbuf[y], n, a.size // n,
+                   node.attrs["rate"], Ptr(self.b_hp), node.attrs["layer"], node.attrs["act"],
+                   node.attrs["alpha"], pa, pb, tag=node.scope + "/bwd")
+        for t, p, h in ((a, pa, ha), (b, pb, hb)):
+            if h is None:
+                continue
+            if t not in self.g:
+                self.g[t] = (p, h)          # first contribution: hand the buffer over
+            else:
+                self.L("b", "mcn_accumulate", DT_CODE[t.dtype], self.g[t][0], p, t.size, tag="grad_accumulate")
+                self.tfree(h)
+
+    def _f_dropout(self, node):
+        x, y = node.inputs[0], node.outputs[0]
+        py = self.alloc_act(y)
+        if self.phase == "infer":      # is_train False -> rate 0: identity
+            self.L("f", "mcn_cast", DT_CODE[x.dtype], self.tbuf[x], DT_CODE[x.dtype], py, x.size, tag="dropout_off")
+            return
+        self.L("f", "mcn_dropout", DT_CODE[x.dtype], self.tbuf[x], x.size, node.attrs["rate"], Ptr(self.b_hp),
+               node.attrs["layer"], py, tag="dropout")
+
+    def _b_dropout(self, node, gy):
+        x = node.inputs[0]
+        self.contribute(x, x.size * DT_SIZE[x.dtype],
+                        lambda p: self.L("b", "mcn_dropout", DT_CODE[x.dtype], gy, x.size, node.attrs["rate"],
+                                         Ptr(self.b_hp), node.attrs["layer"], p, tag="dropout_bwd"))
+
+    def _f_resize_nearest(self, node):
+        x, y = node.inputs[0], node.outputs[0]
+        n, h, w, c = x.shape
+        _, ho, wo, _ = y.shape
+        py = self.alloc_act(y)
+        self.L("f", "mcn_resize_nearest_fwd", DT_CODE[x.dtype], self.tbuf[x], n, h, w, c, ho, wo,
+               node.attrs["mode"], py, tag="resize_nearest")
+
+    def _b_resize_nearest(self, node, gy):
+        x, y = node.inputs[0], node.outputs[0]
+        n, h, w, c = x.shape
+        _, ho, wo, _ = y.shape
+        self.contribute(x, x.size * DT_SIZE[x.dtype],
+                        lambda p: self.L("b", "mcn_resize_nearest_bwd", DT_CODE[x.dtype], gy, n, h, w, c,
+                                         ho, wo, node.attrs["mode"], p, tag="resize_nearest_bwd"))
+
     def _f_scale_bcast(self, node):
         x, m = node.inputs
         y = node.outputs[0]
@@ -713,6 +792,16 @@ class Plan(object):
         n, h, w, c = x.shape
         _, ho, wo, _ = y.shape
         py = self.alloc_act(y)
+        # compact form: the winning tap of the window as one byte (the int32 TF argmax is twice
+        # the size of a bf16 tensor); expanded on demand by mcn_maxpool_tap_to_argmax
+        vec = 16 // DT_SIZE[x.dtype]
+        a["tap_form"] = (c % vec == 0 and a["k"][0] * a["k"][1] <= 255 and x.size // 4 < 2 ** 31)
+        if a["tap_form"]:
+            arg = self.node_buf(node, "tap", "pool_tap:%s" % node.scope, y.size)
+            node.attrs["argmax"] = arg
+            self.L("f", "mcn_maxpool_fwd_tap", DT_CODE[x.dtype], self.tbuf[x], n, h, w, c, a["k"][0], a["k"][1],
+                   a["s"][0], a["s"][1], a["pad"][0], a["pad"][1], ho, wo, py, Ptr(arg), tag="max_pool")
+            return
         arg = self.node_buf(node, "argmax", "argmax:%s" % node.scope, y.size * 4)
         node.attrs["argmax"] = arg
         self.L("f", "mcn_maxpool_fwd", DT_CODE[x.dtype], self.tbuf[x], n, h, w, c, a["k"][0], a["k"][1],
@@ -801,9 +890,10 @@ class Plan(object):
             node.attrs["cw_buf"] = cwb
             cw = Ptr(cwb)
         # loss = mean over rows (convnet.py:594); gradient seeded with loss_scale / rows
+        seg_h, seg_w = a.get("seg_hw") or (0, 0)
         self.L("f", "mcn_softmax_xent", self.tbuf[logits], self.tbuf[labels], rows, c, cw,
-               a["label_smoothing"], self.loss_scale / rows, Ptr(loss), Ptr(dlog), probs,
-               tag="softmax_xent")
+               a["label_smoothing"], a.get("focal_gamma", 0.0), a.get("sigmoid_focal_alpha", 0.0),
+               seg_h, seg_w, self.loss_scale / rows, Ptr(loss), Ptr(dlog), probs, tag="softmax_xent")
 
     def _f_gan_loss(self, node):
         if self.phase == "infer":
@@ -1083,7 +1173,12 @@ class Plan(object):
                Ptr(save, c * 4), pg, pbeta, act, node.attrs["alpha"], s1, s2, tag=node.scope + "/bwd_reduce")
         g1, g2, gh = s1, s2, None
         count = float(rows)
-        if self.sync_bn:
+        if not node.attrs["update"]:
+            # frozen statistics: dx = dz*gamma*invstd — the batch-statistics terms vanish (zero sums)
+            gp, gh = self.talloc(2 * c * 4)
+            self.L("b", "mcn_fill_f32", gp, 2 * c, 0.0, tag="zero")
+            g1, g2 = gp, gp + c * 4
+        elif self.sync_bn:
             # global sums go to a scratch vector: the LOCAL sums stay in place as dbeta / dgamma
             # (they are averaged over ranks with the other gradients).  The exchange gathers its
             # two source segments itself (mcn_peer_allreduce src0/src1), no staging copies.
@@ -1174,8 +1269,9 @@ class Plan(object):
         a = node.attrs
         n, h, w, c = x.shape
         _, ho, wo, _ = y.shape
+        fn = "mcn_maxpool_bwd_tap" if a.get("tap_form") else "mcn_maxpool_bwd"
         self.contribute(x, x.size * DT_SIZE[x.dtype],
-                        lambda p: self.L("b", "mcn_maxpool_bwd", DT_CODE[x.dtype], gy, Ptr(a["argmax"]), n,
+                        lambda p: self.L("b", fn, DT_CODE[x.dtype], gy, Ptr(a["argmax"]), n,
                                          h, w, c, a["k"][0], a["k"][1], a["s"][0], a["s"][1], a["pad"][0],
                                          a["pad"][1], ho, wo, p, tag="max_pool_bwd"))
 

@@ -38,6 +38,7 @@ class SegNet(ConvNet):
     def _build_model_seg(self, d_backbone):
         raise NotImplementedError
 
-    def _label_smoothing(self, labels, ls_factor, name='label_smoothing'):
-        raise NotImplementedError('segmentation label smoothing (5x5 average of the one-hot map, '
-                                  'segnet.py:116-121) is not supported yet')
+    def _label_smoothing_map(self):
+        # labels*(1-ls) + ls*avg_pool2d(labels, 5x5, SAME) (segnet.py:116-121): evaluated inside the
+        # loss kernel from the integer label map (mcn_softmax_xent seg_h / seg_w)
+        return (int(self.input_size[0]), int(self.input_size[1]))

@@ -104,3 +104,25 @@ class Trainer(object):
                         callback(self)
                 self.curr_step += 1
         return losses
+
+    def fit_dataset(self, dataset, num_steps=None, fetch_loss=True):
+        """Same loop over a DataSet(from_memory=True) (dataset.py): the data set's own shard order
+        and labels (NaN = fake label), this trainer's learning-rate schedule."""
+        total = self.steps_per_epoch * self.num_epochs
+        limit = total if num_steps is None else min(total, self.curr_step + int(num_steps))
+        losses = []
+        while self.curr_step < limit:
+            stepped = False
+            for Xb, Yb in dataset.shard_batches(self.rank):
+                if self.curr_step >= limit:
+                    break
+                mult = self.schedule(self.curr_step)
+                loss = self.engine.train_step(np.ascontiguousarray(Xb), np.ascontiguousarray(Yb),
+                                              lr_multiplier=mult, fetch_loss=fetch_loss)
+                losses.append(loss)
+                self.history.append((self.curr_step, self.curr_epoch, mult, loss))
+                self.curr_step += 1
+                stepped = True
+            if not stepped:
+                break
+        return losses

@@ -78,9 +78,22 @@ class OTensor(object):
         return OTensor(ops.activation(self.t, kind, alpha))
 
     def _tf_dropout(self, rate):
-        if float(rate) == 0.0:
+        # tf.nn.dropout(x, rate): keep u >= rate, scale 1/(1-rate); the keep mask is the device's
+        # counter-based one (oracle/philox.py), off at inference
+        rate = float(rate)
+        m = _CURRENT[0]
+        if rate == 0.0:
             return self
-        raise NotImplementedError("oracle: dropout rate > 0")
+        layer = m._next_random_layer()
+        if not getattr(m, "is_train", True):
+            return self
+        from . import philox
+        keep = philox.dropout_keep(self.t.numel(), rate, m.random_seed, m.random_step, layer)
+        mask = torch.from_numpy(keep.reshape(tuple(self.t.shape))).to(self.t.dtype) / (1.0 - rate)
+        return OTensor(m._q(self.t * mask))
+
+
+_CURRENT = [None]      # the model whose forward is running (tensor-level ops need its RNG context)
 
 
 class ConvNet(object):
@@ -113,6 +126,13 @@ class ConvNet(object):
         self.var_meta = {}      # name -> dict(kind, trainable, block, init, shape)
         self.collections = {}
         self.bn_updates = {}    # name -> new moving value computed this forward
+        # random train-time ops: same (seed, step, layer) -> same masks as the device (philox.py)
+        self.random_seed = int(kwargs.get("random_seed", 0))
+        self.random_step = 0
+        self._random_layers = 0
+        # teacher-forced ReLU pattern: list of boolean arrays in call order (see _relu)
+        self.forced_relu_masks = None
+        self._relu_calls = 0
         self._flops = 0
         self._params = 0
         self._init_params(**kwargs)
@@ -204,6 +224,25 @@ class ConvNet(object):
             t = torch.tensor(np.asarray(v), dtype=self.dtype)
             self.vars[k] = t
 
+    def _next_random_layer(self):
+        self._random_layers += 1
+        return self._random_layers
+
+    def _relu(self, t):
+        """max(x, 0) — or, with forced_relu_masks, x*mask with the DEVICE's activation pattern.
+        A ReLU network's gradient is discontinuous in its pre-activations: two correct
+        implementations whose activations differ by rounding flip a few masks, and every flip moves
+        gradients by a finite amount (measured at BASELINE config 1, fp32: activations agree to
+        3e-5 and gradients only to 1e-2; in bf16 the patterns decorrelate the gradients
+        completely).  Evaluating the oracle ON the device's pattern removes that noise floor, so
+        the comparison measures the arithmetic and tolerances can be tight.  The pattern itself is
+        checked separately (unforced fp32 activations)."""
+        if self.forced_relu_masks is None:
+            return torch.relu(t)
+        m = self.forced_relu_masks[self._relu_calls]
+        self._relu_calls += 1
+        return t * torch.from_numpy(np.ascontiguousarray(m)).to(t.dtype).reshape(t.shape)
+
     def _q(self, t):
         if self.round_bf16:
             # straight-through bf16 rounding: forward sees the rounded value, gradient passes
@@ -214,6 +253,9 @@ class ConvNet(object):
     def forward(self, X, Y):
         """X: float [N,H,W,C] in [0,1]; Y: int labels.  Returns the loss; fills self.d."""
         tf.reset_scopes()
+        _CURRENT[0] = self
+        self._random_layers = 0
+        self._relu_calls = 0
         self._block_list = []
         self.collections = {}       # every forward is a fresh build (block registry included)
         self.bn_updates = {}
@@ -231,15 +273,23 @@ class ConvNet(object):
         return self._build_loss(**self._parameters)
 
     def _build_loss(self, **kwargs):
+        l1_factor = kwargs.get("l1_reg", 0.0)
         l2_factor = kwargs.get("l2_reg", 1e-4)
         ls = kwargs.get("label_smoothing", 0.0)
-        data = ops.classification_loss(self.logits, self.Y, self.num_classes, self.loss_weights, ls)
+        data = ops.classification_loss(self.logits, self.Y, self.num_classes, self.loss_weights, ls,
+                                       focal_gamma=kwargs.get("focal_loss_factor", 0.0),
+                                       sigmoid_focal_alpha=kwargs.get("sigmoid_focal_loss_factor", 0.0),
+                                       spatial_smoothing=self._spatial_label_smoothing)
         names = [n for n, m in self.var_meta.items() if m["kind"] == "weight"]
         if kwargs.get("bias_norm_decay", False):
             names += [n for n, m in self.var_meta.items() if m["kind"] in ("bias", "norm")]
         reg = sum(ops.l2_loss(self.vars[n]) for n in names) * l2_factor if l2_factor > 0 else 0.0
+        if l1_factor > 0:
+            reg = reg + l1_factor * sum(self.vars[n].abs().sum() for n in names)
         self.data_loss = data
         return data + reg
+
+    _spatial_label_smoothing = False
 
     # ---- layer ops (signatures of reference convnet.py)
     def max_pool(self, x, side_l, stride, padding="SAME"):
@@ -266,11 +316,11 @@ class ConvNet(object):
         with tf.variable_scope(scope) if scope is not None else nullcontext():
             if depthwise:
                 mult = max(out_channels // cin, 1)
-                w = self._q(self._get_var("weights", [kernel[0], kernel[1], cin, mult], weight_initializer, "weight"))
+                w = self._q(self._ws(self._get_var("weights", [kernel[0], kernel[1], cin, mult], weight_initializer, "weight"), ws))
                 y = ops.depthwise_conv2d(x.t, w, stride, padding, dilation)
                 out_c = cin * mult
             else:
-                w = self._q(self._get_var("weights", [kernel[0], kernel[1], cin, out_channels], weight_initializer, "weight"))
+                w = self._q(self._ws(self._get_var("weights", [kernel[0], kernel[1], cin, out_channels], weight_initializer, "weight"), ws))
                 y = ops.conv2d(x.t, w, stride, padding, dilation)
                 out_c = out_channels
             if biased:
@@ -284,7 +334,7 @@ class ConvNet(object):
                     zero_scale_init=False, epsilon=1e-3, act_type="relu", act_params=None, verbose=False):
         with tf.variable_scope(scope) if scope is not None else nullcontext():
             x = self.conv_layer(x, kernel, stride, out_channels, padding=padding, biased=biased,
-                                depthwise=depthwise, dilation=dilation,
+                                depthwise=depthwise, dilation=dilation, ws=ws,
                                 weight_initializer=weight_initializer, bias_initializer=bias_initializer)
             x = self.batch_norm(x, scale=scale, shift=shift, zero_scale_init=zero_scale_init, epsilon=epsilon)
             x = self.activation(x, activation_type=act_type, params=act_params)
@@ -304,7 +354,7 @@ class ConvNet(object):
         else:
             out_hw = list(output_shape[1:3])
         with tf.variable_scope(scope) if scope is not None else nullcontext():
-            w = self._q(self._get_var("weights", [kernel[0], kernel[1], cin, out_channels], weight_initializer, "weight"))
+            w = self._q(self._ws(self._get_var("weights", [kernel[0], kernel[1], cin, out_channels], weight_initializer, "weight"), ws))
             y = ops.conv2d_transpose(x.t, w, out_hw, stride, padding, dilation)
             if biased:
                 y = y + self._get_var("biases", [out_channels], bias_initializer, "bias")
@@ -315,10 +365,14 @@ class ConvNet(object):
                  bias_initializer=tf.initializers.zeros(), verbose=False):
         in_dim = int(x.t.shape[-1])
         with tf.variable_scope(scope) if scope is not None else nullcontext():
-            w = self._q(self._get_var("weights", [in_dim, out_dim], weight_initializer, "weight"))
+            w = self._q(self._ws(self._get_var("weights", [in_dim, out_dim], weight_initializer, "weight"), ws))
             b = self._get_var("biases", [out_dim], bias_initializer, "bias") if biased else None
             y = ops.dense(x.t, w, b)
         return OTensor(y)   # logits stay fp32 (device epilogue writes fp32)
+
+    @staticmethod
+    def _ws(w, enabled):
+        return ops.weight_standardization(w) if enabled else w
 
     def normalization(self, x, norm_type="batch", norm_param=None, scale=True, shift=True,
                       zero_scale_init=False, epsilon=1e-3, scope="norm"):
@@ -327,7 +381,24 @@ class ConvNet(object):
         if norm_type.lower() == "batch":
             return self.batch_norm(x, scale=scale, shift=shift, zero_scale_init=zero_scale_init,
                                    epsilon=epsilon, scope=scope)
+        if norm_type.lower() == "group":
+            return self.group_norm(x, num_groups=32 if norm_param is None else norm_param, scale=scale,
+                                   shift=shift, zero_scale_init=zero_scale_init, epsilon=epsilon, scope=scope)
         raise NotImplementedError("oracle: norm_type %s" % norm_type)
+
+    def group_norm(self, x, num_groups=32, scale=True, shift=True, zero_scale_init=False, epsilon=1e-3,
+                   scope="gn"):
+        """convnet.py:1928-2013."""
+        trainable = self._trainable()
+        c = x.t.shape[-1]
+        assert c // num_groups * num_groups == c, \
+            "Number of channels must be a multiple of num_groups ({})".format(num_groups)
+        with tf.variable_scope(scope):
+            gamma = self._get_var("gamma", [c], tf.zeros_initializer() if zero_scale_init else tf.ones_initializer(),
+                                  "norm", trainable=trainable) if scale else None
+            beta = self._get_var("beta", [c], tf.zeros_initializer(), "norm", trainable=trainable) if shift else None
+            y = ops.group_norm(x.t, gamma, beta, num_groups, epsilon)
+        return OTensor(y)   # rounding happens after the fused activation, as on device
 
     def batch_norm(self, x, scale=True, shift=True, zero_scale_init=False, epsilon=1e-3, scope="bn"):
         """convnet.py:1780-1926, training branch; moving statistics recorded in self.bn_updates."""
@@ -344,9 +415,13 @@ class ConvNet(object):
             gamma = self._get_var("gamma", [c], tf.zeros_initializer() if zero_scale_init else tf.ones_initializer(),
                                   "norm", trainable=trainable) if scale else None
             beta = self._get_var("beta", [c], tf.zeros_initializer(), "norm", trainable=trainable) if shift else None
-            if not getattr(self, "is_train", True):
-                # is_train=False: moving statistics (their EMA shadows, loaded by the trainer)
-                return OTensor(ops.fused_batch_norm_infer(x.t, gamma, beta, mu, sigma, epsilon))
+            if not getattr(self, "is_train", True) or not update:
+                # is_train=False: moving statistics (their EMA shadows, loaded by the trainer).
+                # update=False (blocks outside blocks_to_train / update_batch_norm=False): the
+                # reference calls fused_batch_norm(is_training=False, mean=mu, variance=sigma) even
+                # while training (convnet.py:1916-1924) — frozen layers normalise with the stored
+                # moving statistics and have no batch-statistics terms in their backward pass
+                return OTensor(ops.fused_batch_norm_infer(x.t, gamma, beta, mu.detach(), sigma.detach(), epsilon))
             y, bm, bv = ops.fused_batch_norm_train(x.t, gamma, beta, epsilon)
             if update:
                 m = self.batch_norm_decay
@@ -364,22 +439,35 @@ class ConvNet(object):
             ac, hp = False, False
         else:
             ac, hp = align_corners, not align_corners
+        if upsampling_method.lower() in ("nearest", "nearest_neighbor"):
+            return OTensor(ops.resize_nearest(x.t, [int(s) for s in out_shape], ac, hp))
         if upsampling_method.lower() != "bilinear":
-            raise NotImplementedError("oracle: nearest upsampling")
+            raise ValueError("Upsampling method of {} is not supported".format(upsampling_method))
         return OTensor(self._q(ops.resize_bilinear(x.t, [int(s) for s in out_shape], ac, hp)))
 
     def stochastic_depth(self, x, skip, drop_rate=0.0, name="drop"):
+        """convnet.py:2500-2512: x*survived + skip, survived[n] = (u_n >= rate)/(1-rate) per sample
+        while training; the uniform numbers are the device's (oracle/philox.py)."""
         if drop_rate > 0.0:
-            raise NotImplementedError("oracle: stochastic depth > 0")
+            layer = self._next_random_layer()
+            if not getattr(self, "is_train", True):
+                return x + skip
+            from . import philox
+            n = x.t.shape[0]
+            keep = philox.survive(n, drop_rate, self.random_seed, self.random_step, layer)
+            s = torch.from_numpy(keep).to(x.t.dtype).reshape([n] + [1] * (x.t.dim() - 1)) / (1.0 - drop_rate)
+            return OTensor(x.t * s + skip.t)
         return x + skip
 
     def activation(self, x, activation_type="relu", params=None):
         if activation_type is None:
             return x
+        if activation_type.lower() == "relu":
+            return OTensor(self._q(self._relu(x.t)))
         return OTensor(self._q(ops.activation(x.t, activation_type, params)))
 
     def relu(self, x, name="relu"):
-        return OTensor(self._q(torch.relu(x.t)))
+        return OTensor(self._q(self._relu(x.t)))
 
     def relu6(self, x, name="relu6"):
         return OTensor(self._q(ops.activation(x.t, "relu6")))

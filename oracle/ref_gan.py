@@ -16,6 +16,10 @@ class GAN(ConvNet):
     def forward(self, X, Z):
         """X real images in [0,1], Z latent vectors.  Returns (loss_d, loss_g)."""
         tf.reset_scopes()
+        from . import ref_convnet
+        ref_convnet._CURRENT[0] = self
+        self._random_layers = 0
+        self._relu_calls = 0
         self._block_list = []
         self.collections = {}
         self.bn_updates = {}

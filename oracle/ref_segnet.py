@@ -11,8 +11,14 @@ from .ref_convnet import ConvNet, OTensor
 
 
 class SegNet(ConvNet):
+    _spatial_label_smoothing = True      # segnet.py:116-121: 5x5 SAME average of the one-hot map
+
     def forward(self, X, Y):
         tf.reset_scopes()
+        from . import ref_convnet
+        ref_convnet._CURRENT[0] = self
+        self._random_layers = 0
+        self._relu_calls = 0
         self._block_list = []
         self.collections = {}
         self.bn_updates = {}

@@ -32,6 +32,7 @@ class OracleTrainer(object):
     def step(self, X, Y, lr_multiplier=1.0, update=True):
         m = self.model
         batch = self.batch_size or len(X)
+        m.random_step = self.global_step        # same (seed, step) as the device's random ops
         loss = m.forward(X, Y)
         if self.ema is None:
             self.ema = {k: v.detach().clone() for k, v in m.vars.items()}
@@ -89,8 +90,15 @@ class OracleTrainer(object):
                 meta = m.var_meta[k]
                 decayed = meta["kind"] == "weight" or (self.bias_norm_decay and meta["kind"] in ("bias", "norm"))
                 if self.base_wd > 0 and decayed:
+                    # decoupled weight decay and its l1 / pseudo-Huber forms (optimizers.py:163-172)
                     wd = self.base_wd * batch / 256.0 * (lr_multiplier if self.wd_sched else 1.0)
-                    w = w - wd * w
+                    delta = self.kw.get("huber_decay_delta", None)
+                    if delta is not None:
+                        w = w - wd * w / torch.sqrt(1 + (w / delta) ** 2)
+                    elif self.kw.get("l1_weight_decay", False):
+                        w = w - wd * torch.sign(w)
+                    else:
+                        w = w - wd * w
                 m.vars[k] = w.clone()
         self.global_step += 1
         return float(loss.detach())

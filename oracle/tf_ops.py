@@ -176,6 +176,47 @@ def resize_bilinear(x, out_hw, align_corners=False, half_pixel_centers=False):
     return top + (bot - top) * fh
 
 
+def resize_nearest(x, out_hw, align_corners=False, half_pixel_centers=False):
+    """tf.image.resize_nearest_neighbor (convnet.py:2393-2395; Appendix A.7): src = round(dst*
+    (in-1)/(out-1)) with align_corners, floor((dst+0.5)*in/out) with half-pixel centres, else
+    floor(dst*in/out); clamped to in-1.  fp32 coordinate arithmetic as in the TF kernel."""
+    def src(out_size, in_size):
+        d = torch.arange(out_size, dtype=torch.float32)
+        if align_corners:
+            sc = torch.tensor((in_size - 1) / (out_size - 1) if out_size > 1 else 0.0, dtype=torch.float32)
+            s = torch.floor(d * sc + 0.5)          # roundf: half away from zero (coordinates are >= 0)
+        elif half_pixel_centers:
+            s = torch.floor((d + 0.5) * torch.tensor(in_size / out_size, dtype=torch.float32))
+        else:
+            s = torch.floor(d * torch.tensor(in_size / out_size, dtype=torch.float32))
+        return s.long().clamp(0, in_size - 1)
+    return x[:, src(out_hw[0], x.shape[1])][:, :, src(out_hw[1], x.shape[2])]
+
+
+def group_norm(x, gamma, beta, num_groups, eps):
+    """ConvNet.group_norm (convnet.py:1928-2013): per sample and group of C/G channels,
+    tf.nn.moments over (H, W, C/G) (biased variance), (x-mean)/sqrt(var+eps)*gamma+beta."""
+    n, c = x.shape[0], x.shape[-1]
+    xg = x.reshape(n, -1, num_groups, c // num_groups)
+    mean = xg.mean(dim=(1, 3), keepdim=True)
+    var = ((xg - mean) ** 2).mean(dim=(1, 3), keepdim=True)
+    y = ((xg - mean) / torch.sqrt(var + eps)).reshape(x.shape)
+    if gamma is not None:
+        y = y * gamma
+    if beta is not None:
+        y = y + beta
+    return y
+
+
+def weight_standardization(w):
+    """weight_variable(weight_standardization=True) (convnet.py:1410-1419): per output channel
+    (last axis) subtract the mean over all other axes, divide by (population std + 1e-5)."""
+    axes = tuple(range(w.dim() - 1))
+    c = w - w.mean(dim=axes, keepdim=True)
+    std = torch.sqrt((c ** 2).mean(dim=axes, keepdim=True))
+    return c / (std + 1e-5)
+
+
 def activation(x, kind, alpha=None):
     """convnet.py:2514-2556 (Appendix A.13)."""
     kind = (kind or "none").lower()
@@ -207,9 +248,13 @@ def sigmoid_cross_entropy(logits, labels):
     return torch.clamp(logits, min=0) - logits * labels + torch.log1p(torch.exp(-logits.abs()))
 
 
-def classification_loss(logits, labels_int, num_classes, class_w=None, label_smoothing=0.0):
+def classification_loss(logits, labels_int, num_classes, class_w=None, label_smoothing=0.0,
+                        focal_gamma=0.0, sigmoid_focal_alpha=0.0, spatial_smoothing=False):
     """Data term of reference convnet.py:552-594: one-hot (label -1 -> zero row), valid mask
-    |sum(Y)-1| < 1e-5, mean over ALL rows of w*valid*CE."""
+    |sum(Y)-1| < 1e-5, mean over ALL rows of w*valid*CE.  Label smoothing: uniform
+    (convnet.py:603-607) or, spatial_smoothing, the 5x5 SAME average of the one-hot map
+    (segmentation/segnet.py:116-121; labels_int is then [N,H,W]).  Focal factors of
+    convnet.py:580-592: (1-p_true)^gamma (differentiated) and the stop-gradient sigmoid form."""
     onehot = torch.zeros(labels_int.shape + (num_classes,), dtype=logits.dtype)
     ok = (labels_int >= 0) & (labels_int < num_classes)
     idx = labels_int.clamp(min=0, max=num_classes - 1)
@@ -218,8 +263,20 @@ def classification_loss(logits, labels_int, num_classes, class_w=None, label_smo
     w = torch.ones(num_classes, dtype=logits.dtype) if class_w is None else torch.as_tensor(class_w, dtype=logits.dtype)
     batch_w = (onehot * w).sum(-1)
     valid = ((onehot.sum(-1) - 1.0).abs() < 1e-5).to(logits.dtype)
-    labels = onehot * (1.0 - label_smoothing) + label_smoothing / num_classes if label_smoothing > 0 else onehot
+    if label_smoothing > 0 and spatial_smoothing:
+        labels = (1.0 - label_smoothing) * onehot + label_smoothing * avg_pool(onehot, (5, 5), (1, 1), "SAME")
+    elif label_smoothing > 0:
+        labels = onehot * (1.0 - label_smoothing) + label_smoothing / num_classes
+    else:
+        labels = onehot
     ce = softmax_cross_entropy(logits, labels)
+    if focal_gamma > 0 or sigmoid_focal_alpha > 0:
+        p_true = (onehot * torch.softmax(logits, dim=-1)).sum(-1)
+        if focal_gamma > 0:
+            ce = ce * torch.pow(1.0 - p_true, focal_gamma)
+        if sigmoid_focal_alpha > 0:
+            f = (1.0 - torch.sigmoid(sigmoid_focal_alpha * (p_true - 0.5))).detach()
+            ce = ce * (f / (1.0 - torch.sigmoid(torch.tensor(-0.5 * sigmoid_focal_alpha, dtype=logits.dtype))))
     return (batch_w * valid * ce).mean()
 
 

@@ -7,9 +7,21 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# Cheap, independent kernel tests run before the long model tests, so that a single model-level
+# failure under `pytest -x` cannot hide them (round-1 lesson: the bit-exact argmax test sat
+# behind a failing trajectory test and never ran on the driver's box).
+_ORDER = ["test_gpu_ops.py", "test_gpu_features.py", "test_gpu_resnet.py", "test_gpu_models.py"]
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def pytest_collection_modifyitems(session, config, items):
+    def key(item):
+        name = os.path.basename(str(item.fspath))
+        return (_ORDER.index(name) if name in _ORDER else -1)
+    items.sort(key=key)          # stable: keeps the order inside a file
 
 
 @pytest.fixture(scope="session")

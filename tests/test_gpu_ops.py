@@ -470,8 +470,8 @@ def test_softmax_xent_and_sigmoid_xent(L):
         loss = torch.zeros(3, dtype=torch.int64, device="cuda")     # xsum accumulator
         dl = torch.empty(rows, C, device="cuda")
         pr = torch.empty(rows, C, device="cuda")
-        L.check(lib.mcn_softmax_xent(zd.data_ptr(), yd.data_ptr(), rows, C, cwd.data_ptr(), ls, 1.0 / rows,
-                                     loss.data_ptr(), dl.data_ptr(), pr.data_ptr(), None))
+        L.check(lib.mcn_softmax_xent(zd.data_ptr(), yd.data_ptr(), rows, C, cwd.data_ptr(), ls, 0.0, 0.0, 0, 0,
+                                     1.0 / rows, loss.data_ptr(), dl.data_ptr(), pr.data_ptr(), None))
         torch.cuda.synchronize()
         assert abs(L.xsum_value(loss.cpu().numpy()) / rows - ref.item()) < 1e-5 * abs(ref.item()) + 1e-6
         assert rel_l2(dl.cpu(), z.grad) < 1e-5
@@ -488,3 +488,48 @@ def test_softmax_xent_and_sigmoid_xent(L):
         torch.cuda.synchronize()
         assert abs(L.xsum_value(loss.cpu().numpy()) / 50 - ref.item()) < 1e-5
         assert rel_l2(dl.cpu(), x.grad) < 1e-5
+
+
+def test_maxpool_argmax_bit_exact():
+    """Pooling argmax indices are bit-exact against the oracle's first-max-in-window rule."""
+    import ctypes
+    from myconvnet_b200 import lib as L
+    from oracle import tf_ops
+    lib = L.load()
+    rng = np.random.default_rng(3)
+    # quantised values make ties frequent
+    x = (rng.integers(0, 4, size=(2, 9, 11, 16)).astype(np.float32)) * 0.5
+    xt = torch.from_numpy(x).cuda()
+    for k, s, pad in [(3, 2, "SAME"), (2, 2, "VALID"), (3, 1, "SAME")]:
+        ho, pt, _ = tf_ops.same_pad(9, k, s, 1, pad)
+        wo, pl, _ = tf_ops.same_pad(11, k, s, 1, pad)
+        y = torch.empty(2, ho, wo, 16, device="cuda")
+        am = torch.empty(2, ho, wo, 16, dtype=torch.int32, device="cuda")
+        L.check(lib.mcn_maxpool_fwd(0, xt.data_ptr(), 2, 9, 11, 16, k, k, s, s, pt, pl, ho, wo,
+                                    y.data_ptr(), am.data_ptr(), None))
+        torch.cuda.synchronize()
+        ref_idx = tf_ops.max_pool_argmax(torch.from_numpy(x), [k, k], [s, s], pad).numpy()
+        ref_val = tf_ops.max_pool(torch.from_numpy(x), [k, k], [s, s], pad).numpy()
+        assert np.array_equal(am.cpu().numpy().astype(np.int64), ref_idx)
+        assert np.array_equal(y.cpu().numpy(), ref_val)
+        # compact (tap) form of the training step: same values, same argmax after expansion, and its
+        # backward equals the int32-argmax backward bit for bit (fp32 and bf16)
+        for code, dt in ((0, torch.float32), (1, torch.bfloat16)):
+            xc = xt.to(dt)
+            y2 = torch.empty(2, ho, wo, 16, device="cuda", dtype=dt)
+            tap = torch.empty(2, ho, wo, 16, dtype=torch.uint8, device="cuda")
+            am2 = torch.empty(2, ho, wo, 16, dtype=torch.int32, device="cuda")
+            L.check(lib.mcn_maxpool_fwd_tap(code, xc.data_ptr(), 2, 9, 11, 16, k, k, s, s, pt, pl, ho, wo,
+                                            y2.data_ptr(), tap.data_ptr(), None))
+            L.check(lib.mcn_maxpool_tap_to_argmax(tap.data_ptr(), 2, 9, 11, 16, k, k, s, s, pt, pl, ho, wo,
+                                                  am2.data_ptr(), None))
+            gy = torch.randn(2, ho, wo, 16, device="cuda").to(dt)
+            dx1, dx2 = torch.empty_like(xc), torch.empty_like(xc)
+            L.check(lib.mcn_maxpool_bwd(code, gy.data_ptr(), am.data_ptr(), 2, 9, 11, 16, k, k, s, s, pt, pl, ho, wo,
+                                        dx1.data_ptr(), None))
+            L.check(lib.mcn_maxpool_bwd_tap(code, gy.data_ptr(), tap.data_ptr(), 2, 9, 11, 16, k, k, s, s, pt, pl,
+                                            ho, wo, dx2.data_ptr(), None))
+            torch.cuda.synchronize()
+            assert np.array_equal(am2.cpu().numpy().astype(np.int64), ref_idx)
+            assert torch.equal(y2.float(), y)
+            assert torch.equal(dx1, dx2)
