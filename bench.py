@@ -177,7 +177,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the reference arm uses every host core
+    import torch
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    steps, warmup = max(1, args.steps), max(1, args.warmup)     # ~1.5 s per batch-32 step on 16 cores
     rate, dt, threads = cpu_reference_step_rate(steps, warmup)
     line = {
         "impl": "reference", "metric": "train_images_per_sec", "value": rate, "unit": "img/s",
@@ -196,9 +199,11 @@ def run_reference(args):
 
 # ------------------------------------------------------------------ roofline helpers
 def launch_work(name, args, esz):
-    """Algorithmic (bytes, flops) of one libmcn launch from its resolved argument tuple."""
+    """Algorithmic (bytes, flops) of one libmcn launch from its resolved argument tuple — the
+    per-unit figures of SURVEY 8(d) / DESIGN.md section 4 times the units the launch processes."""
     if name in ("mcn_conv2d_fprop_tc", "mcn_conv2d_fprop_tc_stats", "mcn_conv2d_dgrad_tc",
-                "mcn_conv2d_wgrad_tc"):
+                "mcn_conv2d_wgrad_tc", "mcn_conv2d_fprop_direct", "mcn_conv2d_dgrad_direct",
+                "mcn_conv2d_wgrad_direct"):
         d = args[0]._obj
         m = d.N * d.Ho * d.Wo
         flops = 2.0 * m * d.kh * d.kw * d.Cin * d.Cout
@@ -210,6 +215,9 @@ def launch_work(name, args, esz):
         flops = 2.0 * m * d.kh * d.kw * 3 * d.Cout            # the real taps / channels
         byt = esz * (d.N * d.H * d.W * 4 + m * d.Cout)
         return byt, flops
+    if name in ("mcn_dwconv2d_fwd", "mcn_dwconv2d_bwd_data", "mcn_dwconv2d_bwd_filter"):
+        d = args[0]._obj
+        return esz * (d.N * d.H * d.W * d.Cin + d.N * d.Ho * d.Wo * d.Cin), 0.0       # (|x| + |y|) * s
     if name == "mcn_bn_stats":
         return args[2] * args[3] * esz, 0.0
     if name == "mcn_bn_apply":
@@ -224,15 +232,44 @@ def launch_work(name, args, esz):
     if name == "mcn_bn_bwd_apply":
         n = args[4] * args[5]
         return n * esz * (3 + (1 if args[3] else 0) + (1 if args[16] else 0)), 0.0
+    if name in ("mcn_maxpool_fwd_tap", "mcn_maxpool_bwd_tap"):
+        # fwd: x in [N,H,W,C], y + one tap byte out; bwd: dy + tap in, dx out — same bytes
+        off = 2 if name == "mcn_maxpool_fwd_tap" else 3
+        n, h, w, c = args[off:off + 4]
+        ho, wo = args[off + 10], args[off + 11]
+        return n * c * (h * w * esz + ho * wo * (esz + 1)), 0.0
+    if name == "mcn_gap_fwd":
+        return args[2] * args[3] * args[4] * esz, 0.0
+    if name == "mcn_gap_bwd":
+        return args[3] * args[4] * args[5] * esz, 0.0
+    if name in ("mcn_scale_bcast_fwd", "mcn_scale_bcast_bwd"):
+        off = 3 if name == "mcn_scale_bcast_fwd" else 4
+        n = args[off] * args[off + 1] * args[off + 2]
+        return n * esz * (2 if name == "mcn_scale_bcast_fwd" else 3), 0.0
+    if name in ("mcn_act_fwd", "mcn_add_act_fwd"):
+        return args[2 if name == "mcn_act_fwd" else 3] * esz * (2 if name == "mcn_act_fwd" else 3), 0.0
     return 0.0, 0.0
 
 
+# libmcn entry point -> the CUDA kernel (family) it launches: launches are grouped by KERNEL, so the
+# fprop and dgrad calls of gemm_conv_kernel / halo_conv_kernel form one class
+KERNEL_OF = {
+    "mcn_conv2d_fprop_tc": "conv_tc (gemm_conv_kernel / halo_conv_kernel: fprop + dgrad)",
+    "mcn_conv2d_fprop_tc_stats": "conv_tc (gemm_conv_kernel / halo_conv_kernel: fprop + dgrad)",
+    "mcn_conv2d_dgrad_tc": "conv_tc (gemm_conv_kernel / halo_conv_kernel: fprop + dgrad)",
+    "mcn_conv2d_wgrad_tc": "wgrad_tc (wgrad_kernel / wgrad_halo_kernel + splitk_reduce)",
+    "mcn_stem_conv_fprop": "stem (stem_fprop_kernel / stem_wgrad_kernel)",
+    "mcn_stem_conv_wgrad": "stem (stem_fprop_kernel / stem_wgrad_kernel)",
+    "mcn_bn_apply_stats": "bn_apply", "mcn_bn_apply": "bn_apply",
+    "mcn_maxpool_fwd_tap": "maxpool", "mcn_maxpool_bwd_tap": "maxpool",
+    "mcn_dwconv2d_fwd": "dwconv", "mcn_dwconv2d_bwd_data": "dwconv", "mcn_dwconv2d_bwd_filter": "dwconv",
+    "mcn_conv2d_fprop_direct": "conv_direct (igemm_kernel)", "mcn_conv2d_dgrad_direct": "conv_direct (igemm_kernel)",
+    "mcn_conv2d_wgrad_direct": "conv_direct (igemm_kernel)",
+}
+
+
 def kernel_class(name, tag):
-    if name in ("mcn_conv2d_fprop_tc", "mcn_conv2d_fprop_tc_stats"):
-        return "conv_fprop_tc" if not tag.endswith("/dgrad") else "conv_dgrad_tc"
-    if name == "mcn_bn_apply_stats":
-        return "bn_apply"
-    return name.replace("mcn_", "")
+    return KERNEL_OF.get(name, name.replace("mcn_", ""))
 
 
 def profile_step(eng):
@@ -394,6 +431,12 @@ def main():
         t = torch.tensor([ms, ms_e2e], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(t[0]), float(t[1])
+    dp = None
+    if world > 1 and args.config == "r50":
+        # numeric parity of the N-rank step against one device at the global batch (small model)
+        from myconvnet_b200.dp_check import dp_parity
+        dp = dp_parity(rank, world, dtype="bf16", graph=True)
+        stage("data-parallel parity check done")
     if world > 1:
         # Tearing the NCCL communicator down while captured graphs still reference it can block;
         # peers leave right after the last collective and rank 0 exits with os._exit below.
@@ -408,26 +451,49 @@ def main():
     prof = profile_step(eng)
     prof = profile_step(eng)
     total_ms = sum(v[0] for v in prof.values())
+    esz = 2 if eng.plan.cdt == "bf16" else 4
+
+    def roof_of(cname, cms, cbytes, cflops, cn):
+        """achieved = algorithmic bytes (flops) of the class / its measured time; the bound is the one
+        that takes longer at the measured peaks."""
+        tensor_bound = cflops > 0 and (cflops / (tc_peak * 1e12)) > (cbytes / (hbm_peak * 1e9))
+        if tensor_bound:
+            ach = cflops / (cms * 1e-3) / 1e12
+            r = {"bound": "tensor", "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s", "frac": ach / tc_peak}
+        else:
+            ach = cbytes / (cms * 1e-3) / 1e9
+            r = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak}
+        r.update({"kernel": cname, "launches_per_step": cn, "share_of_step": cms / total_ms,
+                  "ms_per_step": cms})
+        return r
+    # per-LAUNCH roofline time = max(bytes / HBM peak, flops / tensor peak): what the class would take
+    # if every launch sat on its own roof (a class mixes HBM-bound 1x1 and tensor-bound 3x3 layers)
+    per_launch = {}
+    for cname, tag, lms, lb, lf in profile_step.detail:
+        t_roof = max(lb / (hbm_peak * 1e9), lf / (tc_peak * 1e12)) * 1e3
+        per_launch[cname] = per_launch.get(cname, 0.0) + t_roof
+    by_kernel = []
+    for cname, (cms, cbytes, cflops, cn) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+        if cms / total_ms < 0.005 or (cbytes == 0 and cflops == 0):
+            continue
+        r = roof_of(cname, cms, cbytes, cflops, cn)
+        r["frac_of_per_launch_roofline"] = per_launch.get(cname, 0.0) / cms if cms > 0 else None
+        by_kernel.append(r)
     top = max(prof.items(), key=lambda kv: kv[1][0])
     cname, (cms, cbytes, cflops, cn) = top
-    tensor_bound = cflops > 0 and (cflops / (tc_peak * 1e12)) > (cbytes / (hbm_peak * 1e9))
-    if tensor_bound:
-        ach = cflops / (cms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s", "frac": ach / tc_peak}
-    else:
-        ach = cbytes / (cms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak}
+    roof = roof_of(cname, cms, cbytes, cflops, cn)
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
         # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel class, from the
         # committed ncu capture of the same command (scripts/ncu_profile.sh)
-        t = json.load(open(tpath)).get("classes", {}).get(cname)
+        t = json.load(open(tpath)).get("classes", {}).get(cname.split(" ")[0])
         if t:
             traffic = t["dram_bytes_per_launch"]
-    roof.update({"kernel": cname, "launches_per_step": cn, "share_of_step": cms / total_ms,
-                 "peak_source": peak_src, "traffic": traffic,
-                 "note": "aggregate over the class's launches in one step; algorithmic bytes/flops per DESIGN.md"})
+    roof.update({"peak_source": peak_src, "traffic": traffic,
+                 "note": "dominant CUDA kernel by time share (fprop and dgrad are the same kernel); "
+                         "achieved = algorithmic flops or bytes of all its launches in one step / their "
+                         "CUDA-event time; peak = sustained bf16 GEMM / copy bandwidth of MEASURED_PEAKS.json"})
     table = {k: {"ms": v[0], "GB": v[1] / 1e9, "TFLOP": v[2] / 1e12, "launches": v[3],
                  "GB/s": (v[1] / 1e9) / (v[0] * 1e-3) if v[0] > 0 else 0,
                  "TFLOP/s": (v[2] / 1e12) / (v[0] * 1e-3) if v[0] > 0 else 0}
@@ -470,7 +536,9 @@ def main():
         "gpu_launches": eager_launches * args.steps,
         "launches_counted_by_library": L.launch_count() - launches0,
         "final_loss": loss,
+        "dp_parity": dp,
         "roofline": roof,
+        "roofline_by_kernel": by_kernel,
         "cpu_baseline": cpu,
         "clocks": sampler.summary(),
     }

@@ -335,14 +335,18 @@ int mcn_transpose_add_f32(const float* in, int taps, int rows, int cols, float* 
  * mailbox slot in every peer's memory over NVLink, raises a flag, waits for all flags and sums the
  * slots in rank order (bit-identical on all ranks).
  *   peers    : DEVICE array [world] of the peer-mapped base address of every rank's symmetric region
- *   mail_off : byte offset of this collective point's mailbox ([world][n0+n1] elements) in a region
+ *   mail_off : byte offset of this collective point's two mailboxes in a region: mailbox
+ *              (sequence & 1) starts at mail_off + (sequence & 1)*parity_stride and holds
+ *              [world][n0+n1] elements (double-buffered so that reuse can never overtake a slower
+ *              peer's read, whatever the number of collective points per step)
  *   flag_off : byte offset of its flag row ([world] uint64, zero-initialised)
+ *   The wait for the peers' flags is bounded by MCN_PEER_TIMEOUT_S seconds (default 1800).
  *   counter  : local device uint64 sequence number of this collective point (starts at 0)
  *   src0/src1: local source segments (n0, n1 elements; src1 may be NULL when n1 == 0)
  *   dst      : local destination, n0+n1 elements (may alias src0) */
-int mcn_peer_allreduce(const unsigned long long* peers, long long mail_off, long long flag_off,
-                       unsigned long long* counter, int is_f64, const void* src0, int n0,
-                       const void* src1, int n1, void* dst, int rank, int world, void* stream);
+int mcn_peer_allreduce(const unsigned long long* peers, long long mail_off, long long parity_stride,
+                       long long flag_off, unsigned long long* counter, int is_f64, const void* src0,
+                       int n0, const void* src1, int n1, void* dst, int rank, int world, void* stream);
 
 /* ---- generic helpers ---- */
 int mcn_fill_f32(float* p, long long n, float v, void* stream);

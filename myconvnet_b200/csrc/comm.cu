@@ -9,11 +9,19 @@
 // Replaces the reference's tower-after-tower statistics chain (convnet.py:1898-1914).
 //
 // Memory: a symmetric region per rank (torch.distributed._symmetric_memory; `peers` holds the
-// peer-mapped base address of every rank's region).  Each collective point of the step owns a
-// mailbox [world][n] and a flag row [world] inside it, and a local sequence counter.  A mailbox is
-// reused one step later; every rank passes at least one other collective point in between, which
-// orders the reuse after the previous read (a rank cannot raise its next flag before it has left
-// this kernel).
+// peer-mapped base address of every rank's region).  Each collective point of the step owns TWO
+// mailboxes [world][n] (selected by the parity of its sequence number), a flag row [world] and a
+// local sequence counter.  Double buffering makes reuse safe whatever the plan looks like: a rank
+// writes mailbox (seq & 1) again at seq + 2, which it can only reach after every peer has raised
+// its flag for seq + 1 — and a peer raises that flag only after it has left the kernel of seq,
+// i.e. after it has finished reading that mailbox.  (With a single buffer a plan with one
+// collective point per step could overwrite a slot a slower peer was still summing.)
+// The wait is bounded in TIME (%globaltimer), long and configurable (MCN_PEER_TIMEOUT_S, default
+// 1800 s like a process-group timeout): ranks legitimately drift apart by seconds (checkpoint
+// writes on rank 0, lazy initialisation, a data stall), and only a peer that is really gone should
+// turn into a launch failure.
+#include <cstdlib>
+
 #include "mcn_common.cuh"
 
 namespace mcn {
@@ -35,9 +43,9 @@ __device__ __forceinline__ T ld_sys(const T* p) {
 template <typename T>
 __global__ void __launch_bounds__(512)
 peer_allreduce_kernel(const unsigned long long* __restrict__ peers, long long mail_off,
-                      long long flag_off, unsigned long long* counter, const T* __restrict__ src0,
-                      int n0, const T* __restrict__ src1, int n1, T* __restrict__ dst, int rank,
-                      int world) {
+                      long long parity_stride, long long flag_off, unsigned long long* counter,
+                      const T* __restrict__ src0, int n0, const T* __restrict__ src1, int n1,
+                      T* __restrict__ dst, int rank, int world, unsigned long long timeout_ns) {
   __shared__ unsigned long long seq_s;
   const int n = n0 + n1;
   if (threadIdx.x == 0) {
@@ -46,9 +54,10 @@ peer_allreduce_kernel(const unsigned long long* __restrict__ peers, long long ma
   }
   __syncthreads();
   const unsigned long long seq = seq_s;
+  const long long box_off = mail_off + static_cast<long long>(seq & 1ull) * parity_stride;
   // 1. push my vector into slot [rank] of every rank's mailbox (my own included)
   for (int p = 0; p < world; ++p) {
-    T* slot = reinterpret_cast<T*>(peers[p] + mail_off) + static_cast<size_t>(rank) * n;
+    T* slot = reinterpret_cast<T*>(peers[p] + box_off) + static_cast<size_t>(rank) * n;
     for (int i = threadIdx.x; i < n; i += blockDim.x) slot[i] = i < n0 ? src0[i] : src1[i - n0];
   }
   __threadfence_system();
@@ -58,18 +67,23 @@ peer_allreduce_kernel(const unsigned long long* __restrict__ peers, long long ma
     st_release_sys(reinterpret_cast<unsigned long long*>(peers[threadIdx.x] + flag_off) + rank, seq);
     const unsigned long long* mine =
         reinterpret_cast<const unsigned long long*>(peers[rank] + flag_off) + threadIdx.x;
-    unsigned long long spins = 0;
+    unsigned long long t0 = 0, spins = 0;
     while (ld_acquire_sys(mine) < seq) {
-      if (++spins > (1ull << 25)) {   // ~20 s: a missing peer becomes a launch failure, not a hang
-        printf("mcn: peer all-reduce timeout rank=%d waiting for rank=%d seq=%llu\n", rank,
-               (int)threadIdx.x, seq);
-        __trap();
+      if ((++spins & 0xFFFFull) == 0) {            // look at the clock every 64k polls
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        if (now - t0 > timeout_ns) {               // a peer that is really gone: fail the launch
+          printf("mcn: peer all-reduce timeout rank=%d waiting for rank=%d seq=%llu\n", rank,
+                 (int)threadIdx.x, seq);
+          __trap();
+        }
       }
     }
   }
   __syncthreads();
   // 4. sum the mailbox in rank order
-  const T* box = reinterpret_cast<const T*>(peers[rank] + mail_off);
+  const T* box = reinterpret_cast<const T*>(peers[rank] + box_off);
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     T acc = ld_sys(box + i);
     for (int q = 1; q < world; ++q) acc += ld_sys(box + static_cast<size_t>(q) * n + i);
@@ -82,23 +96,35 @@ peer_allreduce_kernel(const unsigned long long* __restrict__ peers, long long ma
 
 using namespace mcn;
 
+static unsigned long long peer_timeout_ns() {
+  static unsigned long long v = 0;
+  if (v == 0) {
+    const char* e = getenv("MCN_PEER_TIMEOUT_S");
+    const double s = e ? atof(e) : 1800.0;
+    v = static_cast<unsigned long long>((s > 0 ? s : 1800.0) * 1e9);
+  }
+  return v;
+}
+
 extern "C" int mcn_peer_allreduce(const unsigned long long* peers, long long mail_off,
-                                  long long flag_off, unsigned long long* counter, int is_f64,
-                                  const void* src0, int n0, const void* src1, int n1, void* dst,
-                                  int rank, int world, void* stream) {
+                                  long long parity_stride, long long flag_off,
+                                  unsigned long long* counter, int is_f64, const void* src0, int n0,
+                                  const void* src1, int n1, void* dst, int rank, int world,
+                                  void* stream) {
   MCN_REQUIRE(peers && counter && src0 && dst && n0 > 0 && n1 >= 0 && (n1 == 0 || src1) &&
-                  world >= 1 && world <= 64 && rank >= 0 && rank < world,
+                  world >= 1 && world <= 64 && rank >= 0 && rank < world && parity_stride >= 0,
               "peer_allreduce: bad argument");
+  const unsigned long long tmo = peer_timeout_ns();
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (is_f64)
-    peer_allreduce_kernel<double><<<1, 512, 0, st>>>(peers, mail_off, flag_off, counter,
+    peer_allreduce_kernel<double><<<1, 512, 0, st>>>(peers, mail_off, parity_stride, flag_off, counter,
                                                      static_cast<const double*>(src0), n0,
                                                      static_cast<const double*>(src1), n1,
-                                                     static_cast<double*>(dst), rank, world);
+                                                     static_cast<double*>(dst), rank, world, tmo);
   else
-    peer_allreduce_kernel<float><<<1, 512, 0, st>>>(peers, mail_off, flag_off, counter,
+    peer_allreduce_kernel<float><<<1, 512, 0, st>>>(peers, mail_off, parity_stride, flag_off, counter,
                                                     static_cast<const float*>(src0), n0,
                                                     static_cast<const float*>(src1), n1,
-                                                    static_cast<float*>(dst), rank, world);
+                                                    static_cast<float*>(dst), rank, world, tmo);
   return after_launch("peer_allreduce");
 }

@@ -1,0 +1,64 @@
+"""Numeric parity of the data-parallel step: N ranks (synchronised BN over the peer all-reduce,
+bucketed gradient mean) against ONE device at the global batch — the parity target of SURVEY 8e
+(n GPUs are numerically one tower at the global batch; replaces the reference's per-tower
+normalisation and CPU gradient averaging, optimizers.py:117-147, convnet.py:1898-1914).
+
+Called under an initialised torch.distributed NCCL group (scripts/check_dp.py, bench.py --gpus N):
+a small ResNet-v1.5-50 (64x64, 8 images per rank) takes `steps` optimiser steps on every rank;
+rank 0 repeats them on one device with the concatenated batch and compares losses and variables;
+all ranks check that their replicas stayed bit-identical."""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def _rel_l2(a, b):
+    a = np.asarray(a, np.float64).ravel()
+    b = np.asarray(b, np.float64).ravel()
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-12))
+
+
+def dp_parity(rank, world, dtype="bf16", graph=True, steps=3, group=None):
+    from .engine import Engine, draw_initial_value
+    from .zoo import resnet50
+    group = group if group is not None else dist.group.WORLD
+    shape, ncls, b = [64, 64, 3], 16, 8
+    pm, _ = resnet50(shape, ncls, batch_size=b, compute_dtype=dtype)
+    rng = np.random.default_rng(0)
+    vals = {v.name: draw_initial_value(v, rng) for v in pm.graph.vars.values()}
+    for k in vals:
+        if k.endswith("gamma") and not vals[k].any():
+            vals[k] = np.full_like(vals[k], 0.5)
+    Xg = rng.uniform(size=[b * world] + shape).astype(np.float32)
+    Yg = rng.integers(0, ncls, size=b * world).astype(np.int32)
+    X, Y = Xg[rank * b:(rank + 1) * b], Yg[rank * b:(rank + 1) * b]
+    eng = Engine(pm, world_size=world, rank=rank, process_group=group, use_cuda_graph=graph,
+                 base_learning_rate=0.05)
+    eng.set_variables(vals)
+    losses = [eng.train_step(X, Y) for _ in range(steps)]
+    v_dp = eng.get_variables()
+    lt = torch.tensor(losses, dtype=torch.float64, device="cuda")
+    dist.all_reduce(lt, group=group)
+    lt /= world
+    chk = torch.tensor([float(np.sum(v_dp["block_None/logits/weights"].astype(np.float64)))],
+                       dtype=torch.float64, device="cuda")
+    lo, hi = chk.clone(), chk.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+    out = {"world": world, "dtype": dtype, "cuda_graph": bool(graph), "steps": steps,
+           "peer_allreduce": eng._peer is not None, "replicas_identical": float(hi - lo) == 0.0}
+    del eng
+    if rank == 0:
+        pm1, _ = resnet50(shape, ncls, batch_size=b * world, compute_dtype=dtype)
+        e1 = Engine(pm1, base_learning_rate=0.05)
+        e1.set_variables(vals)
+        l1 = [e1.train_step(Xg, Yg) for _ in range(steps)]
+        v1 = e1.get_variables()
+        worst = max((_rel_l2(v_dp[k], v1[k]), k) for k in v1 if "weights" in k or k.endswith("gamma"))
+        tol_v = 2e-3 if dtype == "f32" else 6e-2
+        tol_l = 1e-3 * abs(l1[0]) + (1e-4 if dtype == "f32" else 3e-2)
+        out.update({"loss_dp": [float(x) for x in lt.tolist()], "loss_one_device": [float(x) for x in l1],
+                    "worst_variable": worst[1], "worst_variable_rel_l2": worst[0],
+                    "pass": bool(worst[0] < tol_v and abs(float(lt[0]) - l1[0]) < tol_l and out["replicas_identical"])})
+        del e1
+    return out

@@ -51,7 +51,7 @@ def draw_initial_value(var, rng):
 class Engine(object):
     def __init__(self, model, optimizer="nesterov", keep=(), seed=0, conv_mode=2, device=None,
                  world_size=1, rank=0, process_group=None, use_cuda_graph=False,
-                 fetch_pred=True, **kwargs):
+                 fetch_pred=True, keep_grads=False, **kwargs):
         if not torch.cuda.is_available():
             raise RuntimeError("myconvnet_b200.Engine needs a CUDA device: there is no CPU execution "
                                "path (plans can be inspected on CPU through myconvnet_b200.plan.Plan)")
@@ -66,7 +66,8 @@ class Engine(object):
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         self.opt_kind = OPT_KINDS[optimizer.lower()]
         self.plan = Plan(self.graph, world_size=self.world, keep=keep, conv_mode=conv_mode,
-                         fetch_pred=fetch_pred, loss_scale=float(self.kw.get("loss_scaling_factor", 1.0)))
+                         fetch_pred=fetch_pred, loss_scale=float(self.kw.get("loss_scaling_factor", 1.0)),
+                         keep_grads=keep_grads)
         p = self.plan
         self.arena = torch.empty(p.arena_bytes + 1024, dtype=torch.uint8, device=self.device)
         base = self.arena.data_ptr()
@@ -147,6 +148,17 @@ class Engine(object):
         v = self.tensor_view(t)
         return v.float().cpu().numpy() if v.dtype != torch.int32 else v.cpu().numpy()
 
+    def fetch_grad(self, t):
+        """Gradient of the loss w.r.t. graph tensor t after the last backward pass, as float32 numpy
+        (Engine(keep_grads=True) only: gradient buffers are then never recycled).  None when the
+        tensor received no gradient."""
+        p = self.plan.grad_ptr.get(t)
+        if p is None:
+            return None
+        dt = self.plan._logits_dtype(t)
+        tdt = {"f32": torch.float32, "bf16": torch.bfloat16}[dt]
+        return self.view(p, t.size, tdt).view(*t.shape).float().cpu().numpy()
+
     # ------------------------------------------------------------------ launch resolution
     def _carg(self, a):
         if isinstance(a, Ptr):
@@ -204,7 +216,7 @@ class Engine(object):
                         else:
                             a0, n0, a1, n1 = seg[0].data_ptr(), seg[0].numel(), seg[1].data_ptr(), seg[1].numel()
                         check(self.lib.mcn_peer_allreduce(
-                            peer["peers"], peer["mail"][k], peer["flag"][k], peer["ctr"] + 8 * k,
+                            peer["peers"], peer["mail"][k], peer["stride"][k], peer["flag"][k], peer["ctr"] + 8 * k,
                             1 if t.dtype == torch.float64 else 0, a0, n0, a1, n1, t.data_ptr(), self.rank,
                             self.world, stream), "peer_allreduce")
                     else:
@@ -239,10 +251,11 @@ class Engine(object):
         import torch.distributed as dist
         try:
             import torch.distributed._symmetric_memory as symm
-            mail, off = [], 0
+            mail, stride, off = [], [], 0
             for _, _, _, nbytes, _, _ in pts:
                 mail.append(off)
-                off += (self.world * nbytes + 255) // 256 * 256
+                stride.append((self.world * nbytes + 255) // 256 * 256)
+                off += 2 * stride[-1]                      # two mailboxes per point (sequence parity)
             flag = [off + 512 * k for k in range(len(pts))]       # [world] uint64 per point, world <= 64
             off += 512 * len(pts)
             buf = symm.empty(off, dtype=torch.uint8, device=self.device)
@@ -254,7 +267,7 @@ class Engine(object):
             torch.cuda.synchronize(self.device)
             dist.barrier(group=group)                          # every region is zeroed before any push
             self._peer = {"buf": buf, "hdl": hdl, "ctr_t": ctr, "ctr": ctr.data_ptr(),
-                          "peers": int(hdl.buffer_ptrs_dev), "mail": mail, "flag": flag}
+                          "peers": int(hdl.buffer_ptrs_dev), "mail": mail, "stride": stride, "flag": flag}
         except Exception as e:                                     # noqa: BLE001
             sys.stderr.write("[myconvnet_b200] peer-memory all-reduce unavailable (%s: %s); "
                              "using NCCL for the BN statistics\n" % (type(e).__name__, e))

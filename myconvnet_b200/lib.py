@@ -85,7 +85,7 @@ SIGNATURES = {
     "mcn_opt_step": "ipilppp",
     "mcn_grad_sqnorm": "pilpp",
     "mcn_transpose_add_f32": "piiip",
-    "mcn_peer_allreduce": "pllpipipipii",
+    "mcn_peer_allreduce": "plllpipipipii",
     "mcn_xsum_decode": "pippi",
     "mcn_fill_f32": "plf",
     "mcn_scale_f32": "plf",

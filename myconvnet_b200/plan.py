@@ -112,13 +112,17 @@ class TempAllocator(object):
 
 class Plan(object):
     def __init__(self, graph, world_size=1, keep=(), conv_mode=2, fetch_pred=True,
-                 sync_bn=True, loss_scale=1.0, fuse_bn_stats=None):
+                 sync_bn=True, loss_scale=1.0, fuse_bn_stats=None, keep_grads=False):
         self.graph = graph
         if fuse_bn_stats is None:
             fuse_bn_stats = os.environ.get("MCN_FUSE_BN_STATS", "1") != "0"
         self.fuse_bn_stats = bool(fuse_bn_stats)
         self.world = int(world_size)
         self.keep = set(keep)            # tensors that must stay materialised (parity taps)
+        # parity aid: gradient buffers are never recycled and their addresses are recorded, so a
+        # test can read the gradient of ANY tensor after a step (layer-wise backward checks)
+        self.keep_grads = bool(keep_grads)
+        self.grad_ptr = {}
         self.conv_mode = conv_mode       # 2 = halo tiles where they pay off else im2col TMA, 1 = im2col, 0 = box
         self.fetch_pred = fetch_pred
         self.sync_bn = sync_bn and self.world > 1
@@ -471,6 +475,8 @@ class Plan(object):
         n = t.node
         if n is not None and n.op == "dense" and n.attrs.get("final") is not t:
             return n.attrs["final"].dtype
+        if n is not None and n.op == "softmax":
+            return "f32"          # probabilities are always written in fp32 (mcn_softmax_xent)
         return t.dtype
 
     def _f_input(self, node):
@@ -976,6 +982,9 @@ class Plan(object):
 
     def _release_grad(self, t):
         p, h = self.g.pop(t)
+        if self.keep_grads:
+            self.grad_ptr.setdefault(t, p)
+            return
         if h is not None:
             self.tfree(h)
 

@@ -66,11 +66,15 @@ class OracleTrainer(object):
         lr = self.base_lr * batch / 256.0 * lr_multiplier
         d_t = ops.ema_decay(m.moving_average_decay, self.global_step)
         with torch.no_grad():
-            # EMA shadows see the pre-step values (control deps optimizers.py:159,175)
-            for k, v in m.vars.items():
-                self.ema[k] = self.ema[k] - (1.0 - d_t) * (self.ema[k] - v)
+            # BN moving statistics are assigned, then the EMA shadows are updated: shadows of the
+            # trainable variables see their PRE-step values (control deps optimizers.py:159,175);
+            # the shadow of a moving statistic and the statistic's own assign are two unordered
+            # update ops in the reference (convnet.py:1869-1914 — a race, like SURVEY Appendix D.9),
+            # resolved here as "assign first": the shadow tracks the value inference would read.
             for k, v in m.bn_updates.items():
                 m.vars[k] = v.clone()
+            for k, v in m.vars.items():
+                self.ema[k] = self.ema[k] - (1.0 - d_t) * (self.ema[k] - v)
             t = self.global_step + 1
             for k in train:
                 w, g = m.vars[k].detach(), self.grads[k]

@@ -60,7 +60,7 @@ def main():
                 pr = eng._peer
                 for rep in range(3):
                     u = t.clone() + rep
-                    L.check(eng.lib.mcn_peer_allreduce(pr["peers"], pr["mail"][0], pr["flag"][0], pr["ctr"], 1,
+                    L.check(eng.lib.mcn_peer_allreduce(pr["peers"], pr["mail"][0], pr["stride"][0], pr["flag"][0], pr["ctr"], 1,
                                                        u.data_ptr(), 128, None, 0, u.data_ptr(), rank, world,
                                                        torch.cuda.current_stream().cuda_stream))
                     torch.cuda.synchronize()

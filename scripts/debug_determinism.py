@@ -1,4 +1,5 @@
-"""Diagnostic: run the same step repeatedly and report gradient entries that change between runs."""
+"""Diagnostic: run the same step repeatedly at a given shape and report the first activations /
+gradients / tensor gradients that change between runs (bitwise)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -6,26 +7,38 @@ from tests.util import build_pair, synthetic_batch
 from myconvnet_b200.engine import Engine
 
 dtype = sys.argv[1]
-keep = sys.argv[2] == "keep"
-SHAPE, NCLS, BATCH = [64, 64, 3], 16, 8
-pm, om, vals = build_pair("models/resnet_v1_5.py", "ResNet50", SHAPE, NCLS, BATCH, dtype)
-X, Y = synthetic_batch(BATCH, SHAPE, NCLS)
-taps = {k: t for k, t in pm.d.items() if hasattr(t, "shape") and k not in ("pred",)}
-eng = Engine(pm, keep=list(taps.values()) if keep else ())
+hw, batch, ncls = int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
+runs_n = int(sys.argv[5]) if len(sys.argv) > 5 else 4
+SHAPE = [hw, hw, 3]
+pm, om, vals = build_pair("models/resnet_v1_5.py", "ResNet50", SHAPE, ncls, batch, dtype)
+X, Y = synthetic_batch(batch, SHAPE, ncls)
+eng = Engine(pm, keep_grads=True)
 eng.set_variables(vals)
+acts = [t for n in pm.graph.nodes for t in n.outputs if t in eng.plan.tbuf]
 runs = []
-for r in range(6):
-    eng.train_step(X, Y, update=False)
-    runs.append(eng.get_gradients())
-names = list(runs[0].keys())
-for k in names:
-    base = runs[0][k].ravel()
-    worst = 0.0
-    nvar = 0
-    for r in runs[1:]:
-        d = np.abs(r[k].ravel() - base)
-        worst = max(worst, float(d.max() / (np.abs(base).max() + 1e-20)))
-        nvar = max(nvar, int((d > 1e-4 * np.abs(base).max()).sum()))
-    if worst > 1e-4:
-        print("%-50s max rel change %.3g  entries varying %d / %d" % (k, worst, nvar, base.size))
+for r in range(runs_n):
+    loss = eng.train_step(X, Y, update=False)
+    a = {("act", t.node.scope, t.node.op, t.id if hasattr(t, "id") else 0): eng.fetch(t) for t in acts}
+    tg = {}
+    for t in acts:
+        g = eng.fetch_grad(t)
+        if g is not None:
+            tg[("tgrad", t.node.scope, t.node.op, 0)] = g
+    pg = {("pgrad", k, "", 0): v for k, v in eng.get_gradients().items()}
+    runs.append((loss, a, tg, pg))
+print("losses", [r[0] for r in runs])
+for idx, label in ((1, "activations"), (2, "tensor gradients (backward order = reverse)"), (3, "parameter gradients")):
+    print("==", label)
+    keys = list(runs[0][idx].keys())
+    if idx == 2:
+        keys = keys[::-1]
+    shown = 0
+    for k in keys:
+        base = runs[0][idx][k]
+        nd = max(int((r[idx][k] != base).sum()) for r in runs[1:])
+        if nd:
+            print("  %-70s differing %d / %d" % (k[1] + " " + k[2], nd, base.size))
+            shown += 1
+            if shown >= 12:
+                break
 print("done")

@@ -7,7 +7,7 @@ import pytest
 
 from myconvnet_b200 import loader
 from myconvnet_b200.engine import draw_initial_value
-from tests.util import rel_l2
+from tests.util import layerwise_backward_errors, layerwise_forward_errors, rel_l2, worst
 
 pytestmark = pytest.mark.gpu
 
@@ -48,6 +48,17 @@ def _check(pm, om, vals, X, Y, dtype, steps=3, curve_tol=None):
         assert not bad, bad[:6]
     grads = eng.get_gradients()
     assert all(np.isfinite(g).all() for g in grads.values())
+    # the production (fused) plan, layer by layer with teacher forcing, forward and backward: every
+    # conv / depthwise conv / dense / BN(+activation) / pool node against the oracle op at the
+    # device's own tensors (tests/util.py) — one layer's arithmetic per comparison
+    eng3 = Engine(pm, keep_grads=True)
+    eng3.set_variables(vals)
+    eng3.train_step(X, Y, update=False)
+    ferr = layerwise_forward_errors(eng3, pm)
+    berr = layerwise_backward_errors(eng3, pm)
+    assert ferr and worst(ferr, 1)[0][1] <= (5e-5 if dtype == "f32" else 6e-3), worst(ferr)
+    assert berr and worst(berr, 1)[0][1] <= (2e-4 if dtype == "f32" else 1e-2), worst(berr)
+    del eng3
     # fused plan over a few optimiser steps
     eng2 = Engine(pm)
     eng2.set_variables(vals)

@@ -124,3 +124,121 @@ def layerwise_forward_errors(eng, pm):
             errs["gap:%d" % node.id] = rel_l2(fetch(node.outputs[0]).numpy().reshape(x.shape[0], -1),
                                               x.mean(dim=(1, 2)).numpy())
     return errs
+
+
+def layerwise_backward_errors(eng, pm):
+    """Teacher-forced layer-by-layer check of the LAST backward pass of `eng`
+    (Engine(keep_grads=True), after train_step(update=False)): for every convolution, dense layer,
+    batch-norm (+ fused residual / activation), max-pool and global-average-pool node the oracle
+    op is differentiated (torch autograd) at the DEVICE's own input tensors with the DEVICE's own
+    upstream gradient; its parameter gradients are compared with the device's (all of them) and its
+    input gradient with the device's whenever that input has no other consumer.  Returns
+    {node scope / what: rel-L2}."""
+    import torch
+    from oracle import tf_ops as ops
+    rd = (lambda t: t.bfloat16().float()) if pm.graph.compute_dtype == "bf16" else (lambda t: t)
+    variables = {k: torch.from_numpy(v) for k, v in eng.get_variables().items()}
+    dev_grads = eng.get_gradients()
+    uses = {}
+    for node in pm.graph.nodes:
+        for v in node.vars.values():
+            uses[v.name] = uses.get(v.name, 0) + 1
+    kinds = {0: None, 1: "relu", 2: "relu6", 3: "lrelu", 4: "tanh", 5: "sigmoid", 6: "swish"}
+    errs = {}
+
+    def fetch(t, grad=False):
+        a = eng.fetch_grad(t) if grad else eng.fetch(t)
+        return None if a is None else torch.from_numpy(np.asarray(a, dtype=np.float32))
+
+    def leaf(t):
+        return t.clone().requires_grad_(True)
+
+    def sole_consumer(t, node):
+        cons = [c.attrs.get("fused_into") or c for c in t.consumers]
+        return len(cons) == 1 and cons[0] is node
+
+    def cmp_var(node, key, grad_t, tag, floor=0.0):
+        """floor: natural scale of the sum (||upstream gradient||_F for the per-channel sums dbeta /
+        dgamma / dbias).  When the true value cancels to rounding noise (a BN whose shift is removed
+        by a following BN has dbeta == 0 up to 1e-10) the error is measured against 1 % of that
+        scale instead of against the noise."""
+        v = node.vars.get(key)
+        if v is not None and v.trainable and uses[v.name] == 1 and v.name in dev_grads:
+            ref = grad_t.numpy().astype(np.float64)
+            den = max(float(np.linalg.norm(ref)), 0.01 * floor)
+            if den > 1e-30:
+                errs[node.scope + "/" + tag] = float(np.linalg.norm(dev_grads[v.name].astype(np.float64) - ref) / den)
+
+    for node in pm.graph.nodes:
+        if node.attrs.get("fused_into") is not None:
+            continue
+        a = node.attrs
+        if node.op in ("conv2d", "dwconv2d", "dense"):
+            out = a.get("final", node.outputs[0])
+            gy = fetch(out, grad=True)
+            if gy is None:
+                continue
+            x = leaf(fetch(node.inputs[0]))
+            w = leaf(rd(variables[node.vars["w"].name]))
+            b = leaf(variables[node.vars["b"].name]) if "b" in node.vars else None
+            if node.op == "dense":
+                y = ops.dense(x, w, b)
+            else:
+                pad = "SAME" if (a["pad"][0] or a["pad"][1] or node.outputs[0].shape[1] * a["s"][0] >= x.shape[1]) else "VALID"
+                f = ops.depthwise_conv2d if node.op == "dwconv2d" else ops.conv2d
+                y = f(x, w, a["s"], pad, a["d"])
+                if b is not None:
+                    y = y + b
+            y.backward(gy)
+            cmp_var(node, "w", w.grad, "dw")
+            if b is not None:
+                cmp_var(node, "b", b.grad, "db", floor=float(gy.norm()))
+            gx = fetch(node.inputs[0], grad=True)
+            if gx is not None and sole_consumer(node.inputs[0], node) and float(x.grad.norm()) > 1e-12:
+                errs[node.scope + "/dx"] = rel_l2(gx.numpy(), x.grad.numpy())
+        elif node.op == "bn" and a.get("update", True):
+            final = a.get("final", node.outputs[0])
+            gy = fetch(final, grad=True)
+            if gy is None:
+                continue
+            x = leaf(fetch(node.inputs[0]))
+            g = leaf(variables[node.vars["gamma"].name]) if "gamma" in node.vars else None
+            be = leaf(variables[node.vars["beta"].name]) if "beta" in node.vars else None
+            y, _, _ = ops.fused_batch_norm_train(x, g, be, a["eps"])
+            r = None
+            if a.get("residual") is not None:
+                r = leaf(fetch(a["residual"]))
+                y = y + r
+            if a.get("act", 0) == 1:
+                # ReLU on the DEVICE's pattern: a pre-activation within one ulp of zero may round to
+                # the other side in the oracle's summation order, and one flipped element moves a
+                # per-channel sum over 1e5 rows by ~1e-3 relative — mask luck, not arithmetic
+                y = y * (fetch(final) > 0).to(y.dtype)
+            elif a.get("act", 0):
+                y = ops.activation(y, kinds[a["act"]], a.get("alpha") or None)
+            y.backward(gy)
+            if g is not None:
+                cmp_var(node, "gamma", g.grad, "dgamma", floor=float(gy.norm()))
+            if be is not None:
+                cmp_var(node, "beta", be.grad, "dbeta", floor=float(gy.norm()))
+            gx = fetch(node.inputs[0], grad=True)
+            if gx is not None and sole_consumer(node.inputs[0], node):
+                errs[node.scope + "/bn_dx"] = rel_l2(gx.numpy(), x.grad.numpy())
+            if r is not None:
+                gr = fetch(a["residual"], grad=True)
+                if gr is not None and sole_consumer(a["residual"], node):
+                    errs[node.scope + "/bn_dres"] = rel_l2(gr.numpy(), r.grad.numpy())
+        elif node.op in ("max_pool", "gap"):
+            gy = fetch(node.outputs[0], grad=True)
+            gx = fetch(node.inputs[0], grad=True)
+            if gy is None or gx is None or not sole_consumer(node.inputs[0], node):
+                continue
+            x = leaf(fetch(node.inputs[0]))
+            if node.op == "gap":
+                y = x.mean(dim=(1, 2)).reshape(gy.shape)
+            else:
+                pad = "SAME" if node.outputs[0].shape[1] * a["s"][0] >= x.shape[1] else "VALID"
+                y = ops.max_pool(x, a["k"], a["s"], pad)
+            y.backward(gy)
+            errs["%s:%d/dx" % (node.op, node.id)] = rel_l2(gx.numpy(), x.grad.numpy())
+    return errs
