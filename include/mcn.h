@@ -52,6 +52,11 @@ const char* mcn_last_error(void);
 int mcn_version(void);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 long long mcn_launch_count(void);
+/* Debug aid: cycles each warp role of the tensor-core conv kernels spent waiting on its barriers,
+ * summed over all CTAs since the last reset.  Only the -DMCN_ROLE_TIMING build (MCN_ROLE_TIMING=1
+ * python -m myconvnet_b200.build -> libmcn_timing.so, scripts/role_timing.py) counts; the production
+ * library returns zeros. */
+int mcn_debug_role_cycles(unsigned long long* out16, int reset);
 
 /* ---- determinism: workspace and exact accumulators --------------------------------------
  * No entry point of this library uses floating-point atomics: every cross-block reduction is

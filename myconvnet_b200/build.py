@@ -9,7 +9,10 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libmcn.so")
+# MCN_ROLE_TIMING=1: the instrumented build (per-role stall counters in the conv kernels) as a
+# separate library, never loaded by default (MCN_LIB=.../libmcn_timing.so selects it)
+TIMING = os.environ.get("MCN_ROLE_TIMING", "0") == "1"
+LIB = os.path.join(HERE, "libmcn_timing.so" if TIMING else "libmcn.so")
 SOURCES = ["runtime.cu", "conv_tc.cu", "conv_direct.cu", "bn.cu", "pool.cu", "eltwise.cu",
            "loss.cu", "opt.cu", "comm.cu", "dropout.cu", "dwconv.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -37,14 +40,15 @@ def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    objdir = os.path.join(HERE, "..", "build", "obj")
+    objdir = os.path.join(HERE, "..", "build", "obj_timing" if TIMING else "obj")
     os.makedirs(objdir, exist_ok=True)
     procs = []
     objs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [nvcc, *NVCC_FLAGS, *(["--use_fast_math"] if src in FAST_MATH else []), "-c",
+        cmd = [nvcc, *NVCC_FLAGS, *(["-DMCN_ROLE_TIMING"] if TIMING else []),
+               *(["--use_fast_math"] if src in FAST_MATH else []), "-c",
                os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")

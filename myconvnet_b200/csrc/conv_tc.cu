@@ -31,6 +31,31 @@
 namespace mcn {
 namespace {
 
+// Per-role stall accounting (build with -DMCN_ROLE_TIMING, scripts/role_timing.py): cycles each
+// role spends waiting on its barriers, summed over the CTAs of every launch since the last reset.
+//   0 producer waits for a free stage   1 MMA waits for operands      2 MMA waits for a free accumulator
+//   3 epilogue waits for an accumulator 4 epilogue total              5 CTA lifetime   6 CTAs   7 MMA total
+#ifdef MCN_ROLE_TIMING
+__device__ unsigned long long g_role_cycles[16];
+#define RT_DECL unsigned long long rt_acc = 0, rt_acc2 = 0, rt_t0 = 0; (void)rt_acc2; (void)rt_t0
+#define RT_BEGIN rt_t0 = clock64()
+#define RT_END rt_acc += clock64() - rt_t0
+#define RT_END2 rt_acc2 += clock64() - rt_t0
+#define RT_FLUSH(slot) atomicAdd(&g_role_cycles[slot], rt_acc)
+#define RT_FLUSH2(slot) atomicAdd(&g_role_cycles[slot], rt_acc2)
+#define RT_ADD(slot, v) atomicAdd(&g_role_cycles[slot], static_cast<unsigned long long>(v))
+#define RT_NOW() clock64()
+#else
+#define RT_DECL
+#define RT_BEGIN
+#define RT_END
+#define RT_END2
+#define RT_FLUSH(slot)
+#define RT_FLUSH2(slot)
+#define RT_ADD(slot, v)
+#define RT_NOW() 0ll
+#endif
+
 constexpr int kMaxTaps = 52;
 constexpr int kABytes = 128 * 128;  // one activation tile: 128 rows x 64 bf16
 
@@ -209,7 +234,13 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t tmem_ac
     }
   };
   if (acc_bf16 && chunk_first < e.block_n) prefetch_old(chunk_first);
+#ifdef MCN_ROLE_TIMING
+  const long long rt_w0 = clock64();
+#endif
   ptx::mbar_wait(tmem_full_bar, tph);
+#ifdef MCN_ROLE_TIMING
+  if (quad == 0 && lane == 0) RT_ADD(3, clock64() - rt_w0);
+#endif
   ptx::tc_fence_after();
   if (chunk_first >= e.block_n) {
     // nothing to drain for this warp (narrow tile): it still takes part in the hand-back count
@@ -393,10 +424,13 @@ gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const long long rt_cta0 = RT_NOW();
+  (void)rt_cta0;
 
   if (warp == 0) {
     // ---------------- TMA producer ----------------
     if (ptx::elect_one()) {
+      RT_DECL;
       const uint32_t a_tx = (args.g.a_mode == 0) ? static_cast<uint32_t>(args.g.rows_box) * 128u
                                                  : static_cast<uint32_t>(kABytes);
       if (bstat) {
@@ -416,7 +450,9 @@ gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
           for (int kc = 0; kc < args.k_chunks; ++kc, ++it) {
             const int s = it % stages;
             const uint32_t ph = static_cast<uint32_t>(it / stages) & 1u;
+            RT_BEGIN;
             ptx::mbar_wait(&empty[s], ph ^ 1u);
+            RT_END;
             ptx::mbar_expect_tx(&full[s], bstat ? a_tx : a_tx + b_bytes);
             uint8_t* sA = smem + static_cast<size_t>(s) * stage_bytes;
             uint8_t* sB = sA + kABytes;
@@ -434,16 +470,22 @@ gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
           }
         }
       }
+      RT_FLUSH(0);
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
+    RT_DECL;
+    const long long rt_m0 = RT_NOW();
+    (void)rt_m0;
     const uint32_t idesc = ptx::make_idesc_bf16(128, args.block_n, 0, 0);
     if (bstat) ptx::mbar_wait(bstat_bar, 0);
     int it = 0, lt = 0;
     for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x, ++lt) {
       const int buf = lt & 1;
       const uint32_t tph = static_cast<uint32_t>(lt >> 1) & 1u;
+      RT_BEGIN;
       ptx::mbar_wait(&tmem_empty[buf], tph ^ 1u);   // epilogue has drained this accumulator
+      RT_END2;
       ptx::tc_fence_after();
       const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * args.block_n);
       int kit = 0;
@@ -451,7 +493,9 @@ gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
         for (int kc = 0; kc < args.k_chunks; ++kc, ++it, ++kit) {
           const int s = it % stages;
           const uint32_t ph = static_cast<uint32_t>(it / stages) & 1u;
+          RT_BEGIN;
           ptx::mbar_wait(&full[s], ph);
+          RT_END;
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
             const uint32_t a_addr = ptx::smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
@@ -470,8 +514,15 @@ gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
         }
       }
     }
+    if (lane == 0) {
+      RT_FLUSH(1);
+      RT_FLUSH2(2);
+      RT_ADD(7, RT_NOW() - rt_m0);
+    }
   } else {
     // ---------------- epilogue: TMEM -> registers -> global ----------------
+    const long long rt_e0 = RT_NOW();
+    (void)rt_e0;
     // Each thread owns one output pixel (row) and walks its channels 64 at a time: 64 bf16 = one
     // full 128-byte line written with four 32-byte stores (fp32 output: eight).
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
@@ -511,10 +562,15 @@ gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
                     chunk_step);
     }
     if (stats && cur_nt >= 0) stats_flush(args.e, stat_acc_all, cur_nt, row, pending, stat_flag);
+    if (row == 0) RT_ADD(4, RT_NOW() - rt_e0);
   }
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) {
+    RT_ADD(5, RT_NOW() - rt_cta0);
+    RT_ADD(6, 1);
+  }
   if (warp == 1) ptx::tmem_dealloc(tmem_base, static_cast<uint32_t>(args.tmem_cols));
 }
 
@@ -589,10 +645,13 @@ halo_conv_kernel(const __grid_constant__ HaloArgs args) {
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int tiles_per_img = args.tiles_w * args.tiles_h;
+  const long long rt_cta0 = RT_NOW();
+  (void)rt_cta0;
 
   if (warp == 0) {
     // ---------------- activation (halo) producer ----------------
     if (ptx::elect_one()) {
+      RT_DECL;
       const uint32_t a_tx = static_cast<uint32_t>(args.hwb * args.hhb) * 128u;
       int ita = 0;
       for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x) {
@@ -603,12 +662,15 @@ halo_conv_kernel(const __grid_constant__ HaloArgs args) {
         for (int kc = 0; kc < args.k_chunks; ++kc, ++ita) {
           const int s = ita % args.a_stages;
           const uint32_t ph = static_cast<uint32_t>(ita / args.a_stages) & 1u;
+          RT_BEGIN;
           ptx::mbar_wait(&empty_a[s], ph ^ 1u);
+          RT_END;
           ptx::mbar_expect_tx(&full_a[s], a_tx);
           ptx::tma_load_4d(&args.mapA, &full_a[s], smemA + static_cast<size_t>(s) * args.halo_stride,
                            kc * 64, w0 + args.org_w, h0 + args.org_h, n);
         }
       }
+      RT_FLUSH(0);
     }
   } else if (warp == 2) {
     // ---------------- weight producer ----------------
@@ -643,17 +705,24 @@ halo_conv_kernel(const __grid_constant__ HaloArgs args) {
     const uint32_t idesc = ptx::make_idesc_bf16(128, args.e.block_n, 0, 0);
     const uint32_t sbo = static_cast<uint32_t>(args.hwb) * 128u;
     int ita = 0, itb = 0, lt = 0;
+    RT_DECL;
+    const long long rt_m0 = RT_NOW();
+    (void)rt_m0;
     if (args.b_stationary) ptx::mbar_wait(&full_b[0], 0);
     for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x, ++lt) {
       const int buf = lt & 1;
       const uint32_t tph = static_cast<uint32_t>(lt >> 1) & 1u;
+      RT_BEGIN;
       ptx::mbar_wait(&tmem_empty[buf], tph ^ 1u);
+      RT_END2;
       ptx::tc_fence_after();
       const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * args.e.block_n);
       int kit = 0;
       for (int kc = 0; kc < args.k_chunks; ++kc, ++ita) {
         const int sa = ita % args.a_stages;
+        RT_BEGIN;
         ptx::mbar_wait(&full_a[sa], static_cast<uint32_t>(ita / args.a_stages) & 1u);
+        RT_END;
         ptx::tc_fence_after();
         const uint32_t a_base = ptx::smem_u32(smemA + static_cast<size_t>(sa) * args.halo_stride);
         for (int t = 0; t < args.taps; ++t, ++itb, ++kit) {
@@ -662,7 +731,9 @@ halo_conv_kernel(const __grid_constant__ HaloArgs args) {
             sb = kc * args.taps + t;
           } else {
             sb = itb % args.b_stages;
+            RT_BEGIN;
             ptx::mbar_wait(&full_b[sb], static_cast<uint32_t>(itb / args.b_stages) & 1u);
+            RT_END;
             ptx::tc_fence_after();
           }
           if (ptx::elect_one()) {
@@ -682,8 +753,15 @@ halo_conv_kernel(const __grid_constant__ HaloArgs args) {
         }
       }
     }
+    if (lane == 0) {
+      RT_FLUSH(1);
+      RT_FLUSH2(2);
+      RT_ADD(7, RT_NOW() - rt_m0);
+    }
   } else {
     // ---------------- epilogue (warps 3..6) ----------------
+    const long long rt_e0 = RT_NOW();
+    (void)rt_e0;
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     uint32_t* stat_stage = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + kBarRegionBytes);
@@ -719,10 +797,15 @@ halo_conv_kernel(const __grid_constant__ HaloArgs args) {
                     off, n_t, &tmem_full[buf], tph, &tmem_empty[buf], stat_stage, stat_acc);
     }
     if (stats && cur_nt >= 0) stats_flush(args.e, stat_acc_all, cur_nt, row, pending, stat_flag);
+    if (row == 0) RT_ADD(4, RT_NOW() - rt_e0);
   }
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) {
+    RT_ADD(5, RT_NOW() - rt_cta0);
+    RT_ADD(6, 1);
+  }
   if (warp == 1) ptx::tmem_dealloc(tmem_base, static_cast<uint32_t>(args.tmem_cols));
 }
 
@@ -794,6 +877,8 @@ wgrad_kernel(const __grid_constant__ WgradArgs args) {
   const int kb0 = static_cast<int>(static_cast<long long>(split) * args.kblocks_total / args.splits);
   const int kb1 =
       static_cast<int>(static_cast<long long>(split + 1) * args.kblocks_total / args.splits);
+  const long long rt_cta0 = RT_NOW();
+  (void)rt_cta0;
 
   // Rows a tiled box does not cover must read as zero (K padding): clear the stage buffers once.
   {
@@ -826,10 +911,14 @@ wgrad_kernel(const __grid_constant__ WgradArgs args) {
       const uint32_t rows_bytes =
           (args.g.a_mode == 0) ? static_cast<uint32_t>(args.g.rows_box) * 128u : kABytes;
       const uint32_t tx = rows_bytes * static_cast<uint32_t>(2 + args.nb_atoms);
+      RT_DECL;
+      RT_ADD(2, RT_NOW() - rt_cta0);      // wgrad: slot 2 = prologue (smem clear, barrier init, TMEM alloc)
       for (int kb = kb0, it = 0; kb < kb1; ++kb, ++it) {
         const int s = it % stages;
         const uint32_t ph = static_cast<uint32_t>(it / stages) & 1u;
+        RT_BEGIN;
         ptx::mbar_wait(&empty[s], ph ^ 1u);
+        RT_END;
         ptx::mbar_expect_tx(&full[s], tx);
         uint8_t* sA = smem + static_cast<size_t>(s) * stage_bytes;
         uint8_t* sB = sA + a_bytes;
@@ -856,13 +945,19 @@ wgrad_kernel(const __grid_constant__ WgradArgs args) {
           }
         }
       }
+      RT_FLUSH(0);
     }
   } else if (warp == 1) {
     const uint32_t idesc = ptx::make_idesc_bf16(128, args.block_n, 1, 1);
+    RT_DECL;
+    const long long rt_m0 = RT_NOW();
+    (void)rt_m0;
     for (int kb = kb0, it = 0; kb < kb1; ++kb, ++it) {
       const int s = it % stages;
       const uint32_t ph = static_cast<uint32_t>(it / stages) & 1u;
+      RT_BEGIN;
       ptx::mbar_wait(&full[s], ph);
+      RT_END;
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
         const uint32_t a_addr = ptx::smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
@@ -879,8 +974,15 @@ wgrad_kernel(const __grid_constant__ WgradArgs args) {
       }
       __syncwarp();
     }
+    if (lane == 0) {
+      RT_FLUSH(1);
+      RT_ADD(7, RT_NOW() - rt_m0);
+    }
   } else {
+    const long long rt_e0 = RT_NOW();
+    (void)rt_e0;
     ptx::mbar_wait(tmem_full, 0);
+    if (threadIdx.x == 64) RT_ADD(3, RT_NOW() - rt_e0);
     ptx::tc_fence_after();
     const int quad = warp & 3;
     const int ci = mi * 128 + quad * 32 + lane;
@@ -906,10 +1008,15 @@ wgrad_kernel(const __grid_constant__ WgradArgs args) {
           }
       }
     }
+    if (threadIdx.x == 64) RT_ADD(4, RT_NOW() - rt_e0);
   }
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) {
+    RT_ADD(5, RT_NOW() - rt_cta0);
+    RT_ADD(6, 1);
+  }
   if (warp == 1) ptx::tmem_dealloc(tmem_base, static_cast<uint32_t>(args.tmem_cols));
 }
 
@@ -2281,7 +2388,9 @@ static int wgrad_tc_impl(const mcn_conv_desc* d, const void* x, const void* dy, 
   a.ksteps = (a.g.a_mode == 0) ? (a.g.rows_box + 15) / 16 : 8;
   {
     const int base = taps * a.tiles_mi * a.tiles_ni;
-    int want = (2 * num_sms() + base - 1) / base;
+    // two full waves of one-CTA-per-SM at most: rounding the split count UP (304 CTAs for a base of
+    // 16) left a third, nearly empty wave behind
+    int want = std::max(1, (2 * num_sms()) / base);
     // one CTA per SM is resident at a time, so a grid that already fills 3/4 of the SMs gains
     // nothing from splitting K — and an un-split K needs no slices and no second pass
     if (4 * base >= 3 * num_sms()) want = 1;
@@ -2481,4 +2590,22 @@ extern "C" long long mcn_conv2d_wgrad_workspace_bytes(const mcn_conv_desc* d, in
   const int rc = stem ? stem_wgrad_impl(d, nullptr, nullptr, nullptr, nullptr, &q)
                       : wgrad_tc_impl(d, nullptr, nullptr, nullptr, a_mode, nullptr, &q);
   return rc ? static_cast<long long>(rc) : q;
+}
+
+// Debug: per-role stall cycles accumulated by the -DMCN_ROLE_TIMING build (zeros otherwise).
+extern "C" int mcn_debug_role_cycles(unsigned long long* out16, int reset) {
+  MCN_REQUIRE(out16 != nullptr, "debug_role_cycles: null argument");
+#ifdef MCN_ROLE_TIMING
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out16, g_role_cycles, sizeof(unsigned long long) * 16);
+  if (reset) {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(g_role_cycles, z, sizeof(z));
+  }
+  return MCN_OK;
+#else
+  for (int i = 0; i < 16; ++i) out16[i] = 0;
+  (void)reset;
+  return MCN_OK;
+#endif
 }

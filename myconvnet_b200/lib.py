@@ -7,7 +7,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmcn.so")
+LIB_PATH = os.environ.get("MCN_LIB") or os.path.join(HERE, "libmcn.so")   # MCN_LIB: the instrumented build (build.py)
 
 
 class ConvDescC(ctypes.Structure):
@@ -114,6 +114,8 @@ def load():
     lib.mcn_launch_count.restype = ctypes.c_longlong
     lib.mcn_stem_conv_kpad.restype = ctypes.c_int
     lib.mcn_stem_conv_kpad.argtypes = [ctypes.POINTER(ConvDescC)]
+    lib.mcn_debug_role_cycles.restype = ctypes.c_int
+    lib.mcn_debug_role_cycles.argtypes = [ctypes.c_void_p, ctypes.c_int]
     lib.mcn_set_workspace.restype = ctypes.c_int
     lib.mcn_set_workspace.argtypes = [ctypes.c_void_p, ctypes.c_longlong]
     lib.mcn_workspace_min_bytes.restype = ctypes.c_longlong
