@@ -134,7 +134,9 @@ struct EpiArgs {
   unsigned int* xs_counter;   // one tile counter per n-tile
   int tiles_m;     // tiles per n-tile
   int out_f32, vec_ok, accumulate, block_n, n_total;
-  int debug;   // bit0: skip stores, bit1: skip MMA issue, bit2: skip TMEM loads (timing experiments)
+  int debug;   // bit0: skip stores, bit2: skip TMEM loads (timing experiments, direct epilogue only)
+  int stg_bufs;    // TMA-store epilogue: 4 KB staging tiles per epilogue warp (1 or 2)
+  int out_rank4;   // TMA-store epilogue: the output map is (C, W, H, N) instead of [M, C]
 };
 
 // Fused BN statistics (conv -> BN): the epilogue already holds every output element in
@@ -154,7 +156,7 @@ constexpr int kStatAccWarp = 2 * 256;                            // [sum | sum s
 constexpr int kStatAccFloats = 4 * kStatAccWarp;                 // one slice per epilogue warp
 constexpr int kEpiStageBytes = kStatStageWords * 4;              // always: the store path stages through it
 constexpr int kStatAccBytes = kStatAccFloats * 4;                // only with fused statistics
-constexpr int kBarRegionBytes = 256;                             // mbarriers + tmem slot
+constexpr int kBarRegionBytes = 512;                             // mbarriers + tmem slot, halo tap table at +256
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
@@ -359,10 +361,120 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& e, uint32_t tmem_ac
   }
 }
 
+// ------------------------------------------------------------------ TMA-store epilogue
+// The direct epilogue above writes one 128-byte row segment per THREAD: every 32-byte store
+// instruction of a warp touches 32 different lines, and the L1 store path (one line per cycle or
+// so) — not HBM, not the tensor pipe — paced the store-heavy 1x1 convolutions (per-role counters,
+// profiles/r02_role_timing.txt: the MMA warp spent 71 % of a 64->256 fprop waiting for a free
+// accumulator).  Here a warp packs its 32 rows x 64 channels into a 4 KB shared-memory tile in the
+// tensor map's 128-byte swizzle (conflict-free 16-byte stores) and one lane hands it to the TMA
+// unit: cp.async.bulk.tensor store, or cp.reduce.async.bulk.tensor .add for the accumulating dgrad
+// (the sum happens in the memory system: no read-modify-write through registers; the addend is
+// rounded to bf16 first, i.e. dx = bf16(dx + bf16(acc))).  Rows and columns outside the tensor are
+// clipped by the hardware, so partial tiles need no predicates.  Fused BN statistics read the same
+// staged tile column-wise (conflict-free under the swizzle).
+constexpr int kStgBytes = 4096;   // 32 rows x 128 B
+
+struct OutTile {   // coordinates of a warp's 32-row slab: 2-D map (channel, c1); 4-D (channel, c1, c2, c3)
+  int c1, c2, c3;
+};
+
+template <bool kStats>
+__device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& e, const CUtensorMap* omap,
+                                                  const OutTile& o, uint32_t tmem_acc, int quad,
+                                                  int lane, bool valid, int n_t,
+                                                  uint64_t* tmem_full_bar, uint32_t tph,
+                                                  uint64_t* tmem_empty_bar, uint8_t* stg, int& stg_i,
+                                                  float* stat_acc) {
+#ifdef MCN_ROLE_TIMING
+  const long long rt_w0 = clock64();
+#endif
+  ptx::mbar_wait(tmem_full_bar, tph);
+#ifdef MCN_ROLE_TIMING
+  if (quad == 0 && lane == 0) RT_ADD(3, clock64() - rt_w0);
+#endif
+  ptx::tc_fence_after();
+  const uint32_t swz = static_cast<uint32_t>(lane & 7) << 4;
+  for (int c0 = 0; c0 < e.block_n; c0 += 64) {
+    uint32_t r[64];
+    const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quad * 32) << 16) +
+                           static_cast<uint32_t>(c0);
+    ptx::tmem_ld_32x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+    ptx::tmem_ld_32x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+    ptx::tmem_ld_wait();
+    if (c0 + 64 >= e.block_n) {
+      // last read of this accumulator: hand the TMEM buffer back before the stores drain
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tmem_empty_bar);
+    }
+    const int col0 = n_t * e.block_n + c0;
+    if (col0 >= e.n_total) continue;   // warp-uniform (n_total % 64 == 0: a chunk is whole or absent)
+    uint32_t v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+      v[i] = *reinterpret_cast<uint32_t*>(&h);
+      if (kStats && !valid) v[i] = 0u;   // rows outside the tensor must not reach the sums
+    }
+    uint8_t* buf = stg + stg_i * kStgBytes;
+    // the bulk store that last used this buffer has finished reading it
+    if (lane == 0) {
+      if (e.stg_bufs == 2) ptx::bulk_wait_read<1>();
+      else ptx::bulk_wait_read<0>();
+    }
+    __syncwarp();
+    const uint32_t rowaddr = ptx::smem_u32(buf) + static_cast<uint32_t>(lane) * 128u;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      ptx::st_shared_v4(rowaddr + ((static_cast<uint32_t>(j) << 4) ^ swz), v[4 * j], v[4 * j + 1],
+                        v[4 * j + 2], v[4 * j + 3]);
+    ptx::fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      if (e.out_rank4) {
+        if (e.accumulate) ptx::tma_reduce_add_4d(omap, buf, col0, o.c1, o.c2, o.c3);
+        else ptx::tma_store_4d(omap, buf, col0, o.c1, o.c2, o.c3);
+      } else {
+        if (e.accumulate) ptx::tma_reduce_add_2d(omap, buf, col0, o.c1);
+        else ptx::tma_store_2d(omap, buf, col0, o.c1);
+      }
+      ptx::bulk_commit();
+    }
+    if (kStats) {
+      // lane L sums channels 2L, 2L+1 down the warp's 32 rows; word L of row r sits in 16-byte
+      // chunk (L/4) ^ (r & 7) of the swizzled row: 32 lanes, 32 banks
+      const uint32_t* bw = reinterpret_cast<const uint32_t*>(buf);
+      const int wq = lane >> 2, wr = lane & 3;
+      float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+#pragma unroll
+      for (int rr = 0; rr < 32; ++rr) {
+        const uint32_t w = bw[rr * 32 + (((wq ^ (rr & 7)) << 2) | wr)];
+        const float lo = __uint_as_float(w << 16), hi = __uint_as_float(w & 0xFFFF0000u);
+        s1a += lo;
+        s1b += hi;
+        s2a = fmaf(lo, lo, s2a);
+        s2b = fmaf(hi, hi, s2b);
+      }
+      float2* a1 = reinterpret_cast<float2*>(stat_acc + c0 + 2 * lane);
+      float2* a2 = reinterpret_cast<float2*>(stat_acc + 256 + c0 + 2 * lane);
+      float2 t1 = *a1, t2 = *a2;
+      t1.x += s1a;
+      t1.y += s1b;
+      t2.x += s2a;
+      t2.y += s2b;
+      *a1 = t1;
+      *a2 = t2;
+    }
+    stg_i = (stg_i + 1 == e.stg_bufs) ? 0 : stg_i + 1;
+  }
+}
+
 // ------------------------------------------------------------------ fprop / dgrad kernel
 struct GemmConvArgs {
   CUtensorMap mapA[4];
   CUtensorMap mapB;
+  CUtensorMap mapOut;   // TMA-store epilogue: [M, Cout] bf16, box 64 x 32
   TileGeom g;
   int taps, k_chunks, ksteps_last, block_n, stages, tiles_n, tmem_cols, total_tiles;
   int b_stationary;   // the CTA's whole weight slab (all taps / k-chunks of its n-tile) stays in smem
@@ -373,10 +485,15 @@ struct GemmConvArgs {
 
 // Persistent: one CTA per SM walks tiles (tile = blockIdx.x + i*gridDim.x).  The shared-memory
 // ring and its phases run across tile boundaries, so the producer prefetches the next tile while
-// the MMA warp finishes the current one; the accumulator is double-buffered in TMEM so the
+// the MMA thread finishes the current one; the accumulator is double-buffered in TMEM so the
 // epilogue of tile i overlaps the MMAs of tile i+1.
-template <int kEpiWarps>
-__global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1)
+// The MMA role is ONE thread running a tight loop: descriptors are a constant upper half plus the
+// shifted address, ring indices advance by increment, the four K=16 steps of a stage are unrolled.
+// (Per-role counters showed the old per-iteration elect / descriptor rebuild / modulo chain cost
+// ~160 cycles per tcgen05.mma — five times the 32 cycles an N=64 instruction occupies the pipe.)
+// kTma: TMA-store epilogue (bf16 [M, Cout] output with Cout % 64 == 0) or the direct one.
+template <bool kTma>
+__global__ void __launch_bounds__(192, 1)
 gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
@@ -392,7 +509,8 @@ gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
   const uint32_t stage_bytes = bstat ? kABytes : kABytes + b_bytes;
   const int k_iters = args.taps * args.k_chunks;
   uint8_t* smemBs = smem + static_cast<size_t>(stages) * stage_bytes;
-  uint8_t* tail = smemBs + (bstat ? static_cast<size_t>(k_iters) * b_bytes : 0);
+  uint8_t* stg_all = smemBs + (bstat ? static_cast<size_t>(k_iters) * b_bytes : 0);   // 1024-aligned
+  uint8_t* tail = stg_all + (kTma ? static_cast<size_t>(4 * args.e.stg_bufs) * kStgBytes : 0);
   uint64_t* full = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty = full + stages;
   uint64_t* tmem_full = empty + stages;     // [2]
@@ -405,13 +523,14 @@ gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) ptx::prefetch_tmap(&args.mapA[i]);
     ptx::prefetch_tmap(&args.mapB);
+    if (kTma) ptx::prefetch_tmap(&args.mapOut);
     for (int s = 0; s < stages; ++s) {
       ptx::mbar_init(&full[s], 1);
       ptx::mbar_init(&empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&tmem_full[b], 1);
-      ptx::mbar_init(&tmem_empty[b], (blockDim.x >> 5) - 2);   // one arrival per epilogue warp (4 or 8)
+      ptx::mbar_init(&tmem_empty[b], 4);   // one arrival per epilogue warp
     }
     ptx::mbar_init(bstat_bar, 1);
     ptx::fence_barrier_init();
@@ -442,16 +561,15 @@ gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
                              smemBs + static_cast<size_t>(t * args.k_chunks + kc) * b_bytes, kc * 64,
                              args.tab.brow[t] + n_t * args.block_n);
       }
-      int it = 0;
+      int s = 0;
+      uint32_t ph = 0;
       for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x) {
         const int n_t = tile_id % args.tiles_n;
         const PixelTile tile = decode_tile(args.g, tile_id / args.tiles_n);
         for (int t = 0; t < args.taps; ++t) {
-          for (int kc = 0; kc < args.k_chunks; ++kc, ++it) {
-            const int s = it % stages;
-            const uint32_t ph = static_cast<uint32_t>(it / stages) & 1u;
+          for (int kc = 0; kc < args.k_chunks; ++kc) {
             RT_BEGIN;
-            ptx::mbar_wait(&empty[s], ph ^ 1u);
+            ptx::mbar_wait_quiet(&empty[s], ph ^ 1u);
             RT_END;
             ptx::mbar_expect_tx(&full[s], bstat ? a_tx : a_tx + b_bytes);
             uint8_t* sA = smem + static_cast<size_t>(s) * stage_bytes;
@@ -467,80 +585,91 @@ gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
             if (!bstat)
               ptx::tma_load_2d(&args.mapB, &full[s], sB, kc * 64,
                                args.tab.brow[t] + n_t * args.block_n);
+            if (++s == stages) {
+              s = 0;
+              ph ^= 1u;
+            }
           }
         }
       }
       RT_FLUSH(0);
     }
   } else if (warp == 1) {
-    // ---------------- MMA issuer ----------------
-    RT_DECL;
-    const long long rt_m0 = RT_NOW();
-    (void)rt_m0;
-    const uint32_t idesc = ptx::make_idesc_bf16(128, args.block_n, 0, 0);
-    if (bstat) ptx::mbar_wait(bstat_bar, 0);
-    int it = 0, lt = 0;
-    for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x, ++lt) {
-      const int buf = lt & 1;
-      const uint32_t tph = static_cast<uint32_t>(lt >> 1) & 1u;
-      RT_BEGIN;
-      ptx::mbar_wait(&tmem_empty[buf], tph ^ 1u);   // epilogue has drained this accumulator
-      RT_END2;
-      ptx::tc_fence_after();
-      const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * args.block_n);
-      int kit = 0;
-      for (int t = 0; t < args.taps; ++t) {
-        for (int kc = 0; kc < args.k_chunks; ++kc, ++it, ++kit) {
-          const int s = it % stages;
-          const uint32_t ph = static_cast<uint32_t>(it / stages) & 1u;
+    // ---------------- MMA issuer (one thread) ----------------
+    if (ptx::elect_one()) {
+      RT_DECL;
+      const long long rt_m0 = RT_NOW();
+      (void)rt_m0;
+      const uint32_t idesc = ptx::make_idesc_bf16(128, args.block_n, 0, 0);
+      const uint64_t dhi = ptx::smem_desc_hi(16, 1024);
+      const uint32_t smem_a0 = ptx::smem_u32(smem);
+      const uint32_t smem_b0 = ptx::smem_u32(smemBs);
+      const int kch = args.k_chunks, last_steps = args.ksteps_last;
+      if (bstat) ptx::mbar_wait_quiet(bstat_bar, 0);
+      int s = 0, lt = 0;
+      uint32_t ph = 0;
+      for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x, ++lt) {
+        const int buf = lt & 1;
+        const uint32_t tph = static_cast<uint32_t>(lt >> 1) & 1u;
+        RT_BEGIN;
+        ptx::mbar_wait_quiet(&tmem_empty[buf], tph ^ 1u);   // epilogue has drained this accumulator
+        RT_END2;
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * args.block_n);
+        uint32_t acc = 0u, b_stat_addr = smem_b0;
+        int kc = 0;
+        for (int kit = 0; kit < k_iters; ++kit) {
           RT_BEGIN;
-          ptx::mbar_wait(&full[s], ph);
+          ptx::mbar_wait_quiet(&full[s], ph);
           RT_END;
           ptx::tc_fence_after();
-          if (ptx::elect_one()) {
-            const uint32_t a_addr = ptx::smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
-            const uint32_t b_addr = bstat ? ptx::smem_u32(smemBs) + static_cast<uint32_t>(kit) * b_bytes
-                                          : a_addr + kABytes;
-            const int ksteps = (args.e.debug & 2) ? 0 : ((kc == args.k_chunks - 1) ? args.ksteps_last : 4);
-            for (int k = 0; k < ksteps; ++k) {
-              const uint64_t ad = ptx::make_smem_desc(a_addr + k * 32, 16, 1024);
-              const uint64_t bd = ptx::make_smem_desc(b_addr + k * 32, 16, 1024);
-              ptx::umma_bf16(tmem_d, ad, bd, idesc, (kit | k) != 0 ? 1u : 0u);
-            }
-            ptx::umma_commit(&empty[s]);
-            if (kit == k_iters - 1) ptx::umma_commit(&tmem_full[buf]);
+          const uint32_t a_addr = smem_a0 + static_cast<uint32_t>(s) * stage_bytes;
+          const uint64_t ad = ptx::smem_desc_at(dhi, a_addr);
+          const uint64_t bd = ptx::smem_desc_at(dhi, bstat ? b_stat_addr : a_addr + kABytes);
+          if (kc != kch - 1 || last_steps == 4) {
+            ptx::umma_bf16(tmem_d, ad, bd, idesc, acc);
+            ptx::umma_bf16(tmem_d, ad + 2, bd + 2, idesc, 1u);
+            ptx::umma_bf16(tmem_d, ad + 4, bd + 4, idesc, 1u);
+            ptx::umma_bf16(tmem_d, ad + 6, bd + 6, idesc, 1u);
+          } else {
+            for (int k = 0; k < last_steps; ++k)
+              ptx::umma_bf16(tmem_d, ad + 2 * k, bd + 2 * k, idesc, (k == 0) ? acc : 1u);
           }
-          __syncwarp();
+          acc = 1u;
+          ptx::umma_commit(&empty[s]);
+          b_stat_addr += b_bytes;
+          if (++kc == kch) kc = 0;
+          if (++s == stages) {
+            s = 0;
+            ph ^= 1u;
+          }
         }
+        ptx::umma_commit(&tmem_full[buf]);
       }
-    }
-    if (lane == 0) {
       RT_FLUSH(1);
       RT_FLUSH2(2);
       RT_ADD(7, RT_NOW() - rt_m0);
     }
   } else {
-    // ---------------- epilogue: TMEM -> registers -> global ----------------
+    // ---------------- epilogue ----------------
     const long long rt_e0 = RT_NOW();
     (void)rt_e0;
-    // Each thread owns one output pixel (row) and walks its channels 64 at a time: 64 bf16 = one
-    // full 128-byte line written with four 32-byte stores (fp32 output: eight).
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;
-    // 8 epilogue warps (never together with fused statistics): warps w and w+4 share a quadrant
-    // and take alternate 64-channel chunks
-    const int epi_pairs = ((blockDim.x >> 5) - 2) >> 2;            // 1 or 2
-    const int chunk_first = ((warp - 2) >> 2) * 64, chunk_step = 64 * epi_pairs;
+    const bool stats = args.e.stats != nullptr;
     uint32_t* stat_stage = reinterpret_cast<uint32_t*>(tail + kBarRegionBytes);
-    float* stat_acc_all = reinterpret_cast<float*>(stat_stage + kStatStageWords);
+    // direct epilogue: [staging 18 KB][accumulators]; TMA epilogue: accumulators only
+    float* stat_acc_all = kTma ? reinterpret_cast<float*>(stat_stage)
+                               : reinterpret_cast<float*>(stat_stage + kStatStageWords);
     float* stat_acc = stat_acc_all + quad * kStatAccWarp;
     stat_stage += quad * 32 * kStatRowWords;
-    const bool stats = args.e.stats != nullptr;
     if (stats) {
       for (int i = row; i < kStatAccFloats; i += 128) stat_acc_all[i] = 0.f;
       epi_bar_sync();
     }
     int* stat_flag = reinterpret_cast<int*>(tail + kBarRegionBytes - 16);
+    uint8_t* stg = stg_all + static_cast<size_t>(quad * args.e.stg_bufs) * kStgBytes;
+    int stg_i = 0;
     int lt = 0, cur_nt = -1, pending = 0;
     for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x, ++lt) {
       const int buf = lt & 1;
@@ -553,15 +682,30 @@ gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
         pending = 0;
       }
       ++pending;
-      const PixelTile tile = decode_tile(args.g, tile_id / args.tiles_n);
-      int n, p, q;
-      const bool valid = row_coords(args.g, tile, row, n, p, q);
-      const long long off = valid ? (n * args.out_sn + p * args.out_sh + q * args.out_sw) : 0;
-      epilogue_tile(args.e, tmem_base + static_cast<uint32_t>(buf * args.e.block_n), quad, lane, valid,
-                    off, n_t, &tmem_full[buf], tph, &tmem_empty[buf], stat_stage, stat_acc, chunk_first,
-                    chunk_step);
+      if (kTma) {
+        // the tile is 128 consecutive rows of the [M, Cout] output matrix
+        const long long m0 = static_cast<long long>(tile_id / args.tiles_n) * 128;
+        const bool valid = m0 + row < args.g.m_total;
+        const OutTile o{static_cast<int>(m0) + quad * 32, 0, 0};
+        if (stats)
+          epilogue_tile_tma<true>(args.e, &args.mapOut, o, tmem_base + static_cast<uint32_t>(buf * args.e.block_n),
+                                  quad, lane, valid, n_t, &tmem_full[buf], tph, &tmem_empty[buf], stg, stg_i,
+                                  stat_acc);
+        else
+          epilogue_tile_tma<false>(args.e, &args.mapOut, o, tmem_base + static_cast<uint32_t>(buf * args.e.block_n),
+                                   quad, lane, valid, n_t, &tmem_full[buf], tph, &tmem_empty[buf], stg, stg_i,
+                                   stat_acc);
+      } else {
+        const PixelTile tile = decode_tile(args.g, tile_id / args.tiles_n);
+        int n, p, q;
+        const bool valid = row_coords(args.g, tile, row, n, p, q);
+        const long long off = valid ? (n * args.out_sn + p * args.out_sh + q * args.out_sw) : 0;
+        epilogue_tile(args.e, tmem_base + static_cast<uint32_t>(buf * args.e.block_n), quad, lane, valid,
+                      off, n_t, &tmem_full[buf], tph, &tmem_empty[buf], stat_stage, stat_acc);
+      }
     }
     if (stats && cur_nt >= 0) stats_flush(args.e, stat_acc_all, cur_nt, row, pending, stat_flag);
+    if (kTma && lane == 0) ptx::bulk_wait_all();   // the staged tiles must outlive their stores
     if (row == 0) RT_ADD(4, RT_NOW() - rt_e0);
   }
 
@@ -586,6 +730,7 @@ gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
 struct HaloArgs {
   CUtensorMap mapA;
   CUtensorMap mapB;
+  CUtensorMap mapOut;    // TMA-store epilogue: (C, W, H, N) bf16, box 64 x 8 x 4 x 1
   EpiArgs e;
   int taps, k_chunks, tiles_n, tmem_cols, total_tiles;
   int tiles_w, tiles_h;
@@ -598,6 +743,7 @@ struct HaloArgs {
   short toff[kMaxTaps];  // halo row (pixel) offset of each tap
 };
 
+template <bool kTma>
 __global__ void __launch_bounds__(224, 1)
 halo_conv_kernel(const __grid_constant__ HaloArgs args) {
   extern __shared__ uint8_t smem_raw[];
@@ -609,7 +755,9 @@ halo_conv_kernel(const __grid_constant__ HaloArgs args) {
   const int nb_slots = args.b_stationary ? args.taps * args.k_chunks : args.b_stages;
   uint8_t* smemA = smem;
   uint8_t* smemB = smem + static_cast<size_t>(args.a_stages) * args.halo_stride;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smemB + static_cast<size_t>(nb_slots) * b_bytes);
+  uint8_t* stg_all = smemB + static_cast<size_t>(nb_slots) * b_bytes;   // 1024-aligned
+  uint8_t* tail = stg_all + (kTma ? static_cast<size_t>(4 * args.e.stg_bufs) * kStgBytes : 0);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
   uint64_t* full_a = bars;
   uint64_t* empty_a = full_a + args.a_stages;
   uint64_t* full_b = empty_a + args.a_stages;      // [b_stages] (stationary: [0] only)
@@ -617,11 +765,13 @@ halo_conv_kernel(const __grid_constant__ HaloArgs args) {
   uint64_t* tmem_full = empty_b + args.b_stages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;            // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint32_t* tap_desc = reinterpret_cast<uint32_t*>(tail + 256);   // [taps] descriptor steps (16-byte units)
   const int total_tiles = args.total_tiles;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&args.mapA);
     ptx::prefetch_tmap(&args.mapB);
+    if (kTma) ptx::prefetch_tmap(&args.mapOut);
     for (int s = 0; s < args.a_stages; ++s) {
       ptx::mbar_init(&full_a[s], 1);
       ptx::mbar_init(&empty_a[s], 1);
@@ -637,6 +787,7 @@ halo_conv_kernel(const __grid_constant__ HaloArgs args) {
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
+    for (int t = lane; t < args.taps; t += 32) tap_desc[t] = static_cast<uint32_t>(args.toff[t]) * 8u;
     ptx::tmem_alloc(tmem_slot, static_cast<uint32_t>(args.tmem_cols));
     ptx::tmem_relinquish();
   }
@@ -653,21 +804,24 @@ halo_conv_kernel(const __grid_constant__ HaloArgs args) {
     if (ptx::elect_one()) {
       RT_DECL;
       const uint32_t a_tx = static_cast<uint32_t>(args.hwb * args.hhb) * 128u;
-      int ita = 0;
+      int s = 0;
+      uint32_t ph = 0;
       for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x) {
         const int m = tile_id / args.tiles_n;
         const int n = m / tiles_per_img;
         const int r = m - n * tiles_per_img;
         const int h0 = (r / args.tiles_w) * 16, w0 = (r % args.tiles_w) * 8;
-        for (int kc = 0; kc < args.k_chunks; ++kc, ++ita) {
-          const int s = ita % args.a_stages;
-          const uint32_t ph = static_cast<uint32_t>(ita / args.a_stages) & 1u;
+        for (int kc = 0; kc < args.k_chunks; ++kc) {
           RT_BEGIN;
-          ptx::mbar_wait(&empty_a[s], ph ^ 1u);
+          ptx::mbar_wait_quiet(&empty_a[s], ph ^ 1u);
           RT_END;
           ptx::mbar_expect_tx(&full_a[s], a_tx);
           ptx::tma_load_4d(&args.mapA, &full_a[s], smemA + static_cast<size_t>(s) * args.halo_stride,
                            kc * 64, w0 + args.org_w, h0 + args.org_h, n);
+          if (++s == args.a_stages) {
+            s = 0;
+            ph ^= 1u;
+          }
         }
       }
       RT_FLUSH(0);
@@ -685,75 +839,92 @@ halo_conv_kernel(const __grid_constant__ HaloArgs args) {
                              smemB + static_cast<size_t>(kc * args.taps + t) * b_bytes, kc * 64,
                              args.brow[t] + n_t * args.e.block_n);
       } else {
-        int itb = 0;
+        int s = 0;
+        uint32_t ph = 0;
         for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x) {
           const int n_t = tile_id % args.tiles_n;
           for (int kc = 0; kc < args.k_chunks; ++kc)
-            for (int t = 0; t < args.taps; ++t, ++itb) {
-              const int s = itb % args.b_stages;
-              const uint32_t ph = static_cast<uint32_t>(itb / args.b_stages) & 1u;
-              ptx::mbar_wait(&empty_b[s], ph ^ 1u);
+            for (int t = 0; t < args.taps; ++t) {
+              ptx::mbar_wait_quiet(&empty_b[s], ph ^ 1u);
               ptx::mbar_expect_tx(&full_b[s], b_bytes);
               ptx::tma_load_2d(&args.mapB, &full_b[s], smemB + static_cast<size_t>(s) * b_bytes,
                                kc * 64, args.brow[t] + n_t * args.e.block_n);
+              if (++s == args.b_stages) {
+                s = 0;
+                ph ^= 1u;
+              }
             }
         }
       }
     }
   } else if (warp == 1) {
-    // ---------------- MMA issuer ----------------
-    const uint32_t idesc = ptx::make_idesc_bf16(128, args.e.block_n, 0, 0);
-    const uint32_t sbo = static_cast<uint32_t>(args.hwb) * 128u;
-    int ita = 0, itb = 0, lt = 0;
-    RT_DECL;
-    const long long rt_m0 = RT_NOW();
-    (void)rt_m0;
-    if (args.b_stationary) ptx::mbar_wait(&full_b[0], 0);
-    for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x, ++lt) {
-      const int buf = lt & 1;
-      const uint32_t tph = static_cast<uint32_t>(lt >> 1) & 1u;
-      RT_BEGIN;
-      ptx::mbar_wait(&tmem_empty[buf], tph ^ 1u);
-      RT_END2;
-      ptx::tc_fence_after();
-      const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * args.e.block_n);
-      int kit = 0;
-      for (int kc = 0; kc < args.k_chunks; ++kc, ++ita) {
-        const int sa = ita % args.a_stages;
+    // ---------------- MMA issuer (one thread, see gemm_conv_kernel) ----------------
+    if (ptx::elect_one()) {
+      RT_DECL;
+      const long long rt_m0 = RT_NOW();
+      (void)rt_m0;
+      const uint32_t idesc = ptx::make_idesc_bf16(128, args.e.block_n, 0, 0);
+      const uint64_t dhi_a = ptx::smem_desc_hi(16, static_cast<uint32_t>(args.hwb) * 128u);
+      const uint64_t dhi_b = ptx::smem_desc_hi(16, 1024);
+      const uint32_t smem_a0 = ptx::smem_u32(smemA), smem_b0 = ptx::smem_u32(smemB);
+      const bool bstat = args.b_stationary != 0, use_bo = args.use_base_offset != 0;
+      const int taps = args.taps;
+      int sa = 0, sb = 0, lt = 0;
+      uint32_t pha = 0, phb = 0;
+      if (bstat) ptx::mbar_wait_quiet(&full_b[0], 0);
+      for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x, ++lt) {
+        const int buf = lt & 1;
+        const uint32_t tph = static_cast<uint32_t>(lt >> 1) & 1u;
         RT_BEGIN;
-        ptx::mbar_wait(&full_a[sa], static_cast<uint32_t>(ita / args.a_stages) & 1u);
-        RT_END;
+        ptx::mbar_wait_quiet(&tmem_empty[buf], tph ^ 1u);
+        RT_END2;
         ptx::tc_fence_after();
-        const uint32_t a_base = ptx::smem_u32(smemA + static_cast<size_t>(sa) * args.halo_stride);
-        for (int t = 0; t < args.taps; ++t, ++itb, ++kit) {
-          int sb;
-          if (args.b_stationary) {
-            sb = kc * args.taps + t;
-          } else {
-            sb = itb % args.b_stages;
-            RT_BEGIN;
-            ptx::mbar_wait(&full_b[sb], static_cast<uint32_t>(itb / args.b_stages) & 1u);
-            RT_END;
-            ptx::tc_fence_after();
-          }
-          if (ptx::elect_one()) {
-            const uint32_t a_addr = a_base + static_cast<uint32_t>(args.toff[t]) * 128u;
-            const uint32_t b_addr = ptx::smem_u32(smemB + static_cast<size_t>(sb) * b_bytes);
-            const uint32_t bo = args.use_base_offset ? ((a_addr >> 7) & 7u) : 0u;
-            for (int k = 0; k < ((args.e.debug & 2) ? 0 : 4); ++k) {
-              const uint64_t ad = ptx::make_smem_desc(a_addr + k * 32, 16, sbo, bo);
-              const uint64_t bd = ptx::make_smem_desc(b_addr + k * 32, 16, 1024);
-              ptx::umma_bf16(tmem_d, ad, bd, idesc, (kit | k) != 0 ? 1u : 0u);
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * args.e.block_n);
+        uint32_t acc = 0u, b_stat_addr = smem_b0;
+        for (int kc = 0; kc < args.k_chunks; ++kc) {
+          RT_BEGIN;
+          ptx::mbar_wait_quiet(&full_a[sa], pha);
+          RT_END;
+          ptx::tc_fence_after();
+          const uint32_t a_base = smem_a0 + static_cast<uint32_t>(sa) * static_cast<uint32_t>(args.halo_stride);
+          const uint64_t ad0 = ptx::smem_desc_at(dhi_a, a_base);
+          for (int t = 0; t < taps; ++t) {
+            uint32_t b_addr;
+            if (bstat) {
+              b_addr = b_stat_addr;
+              b_stat_addr += b_bytes;
+            } else {
+              RT_BEGIN;
+              ptx::mbar_wait_quiet(&full_b[sb], phb);
+              RT_END;
+              ptx::tc_fence_after();
+              b_addr = smem_b0 + static_cast<uint32_t>(sb) * b_bytes;
             }
-            if (!args.b_stationary) ptx::umma_commit(&empty_b[sb]);
-            if (t == args.taps - 1) ptx::umma_commit(&empty_a[sa]);
-            if (kc == args.k_chunks - 1 && t == args.taps - 1) ptx::umma_commit(&tmem_full[buf]);
+            const uint32_t step = tap_desc[t];
+            uint64_t ad = ad0 + step;
+            if (use_bo) ad |= static_cast<uint64_t>(((a_base >> 7) + (step >> 3)) & 7u) << 49;
+            const uint64_t bd = ptx::smem_desc_at(dhi_b, b_addr);
+            ptx::umma_bf16(tmem_d, ad, bd, idesc, acc);
+            ptx::umma_bf16(tmem_d, ad + 2, bd + 2, idesc, 1u);
+            ptx::umma_bf16(tmem_d, ad + 4, bd + 4, idesc, 1u);
+            ptx::umma_bf16(tmem_d, ad + 6, bd + 6, idesc, 1u);
+            acc = 1u;
+            if (!bstat) {
+              ptx::umma_commit(&empty_b[sb]);
+              if (++sb == args.b_stages) {
+                sb = 0;
+                phb ^= 1u;
+              }
+            }
           }
-          __syncwarp();
+          ptx::umma_commit(&empty_a[sa]);
+          if (++sa == args.a_stages) {
+            sa = 0;
+            pha ^= 1u;
+          }
         }
+        ptx::umma_commit(&tmem_full[buf]);
       }
-    }
-    if (lane == 0) {
       RT_FLUSH(1);
       RT_FLUSH2(2);
       RT_ADD(7, RT_NOW() - rt_m0);
@@ -764,16 +935,19 @@ halo_conv_kernel(const __grid_constant__ HaloArgs args) {
     (void)rt_e0;
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
-    uint32_t* stat_stage = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + kBarRegionBytes);
-    float* stat_acc_all = reinterpret_cast<float*>(stat_stage + kStatStageWords);
+    const bool stats = args.e.stats != nullptr;
+    uint32_t* stat_stage = reinterpret_cast<uint32_t*>(tail + kBarRegionBytes);
+    float* stat_acc_all = kTma ? reinterpret_cast<float*>(stat_stage)
+                               : reinterpret_cast<float*>(stat_stage + kStatStageWords);
     float* stat_acc = stat_acc_all + quad * kStatAccWarp;
     stat_stage += quad * 32 * kStatRowWords;
-    const bool stats = args.e.stats != nullptr;
     if (stats) {
       for (int i = row; i < kStatAccFloats; i += 128) stat_acc_all[i] = 0.f;
       epi_bar_sync();
     }
-    int* stat_flag = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(bars) + kBarRegionBytes - 16);
+    int* stat_flag = reinterpret_cast<int*>(tail + kBarRegionBytes - 16);
+    uint8_t* stg = stg_all + static_cast<size_t>(quad * args.e.stg_bufs) * kStgBytes;
+    int stg_i = 0;
     int lt = 0, cur_nt = -1, pending = 0;
     for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x, ++lt) {
       const int buf = lt & 1;
@@ -789,14 +963,28 @@ halo_conv_kernel(const __grid_constant__ HaloArgs args) {
       const int m = tile_id / args.tiles_n;
       const int n = m / tiles_per_img;
       const int r = m - n * tiles_per_img;
-      const int p = (r / args.tiles_w) * 16 + (row >> 3);
-      const int q = (r % args.tiles_w) * 8 + (row & 7);
+      const int h0 = (r / args.tiles_w) * 16, w0 = (r % args.tiles_w) * 8;
+      const int p = h0 + (row >> 3);
+      const int q = w0 + (row & 7);
       const bool valid = p < args.Ho && q < args.Wo;
-      const long long off = valid ? (n * args.out_sn + p * args.out_sh + q * args.out_sw) : 0;
-      epilogue_tile(args.e, tmem_base + static_cast<uint32_t>(buf * args.e.block_n), quad, lane, valid,
-                    off, n_t, &tmem_full[buf], tph, &tmem_empty[buf], stat_stage, stat_acc);
+      if (kTma) {
+        const OutTile o{w0, h0 + quad * 4, n};   // this warp's 4 output rows x 8 columns
+        if (stats)
+          epilogue_tile_tma<true>(args.e, &args.mapOut, o, tmem_base + static_cast<uint32_t>(buf * args.e.block_n),
+                                  quad, lane, valid, n_t, &tmem_full[buf], tph, &tmem_empty[buf], stg, stg_i,
+                                  stat_acc);
+        else
+          epilogue_tile_tma<false>(args.e, &args.mapOut, o, tmem_base + static_cast<uint32_t>(buf * args.e.block_n),
+                                   quad, lane, valid, n_t, &tmem_full[buf], tph, &tmem_empty[buf], stg, stg_i,
+                                   stat_acc);
+      } else {
+        const long long off = valid ? (n * args.out_sn + p * args.out_sh + q * args.out_sw) : 0;
+        epilogue_tile(args.e, tmem_base + static_cast<uint32_t>(buf * args.e.block_n), quad, lane, valid,
+                      off, n_t, &tmem_full[buf], tph, &tmem_empty[buf], stat_stage, stat_acc);
+      }
     }
     if (stats && cur_nt >= 0) stats_flush(args.e, stat_acc_all, cur_nt, row, pending, stat_flag);
+    if (kTma && lane == 0) ptx::bulk_wait_all();
     if (row == 0) RT_ADD(4, RT_NOW() - rt_e0);
   }
 
@@ -1750,7 +1938,9 @@ int plan_splits(long long n, int want, SplitPlan* sp, long long* query, const ch
   return MCN_OK;
 }
 
-int launch_gemm_conv(GemmConvArgs& a, int tiles_m, cudaStream_t st) {
+// dense_out: the output is a plain [m_total, n_total] matrix whose row order is the tile order (1x1
+// convolutions and the im2col feed) — the precondition of the TMA-store epilogue.
+int launch_gemm_conv(GemmConvArgs& a, int tiles_m, bool dense_out, cudaStream_t st) {
   a.e.block_n = a.block_n;
   a.total_tiles = tiles_m * a.tiles_n;
   {
@@ -1769,6 +1959,19 @@ int launch_gemm_conv(GemmConvArgs& a, int tiles_m, cudaStream_t st) {
 #else
   a.e.debug = 0;
 #endif
+  static int tma_enabled = -1;
+  if (tma_enabled < 0) {
+    const char* e = getenv("MCN_TMA_STORE");      // MCN_TMA_STORE=0: direct epilogue everywhere (A/B)
+    tma_enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  const bool tma = tma_enabled && dense_out && !a.e.out_f32 && a.e.bias == nullptr &&
+                   a.e.n_total % 64 == 0 && reinterpret_cast<uintptr_t>(a.e.out) % 16 == 0 &&
+                   a.g.m_total < (1LL << 31);
+  a.e.out_rank4 = 0;
+  if (tma) {
+    const int rc = encode_matrix(&a.mapOut, a.e.out, a.g.m_total, a.e.n_total, 32);
+    if (rc) return rc;
+  }
   const int grid_n = std::min(a.total_tiles, num_sms());
   // weight-stationary when the CTA's weight slab is small and it sees one n-tile only
   static int ws_enabled = -1;
@@ -1780,41 +1983,38 @@ int launch_gemm_conv(GemmConvArgs& a, int tiles_m, cudaStream_t st) {
   a.b_stationary = (ws_enabled && b_slab <= 128 * 1024 && grid_n % a.tiles_n == 0 &&
                     (a.total_tiles >= 2 * grid_n || ws_enabled == 2)) ? 1 : 0;
   const uint32_t stage_bytes = a.b_stationary ? kABytes : kABytes + a.block_n * 128;
-  // one persistent CTA per SM: the whole shared memory is the TMA ring
-  const size_t fixed = kBarRegionBytes + (a.e.stats ? kEpiStageBytes + kStatAccBytes : 0) + 1024 +
-                       (a.b_stationary ? b_slab : 0);
-  const size_t ring_budget = std::min<size_t>(200 * 1024, static_cast<size_t>(smem_optin_limit()) - fixed);
-  int stages = std::min(8, static_cast<int>(ring_budget / stage_bytes));
-  stages = std::max(2, stages);
+  // one persistent CTA per SM: the whole shared memory is the TMA ring, minus the epilogue's share
+  auto fixed_for = [&](int bufs) {
+    const size_t epi = tma ? static_cast<size_t>(4 * bufs) * kStgBytes + (a.e.stats ? kStatAccBytes : 0)
+                           : (a.e.stats ? kEpiStageBytes + kStatAccBytes : 0);
+    return kBarRegionBytes + epi + 1024 + (a.b_stationary ? b_slab : 0);
+  };
+  auto stages_for = [&](int bufs) {
+    const size_t ring = std::min<size_t>(200 * 1024, static_cast<size_t>(smem_optin_limit()) - fixed_for(bufs));
+    return std::max(2, std::min(8, static_cast<int>(ring / stage_bytes)));
+  };
+  // two staging tiles per warp unless the second one costs a ring stage the kernel is short of
+  a.e.stg_bufs = (tma && stages_for(2) < stages_for(1) && stages_for(2) < 4) ? 1 : 2;
+  const int stages = stages_for(a.e.stg_bufs);
   a.stages = stages;
   a.tmem_cols = 2 * tmem_cols_for(a.block_n);   // double-buffered accumulator
-  size_t smem = static_cast<size_t>(stages) * stage_bytes + (a.b_stationary ? b_slab : 0) +
-                kBarRegionBytes + (a.e.stats ? kEpiStageBytes + kStatAccBytes : 0) + 1024;
+  const size_t smem = static_cast<size_t>(stages) * stage_bytes + fixed_for(a.e.stg_bufs);
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(gemm_conv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(gemm_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              smem_optin_limit()) != cudaSuccess ||
-        cudaFuncSetAttribute(gemm_conv_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(gemm_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              smem_optin_limit()) != cudaSuccess) {
       set_error("cudaFuncSetAttribute(gemm_conv_kernel) failed");
       return MCN_ECUDA;
     }
     configured = true;
   }
-  // MCN_EPI_WARPS=8 (experimental, default 4): two epilogue warps per TMEM quadrant for tiles of at
-  // least two 64-channel chunks — the store-heavy 1x1 convolutions are bound by the epilogue warps'
-  // instruction issue (profiles/r01_epilogue_knockout.txt).  Not combined with fused statistics.
-  static int epi_warps = 0;
-  if (!epi_warps) {
-    const char* e = getenv("MCN_EPI_WARPS");
-    epi_warps = (e && atoi(e) == 8) ? 8 : 4;
-  }
-  const int threads = (epi_warps == 8 && a.e.stats == nullptr && a.block_n >= 128) ? 320 : 192;
   dim3 grid(static_cast<unsigned>(grid_n));
-  if (threads == 320)
-    gemm_conv_kernel<8><<<grid, 320, smem, st>>>(a);
+  if (tma)
+    gemm_conv_kernel<true><<<grid, 192, smem, st>>>(a);
   else
-    gemm_conv_kernel<4><<<grid, 192, smem, st>>>(a);
+    gemm_conv_kernel<false><<<grid, 192, smem, st>>>(a);
   return after_launch("gemm_conv_kernel");
 }
 
@@ -1875,7 +2075,21 @@ int launch_halo(const void* in, int C_in, int W_in, int H_in, int N, const void*
   const long long b_all = (long long)a.taps * a.k_chunks * b_bytes;
   a.b_stationary = (a.tiles_n == 1 && b_all <= 100 * 1024) ? 1 : 0;
   a.a_stages = 3;
-  const long long budget = (stats ? 192 : 200) * 1024 - (long long)a.a_stages * a.halo_stride;
+  static int tma_enabled = -1;
+  if (tma_enabled < 0) {
+    const char* e = getenv("MCN_TMA_STORE");
+    tma_enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  const bool tma = tma_enabled && !out_f32 && bias == nullptr && n_total % 64 == 0 &&
+                   reinterpret_cast<uintptr_t>(out) % 16 == 0;
+  a.e.out_rank4 = 1;
+  a.e.stg_bufs = 2;
+  if (tma && (rc = encode_nhwc(&a.mapOut, out, n_total, Wo, Ho, N, 8, 4, 1))) return rc;
+  const size_t epi_bytes = tma ? static_cast<size_t>(4 * a.e.stg_bufs) * kStgBytes + (stats ? kStatAccBytes : 0)
+                               : (stats ? kEpiStageBytes + kStatAccBytes : 0);
+  const long long budget = static_cast<long long>(smem_optin_limit()) - 1024 - kBarRegionBytes -
+                           static_cast<long long>(epi_bytes) - (long long)a.a_stages * a.halo_stride;
+  if (a.b_stationary && b_all > budget) a.b_stationary = 0;   // resident weights do not fit: stream them
   if (a.b_stationary) {
     a.b_stages = 1;
   } else {
@@ -1899,10 +2113,16 @@ int launch_halo(const void* in, int C_in, int W_in, int H_in, int N, const void*
   a.total_tiles = a.tiles_w * a.tiles_h * N * a.tiles_n;
   const int nb_slots = a.b_stationary ? a.taps * a.k_chunks : a.b_stages;
   size_t smem = (size_t)a.a_stages * a.halo_stride + (size_t)nb_slots * b_bytes + kBarRegionBytes +
-                (a.e.stats ? kEpiStageBytes + kStatAccBytes : 0) + 1024;
+                epi_bytes + 1024;
+  if (smem > static_cast<size_t>(smem_optin_limit())) {
+    set_error("halo_conv_kernel: %zu bytes of shared memory needed", smem);
+    return MCN_EINVAL;
+  }
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(halo_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(halo_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             smem_optin_limit()) != cudaSuccess ||
+        cudaFuncSetAttribute(halo_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              smem_optin_limit()) != cudaSuccess) {
       set_error("cudaFuncSetAttribute(halo_conv_kernel) failed");
       return MCN_ECUDA;
@@ -1911,7 +2131,10 @@ int launch_halo(const void* in, int C_in, int W_in, int H_in, int N, const void*
   }
   if ((rc = attach_xs(&a.e, a.total_tiles / a.tiles_n, a.tiles_n))) return rc;
   dim3 grid((unsigned)std::min(a.total_tiles, num_sms()));
-  halo_conv_kernel<<<grid, 224, smem, st>>>(a);
+  if (tma)
+    halo_conv_kernel<true><<<grid, 224, smem, st>>>(a);
+  else
+    halo_conv_kernel<false><<<grid, 224, smem, st>>>(a);
   return after_launch("halo_conv_kernel");
 }
 
@@ -2029,7 +2252,7 @@ static int fprop_tc_impl(const mcn_conv_desc* d, const void* x, const void* w_oh
         a.tab.dw[t] = (short)(s * d->dw);
       }
     }
-  return launch_gemm_conv(a, tiles_m_of(a.g), static_cast<cudaStream_t>(stream));
+  return launch_gemm_conv(a, tiles_m_of(a.g), pointwise || a.g.a_mode == 1, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int mcn_conv2d_fprop_tc(const mcn_conv_desc* d, const void* x, const void* w_ohwi,
@@ -2145,7 +2368,7 @@ static int dgrad_phase(const mcn_conv_desc* d, const void* dy, const void* w_hwi
       a.tab.dw[t] = (short)(e_w[t] - min_ew);
     }
   }
-  return launch_gemm_conv(a, tiles_m_of(a.g), st);
+  return launch_gemm_conv(a, tiles_m_of(a.g), pointwise || (a.g.a_mode == 1 && unit), st);
 }
 
 extern "C" int mcn_conv2d_dgrad_tc(const mcn_conv_desc* d, const void* dy, const void* w_hwio,

@@ -63,6 +63,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Same, for the single-thread issue loops (no printf: keeps their register count and code small).
+__device__ __forceinline__ void mbar_wait_quiet(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -93,6 +101,53 @@ __device__ __forceinline__ void tma_load_im2col_4d(const CUtensorMap* m, uint64_
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n),
       "h"(off_w), "h"(off_h)
       : "memory");
+}
+
+// TMA stores (shared -> global, bulk async group of the issuing thread).  The tile in shared memory
+// uses the tensor map's swizzle; rows / columns outside the tensor are clipped by the hardware.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1,
+                                             int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+          reinterpret_cast<uint64_t>(m)),
+      "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// global[tile] += shared[tile], element-wise in the tensor map's data type (bf16 here), performed
+// by the memory system: no read-modify-write through registers.
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* src, int c0,
+                                                  int c1) {
+  asm volatile(
+      "cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+          reinterpret_cast<uint64_t>(m)),
+      "r"(smem_u32(src)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* m, const void* src, int c0,
+                                                  int c1, int c2, int c3) {
+  asm volatile(
+      "cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], "
+      "[%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+      "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// at most N of this thread's bulk groups still READING their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+// all of this thread's bulk groups complete (writes performed)
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
 }
 
 // ---------------------------------------------------------------- tcgen05
@@ -181,6 +236,15 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= static_cast<uint64_t>(1) << 46;  // descriptor version (sm_100)
   d |= static_cast<uint64_t>(2) << 61;  // SWIZZLE_128B
   return d;
+}
+// Upper (address-independent) part of a descriptor: desc(addr) = hi | ((addr & 0x3FFFF) >> 4); an
+// address step of 16*n bytes is "+ n" on the descriptor (the 14-bit field cannot overflow inside
+// the 227 KB of shared memory a kernel can own).
+__device__ __forceinline__ uint64_t smem_desc_hi(uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return make_smem_desc(0, lbo_bytes, sbo_bytes);
+}
+__device__ __forceinline__ uint64_t smem_desc_at(uint64_t hi, uint32_t saddr) {
+  return hi | static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
 }
 // Instruction descriptor for kind::f16 with bf16 A/B and fp32 D.
 __host__ __device__ inline uint32_t make_idesc_bf16(int m, int n, int a_mn_major, int b_mn_major) {
