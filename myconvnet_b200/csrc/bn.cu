@@ -39,6 +39,15 @@ inline int bn_bwd_unroll() {
   }
   return v;
 }
+// the same for the variants without a y stream (two read streams): default 4, MCN_BN_NOY_UNROLL=2|4
+inline int bn_noy_unroll() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MCN_BN_NOY_UNROLL");
+    v = (e && e[0] == '2') ? 2 : 4;
+  }
+  return v;
+}
 inline bool bn_float_atomics() {
   static int v = -1;
   if (v < 0) {
@@ -161,6 +170,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 bn_stats_kernel(const T* __restrict__ x, long long rows, int C, int slab_v, int rowlanes,
                 double* __restrict__ sums, XsScratch xsc) {
+  MCN_PDL_PROLOGUE();
   constexpr int V = Vec16<T>::N;
   extern __shared__ float sh[];
   const int sv = threadIdx.x % slab_v, rl = threadIdx.x / slab_v;
@@ -211,6 +221,7 @@ bn_stats_kernel(const T* __restrict__ x, long long rows, int C, int slab_v, int 
 template <typename T>
 __global__ void bn_stats_scalar_kernel(const T* __restrict__ x, long long rows, int C,
                                        double* __restrict__ sums, XsScratch xsc) {
+  MCN_PDL_PROLOGUE();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) {
     long long r0 = rows * blockIdx.y / gridDim.y, r1 = rows * (blockIdx.y + 1) / gridDim.y;
@@ -232,6 +243,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
                                    float momentum, float* __restrict__ mean,
                                    float* __restrict__ invstd, float* __restrict__ moving_mean,
                                    float* __restrict__ moving_var) {
+  MCN_PDL_PROLOGUE();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double m = sums[c] / count;
@@ -254,6 +266,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
 __global__ void bn_frozen_stats_kernel(const float* __restrict__ moving_mean,
                                        const float* __restrict__ moving_var, int C, float eps,
                                        float* __restrict__ mean, float* __restrict__ invstd) {
+  MCN_PDL_PROLOGUE();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   mean[c] = moving_mean[c];
@@ -329,6 +342,7 @@ bn_apply_kernel(const T* __restrict__ x, long long nvec, int cv, const float* __
                 const float* __restrict__ gamma, const float* __restrict__ beta,
                 const T* __restrict__ residual, int act, float alpha, T* __restrict__ y,
                 BnSumsArgs fs) {
+  MCN_PDL_PROLOGUE();
   constexpr int V = Vec16<T>::N;
   const int c0 = (threadIdx.x % cv) * V;
   float sc[V], sf[V];
@@ -374,6 +388,7 @@ bn_apply_runs_kernel(const T* __restrict__ x, long long nvec, int cv, const floa
                      const float* __restrict__ gamma, const float* __restrict__ beta,
                      const T* __restrict__ residual, int act, float alpha, T* __restrict__ y,
                      BnSumsArgs fs, int runs_per_block) {
+  MCN_PDL_PROLOGUE();
   constexpr int V = Vec16<T>::N;
   const int c0 = (threadIdx.x % cv) * V;
   long long v = (long long)blockIdx.x * runs_per_block * (256 * U) + threadIdx.x;
@@ -418,6 +433,7 @@ __global__ void bn_apply_scalar_kernel(const T* __restrict__ x, long long n, int
                                        const float* __restrict__ beta,
                                        const T* __restrict__ residual, int act, float alpha,
                                        T* __restrict__ y) {
+  MCN_PDL_PROLOGUE();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     int c = (int)(i % C);
@@ -451,6 +467,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T*
                      const float* __restrict__ gamma, const float* __restrict__ beta, int act,
                      float alpha, float* __restrict__ sum_dz, float* __restrict__ sum_dz_xhat,
                      XsScratch xsc) {
+  MCN_PDL_PROLOGUE();
   constexpr int V = Vec16<T>::N;
   extern __shared__ float sh[];
   const int sv = threadIdx.x % slab_v, rl = threadIdx.x / slab_v;
@@ -511,14 +528,15 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T*
   slab_finish<V, float>(sh, slab_v, rowlanes, blockIdx.x, C, sum_dz, sum_dz_xhat, xsc);
 }
 
-template <typename T, int U>
-__global__ void __launch_bounds__(512)
+template <typename T, int U, bool kHaveY>
+__global__ void __launch_bounds__(sizeof(T) == 2 ? 256 : 512, sizeof(T) == 2 ? 3 : 1)   // fp32: cv up to 512
 bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
                     long long nvec, int cv, const float* __restrict__ mean,
                     const float* __restrict__ invstd, const float* __restrict__ gamma,
                     const float* __restrict__ beta, int act, float alpha,
                     const float* __restrict__ sum_dz, const float* __restrict__ sum_dz_xhat,
                     float inv_count, T* __restrict__ dx, T* __restrict__ d_residual) {
+  MCN_PDL_PROLOGUE();
   constexpr int V = Vec16<T>::N;
   const int c0 = (threadIdx.x % cv) * V;
   // dx = sc*(dz - k1 - xhat*k2) with xhat = (x-mu)*is  ==  A*dz + B*x + Cc
@@ -532,11 +550,11 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
     B[i] = -A[i] * k2 * is;
     Cc[i] = A[i] * (k2 * mu * is - k1);
   }
-  const bool have_y = (y != nullptr);
+  constexpr bool have_y = kHaveY;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec;
        v += U * stride) {
-    Vec16<T> g[U], a[U], o[U];
+    Vec16<T> g[U], a[U], o[kHaveY ? U : 1];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       long long vv = v + u * stride;
@@ -554,7 +572,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
 #pragma unroll
         for (int i = 0; i < V; ++i) {
           float xv = a[u].get(i);
-          float dz = dz_of<T>(g[u].get(i), xv, have_y ? o[u].get(i) : 0.f, have_y, A[i], sf[i],
+          float dz = dz_of<T>(g[u].get(i), xv, have_y ? o[kHaveY ? u : 0].get(i) : 0.f, have_y, A[i], sf[i],
                               act, alpha);
           ox.set(i, fmaf(A[i], dz, fmaf(B[i], xv, Cc[i])));
           orr.set(i, dz);
@@ -577,6 +595,7 @@ bn_bwd_apply_runs_kernel(const T* __restrict__ dy, const T* __restrict__ x, cons
                          const float* __restrict__ sum_dz, const float* __restrict__ sum_dz_xhat,
                          float inv_count, T* __restrict__ dx, T* __restrict__ d_residual,
                          int runs_per_block) {
+  MCN_PDL_PROLOGUE();
   constexpr int V = Vec16<T>::N;
   const int c0 = (threadIdx.x % cv) * V;
   long long v = (long long)blockIdx.x * runs_per_block * (256 * U) + threadIdx.x;
@@ -632,6 +651,7 @@ __global__ void bn_bwd_reduce_scalar_kernel(const T* dy, const T* x, const T* y,
                                             const float* gamma, const float* beta, int act,
                                             float alpha, float* sum_dz, float* sum_dz_xhat,
                                             XsScratch xsc) {
+  MCN_PDL_PROLOGUE();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) {
     long long r0 = rows * blockIdx.y / gridDim.y, r1 = rows * (blockIdx.y + 1) / gridDim.y;
@@ -659,6 +679,7 @@ __global__ void bn_bwd_apply_scalar_kernel(const T* dy, const T* x, const T* y, 
                                            float alpha, const float* sum_dz,
                                            const float* sum_dz_xhat, float inv_count, T* dx,
                                            T* d_residual) {
+  MCN_PDL_PROLOGUE();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     int c = (int)(i % C);
@@ -688,12 +709,12 @@ extern "C" int mcn_bn_stats(int dtype, const void* x, long long rows, int C, dou
     SlabLaunch L;
     if (plan_slab<T>(rows, C, &L, 3 * num_sms())) {
       size_t smem = 2 * (size_t)L.rowlanes * L.slab_v * Vec16<T>::N * sizeof(float);
-      bn_stats_kernel<T><<<L.grid, 256, smem, st>>>(static_cast<const T*>(x), rows, C, L.slab_v,
+      ::mcn::launch(bn_stats_kernel<T>, L.grid, 256, smem, st, static_cast<const T*>(x), rows, C, L.slab_v,
                                                     L.rowlanes, sums, xsc);
     } else {
       MCN_REQUIRE((C + 127) / 128 <= kWsCounters, "bn_stats: too many channels (%d)", C);
       dim3 grid((C + 127) / 128, (unsigned)std::min<long long>(rows, 4LL * num_sms()));
-      bn_stats_scalar_kernel<T><<<grid, 128, 0, st>>>(static_cast<const T*>(x), rows, C, sums, xsc);
+      ::mcn::launch(bn_stats_scalar_kernel<T>, grid, 128, 0, st, static_cast<const T*>(x), rows, C, sums, xsc);
     }
   });
   return after_launch("bn_stats");
@@ -702,7 +723,7 @@ extern "C" int mcn_bn_stats(int dtype, const void* x, long long rows, int C, dou
 extern "C" int mcn_bn_frozen_stats(const float* moving_mean, const float* moving_var, int C, float eps,
                                    float* mean, float* invstd, void* stream) {
   MCN_REQUIRE(moving_mean && moving_var && mean && invstd && C > 0, "bn_frozen_stats: bad argument");
-  bn_frozen_stats_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  ::mcn::launch(bn_frozen_stats_kernel, (C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream), 
       moving_mean, moving_var, C, eps, mean, invstd);
   return after_launch("bn_frozen_stats");
 }
@@ -711,7 +732,7 @@ extern "C" int mcn_bn_finalize(const double* sums, double count, int C, float ep
                                float* mean, float* invstd, float* moving_mean, float* moving_var,
                                void* stream) {
   MCN_REQUIRE(sums && mean && invstd && count > 0, "bn_finalize: bad argument");
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  ::mcn::launch(bn_finalize_kernel, (C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream), 
       sums, count, C, eps, momentum, mean, invstd, moving_mean, moving_var);
   return after_launch("bn_finalize");
 }
@@ -739,21 +760,21 @@ static int bn_apply_impl(int dtype, const void* x, long long rows, int C, const 
       int rpb = (int)std::max<long long>(1, std::min<long long>(8, runs / (4LL * 3 * num_sms())));
       const unsigned grid = (unsigned)((runs + rpb - 1) / rpb);
       if (res)
-        bn_apply_runs_kernel<T, kMode, 4, true><<<grid, 256, 0, st>>>(
+        ::mcn::launch(bn_apply_runs_kernel<T, kMode, 4, true>, grid, 256, 0, st, 
             static_cast<const T*>(x), nvec, cvr, mean, is_or_var, eps, gamma, beta,
             static_cast<const T*>(residual), act, alpha, static_cast<T*>(y), fs, rpb);
       else
-        bn_apply_runs_kernel<T, kMode, 8, false><<<grid, 256, 0, st>>>(
+        ::mcn::launch(bn_apply_runs_kernel<T, kMode, 8, false>, grid, 256, 0, st, 
             static_cast<const T*>(x), nvec, cvr, mean, is_or_var, eps, gamma, beta, nullptr, act, alpha,
             static_cast<T*>(y), fs, rpb);
     } else if (plan<T>(rows, C, &L, 2)) {
-      bn_apply_kernel<T, kMode><<<L.grid, L.block, 0, st>>>(
+      ::mcn::launch(bn_apply_kernel<T, kMode>, L.grid, L.block, 0, st, 
           static_cast<const T*>(x), rows * L.cv, L.cv, mean, is_or_var, eps, gamma, beta,
           static_cast<const T*>(residual), act, alpha, static_cast<T*>(y), fs);
     } else {
       // odd channel counts: finalize as its own launch, then the scalar kernel
       if (kMode == 2) {
-        bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(fs.sums, 1.0 / fs.inv_count, C, fs.eps,
+        ::mcn::launch(bn_finalize_kernel, (C + 127) / 128, 128, 0, st, fs.sums, 1.0 / fs.inv_count, C, fs.eps,
                                                             fs.momentum, fs.save_mean, fs.save_invstd,
                                                             fs.moving_mean, fs.moving_var);
         mean = fs.save_mean;
@@ -761,7 +782,7 @@ static int bn_apply_impl(int dtype, const void* x, long long rows, int C, const 
       }
       long long n = rows * C;
       int grid = (int)std::min<long long>((n + 255) / 256, 8LL * num_sms());
-      bn_apply_scalar_kernel<T, kMode == 1><<<grid, 256, 0, st>>>(
+      ::mcn::launch(bn_apply_scalar_kernel<T, kMode == 1>, grid, 256, 0, st, 
           static_cast<const T*>(x), n, C, mean, is_or_var, eps, gamma, beta,
           static_cast<const T*>(residual), act, alpha, static_cast<T*>(y));
     }
@@ -812,18 +833,18 @@ static void launch_bn_bwd_reduce(const SlabLaunch& L, size_t smem, cudaStream_t 
   const T* pdy = static_cast<const T*>(dy);
   const T* px = static_cast<const T*>(x);
   const T* py = static_cast<const T*>(y);
-  const bool four = bn_bwd_unroll() == 4;
+  const bool four = (y != nullptr) ? bn_bwd_unroll() == 4 : bn_noy_unroll() == 4;
   if (four && y != nullptr)
-    bn_bwd_reduce_kernel<T, 4, true><<<L.grid, 256, smem, st>>>(pdy, px, py, rows, C, L.slab_v, L.rowlanes, mean, invstd,
+    ::mcn::launch(bn_bwd_reduce_kernel<T, 4, true>, L.grid, 256, smem, st, pdy, px, py, rows, C, L.slab_v, L.rowlanes, mean, invstd,
                                                                gamma, beta, act, alpha, sum_dz, sum_dz_xhat, xsc);
   else if (four)
-    bn_bwd_reduce_kernel<T, 4, false><<<L.grid, 256, smem, st>>>(pdy, px, py, rows, C, L.slab_v, L.rowlanes, mean, invstd,
+    ::mcn::launch(bn_bwd_reduce_kernel<T, 4, false>, L.grid, 256, smem, st, pdy, px, py, rows, C, L.slab_v, L.rowlanes, mean, invstd,
                                                                 gamma, beta, act, alpha, sum_dz, sum_dz_xhat, xsc);
   else if (y != nullptr)
-    bn_bwd_reduce_kernel<T, 2, true><<<L.grid, 256, smem, st>>>(pdy, px, py, rows, C, L.slab_v, L.rowlanes, mean, invstd,
+    ::mcn::launch(bn_bwd_reduce_kernel<T, 2, true>, L.grid, 256, smem, st, pdy, px, py, rows, C, L.slab_v, L.rowlanes, mean, invstd,
                                                                gamma, beta, act, alpha, sum_dz, sum_dz_xhat, xsc);
   else
-    bn_bwd_reduce_kernel<T, 2, false><<<L.grid, 256, smem, st>>>(pdy, px, py, rows, C, L.slab_v, L.rowlanes, mean, invstd,
+    ::mcn::launch(bn_bwd_reduce_kernel<T, 2, false>, L.grid, 256, smem, st, pdy, px, py, rows, C, L.slab_v, L.rowlanes, mean, invstd,
                                                                 gamma, beta, act, alpha, sum_dz, sum_dz_xhat, xsc);
 }
 
@@ -845,7 +866,7 @@ extern "C" int mcn_bn_bwd_reduce(int dtype, const void* dy, const void* x, const
     } else {
       MCN_REQUIRE((C + 127) / 128 <= kWsCounters, "bn_bwd_reduce: too many channels (%d)", C);
       dim3 grid((C + 127) / 128, (unsigned)std::min<long long>(rows, 4LL * num_sms()));
-      bn_bwd_reduce_scalar_kernel<T><<<grid, 128, 0, st>>>(
+      ::mcn::launch(bn_bwd_reduce_scalar_kernel<T>, grid, 128, 0, st, 
           static_cast<const T*>(dy), static_cast<const T*>(x), static_cast<const T*>(y), rows, C,
           mean, invstd, gamma, beta, act, act_alpha, sum_dz, sum_dz_xhat, xsc);
     }
@@ -865,18 +886,24 @@ static void launch_bwd_apply_runs(unsigned grid, cudaStream_t st, const void* dy
   T* pdx = static_cast<T*>(dx);
   T* pdr = static_cast<T*>(d_residual);
   if (y != nullptr && d_residual != nullptr)
-    bn_bwd_apply_runs_kernel<T, 4, true, true><<<grid, 256, 0, st>>>(
+    ::mcn::launch(bn_bwd_apply_runs_kernel<T, 4, true, true>, grid, 256, 0, st, 
         pdy, px, py, nvec, cv, mean, invstd, gamma, beta, act, alpha, sum_dz, sum_dz_xhat, inv_count, pdx, pdr, rpb);
   else if (y != nullptr)
-    bn_bwd_apply_runs_kernel<T, 4, true, false><<<grid, 256, 0, st>>>(
+    ::mcn::launch(bn_bwd_apply_runs_kernel<T, 4, true, false>, grid, 256, 0, st, 
         pdy, px, py, nvec, cv, mean, invstd, gamma, beta, act, alpha, sum_dz, sum_dz_xhat, inv_count, pdx, pdr, rpb);
   else if (d_residual != nullptr)
-    bn_bwd_apply_runs_kernel<T, 4, false, true><<<grid, 256, 0, st>>>(
+    ::mcn::launch(bn_bwd_apply_runs_kernel<T, 4, false, true>, grid, 256, 0, st, 
         pdy, px, py, nvec, cv, mean, invstd, gamma, beta, act, alpha, sum_dz, sum_dz_xhat, inv_count, pdx, pdr, rpb);
   else
-    bn_bwd_apply_runs_kernel<T, 4, false, false><<<grid, 256, 0, st>>>(
+    ::mcn::launch(bn_bwd_apply_runs_kernel<T, 4, false, false>, grid, 256, 0, st, 
         pdy, px, py, nvec, cv, mean, invstd, gamma, beta, act, alpha, sum_dz, sum_dz_xhat, inv_count, pdx, pdr, rpb);
 }
+
+#define MCN_BWD_APPLY(U_, Y_)                                                                      \
+  ::mcn::launch(bn_bwd_apply_kernel<T, U_, Y_>, L.grid, L.block, 0, st,                                        \
+      static_cast<const T*>(dy), static_cast<const T*>(x), static_cast<const T*>(y), rows * L.cv,  \
+      L.cv, mean, invstd, gamma, beta, act, act_alpha, sum_dz, sum_dz_xhat, inv_count,             \
+      static_cast<T*>(dx), static_cast<T*>(d_residual))
 
 extern "C" int mcn_bn_bwd_apply(int dtype, const void* dy, const void* x, const void* y,
                                 long long rows, int C, const float* mean, const float* invstd,
@@ -899,21 +926,21 @@ extern "C" int mcn_bn_bwd_apply(int dtype, const void* dy, const void* x, const 
       const unsigned grid = (unsigned)((runs + rpb - 1) / rpb);
       launch_bwd_apply_runs<T>(grid, st, dy, x, y, nvec, cvr, mean, invstd, gamma, beta, act, act_alpha,
                                sum_dz, sum_dz_xhat, inv_count, dx, d_residual, rpb);
-    } else if (plan<T>(rows, C, &L, 3, 256)) {
-      if (bn_bwd_unroll() == 4)
-        bn_bwd_apply_kernel<T, 4><<<L.grid, L.block, 0, st>>>(
-            static_cast<const T*>(dy), static_cast<const T*>(x), static_cast<const T*>(y),
-            rows * L.cv, L.cv, mean, invstd, gamma, beta, act, act_alpha, sum_dz, sum_dz_xhat,
-            inv_count, static_cast<T*>(dx), static_cast<T*>(d_residual));
-      else
-        bn_bwd_apply_kernel<T, 2><<<L.grid, L.block, 0, st>>>(
-            static_cast<const T*>(dy), static_cast<const T*>(x), static_cast<const T*>(y),
-            rows * L.cv, L.cv, mean, invstd, gamma, beta, act, act_alpha, sum_dz, sum_dz_xhat,
-            inv_count, static_cast<T*>(dx), static_cast<T*>(d_residual));
+    } else if (plan<T>(rows, C, &L, 3, 256) && (sizeof(T) != 2 || L.block <= 256)) {
+      // Bytes in flight decide these kernels (ncu: ~37 % of the warp slots, all stalled on loads): the
+      // y-less variant has two read streams instead of three, so it keeps twice the vectors in flight
+      // (768 threads x 4 x 2 x 16 B = 98 KB per SM, the same as the three-stream variant at U = 2).
+      if (y != nullptr) {
+        if (bn_bwd_unroll() == 4) MCN_BWD_APPLY(4, true);
+        else MCN_BWD_APPLY(2, true);
+      } else {
+        if (bn_noy_unroll() == 2) MCN_BWD_APPLY(2, false);
+        else MCN_BWD_APPLY(4, false);
+      }
     } else {
       long long n = rows * C;
       int grid = (int)std::min<long long>((n + 255) / 256, 8LL * num_sms());
-      bn_bwd_apply_scalar_kernel<T><<<grid, 256, 0, st>>>(
+      ::mcn::launch(bn_bwd_apply_scalar_kernel<T>, grid, 256, 0, st, 
           static_cast<const T*>(dy), static_cast<const T*>(x), static_cast<const T*>(y), n, C,
           mean, invstd, gamma, beta, act, act_alpha, sum_dz, sum_dz_xhat, inv_count,
           static_cast<T*>(dx), static_cast<T*>(d_residual));

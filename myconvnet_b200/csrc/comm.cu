@@ -46,6 +46,7 @@ peer_allreduce_kernel(const unsigned long long* __restrict__ peers, long long ma
                       long long parity_stride, long long flag_off, unsigned long long* counter,
                       const T* __restrict__ src0, int n0, const T* __restrict__ src1, int n1,
                       T* __restrict__ dst, int rank, int world, unsigned long long timeout_ns) {
+  MCN_PDL_PROLOGUE();
   __shared__ unsigned long long seq_s;
   const int n = n0 + n1;
   if (threadIdx.x == 0) {
@@ -117,12 +118,12 @@ extern "C" int mcn_peer_allreduce(const unsigned long long* peers, long long mai
   const unsigned long long tmo = peer_timeout_ns();
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (is_f64)
-    peer_allreduce_kernel<double><<<1, 512, 0, st>>>(peers, mail_off, parity_stride, flag_off, counter,
+    ::mcn::launch(peer_allreduce_kernel<double>, 1, 512, 0, st, peers, mail_off, parity_stride, flag_off, counter,
                                                      static_cast<const double*>(src0), n0,
                                                      static_cast<const double*>(src1), n1,
                                                      static_cast<double*>(dst), rank, world, tmo);
   else
-    peer_allreduce_kernel<float><<<1, 512, 0, st>>>(peers, mail_off, parity_stride, flag_off, counter,
+    ::mcn::launch(peer_allreduce_kernel<float>, 1, 512, 0, st, peers, mail_off, parity_stride, flag_off, counter,
                                                     static_cast<const float*>(src0), n0,
                                                     static_cast<const float*>(src1), n1,
                                                     static_cast<float*>(dst), rank, world, tmo);

@@ -35,6 +35,7 @@ template <typename T, typename TW, int CO>
 __global__ void conv_fprop_direct_kernel(mcn_conv_desc d, const T* __restrict__ x,
                                          const TW* __restrict__ w, const float* __restrict__ bias,
                                          T* __restrict__ y) {
+  MCN_PDL_PROLOGUE();
   const int cog = d.Cout / CO;
   const long long total = (long long)d.N * d.Ho * d.Wo * cog;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -73,6 +74,7 @@ __global__ void conv_fprop_direct_kernel(mcn_conv_desc d, const T* __restrict__ 
 template <typename T, typename TW>
 __global__ void conv_dgrad_direct_kernel(mcn_conv_desc d, const T* __restrict__ dy,
                                          const TW* __restrict__ w, T* __restrict__ dx) {
+  MCN_PDL_PROLOGUE();
   const long long total = (long long)d.N * d.H * d.W * d.Cin;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -108,6 +110,7 @@ template <typename T>
 __global__ void conv_wgrad_direct_kernel(mcn_conv_desc d, const T* __restrict__ x,
                                          const T* __restrict__ dy, float* __restrict__ dw,
                                          long long slice_stride) {
+  MCN_PDL_PROLOGUE();
   // grid.x: (tap*Cin + ci) * ceil(Cout/blockDim.x) ; grid.y: pixel chunks
   const int cob = (d.Cout + blockDim.x - 1) / blockDim.x;
   const int co = (blockIdx.x % cob) * blockDim.x + threadIdx.x;
@@ -150,6 +153,7 @@ template <typename T, typename TW, int MODE, int TN>
 __global__ void __launch_bounds__(256)
 igemm_kernel(mcn_conv_desc d, const T* __restrict__ a_src, const void* __restrict__ b_src,
              const float* __restrict__ bias, void* __restrict__ out, long long slice_stride) {
+  MCN_PDL_PROLOGUE();
   constexpr int BN = 16 * TN;
   __shared__ float As[kIgBK][kIgBM + 4];
   __shared__ float Bs[kIgBK][BN + 4];
@@ -315,10 +319,10 @@ void launch_igemm(const mcn_conv_desc* d, const void* a, const void* b, const fl
   const int Nn = MODE == kIgDgrad ? d->Cin : d->Cout;
   if (Nn <= 16) {
     dim3 grid((unsigned)((M + kIgBM - 1) / kIgBM), (unsigned)((Nn + 15) / 16), (unsigned)zchunks);
-    igemm_kernel<T, TW, MODE, 1><<<grid, 256, 0, st>>>(*d, static_cast<const T*>(a), b, bias, out, slice_stride);
+    ::mcn::launch(igemm_kernel<T, TW, MODE, 1>, grid, 256, 0, st, *d, static_cast<const T*>(a), b, bias, out, slice_stride);
   } else {
     dim3 grid((unsigned)((M + kIgBM - 1) / kIgBM), (unsigned)((Nn + 63) / 64), (unsigned)zchunks);
-    igemm_kernel<T, TW, MODE, 4><<<grid, 256, 0, st>>>(*d, static_cast<const T*>(a), b, bias, out, slice_stride);
+    ::mcn::launch(igemm_kernel<T, TW, MODE, 4>, grid, 256, 0, st, *d, static_cast<const T*>(a), b, bias, out, slice_stride);
   }
 }
 
@@ -335,6 +339,7 @@ inline bool igemm_enabled() {
 template <typename T, typename TW>
 __global__ void dwconv_fwd_kernel(mcn_conv_desc d, int mult, const T* __restrict__ x,
                                   const TW* __restrict__ w, T* __restrict__ y) {
+  MCN_PDL_PROLOGUE();
   const int Co = d.Cin * mult;
   const long long total = (long long)d.N * d.Ho * d.Wo * Co;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -363,6 +368,7 @@ __global__ void dwconv_fwd_kernel(mcn_conv_desc d, int mult, const T* __restrict
 template <typename T, typename TW>
 __global__ void dwconv_bwd_data_kernel(mcn_conv_desc d, int mult, const T* __restrict__ dy,
                                        const TW* __restrict__ w, T* __restrict__ dx) {
+  MCN_PDL_PROLOGUE();
   const int Co = d.Cin * mult;
   const long long total = (long long)d.N * d.H * d.W * d.Cin;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -397,6 +403,7 @@ template <typename T>
 __global__ void dwconv_bwd_filter_kernel(mcn_conv_desc d, int mult, const T* __restrict__ x,
                                          const T* __restrict__ dy, float* __restrict__ dw,
                                          long long slice_stride) {
+  MCN_PDL_PROLOGUE();
   __shared__ float sh[8][33];
   const int Co = d.Cin * mult;
   const int oc = blockIdx.x * 32 + threadIdx.x;
@@ -436,6 +443,7 @@ __global__ void dwconv_bwd_filter_kernel(mcn_conv_desc d, int mult, const T* __r
 template <typename T>
 __global__ void im2col_rows_kernel(mcn_conv_desc d, const T* __restrict__ x,
                                    __nv_bfloat16* __restrict__ col, int kpad) {
+  MCN_PDL_PROLOGUE();
   const int K = d.kh * d.kw * d.Cin;
   const int RL = d.kw * d.Cin;        // run length of one filter row
   const int WL = d.W * d.Cin;         // elements in one input row
@@ -480,6 +488,7 @@ __global__ void im2col_rows_kernel(mcn_conv_desc d, const T* __restrict__ x,
 template <typename T>
 __global__ void im2col_kernel(mcn_conv_desc d, const T* __restrict__ x,
                               __nv_bfloat16* __restrict__ col, int kpad) {
+  MCN_PDL_PROLOGUE();
   const int K = d.kh * d.kw * d.Cin;
   const long long total = (long long)d.N * d.Ho * d.Wo * kpad;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -532,11 +541,11 @@ extern "C" int mcn_conv2d_fprop_direct(const mcn_conv_desc* d, int dtype, const 
   MCN_DISPATCH_DTYPE(dtype, T, MCN_DISPATCH_W(wdtype, TW, {
     if (d->Cout % 4 == 0) {
       long long total = (long long)d->N * d->Ho * d->Wo * (d->Cout / 4);
-      conv_fprop_direct_kernel<T, TW, 4><<<grid_for(total, 128), 128, 0, st>>>(
+      ::mcn::launch(conv_fprop_direct_kernel<T, TW, 4>, grid_for(total, 128), 128, 0, st, 
           *d, static_cast<const T*>(x), static_cast<const TW*>(w), bias, static_cast<T*>(y));
     } else {
       long long total = (long long)d->N * d->Ho * d->Wo * d->Cout;
-      conv_fprop_direct_kernel<T, TW, 1><<<grid_for(total, 128), 128, 0, st>>>(
+      ::mcn::launch(conv_fprop_direct_kernel<T, TW, 1>, grid_for(total, 128), 128, 0, st, 
           *d, static_cast<const T*>(x), static_cast<const TW*>(w), bias, static_cast<T*>(y));
     }
   }));
@@ -554,7 +563,7 @@ extern "C" int mcn_conv2d_dgrad_direct(const mcn_conv_desc* d, int dtype, const 
   }
   long long total = (long long)d->N * d->H * d->W * d->Cin;
   MCN_DISPATCH_DTYPE(dtype, T, MCN_DISPATCH_W(wdtype, TW, {
-    conv_dgrad_direct_kernel<T, TW><<<grid_for(total, 128), 128, 0, st>>>(
+    ::mcn::launch(conv_dgrad_direct_kernel<T, TW>, grid_for(total, 128), 128, 0, st, 
         *d, static_cast<const T*>(dy), static_cast<const TW*>(w), static_cast<T*>(dx));
   }));
   return after_launch("conv_dgrad_direct");
@@ -592,7 +601,7 @@ extern "C" int mcn_conv2d_wgrad_direct(const mcn_conv_desc* d, int dtype, const 
   }
   dim3 grid((unsigned)gx, (unsigned)chunks);
   MCN_DISPATCH_DTYPE(dtype, T, {
-    conv_wgrad_direct_kernel<T><<<grid, block, 0, st>>>(*d, static_cast<const T*>(x),
+    ::mcn::launch(conv_wgrad_direct_kernel<T>, grid, block, 0, st, *d, static_cast<const T*>(x),
                                                         static_cast<const T*>(dy), slices, stride);
   });
   int rc = after_launch("conv_wgrad_direct");
@@ -608,7 +617,7 @@ extern "C" int mcn_dwconv2d_fwd(const mcn_conv_desc* d, int mult, int dtype, con
     return dw_fast_fwd(d, dtype, x, static_cast<const float*>(w), y, st);
   long long total = (long long)d->N * d->Ho * d->Wo * d->Cin * mult;
   MCN_DISPATCH_DTYPE(dtype, T, MCN_DISPATCH_W(wdtype, TW, {
-    dwconv_fwd_kernel<T, TW><<<grid_for(total, 256), 256, 0, st>>>(
+    ::mcn::launch(dwconv_fwd_kernel<T, TW>, grid_for(total, 256), 256, 0, st, 
         *d, mult, static_cast<const T*>(x), static_cast<const TW*>(w), static_cast<T*>(y));
   }));
   return after_launch("dwconv_fwd");
@@ -621,7 +630,7 @@ extern "C" int mcn_dwconv2d_bwd_data(const mcn_conv_desc* d, int mult, int dtype
     return dw_fast_bwd_data(d, dtype, dy, static_cast<const float*>(w), dx, st);
   long long total = (long long)d->N * d->H * d->W * d->Cin;
   MCN_DISPATCH_DTYPE(dtype, T, MCN_DISPATCH_W(wdtype, TW, {
-    dwconv_bwd_data_kernel<T, TW><<<grid_for(total, 256), 256, 0, st>>>(
+    ::mcn::launch(dwconv_bwd_data_kernel<T, TW>, grid_for(total, 256), 256, 0, st, 
         *d, mult, static_cast<const T*>(dy), static_cast<const TW*>(w), static_cast<T*>(dx));
   }));
   return after_launch("dwconv_bwd_data");
@@ -647,7 +656,7 @@ extern "C" int mcn_dwconv2d_bwd_filter(const mcn_conv_desc* d, int mult, int dty
   float* slices = reinterpret_cast<float*>(w.base + kWsSplitOff);
   dim3 grid((unsigned)gx, (unsigned)taps, (unsigned)chunks), block(32, 8);
   MCN_DISPATCH_DTYPE(dtype, T, {
-    dwconv_bwd_filter_kernel<T><<<grid, block, 0, st>>>(*d, mult, static_cast<const T*>(x),
+    ::mcn::launch(dwconv_bwd_filter_kernel<T>, grid, block, 0, st, *d, mult, static_cast<const T*>(x),
                                                         static_cast<const T*>(dy), slices, stride);
   });
   int rc = after_launch("dwconv_bwd_filter");
@@ -663,11 +672,11 @@ extern "C" int mcn_im2col(const mcn_conv_desc* d, int dtype, const void* x, void
   MCN_DISPATCH_DTYPE(dtype, T, {
     if (d->dw == 1) {
       long long total = (long long)d->N * d->Ho * d->Wo * (kpad / 8);
-      im2col_rows_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(
+      ::mcn::launch(im2col_rows_kernel<T>, grid_for(total, 256), 256, 0, st, 
           *d, static_cast<const T*>(x), static_cast<__nv_bfloat16*>(col), kpad);
     } else {
       long long total = (long long)d->N * d->Ho * d->Wo * kpad;
-      im2col_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(*d, static_cast<const T*>(x),
+      ::mcn::launch(im2col_kernel<T>, grid_for(total, 256), 256, 0, st, *d, static_cast<const T*>(x),
                                                             static_cast<__nv_bfloat16*>(col), kpad);
     }
   });

@@ -543,6 +543,8 @@ gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // barriers, tensor-map prefetch and the TMEM allocation above overlap the previous kernel's tail
+  MCN_PDL_PROLOGUE();
   const long long rt_cta0 = RT_NOW();
   (void)rt_cta0;
 
@@ -795,6 +797,8 @@ halo_conv_kernel(const __grid_constant__ HaloArgs args) {
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // barriers, tensor-map prefetch and the TMEM allocation above overlap the previous kernel's tail
+  MCN_PDL_PROLOGUE();
   const int tiles_per_img = args.tiles_w * args.tiles_h;
   const long long rt_cta0 = RT_NOW();
   (void)rt_cta0;
@@ -1093,6 +1097,8 @@ wgrad_kernel(const __grid_constant__ WgradArgs args) {
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // barriers, tensor-map prefetch and the TMEM allocation above overlap the previous kernel's tail
+  MCN_PDL_PROLOGUE();
 
   if (warp == 0) {
     if (ptx::elect_one()) {
@@ -1136,33 +1142,44 @@ wgrad_kernel(const __grid_constant__ WgradArgs args) {
       RT_FLUSH(0);
     }
   } else if (warp == 1) {
-    const uint32_t idesc = ptx::make_idesc_bf16(128, args.block_n, 1, 1);
-    RT_DECL;
-    const long long rt_m0 = RT_NOW();
-    (void)rt_m0;
-    for (int kb = kb0, it = 0; kb < kb1; ++kb, ++it) {
-      const int s = it % stages;
-      const uint32_t ph = static_cast<uint32_t>(it / stages) & 1u;
-      RT_BEGIN;
-      ptx::mbar_wait(&full[s], ph);
-      RT_END;
-      ptx::tc_fence_after();
-      if (ptx::elect_one()) {
-        const uint32_t a_addr = ptx::smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
-        const uint32_t b_addr = a_addr + a_bytes;
-        for (int k = 0; k < args.ksteps; ++k) {
-          // MN-major: 64-channel atoms kABytes apart (LBO), 8-pixel groups 1024 B apart (SBO);
-          // one instruction consumes 16 pixels = 2048 B of each atom.
-          const uint64_t ad = ptx::make_smem_desc(a_addr + k * 2048, kABytes, 1024);
-          const uint64_t bd = ptx::make_smem_desc(b_addr + k * 2048, kABytes, 1024);
-          ptx::umma_bf16(tmem_base, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+    // one thread, tight loop (see gemm_conv_kernel)
+    if (ptx::elect_one()) {
+      const uint32_t idesc = ptx::make_idesc_bf16(128, args.block_n, 1, 1);
+      RT_DECL;
+      const long long rt_m0 = RT_NOW();
+      (void)rt_m0;
+      // MN-major: 64-channel atoms kABytes apart (LBO), 8-pixel groups 1024 B apart (SBO);
+      // one instruction consumes 16 pixels = 2048 B of each atom (descriptor step 128).
+      const uint64_t dhi = ptx::smem_desc_hi(kABytes, 1024);
+      const uint32_t smem0 = ptx::smem_u32(smem);
+      const int ksteps = args.ksteps;
+      int s = 0;
+      uint32_t ph = 0, acc = 0u;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        RT_BEGIN;
+        ptx::mbar_wait_quiet(&full[s], ph);
+        RT_END;
+        ptx::tc_fence_after();
+        const uint32_t a_addr = smem0 + static_cast<uint32_t>(s) * stage_bytes;
+        uint64_t ad = ptx::smem_desc_at(dhi, a_addr);
+        uint64_t bd = ptx::smem_desc_at(dhi, a_addr + a_bytes);
+        if (ksteps == 8) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            ptx::umma_bf16(tmem_base, ad + 128 * k, bd + 128 * k, idesc, k == 0 ? acc : 1u);
+          }
+        } else {
+          for (int k = 0; k < ksteps; ++k)
+            ptx::umma_bf16(tmem_base, ad + 128 * k, bd + 128 * k, idesc, k == 0 ? acc : 1u);
         }
+        acc = 1u;
         ptx::umma_commit(&empty[s]);
-        if (kb == kb1 - 1) ptx::umma_commit(tmem_full);
+        if (++s == stages) {
+          s = 0;
+          ph ^= 1u;
+        }
       }
-      __syncwarp();
-    }
-    if (lane == 0) {
+      ptx::umma_commit(tmem_full);
       RT_FLUSH(1);
       RT_ADD(7, RT_NOW() - rt_m0);
     }
@@ -1283,6 +1300,8 @@ wgrad_halo_kernel(const __grid_constant__ WgradHaloArgs args) {
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // barriers, tensor-map prefetch and the TMEM allocation above overlap the previous kernel's tail
+  MCN_PDL_PROLOGUE();
   const int tiles_per_img = args.tiles_w * args.tiles_h;
 
   if (warp == 0) {
@@ -1307,32 +1326,38 @@ wgrad_halo_kernel(const __grid_constant__ WgradHaloArgs args) {
       }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = ptx::make_idesc_bf16(128, args.block_n, 1, 1);
-    const uint32_t row_pitch = static_cast<uint32_t>(args.hwb) * 128u;   // one output row further
-    for (int t = t0, it = 0; t < t1; ++t, ++it) {
-      const int s = it % stages;
-      const uint32_t ph = static_cast<uint32_t>(it / stages) & 1u;
-      ptx::mbar_wait(&full[s], ph);
-      ptx::tc_fence_after();
-      if (ptx::elect_one()) {
-        const uint32_t a_addr = ptx::smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
-        const uint32_t b_addr = a_addr + a_bytes;
-        for (int acc = 0; acc < args.n_acc; ++acc) {
-          const uint32_t a0 = a_addr + static_cast<uint32_t>(args.aoff[g][acc]);
-          const uint32_t lbo = static_cast<uint32_t>(args.lbo[g][acc]);
+    // one thread, tight loop (see gemm_conv_kernel)
+    if (ptx::elect_one() && t1 > t0) {
+      const uint32_t idesc = ptx::make_idesc_bf16(128, args.block_n, 1, 1);
+      const uint32_t row_pitch = static_cast<uint32_t>(args.hwb) * 128u;   // one output row further
+      const uint32_t kstep_a = (2u * row_pitch) >> 4;   // K = 16 pixels = two output rows of the tile
+      const uint64_t dhi_b = ptx::smem_desc_hi(kABytes, 1024);
+      const uint32_t smem0 = ptx::smem_u32(smem);
+      const int n_acc = args.n_acc;
+      int s = 0;
+      uint32_t ph = 0, accf = 0u;
+      for (int t = t0; t < t1; ++t) {
+        ptx::mbar_wait_quiet(&full[s], ph);
+        ptx::tc_fence_after();
+        const uint32_t a_addr = smem0 + static_cast<uint32_t>(s) * stage_bytes;
+        const uint64_t bd = ptx::smem_desc_at(dhi_b, a_addr + a_bytes);
+        for (int acc = 0; acc < n_acc; ++acc) {
+          const uint64_t ad = ptx::make_smem_desc(a_addr + static_cast<uint32_t>(args.aoff[g][acc]),
+                                                  static_cast<uint32_t>(args.lbo[g][acc]), row_pitch);
           const uint32_t td = tmem_base + static_cast<uint32_t>(acc * args.block_n);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            // K = 16 pixels = output rows 2j and 2j+1 of the tile (8 pixels each)
-            const uint64_t ad = ptx::make_smem_desc(a0 + j * 2 * row_pitch, lbo, row_pitch);
-            const uint64_t bd = ptx::make_smem_desc(b_addr + j * 2048, kABytes, 1024);
-            ptx::umma_bf16(td, ad, bd, idesc, (it | j) != 0 ? 1u : 0u);
-          }
+          for (int j = 0; j < 8; ++j)
+            ptx::umma_bf16(td, ad + static_cast<uint64_t>(kstep_a * j), bd + 128 * j, idesc,
+                           j == 0 ? accf : 1u);
         }
+        accf = 1u;
         ptx::umma_commit(&empty[s]);
-        if (t == t1 - 1) ptx::umma_commit(tmem_full);
+        if (++s == stages) {
+          s = 0;
+          ph ^= 1u;
+        }
       }
-      __syncwarp();
+      ptx::umma_commit(tmem_full);
     }
   } else if (t1 > t0) {
     ptx::mbar_wait(tmem_full, 0);
@@ -1490,6 +1515,8 @@ stem_fprop_kernel(const __grid_constant__ StemArgs args) {
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // barriers, tensor-map prefetch and the TMEM allocation above overlap the previous kernel's tail
+  MCN_PDL_PROLOGUE();
 
   if (warp < 4) {
     // ---------------- gather producers ----------------
@@ -1629,6 +1656,8 @@ stem_wgrad_kernel(const __grid_constant__ StemArgs args) {
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // barriers, tensor-map prefetch and the TMEM allocation above overlap the previous kernel's tail
+  MCN_PDL_PROLOGUE();
   const int m_tiles = args.kc_alloc / 2;     // accumulators of 128 k-rows
 
   if (warp < 4) {
@@ -2012,9 +2041,9 @@ int launch_gemm_conv(GemmConvArgs& a, int tiles_m, bool dense_out, cudaStream_t 
   }
   dim3 grid(static_cast<unsigned>(grid_n));
   if (tma)
-    gemm_conv_kernel<true><<<grid, 192, smem, st>>>(a);
+    ::mcn::launch(gemm_conv_kernel<true>, grid, 192, smem, st, a);
   else
-    gemm_conv_kernel<false><<<grid, 192, smem, st>>>(a);
+    ::mcn::launch(gemm_conv_kernel<false>, grid, 192, smem, st, a);
   return after_launch("gemm_conv_kernel");
 }
 
@@ -2132,9 +2161,9 @@ int launch_halo(const void* in, int C_in, int W_in, int H_in, int N, const void*
   if ((rc = attach_xs(&a.e, a.total_tiles / a.tiles_n, a.tiles_n))) return rc;
   dim3 grid((unsigned)std::min(a.total_tiles, num_sms()));
   if (tma)
-    halo_conv_kernel<true><<<grid, 224, smem, st>>>(a);
+    ::mcn::launch(halo_conv_kernel<true>, grid, 224, smem, st, a);
   else
-    halo_conv_kernel<false><<<grid, 224, smem, st>>>(a);
+    ::mcn::launch(halo_conv_kernel<false>, grid, 224, smem, st, a);
   return after_launch("halo_conv_kernel");
 }
 
@@ -2525,7 +2554,7 @@ static int try_wgrad_halo(const mcn_conv_desc* d, const void* x, const void* dy,
     configured = true;
   }
   dim3 grid((unsigned)(units * a.splits));
-  wgrad_halo_kernel<<<grid, 192, smem, st>>>(a);
+  ::mcn::launch(wgrad_halo_kernel, grid, 192, smem, st, a);
   rc = after_launch("wgrad_halo_kernel");
   if (rc) return rc;
   if (sp.stride && (rc = launch_splitk_reduce(sp.base, sp.stride, a.splits, dw_elems, dw, st))) return rc;
@@ -2665,7 +2694,7 @@ static int wgrad_tc_impl(const mcn_conv_desc* d, const void* x, const void* dy, 
     configured = true;
   }
   dim3 grid((unsigned)(taps * a.tiles_mi * a.tiles_ni * a.splits));
-  wgrad_kernel<<<grid, 192, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  ::mcn::launch(wgrad_kernel, grid, 192, smem, static_cast<cudaStream_t>(stream), a);
   if ((rc = after_launch("wgrad_kernel"))) return rc;
   if (sp.stride)
     return launch_splitk_reduce(sp.base, sp.stride, a.splits, dw_elems, dw, static_cast<cudaStream_t>(stream));
@@ -2752,7 +2781,7 @@ extern "C" int mcn_stem_conv_fprop(const mcn_conv_desc* d, const void* x4, const
   }
   if ((rc = attach_xs(&a.e, a.total_tiles, 1))) return rc;
   dim3 grid(static_cast<unsigned>(std::min(a.total_tiles, num_sms())));
-  stem_fprop_kernel<<<grid, 288, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  ::mcn::launch(stem_fprop_kernel, grid, 288, smem, static_cast<cudaStream_t>(stream), a);
   return after_launch("stem_fprop_kernel");
 }
 
@@ -2793,7 +2822,7 @@ static int stem_wgrad_impl(const mcn_conv_desc* d, const void* x4, const void* d
     }
     configured = true;
   }
-  stem_wgrad_kernel<<<a.splits, 288, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  ::mcn::launch(stem_wgrad_kernel, a.splits, 288, smem, static_cast<cudaStream_t>(stream), a);
   if ((rc = after_launch("stem_wgrad_kernel"))) return rc;
   if (sp.stride)
     return launch_splitk_reduce(sp.base, sp.stride, a.splits, dw_elems, dw, static_cast<cudaStream_t>(stream));

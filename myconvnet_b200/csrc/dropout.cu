@@ -47,6 +47,7 @@ __device__ __forceinline__ float u01(uint32_t bits) { return static_cast<float>(
 template <typename T>
 __global__ void dropout_kernel(const T* __restrict__ x, long long n, float rate, const float* __restrict__ hp,
                                uint32_t layer, T* __restrict__ y) {
+  MCN_PDL_PROLOGUE();
   const uint32_t seed = reinterpret_cast<const uint32_t*>(hp)[kHpSeedSlot];
   const uint32_t step = reinterpret_cast<const uint32_t*>(hp)[kHpStepSlot];
   const float scale = 1.f / (1.f - rate);
@@ -75,6 +76,7 @@ template <typename T>
 __global__ void sd_add_fwd_kernel(const T* __restrict__ a, const T* __restrict__ b, int N, long long per,
                                   float rate, const float* __restrict__ hp, uint32_t layer, int act,
                                   float alpha, T* __restrict__ y) {
+  MCN_PDL_PROLOGUE();
   const uint32_t seed = reinterpret_cast<const uint32_t*>(hp)[kHpSeedSlot];
   const uint32_t step = reinterpret_cast<const uint32_t*>(hp)[kHpStepSlot];
   const long long total = (long long)N * per;
@@ -89,6 +91,7 @@ template <typename T>
 __global__ void sd_add_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, int N, long long per,
                                   float rate, const float* __restrict__ hp, uint32_t layer, int act,
                                   float alpha, T* __restrict__ da, T* __restrict__ db) {
+  MCN_PDL_PROLOGUE();
   const uint32_t seed = reinterpret_cast<const uint32_t*>(hp)[kHpSeedSlot];
   const uint32_t step = reinterpret_cast<const uint32_t*>(hp)[kHpStepSlot];
   const long long total = (long long)N * per;
@@ -119,6 +122,7 @@ __device__ __forceinline__ int nearest_src(int dst, int in, int out, int mode) {
 template <typename T>
 __global__ void resize_nearest_fwd_kernel(const T* __restrict__ x, int N, int H, int W, int C, int Ho,
                                           int Wo, int mode, T* __restrict__ y) {
+  MCN_PDL_PROLOGUE();
   const long long total = (long long)N * Ho * Wo * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -137,6 +141,7 @@ __global__ void resize_nearest_fwd_kernel(const T* __restrict__ x, int N, int H,
 template <typename T>
 __global__ void resize_nearest_bwd_kernel(const T* __restrict__ dy, int N, int H, int W, int C, int Ho,
                                           int Wo, int mode, T* __restrict__ dx) {
+  MCN_PDL_PROLOGUE();
   const long long total = (long long)N * H * W * C;
   const int rh = Ho / max(H, 1) + 2, rw = Wo / max(W, 1) + 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -172,7 +177,7 @@ extern "C" int mcn_dropout(int dtype, const void* x, long long n, float rate, co
   MCN_REQUIRE(x && y && hp && n >= 0 && rate >= 0.f && rate < 1.f, "dropout: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MCN_DISPATCH_DTYPE(dtype, T, {
-    dropout_kernel<T><<<grid_for((n + 3) / 4, 256), 256, 0, st>>>(static_cast<const T*>(x), n, rate, hp,
+    ::mcn::launch(dropout_kernel<T>, grid_for((n + 3) / 4, 256), 256, 0, st, static_cast<const T*>(x), n, rate, hp,
                                                               static_cast<uint32_t>(layer), static_cast<T*>(y));
   });
   return after_launch("dropout");
@@ -187,7 +192,7 @@ extern "C" int mcn_sd_add_fwd(int dtype, const void* a, const void* b, int N, lo
               "sd_add_fwd: only relu-family activations can be fused (derivative from the output)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MCN_DISPATCH_DTYPE(dtype, T, {
-    sd_add_fwd_kernel<T><<<grid_for((long long)N * per_sample, 256), 256, 0, st>>>(
+    ::mcn::launch(sd_add_fwd_kernel<T>, grid_for((long long)N * per_sample, 256), 256, 0, st, 
         static_cast<const T*>(a), static_cast<const T*>(b), N, per_sample, rate, hp,
         static_cast<uint32_t>(layer), act, alpha, static_cast<T*>(y));
   });
@@ -199,7 +204,7 @@ extern "C" int mcn_sd_add_bwd(int dtype, const void* dy, const void* y, int N, l
   MCN_REQUIRE(dy && hp && N > 0 && per_sample > 0 && (act == MCN_ACT_NONE || y), "sd_add_bwd: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MCN_DISPATCH_DTYPE(dtype, T, {
-    sd_add_bwd_kernel<T><<<grid_for((long long)N * per_sample, 256), 256, 0, st>>>(
+    ::mcn::launch(sd_add_bwd_kernel<T>, grid_for((long long)N * per_sample, 256), 256, 0, st, 
         static_cast<const T*>(dy), static_cast<const T*>(y), N, per_sample, rate, hp,
         static_cast<uint32_t>(layer), act, alpha, static_cast<T*>(da), static_cast<T*>(db));
   });
@@ -211,7 +216,7 @@ extern "C" int mcn_resize_nearest_fwd(int dtype, const void* x, int N, int H, in
   MCN_REQUIRE(x && y && mode >= 0 && mode <= 2, "resize_nearest_fwd: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MCN_DISPATCH_DTYPE(dtype, T, {
-    resize_nearest_fwd_kernel<T><<<grid_for((long long)N * Ho * Wo * C, 256), 256, 0, st>>>(
+    ::mcn::launch(resize_nearest_fwd_kernel<T>, grid_for((long long)N * Ho * Wo * C, 256), 256, 0, st, 
         static_cast<const T*>(x), N, H, W, C, Ho, Wo, mode, static_cast<T*>(y));
   });
   return after_launch("resize_nearest_fwd");
@@ -221,7 +226,7 @@ extern "C" int mcn_resize_nearest_bwd(int dtype, const void* dy, int N, int H, i
   MCN_REQUIRE(dy && dx && mode >= 0 && mode <= 2, "resize_nearest_bwd: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MCN_DISPATCH_DTYPE(dtype, T, {
-    resize_nearest_bwd_kernel<T><<<grid_for((long long)N * H * W * C, 256), 256, 0, st>>>(
+    ::mcn::launch(resize_nearest_bwd_kernel<T>, grid_for((long long)N * H * W * C, 256), 256, 0, st, 
         static_cast<const T*>(dy), N, H, W, C, Ho, Wo, mode, static_cast<T*>(dx));
   });
   return after_launch("resize_nearest_bwd");

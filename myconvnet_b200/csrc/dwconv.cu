@@ -48,6 +48,7 @@ template <typename T, int K, int S, int TW, bool kFlip>
 __global__ void __launch_bounds__(256)
 dw_fwd_kernel(const T* __restrict__ in, const float* __restrict__ wt, int N, int H, int W, int C, int Ho, int Wo,
               int pad_t, int pad_l, T* __restrict__ out) {
+  MCN_PDL_PROLOGUE();
   constexpr int V = Vec16<T>::N;
   constexpr int SEG = (TW - 1) * S + K;
   const int cv = C / V;
@@ -107,6 +108,7 @@ template <typename T, int K, int S>
 __global__ void __launch_bounds__(256)
 dw_bwd_data_strided_kernel(const T* __restrict__ dy, const float* __restrict__ wt, int N, int H, int W, int C,
                            int Ho, int Wo, int pad_t, int pad_l, T* __restrict__ dx) {
+  MCN_PDL_PROLOGUE();
   constexpr int V = Vec16<T>::N;
   constexpr int NT = (K + S - 1) / S;          // taps of one parity along an axis
   const int cv = C / V;
@@ -155,6 +157,7 @@ __global__ void __launch_bounds__(256)
 dw_bwd_filter_kernel(const T* __restrict__ x, const T* __restrict__ dy, int N, int H, int W, int C, int Ho,
                      int Wo, int pad_t, int pad_l, int cvb, int pl, float* __restrict__ slices,
                      long long slice_stride) {
+  MCN_PDL_PROLOGUE();
   constexpr int V = Vec16<T>::N;
   constexpr int SEG = (TW - 1) * S + K;
   extern __shared__ float sh[];                       // [pl][K][cvb][K*V]
@@ -228,7 +231,7 @@ template <typename T, int K, int S, int TW, bool kFlip>
 void launch_fwd(const void* in, const float* w, int N, int H, int W, int C, int Ho, int Wo, int pad_t, int pad_l,
                 void* out, cudaStream_t st) {
   const long long total = (long long)N * Ho * ((Wo + TW - 1) / TW) * (C / Vec16<T>::N);
-  dw_fwd_kernel<T, K, S, TW, kFlip><<<grid_for(total, 256), 256, 0, st>>>(
+  ::mcn::launch(dw_fwd_kernel<T, K, S, TW, kFlip>, grid_for(total, 256), 256, 0, st, 
       static_cast<const T*>(in), w, N, H, W, C, Ho, Wo, pad_t, pad_l, static_cast<T*>(out));
 }
 
@@ -270,7 +273,7 @@ int dw_fast_bwd_data(const mcn_conv_desc* d, int dtype, const void* dy, const fl
         launch_fwd<T, K, 1, 1, true>(dy, w, d->N, d->Ho, d->Wo, d->Cin, d->H, d->W, K - 1 - d->pad_t, K - 1 - d->pad_l, dx, st);
     } else {
       const long long total = (long long)d->N * d->H * d->W * (d->Cin / Vec16<T>::N);
-      dw_bwd_data_strided_kernel<T, K, (S == 1 ? 2 : S)><<<grid_for(total, 256), 256, 0, st>>>(
+      ::mcn::launch(dw_bwd_data_strided_kernel<T, K, (S == 1 ? 2 : S)>, grid_for(total, 256), 256, 0, st, 
           static_cast<const T*>(dy), w, d->N, d->H, d->W, d->Cin, d->Ho, d->Wo, d->pad_t, d->pad_l,
           static_cast<T*>(dx));
     }
@@ -300,11 +303,11 @@ int dw_fast_bwd_filter(const mcn_conv_desc* d, int dtype, const void* x, const v
   dim3 grid((unsigned)groups, (unsigned)chunks), block((unsigned)cvb, (unsigned)K0, (unsigned)pl);
   MCN_DISPATCH_DTYPE(dtype, T, MCN_DW_DISPATCH_KS(d->kh, d->sh, {
     if (d->Wo >= 4)
-      dw_bwd_filter_kernel<T, K, S, 4><<<grid, block, smem, st>>>(
+      ::mcn::launch(dw_bwd_filter_kernel<T, K, S, 4>, grid, block, smem, st, 
           static_cast<const T*>(x), static_cast<const T*>(dy), d->N, d->H, d->W, d->Cin, d->Ho, d->Wo, d->pad_t,
           d->pad_l, cvb, pl, slices, stride);
     else
-      dw_bwd_filter_kernel<T, K, S, 1><<<grid, block, smem, st>>>(
+      ::mcn::launch(dw_bwd_filter_kernel<T, K, S, 1>, grid, block, smem, st, 
           static_cast<const T*>(x), static_cast<const T*>(dy), d->N, d->H, d->W, d->Cin, d->Ho, d->Wo, d->pad_t,
           d->pad_l, cvb, pl, slices, stride);
   }));

@@ -17,6 +17,7 @@ inline int grid_for(long long n, int block) {
 template <typename T, bool kTwo, typename F>
 __global__ void map_kernel(const T* __restrict__ a, const T* __restrict__ b, long long n,
                            T* __restrict__ y, F f) {
+  MCN_PDL_PROLOGUE();
   constexpr int V = Vec16<T>::N;
   const long long nvec = n / V;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -37,7 +38,7 @@ template <typename T, bool kTwo, typename F>
 int launch_map(const void* a, const void* b, long long n, void* y, cudaStream_t st, F f,
                const char* what) {
   constexpr int V = Vec16<T>::N;
-  map_kernel<T, kTwo, F><<<grid_for((n + V - 1) / V, 256), 256, 0, st>>>(
+  ::mcn::launch(map_kernel<T, kTwo, F>, grid_for((n + V - 1) / V, 256), 256, 0, st, 
       static_cast<const T*>(a), static_cast<const T*>(b), n, static_cast<T*>(y), f);
   return after_launch(what);
 }
@@ -69,6 +70,7 @@ struct AddF {
 template <typename T>
 __global__ void scale_bcast_fwd_kernel(const T* __restrict__ x, const T* __restrict__ m, int HW,
                                        int C, long long total, T* __restrict__ y) {
+  MCN_PDL_PROLOGUE();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     int c = (int)(i % C);
@@ -81,6 +83,7 @@ template <typename T>
 __global__ void scale_bcast_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                                        const T* __restrict__ m, int HW, int C,
                                        T* __restrict__ dx, float* __restrict__ dm) {
+  MCN_PDL_PROLOGUE();
   __shared__ float sh[8][33];
   int n = blockIdx.y;
   int c = blockIdx.x * 32 + threadIdx.x;
@@ -107,6 +110,7 @@ __global__ void scale_bcast_bwd_kernel(const T* __restrict__ dy, const T* __rest
 template <typename T>
 __global__ void bias_add_kernel(T* __restrict__ y, long long total, int C,
                                 const float* __restrict__ bias) {
+  MCN_PDL_PROLOGUE();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x)
     y[i] = from_f32<T>(to_f32(y[i]) + bias[i % C]);
@@ -115,6 +119,7 @@ __global__ void bias_add_kernel(T* __restrict__ y, long long total, int C,
 template <typename T>
 __global__ void bias_grad_kernel(const T* __restrict__ dy, long long rows, int C,
                                  float* __restrict__ db, XsScratch xsc) {
+  MCN_PDL_PROLOGUE();
   __shared__ float sh[8][33];
   int c = blockIdx.x * 32 + threadIdx.x;
   long long r0 = rows * blockIdx.y / gridDim.y, r1 = rows * (blockIdx.y + 1) / gridDim.y;
@@ -140,6 +145,7 @@ __global__ void bias_grad_kernel(const T* __restrict__ dy, long long rows, int C
 
 template <typename TS, typename TD>
 __global__ void cast_kernel(const TS* __restrict__ s, TD* __restrict__ d, long long n) {
+  MCN_PDL_PROLOGUE();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)
     d[i] = from_f32<TD>(to_f32(s[i]));
@@ -150,6 +156,7 @@ __global__ void cast_kernel(const TS* __restrict__ s, TD* __restrict__ d, long l
 template <typename TS, typename TD>
 __global__ void input_prep_kernel(const TS* __restrict__ x, int N, int Hi, int Wi, int H, int W, int C,
                                   float mean, float scale, TD* __restrict__ y) {
+  MCN_PDL_PROLOGUE();
   const int oh = (Hi - H) / 2, ow = (Wi - W) / 2;
   const long long row = (long long)W * C;
   const long long total = (long long)N * H * row;
@@ -171,6 +178,7 @@ template <typename T>
 __global__ void copy_channels_kernel(const T* __restrict__ src, long long rows, int Csrc,
                                      int src_off, T* __restrict__ dst, int Cdst, int dst_off,
                                      int Ccopy, int accumulate) {
+  MCN_PDL_PROLOGUE();
   const long long total = rows * Ccopy;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -207,6 +215,7 @@ __device__ __forceinline__ void lerp_idx(int dst, int in, int out, int mode, int
 template <typename T>
 __global__ void resize_fwd_kernel(const T* __restrict__ x, int N, int H, int W, int C, int Ho,
                                   int Wo, int mode, T* __restrict__ y) {
+  MCN_PDL_PROLOGUE();
   const long long total = (long long)N * Ho * Wo * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -233,6 +242,7 @@ __global__ void resize_fwd_kernel(const T* __restrict__ x, int N, int H, int W, 
 template <typename T>
 __global__ void resize_bwd_kernel(const T* __restrict__ dy, int N, int H, int W, int C, int Ho,
                                   int Wo, int mode, T* __restrict__ dx) {
+  MCN_PDL_PROLOGUE();
   const long long total = (long long)N * H * W * C;
   // conservative footprint of one input pixel in output space
   const int rh = (int)ceilf((float)Ho / (float)max(H - (mode == 1 ? 1 : 0), 1)) + 1;
@@ -269,11 +279,13 @@ __global__ void resize_bwd_kernel(const T* __restrict__ dy, int N, int H, int W,
 }
 
 __global__ void fill_kernel(float* p, long long n, float v) {
+  MCN_PDL_PROLOGUE();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)
     p[i] = v;
 }
 __global__ void scale_kernel(float* p, long long n, float s) {
+  MCN_PDL_PROLOGUE();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)
     p[i] *= s;
@@ -325,7 +337,7 @@ extern "C" int mcn_scale_bcast_fwd(int dtype, const void* x, const void* m, int 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   long long total = (long long)N * HW * C;
   MCN_DISPATCH_DTYPE(dtype, T, {
-    scale_bcast_fwd_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(
+    ::mcn::launch(scale_bcast_fwd_kernel<T>, grid_for(total, 256), 256, 0, st, 
         static_cast<const T*>(x), static_cast<const T*>(m), HW, C, total, static_cast<T*>(y));
   });
   return after_launch("scale_bcast_fwd");
@@ -336,7 +348,7 @@ extern "C" int mcn_scale_bcast_bwd(int dtype, const void* dy, const void* x, con
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 grid((C + 31) / 32, N), block(32, 8);
   MCN_DISPATCH_DTYPE(dtype, T, {
-    scale_bcast_bwd_kernel<T><<<grid, block, 0, st>>>(
+    ::mcn::launch(scale_bcast_bwd_kernel<T>, grid, block, 0, st, 
         static_cast<const T*>(dy), static_cast<const T*>(x), static_cast<const T*>(m), HW, C,
         static_cast<T*>(dx), dm);
   });
@@ -349,7 +361,7 @@ extern "C" int mcn_bias_add(int dtype, void* y, long long rows, int C, const flo
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   long long total = rows * C;
   MCN_DISPATCH_DTYPE(dtype, T, {
-    bias_add_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(static_cast<T*>(y), total, C, bias);
+    ::mcn::launch(bias_add_kernel<T>, grid_for(total, 256), 256, 0, st, static_cast<T*>(y), total, C, bias);
   });
   return after_launch("bias_add");
 }
@@ -362,7 +374,7 @@ extern "C" int mcn_bias_grad(int dtype, const void* dy, long long rows, int C, f
   int chunks = (int)std::max<long long>(1, std::min<long long>(rows / 64, 2LL * num_sms()));
   dim3 grid((C + 31) / 32, chunks), block(32, 8);
   MCN_DISPATCH_DTYPE(dtype, T, {
-    bias_grad_kernel<T><<<grid, block, 0, st>>>(static_cast<const T*>(dy), rows, C, db, xsc);
+    ::mcn::launch(bias_grad_kernel<T>, grid, block, 0, st, static_cast<const T*>(dy), rows, C, db, xsc);
   });
   return after_launch("bias_grad");
 }
@@ -373,13 +385,13 @@ extern "C" int mcn_cast(int src_dtype, const void* src, int dst_dtype, void* dst
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int g = grid_for(n, 256);
   if (src_dtype == MCN_F32 && dst_dtype == MCN_BF16)
-    cast_kernel<float, __nv_bfloat16><<<g, 256, 0, st>>>((const float*)src, (__nv_bfloat16*)dst, n);
+    ::mcn::launch(cast_kernel<float, __nv_bfloat16>, g, 256, 0, st, (const float*)src, (__nv_bfloat16*)dst, n);
   else if (src_dtype == MCN_BF16 && dst_dtype == MCN_F32)
-    cast_kernel<__nv_bfloat16, float><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, (float*)dst, n);
+    ::mcn::launch(cast_kernel<__nv_bfloat16, float>, g, 256, 0, st, (const __nv_bfloat16*)src, (float*)dst, n);
   else if (src_dtype == MCN_F32 && dst_dtype == MCN_F32)
-    cast_kernel<float, float><<<g, 256, 0, st>>>((const float*)src, (float*)dst, n);
+    ::mcn::launch(cast_kernel<float, float>, g, 256, 0, st, (const float*)src, (float*)dst, n);
   else if (src_dtype == MCN_BF16 && dst_dtype == MCN_BF16)
-    cast_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)src,
+    ::mcn::launch(cast_kernel<__nv_bfloat16, __nv_bfloat16>, g, 256, 0, st, (const __nv_bfloat16*)src,
                                                                  (__nv_bfloat16*)dst, n);
   else {
     set_error("cast: unsupported dtypes %d -> %d", src_dtype, dst_dtype);
@@ -392,6 +404,7 @@ extern "C" int mcn_cast(int src_dtype, const void* src, int dst_dtype, void* dst
 template <typename TD>
 __global__ void input_prep_u8_flat_kernel(const uint4* __restrict__ x, long long n16, float mean, float scale,
                                           TD* __restrict__ y) {
+  MCN_PDL_PROLOGUE();
   const float k = scale * (1.f / 255.f), b = -mean * scale;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16;
        i += (long long)gridDim.x * blockDim.x) {
@@ -420,20 +433,20 @@ extern "C" int mcn_input_prep(const void* x, int src_dtype, int N, int Hi, int W
   const int g = grid_for(n, 256);
   if (src_dtype == MCN_F32) {
     if (dst_dtype == MCN_F32)
-      input_prep_kernel<float, float><<<g, 256, 0, st>>>((const float*)x, N, Hi, Wi, H, W, C, mean, scale, (float*)y);
+      ::mcn::launch(input_prep_kernel<float, float>, g, 256, 0, st, (const float*)x, N, Hi, Wi, H, W, C, mean, scale, (float*)y);
     else
-      input_prep_kernel<float, __nv_bfloat16><<<g, 256, 0, st>>>((const float*)x, N, Hi, Wi, H, W, C, mean, scale,
+      ::mcn::launch(input_prep_kernel<float, __nv_bfloat16>, g, 256, 0, st, (const float*)x, N, Hi, Wi, H, W, C, mean, scale,
                                                                (__nv_bfloat16*)y);
   } else if (Hi == H && Wi == W && n % 16 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0 &&
              reinterpret_cast<uintptr_t>(y) % 16 == 0 && dst_dtype == MCN_BF16) {
-    input_prep_u8_flat_kernel<__nv_bfloat16><<<grid_for(n / 16, 256), 256, 0, st>>>(
+    ::mcn::launch(input_prep_u8_flat_kernel<__nv_bfloat16>, grid_for(n / 16, 256), 256, 0, st, 
         (const uint4*)x, n / 16, mean, scale, (__nv_bfloat16*)y);
   } else {
     if (dst_dtype == MCN_F32)
-      input_prep_kernel<uint8_t, float><<<g, 256, 0, st>>>((const uint8_t*)x, N, Hi, Wi, H, W, C, mean, scale,
+      ::mcn::launch(input_prep_kernel<uint8_t, float>, g, 256, 0, st, (const uint8_t*)x, N, Hi, Wi, H, W, C, mean, scale,
                                                          (float*)y);
     else
-      input_prep_kernel<uint8_t, __nv_bfloat16><<<g, 256, 0, st>>>((const uint8_t*)x, N, Hi, Wi, H, W, C, mean,
+      ::mcn::launch(input_prep_kernel<uint8_t, __nv_bfloat16>, g, 256, 0, st, (const uint8_t*)x, N, Hi, Wi, H, W, C, mean,
                                                                  scale, (__nv_bfloat16*)y);
   }
   return after_launch("input_prep");
@@ -442,6 +455,7 @@ extern "C" int mcn_input_prep(const void* x, int src_dtype, int N, int Hi, int W
 // RGB -> 4-channel pixels (the stem convolution's input format): 4 pixels per thread, 24 bytes in
 // (three aligned 8-byte loads), 32 bytes out; the 4th channel is written as zero.
 __global__ void pad3to4_kernel(const uint2* __restrict__ x, long long quads, uint4* __restrict__ y) {
+  MCN_PDL_PROLOGUE();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < quads;
        i += (long long)gridDim.x * blockDim.x) {
     const uint2 a = x[3 * i], b = x[3 * i + 1], c = x[3 * i + 2];
@@ -461,6 +475,7 @@ __global__ void pad3to4_kernel(const uint2* __restrict__ x, long long quads, uin
 }
 __global__ void pad3to4_tail_kernel(const __nv_bfloat16* __restrict__ x, long long p0, long long p1,
                                     __nv_bfloat16* __restrict__ y) {
+  MCN_PDL_PROLOGUE();
   for (long long p = p0 + blockIdx.x * blockDim.x + threadIdx.x; p < p1; p += (long long)gridDim.x * blockDim.x) {
     y[4 * p] = x[3 * p];
     y[4 * p + 1] = x[3 * p + 1];
@@ -476,10 +491,10 @@ extern "C" int mcn_pad_rgb4(const void* x_bf16, long long pixels, void* y_bf16, 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long quads = pixels / 4;
   if (quads > 0)
-    pad3to4_kernel<<<grid_for(quads, 256), 256, 0, st>>>(static_cast<const uint2*>(x_bf16), quads,
+    ::mcn::launch(pad3to4_kernel, grid_for(quads, 256), 256, 0, st, static_cast<const uint2*>(x_bf16), quads,
                                                          static_cast<uint4*>(y_bf16));
   if (quads * 4 < pixels)
-    pad3to4_tail_kernel<<<1, 32, 0, st>>>(static_cast<const __nv_bfloat16*>(x_bf16), quads * 4, pixels,
+    ::mcn::launch(pad3to4_tail_kernel, 1, 32, 0, st, static_cast<const __nv_bfloat16*>(x_bf16), quads * 4, pixels,
                                           static_cast<__nv_bfloat16*>(y_bf16));
   return after_launch("pad_rgb4");
 }
@@ -491,7 +506,7 @@ extern "C" int mcn_copy_channels(int dtype, const void* src, long long rows, int
               "copy_channels: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MCN_DISPATCH_DTYPE(dtype, T, {
-    copy_channels_kernel<T><<<grid_for(rows * Ccopy, 256), 256, 0, st>>>(
+    ::mcn::launch(copy_channels_kernel<T>, grid_for(rows * Ccopy, 256), 256, 0, st, 
         static_cast<const T*>(src), rows, Csrc, src_off, static_cast<T*>(dst), Cdst, dst_off, Ccopy,
         accumulate);
   });
@@ -504,7 +519,7 @@ extern "C" int mcn_resize_bilinear_fwd(int dtype, const void* x, int N, int H, i
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   long long total = (long long)N * Ho * Wo * C;
   MCN_DISPATCH_DTYPE(dtype, T, {
-    resize_fwd_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const T*>(x), N, H, W, C,
+    ::mcn::launch(resize_fwd_kernel<T>, grid_for(total, 256), 256, 0, st, static_cast<const T*>(x), N, H, W, C,
                                                               Ho, Wo, mode, static_cast<T*>(y));
   });
   return after_launch("resize_fwd");
@@ -515,7 +530,7 @@ extern "C" int mcn_resize_bilinear_bwd(int dtype, const void* dy, int N, int H, 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   long long total = (long long)N * H * W * C;
   MCN_DISPATCH_DTYPE(dtype, T, {
-    resize_bwd_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const T*>(dy), N, H, W,
+    ::mcn::launch(resize_bwd_kernel<T>, grid_for(total, 256), 256, 0, st, static_cast<const T*>(dy), N, H, W,
                                                               C, Ho, Wo, mode, static_cast<T*>(dx));
   });
   return after_launch("resize_bwd");
@@ -523,11 +538,11 @@ extern "C" int mcn_resize_bilinear_bwd(int dtype, const void* dy, int N, int H, 
 
 extern "C" int mcn_fill_f32(float* p, long long n, float v, void* stream) {
   MCN_REQUIRE(p, "fill: null");
-  fill_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, n, v);
+  ::mcn::launch(fill_kernel, grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream), p, n, v);
   return after_launch("fill");
 }
 extern "C" int mcn_scale_f32(float* p, long long n, float s, void* stream) {
   MCN_REQUIRE(p, "scale: null");
-  scale_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, n, s);
+  ::mcn::launch(scale_kernel, grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream), p, n, s);
   return after_launch("scale");
 }

@@ -55,6 +55,7 @@ __global__ void softmax_xent_kernel(const float* __restrict__ logits,
                                     const float* __restrict__ class_w, XentOpts o, float grad_scale,
                                     long long* __restrict__ loss_xs, float* __restrict__ dlogits,
                                     float* __restrict__ probs) {
+  MCN_PDL_PROLOGUE();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   float block_loss = 0.f;
@@ -122,6 +123,7 @@ __global__ void softmax_xent_kernel(const float* __restrict__ logits,
 __global__ void sigmoid_xent_kernel(const float* __restrict__ logits, long long n, float label,
                                     float weight, float grad_scale, long long* __restrict__ loss_xs,
                                     float* __restrict__ dlogits, int accumulate) {
+  MCN_PDL_PROLOGUE();
   float acc = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -151,7 +153,7 @@ extern "C" int mcn_softmax_xent(const float* logits, const int32_t* labels, long
   XentOpts o{label_smoothing, focal_gamma, sigmoid_focal_alpha, seg_h, seg_w};
   const int wpb = 8;
   int grid = (int)std::max<long long>(1, std::min<long long>((rows + wpb - 1) / wpb, 8LL * num_sms()));
-  softmax_xent_kernel<<<grid, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+  ::mcn::launch(softmax_xent_kernel, grid, wpb * 32, 0, static_cast<cudaStream_t>(stream), 
       logits, labels, rows, C, class_w, o, grad_scale, loss_xs, dlogits, probs);
   return after_launch("softmax_xent");
 }
@@ -161,7 +163,7 @@ extern "C" int mcn_sigmoid_xent(const float* logits, long long n, float label, f
                                 int accumulate_grad, void* stream) {
   MCN_REQUIRE(logits && n > 0, "sigmoid_xent: bad argument");
   int grid = (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, 4LL * num_sms()));
-  sigmoid_xent_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  ::mcn::launch(sigmoid_xent_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), 
       logits, n, label, weight, grad_scale, loss_xs, dlogits, accumulate_grad);
   return after_launch("sigmoid_xent");
 }

@@ -27,6 +27,36 @@ inline int after_launch(const char* what) {
   return MCN_OK;
 }
 
+// Programmatic dependent launch: every kernel of the library is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so the NEXT kernel's blocks may be scheduled
+// (and run their private prologue) while this one drains.  MCN_PDL_PROLOGUE() is the first thing a
+// kernel does before it touches global memory: it waits until the previous grid has completed and
+// its writes are visible.  Correctness never depends
+// on it (without the attribute the instruction is a no-op).  MCN_PDL=1 switches the attribute ON: it
+// is off by default because replayed CUDA graphs showed no gain from it (profiles/README.md).
+// (An explicit early griddepcontrol.launch_dependents was measured SLOWER, 25.1 vs 22.8 ms/step:
+// dependent blocks then sit resident next to the primary for its whole run.  The implicit trigger at
+// block exit keeps co-residency to the primary's tail.)
+#define MCN_PDL_PROLOGUE() asm volatile("griddepcontrol.wait;" ::: "memory")
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                   Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline int num_sms() {
   static int n = 0;
   if (n == 0) {

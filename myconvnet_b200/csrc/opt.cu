@@ -19,6 +19,7 @@ constexpr int kBlock = 256;
 __global__ void __launch_bounds__(kBlock)
 grad_sqnorm_kernel(const mcn_opt_tensor* __restrict__ table, const float* __restrict__ hp,
                    long long* __restrict__ out_xs) {
+  MCN_PDL_PROLOGUE();
   const mcn_opt_tensor t = table[blockIdx.y];
   const long long base = (long long)blockIdx.x * (kBlock * kItems);
   if (base >= t.n || t.g == nullptr) return;
@@ -52,6 +53,7 @@ grad_sqnorm_kernel(const mcn_opt_tensor* __restrict__ table, const float* __rest
 __global__ void __launch_bounds__(kBlock)
 opt_step_kernel(int kind, const mcn_opt_tensor* __restrict__ table, const float* __restrict__ hp,
                 long long* __restrict__ l2_xs, const long long* __restrict__ grad_sqnorm_xs) {
+  MCN_PDL_PROLOGUE();
   const mcn_opt_tensor t = table[blockIdx.y];
   const long long base = (long long)blockIdx.x * (kBlock * kItems);
   if (base >= t.n) return;
@@ -124,6 +126,7 @@ opt_step_kernel(int kind, const mcn_opt_tensor* __restrict__ table, const float*
 // out[t][c][r] += in[t][r][c]   (in: [taps][rows][cols])
 __global__ void transpose_add_kernel(const float* __restrict__ in, int rows, int cols,
                                      float* __restrict__ out) {
+  MCN_PDL_PROLOGUE();
   __shared__ float tile[32][33];
   const int t = blockIdx.z;
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
@@ -144,6 +147,7 @@ __global__ void transpose_add_kernel(const float* __restrict__ in, int rows, int
 __global__ void weight_prep_kernel(const float* __restrict__ w, int cin, int cout,
                                    __nv_bfloat16* __restrict__ o_same,
                                    __nv_bfloat16* __restrict__ o_t) {
+  MCN_PDL_PROLOGUE();
   __shared__ float tile[32][33];
   const int tap = blockIdx.z;
   const int ci0 = blockIdx.y * 32, co0 = blockIdx.x * 32;
@@ -177,7 +181,7 @@ extern "C" int mcn_opt_step(int kind, const mcn_opt_tensor* table, int ntensors,
   MCN_REQUIRE(kind >= MCN_OPT_NESTEROV && kind <= MCN_OPT_ADAM, "opt_step: unknown optimiser %d", kind);
   MCN_REQUIRE(ntensors <= 65535, "opt_step: too many tensors");
   dim3 grid((unsigned)((max_n + kBlock * kItems - 1) / (kBlock * kItems)), (unsigned)ntensors);
-  opt_step_kernel<<<grid, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(kind, table, hp, l2_xs,
+  ::mcn::launch(opt_step_kernel, grid, kBlock, 0, static_cast<cudaStream_t>(stream), kind, table, hp, l2_xs,
                                                                          grad_sqnorm_xs);
   return after_launch("opt_step");
 }
@@ -187,7 +191,7 @@ extern "C" int mcn_grad_sqnorm(const mcn_opt_tensor* table, int ntensors, long l
   MCN_REQUIRE(table && hp && out_xs && ntensors > 0 && max_n > 0, "grad_sqnorm: bad argument");
   MCN_REQUIRE(ntensors <= 65535, "grad_sqnorm: too many tensors");
   dim3 grid((unsigned)((max_n + kBlock * kItems - 1) / (kBlock * kItems)), (unsigned)ntensors);
-  grad_sqnorm_kernel<<<grid, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(table, hp, out_xs);
+  ::mcn::launch(grad_sqnorm_kernel, grid, kBlock, 0, static_cast<cudaStream_t>(stream), table, hp, out_xs);
   return after_launch("grad_sqnorm");
 }
 
@@ -195,7 +199,7 @@ extern "C" int mcn_weight_prep(const float* w_hwio_f32, int taps, int cin, int c
                                void* w_hwio_bf16, void* w_ohwi_bf16, void* stream) {
   MCN_REQUIRE(w_hwio_f32 && taps > 0 && cin > 0 && cout > 0, "weight_prep: bad argument");
   dim3 grid((cout + 31) / 32, (cin + 31) / 32, taps), block(32, 8);
-  weight_prep_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+  ::mcn::launch(weight_prep_kernel, grid, block, 0, static_cast<cudaStream_t>(stream), 
       w_hwio_f32, cin, cout, static_cast<__nv_bfloat16*>(w_hwio_bf16),
       static_cast<__nv_bfloat16*>(w_ohwi_bf16));
   return after_launch("weight_prep");
@@ -205,6 +209,6 @@ extern "C" int mcn_transpose_add_f32(const float* in, int taps, int rows, int co
                                      void* stream) {
   MCN_REQUIRE(in && out && taps > 0 && rows > 0 && cols > 0, "transpose_add: bad argument");
   dim3 grid((cols + 31) / 32, (rows + 31) / 32, taps), block(32, 8);
-  transpose_add_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(in, rows, cols, out);
+  ::mcn::launch(transpose_add_kernel, grid, block, 0, static_cast<cudaStream_t>(stream), in, rows, cols, out);
   return after_launch("transpose_add");
 }

@@ -17,6 +17,7 @@ template <typename T, int V>
 __global__ void maxpool_fwd_kernel(const T* __restrict__ x, int N, int H, int W, int C, int kh,
                                    int kw, int sh, int sw, int pad_t, int pad_l, int Ho, int Wo,
                                    T* __restrict__ y, int32_t* __restrict__ argmax) {
+  MCN_PDL_PROLOGUE();
   const int cv = C / V;
   const long long total = (long long)N * Ho * Wo * cv;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -82,6 +83,7 @@ template <typename T>
 __global__ void maxpool_bwd_kernel(const T* __restrict__ dy, const int32_t* __restrict__ argmax,
                                    int N, int H, int W, int C, int kh, int kw, int sh, int sw,
                                    int pad_t, int pad_l, int Ho, int Wo, T* __restrict__ dx) {
+  MCN_PDL_PROLOGUE();
   const long long total = (long long)N * H * W * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -114,6 +116,7 @@ template <typename T, int V>
 __global__ void maxpool_bwd_vec_kernel(const T* __restrict__ dy, const int32_t* __restrict__ argmax,
                                        int N, int H, int W, int C, int kh, int kw, int sh, int sw,
                                        int pad_t, int pad_l, int Ho, int Wo, T* __restrict__ dx) {
+  MCN_PDL_PROLOGUE();
   const int cv = C / V;
   // 32-bit index arithmetic (the host falls back to the scalar kernel beyond 2^31 vectors): the
   // 64-bit divisions were a third of this kernel's instructions
@@ -170,6 +173,7 @@ template <typename T, int V, int K, int S>
 __global__ void __launch_bounds__(256)
 maxpool_fwd_tap_kernel(const T* __restrict__ x, int N, int H, int W, int C, int kh_, int kw_, int sh_, int sw_,
                        int pad_t, int pad_l, int Ho, int Wo, T* __restrict__ y, uint8_t* __restrict__ tap) {
+  MCN_PDL_PROLOGUE();
   const int kh = K ? K : kh_, kw = K ? K : kw_, sh = S ? S : sh_, sw = S ? S : sw_;
   const int cv = C / V;
   const uint32_t total = (uint32_t)N * Ho * Wo * cv;
@@ -255,6 +259,7 @@ __global__ void __launch_bounds__(256)
 maxpool_bwd_tap_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ tap, int N, int H, int W, int C,
                        int kh_, int kw_, int sh_, int sw_, int pad_t, int pad_l, int Ho, int Wo,
                        T* __restrict__ dx) {
+  MCN_PDL_PROLOGUE();
   const int kh = K ? K : kh_, kw = K ? K : kw_, sh = S ? S : sh_, sw = S ? S : sw_;
   constexpr int MAXW = K ? (K + S - 1) / S : 1;      // windows covering a pixel along one axis
   const int cv = C / V;
@@ -328,6 +333,7 @@ maxpool_bwd_tap_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ tap
 __global__ void maxpool_tap_to_argmax_kernel(const uint8_t* __restrict__ tap, long long total, int W, int C,
                                              int kw, int sh, int sw, int pad_t, int pad_l, int Ho, int Wo,
                                              int32_t* __restrict__ argmax) {
+  MCN_PDL_PROLOGUE();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
@@ -345,6 +351,7 @@ template <typename T>
 __global__ void avgpool_fwd_kernel(const T* __restrict__ x, int N, int H, int W, int C, int kh,
                                    int kw, int sh, int sw, int pad_t, int pad_l, int Ho, int Wo,
                                    T* __restrict__ y) {
+  MCN_PDL_PROLOGUE();
   const long long total = (long long)N * Ho * Wo * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -373,6 +380,7 @@ template <typename T>
 __global__ void avgpool_bwd_kernel(const T* __restrict__ dy, int N, int H, int W, int C, int kh,
                                    int kw, int sh, int sw, int pad_t, int pad_l, int Ho, int Wo,
                                    T* __restrict__ dx) {
+  MCN_PDL_PROLOGUE();
   const long long total = (long long)N * H * W * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -404,6 +412,7 @@ __global__ void avgpool_bwd_kernel(const T* __restrict__ dy, int N, int H, int W
 // Global average pool: one block per (image, 32-channel-vector slab); threads split HW.
 template <typename T, typename TO>
 __global__ void gap_fwd_kernel(const T* __restrict__ x, int HW, int C, TO* __restrict__ y) {
+  MCN_PDL_PROLOGUE();
   // blockDim = (32, 8): x -> channel, y -> spatial lane
   __shared__ float sh[8][33];
   int n = blockIdx.y;
@@ -423,6 +432,7 @@ __global__ void gap_fwd_kernel(const T* __restrict__ x, int HW, int C, TO* __res
 template <typename T, typename TI>
 __global__ void gap_bwd_kernel(const TI* __restrict__ dy, int HW, int C, long long total,
                                T* __restrict__ dx) {
+  MCN_PDL_PROLOGUE();
   const float inv = 1.f / (float)HW;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -450,12 +460,12 @@ extern "C" int mcn_maxpool_fwd(int dtype, const void* x, int N, int H, int W, in
     constexpr int V = Vec16<T>::N;
     if (C % V == 0) {
       long long total = (long long)N * Ho * Wo * (C / V);
-      maxpool_fwd_kernel<T, V><<<grid_for(total, 256), 256, 0, st>>>(
+      ::mcn::launch(maxpool_fwd_kernel<T, V>, grid_for(total, 256), 256, 0, st, 
           static_cast<const T*>(x), N, H, W, C, kh, kw, sh, sw, pad_t, pad_l, Ho, Wo,
           static_cast<T*>(y), argmax);
     } else {
       long long total = (long long)N * Ho * Wo * C;
-      maxpool_fwd_kernel<T, 1><<<grid_for(total, 256), 256, 0, st>>>(
+      ::mcn::launch(maxpool_fwd_kernel<T, 1>, grid_for(total, 256), 256, 0, st, 
           static_cast<const T*>(x), N, H, W, C, kh, kw, sh, sw, pad_t, pad_l, Ho, Wo,
           static_cast<T*>(y), argmax);
     }
@@ -473,12 +483,12 @@ extern "C" int mcn_maxpool_bwd(int dtype, const void* dy, const int32_t* argmax,
     if (C % V == 0 && (long long)N * H * W * (C / V) < (1LL << 31) - (1 << 24) &&
         (long long)N * Ho * Wo * C < (1LL << 62)) {
       long long total = (long long)N * H * W * (C / V);
-      maxpool_bwd_vec_kernel<T, V><<<grid_for(total, 256), 256, 0, st>>>(
+      ::mcn::launch(maxpool_bwd_vec_kernel<T, V>, grid_for(total, 256), 256, 0, st, 
           static_cast<const T*>(dy), argmax, N, H, W, C, kh, kw, sh, sw, pad_t, pad_l, Ho, Wo,
           static_cast<T*>(dx));
     } else {
       long long total = (long long)N * H * W * C;
-      maxpool_bwd_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(
+      ::mcn::launch(maxpool_bwd_kernel<T>, grid_for(total, 256), 256, 0, st, 
           static_cast<const T*>(dy), argmax, N, H, W, C, kh, kw, sh, sw, pad_t, pad_l, Ho, Wo,
           static_cast<T*>(dx));
     }
@@ -494,10 +504,10 @@ static void launch_maxpool_tap(bool fwd, const void* in, const uint8_t* tap_in, 
   const int grid = (int)std::max<long long>(1, (total + 255) / 256);
 #define MCN_POOL_CASE(KK, SS)                                                                        \
   if (fwd)                                                                                           \
-    maxpool_fwd_tap_kernel<T, V, KK, SS><<<grid, 256, 0, st>>>(static_cast<const T*>(in), N, H, W, C, kh, kw, sh, \
+    ::mcn::launch(maxpool_fwd_tap_kernel<T, V, KK, SS>, grid, 256, 0, st, static_cast<const T*>(in), N, H, W, C, kh, kw, sh, \
                                                              sw, pad_t, pad_l, Ho, Wo, static_cast<T*>(out), tap_out); \
   else                                                                                               \
-    maxpool_bwd_tap_kernel<T, V, KK, SS><<<grid, 256, 0, st>>>(static_cast<const T*>(in), tap_in, N, H, W, C, kh, \
+    ::mcn::launch(maxpool_bwd_tap_kernel<T, V, KK, SS>, grid, 256, 0, st, static_cast<const T*>(in), tap_in, N, H, W, C, kh, \
                                                              kw, sh, sw, pad_t, pad_l, Ho, Wo, static_cast<T*>(out))
   const bool sq = kh == kw && sh == sw;
   if (sq && kh == 3 && sh == 2) { MCN_POOL_CASE(3, 2); }
@@ -542,7 +552,7 @@ extern "C" int mcn_maxpool_tap_to_argmax(const uint8_t* tap, int N, int H, int W
   (void)H;
   (void)kh;
   const long long total = (long long)N * Ho * Wo * C;
-  maxpool_tap_to_argmax_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  ::mcn::launch(maxpool_tap_to_argmax_kernel, grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       tap, total, W, C, kw, sh, sw, pad_t, pad_l, Ho, Wo, argmax);
   return after_launch("maxpool_tap_to_argmax");
 }
@@ -554,7 +564,7 @@ extern "C" int mcn_avgpool_fwd(int dtype, const void* x, int N, int H, int W, in
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MCN_DISPATCH_DTYPE(dtype, T, {
     long long total = (long long)N * Ho * Wo * C;
-    avgpool_fwd_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(
+    ::mcn::launch(avgpool_fwd_kernel<T>, grid_for(total, 256), 256, 0, st, 
         static_cast<const T*>(x), N, H, W, C, kh, kw, sh, sw, pad_t, pad_l, Ho, Wo,
         static_cast<T*>(y));
   });
@@ -567,7 +577,7 @@ extern "C" int mcn_avgpool_bwd(int dtype, const void* dy, int N, int H, int W, i
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MCN_DISPATCH_DTYPE(dtype, T, {
     long long total = (long long)N * H * W * C;
-    avgpool_bwd_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(
+    ::mcn::launch(avgpool_bwd_kernel<T>, grid_for(total, 256), 256, 0, st, 
         static_cast<const T*>(dy), N, H, W, C, kh, kw, sh, sw, pad_t, pad_l, Ho, Wo,
         static_cast<T*>(dx));
   });
@@ -581,10 +591,10 @@ extern "C" int mcn_gap_fwd(int dtype, const void* x, int N, int HW, int C, void*
   dim3 grid((C + 31) / 32, N), block(32, 8);
   MCN_DISPATCH_DTYPE(dtype, T, {
     if (y_dtype == MCN_F32)
-      gap_fwd_kernel<T, float><<<grid, block, 0, st>>>(static_cast<const T*>(x), HW, C,
+      ::mcn::launch(gap_fwd_kernel<T, float>, grid, block, 0, st, static_cast<const T*>(x), HW, C,
                                                        static_cast<float*>(y));
     else
-      gap_fwd_kernel<T, __nv_bfloat16><<<grid, block, 0, st>>>(
+      ::mcn::launch(gap_fwd_kernel<T, __nv_bfloat16>, grid, block, 0, st, 
           static_cast<const T*>(x), HW, C, static_cast<__nv_bfloat16*>(y));
   });
   return after_launch("gap_fwd");
@@ -596,10 +606,10 @@ extern "C" int mcn_gap_bwd(int dtype, const void* dy, int dy_dtype, int N, int H
   long long total = (long long)N * HW * C;
   MCN_DISPATCH_DTYPE(dtype, T, {
     if (dy_dtype == MCN_F32)
-      gap_bwd_kernel<T, float><<<grid_for(total, 256), 256, 0, st>>>(
+      ::mcn::launch(gap_bwd_kernel<T, float>, grid_for(total, 256), 256, 0, st, 
           static_cast<const float*>(dy), HW, C, total, static_cast<T*>(dx));
     else
-      gap_bwd_kernel<T, __nv_bfloat16><<<grid_for(total, 256), 256, 0, st>>>(
+      ::mcn::launch(gap_bwd_kernel<T, __nv_bfloat16>, grid_for(total, 256), 256, 0, st, 
           static_cast<const __nv_bfloat16*>(dy), HW, C, total, static_cast<T*>(dx));
   });
   return after_launch("gap_bwd");

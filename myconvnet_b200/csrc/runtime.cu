@@ -10,6 +10,15 @@ namespace mcn {
 static thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MCN_PDL");
+    v = (e && e[0] == '1') ? 1 : 0;   // off by default: no gain measured inside a CUDA graph (23.3 vs 23.1 ms)
+  }
+  return v != 0;
+}
+
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -49,6 +58,7 @@ template <int Y>
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ ws, long long stride, int splits, long long n4,
                      float* __restrict__ dw) {
+  MCN_PDL_PROLOGUE();
   constexpr int X = 256 / Y;
   __shared__ float4 part[Y][X];
   const int tx = threadIdx.x % X, ty = threadIdx.x / X;
@@ -105,6 +115,7 @@ splitk_reduce_kernel(const float* __restrict__ ws, long long stride, int splits,
 
 __global__ void splitk_reduce_scalar_kernel(const float* __restrict__ ws, long long stride, int splits,
                                             long long i0, long long n, float* __restrict__ dw) {
+  MCN_PDL_PROLOGUE();
   for (long long i = i0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     float acc = 0.f;
@@ -115,6 +126,7 @@ __global__ void splitk_reduce_scalar_kernel(const float* __restrict__ ws, long l
 
 __global__ void xsum_decode_kernel(const long long* __restrict__ limbs, int n, float* out_f32,
                                    double* out_f64, int accumulate) {
+  MCN_PDL_PROLOGUE();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double v = xs::read(limbs, n, i);
@@ -134,17 +146,17 @@ int launch_splitk_reduce(const float* ws, long long stride, int splits, long lon
     const int y = splits <= 4 ? 1 : (splits <= 8 ? 2 : (splits <= 32 ? 4 : 8));
     const int x = 256 / y;
     const int grid = (int)std::max<long long>(1, std::min<long long>((n4 + x - 1) / x, 16LL * num_sms()));
-    if (y == 1) splitk_reduce_kernel<1><<<grid, 256, 0, st>>>(ws, stride, splits, n4, dw);
-    else if (y == 2) splitk_reduce_kernel<2><<<grid, 256, 0, st>>>(ws, stride, splits, n4, dw);
-    else if (y == 4) splitk_reduce_kernel<4><<<grid, 256, 0, st>>>(ws, stride, splits, n4, dw);
-    else splitk_reduce_kernel<8><<<grid, 256, 0, st>>>(ws, stride, splits, n4, dw);
+    if (y == 1) ::mcn::launch(splitk_reduce_kernel<1>, grid, 256, 0, st, ws, stride, splits, n4, dw);
+    else if (y == 2) ::mcn::launch(splitk_reduce_kernel<2>, grid, 256, 0, st, ws, stride, splits, n4, dw);
+    else if (y == 4) ::mcn::launch(splitk_reduce_kernel<4>, grid, 256, 0, st, ws, stride, splits, n4, dw);
+    else ::mcn::launch(splitk_reduce_kernel<8>, grid, 256, 0, st, ws, stride, splits, n4, dw);
     const int rc = after_launch("splitk_reduce");
     if (rc) return rc;
   }
   if (n4 * 4 < n) {
     const long long rest = n - n4 * 4;
     const int grid = (int)std::max<long long>(1, std::min<long long>((rest + 255) / 256, 8LL * num_sms()));
-    splitk_reduce_scalar_kernel<<<grid, 256, 0, st>>>(ws, stride, splits, n4 * 4, n, dw);
+    ::mcn::launch(splitk_reduce_scalar_kernel, grid, 256, 0, st, ws, stride, splits, n4 * 4, n, dw);
     return after_launch("splitk_reduce");
   }
   return MCN_OK;
@@ -177,7 +189,7 @@ extern "C" long long mcn_workspace_min_bytes(void) { return mcn::kWsMinBytes; }
 extern "C" int mcn_xsum_decode(const long long* limbs, int n, float* out_f32, double* out_f64,
                                int accumulate, void* stream) {
   MCN_REQUIRE(limbs && n > 0 && (out_f32 || out_f64), "xsum_decode: bad argument");
-  mcn::xsum_decode_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  ::mcn::launch(mcn::xsum_decode_kernel, (n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream), 
       limbs, n, out_f32, out_f64, accumulate);
   return mcn::after_launch("xsum_decode");
 }

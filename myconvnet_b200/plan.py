@@ -556,6 +556,9 @@ class Plan(object):
         ResNet-50 at batch 256 (profiles/r01_fused_stats_ab.txt)."""
         kh, kw, ci, co = conv.vars["w"].shape
         k = kh * kw * ci
+        mode = os.environ.get("MCN_FUSE_STATS_RULE", "k")     # "all": every eligible conv (A/B timing)
+        if mode == "all":
+            return True
         return k >= 512 or (k >= 128 and co <= 64)
 
     def _bn_sums_buf(self, bn_node):
