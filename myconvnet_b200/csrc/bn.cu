@@ -644,6 +644,279 @@ bn_bwd_apply_runs_kernel(const T* __restrict__ dy, const T* __restrict__ x, cons
   }
 }
 
+// ---------------------------------------------------------------- asynchronous prefetch rings
+// The register-staged kernels above keep 50-100 KB of loads in flight per SM, which is what a
+// 400 MB tensor needs and far too little for the 25-150 MB tensors of the later blocks: those ran
+// at 1.2-3.7 TB/s because the whole tensor is only a few "rounds" of the in-flight window and every
+// round costs a loaded memory latency (~2.5 us).  The *_pipe kernels keep the same thread ->
+// channel mapping but fetch with cp.async.cg (16 bytes, global -> shared, no registers held): each
+// thread owns a private ring of D slots per input stream, issues D items ahead and consumes them
+// in order with cp.async.wait_group.  S*D = 12 slots x 256 threads x 16 B = 48 KB per block, three
+// blocks per SM: 144 KB in flight per SM whatever the arithmetic needs in registers.  A slot is
+// only ever read by the thread that filled it, so no block synchronisation is involved.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+template <typename T>
+__device__ __forceinline__ Vec16<T> lds_vec(uint32_t addr) {
+  Vec16<T> v;
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "r"(addr)
+               : "memory");
+  v.raw = *reinterpret_cast<decltype(v.raw)*>(&r);
+  return v;
+}
+constexpr int kPipeSlots = 12;                       // S * D
+constexpr int kPipeBytes = kPipeSlots * 256 * 16;    // per 256-thread block
+
+inline bool bn_use_pipe() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MCN_BN_PIPE");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
+// The slab reductions measured SLOWER with the ring (bn_bwd_reduce 3.67 -> 3.82 ms, bn_stats 0.67 ->
+// 0.90 ms per step: their tail — block reduce, exact adds, ticket — not the fetch, is the fixed
+// cost), so only the element-wise passes use it by default; MCN_BN_REDUCE_PIPE=1 selects it there too.
+inline bool bn_reduce_pipe() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MCN_BN_REDUCE_PIPE");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v != 0 && bn_use_pipe();
+}
+
+// forward apply (+ residual): S = 1 or 2 streams
+template <typename T, int kMode, bool kRes>
+__global__ void __launch_bounds__(256, 3)
+bn_apply_pipe_kernel(const T* __restrict__ x, long long nvec, int cv, const float* __restrict__ mean,
+                     const float* __restrict__ invstd_or_var, float eps,
+                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                     const T* __restrict__ residual, int act, float alpha, T* __restrict__ y,
+                     BnSumsArgs fs) {
+  MCN_PDL_PROLOGUE();
+  constexpr int V = Vec16<T>::N;
+  constexpr int S = kRes ? 2 : 1, D = kPipeSlots / S;
+  extern __shared__ uint4 pipe_smem[];
+  const uint32_t base = static_cast<uint32_t>(__cvta_generic_to_shared(pipe_smem)) + threadIdx.x * 16u;
+  constexpr uint32_t kSlot = 256u * 16u;
+  const long long stride = (long long)gridDim.x * 256;
+  long long v = (long long)blockIdx.x * 256 + threadIdx.x;
+  // the loads do not depend on the coefficients: start them first
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const long long vv = v + d * stride;
+    if (vv < nvec) {
+      cp_async16(base + d * kSlot, x + vv * V);
+      if (kRes) cp_async16(base + (D + d) * kSlot, residual + vv * V);
+    }
+    cp_async_commit();
+  }
+  const int c0 = (threadIdx.x % cv) * V;
+  float sc[V], sf[V];
+  bn_apply_coefs<V, kMode>(c0, cv * V, cv, mean, invstd_or_var, eps, gamma, beta, fs, sc, sf);
+  int d = 0;
+  for (; v < nvec; v += stride) {
+    cp_async_wait<D - 1>();
+    const Vec16<T> a = lds_vec<T>(base + d * kSlot);
+    Vec16<T> r;
+    if (kRes) r = lds_vec<T>(base + (D + d) * kSlot);
+    Vec16<T> o;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float f = fmaf(a.get(i), sc[i], sf[i]);
+      if (kRes) f += r.get(i);
+      o.set(i, act_fwd(act, f, alpha));
+    }
+    st_vec(y + v * V, o);
+    const long long vn = v + D * stride;
+    if (vn < nvec) {
+      cp_async16(base + d * kSlot, x + vn * V);
+      if (kRes) cp_async16(base + (D + d) * kSlot, residual + vn * V);
+    }
+    cp_async_commit();
+    d = (d + 1 == D) ? 0 : d + 1;
+  }
+  cp_async_wait<0>();
+}
+
+// backward apply: S = 2 (dy, x) or 3 (+ y)
+template <typename T, bool kHaveY, bool kRes>
+__global__ void __launch_bounds__(256, 3)
+bn_bwd_apply_pipe_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
+                         long long nvec, int cv, const float* __restrict__ mean,
+                         const float* __restrict__ invstd, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, int act, float alpha,
+                         const float* __restrict__ sum_dz, const float* __restrict__ sum_dz_xhat,
+                         float inv_count, T* __restrict__ dx, T* __restrict__ d_residual) {
+  MCN_PDL_PROLOGUE();
+  constexpr int V = Vec16<T>::N;
+  constexpr int S = kHaveY ? 3 : 2, D = kPipeSlots / S;
+  extern __shared__ uint4 pipe_smem[];
+  const uint32_t base = static_cast<uint32_t>(__cvta_generic_to_shared(pipe_smem)) + threadIdx.x * 16u;
+  constexpr uint32_t kSlot = 256u * 16u;
+  const long long stride = (long long)gridDim.x * 256;
+  long long v = (long long)blockIdx.x * 256 + threadIdx.x;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const long long vv = v + d * stride;
+    if (vv < nvec) {
+      cp_async16(base + d * kSlot, dy + vv * V);
+      cp_async16(base + (D + d) * kSlot, x + vv * V);
+      if (kHaveY) cp_async16(base + (2 * D + d) * kSlot, y + vv * V);
+    }
+    cp_async_commit();
+  }
+  const int c0 = (threadIdx.x % cv) * V;
+  // dx = sc*(dz - k1 - xhat*k2) with xhat = (x-mu)*is  ==  A*dz + B*x + Cc
+  float A[V], B[V], Cc[V], sf[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const float mu = mean[c0 + i], is = invstd[c0 + i];
+    const float k1 = sum_dz[c0 + i] * inv_count, k2 = sum_dz_xhat[c0 + i] * inv_count;
+    A[i] = (gamma ? gamma[c0 + i] : 1.f) * is;
+    sf[i] = (beta ? beta[c0 + i] : 0.f) - mu * A[i];
+    B[i] = -A[i] * k2 * is;
+    Cc[i] = A[i] * (k2 * mu * is - k1);
+  }
+  int d = 0;
+  for (; v < nvec; v += stride) {
+    cp_async_wait<D - 1>();
+    const Vec16<T> g = lds_vec<T>(base + d * kSlot);
+    const Vec16<T> a = lds_vec<T>(base + (D + d) * kSlot);
+    Vec16<T> o;
+    if (kHaveY) o = lds_vec<T>(base + (2 * D + d) * kSlot);
+    Vec16<T> ox, orr;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float xv = a.get(i);
+      const float dz = dz_of<T>(g.get(i), xv, kHaveY ? o.get(i) : 0.f, kHaveY, A[i], sf[i], act, alpha);
+      ox.set(i, fmaf(A[i], dz, fmaf(B[i], xv, Cc[i])));
+      if (kRes) orr.set(i, dz);
+    }
+    st_vec(dx + v * V, ox);
+    if (kRes) st_vec(d_residual + v * V, orr);
+    const long long vn = v + D * stride;
+    if (vn < nvec) {
+      cp_async16(base + d * kSlot, dy + vn * V);
+      cp_async16(base + (D + d) * kSlot, x + vn * V);
+      if (kHaveY) cp_async16(base + (2 * D + d) * kSlot, y + vn * V);
+    }
+    cp_async_commit();
+    d = (d + 1 == D) ? 0 : d + 1;
+  }
+  cp_async_wait<0>();
+}
+
+// row reductions on the slab grid of bn_stats_kernel / bn_bwd_reduce_kernel.
+//   kStats: S = 1, sums of x and x^2 (fp64 outputs); otherwise S = 2 or 3, sums of dz and dz*xhat
+template <typename T, bool kStats, bool kHaveY, typename TAcc>
+__global__ void __launch_bounds__(256, 3)
+bn_reduce_pipe_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
+                      long long rows, int C, int slab_v, int rowlanes,
+                      const float* __restrict__ mean, const float* __restrict__ invstd,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, int act,
+                      float alpha, TAcc* __restrict__ out1, TAcc* __restrict__ out2, XsScratch xsc) {
+  MCN_PDL_PROLOGUE();
+  constexpr int V = Vec16<T>::N;
+  constexpr int S = kStats ? 1 : (kHaveY ? 3 : 2), D = kPipeSlots / S;
+  extern __shared__ uint4 pipe_smem[];
+  float* sh = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(pipe_smem) + kPipeBytes);
+  const uint32_t base = static_cast<uint32_t>(__cvta_generic_to_shared(pipe_smem)) + threadIdx.x * 16u;
+  constexpr uint32_t kSlot = 256u * 16u;
+  const int sv = threadIdx.x % slab_v, rl = threadIdx.x / slab_v;
+  const int vec = blockIdx.x * slab_v + sv;
+  const bool active = rl < rowlanes && vec * V < C;
+  const long long r0 = rows * blockIdx.y / gridDim.y, r1 = rows * (blockIdx.y + 1) / gridDim.y;
+  const int c0 = vec * V;
+  float s1[V], s2[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) s1[i] = s2[i] = 0.f;
+  if (active) {
+    long long r = r0 + rl;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const long long rr = r + (long long)d * rowlanes;
+      if (rr < r1) {
+        const long long off = rr * C + c0;
+        cp_async16(base + d * kSlot, x + off);
+        if (!kStats) cp_async16(base + (D + d) * kSlot, dy + off);
+        if (!kStats && kHaveY) cp_async16(base + (2 * D + d) * kSlot, y + off);
+      }
+      cp_async_commit();
+    }
+    float sc[V], sf[V];
+    if (!kStats) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        sc[i] = (gamma ? gamma[c0 + i] : 1.f) * invstd[c0 + i];
+        sf[i] = (beta ? beta[c0 + i] : 0.f) - mean[c0 + i] * sc[i];
+      }
+    }
+    int d = 0;
+    for (; r < r1; r += rowlanes) {
+      cp_async_wait<D - 1>();
+      const Vec16<T> a = lds_vec<T>(base + d * kSlot);
+      Vec16<T> g, o;
+      if (!kStats) g = lds_vec<T>(base + (D + d) * kSlot);
+      if (!kStats && kHaveY) o = lds_vec<T>(base + (2 * D + d) * kSlot);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float xv = a.get(i);
+        if (kStats) {
+          s1[i] += xv;
+          s2[i] = fmaf(xv, xv, s2[i]);
+        } else {
+          const float dz = dz_of<T>(g.get(i), xv, kHaveY ? o.get(i) : 0.f, kHaveY, sc[i], sf[i], act, alpha);
+          s1[i] += dz;
+          s2[i] = fmaf(dz, xv, s2[i]);          // sum dz*x; turned into sum dz*xhat below
+        }
+      }
+      const long long rn = r + (long long)D * rowlanes;
+      if (rn < r1) {
+        const long long off = rn * C + c0;
+        cp_async16(base + d * kSlot, x + off);
+        if (!kStats) cp_async16(base + (D + d) * kSlot, dy + off);
+        if (!kStats && kHaveY) cp_async16(base + (2 * D + d) * kSlot, y + off);
+      }
+      cp_async_commit();
+      d = (d + 1 == D) ? 0 : d + 1;
+    }
+    cp_async_wait<0>();
+    if (!kStats) {
+      // sum dz*xhat = invstd * (sum dz*x - mean * sum dz)
+#pragma unroll
+      for (int i = 0; i < V; ++i) s2[i] = invstd[c0 + i] * (s2[i] - mean[c0 + i] * s1[i]);
+    }
+  }
+  if (rl < rowlanes) {
+    const int width = slab_v * V;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      sh[(size_t)rl * width + sv * V + i] = s1[i];
+      sh[(size_t)(rowlanes + rl) * width + sv * V + i] = s2[i];
+    }
+  }
+  slab_finish<V, TAcc>(sh, slab_v, rowlanes, blockIdx.x, C, out1, out2, xsc);
+}
+
+// one-time opt-in to > 48 KB of dynamic shared memory for a pipe kernel instantiation
+template <typename K>
+static bool pipe_smem_ok(K kernel, size_t bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess;
+}
+
 // scalar fallbacks for odd channel counts
 template <typename T>
 __global__ void bn_bwd_reduce_scalar_kernel(const T* dy, const T* x, const T* y, long long rows,
@@ -709,8 +982,16 @@ extern "C" int mcn_bn_stats(int dtype, const void* x, long long rows, int C, dou
     SlabLaunch L;
     if (plan_slab<T>(rows, C, &L, 3 * num_sms())) {
       size_t smem = 2 * (size_t)L.rowlanes * L.slab_v * Vec16<T>::N * sizeof(float);
-      ::mcn::launch(bn_stats_kernel<T>, L.grid, 256, smem, st, static_cast<const T*>(x), rows, C, L.slab_v,
-                                                    L.rowlanes, sums, xsc);
+      static bool pipe_ok = pipe_smem_ok(bn_reduce_pipe_kernel<T, true, false, double>, kPipeBytes + 16384);
+      if (bn_reduce_pipe() && pipe_ok && xsc.limbs != nullptr)
+        ::mcn::launch(bn_reduce_pipe_kernel<T, true, false, double>, L.grid, 256, kPipeBytes + smem, st,
+                      static_cast<const T*>(nullptr), static_cast<const T*>(x), static_cast<const T*>(nullptr),
+                      rows, C, L.slab_v, L.rowlanes, static_cast<const float*>(nullptr),
+                      static_cast<const float*>(nullptr), static_cast<const float*>(nullptr),
+                      static_cast<const float*>(nullptr), 0, 0.f, sums, sums + C, xsc);
+      else
+        ::mcn::launch(bn_stats_kernel<T>, L.grid, 256, smem, st, static_cast<const T*>(x), rows, C, L.slab_v,
+                      L.rowlanes, sums, xsc);
     } else {
       MCN_REQUIRE((C + 127) / 128 <= kWsCounters, "bn_stats: too many channels (%d)", C);
       dim3 grid((C + 127) / 128, (unsigned)std::min<long long>(rows, 4LL * num_sms()));
@@ -751,7 +1032,18 @@ static int bn_apply_impl(int dtype, const void* x, long long rows, int C, const 
     const int cvr = (C % V == 0) ? C / V : 0;
     // measured in the training step (profiles/r01_bn_runs_ab.txt): the run-based kernel wins for
     // the single-stream case (170 -> 140 us on 411 MB) and loses once a residual stream is added
-    if (cvr > 0 && cvr <= 256 && 256 % cvr == 0 && bn_use_runs() && residual == nullptr) {
+    if (cvr > 0 && cvr <= 256 && 256 % cvr == 0 && bn_use_pipe()) {
+      const long long nvec = rows * cvr;
+      const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((nvec + 255) / 256, 3LL * num_sms()));
+      if (residual != nullptr)
+        ::mcn::launch(bn_apply_pipe_kernel<T, kMode, true>, grid, 256, kPipeBytes, st, static_cast<const T*>(x), nvec,
+                      cvr, mean, is_or_var, eps, gamma, beta, static_cast<const T*>(residual), act, alpha,
+                      static_cast<T*>(y), fs);
+      else
+        ::mcn::launch(bn_apply_pipe_kernel<T, kMode, false>, grid, 256, kPipeBytes, st, static_cast<const T*>(x), nvec,
+                      cvr, mean, is_or_var, eps, gamma, beta, static_cast<const T*>(nullptr), act, alpha,
+                      static_cast<T*>(y), fs);
+    } else if (cvr > 0 && cvr <= 256 && 256 % cvr == 0 && bn_use_runs() && residual == nullptr) {
       const long long nvec = rows * cvr;
       const bool res = residual != nullptr;
       const int U = res ? 4 : 8;
@@ -833,6 +1125,20 @@ static void launch_bn_bwd_reduce(const SlabLaunch& L, size_t smem, cudaStream_t 
   const T* pdy = static_cast<const T*>(dy);
   const T* px = static_cast<const T*>(x);
   const T* py = static_cast<const T*>(y);
+  if (bn_reduce_pipe() && xsc.limbs != nullptr) {
+    static bool ok_y = pipe_smem_ok(bn_reduce_pipe_kernel<T, false, true, float>, kPipeBytes + 16384);
+    static bool ok_n = pipe_smem_ok(bn_reduce_pipe_kernel<T, false, false, float>, kPipeBytes + 16384);
+    if (y != nullptr && ok_y) {
+      ::mcn::launch(bn_reduce_pipe_kernel<T, false, true, float>, L.grid, 256, kPipeBytes + smem, st, pdy, px, py, rows,
+                    C, L.slab_v, L.rowlanes, mean, invstd, gamma, beta, act, alpha, sum_dz, sum_dz_xhat, xsc);
+      return;
+    }
+    if (y == nullptr && ok_n) {
+      ::mcn::launch(bn_reduce_pipe_kernel<T, false, false, float>, L.grid, 256, kPipeBytes + smem, st, pdy, px, py, rows,
+                    C, L.slab_v, L.rowlanes, mean, invstd, gamma, beta, act, alpha, sum_dz, sum_dz_xhat, xsc);
+      return;
+    }
+  }
   const bool four = (y != nullptr) ? bn_bwd_unroll() == 4 : bn_noy_unroll() == 4;
   if (four && y != nullptr)
     ::mcn::launch(bn_bwd_reduce_kernel<T, 4, true>, L.grid, 256, smem, st, pdy, px, py, rows, C, L.slab_v, L.rowlanes, mean, invstd,
@@ -899,6 +1205,12 @@ static void launch_bwd_apply_runs(unsigned grid, cudaStream_t st, const void* dy
         pdy, px, py, nvec, cv, mean, invstd, gamma, beta, act, alpha, sum_dz, sum_dz_xhat, inv_count, pdx, pdr, rpb);
 }
 
+#define MCN_BWD_APPLY_PIPE(Y_, R_)                                                                         \
+  ::mcn::launch(bn_bwd_apply_pipe_kernel<T, Y_, R_>, grid, 256, kPipeBytes, st, static_cast<const T*>(dy), \
+                static_cast<const T*>(x), static_cast<const T*>(y), nvec, cvr, mean, invstd, gamma, beta,  \
+                act, act_alpha, sum_dz, sum_dz_xhat, inv_count, static_cast<T*>(dx),                       \
+                static_cast<T*>(d_residual))
+
 #define MCN_BWD_APPLY(U_, Y_)                                                                      \
   ::mcn::launch(bn_bwd_apply_kernel<T, U_, Y_>, L.grid, L.block, 0, st,                                        \
       static_cast<const T*>(dy), static_cast<const T*>(x), static_cast<const T*>(y), rows * L.cv,  \
@@ -918,7 +1230,14 @@ extern "C" int mcn_bn_bwd_apply(int dtype, const void* dy, const void* x, const 
     ChanLaunch L;
     constexpr int V = Vec16<T>::N;
     const int cvr = (C % V == 0) ? C / V : 0;
-    if (cvr > 0 && cvr <= 256 && 256 % cvr == 0 && bn_bwd_use_runs()) {
+    if (cvr > 0 && cvr <= 256 && 256 % cvr == 0 && bn_use_pipe()) {
+      const long long nvec = rows * cvr;
+      const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((nvec + 255) / 256, 3LL * num_sms()));
+      if (y != nullptr && d_residual != nullptr) MCN_BWD_APPLY_PIPE(true, true);
+      else if (y != nullptr) MCN_BWD_APPLY_PIPE(true, false);
+      else if (d_residual != nullptr) MCN_BWD_APPLY_PIPE(false, true);
+      else MCN_BWD_APPLY_PIPE(false, false);
+    } else if (cvr > 0 && cvr <= 256 && 256 % cvr == 0 && bn_bwd_use_runs()) {
       const long long nvec = rows * cvr;
       constexpr int U = 4;
       const long long runs = (nvec + 256LL * U - 1) / (256LL * U);
