@@ -353,6 +353,25 @@ int mcn_peer_allreduce(const unsigned long long* peers, long long mail_off, long
                        long long flag_off, unsigned long long* counter, int is_f64, const void* src0,
                        int n0, const void* src1, int n1, void* dst, int rank, int world, void* stream);
 
+/* ---- group normalisation (convnet.py:1928-2013) and weight standardisation (convnet.py:1410-1419) ----
+ * x, y, dy, dx: [N, HW, C] (NHWC with HW = H*W; HW = 1 for [N, C] tensors); G groups of C/G channels.
+ * gn_fwd: save[(n*G+g)*2] = {mean, 1/sqrt(var+eps)} of group g of sample n (population variance),
+ *         y = (x - mean) * invstd * gamma[c] + beta[c]   (gamma / beta may be NULL = 1 / 0).
+ * gn_bwd: dx (may be NULL) = invstd*(dy*gamma - mean_g(dy*gamma) - xhat*mean_g(dy*gamma*xhat));
+ *         dgamma[c] += sum dy*xhat, dbeta[c] += sum dy (either may be NULL).  scratch: fp32
+ *         [2*N*G + 2*N*C].  Every sum has a fixed order: results are bit-reproducible.
+ * ws_fwd: w [rows][cols] fp32 (cols = output channels, the LAST axis of the reference's weight):
+ *         w_std = (w - mean_col) / (std_col + eps), stats = [mean | std] per column (population std).
+ * ws_bwd: grad += d(loss)/dw given g_std = d(loss)/d(w_std) (the autodiff of the three lines above). */
+int mcn_gn_fwd(int dtype, const void* x, int N, long long HW, int C, int G, float eps,
+               const float* gamma, const float* beta, void* y, float* save, void* stream);
+int mcn_gn_bwd(int dtype, const void* dy, const void* x, int N, long long HW, int C, int G,
+               const float* gamma, const float* save, float* scratch, void* dx, float* dgamma,
+               float* dbeta, void* stream);
+int mcn_ws_fwd(const float* w, int rows, int cols, float eps, float* w_std, float* stats, void* stream);
+int mcn_ws_bwd(const float* g_std, const float* w, const float* stats, int rows, int cols, float eps,
+               float* grad, void* stream);
+
 /* ---- generic helpers ---- */
 int mcn_fill_f32(float* p, long long n, float v, void* stream);
 int mcn_scale_f32(float* p, long long n, float s, void* stream);

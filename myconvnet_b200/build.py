@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 TIMING = os.environ.get("MCN_ROLE_TIMING", "0") == "1"
 LIB = os.path.join(HERE, "libmcn_timing.so" if TIMING else "libmcn.so")
 SOURCES = ["runtime.cu", "conv_tc.cu", "conv_direct.cu", "bn.cu", "pool.cu", "eltwise.cu",
-           "loss.cu", "opt.cu", "comm.cu", "dropout.cu", "dwconv.cu"]
+           "loss.cu", "opt.cu", "comm.cu", "dropout.cu", "dwconv.cu", "norm_extra.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 # Approximate division / sqrt and flush-to-zero only where they cannot reach the fp32 parity of the

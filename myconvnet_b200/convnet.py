@@ -342,11 +342,12 @@ class ConvNet(object):
 
     def weight_variable(self, shape, initializer=tf.initializers.he_normal(),
                         weight_standardization=False, paddings=((0, 0), (0, 0)), name='weights'):
-        if weight_standardization:
-            raise NotImplementedError('weight standardisation (ws=True) is not supported yet')
         if any(p != 0 for pp in paddings for p in pp):
             raise NotImplementedError('kernel_paddings are not supported')
         v, _ = self._get_var(name, shape, initializer, 'weight')
+        # weight standardisation (reference convnet.py:1410-1419) happens inside the graph: the layer
+        # that asked for it flags its node (attrs['ws']) and the plan standardises per step
+        self._ws_requested = bool(weight_standardization)
         return v
 
     def bias_variable(self, shape, initializer=tf.initializers.zeros(), name='biases'):
@@ -437,6 +438,7 @@ class ConvNet(object):
             self._counted.add(weights.name)
             attrs = {'k': kernel, 's': stride, 'd': dilation, 'pad': (pt, pl), 'mult': mult,
                      'biased': bool(biased)}
+            attrs['ws'] = bool(ws)
             node = self.graph._add(op, [x], [(n, ho, wo, out_c)], [x.dtype], attrs, sc)
             node.vars['w'] = weights
             if biased:
@@ -472,7 +474,8 @@ class ConvNet(object):
             self._counted.add(weights.name)
             flops = out_hw[0] * out_hw[1] * kernel[0] * kernel[1] * in_channels * out_channels
             params = kernel[0] * kernel[1] * in_channels * out_channels
-            attrs = {'k': kernel, 's': stride, 'd': dilation, 'pad': (pt, pl), 'biased': bool(biased)}
+            attrs = {'k': kernel, 's': stride, 'd': dilation, 'pad': (pt, pl), 'biased': bool(biased),
+                     'ws': bool(ws)}
             node = self.graph._add('conv2d_transpose', [x], [(n, out_hw[0], out_hw[1], out_channels)],
                                    [x.dtype], attrs, sc)
             node.vars['w'] = weights
@@ -499,7 +502,7 @@ class ConvNet(object):
             flops = in_dim * out_dim
             params = in_dim * out_dim
             node = self.graph._add('dense', [x], [(x.shape[0], out_dim)], [x.dtype],
-                                   {'biased': bool(biased)}, sc)
+                                   {'biased': bool(biased), 'ws': bool(ws)}, sc)
             node.vars['w'] = weights
             if biased:
                 node.vars['b'] = self.bias_variable(out_dim, initializer=bias_initializer)
@@ -517,8 +520,13 @@ class ConvNet(object):
         elif norm_type.lower() == 'batch':
             return self.batch_norm(x, scale=scale, shift=shift, zero_scale_init=zero_scale_init,
                                    epsilon=epsilon, scope=scope)
-        elif norm_type.lower() in ('group', 'grouped_batch'):
-            raise NotImplementedError('norm_type {} is not supported yet (SURVEY 8f-3)'.format(norm_type))
+        elif norm_type.lower() == 'group':
+            return self.group_norm(x, num_groups=32 if norm_param is None else norm_param, scale=scale,
+                                   shift=shift, zero_scale_init=zero_scale_init, epsilon=epsilon, scope=scope)
+        elif norm_type.lower() == 'grouped_batch':
+            # "Experimental grouped batch normalization" of the reference (convnet.py:2175): no model
+            # file uses it; out of scope
+            raise NotImplementedError('norm_type grouped_batch (experimental in the reference) is not supported')
         else:
             raise ValueError('Normalization type of {} is not supported. Supported types: {}'
                              .format(norm_type, supported_types))
@@ -559,8 +567,34 @@ class ConvNet(object):
 
     def group_norm(self, x, num_groups=32, scale=True, shift=True, zero_scale_init=False, epsilon=1e-3,
                    scope='gn'):
-        # signature of reference convnet.py:1928; the kernels are a "next" row
-        raise NotImplementedError('group_norm is not supported yet (SURVEY 8f-3)')
+        """Reference convnet.py:1928-2013: per-sample moments over H x W x (C / num_groups), then the
+        per-channel affine; gamma / beta are ordinary trainable norm variables (no moving statistics)."""
+        trainable = self._trainable()
+        c = x.shape[-1]
+        hw = int(np.prod(x.shape[1:-1])) if len(x.shape) > 2 else 1
+        assert c // num_groups * num_groups == c, \
+            'Number of channels must be a multiple of num_groups ({})'.format(num_groups)
+        with tf.variable_scope(scope):
+            sc = tf.current_scope()
+            gamma = beta = None
+            if scale:
+                init = tf.zeros_initializer() if zero_scale_init else tf.ones_initializer()
+                gamma, created = self._get_var('gamma', [c], init, 'norm', trainable=trainable)
+                if created:
+                    self._params += c
+                self._flops += hw * c
+            if shift:
+                beta, created = self._get_var('beta', [c], tf.zeros_initializer(), 'norm', trainable=trainable)
+                if created:
+                    self._params += c
+                self._flops += hw * c
+            node = self.graph._add('gn', [x], [x.shape], [x.dtype],
+                                   {'eps': float(epsilon), 'groups': int(num_groups)}, sc)
+            if gamma is not None:
+                node.vars['gamma'] = gamma
+            if beta is not None:
+                node.vars['beta'] = beta
+        return node.outputs[0]
 
     # ------------------------------------------------------------------ resize
     def upsampling_2d_layer(self, x, scale=2, out_shape=None, align_corners=False,

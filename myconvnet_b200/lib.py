@@ -87,6 +87,10 @@ SIGNATURES = {
     "mcn_transpose_add_f32": "piiip",
     "mcn_peer_allreduce": "plllpipipipii",
     "mcn_xsum_decode": "pippi",
+    "mcn_gn_fwd": "ipiliifpppp",
+    "mcn_gn_bwd": "ippiliipppppp",
+    "mcn_ws_fwd": "piifpp",
+    "mcn_ws_bwd": "pppiifp",
     "mcn_fill_f32": "plf",
     "mcn_scale_f32": "plf",
 }

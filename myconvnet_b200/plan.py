@@ -265,6 +265,8 @@ class Plan(object):
             return "direct"
         if ci % 8 == 0 and co % 8 == 0 and kh * kw <= 52:
             return "tc"
+        if node.attrs.get("ws"):
+            return "direct"      # the stem / im2col routes store the weight permuted and padded
         if self._stem_geometry(node) is not None:
             return "stem"
         if co % 8 == 0 and kh * kw <= 52:
@@ -338,6 +340,69 @@ class Plan(object):
 
     def pbf16t(self, v):
         return Ptr(self.b_bf16_ema if self.phase == "infer" else self.b_bf16, self.bf16t_off[v])
+
+    # ------------------------------------------------------------------ weight standardisation
+    # convnet.py:1410-1419: w' = (w - mean_o) / (std_o + 1e-5) per output channel, inside the graph.
+    # A node whose weight is standardised computes w' (fp32 + the bf16 operand copies) into buffers
+    # of its own at the start of its forward pass, runs on those, collects d(loss)/dw' in a buffer
+    # of its own and folds it back onto the raw weight's gradient with mcn_ws_bwd.
+    WS_EPS = 1e-5
+
+    def _ws_dims(self, node):
+        w = node.vars["w"]
+        cols = w.shape[-1]
+        return w.size // cols, cols
+
+    def _ws_prepare(self, node):
+        if not node.attrs.get("ws"):
+            return
+        w = node.vars["w"]
+        assert tuple(w.storage_shape) == tuple(w.shape), "weight standardisation needs the plain storage layout"
+        rows, cols = self._ws_dims(node)
+        ws = {"f32": self.node_buf(node, "ws_f32", "ws_f32:%s" % node.scope, w.size * 4),
+              "stats": self.node_buf(node, "ws_stats", "ws_stats:%s" % node.scope, 2 * cols * 4)}
+        self.L("f", "mcn_ws_fwd", self.pvar(w), rows, cols, self.WS_EPS, Ptr(ws["f32"]), Ptr(ws["stats"]),
+               tag=node.scope + "/ws")
+        if w.needs_bf16 or w.needs_bf16_t:
+            taps, ci, co = w.gemm_dims
+            if w.needs_bf16:
+                ws["bf16"] = self.node_buf(node, "ws_bf16", "ws_bf16:%s" % node.scope, w.size * 2)
+            if w.needs_bf16_t:
+                ws["bf16t"] = self.node_buf(node, "ws_bf16t", "ws_bf16t:%s" % node.scope, w.size * 2)
+            self.L("f", "mcn_weight_prep", Ptr(ws["f32"]), taps, ci, co,
+                   Ptr(ws["bf16"]) if "bf16" in ws else NULL, Ptr(ws["bf16t"]) if "bf16t" in ws else NULL,
+                   tag=node.scope + "/ws_prep")
+        node.attrs["ws_buf"] = ws
+
+    def _w_f32(self, node):
+        return Ptr(node.attrs["ws_buf"]["f32"]) if node.attrs.get("ws") else self.pvar(node.vars["w"])
+
+    def _w_bf16(self, node):
+        return Ptr(node.attrs["ws_buf"]["bf16"]) if node.attrs.get("ws") else self.pbf16(node.vars["w"])
+
+    def _w_bf16t(self, node):
+        return Ptr(node.attrs["ws_buf"]["bf16t"]) if node.attrs.get("ws") else self.pbf16t(node.vars["w"])
+
+    def _w_grad(self, node):
+        """Where the weight-gradient kernels accumulate: the variable's gradient, or (standardised
+        weight) a zeroed buffer of the node's own that _ws_finish folds back."""
+        if not node.attrs.get("ws"):
+            return self.pgrad(node.vars["w"])
+        w = node.vars["w"]
+        buf = self.node_buf(node, "ws_grad", "ws_grad:%s" % node.scope, w.size * 4)
+        node.attrs["ws_buf"]["grad"] = buf
+        self.L("b", "mcn_fill_f32", Ptr(buf), w.size, 0.0, tag="zero")
+        return Ptr(buf)
+
+    def _ws_finish(self, node):
+        ws = node.attrs.get("ws_buf") if node.attrs.get("ws") else None
+        if not ws or "grad" not in ws:
+            return
+        rows, cols = self._ws_dims(node)
+        w = node.vars["w"]
+        self.L("b", "mcn_ws_bwd", Ptr(ws["grad"]), self.pvar(w), Ptr(ws["stats"]), rows, cols, self.WS_EPS,
+               self.pgrad(w), tag=node.scope + "/ws_bwd")
+        del ws["grad"]
 
     # ------------------------------------------------------------------ fusion
     def _single_consumer(self, t):
@@ -503,6 +568,7 @@ class Plan(object):
     def _f_conv2d(self, node):
         x, y = node.inputs[0], node.outputs[0]
         w = node.vars["w"]
+        self._ws_prepare(node)
         b = node.vars.get("b")
         d = self._conv_geometry(node)
         node.attrs["desc"] = d
@@ -513,10 +579,10 @@ class Plan(object):
         psums = Ptr(self._bn_sums_buf(bn)) if bn is not None else None
         if route == "tc":
             if bn is not None:
-                self.L("f", "mcn_conv2d_fprop_tc_stats", d, self.tbuf[x], self.pbf16t(w), pb, py,
+                self.L("f", "mcn_conv2d_fprop_tc_stats", d, self.tbuf[x], self._w_bf16t(node), pb, py,
                        self.conv_mode, psums, tag=node.scope)
             else:
-                self.L("f", "mcn_conv2d_fprop_tc", d, self.tbuf[x], self.pbf16t(w), pb, py, self.ccode,
+                self.L("f", "mcn_conv2d_fprop_tc", d, self.tbuf[x], self._w_bf16t(node), pb, py, self.ccode,
                        self.conv_mode, 0, tag=node.scope)
         elif route == "stem":
             # 4-channel copy of the image, then the gather convolution (no im2col matrix)
@@ -525,7 +591,7 @@ class Plan(object):
             d4 = self.conv_desc(**dict({f: getattr(d, f) for f in ConvDesc.FIELDS}, Cin=4))
             node.attrs["desc4"] = d4
             self.L("f", "mcn_pad_rgb4", self.tbuf[x], d.N * d.H * d.W, Ptr(x4), tag=node.scope + "/rgb4")
-            self.L("f", "mcn_stem_conv_fprop", d4, Ptr(x4), self.pbf16t(w), pb, py,
+            self.L("f", "mcn_stem_conv_fprop", d4, Ptr(x4), self._w_bf16t(node), pb, py,
                    psums if bn is not None else NULL, tag=node.scope)
         elif route == "im2col":
             kpad = node.attrs["kpad"]
@@ -538,10 +604,10 @@ class Plan(object):
             self.L("f", "mcn_im2col", d, DT_CODE[x.dtype], self.tbuf[x], Ptr(col), kpad,
                    tag=node.scope + "/im2col")
             if bn is not None:
-                self.L("f", "mcn_conv2d_fprop_tc_stats", gd, Ptr(col), self.pbf16t(w), pb, py, 0, psums,
+                self.L("f", "mcn_conv2d_fprop_tc_stats", gd, Ptr(col), self._w_bf16t(node), pb, py, 0, psums,
                        tag=node.scope)
             else:
-                self.L("f", "mcn_conv2d_fprop_tc", gd, Ptr(col), self.pbf16t(w), pb, py, self.ccode, 0, 0,
+                self.L("f", "mcn_conv2d_fprop_tc", gd, Ptr(col), self._w_bf16t(node), pb, py, self.ccode, 0, 0,
                        tag=node.scope)
         else:
             wdt, pw = self._direct_weight(w)
@@ -571,13 +637,14 @@ class Plan(object):
     def _f_dwconv2d(self, node):
         x, y = node.inputs[0], node.outputs[0]
         w = node.vars["w"]
+        self._ws_prepare(node)
         d = self._conv_geometry(node)
         # depthwise: desc.Cout is unused by the kernels; keep the input channel count
         d = self.conv_desc(**dict({f: getattr(d, f) for f in ConvDesc.FIELDS}, Cout=d.Cin))
         node.attrs["desc"] = d
         py = self.alloc_act(y)
         self.L("f", "mcn_dwconv2d_fwd", d, node.attrs["mult"], self.ccode, self.tbuf[x], 0,
-               self.pvar(w), py, tag=node.scope)
+               self._w_f32(node), py, tag=node.scope)
         if "b" in node.vars:
             self.L("f", "mcn_bias_add", self.ccode, py, y.size // y.shape[-1], y.shape[-1],
                    self.pvar(node.vars["b"]), tag=node.scope + "/bias")
@@ -586,6 +653,7 @@ class Plan(object):
         # forward of conv2d_transpose == dgrad of the conv mapping y-shaped -> x-shaped tensors
         x, y = node.inputs[0], node.outputs[0]
         w = node.vars["w"]   # stored [kh,kw,Cin_t,Cout_t] (reference convnet.py:2460)
+        self._ws_prepare(node)
         a = node.attrs
         n, h, wd, ci = x.shape
         _, ho, wo, co = y.shape
@@ -599,7 +667,7 @@ class Plan(object):
         py = self.alloc_act(y)
         if node.attrs["route"] in ("tc", "mixed"):
             # dgrad wants W_conv[tap][Cin_conv=co][Cout_conv=ci] = stored[tap][ci][co]^T = bf16_t copy
-            self.L("f", "mcn_conv2d_dgrad_tc", d, self.tbuf[x], self.pbf16t(w), py, self.ccode,
+            self.L("f", "mcn_conv2d_dgrad_tc", d, self.tbuf[x], self._w_bf16t(node), py, self.ccode,
                    self.conv_mode, 0, tag=node.scope)
         else:
             # exact / odd-channel path on CUDA cores: the underlying conv's HWIO weight
@@ -608,7 +676,7 @@ class Plan(object):
             wT = self.node_buf(node, "wT", "tconv_wT:%s" % node.scope, w.size * 4)
             node.attrs["wT"] = wT
             self.L("f", "mcn_fill_f32", Ptr(wT), w.size, 0.0, tag="zero")
-            self.L("f", "mcn_transpose_add_f32", self.pvar(w), kh * kw, ci_t, co_t, Ptr(wT),
+            self.L("f", "mcn_transpose_add_f32", self._w_f32(node), kh * kw, ci_t, co_t, Ptr(wT),
                    tag=node.scope + "/wT")
             self.L("f", "mcn_conv2d_dgrad_direct", d, self.ccode, self.tbuf[x], 0, Ptr(wT), py,
                    tag=node.scope)
@@ -620,6 +688,7 @@ class Plan(object):
         x = node.inputs[0]
         y = node.attrs["final"]
         w = node.vars["w"]
+        self._ws_prepare(node)
         b = node.vars.get("b")
         n, ci = x.shape
         co = w.shape[1]
@@ -631,10 +700,10 @@ class Plan(object):
             self.tbuf[node.outputs[0]] = py
         pb = self.pvar(b) if b is not None else NULL
         if node.attrs["route"] == "tc":
-            self.L("f", "mcn_conv2d_fprop_tc", d, self.tbuf[x], self.pbf16t(w), pb, py,
+            self.L("f", "mcn_conv2d_fprop_tc", d, self.tbuf[x], self._w_bf16t(node), pb, py,
                    DT_CODE[y.dtype], 0, 0, tag=node.scope)
         else:
-            self.L("f", "mcn_conv2d_fprop_direct", d, self.ccode, self.tbuf[x], 0, self.pvar(w), pb,
+            self.L("f", "mcn_conv2d_fprop_direct", d, self.ccode, self.tbuf[x], 0, self._w_f32(node), pb,
                    py, tag=node.scope)
 
     def _f_cast(self, node):
@@ -1039,22 +1108,23 @@ class Plan(object):
                 gyb, h = self.talloc(n * co * 2)
                 self.L("b", "mcn_cast", DT_CODE[y.dtype], gy, 1, gyb, n * co, tag="dlogits_bf16")
             if self._var_trains(w):
-                self.L("b", "mcn_conv2d_wgrad_tc", d, self.tbuf[x], gyb, self.pgrad(w), 0,
+                self.L("b", "mcn_conv2d_wgrad_tc", d, self.tbuf[x], gyb, self._w_grad(node), 0,
                        tag=node.scope + "/wgrad")
             self.contribute(x, x.size * 2,
-                            lambda p: self.L("b", "mcn_conv2d_dgrad_tc", d, gyb, self.pbf16(w), p, 1, 0, 0,
+                            lambda p: self.L("b", "mcn_conv2d_dgrad_tc", d, gyb, self._w_bf16(node), p, 1, 0, 0,
                                              tag=node.scope + "/dgrad"),
-                            emit_acc=lambda p: self.L("b", "mcn_conv2d_dgrad_tc", d, gyb, self.pbf16(w), p,
+                            emit_acc=lambda p: self.L("b", "mcn_conv2d_dgrad_tc", d, gyb, self._w_bf16(node), p,
                                                       1, 0, 1, tag=node.scope + "/dgrad+"))
             if h is not None:
                 self.tfree(h)
         else:
             if self._var_trains(w):
-                self.L("b", "mcn_conv2d_wgrad_direct", d, self.ccode, self.tbuf[x], gy, self.pgrad(w),
+                self.L("b", "mcn_conv2d_wgrad_direct", d, self.ccode, self.tbuf[x], gy, self._w_grad(node),
                        tag=node.scope + "/wgrad")
             self.contribute(x, x.size * self.csz,
                             lambda p: self.L("b", "mcn_conv2d_dgrad_direct", d, self.ccode, gy, 0,
-                                             self.pvar(w), p, tag=node.scope + "/dgrad"))
+                                             self._w_f32(node), p, tag=node.scope + "/dgrad"))
+        self._ws_finish(node)
 
     def _b_conv2d(self, node, gy):
         x, y = node.inputs[0], node.outputs[0]
@@ -1066,35 +1136,36 @@ class Plan(object):
                    self.pgrad(node.vars["b"]), tag=node.scope + "/dbias")
         if route == "tc":
             if self._var_trains(w):
-                self.L("b", "mcn_conv2d_wgrad_tc", d, self.tbuf[x], gy, self.pgrad(w), self.conv_mode,
+                self.L("b", "mcn_conv2d_wgrad_tc", d, self.tbuf[x], gy, self._w_grad(node), self.conv_mode,
                        tag=node.scope + "/wgrad")
             self.contribute(x, x.size * 2,
-                            lambda p: self.L("b", "mcn_conv2d_dgrad_tc", d, gy, self.pbf16(w), p, 1,
+                            lambda p: self.L("b", "mcn_conv2d_dgrad_tc", d, gy, self._w_bf16(node), p, 1,
                                              self.conv_mode, 0, tag=node.scope + "/dgrad"),
-                            emit_acc=lambda p: self.L("b", "mcn_conv2d_dgrad_tc", d, gy, self.pbf16(w), p, 1,
+                            emit_acc=lambda p: self.L("b", "mcn_conv2d_dgrad_tc", d, gy, self._w_bf16(node), p, 1,
                                                       self.conv_mode, 1, tag=node.scope + "/dgrad+"))
         elif route == "stem":
             if self._var_trains(w):
                 self.L("b", "mcn_stem_conv_wgrad", node.attrs["desc4"], Ptr(node.attrs["x4"]), gy,
-                       self.pgrad(w), tag=node.scope + "/wgrad")
+                       self._w_grad(node), tag=node.scope + "/wgrad")
             assert not self._needs_input_grad(node), "stem route is only chosen for network inputs"
         elif route == "im2col":
             if self._var_trains(w):
                 self.L("b", "mcn_conv2d_wgrad_tc", node.attrs["gemm_desc"], Ptr(node.attrs["col"]), gy,
-                       self.pgrad(w), 0, tag=node.scope + "/wgrad")
+                       self._w_grad(node), 0, tag=node.scope + "/wgrad")
             # the padded [kpad, Cout] storage is [tap][Cin][Cout] for its first rows = dgrad's B operand
             self.contribute(x, x.size * 2,
-                            lambda p: self.L("b", "mcn_conv2d_dgrad_tc", d, gy, self.pbf16(w), p, 1,
+                            lambda p: self.L("b", "mcn_conv2d_dgrad_tc", d, gy, self._w_bf16(node), p, 1,
                                              self.conv_mode, 0, tag=node.scope + "/dgrad"),
-                            emit_acc=lambda p: self.L("b", "mcn_conv2d_dgrad_tc", d, gy, self.pbf16(w), p, 1,
+                            emit_acc=lambda p: self.L("b", "mcn_conv2d_dgrad_tc", d, gy, self._w_bf16(node), p, 1,
                                                       self.conv_mode, 1, tag=node.scope + "/dgrad+"))
         else:
             if self._var_trains(w):
-                self.L("b", "mcn_conv2d_wgrad_direct", d, self.ccode, self.tbuf[x], gy, self.pgrad(w),
+                self.L("b", "mcn_conv2d_wgrad_direct", d, self.ccode, self.tbuf[x], gy, self._w_grad(node),
                        tag=node.scope + "/wgrad")
             self.contribute(x, x.size * self.csz,
                             lambda p: self.L("b", "mcn_conv2d_dgrad_direct", d, self.ccode, gy, 0,
-                                             self.pvar(w), p, tag=node.scope + "/dgrad"))
+                                             self._w_f32(node), p, tag=node.scope + "/dgrad"))
+        self._ws_finish(node)
 
     def _b_dwconv2d(self, node, gy):
         x, y = node.inputs[0], node.outputs[0]
@@ -1105,11 +1176,12 @@ class Plan(object):
             self.L("b", "mcn_bias_grad", self.ccode, gy, y.size // y.shape[-1], y.shape[-1],
                    self.pgrad(node.vars["b"]), tag=node.scope + "/dbias")
         if self._var_trains(w):
-            self.L("b", "mcn_dwconv2d_bwd_filter", d, mult, self.ccode, self.tbuf[x], gy, self.pgrad(w),
+            self.L("b", "mcn_dwconv2d_bwd_filter", d, mult, self.ccode, self.tbuf[x], gy, self._w_grad(node),
                    tag=node.scope + "/dw_wgrad")
         self.contribute(x, x.size * self.csz,
                         lambda p: self.L("b", "mcn_dwconv2d_bwd_data", d, mult, self.ccode, gy, 0,
-                                         self.pvar(w), p, tag=node.scope + "/dw_dgrad"))
+                                         self._w_f32(node), p, tag=node.scope + "/dw_dgrad"))
+        self._ws_finish(node)
 
     def _b_conv2d_transpose(self, node, gy):
         # y = dgrad_conv(x): dL/dx = fprop_conv(gy); dL/dW_conv[tap][co][ci] = wgrad_conv(a=gy, dy=x)
@@ -1134,7 +1206,7 @@ class Plan(object):
                 self.L("b", "mcn_conv2d_wgrad_tc", d, gy, self.tbuf[x], tmp, self.conv_mode,
                        tag=node.scope + "/wgrad")
             taps, ci, co = w.gemm_dims
-            self.L("b", "mcn_transpose_add_f32", tmp, taps, co, ci, self.pgrad(w), tag="wgrad_T")
+            self.L("b", "mcn_transpose_add_f32", tmp, taps, co, ci, self._w_grad(node), tag="wgrad_T")
             self.tfree(h)
         if mixed:
             # conv HWIO [tap][Cin_conv=co][Cout_conv=ci] is the transposed bf16 copy
@@ -1145,14 +1217,16 @@ class Plan(object):
             else:
                 self.contribute(x, x.size * 2,
                                 lambda p: self.L("b", "mcn_conv2d_fprop_direct", d, self.ccode, gy, 1,
-                                                 self.pbf16t(w), NULL, p, tag=node.scope + "/dgrad"))
+                                                 self._w_bf16t(node), NULL, p, tag=node.scope + "/dgrad"))
+            self._ws_finish(node)
             return
         # fprop of the underlying conv needs W_conv as [tap][Cout_conv=ci][Cin_conv=co] = stored layout
         self.contribute(x, x.size * 2,
-                        lambda p: self.L("b", "mcn_conv2d_fprop_tc", d, gy, self.pbf16(w), NULL, p, 1,
+                        lambda p: self.L("b", "mcn_conv2d_fprop_tc", d, gy, self._w_bf16(node), NULL, p, 1,
                                          self.conv_mode, 0, tag=node.scope + "/dgrad"),
-                        emit_acc=lambda p: self.L("b", "mcn_conv2d_fprop_tc", d, gy, self.pbf16(w), NULL, p,
+                        emit_acc=lambda p: self.L("b", "mcn_conv2d_fprop_tc", d, gy, self._w_bf16(node), NULL, p,
                                                   1, self.conv_mode, 1, tag=node.scope + "/dgrad+"))
+        self._ws_finish(node)
 
     def _b_bn(self, node, gy):
         x = node.inputs[0]
@@ -1235,6 +1309,43 @@ class Plan(object):
             if "gamma" in v and self._var_trains(v["gamma"]):
                 self.L("b", "mcn_accumulate", 0, self.pgrad(v["gamma"]), s2, c, tag="dgamma+=")
             self.tfree(scratch)
+
+    # ------------------------------------------------------------------ group normalisation
+    def _gn_dims(self, node):
+        x = node.inputs[0]
+        n, c = x.shape[0], x.shape[-1]
+        return n, x.size // (n * c), c, node.attrs["groups"]
+
+    def _f_gn(self, node):
+        x, y = node.inputs[0], node.outputs[0]
+        n, hw, c, g = self._gn_dims(node)
+        v = node.vars
+        save = self.node_buf(node, "save", "gn_save:%s" % node.scope, n * g * 2 * 4)
+        node.attrs["save"] = save
+        py = self.alloc_act(y)
+        self.L("f", "mcn_gn_fwd", DT_CODE[x.dtype], self.tbuf[x], n, hw, c, g, node.attrs["eps"],
+               self.pvar(v["gamma"]) if "gamma" in v else NULL, self.pvar(v["beta"]) if "beta" in v else NULL,
+               py, Ptr(save), tag=node.scope)
+
+    def _b_gn(self, node, gy):
+        x = node.inputs[0]
+        n, hw, c, g = self._gn_dims(node)
+        v = node.vars
+        sp, sh = self.talloc((2 * n * g + 2 * n * c) * 4)
+        dgam = self.pgrad(v["gamma"]) if "gamma" in v and self._var_trains(v["gamma"]) else NULL
+        dbet = self.pgrad(v["beta"]) if "beta" in v and self._var_trains(v["beta"]) else NULL
+        pg = self.pvar(v["gamma"]) if "gamma" in v else NULL
+        done = []
+
+        def emit(p, params=True):
+            self.L("b", "mcn_gn_bwd", DT_CODE[x.dtype], gy, self.tbuf[x], n, hw, c, g, pg,
+                   Ptr(node.attrs["save"]), sp, p, dgam if params else NULL, dbet if params else NULL,
+                   tag=node.scope + "/bwd")
+            done.append(1)
+        self.contribute(x, x.size * DT_SIZE[x.dtype], emit)
+        if not done and (dgam is not NULL or dbet is not NULL):
+            emit(NULL)                     # no gradient into x: parameter gradients only
+        self.tfree(sh)
 
     def _b_act(self, node, gy):
         x = node.inputs[0]

@@ -12,7 +12,8 @@ import sys
 SRC = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
 DST = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
 FILES = ["models/resnet_v1_5.py", "models/resnet_v1_5_dilated.py", "models/efficientnet.py",
-         "models/deeplabv3plus.py", "models/dcgan.py"]
+         "models/deeplabv3plus.py", "models/dcgan.py", "models/resnet_v1_5_wsgn.py",
+         "models/efficientnet_wsgn.py"]
 
 if not os.path.isdir(SRC):
     print("reference not found at", SRC)

@@ -354,3 +354,93 @@ def test_efficientnet_depthwise_shapes(L, code, case):
     assert rel_l2(dx.float().cpu(), xt.grad) < tol
     assert rel_l2(dws[0].cpu(), wtt.grad) < 2e-5
     assert torch.equal(dws[0], dws[1])
+
+
+# ------------------------------------------------------------------ group norm / weight standardisation
+@pytest.mark.parametrize("code", [0, 1])
+@pytest.mark.parametrize("case", [(3, (7, 5), 64, 32), (2, (), 96, 8), (4, (9, 9), 40, 5)],
+                         ids=["hw35_c64_g32", "dense_c96_g8", "hw81_c40_g5"])
+def test_group_norm_kernels(L, code, case):
+    """mcn_gn_fwd / mcn_gn_bwd against the oracle's group_norm (reference convnet.py:1928-2013) and its
+    autograd: output, input gradient, dgamma, dbeta; a second backward gives bit-identical results."""
+    n, hw, c, g = case
+    rng = np.random.default_rng(5)
+    shape = (n,) + tuple(hw) + (c,)
+    x = rng.standard_normal(shape).astype(np.float32) * 1.5 + 0.3
+    dy = rng.standard_normal(shape).astype(np.float32)
+    gamma = rng.uniform(0.5, 1.5, c).astype(np.float32)
+    beta = rng.standard_normal(c).astype(np.float32)
+    dt = torch.float32 if code == 0 else torch.bfloat16
+    if code == 1:
+        x, dy = bf16_round(x), bf16_round(dy)
+    xt, gt, bt = (torch.tensor(a, requires_grad=True) for a in (x, gamma, beta))
+    yref = tf_ops.group_norm(xt, gt, bt, g, 1e-3)
+    yref.backward(torch.tensor(dy))
+    lib = L.load()
+    HW = int(np.prod(hw)) if hw else 1
+    xd, dyd, gd, bd = dev(x, dt), dev(dy, dt), dev(gamma), dev(beta)
+    y = torch.empty_like(xd)
+    save = torch.zeros(n * g * 2, device="cuda")
+    L.check(lib.mcn_gn_fwd(code, xd.data_ptr(), n, HW, c, g, 1e-3, gd.data_ptr(), bd.data_ptr(), y.data_ptr(),
+                           save.data_ptr(), None))
+    outs = []
+    for _ in range(2):
+        dx = torch.empty_like(xd)
+        dgam, dbet = torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda")
+        scratch = torch.zeros(2 * n * g + 2 * n * c, device="cuda")
+        L.check(lib.mcn_gn_bwd(code, dyd.data_ptr(), xd.data_ptr(), n, HW, c, g, gd.data_ptr(), save.data_ptr(),
+                               scratch.data_ptr(), dx.data_ptr(), dgam.data_ptr(), dbet.data_ptr(), None))
+        outs.append((dx, dgam, dbet))
+    torch.cuda.synchronize()
+    tol = 2e-5 if code == 0 else 6e-3
+    assert rel_l2(y.float().cpu(), yref.detach()) < tol
+    assert rel_l2(outs[0][0].float().cpu(), xt.grad) < tol
+    assert rel_l2(outs[0][1].cpu(), gt.grad) < 2e-5 and rel_l2(outs[0][2].cpu(), bt.grad) < 2e-5
+    assert all(torch.equal(a, b) for a, b in zip(outs[0], outs[1]))
+
+
+@pytest.mark.parametrize("wshape", [(3, 3, 16, 24), (1, 1, 64, 256), (72, 10), (5, 5, 8, 1)])
+def test_weight_standardisation_kernels(L, wshape):
+    """mcn_ws_fwd / mcn_ws_bwd against the oracle's restatement of convnet.py:1410-1419 and its autograd
+    (the statistic is per LAST axis, population std + 1e-5)."""
+    rng = np.random.default_rng(6)
+    w = (rng.standard_normal(wshape) * 0.1 + 0.02).astype(np.float32)
+    g = rng.standard_normal(wshape).astype(np.float32)
+    wt = torch.tensor(w, requires_grad=True)
+    ref = tf_ops.weight_standardization(wt)
+    ref.backward(torch.tensor(g))
+    lib = L.load()
+    cols = wshape[-1]
+    rows = w.size // cols
+    wd, gd = dev(w), dev(g)
+    ws = torch.empty_like(wd)
+    stats = torch.zeros(2 * cols, device="cuda")
+    L.check(lib.mcn_ws_fwd(wd.data_ptr(), rows, cols, 1e-5, ws.data_ptr(), stats.data_ptr(), None))
+    base = rng.standard_normal(wshape).astype(np.float32)
+    grad = dev(base)
+    L.check(lib.mcn_ws_bwd(gd.data_ptr(), wd.data_ptr(), stats.data_ptr(), rows, cols, 1e-5, grad.data_ptr(), None))
+    torch.cuda.synchronize()
+    assert rel_l2(ws.cpu(), ref.detach()) < 2e-6
+    assert rel_l2(grad.cpu().numpy() - base, wt.grad) < 2e-5        # accumulates into the gradient
+
+
+@pytest.mark.parametrize("dtype,tol", [("f32", 3e-3), ("bf16", 0.3)])
+def test_wsgn_resnet_step(have_reference_models, dtype, tol):
+    """models/resnet_v1_5_wsgn.py, unchanged: every convolution runs on standardised weights
+    (tensor-core routes on per-step bf16 copies, the RGB stem on the CUDA-core route) and every
+    normalisation is a group norm.  One optimiser step against the oracle: loss and every update
+    (fp32 is the parity run; bf16 checks the tensor-core plan end to end, see test_gpu_resnet.py)."""
+    pm, om, vals = build_pair("models/resnet_v1_5_wsgn.py", "ResNet50", [64, 64, 3], SMALL_NCLS, 8, dtype,
+                              base_learning_rate=0.05)
+    hist = {}
+    from myconvnet_b200.plan import Plan
+    for l in Plan(pm.graph).fwd:
+        hist[l.fn] = hist.get(l.fn, 0) + 1
+    assert hist["mcn_ws_fwd"] == 53 and hist["mcn_gn_fwd"] == 53 and "mcn_bn_apply_stats" not in hist
+    X, Y = synthetic_batch(8, [64, 64, 3], SMALL_NCLS)
+    eng, tr, a, b, uerr = _one_step(pm, om, vals, X, Y)
+    assert abs(a - b) <= (2e-5 if dtype == "f32" else 2e-2) * abs(b), (a, b)
+    assert len(uerr) >= 150 and worst(uerr, 1)[0][1] <= tol, worst(uerr)
+    # inference runs the same standardisation on the EMA weights
+    p = eng.predict(X)
+    assert p.shape == (8, SMALL_NCLS) and np.isfinite(p).all() and np.allclose(p.sum(-1), 1.0, atol=1e-3)

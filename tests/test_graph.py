@@ -227,3 +227,30 @@ def test_every_launch_pointer_lies_inside_its_buffer(r50):
                 nxt = (p.fwd if phase == "f" else p.bwd)[idx]
                 assert nxt.fn == ("mcn_bn_apply_stats" if phase == "f" else "mcn_bn_bwd_apply"), nxt.fn
                 assert any(isinstance(a, Ptr) and a.buf is ptr.buf and a.off == ptr.off for a in nxt.args)
+
+
+def test_wsgn_model_plans_standardised_weights_and_group_norm():
+    """models/resnet_v1_5_wsgn.py (unchanged): every convolution's weight is standardised per step into
+    node-owned buffers (the tensor-core routes then run on per-step bf16 copies), the weight gradient
+    is folded back onto the raw weight, and every normalisation is a group norm."""
+    from myconvnet_b200 import loader
+    if loader.reference_root() is None:
+        pytest.skip("reference model files not staged")
+    from tests.util import build_pair
+    pm, _, _ = build_pair("models/resnet_v1_5_wsgn.py", "ResNet50", [64, 64, 3], 16, 8, "bf16")
+    p = Plan(pm.graph)
+    f, b = {}, {}
+    for l in p.fwd:
+        f[l.fn] = f.get(l.fn, 0) + 1
+    for l in p.bwd:
+        b[l.fn] = b.get(l.fn, 0) + 1
+    assert f["mcn_ws_fwd"] == 53 and f["mcn_weight_prep"] == 52 and f["mcn_gn_fwd"] == 53
+    assert f["mcn_conv2d_fprop_direct"] == 1           # the RGB stem: plain storage layout, CUDA cores
+    assert b["mcn_ws_bwd"] == 53 and b["mcn_gn_bwd"] == 53 and "mcn_bn_bwd_reduce" not in b
+    # the standardised operand, not the raw bf16 copy, feeds the tensor-core launches
+    raw = {id(p.b_bf16)}
+    for l in p.fwd:
+        if l.fn == "mcn_conv2d_fprop_tc" and "logits" not in l.tag:
+            assert id(l.args[2].buf) not in raw, l.tag
+    # inference standardises the EMA weights the same way
+    assert sum(1 for l in p.inf if l.fn == "mcn_ws_fwd") == 53
