@@ -610,9 +610,8 @@ class Plan(object):
                 self.L("f", "mcn_conv2d_fprop_tc", gd, Ptr(col), self._w_bf16t(node), pb, py, self.ccode, 0, 0,
                        tag=node.scope)
         else:
-            wdt, pw = self._direct_weight(w)
-            self.L("f", "mcn_conv2d_fprop_direct", d, self.ccode, self.tbuf[x], wdt, pw, pb, py,
-                   tag=node.scope)
+            self.L("f", "mcn_conv2d_fprop_direct", d, self.ccode, self.tbuf[x], 0, self._w_f32(node), pb, py,
+                   tag=node.scope)            # fp32 master (or standardised) weights
 
     @staticmethod
     def _stats_fusion_pays(conv):
@@ -630,9 +629,6 @@ class Plan(object):
     def _bn_sums_buf(self, bn_node):
         c = bn_node.inputs[0].shape[-1]
         return self.node_buf(bn_node, "sums", "bn_sums:%s" % bn_node.scope, 2 * c * 8, "zero")
-
-    def _direct_weight(self, w):
-        return 0, self.pvar(w)   # fp32 master weights
 
     def _f_dwconv2d(self, node):
         x, y = node.inputs[0], node.outputs[0]

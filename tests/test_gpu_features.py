@@ -424,23 +424,24 @@ def test_weight_standardisation_kernels(L, wshape):
     assert rel_l2(grad.cpu().numpy() - base, wt.grad) < 2e-5        # accumulates into the gradient
 
 
-@pytest.mark.parametrize("dtype,tol", [("f32", 3e-3), ("bf16", 0.3)])
+@pytest.mark.parametrize("dtype,tol", [("f32", 3e-3), ("bf16", 0.35)])
 def test_wsgn_resnet_step(have_reference_models, dtype, tol):
     """models/resnet_v1_5_wsgn.py, unchanged: every convolution runs on standardised weights
     (tensor-core routes on per-step bf16 copies, the RGB stem on the CUDA-core route) and every
     normalisation is a group norm.  One optimiser step against the oracle: loss and every update
     (fp32 is the parity run; bf16 checks the tensor-core plan end to end, see test_gpu_resnet.py)."""
-    pm, om, vals = build_pair("models/resnet_v1_5_wsgn.py", "ResNet50", [64, 64, 3], SMALL_NCLS, 8, dtype,
+    shape, batch = ([64, 64, 3], 8) if dtype == "f32" else (SMALL_SHAPE, SMALL_BATCH)
+    pm, om, vals = build_pair("models/resnet_v1_5_wsgn.py", "ResNet50", shape, SMALL_NCLS, batch, dtype,
                               base_learning_rate=0.05)
     hist = {}
     from myconvnet_b200.plan import Plan
     for l in Plan(pm.graph).fwd:
         hist[l.fn] = hist.get(l.fn, 0) + 1
     assert hist["mcn_ws_fwd"] == 53 and hist["mcn_gn_fwd"] == 53 and "mcn_bn_apply_stats" not in hist
-    X, Y = synthetic_batch(8, [64, 64, 3], SMALL_NCLS)
+    X, Y = synthetic_batch(batch, shape, SMALL_NCLS)
     eng, tr, a, b, uerr = _one_step(pm, om, vals, X, Y)
     assert abs(a - b) <= (2e-5 if dtype == "f32" else 2e-2) * abs(b), (a, b)
     assert len(uerr) >= 150 and worst(uerr, 1)[0][1] <= tol, worst(uerr)
     # inference runs the same standardisation on the EMA weights
     p = eng.predict(X)
-    assert p.shape == (8, SMALL_NCLS) and np.isfinite(p).all() and np.allclose(p.sum(-1), 1.0, atol=1e-3)
+    assert p.shape == (batch, SMALL_NCLS) and np.isfinite(p).all() and np.allclose(p.sum(-1), 1.0, atol=1e-3)
