@@ -442,6 +442,25 @@ __global__ void gap_bwd_kernel(const TI* __restrict__ dy, int HW, int C, long lo
   }
 }
 
+// 16-byte stores: one thread writes V consecutive channels of one pixel
+template <typename T, typename TI>
+__global__ void gap_bwd_vec_kernel(const TI* __restrict__ dy, int HW, int C, long long nvec,
+                                   T* __restrict__ dx) {
+  MCN_PDL_PROLOGUE();
+  constexpr int V = Vec16<T>::N;
+  const float inv = 1.f / (float)HW;
+  const int cv = C / V;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % cv) * V;
+    const long long n = i / ((long long)HW * cv);
+    Vec16<T> o;
+#pragma unroll
+    for (int e = 0; e < V; ++e) o.set(e, to_f32(dy[n * C + c0 + e]) * inv);
+    st_vec(dx + i * V, o);
+  }
+}
+
 inline int grid_for(long long n, int block) {
   return (int)std::max<long long>(1, std::min<long long>((n + block - 1) / block, 16LL * num_sms()));
 }
@@ -501,7 +520,14 @@ static void launch_maxpool_tap(bool fwd, const void* in, const uint8_t* tap_in, 
                                int kw, int sh, int sw, int pad_t, int pad_l, int Ho, int Wo, void* out,
                                uint8_t* tap_out, cudaStream_t st) {
   const long long total = fwd ? (long long)N * Ho * Wo * (C / V) : (long long)N * H * W * (C / V);
-  const int grid = (int)std::max<long long>(1, (total + 255) / 256);
+  // persistent grid-stride blocks: one short-lived block per 256 outputs (100 k blocks for the ResNet
+  // stem's backward) spent its time in block scheduling; MCN_POOL_BLOCKS_PER_SM overrides (A/B)
+  static int bps = 0;
+  if (!bps) {
+    const char* e = getenv("MCN_POOL_BLOCKS_PER_SM");
+    bps = e ? std::max(1, atoi(e)) : 16;   // measured: 0.54 (one block per 256 outputs) / 0.50 (8) / 0.48 ms (16)
+  }
+  const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)bps * num_sms()));
 #define MCN_POOL_CASE(KK, SS)                                                                        \
   if (fwd)                                                                                           \
     ::mcn::launch(maxpool_fwd_tap_kernel<T, V, KK, SS>, grid, 256, 0, st, static_cast<const T*>(in), N, H, W, C, kh, kw, sh, \
@@ -605,7 +631,16 @@ extern "C" int mcn_gap_bwd(int dtype, const void* dy, int dy_dtype, int N, int H
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   long long total = (long long)N * HW * C;
   MCN_DISPATCH_DTYPE(dtype, T, {
-    if (dy_dtype == MCN_F32)
+    constexpr int V = Vec16<T>::N;
+    if (C % V == 0 && reinterpret_cast<uintptr_t>(dx) % 16 == 0) {
+      const long long nvec = total / V;
+      if (dy_dtype == MCN_F32)
+        ::mcn::launch(gap_bwd_vec_kernel<T, float>, grid_for(nvec, 256), 256, 0, st,
+                      static_cast<const float*>(dy), HW, C, nvec, static_cast<T*>(dx));
+      else
+        ::mcn::launch(gap_bwd_vec_kernel<T, __nv_bfloat16>, grid_for(nvec, 256), 256, 0, st,
+                      static_cast<const __nv_bfloat16*>(dy), HW, C, nvec, static_cast<T*>(dx));
+    } else if (dy_dtype == MCN_F32)
       ::mcn::launch(gap_bwd_kernel<T, float>, grid_for(total, 256), 256, 0, st, 
           static_cast<const float*>(dy), HW, C, total, static_cast<T*>(dx));
     else
