@@ -1007,6 +1007,8 @@ struct WgradArgs {
   CUtensorMap mapDy;
   TileGeom g;
   int taps, stages, block_n, nb_atoms, tmem_cols;
+  int a_atoms;     // 64-channel atoms of x per CTA: 2 (M = 128) or 4 (two M = 128 accumulators: "wide" tile)
+  int atom_bytes;  // shared-memory bytes of one atom: (pixels per stage) x 128
   int cin, cout;
   int tiles_mi, tiles_ni, splits, kblocks_total, ksteps;
   float* dw;          // split-K partial slices (deterministic) or the gradient itself (atomics)
@@ -1051,9 +1053,11 @@ wgrad_kernel(const __grid_constant__ WgradArgs args) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int stages = args.stages;
-  const uint32_t a_bytes = 2u * kABytes;
-  const uint32_t b_bytes = static_cast<uint32_t>(args.nb_atoms) * kABytes;
+  const uint32_t atom = static_cast<uint32_t>(args.atom_bytes);
+  const uint32_t a_bytes = static_cast<uint32_t>(args.a_atoms) * atom;
+  const uint32_t b_bytes = static_cast<uint32_t>(args.nb_atoms) * atom;
   const uint32_t stage_bytes = a_bytes + b_bytes;
+  const int m_halves = args.a_atoms >> 1;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(stages) * stage_bytes);
   uint64_t* empty = full + stages;
   uint64_t* tmem_full = empty + stages;
@@ -1104,7 +1108,7 @@ wgrad_kernel(const __grid_constant__ WgradArgs args) {
     if (ptx::elect_one()) {
       const uint32_t rows_bytes =
           (args.g.a_mode == 0) ? static_cast<uint32_t>(args.g.rows_box) * 128u : kABytes;
-      const uint32_t tx = rows_bytes * static_cast<uint32_t>(2 + args.nb_atoms);
+      const uint32_t tx = rows_bytes * static_cast<uint32_t>(args.a_atoms + args.nb_atoms);
       RT_DECL;
       RT_ADD(2, RT_NOW() - rt_cta0);      // wgrad: slot 2 = prologue (smem clear, barrier init, TMEM alloc)
       for (int kb = kb0, it = 0; kb < kb1; ++kb, ++it) {
@@ -1117,13 +1121,13 @@ wgrad_kernel(const __grid_constant__ WgradArgs args) {
         uint8_t* sA = smem + static_cast<size_t>(s) * stage_bytes;
         uint8_t* sB = sA + a_bytes;
         const PixelTile t = decode_tile(args.g, kb);
-        for (int a = 0; a < 2; ++a) {
-          const int c = mi * 128 + a * 64;
+        for (int a = 0; a < args.a_atoms; ++a) {
+          const int c = mi * 64 * args.a_atoms + a * 64;
           if (args.g.a_mode == 0) {
-            ptx::tma_load_4d(&args.mapX[args.tab.map[tap]], &full[s], sA + a * kABytes, c,
+            ptx::tma_load_4d(&args.mapX[args.tab.map[tap]], &full[s], sA + a * atom, c,
                              t.w0 + args.tab.dw[tap], t.h0 + args.tab.dh[tap], t.n0);
           } else {
-            ptx::tma_load_im2col_4d(&args.mapX[0], &full[s], sA + a * kABytes, c, t.w0, t.h0, t.n0,
+            ptx::tma_load_im2col_4d(&args.mapX[0], &full[s], sA + a * atom, c, t.w0, t.h0, t.n0,
                                     static_cast<uint16_t>(args.tab.dw[tap]),
                                     static_cast<uint16_t>(args.tab.dh[tap]));
           }
@@ -1131,10 +1135,10 @@ wgrad_kernel(const __grid_constant__ WgradArgs args) {
         for (int j = 0; j < args.nb_atoms; ++j) {
           const int c = ni * args.block_n + j * 64;
           if (args.g.a_mode == 0) {
-            ptx::tma_load_4d(&args.mapDy, &full[s], sB + j * kABytes, c, t.w0, t.h0, t.n0);
+            ptx::tma_load_4d(&args.mapDy, &full[s], sB + j * atom, c, t.w0, t.h0, t.n0);
           } else {
             // dy is addressed as a [m_total, Cout] matrix through a (C, M, 1, 1) map
-            ptx::tma_load_4d(&args.mapDy, &full[s], sB + j * kABytes, c,
+            ptx::tma_load_4d(&args.mapDy, &full[s], sB + j * atom, c,
                              static_cast<int>(t.m0), 0, 0);
           }
         }
@@ -1148,9 +1152,10 @@ wgrad_kernel(const __grid_constant__ WgradArgs args) {
       RT_DECL;
       const long long rt_m0 = RT_NOW();
       (void)rt_m0;
-      // MN-major: 64-channel atoms kABytes apart (LBO), 8-pixel groups 1024 B apart (SBO);
-      // one instruction consumes 16 pixels = 2048 B of each atom (descriptor step 128).
-      const uint64_t dhi = ptx::smem_desc_hi(kABytes, 1024);
+      // MN-major: 64-channel atoms `atom` bytes apart (LBO), 8-pixel groups 1024 B apart (SBO);
+      // one instruction consumes 16 pixels = 2048 B of each atom (descriptor step 128).  A wide tile
+      // (a_atoms == 4) runs two M = 128 accumulators off the same dy operand.
+      const uint64_t dhi = ptx::smem_desc_hi(atom, 1024);
       const uint32_t smem0 = ptx::smem_u32(smem);
       const int ksteps = args.ksteps;
       int s = 0;
@@ -1161,16 +1166,20 @@ wgrad_kernel(const __grid_constant__ WgradArgs args) {
         RT_END;
         ptx::tc_fence_after();
         const uint32_t a_addr = smem0 + static_cast<uint32_t>(s) * stage_bytes;
-        uint64_t ad = ptx::smem_desc_at(dhi, a_addr);
-        uint64_t bd = ptx::smem_desc_at(dhi, a_addr + a_bytes);
-        if (ksteps == 8) {
+        const uint64_t bd = ptx::smem_desc_at(dhi, a_addr + a_bytes);
+        for (int half = 0; half < m_halves; ++half) {
+          const uint64_t ad = ptx::smem_desc_at(dhi, a_addr + static_cast<uint32_t>(half) * 2u * atom);
+          const uint32_t td = tmem_base + static_cast<uint32_t>(half * args.block_n);
+          if (ksteps == 8) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            ptx::umma_bf16(tmem_base, ad + 128 * k, bd + 128 * k, idesc, k == 0 ? acc : 1u);
+            for (int k = 0; k < 8; ++k) ptx::umma_bf16(td, ad + 128 * k, bd + 128 * k, idesc, k == 0 ? acc : 1u);
+          } else if (ksteps == 4) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ptx::umma_bf16(td, ad + 128 * k, bd + 128 * k, idesc, k == 0 ? acc : 1u);
+          } else {
+            for (int k = 0; k < ksteps; ++k)
+              ptx::umma_bf16(td, ad + 128 * k, bd + 128 * k, idesc, k == 0 ? acc : 1u);
           }
-        } else {
-          for (int k = 0; k < ksteps; ++k)
-            ptx::umma_bf16(tmem_base, ad + 128 * k, bd + 128 * k, idesc, k == 0 ? acc : 1u);
         }
         acc = 1u;
         ptx::umma_commit(&empty[s]);
@@ -1190,10 +1199,11 @@ wgrad_kernel(const __grid_constant__ WgradArgs args) {
     if (threadIdx.x == 64) RT_ADD(3, RT_NOW() - rt_e0);
     ptx::tc_fence_after();
     const int quad = warp & 3;
-    const int ci = mi * 128 + quad * 32 + lane;
-    for (int c0 = 0; c0 < args.block_n; c0 += 32) {
+    for (int hc = 0; hc < m_halves * args.block_n; hc += 32) {
+      const int half = hc / args.block_n, c0 = hc - half * args.block_n;
+      const int ci = mi * 64 * args.a_atoms + half * 128 + quad * 32 + lane;
       uint32_t r[32];
-      ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c0, r);
+      ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(hc), r);
       ptx::tmem_ld_wait();
       if (ci >= args.cin) continue;
       const int co0 = ni * args.block_n + c0;
@@ -2581,10 +2591,34 @@ static int wgrad_tc_impl(const mcn_conv_desc* d, const void* x, const void* dy, 
   const int taps = d->kh * d->kw;
   a.block_n = pick_block_n(d->Cout);
   if (a.block_n > 128) a.block_n = 128;  // keep a stage at 64 KB
+  a.a_atoms = 2;
+  a.atom_bytes = kABytes;
+  // Wide tiles for the 1x1 convolutions.  Per-role counters put the MMA thread of these launches in
+  // "waiting for operands" with the L2 -> shared-memory traffic at the chip's ~6300 B/cycle cap: a
+  // 128 x 128 output tile moves 512 operand bytes per 128 x 128 x 1 MACs.  Two M = 128 accumulators
+  // (256 input channels) against a 256-wide dy tile halve that; the pixel box shrinks to 64 rows so
+  // three stages of (4 + 4) x 8 KB still fit.  MCN_WGRAD_WIDE=0 restores the narrow tiles (A/B).
+  static int wide_enabled = -1;
+  if (wide_enabled < 0) {
+    const char* e = getenv("MCN_WGRAD_WIDE");
+    wide_enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  const bool wide = wide_enabled && pointwise && (d->Cin % 256 == 0 || d->Cout % 256 == 0) &&
+                    (long long)d->N * d->H * d->W >= 4096;
+  if (wide) {
+    if (d->Cin % 256 == 0) a.a_atoms = 4;
+    if (d->Cout % 256 == 0) a.block_n = 256;
+    a.atom_bytes = 64 * 128;
+  }
   a.nb_atoms = a.block_n / 64;
   if (pointwise) {
     PixelSpace ps{static_cast<int>((long long)d->N * d->H * d->W), 1, 1};
     fill_geom_tiled(&a.g, ps);
+    if (wide) {   // 64-pixel boxes
+      a.g.TW = std::min(ps.W, 64);
+      a.g.rows_box = a.g.TW;
+      a.g.tiles_w = (ps.W + a.g.TW - 1) / a.g.TW;
+    }
     uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)ps.W, 1, 1};
     uint64_t stb[4] = {2, (uint64_t)d->Cin * 2, (uint64_t)ps.W * d->Cin * 2,
                        (uint64_t)ps.W * d->Cin * 2};
@@ -2634,15 +2668,16 @@ static int wgrad_tc_impl(const mcn_conv_desc* d, const void* x, const void* dy, 
   a.taps = taps;
   a.cin = d->Cin;
   a.cout = d->Cout;
-  a.tiles_mi = (d->Cin + 127) / 128;
+  a.tiles_mi = (d->Cin + 64 * a.a_atoms - 1) / (64 * a.a_atoms);
   a.tiles_ni = (d->Cout + a.block_n - 1) / a.block_n;
   a.kblocks_total = tiles_m_of(a.g);
   a.ksteps = (a.g.a_mode == 0) ? (a.g.rows_box + 15) / 16 : 8;
   {
     const int base = taps * a.tiles_mi * a.tiles_ni;
     // two full waves of one-CTA-per-SM at most: rounding the split count UP (304 CTAs for a base of
-    // 16) left a third, nearly empty wave behind
-    int want = std::max(1, (2 * num_sms()) / base);
+    // 16) left a third, nearly empty wave behind.  Wide tiles: one wave (every extra split is another
+    // 256 KB partial tile to write and sum)
+    int want = std::max(1, ((wide ? 1 : 2) * num_sms()) / base);
     // one CTA per SM is resident at a time, so a grid that already fills 3/4 of the SMs gains
     // nothing from splitting K — and an un-split K needs no slices and no second pass
     if (4 * base >= 3 * num_sms()) want = 1;
@@ -2680,9 +2715,9 @@ static int wgrad_tc_impl(const mcn_conv_desc* d, const void* x, const void* dy, 
         a.tab.dw[t] = (short)(s * d->dw);
       }
     }
-  const uint32_t stage_bytes = (2 + a.nb_atoms) * kABytes;
+  const uint32_t stage_bytes = (a.a_atoms + a.nb_atoms) * a.atom_bytes;
   a.stages = std::max(2, std::min(4, (int)((200 * 1024) / stage_bytes)));
-  a.tmem_cols = tmem_cols_for(a.block_n);
+  a.tmem_cols = tmem_cols_for(a.block_n) * (a.a_atoms / 2);   // 64 .. 512, a power of two
   size_t smem = (size_t)a.stages * stage_bytes + (2 * a.stages + 1) * 8 + 16 + 1024;
   static bool configured = false;
   if (!configured) {

@@ -10,8 +10,8 @@ ncu --nvtx --nvtx-include "mcn_profiled_step/" --metrics gpu__time_duration.sum,
     --clock-control none -c 400 --csv --log-file gpurun_out/ncu/launches.csv $CMD > gpurun_out/ncu/ncu1.log 2>&1
 echo "launch list rc=$? lines=$(wc -l < gpurun_out/ncu/launches.csv)"
 ncu --nvtx --nvtx-include "mcn_profiled_step/" --set full --clock-control none \
-    -k regex:"gemm_conv_kernel|halo_conv_kernel|wgrad_halo_kernel|wgrad_kernel|stem_fprop_kernel|stem_wgrad_kernel|bn_bwd_apply_kernel|bn_bwd_reduce_kernel|bn_apply_runs_kernel|bn_apply_kernel" \
-    -s 4 -c 26 -o /tmp/prof_full $CMD > gpurun_out/ncu/ncu2.log 2>&1
+    -k regex:"gemm_conv_kernel|halo_conv_kernel|wgrad_halo_kernel|wgrad_kernel|stem_fprop_kernel|stem_wgrad_kernel|bn_bwd_apply_pipe_kernel|bn_bwd_reduce_kernel|bn_apply_pipe_kernel|maxpool_fwd_tap_kernel|maxpool_bwd_tap_kernel" \
+    -s 6 -c 40 -o /tmp/prof_full $CMD > gpurun_out/ncu/ncu2.log 2>&1
 echo "full set rc=$?"
 ncu -i /tmp/prof_full.ncu-rep --page raw --csv > gpurun_out/ncu/full_raw.csv 2> gpurun_out/ncu/export.log
 ls -la /tmp/prof_full.ncu-rep gpurun_out/ncu/ | tail -8

@@ -26,29 +26,26 @@ def main():
     for r in rows[1:]:
         d = launches.setdefault(int(r[iid]), {"kernel": short(r[ik]), "grid": r[igrid], "block": r[iblk]})
         d[r[im]] = float(r[iv].replace(",", ""))
-    # classes: gemm/halo launches before the loss kernel are fprop, after it dgrad
-    seen_loss = False
+    # classes = bench.py's KERNEL_OF groups (launches are grouped by CUDA kernel family)
     out = []
     for i, d in launches.items():
         k = d["kernel"]
-        if "softmax_xent" in k:
-            seen_loss = True
         if k in ("gemm_conv_kernel", "halo_conv_kernel"):
-            cls = "conv2d_dgrad_tc" if seen_loss else "conv_fprop_tc"
-        elif k in ("wgrad_kernel", "wgrad_halo_kernel"):
-            cls = "conv2d_wgrad_tc"
-        elif k in ("bn_apply_kernel", "bn_apply_runs_kernel"):
-            cls = "bn_apply"
+            cls = "conv_tc"
+        elif k in ("wgrad_kernel", "wgrad_halo_kernel") or k.startswith("splitk_reduce"):
+            cls = "wgrad_tc"
         elif k.startswith("bn_bwd_apply"):
             cls = "bn_bwd_apply"
-        elif k.startswith("bn_bwd_reduce"):
+        elif k.startswith("bn_bwd_reduce") or k.startswith("bn_reduce_pipe"):
             cls = "bn_bwd_reduce"
+        elif k.startswith("bn_apply"):
+            cls = "bn_apply"
         elif k.startswith("bn_stats"):
             cls = "bn_stats"
-        elif k.startswith("stem_fprop"):
-            cls = "stem_conv_fprop"
-        elif k.startswith("stem_wgrad"):
-            cls = "stem_conv_wgrad"
+        elif k.startswith("stem_"):
+            cls = "stem"
+        elif k.startswith("maxpool"):
+            cls = "maxpool"
         else:
             cls = k.replace("_kernel", "")
         d["class"] = cls
@@ -80,6 +77,8 @@ def main():
                                "share_of_step": ns / total_ns}
                            for c, (n, ns, b) in agg.items()}},
               open(os.path.join(prof, "ncu_traffic.json"), "w"), indent=1)
+    import shutil
+    shutil.copyfile(os.path.join(prof, "ncu_traffic.json"), os.path.join(prof, "%s_ncu_traffic.json" % tag))
     print("launches %d, step under ncu %.2f ms" % (len(out), total_ns / 1e6))
     for c, (n, ns, b) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:12]:
         print("%-18s n=%3d %8.1f us  %5.1f%%  %8.1f MB  %6.0f GB/s" % (c, n, ns / 1e3, 100 * ns / total_ns, b / 1e6, b / ns if ns else 0))
