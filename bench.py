@@ -408,6 +408,10 @@ def main():
     ms = e0.elapsed_time(e1) / args.steps
     stage("timed region done: %.2f ms/step" % ms)
     sampler.stop_flag = True
+    if rank == 0:
+        # a query still in flight (the first nvidia-smi on a fresh box takes seconds) must not overlap
+        # the end-to-end region: it measurably slows kernel launches (33 vs 23 ms/step observed)
+        sampler.join(timeout=10)
     loss = eng.read_loss()
     eager_launches = eng.launches_per_step()
     # ---- end-to-end: every step's batch comes from pinned HOST memory (H2D inside the timed

@@ -48,14 +48,6 @@ inline int bn_noy_unroll() {
   }
   return v;
 }
-inline bool bn_float_atomics() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MCN_BN_ATOMICS");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v != 0;
-}
 inline bool bn_use_runs() {
   static int v = -1;
   if (v < 0) {
@@ -142,18 +134,6 @@ __device__ __forceinline__ void slab_finish(float* sh, int slab_v, int rowlanes,
                                             TAcc* out1, TAcc* out2, const XsScratch& xsc) {
   __syncthreads();
   const int width = slab_v * V;
-  if (xsc.limbs == nullptr) {
-    // MCN_BN_ATOMICS=1 (A/B timing only): the round-1 floating-point atomics, order-dependent
-    for (int t = threadIdx.x; t < 2 * width; t += blockDim.x) {
-      const int which = t / width, e = t - which * width;
-      const float* src = sh + (size_t)which * rowlanes * width + e;
-      float acc = 0.f;
-      for (int r = 0; r < rowlanes; ++r) acc += src[(size_t)r * width];
-      const int c = slab * width + e;
-      if (c < C) atomicAdd((which ? out2 : out1) + c, (TAcc)acc);
-    }
-    return;
-  }
   for (int t = threadIdx.x; t < 2 * width; t += blockDim.x) {
     const int which = t / width, e = t - which * width;
     const float* src = sh + (size_t)which * rowlanes * width + e;
@@ -977,7 +957,6 @@ extern "C" int mcn_bn_stats(int dtype, const void* x, long long rows, int C, dou
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   XsScratch xsc = xs_scratch(2 * C, "bn_stats");
   if (xsc.limbs == nullptr) return MCN_EINVAL;
-  if (bn_float_atomics() && C % 8 == 0) xsc.limbs = nullptr;
   MCN_DISPATCH_DTYPE(dtype, T, {
     SlabLaunch L;
     if (plan_slab<T>(rows, C, &L, 3 * num_sms())) {
@@ -1162,7 +1141,6 @@ extern "C" int mcn_bn_bwd_reduce(int dtype, const void* dy, const void* x, const
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   XsScratch xsc = xs_scratch(2 * C, "bn_bwd_reduce");
   if (xsc.limbs == nullptr) return MCN_EINVAL;
-  if (bn_float_atomics() && C % 8 == 0) xsc.limbs = nullptr;
   MCN_DISPATCH_DTYPE(dtype, T, {
     SlabLaunch L;
     if (plan_slab<T>(rows, C, &L, 3 * num_sms())) {

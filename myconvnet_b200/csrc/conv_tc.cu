@@ -8,7 +8,7 @@
 //   dgrad : dX[pixel, ci] = sum_tap sum_co dY[pixel shifted by -tap, co] * W[tap, ci, co]
 //   wgrad : dW[tap, ci, co] = sum_pixel X[pixel shifted by tap, ci] * dY[pixel, co]
 // fprop and dgrad share one kernel (A = activations, K-major; B = weights, K-major);
-// wgrad has its own (both operands MN-major, K = pixels, split-K with fp32 atomics).
+// wgrad has its own (both operands MN-major, K = pixels, deterministic split-K through workspace slices).
 //
 // Data movement: every operand tile is brought in by TMA into 128-byte-swizzled shared memory.
 // The shifted activation window of a tap is either a 4-D TMA *box* (a_mode 0: the tile is a
@@ -1011,19 +1011,17 @@ struct WgradArgs {
   int atom_bytes;  // shared-memory bytes of one atom: (pixels per stage) x 128
   int cin, cout;
   int tiles_mi, tiles_ni, splits, kblocks_total, ksteps;
-  float* dw;          // split-K partial slices (deterministic) or the gradient itself (atomics)
-  long long ws_stride;  // elements between the slices of consecutive splits; 0 = fp32 atomics into
+  float* dw;          // split-K partial slices, or the gradient itself when K is not split
+  long long ws_stride;  // elements between the slices of consecutive splits;
                         // dw; -1 = K is not split: every element has one owner, added in place
   TapTab tab;
 };
 
-// A thread's 32 consecutive output channels of one dw row: plain 16-byte stores into this
-// split's private slice (summed later in split order by splitk_reduce), or, in the legacy
-// MCN_WGRAD_ATOMICS=1 mode, fp32 reductions straight into the gradient.
-__device__ __forceinline__ void wgrad_out32(float* o, const uint32_t (&r)[32], bool atomics,
-                                            bool owner_rmw = false) {
+// A thread's 32 consecutive output channels of one dw row: plain 16-byte stores into this split's
+// private slice (summed later in split order by splitk_reduce), or — K not split, every element has
+// one owner in the grid — a read-modify-write of the gradient itself.  No floating-point atomics.
+__device__ __forceinline__ void wgrad_out32(float* o, const uint32_t (&r)[32], bool owner_rmw = false) {
   if (owner_rmw) {
-    // un-split K: this thread is the only writer of these elements in the whole grid
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       float4 v = *reinterpret_cast<float4*>(o + j);
@@ -1033,11 +1031,6 @@ __device__ __forceinline__ void wgrad_out32(float* o, const uint32_t (&r)[32], b
       v.w += __uint_as_float(r[j + 3]);
       *reinterpret_cast<float4*>(o + j) = v;
     }
-  } else if (atomics) {
-#pragma unroll
-    for (int j = 0; j < 32; j += 4)
-      ptx::red_add_v4(o + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                      __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
   } else {
 #pragma unroll
     for (int j = 0; j < 32; j += 4)
@@ -1207,18 +1200,16 @@ wgrad_kernel(const __grid_constant__ WgradArgs args) {
       ptx::tmem_ld_wait();
       if (ci >= args.cin) continue;
       const int co0 = ni * args.block_n + c0;
-      const bool atomics = args.ws_stride == 0;
       const bool rmw = args.ws_stride < 0;      // splits == 1: add straight into the gradient
       float* o = args.dw + (rmw ? 0 : static_cast<long long>(split) * args.ws_stride) +
                  (static_cast<long long>(tap) * args.cin + ci) * args.cout + co0;
       if ((args.cout & 3) == 0 && co0 + 32 <= args.cout) {
-        wgrad_out32(o, r, atomics, rmw);
+        wgrad_out32(o, r, rmw);
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           if (co0 + j < args.cout) {
-            if (atomics) atomicAdd(o + j, __uint_as_float(r[j]));
-            else if (rmw) o[j] += __uint_as_float(r[j]);
+            if (rmw) o[j] += __uint_as_float(r[j]);
             else o[j] = __uint_as_float(r[j]);
           }
       }
@@ -1254,7 +1245,7 @@ constexpr int kWhMaxAcc = 8;
 struct WgradHaloArgs {
   CUtensorMap mapX;    // box (64 ch, hwb, box_h, 1)
   CUtensorMap mapDy;   // box (64 ch, 8, 16, 1)
-  float* dw;           // split-K slices (ws_stride > 0) or the gradient (atomics)
+  float* dw;           // split-K slices (ws_stride > 0)
   long long ws_stride;
   int n_acc, block_n, nb_atoms, a_atoms, a_box_bytes, a_stride, stages, tmem_cols;
   int hwb, tiles_w, tiles_h, tiles_total, units_ci, units_co, groups, splits;
@@ -1395,7 +1386,7 @@ wgrad_halo_kernel(const __grid_constant__ WgradHaloArgs args) {
         if (co0 >= args.cout) continue;
         float* o = args.dw + static_cast<long long>(split) * args.ws_stride +
                    (static_cast<long long>(tap) * args.cin + ci) * args.cout + co0;
-        wgrad_out32(o, r, args.ws_stride == 0);
+        wgrad_out32(o, r);
       }
     }
   }
@@ -1742,17 +1733,15 @@ stem_wgrad_kernel(const __grid_constant__ StemArgs args) {
                                static_cast<uint32_t>(mt * args.e.block_n + c0), r);
         ptx::tmem_ld_wait();
         if (c0 >= args.cout) continue;
-        const bool atomics = args.ws_stride == 0;
         if (!ok) {
           // rows of the widening tap / K padding carry no gradient: the slice still needs defined
           // values there because splitk_reduce sums whole slices
-          if (atomics) continue;
 #pragma unroll
           for (int j = 0; j < 32; ++j) r[j] = 0u;
         }
         float* o = args.dw + static_cast<long long>(split) * args.ws_stride +
                    static_cast<long long>(k) * args.cout + c0;
-        wgrad_out32(o, r, atomics);
+        wgrad_out32(o, r);
       }
     }
   }
@@ -1933,16 +1922,7 @@ int attach_xs(EpiArgs* e, int tiles_m, int tiles_n) {
 }
 
 // Deterministic split-K: every split writes its partial dw into a private slice of the workspace
-// and splitk_reduce sums the slices in split order.  MCN_WGRAD_ATOMICS=1 selects the old fp32
-// atomics (A/B timing only; run-to-run results then differ in the low bits).
-bool wgrad_atomics() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MCN_WGRAD_ATOMICS");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v != 0;
-}
+// and splitk_reduce sums the slices in split order.
 struct SplitPlan {
   float* base;         // first slice (nullptr in query / atomics mode)
   long long stride;    // elements per slice
@@ -1955,10 +1935,6 @@ int plan_splits(long long n, int want, SplitPlan* sp, long long* query, const ch
   sp->base = nullptr;
   if (query != nullptr) {
     *query = kWsSplitOff + static_cast<long long>(want) * sp->stride * 4;
-    return MCN_OK;
-  }
-  if (wgrad_atomics()) {
-    sp->stride = 0;
     return MCN_OK;
   }
   const Workspace w = current_workspace();
@@ -2688,7 +2664,7 @@ static int wgrad_tc_impl(const mcn_conv_desc* d, const void* x, const void* dy, 
   sp.base = nullptr;
   sp.stride = 0;
   sp.splits = 1;
-  if (a.splits == 1 && !wgrad_atomics()) {
+  if (a.splits == 1) {
     if (query != nullptr) {
       *query = kWsMinBytes;
       return MCN_OK;

@@ -218,10 +218,6 @@ __device__ __forceinline__ void ld_global_v8(const void* p, uint32_t (&v)[8]) {
                : "l"(p)
                : "memory");
 }
-__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
-               : "memory");
-}
 
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor (sm_100 "version 1"): 128-byte swizzle.

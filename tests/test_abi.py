@@ -69,6 +69,10 @@ def test_ctypes_table_matches_header(built_lib):
 def test_sass_is_blackwell_native(built_lib):
     """tcgen05 / TMA evidence in the shipped binary (B200_PROFILING.md mnemonics)."""
     sass = subprocess.check_output(["cuobjdump", "-sass", built_lib]).decode()
-    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "UTMALDG.4D.IM2COL"):
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "UTMALDG.4D.IM2COL", "UTMASTG", "UTMAREDG"):
         assert mnemonic in sass, mnemonic
     assert "HMMA.16816" not in sass      # no legacy mma.sync path
+    # determinism: no floating-point atomic / reduction instruction anywhere in the library (the
+    # exact accumulators of xsum.cuh use 64-bit integer atomics; bf16 accumulation is TMA reduce-add)
+    import re
+    assert not re.search(r"(ATOMG|REDG|ATOM|RED)\.E\.ADD\.F(16|32|64)", sass)
