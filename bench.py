@@ -201,6 +201,13 @@ def run_reference(args):
 def launch_work(name, args, esz):
     """Algorithmic (bytes, flops) of one libmcn launch from its resolved argument tuple — the
     per-unit figures of SURVEY 8(d) / DESIGN.md section 4 times the units the launch processes."""
+    if name == "mcn_conv2d_dgrad_tc_bnred":
+        # the dgrad's own bytes + one read of the BN input (the reduction pass it replaces read 2 tensors)
+        d = args[0]._obj
+        m = d.N * d.Ho * d.Wo
+        flops = 2.0 * m * d.kh * d.kw * d.Cin * d.Cout
+        byt = esz * (2 * d.N * d.H * d.W * d.Cin + m * d.Cout) + esz * d.kh * d.kw * d.Cin * d.Cout
+        return byt, flops
     if name in ("mcn_conv2d_fprop_tc", "mcn_conv2d_fprop_tc_stats", "mcn_conv2d_dgrad_tc",
                 "mcn_conv2d_wgrad_tc", "mcn_conv2d_fprop_direct", "mcn_conv2d_dgrad_direct",
                 "mcn_conv2d_wgrad_direct"):
@@ -257,6 +264,7 @@ KERNEL_OF = {
     "mcn_conv2d_fprop_tc": "conv_tc (gemm_conv_kernel / halo_conv_kernel: fprop + dgrad)",
     "mcn_conv2d_fprop_tc_stats": "conv_tc (gemm_conv_kernel / halo_conv_kernel: fprop + dgrad)",
     "mcn_conv2d_dgrad_tc": "conv_tc (gemm_conv_kernel / halo_conv_kernel: fprop + dgrad)",
+    "mcn_conv2d_dgrad_tc_bnred": "conv_tc (gemm_conv_kernel / halo_conv_kernel: fprop + dgrad)",
     "mcn_conv2d_wgrad_tc": "wgrad_tc (wgrad_kernel / wgrad_halo_kernel + splitk_reduce)",
     "mcn_stem_conv_fprop": "stem (stem_fprop_kernel / stem_wgrad_kernel)",
     "mcn_stem_conv_wgrad": "stem (stem_fprop_kernel / stem_wgrad_kernel)",
@@ -422,11 +430,16 @@ def main():
     barrier()
     t0 = time.perf_counter()
     eng.prefetch_inputs(X=X, Y=Y)
+    e2e_losses = []
     for i in range(args.steps):
         eng._consume_prefetched()
         if i + 1 < args.steps:
             eng.prefetch_inputs(X=X, Y=Y)
-        eng.train_step(fetch_loss=True)
+        eng.train_step(fetch_loss=False)
+        eng.enqueue_loss_read()                  # D2H of this step's loss, asynchronous
+        if i > 0:
+            e2e_losses.append(eng.pop_loss())    # the loss of step i-1, read while step i runs
+    e2e_losses.append(eng.pop_loss())
     barrier()
     ms_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
     stage("end-to-end region done: %.2f ms/step" % ms_e2e)
@@ -536,7 +549,11 @@ def main():
                                       % (sum(len(v) for v in eng._bucket_ready.values()), len(eng._bucket_tail)))},
         "e2e": {"value": gb / (ms_e2e * 1e-3), "unit": "img/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(X.numel() * X.element_size() + Y.numel() * Y.element_size() + 64),
-                "d2h_bytes_per_step": 48},
+                "d2h_bytes_per_step": 48,
+                "pipeline": "batch i+1 uploads on a copy stream while step i runs; the loss of step i is "
+                            "copied to pinned memory behind the step and read by the host while step "
+                            "i+1 runs (Engine.enqueue_loss_read / pop_loss): every step's loss is read",
+                "losses_read": len(e2e_losses), "last_loss": e2e_losses[-1] if e2e_losses else None},
         "gpu_launches": eager_launches * args.steps,
         "launches_counted_by_library": L.launch_count() - launches0,
         "final_loss": loss,

@@ -171,6 +171,21 @@ int mcn_bn_apply_stats(int dtype, const void* x, long long rows, int C, const do
                        const float* beta, const void* residual, int act, float act_alpha, void* y,
                        float* save_mean, float* save_invstd, float* moving_mean,
                        float* moving_var, void* stream);
+/* Backward reduction fused into the dgrad that PRODUCES the BN output's gradient (the conv consuming
+ * the BN+ReLU output): stride-1 bf16 dgrad with dx = d(loss)/d(BN output), plus, from the same
+ * epilogue tile, sums[c] += sum dz and sums[C + c] += sum dz*x over all pixels, where x = bn_x is
+ * the BN INPUT (same shape as dx), dz = dx * act'(x*gamma*invstd + beta - mean*gamma*invstd), act =
+ * MCN_ACT_NONE or MCN_ACT_RELU (the forward pass's own constants: same fmaf, same mask).  sums is an
+ * fp64 [2*C] accumulator (zero it first; exact, order-independent like the forward statistics).
+ * mcn_bn_bwd_finalize turns it into what mcn_bn_bwd_apply (and dbeta / dgamma) expect:
+ * sum_dz += S1, sum_dz_xhat += invstd*(S2 - mean*S1).  Replaces mcn_bn_bwd_reduce for that layer. */
+int mcn_conv2d_dgrad_bnred_supported(const mcn_conv_desc* d, int a_mode);
+int mcn_conv2d_dgrad_tc_bnred(const mcn_conv_desc* d, const void* dy, const void* w_hwio, void* dx,
+                              int a_mode, const void* bn_x, const float* mean, const float* invstd,
+                              const float* gamma, const float* beta, int act, double* sums,
+                              void* stream);
+int mcn_bn_bwd_finalize(const double* sums, const float* mean, const float* invstd, int C,
+                        float* sum_dz, float* sum_dz_xhat, void* stream);
 /* inference mode: y = act(gamma*(x-mean)/sqrt(var+eps)+beta [+ residual]) */
 int mcn_bn_infer(int dtype, const void* x, long long rows, int C, const float* mean,
                  const float* var, float eps, const float* gamma, const float* beta,

@@ -1158,6 +1158,27 @@ extern "C" int mcn_bn_bwd_reduce(int dtype, const void* dy, const void* x, const
   return after_launch("bn_bwd_reduce");
 }
 
+// Backward sums taken in a dgrad epilogue (mcn_conv2d_dgrad_tc_bnred) -> the two vectors the backward
+// apply pass (and dbeta / dgamma) want: sum_dz += S1, sum_dz_xhat += invstd * (S2 - mean * S1), in fp64.
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ mean,
+                                       const float* __restrict__ invstd, int C, float* __restrict__ sum_dz,
+                                       float* __restrict__ sum_dz_xhat) {
+  MCN_PDL_PROLOGUE();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double s1 = sums[c], s2 = sums[C + c];
+  sum_dz[c] += static_cast<float>(s1);
+  sum_dz_xhat[c] += static_cast<float>(static_cast<double>(invstd[c]) * (s2 - static_cast<double>(mean[c]) * s1));
+}
+
+extern "C" int mcn_bn_bwd_finalize(const double* sums, const float* mean, const float* invstd, int C,
+                                   float* sum_dz, float* sum_dz_xhat, void* stream) {
+  MCN_REQUIRE(sums && mean && invstd && sum_dz && sum_dz_xhat && C > 0, "bn_bwd_finalize: bad argument");
+  ::mcn::launch(bn_bwd_finalize_kernel, (C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream), sums, mean,
+                invstd, C, sum_dz, sum_dz_xhat);
+  return after_launch("bn_bwd_finalize");
+}
+
 template <typename T>
 static void launch_bwd_apply_runs(unsigned grid, cudaStream_t st, const void* dy, const void* x,
                                   const void* y, long long nvec, int cv, const float* mean,

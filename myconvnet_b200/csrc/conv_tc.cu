@@ -137,6 +137,13 @@ struct EpiArgs {
   int debug;   // bit0: skip stores, bit2: skip TMEM loads (timing experiments, direct epilogue only)
   int stg_bufs;    // TMA-store epilogue: 4 KB staging tiles per epilogue warp (1 or 2)
   int out_rank4;   // TMA-store epilogue: the output map is (C, W, H, N) instead of [M, C]
+  // fused batch-norm BACKWARD reduction (dgrad whose output is the gradient of a BN+ReLU output):
+  // stats then receives [sum dz | sum dz*x] with dz = dy * relu'(x*sc + sf), x = the BN input
+  int red;                 // 0 off; otherwise 1 + activation code (1 = none, 2 = relu)
+  const float* red_mean;   // saved mean / invstd of the forward pass, gamma / beta (may be NULL)
+  const float* red_invstd;
+  const float* red_gamma;
+  const float* red_beta;
 };
 
 // Fused BN statistics (conv -> BN): the epilogue already holds every output element in
@@ -379,13 +386,19 @@ struct OutTile {   // coordinates of a warp's 32-row slab: 2-D map (channel, c1)
   int c1, c2, c3;
 };
 
-template <bool kStats>
+// kMode: 0 store only, 1 + forward BN statistics (sum y, sum y^2), 2 + backward BN reduction: the
+// tile of the BN input x that matches this output tile arrives by TMA (xmap -> xbuf, xbar) and the
+// column pass accumulates sum dz and sum dz*x.
+template <int kMode>
 __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& e, const CUtensorMap* omap,
                                                   const OutTile& o, uint32_t tmem_acc, int quad,
                                                   int lane, bool valid, int n_t,
                                                   uint64_t* tmem_full_bar, uint32_t tph,
                                                   uint64_t* tmem_empty_bar, uint8_t* stg, int& stg_i,
-                                                  float* stat_acc) {
+                                                  float* stat_acc, const CUtensorMap* xmap = nullptr,
+                                                  uint8_t* xbuf = nullptr, uint64_t* xbar = nullptr,
+                                                  uint32_t* xph = nullptr) {
+  constexpr bool kStats = kMode != 0;
 #ifdef MCN_ROLE_TIMING
   const long long rt_w0 = clock64();
 #endif
@@ -410,6 +423,12 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& e, const CUtens
     }
     const int col0 = n_t * e.block_n + c0;
     if (col0 >= e.n_total) continue;   // warp-uniform (n_total % 64 == 0: a chunk is whole or absent)
+    if (kMode == 2 && lane == 0) {
+      // the x tile of this chunk (the previous chunk's column pass ended with a __syncwarp)
+      ptx::mbar_expect_tx(xbar, kStgBytes);
+      if (e.out_rank4) ptx::tma_load_4d(xmap, xbar, xbuf, col0, o.c1, o.c2, o.c3);
+      else ptx::tma_load_2d(xmap, xbar, xbuf, col0, o.c1);
+    }
     uint32_t v[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
@@ -447,14 +466,47 @@ __device__ __forceinline__ void epilogue_tile_tma(const EpiArgs& e, const CUtens
       const uint32_t* bw = reinterpret_cast<const uint32_t*>(buf);
       const int wq = lane >> 2, wr = lane & 3;
       float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+      if (kMode == 2) {
+        // dz = dy * act'(x*sc + sf) with the forward pass's own constants (same fmaf, same sign)
+        const int ch = col0 + 2 * lane;
+        float sca = 1.f, scb = 1.f, sfa = 0.f, sfb = 0.f;
+        const bool relu = e.red == 2;
+        if (relu) {
+          const float ia = e.red_invstd[ch], ib = e.red_invstd[ch + 1];
+          sca = (e.red_gamma ? e.red_gamma[ch] : 1.f) * ia;
+          scb = (e.red_gamma ? e.red_gamma[ch + 1] : 1.f) * ib;
+          sfa = (e.red_beta ? e.red_beta[ch] : 0.f) - e.red_mean[ch] * sca;
+          sfb = (e.red_beta ? e.red_beta[ch + 1] : 0.f) - e.red_mean[ch + 1] * scb;
+        }
+        ptx::mbar_wait(xbar, *xph);
+        *xph ^= 1u;
+        const uint32_t* xw = reinterpret_cast<const uint32_t*>(xbuf);
 #pragma unroll
-      for (int rr = 0; rr < 32; ++rr) {
-        const uint32_t w = bw[rr * 32 + (((wq ^ (rr & 7)) << 2) | wr)];
-        const float lo = __uint_as_float(w << 16), hi = __uint_as_float(w & 0xFFFF0000u);
-        s1a += lo;
-        s1b += hi;
-        s2a = fmaf(lo, lo, s2a);
-        s2b = fmaf(hi, hi, s2b);
+        for (int rr = 0; rr < 32; ++rr) {
+          const int idx = rr * 32 + (((wq ^ (rr & 7)) << 2) | wr);
+          const uint32_t w = bw[idx], xx = xw[idx];
+          const float xlo = __uint_as_float(xx << 16), xhi = __uint_as_float(xx & 0xFFFF0000u);
+          float lo = __uint_as_float(w << 16), hi = __uint_as_float(w & 0xFFFF0000u);
+          if (relu) {
+            lo = fmaf(xlo, sca, sfa) > 0.f ? lo : 0.f;
+            hi = fmaf(xhi, scb, sfb) > 0.f ? hi : 0.f;
+          }
+          s1a += lo;
+          s1b += hi;
+          s2a = fmaf(lo, xlo, s2a);
+          s2b = fmaf(hi, xhi, s2b);
+        }
+        __syncwarp();   // every lane is done with xbuf before lane 0 refills it
+      } else {
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr) {
+          const uint32_t w = bw[rr * 32 + (((wq ^ (rr & 7)) << 2) | wr)];
+          const float lo = __uint_as_float(w << 16), hi = __uint_as_float(w & 0xFFFF0000u);
+          s1a += lo;
+          s1b += hi;
+          s2a = fmaf(lo, lo, s2a);
+          s2b = fmaf(hi, hi, s2b);
+        }
       }
       float2* a1 = reinterpret_cast<float2*>(stat_acc + c0 + 2 * lane);
       float2* a2 = reinterpret_cast<float2*>(stat_acc + 256 + c0 + 2 * lane);
@@ -475,6 +527,7 @@ struct GemmConvArgs {
   CUtensorMap mapA[4];
   CUtensorMap mapB;
   CUtensorMap mapOut;   // TMA-store epilogue: [M, Cout] bf16, box 64 x 32
+  CUtensorMap mapRed;   // fused BN-backward reduction: the BN input x, same geometry as mapOut
   TileGeom g;
   int taps, k_chunks, ksteps_last, block_n, stages, tiles_n, tmem_cols, total_tiles;
   int b_stationary;   // the CTA's whole weight slab (all taps / k-chunks of its n-tile) stays in smem
@@ -510,7 +563,9 @@ gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
   const int k_iters = args.taps * args.k_chunks;
   uint8_t* smemBs = smem + static_cast<size_t>(stages) * stage_bytes;
   uint8_t* stg_all = smemBs + (bstat ? static_cast<size_t>(k_iters) * b_bytes : 0);   // 1024-aligned
-  uint8_t* tail = stg_all + (kTma ? static_cast<size_t>(4 * args.e.stg_bufs) * kStgBytes : 0);
+  uint8_t* xbuf_all = stg_all + (kTma ? static_cast<size_t>(4 * args.e.stg_bufs) * kStgBytes : 0);
+  uint8_t* tail = xbuf_all + ((kTma && args.e.red) ? static_cast<size_t>(4) * kStgBytes : 0);
+  uint64_t* xbar_all = reinterpret_cast<uint64_t*>(tail + 464);   // [4], one per epilogue warp
   uint64_t* full = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty = full + stages;
   uint64_t* tmem_full = empty + stages;     // [2]
@@ -533,6 +588,8 @@ gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
       ptx::mbar_init(&tmem_empty[b], 4);   // one arrival per epilogue warp
     }
     ptx::mbar_init(bstat_bar, 1);
+    for (int i = 0; i < 4; ++i) ptx::mbar_init(&xbar_all[i], 1);
+    if (kTma && args.e.red) ptx::prefetch_tmap(&args.mapRed);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -672,6 +729,7 @@ gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
     int* stat_flag = reinterpret_cast<int*>(tail + kBarRegionBytes - 16);
     uint8_t* stg = stg_all + static_cast<size_t>(quad * args.e.stg_bufs) * kStgBytes;
     int stg_i = 0;
+    uint32_t xph = 0;
     int lt = 0, cur_nt = -1, pending = 0;
     for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x, ++lt) {
       const int buf = lt & 1;
@@ -689,14 +747,17 @@ gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
         const long long m0 = static_cast<long long>(tile_id / args.tiles_n) * 128;
         const bool valid = m0 + row < args.g.m_total;
         const OutTile o{static_cast<int>(m0) + quad * 32, 0, 0};
-        if (stats)
-          epilogue_tile_tma<true>(args.e, &args.mapOut, o, tmem_base + static_cast<uint32_t>(buf * args.e.block_n),
-                                  quad, lane, valid, n_t, &tmem_full[buf], tph, &tmem_empty[buf], stg, stg_i,
-                                  stat_acc);
+        const uint32_t tacc = tmem_base + static_cast<uint32_t>(buf * args.e.block_n);
+        if (args.e.red)
+          epilogue_tile_tma<2>(args.e, &args.mapOut, o, tacc, quad, lane, valid, n_t, &tmem_full[buf], tph,
+                               &tmem_empty[buf], stg, stg_i, stat_acc, &args.mapRed,
+                               xbuf_all + static_cast<size_t>(quad) * kStgBytes, &xbar_all[quad], &xph);
+        else if (stats)
+          epilogue_tile_tma<1>(args.e, &args.mapOut, o, tacc, quad, lane, valid, n_t, &tmem_full[buf], tph,
+                               &tmem_empty[buf], stg, stg_i, stat_acc);
         else
-          epilogue_tile_tma<false>(args.e, &args.mapOut, o, tmem_base + static_cast<uint32_t>(buf * args.e.block_n),
-                                   quad, lane, valid, n_t, &tmem_full[buf], tph, &tmem_empty[buf], stg, stg_i,
-                                   stat_acc);
+          epilogue_tile_tma<0>(args.e, &args.mapOut, o, tacc, quad, lane, valid, n_t, &tmem_full[buf], tph,
+                               &tmem_empty[buf], stg, stg_i, stat_acc);
       } else {
         const PixelTile tile = decode_tile(args.g, tile_id / args.tiles_n);
         int n, p, q;
@@ -733,6 +794,7 @@ struct HaloArgs {
   CUtensorMap mapA;
   CUtensorMap mapB;
   CUtensorMap mapOut;    // TMA-store epilogue: (C, W, H, N) bf16, box 64 x 8 x 4 x 1
+  CUtensorMap mapRed;    // fused BN-backward reduction: the BN input x, same geometry as mapOut
   EpiArgs e;
   int taps, k_chunks, tiles_n, tmem_cols, total_tiles;
   int tiles_w, tiles_h;
@@ -758,7 +820,9 @@ halo_conv_kernel(const __grid_constant__ HaloArgs args) {
   uint8_t* smemA = smem;
   uint8_t* smemB = smem + static_cast<size_t>(args.a_stages) * args.halo_stride;
   uint8_t* stg_all = smemB + static_cast<size_t>(nb_slots) * b_bytes;   // 1024-aligned
-  uint8_t* tail = stg_all + (kTma ? static_cast<size_t>(4 * args.e.stg_bufs) * kStgBytes : 0);
+  uint8_t* xbuf_all = stg_all + (kTma ? static_cast<size_t>(4 * args.e.stg_bufs) * kStgBytes : 0);
+  uint8_t* tail = xbuf_all + ((kTma && args.e.red) ? static_cast<size_t>(4) * kStgBytes : 0);
+  uint64_t* xbar_all = reinterpret_cast<uint64_t*>(tail + 464);   // [4], one per epilogue warp
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
   uint64_t* full_a = bars;
   uint64_t* empty_a = full_a + args.a_stages;
@@ -786,6 +850,8 @@ halo_conv_kernel(const __grid_constant__ HaloArgs args) {
       ptx::mbar_init(&tmem_full[b], 1);
       ptx::mbar_init(&tmem_empty[b], 4);
     }
+    for (int i = 0; i < 4; ++i) ptx::mbar_init(&xbar_all[i], 1);
+    if (kTma && args.e.red) ptx::prefetch_tmap(&args.mapRed);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -952,6 +1018,7 @@ halo_conv_kernel(const __grid_constant__ HaloArgs args) {
     int* stat_flag = reinterpret_cast<int*>(tail + kBarRegionBytes - 16);
     uint8_t* stg = stg_all + static_cast<size_t>(quad * args.e.stg_bufs) * kStgBytes;
     int stg_i = 0;
+    uint32_t xph = 0;
     int lt = 0, cur_nt = -1, pending = 0;
     for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x, ++lt) {
       const int buf = lt & 1;
@@ -973,14 +1040,17 @@ halo_conv_kernel(const __grid_constant__ HaloArgs args) {
       const bool valid = p < args.Ho && q < args.Wo;
       if (kTma) {
         const OutTile o{w0, h0 + quad * 4, n};   // this warp's 4 output rows x 8 columns
-        if (stats)
-          epilogue_tile_tma<true>(args.e, &args.mapOut, o, tmem_base + static_cast<uint32_t>(buf * args.e.block_n),
-                                  quad, lane, valid, n_t, &tmem_full[buf], tph, &tmem_empty[buf], stg, stg_i,
-                                  stat_acc);
+        const uint32_t tacc = tmem_base + static_cast<uint32_t>(buf * args.e.block_n);
+        if (args.e.red)
+          epilogue_tile_tma<2>(args.e, &args.mapOut, o, tacc, quad, lane, valid, n_t, &tmem_full[buf], tph,
+                               &tmem_empty[buf], stg, stg_i, stat_acc, &args.mapRed,
+                               xbuf_all + static_cast<size_t>(quad) * kStgBytes, &xbar_all[quad], &xph);
+        else if (stats)
+          epilogue_tile_tma<1>(args.e, &args.mapOut, o, tacc, quad, lane, valid, n_t, &tmem_full[buf], tph,
+                               &tmem_empty[buf], stg, stg_i, stat_acc);
         else
-          epilogue_tile_tma<false>(args.e, &args.mapOut, o, tmem_base + static_cast<uint32_t>(buf * args.e.block_n),
-                                   quad, lane, valid, n_t, &tmem_full[buf], tph, &tmem_empty[buf], stg, stg_i,
-                                   stat_acc);
+          epilogue_tile_tma<0>(args.e, &args.mapOut, o, tacc, quad, lane, valid, n_t, &tmem_full[buf], tph,
+                               &tmem_empty[buf], stg, stg_i, stat_acc);
       } else {
         const long long off = valid ? (n * args.out_sn + p * args.out_sh + q * args.out_sw) : 0;
         epilogue_tile(args.e, tmem_base + static_cast<uint32_t>(buf * args.e.block_n), quad, lane, valid,
@@ -1953,11 +2023,31 @@ int plan_splits(long long n, int want, SplitPlan* sp, long long* query, const ch
   return MCN_OK;
 }
 
+// Fused batch-norm backward reduction riding on a dgrad launch (mcn_conv2d_dgrad_tc_bnred).
+struct BnRed {
+  const void* x;   // the BN input (= the producing conv's output), same shape as dx
+  const float *mean, *invstd, *gamma, *beta;
+  int act;         // MCN_ACT_NONE or MCN_ACT_RELU
+  double* sums;    // [2*C]: += sum dz | sum dz*x
+};
+void attach_red(EpiArgs* e, const BnRed* red) {
+  e->red = 0;
+  if (red == nullptr) return;
+  e->stats = red->sums;
+  e->red = red->act == MCN_ACT_RELU ? 2 : 1;
+  e->red_mean = red->mean;
+  e->red_invstd = red->invstd;
+  e->red_gamma = red->gamma;
+  e->red_beta = red->beta;
+}
+
 // dense_out: the output is a plain [m_total, n_total] matrix whose row order is the tile order (1x1
 // convolutions and the im2col feed) — the precondition of the TMA-store epilogue.
-int launch_gemm_conv(GemmConvArgs& a, int tiles_m, bool dense_out, cudaStream_t st) {
+int launch_gemm_conv(GemmConvArgs& a, int tiles_m, bool dense_out, cudaStream_t st,
+                     const BnRed* red = nullptr) {
   a.e.block_n = a.block_n;
   a.total_tiles = tiles_m * a.tiles_n;
+  attach_red(&a.e, red);
   {
     const int rc = attach_xs(&a.e, tiles_m, a.tiles_n);
     if (rc) return rc;
@@ -1987,6 +2077,14 @@ int launch_gemm_conv(GemmConvArgs& a, int tiles_m, bool dense_out, cudaStream_t 
     const int rc = encode_matrix(&a.mapOut, a.e.out, a.g.m_total, a.e.n_total, 32);
     if (rc) return rc;
   }
+  if (red != nullptr) {
+    if (!tma || a.e.accumulate) {
+      set_error("dgrad_tc_bnred: this geometry has no TMA-store epilogue (mcn_conv2d_dgrad_bnred_supported)");
+      return MCN_EINVAL;
+    }
+    const int rc = encode_matrix(&a.mapRed, red->x, a.g.m_total, a.e.n_total, 32);
+    if (rc) return rc;
+  }
   const int grid_n = std::min(a.total_tiles, num_sms());
   // weight-stationary when the CTA's weight slab is small and it sees one n-tile only
   static int ws_enabled = -1;
@@ -2000,7 +2098,7 @@ int launch_gemm_conv(GemmConvArgs& a, int tiles_m, bool dense_out, cudaStream_t 
   const uint32_t stage_bytes = a.b_stationary ? kABytes : kABytes + a.block_n * 128;
   // one persistent CTA per SM: the whole shared memory is the TMA ring, minus the epilogue's share
   auto fixed_for = [&](int bufs) {
-    const size_t epi = tma ? static_cast<size_t>(4 * bufs) * kStgBytes + (a.e.stats ? kStatAccBytes : 0)
+    const size_t epi = tma ? static_cast<size_t>(4 * bufs + (red ? 4 : 0)) * kStgBytes + (a.e.stats ? kStatAccBytes : 0)
                            : (a.e.stats ? kEpiStageBytes + kStatAccBytes : 0);
     return kBarRegionBytes + epi + 1024 + (a.b_stationary ? b_slab : 0);
   };
@@ -2035,6 +2133,8 @@ int launch_gemm_conv(GemmConvArgs& a, int tiles_m, bool dense_out, cudaStream_t 
 
 // Halo mode (a_mode 2): stride-1 k x k convolution whose spatial size makes 16x8 tiles efficient.
 // `flip` selects the dgrad tap order (correlation with mirrored taps).
+constexpr double kHaloMinEff = 0.85;
+constexpr int kHaloMinHw = 48 * 48;
 bool halo_eligible(int cin, int kh, int kw, int sh, int sw, int dh, int dw, int Ho, int Wo) {
   if (sh != 1 || sw != 1 || (kh == 1 && kw == 1) || cin % 64 != 0 || kh * kw > kMaxTaps) return false;
   const int hwb = 8 + (kw - 1) * dw, hhb = 16 + (kh - 1) * dh;
@@ -2043,16 +2143,27 @@ bool halo_eligible(int cin, int kh, int kw, int sh, int sw, int dh, int dw, int 
   // (profiles/r01_halo_vs_im2col.txt): the halo feed wins on the large maps (56x56: 187 -> 144 us)
   // and loses below ~48x48, where the im2col feed's exact 128-pixel tiles matter more.
   const double eff = (double)(Ho * Wo) / ((double)((Ho + 15) / 16 * 16) * ((Wo + 7) / 8 * 8));
-  return eff >= 0.85 && Ho * Wo >= 48 * 48;
+  // MCN_HALO_MIN_EFF / MCN_HALO_MIN_HW override the two thresholds (A/B; plan.py mirrors them)
+  static double min_eff = -1.0;
+  static int min_hw = -1;
+  if (min_eff < 0.0) {
+    const char* e = getenv("MCN_HALO_MIN_EFF");
+    const char* h = getenv("MCN_HALO_MIN_HW");
+    min_hw = h ? atoi(h) : kHaloMinHw;
+    min_eff = e ? atof(e) : kHaloMinEff;
+  }
+  return eff >= min_eff && Ho * Wo >= min_hw;
 }
 
 int launch_halo(const void* in, int C_in, int W_in, int H_in, int N, const void* wmat, int taps_rows,
                 int n_total, int kh, int kw, int dh, int dw, int org_h, int org_w, bool flip,
                 int Ho, int Wo, void* out, int out_f32, const float* bias, int accumulate,
-                double* stats, cudaStream_t st) {
+                double* stats, cudaStream_t st, const BnRed* red = nullptr) {
   HaloArgs a;
   std::memset(&a, 0, sizeof(a));
   a.e.stats = stats;
+  attach_red(&a.e, red);
+  stats = a.e.stats;
   int rc;
   a.hwb = 8 + (kw - 1) * dw;
   a.hhb = 16 + (kh - 1) * dh;
@@ -2100,7 +2211,14 @@ int launch_halo(const void* in, int C_in, int W_in, int H_in, int N, const void*
   a.e.out_rank4 = 1;
   a.e.stg_bufs = 2;
   if (tma && (rc = encode_nhwc(&a.mapOut, out, n_total, Wo, Ho, N, 8, 4, 1))) return rc;
-  const size_t epi_bytes = tma ? static_cast<size_t>(4 * a.e.stg_bufs) * kStgBytes + (stats ? kStatAccBytes : 0)
+  if (red != nullptr) {
+    if (!tma || accumulate) {
+      set_error("dgrad_tc_bnred: this geometry has no TMA-store epilogue (mcn_conv2d_dgrad_bnred_supported)");
+      return MCN_EINVAL;
+    }
+    if ((rc = encode_nhwc(&a.mapRed, red->x, n_total, Wo, Ho, N, 8, 4, 1))) return rc;
+  }
+  const size_t epi_bytes = tma ? static_cast<size_t>(4 * a.e.stg_bufs + (red ? 4 : 0)) * kStgBytes + (stats ? kStatAccBytes : 0)
                                : (stats ? kEpiStageBytes + kStatAccBytes : 0);
   const long long budget = static_cast<long long>(smem_optin_limit()) - 1024 - kBarRegionBytes -
                            static_cast<long long>(epi_bytes) - (long long)a.a_stages * a.halo_stride;
@@ -2290,7 +2408,8 @@ extern "C" int mcn_conv2d_fprop_tc_stats(const mcn_conv_desc* d, const void* x, 
 // to a strided view of dx — one launch per phase, no zero-insertion, no wasted MACs.
 static int dgrad_phase(const mcn_conv_desc* d, const void* dy, const void* w_hwio, void* dx,
                        int dx_dtype, int a_mode, int accumulate, int ph, int pw, bool* empty,
-                       cudaStream_t st) {
+                       cudaStream_t st,
+                       const BnRed* red = nullptr) {
   GemmConvArgs a;
   std::memset(&a, 0, sizeof(a));
   int rc;
@@ -2383,7 +2502,7 @@ static int dgrad_phase(const mcn_conv_desc* d, const void* dy, const void* w_hwi
       a.tab.dw[t] = (short)(e_w[t] - min_ew);
     }
   }
-  return launch_gemm_conv(a, tiles_m_of(a.g), pointwise || (a.g.a_mode == 1 && unit), st);
+  return launch_gemm_conv(a, tiles_m_of(a.g), pointwise || (a.g.a_mode == 1 && unit), st, red);
 }
 
 extern "C" int mcn_conv2d_dgrad_tc(const mcn_conv_desc* d, const void* dy, const void* w_hwio,
@@ -2426,6 +2545,42 @@ extern "C" int mcn_conv2d_dgrad_tc(const mcn_conv_desc* d, const void* dy, const
       if (rc) return rc;
     }
   return MCN_OK;
+}
+
+// dgrad (stride 1, bf16) whose epilogue also takes the batch-norm BACKWARD sums of the layer that
+// produced the conv's input: dx is d(loss)/d(BN output); with x = the BN input,
+// sums[c] += sum dz, sums[C + c] += sum dz*x, dz = dx * act'(x*gamma*invstd + beta - mean*gamma*invstd).
+extern "C" int mcn_conv2d_dgrad_bnred_supported(const mcn_conv_desc* d, int a_mode) {
+  if (d == nullptr || d->sh != 1 || d->sw != 1 || d->Cin % 64 != 0 || d->Cout % 8 != 0) return 0;
+  if (d->kh * d->kw > kMaxTaps || (long long)d->N * d->H * d->W >= (1LL << 31)) return 0;
+  const char* e = getenv("MCN_TMA_STORE");
+  if (e && e[0] == '0') return 0;
+  const bool pointwise = d->kh == 1 && d->kw == 1;
+  if (a_mode == 2 && halo_eligible(d->Cout, d->kh, d->kw, d->sh, d->sw, d->dh, d->dw, d->H, d->W)) return 1;
+  if (pointwise) return 1;
+  return (a_mode >= 1 && d->Cout % 64 == 0) ? 1 : 0;
+}
+
+extern "C" int mcn_conv2d_dgrad_tc_bnred(const mcn_conv_desc* d, const void* dy, const void* w_hwio,
+                                         void* dx, int a_mode, const void* bn_x, const float* mean,
+                                         const float* invstd, const float* gamma, const float* beta,
+                                         int act, double* sums, void* stream) {
+  MCN_REQUIRE(d && dy && w_hwio && dx && bn_x && mean && invstd && sums, "dgrad_tc_bnred: null argument");
+  MCN_REQUIRE(act == MCN_ACT_NONE || act == MCN_ACT_RELU, "dgrad_tc_bnred: activation %d not supported", act);
+  MCN_REQUIRE(mcn_conv2d_dgrad_bnred_supported(d, a_mode), "dgrad_tc_bnred: geometry not supported");
+  MCN_REQUIRE(reinterpret_cast<uintptr_t>(dx) % 16 == 0 && reinterpret_cast<uintptr_t>(bn_x) % 16 == 0,
+              "dgrad_tc_bnred: dx and bn_x must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const BnRed red{bn_x, mean, invstd, gamma, beta, act, sums};
+  if (a_mode == 2) {
+    if (halo_eligible(d->Cout, d->kh, d->kw, d->sh, d->sw, d->dh, d->dw, d->H, d->W))
+      return launch_halo(dy, d->Cout, d->Wo, d->Ho, d->N, w_hwio, d->Cin, d->Cin, d->kh, d->kw, d->dh,
+                         d->dw, d->pad_t - (d->kh - 1) * d->dh, d->pad_l - (d->kw - 1) * d->dw, true,
+                         d->H, d->W, dx, 0, nullptr, 0, nullptr, st, &red);
+    a_mode = 1;
+  }
+  bool empty = false;
+  return dgrad_phase(d, dy, w_hwio, dx, MCN_BF16, a_mode, 0, 0, 0, &empty, st, &red);
 }
 
 // Halo wgrad: returns 1 when the geometry is eligible and the launch was issued, 0 when the

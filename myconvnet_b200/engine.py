@@ -10,6 +10,7 @@ all-reduced per layer (synchronised BN) instead of the reference's tower-after-t
 torch is used for device memory, streams, CUDA-graph capture and torch.distributed only: every
 arithmetic kernel on the step is a libmcn launch.
 """
+import collections
 import ctypes
 import os
 import sys
@@ -97,6 +98,7 @@ class Engine(object):
         self.grad_threshold = None if gt is None else float(gt)
         self.random_seed = int(self.kw.get("random_seed", seed))
         self._pin_rings = {}
+        self._loss_queue = collections.deque()     # enqueue_loss_read() -> pop_loss(), at most 3 pending
         self.hp_dev = self.view(Ptr(p.b_hp), 16, torch.float32)
         self._ws = _lib.ensure_workspace(self._workspace_bytes(), self.device)
         self._build_opt_table()
@@ -678,6 +680,34 @@ class Engine(object):
         v = self.view(p.loss_slots["loss"], 6, torch.int64).cpu().numpy().reshape(2, 3)
         data = _lib.xsum_value(v[0]) / node.attrs["rows"]
         return data + _lib.xsum_value(v[1])
+
+    def enqueue_loss_read(self):
+        """Asynchronous form of read_loss(): copies this step's loss accumulators into a pinned ring
+        slot on the current stream (before the next step's zero-fill, by stream order) and returns at
+        once; pop_loss() later waits for that copy only.  An input pipeline reads the loss of step
+        i while step i+1 is already running, so the device never idles on the host's read-back."""
+        p = self.plan
+        if "loss" not in p.loss_slots:
+            return
+        n = 9 if "loss_g" in p.loss_slots else 6
+        pin = self._pinned_slot("loss", (n,), torch.int64, slots=4)
+        pin.copy_(self.view(p.loss_slots["loss"], n, torch.int64), non_blocking=True)
+        self._pinned_done("loss")
+        ring = self._pin_rings["loss"]
+        self._loss_queue.append((pin, ring["events"][ring["cur"]]))
+
+    def pop_loss(self):
+        """The oldest loss queued by enqueue_loss_read() (blocks until its copy has landed)."""
+        pin, ev = self._loss_queue.popleft()
+        ev.synchronize()
+        node = self.graph.losses[0].node
+        v = pin.numpy()
+        if v.size == 9:
+            v = v.reshape(3, 3)
+            self.last_losses = (_lib.xsum_value(v[0]) / node.attrs["rows"], _lib.xsum_value(v[1]) / node.attrs["rows"])
+            return self.last_losses[0]
+        v = v.reshape(2, 3)
+        return _lib.xsum_value(v[0]) / node.attrs["rows"] + _lib.xsum_value(v[1])
 
     def launches_per_step(self):
         return 1 + len(self._fwd) + len(self._bwd) + 1

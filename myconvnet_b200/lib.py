@@ -87,6 +87,8 @@ SIGNATURES = {
     "mcn_transpose_add_f32": "piiip",
     "mcn_peer_allreduce": "plllpipipipii",
     "mcn_xsum_decode": "pippi",
+    "mcn_conv2d_dgrad_tc_bnred": "Dpppipppppip",
+    "mcn_bn_bwd_finalize": "pppipp",
     "mcn_gn_fwd": "ipiliifpppp",
     "mcn_gn_bwd": "ippiliipppppp",
     "mcn_ws_fwd": "piifpp",
@@ -120,6 +122,8 @@ def load():
     lib.mcn_stem_conv_kpad.argtypes = [ctypes.POINTER(ConvDescC)]
     lib.mcn_debug_role_cycles.restype = ctypes.c_int
     lib.mcn_debug_role_cycles.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    lib.mcn_conv2d_dgrad_bnred_supported.restype = ctypes.c_int
+    lib.mcn_conv2d_dgrad_bnred_supported.argtypes = [ctypes.POINTER(ConvDescC), ctypes.c_int]
     lib.mcn_set_workspace.restype = ctypes.c_int
     lib.mcn_set_workspace.argtypes = [ctypes.c_void_p, ctypes.c_longlong]
     lib.mcn_workspace_min_bytes.restype = ctypes.c_longlong

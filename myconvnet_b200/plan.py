@@ -18,6 +18,9 @@ import os
 import numpy as np
 
 ALIGN = 256
+# halo_eligible() of csrc/conv_tc.cu (kHaloMinEff, kHaloMinHw): keep in step
+HALO_MIN_EFF = 0.85
+HALO_MIN_HW = 48 * 48
 DT_SIZE = {"f32": 4, "bf16": 2, "i32": 4, "f64": 8, "u8": 1}
 DT_CODE = {"f32": 0, "bf16": 1, "u8": 2}
 
@@ -340,6 +343,51 @@ class Plan(object):
 
     def pbf16t(self, v):
         return Ptr(self.b_bf16_ema if self.phase == "infer" else self.b_bf16, self.bf16t_off[v])
+
+    def _bnred_target(self, conv):
+        """The batch-norm node whose backward reduction can ride on this conv's dgrad epilogue
+        (mcn_conv2d_dgrad_tc_bnred), or None.  Conditions: the conv's input is the final output of a
+        BN(+ReLU) layer with this conv as its only consumer (so this dgrad IS the BN output's whole
+        gradient and is written, not accumulated), training statistics, no fused residual, bf16, and a
+        geometry the TMA-store epilogue covers (mirrors mcn_conv2d_dgrad_bnred_supported)."""
+        if self.cdt != "bf16" or os.environ.get("MCN_FUSE_BN_BWD", "1") == "0" \
+                or os.environ.get("MCN_TMA_STORE", "1") == "0":
+            return None
+        x = conv.inputs[0]
+        prod = x.node
+        if prod is None or x in self.keep or len(x.consumers) != 1 or x in self.g or self.keep_grads:
+            return None
+        bn = prod.attrs.get("fused_into") if prod.op == "act" else prod
+        if bn is None or bn.op != "bn" or bn.attrs.get("final") is not x or bn.attrs.get("residual") is not None:
+            return None
+        if not bn.attrs.get("update", True) or bn.attrs.get("act", 0) not in (0, 1) or "save" not in bn.attrs:
+            return None
+        if not self._tensor_needs_grad(x):
+            return None
+        a = conv.attrs
+        kh, kw, ci, co = conv.vars["w"].shape
+        if tuple(a["s"]) != (1, 1) or ci % 64 or co % 8 or bn.inputs[0].shape != x.shape:
+            return None
+        if x.size // ci >= 2 ** 31:
+            return None
+        pointwise = kh == 1 and kw == 1
+        return bn if (pointwise or (self.conv_mode >= 1 and co % 64 == 0) or self._halo_ok(conv)) else None
+
+    def _halo_ok(self, conv):
+        """halo_eligible() of csrc/conv_tc.cu for the dgrad of `conv` (dy is the halo-fed tensor)."""
+        if self.conv_mode != 2:
+            return False
+        kh, kw, ci, co = conv.vars["w"].shape
+        a = conv.attrs
+        n, h, w_, _ = conv.inputs[0].shape
+        if tuple(a["s"]) != (1, 1) or (kh == 1 and kw == 1) or co % 64 or kh * kw > 52:
+            return False
+        hwb, hhb = 8 + (kw - 1) * a["d"][1], 16 + (kh - 1) * a["d"][0]
+        if hwb > 256 or hhb > 256 or hwb * hhb * 128 > 40 * 1024:
+            return False
+        eff = (h * w_) / (((h + 15) // 16 * 16) * ((w_ + 7) // 8 * 8))
+        return eff >= float(os.environ.get("MCN_HALO_MIN_EFF", HALO_MIN_EFF)) \
+            and h * w_ >= int(os.environ.get("MCN_HALO_MIN_HW", HALO_MIN_HW))
 
     # ------------------------------------------------------------------ weight standardisation
     # convnet.py:1410-1419: w' = (w - mean_o) / (std_o + 1e-5) per output channel, inside the graph.
@@ -1134,9 +1182,25 @@ class Plan(object):
             if self._var_trains(w):
                 self.L("b", "mcn_conv2d_wgrad_tc", d, self.tbuf[x], gy, self._w_grad(node), self.conv_mode,
                        tag=node.scope + "/wgrad")
-            self.contribute(x, x.size * 2,
-                            lambda p: self.L("b", "mcn_conv2d_dgrad_tc", d, gy, self._w_bf16(node), p, 1,
-                                             self.conv_mode, 0, tag=node.scope + "/dgrad"),
+            bn = self._bnred_target(node)
+
+            def emit_dgrad(p):
+                if bn is None:
+                    self.L("b", "mcn_conv2d_dgrad_tc", d, gy, self._w_bf16(node), p, 1, self.conv_mode, 0,
+                           tag=node.scope + "/dgrad")
+                    return
+                # the BN layer feeding this conv gets its backward sums from this dgrad's epilogue
+                bx = bn.inputs[0]
+                cb = bx.shape[-1]
+                sums = self.node_buf(bn, "bwd_sums", "bn_bwd_sums:%s" % bn.scope, 2 * cb * 8, "zero")
+                bn.attrs["bwd_sums"] = sums
+                bv, sv = bn.vars, bn.attrs["save"]
+                self.L("b", "mcn_conv2d_dgrad_tc_bnred", d, gy, self._w_bf16(node), p, self.conv_mode,
+                       self.tbuf[bx], Ptr(sv), Ptr(sv, cb * 4),
+                       self.pvar(bv["gamma"]) if "gamma" in bv else NULL,
+                       self.pvar(bv["beta"]) if "beta" in bv else NULL, bn.attrs["act"], Ptr(sums),
+                       tag=node.scope + "/dgrad+bn_bwd_sums")
+            self.contribute(x, x.size * 2, emit_dgrad,
                             emit_acc=lambda p: self.L("b", "mcn_conv2d_dgrad_tc", d, gy, self._w_bf16(node), p, 1,
                                                       self.conv_mode, 1, tag=node.scope + "/dgrad+"))
         elif route == "stem":
@@ -1251,8 +1315,14 @@ class Plan(object):
             sp, scratch = self.talloc(2 * c * 4)
             self.L("b", "mcn_fill_f32", sp, 2 * c, 0.0, tag="zero")
             s1, s2 = sp, sp + c * 4
-        self.L("b", "mcn_bn_bwd_reduce", self.ccode, gy, self.tbuf[x], py, rows, c, Ptr(save),
-               Ptr(save, c * 4), pg, pbeta, act, node.attrs["alpha"], s1, s2, tag=node.scope + "/bwd_reduce")
+        fused = node.attrs.pop("bwd_sums", None)
+        if fused is not None:
+            # the dgrad that produced gy already took sum dz / sum dz*x in its epilogue
+            self.L("b", "mcn_bn_bwd_finalize", Ptr(fused), Ptr(save), Ptr(save, c * 4), c, s1, s2,
+                   tag=node.scope + "/bwd_finalize")
+        else:
+            self.L("b", "mcn_bn_bwd_reduce", self.ccode, gy, self.tbuf[x], py, rows, c, Ptr(save),
+                   Ptr(save, c * 4), pg, pbeta, act, node.attrs["alpha"], s1, s2, tag=node.scope + "/bwd_reduce")
         g1, g2, gh = s1, s2, None
         count = float(rows)
         if not node.attrs["update"]:

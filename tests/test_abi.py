@@ -59,7 +59,8 @@ def test_ctypes_table_matches_header(built_lib):
     missing = set(decls) - set(lib.SIGNATURES) - {"mcn_last_error", "mcn_version", "mcn_launch_count",
                                                         "mcn_stem_conv_kpad", "mcn_set_workspace",
                                                         "mcn_workspace_min_bytes",
-                                                        "mcn_conv2d_wgrad_workspace_bytes", "mcn_debug_role_cycles"}
+                                                        "mcn_conv2d_wgrad_workspace_bytes", "mcn_debug_role_cycles",
+                                                        "mcn_conv2d_dgrad_bnred_supported"}
     assert not missing, missing
     L = lib.load()
     assert L.mcn_version() >= 100

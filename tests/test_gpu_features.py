@@ -8,6 +8,7 @@ import pytest
 import torch
 
 from oracle import philox, tf_ops
+from tests.test_gpu_ops import desc_for
 from tests.util import build_pair, rel_l2, synthetic_batch, worst
 
 pytestmark = pytest.mark.gpu
@@ -445,3 +446,48 @@ def test_wsgn_resnet_step(have_reference_models, dtype, tol):
     # inference runs the same standardisation on the EMA weights
     p = eng.predict(X)
     assert p.shape == (batch, SMALL_NCLS) and np.isfinite(p).all() and np.allclose(p.sum(-1), 1.0, atol=1e-3)
+
+
+# ------------------------------------------------------------------ BN backward sums in the dgrad epilogue
+@pytest.mark.parametrize("act", [0, 1])
+@pytest.mark.parametrize("case", [(8, 28, 128, 256, 1), (4, 56, 64, 64, 3), (8, 14, 256, 256, 3), (3, 20, 64, 128, 3)],
+                         ids=["1x1_28_128<-256", "3x3_halo_56_64<-64", "3x3_im2col_14_256<-256", "3x3_ragged_20_64<-128"])
+def test_dgrad_with_fused_bn_backward_sums(L, case, act):
+    """mcn_conv2d_dgrad_tc_bnred + mcn_bn_bwd_finalize against the separate launches they replace
+    (mcn_conv2d_dgrad_tc, then mcn_bn_bwd_reduce on its output): dx bit-identical, the two sum vectors
+    equal up to fp32 summation order (the fused ones are exact sums of the same products), twice."""
+    n, hw, ci, co, k = case
+    lib = L.load()
+    L.ensure_workspace(64 << 20)
+    rng = np.random.default_rng(11)
+    d, ho, wo = desc_for(L, (n, hw, hw, ci), (k, k, ci, co), 1, 1, "SAME")
+    dy = dev(rng.standard_normal((n, ho, wo, co)).astype(np.float32), torch.bfloat16)
+    w_hwio = dev((rng.standard_normal((k * k, ci, co)) * 0.05).astype(np.float32), torch.bfloat16)
+    x = dev(rng.standard_normal((n, hw, hw, ci)).astype(np.float32) * 2 + 0.5, torch.bfloat16)   # the BN input
+    mean = dev(rng.standard_normal(ci).astype(np.float32) * 0.3)
+    invstd = dev(rng.uniform(0.5, 1.5, ci).astype(np.float32))
+    gamma = dev(rng.uniform(0.5, 1.5, ci).astype(np.float32))
+    beta = dev(rng.standard_normal(ci).astype(np.float32) * 0.3)
+    dx_ref = torch.empty(n, hw, hw, ci, device="cuda", dtype=torch.bfloat16)
+    L.check(lib.mcn_conv2d_dgrad_tc(d, dy.data_ptr(), w_hwio.data_ptr(), dx_ref.data_ptr(), 1, 2, 0, None))
+    s_ref = torch.zeros(2, ci, device="cuda")
+    L.check(lib.mcn_bn_bwd_reduce(1, dx_ref.data_ptr(), x.data_ptr(), None, n * hw * hw, ci, mean.data_ptr(),
+                                  invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), act, 0.0,
+                                  s_ref[0].data_ptr(), s_ref[1].data_ptr(), None))
+    assert lib.mcn_conv2d_dgrad_bnred_supported(d, 2) == 1
+    outs = []
+    for _ in range(2):
+        dx = torch.full_like(dx_ref, 3.0)
+        sums = torch.zeros(2 * ci, device="cuda", dtype=torch.float64)
+        L.check(lib.mcn_conv2d_dgrad_tc_bnred(d, dy.data_ptr(), w_hwio.data_ptr(), dx.data_ptr(), 2, x.data_ptr(),
+                                              mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
+                                              beta.data_ptr(), act, sums.data_ptr(), None))
+        s = torch.zeros(2, ci, device="cuda")
+        L.check(lib.mcn_bn_bwd_finalize(sums.data_ptr(), mean.data_ptr(), invstd.data_ptr(), ci,
+                                        s[0].data_ptr(), s[1].data_ptr(), None))
+        outs.append((dx, s))
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0][0], dx_ref)
+    scale = float(s_ref.abs().max())
+    assert float((outs[0][1] - s_ref).abs().max()) <= 2e-5 * scale + 1e-4, (outs[0][1] - s_ref).abs().max()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])

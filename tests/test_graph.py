@@ -54,7 +54,12 @@ def test_plan_fusion_and_launch_counts(r50):
     assert h["mcn_conv2d_fprop_tc_stats"] + 1 + h["mcn_bn_stats"] == 53             # +1: the stem fuses too
     assert h["mcn_conv2d_fprop_tc_stats"] >= 30 and "mcn_bn_finalize" not in h
     assert h["mcn_conv2d_wgrad_tc"] == 53
-    assert h["mcn_conv2d_dgrad_tc"] == 53                                        # no dgrad into the images
+    # no dgrad into the images; the stride-1 dgrads that produce the whole gradient of a BN+ReLU
+    # output (conv_1 / conv_2 of every unit, minus the three stride-2 3x3) also take that layer's
+    # backward sums in their epilogue, which replaces its reduction pass
+    assert h["mcn_conv2d_dgrad_tc"] + h["mcn_conv2d_dgrad_tc_bnred"] == 53
+    assert h["mcn_conv2d_dgrad_tc_bnred"] == 29 == h["mcn_bn_bwd_finalize"]
+    assert h["mcn_bn_bwd_reduce"] == 53 - 29
     assert h["mcn_bn_apply_stats"] == 53 and "mcn_act_fwd" not in h and "mcn_add_act_fwd" not in h
     # the unfused plan keeps the separate statistics pass
     hu = Plan(r50.graph, fuse_bn_stats=False).launch_histogram()
