@@ -172,8 +172,12 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;"
 // completes the n-tile's tiles_m tiles decodes just that n-tile's channels into the caller's fp64
 // sums and clears limbs and counter — no grid-wide serial tail, and the workspace is zero again
 // when the kernel ends.  `flag` is a shared-memory word visible to all epilogue threads.
+// ticket == false: an intermediate flush (every 8 tiles, bounding the length of the fp32 partial sums):
+// only the exact adds — no fence, no ticket; the tiles stay in the caller's `pending` count and the
+// next ticketed flush (whose __threadfence orders ALL of this thread's earlier adds: thread et always
+// owns the same columns) reports them.
 __device__ __forceinline__ void stats_flush(const EpiArgs& e, float* acc, int n_t, int et, int pending,
-                                            int* flag) {
+                                            int* flag, bool ticket = true) {
   epi_bar_sync();   // every warp's shared-memory sums of the finished tiles have landed
   for (int c = et; c < e.block_n; c += 128) {
     const int col = n_t * e.block_n + c;
@@ -189,6 +193,10 @@ __device__ __forceinline__ void stats_flush(const EpiArgs& e, float* acc, int n_
       xs::add(e.xs, 2 * e.n_total, col, s1);
       xs::add(e.xs, 2 * e.n_total, e.n_total + col, s2);
     }
+  }
+  if (!ticket) {
+    epi_bar_sync();   // the partial sums are cleared before any warp accumulates again
+    return;
   }
   __threadfence();   // the adds are ordered before the ticket
   epi_bar_sync();
@@ -730,18 +738,24 @@ gemm_conv_kernel(const __grid_constant__ GemmConvArgs args) {
     uint8_t* stg = stg_all + static_cast<size_t>(quad * args.e.stg_bufs) * kStgBytes;
     int stg_i = 0;
     uint32_t xph = 0;
-    int lt = 0, cur_nt = -1, pending = 0;
+    int lt = 0, cur_nt = -1, pending = 0, since = 0;
     for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x, ++lt) {
       const int buf = lt & 1;
       const uint32_t tph = static_cast<uint32_t>(lt >> 1) & 1u;
       const int n_t = tile_id % args.tiles_n;
-      if (stats && (n_t != cur_nt || pending == 8)) {
-        // also every 8 tiles: bounds the length of the fp32 partial sums (accuracy of sum x^2)
-        if (cur_nt >= 0) stats_flush(args.e, stat_acc_all, cur_nt, row, pending, stat_flag);
-        cur_nt = n_t;
-        pending = 0;
+      if (stats) {
+        if (n_t != cur_nt) {
+          if (cur_nt >= 0) stats_flush(args.e, stat_acc_all, cur_nt, row, pending, stat_flag);
+          cur_nt = n_t;
+          pending = since = 0;
+        } else if (since == 8) {
+          // every 8 tiles: bounds the length of the fp32 partial sums (accuracy of sum x^2)
+          stats_flush(args.e, stat_acc_all, cur_nt, row, pending, stat_flag, false);
+          since = 0;
+        }
       }
       ++pending;
+      ++since;
       if (kTma) {
         // the tile is 128 consecutive rows of the [M, Cout] output matrix
         const long long m0 = static_cast<long long>(tile_id / args.tiles_n) * 128;
@@ -1019,18 +1033,24 @@ halo_conv_kernel(const __grid_constant__ HaloArgs args) {
     uint8_t* stg = stg_all + static_cast<size_t>(quad * args.e.stg_bufs) * kStgBytes;
     int stg_i = 0;
     uint32_t xph = 0;
-    int lt = 0, cur_nt = -1, pending = 0;
+    int lt = 0, cur_nt = -1, pending = 0, since = 0;
     for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x, ++lt) {
       const int buf = lt & 1;
       const uint32_t tph = static_cast<uint32_t>(lt >> 1) & 1u;
       const int n_t = tile_id % args.tiles_n;
-      if (stats && (n_t != cur_nt || pending == 8)) {
-        // also every 8 tiles: bounds the length of the fp32 partial sums (accuracy of sum x^2)
-        if (cur_nt >= 0) stats_flush(args.e, stat_acc_all, cur_nt, row, pending, stat_flag);
-        cur_nt = n_t;
-        pending = 0;
+      if (stats) {
+        if (n_t != cur_nt) {
+          if (cur_nt >= 0) stats_flush(args.e, stat_acc_all, cur_nt, row, pending, stat_flag);
+          cur_nt = n_t;
+          pending = since = 0;
+        } else if (since == 8) {
+          // every 8 tiles: bounds the length of the fp32 partial sums (accuracy of sum x^2)
+          stats_flush(args.e, stat_acc_all, cur_nt, row, pending, stat_flag, false);
+          since = 0;
+        }
       }
       ++pending;
+      ++since;
       const int m = tile_id / args.tiles_n;
       const int n = m / tiles_per_img;
       const int r = m - n * tiles_per_img;
@@ -1479,6 +1499,9 @@ wgrad_halo_kernel(const __grid_constant__ WgradHaloArgs args) {
 //          one TMEM accumulator per 128 k-rows, split-K over pixel tiles, fp32 red.global at the end.
 struct StemArgs {
   CUtensorMap mapW;     // fprop: [Cout][Kpad] bf16, box 64 x Cout;  wgrad: dy [M][Cout], box 64 x 128
+  CUtensorMap mapOut;   // fprop, TMA-store epilogue (use_tma): y as [M][Cout] bf16, box 64 x 32
+  int use_tma;
+  int async_full;       // producers signal a stage through cp.async.mbarrier.arrive (on completion)
   const __nv_bfloat16* x4;
   EpiArgs e;            // fprop output / statistics
   float* dw;            // wgrad output [Kpad][Cout]: split-K slices (ws_stride > 0) or the gradient
@@ -1489,11 +1512,21 @@ struct StemArgs {
   long long m_total;
 };
 
+// One producer thread per pixel row of the tile.  (Two threads per row, the filter rows split between
+// them — eight gathering warps — measured SLOWER: stem fprop 377 -> 530 us, wgrad 238 -> 257 us; the
+// gather is not bound by its instruction stream.)
 constexpr int kStemProducers = 128;
+constexpr int kStemProducerWarps = kStemProducers / 32;
+constexpr int kStemMmaWarp = kStemProducerWarps;
+constexpr int kStemThreads = kStemProducers + 32 + 128;
 
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, bool valid) {
   const uint32_t n = valid ? 16u : 0u;   // src-size 0: the 16 bytes are zero-filled
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+// the mbarrier receives one arrival from this thread when all its cp.async issued so far have landed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(ptx::smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -1503,7 +1536,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // The filter size is a template parameter: with one warp per scheduler the gather is bound by
 // the latency of its own address arithmetic, so everything that can fold to a constant must
 // (a generic version with run-time kh / kw spent ~8k cycles per tile, mostly in integer divisions).
-template <int KH, int KW>
+template <int KH, int KW, int R0, int R1>
 __device__ __forceinline__ void stem_gather(const StemArgs& a, uint8_t* sA, int t, uint32_t m) {
   constexpr int EPR = (KW + 1) * 4, CPR = EPR / 8, RPC = 64 / EPR;
   const bool live = m < static_cast<uint32_t>(a.m_total);
@@ -1524,7 +1557,7 @@ __device__ __forceinline__ void stem_gather(const StemArgs& a, uint8_t* sA, int 
 #pragma unroll
   for (int j = 0; j < CPR; ++j) wok[j] = (w0 + 2 * j >= 0) && (w0 + 2 * j + 1 < a.W);
 #pragma unroll
-  for (int r = 0; r < KH; ++r) {
+  for (int r = R0; r < R1; ++r) {
     const int h = h0 + r;
     const bool hin = live && h >= 0 && h < a.H;
     const __nv_bfloat16* src = img + ((hin ? h : 0) * a.W + w0) * 4;
@@ -1539,13 +1572,14 @@ __device__ __forceinline__ void stem_gather(const StemArgs& a, uint8_t* sA, int 
 }
 // run-time dispatch on the two supported filter sizes (uniform across the block)
 __device__ __forceinline__ void stem_gather_any(const StemArgs& a, uint8_t* sA, int t, uint32_t m) {
-  if (a.kw == 7) stem_gather<7, 7>(a, sA, t, m);
-  else stem_gather<3, 3>(a, sA, t, m);
+  if (a.kw == 7) stem_gather<7, 7, 0, 7>(a, sA, t, m);
+  else stem_gather<3, 3, 0, 3>(a, sA, t, m);
 }
 
 // Roles (288 threads): warps 0-3 gather A tiles (cp.async, two stages in flight), warp 4 loads the
 // weights once and issues the MMAs, warps 5-8 run the shared epilogue (incl. fused BN statistics).
-__global__ void __launch_bounds__(288, 1)
+template <bool kTma>
+__global__ void __launch_bounds__(kStemThreads, 1)
 stem_fprop_kernel(const __grid_constant__ StemArgs args) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
@@ -1556,7 +1590,12 @@ stem_fprop_kernel(const __grid_constant__ StemArgs args) {
   const uint32_t a_stage = static_cast<uint32_t>(args.kc_alloc) * kABytes;
   const uint32_t b_chunk = static_cast<uint32_t>(args.e.block_n) * 128u;
   uint8_t* smemB = smem + static_cast<size_t>(stages) * a_stage;
-  uint8_t* tail = smemB + static_cast<size_t>(args.kc) * b_chunk;
+  // TMA-store epilogue: per-warp staging tiles (1024-aligned: b_chunk is a multiple of 2 KB ... the
+  // launcher only enables it when the offset is 1024-aligned)
+  constexpr bool tma = kTma;
+  const bool async_full = args.async_full != 0;
+  uint8_t* stg_all = smemB + static_cast<size_t>(args.kc) * b_chunk;
+  uint8_t* tail = stg_all + (tma ? static_cast<size_t>(4 * args.e.stg_bufs) * kStgBytes : 0);
   uint64_t* full = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty = full + stages;
   uint64_t* wbar = empty + stages;
@@ -1567,6 +1606,7 @@ stem_fprop_kernel(const __grid_constant__ StemArgs args) {
 
   if (threadIdx.x == 0) {
     ptx::prefetch_tmap(&args.mapW);
+    if (tma) ptx::prefetch_tmap(&args.mapOut);
     for (int s = 0; s < stages; ++s) {
       ptx::mbar_init(&full[s], kStemProducers);
       ptx::mbar_init(&empty[s], 1);
@@ -1578,7 +1618,7 @@ stem_fprop_kernel(const __grid_constant__ StemArgs args) {
     }
     ptx::fence_barrier_init();
   }
-  if (warp == 4) {
+  if (warp == kStemMmaWarp) {
     ptx::tmem_alloc(tmem_slot, static_cast<uint32_t>(args.tmem_cols));
     ptx::tmem_relinquish();
   }
@@ -1589,27 +1629,48 @@ stem_fprop_kernel(const __grid_constant__ StemArgs args) {
   // barriers, tensor-map prefetch and the TMEM allocation above overlap the previous kernel's tail
   MCN_PDL_PROLOGUE();
 
-  if (warp < 4) {
+  if (warp < kStemProducerWarps) {
     // ---------------- gather producers ----------------
     const int t = threadIdx.x;
     int it = 0;
+    RT_DECL;
+    const long long rt_p0 = RT_NOW();
+    (void)rt_p0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int s = it % stages;
+      RT_BEGIN;
       ptx::mbar_wait(&empty[s], (static_cast<uint32_t>(it / stages) & 1u) ^ 1u);
+      RT_END;
       stem_gather_any(args, smem + static_cast<size_t>(s) * a_stage, t, static_cast<uint32_t>(tile) * 128u + t);
+      if (async_full) {
+        // the stage's barrier gets this thread's arrival when its copies land: the producer moves on
+        // to the next free stage at once.  (Waiting for tile i-1's copies only AFTER issuing tile i,
+        // behind the wait for a free stage, chained gather -> MMA -> gather: role counters showed
+        // producers, MMA thread and epilogue each idle 40-50 % of the kernel.)
+        cp_async_arrive_noinc(&full[s]);
+        continue;
+      }
       cp_async_commit();
       if (it > 0) {
+        RT_BEGIN;
         cp_async_wait<1>();               // the previous tile's copies have landed
+        RT_END2;
         ptx::fence_proxy_async();         // generic-proxy writes -> visible to the tensor core
         ptx::mbar_arrive(&full[(it - 1) % stages]);
       }
     }
-    if (it > 0) {
+    if (t == 0) {      // slot 0: wait for a free stage, slot 8: wait for the copies, slot 9: producer lifetime
+      RT_FLUSH(0);
+      RT_FLUSH2(8);
+      RT_ADD(9, RT_NOW() - rt_p0);
+      RT_ADD(6, 1);
+    }
+    if (it > 0 && !async_full) {
       cp_async_wait<0>();
       ptx::fence_proxy_async();
       ptx::mbar_arrive(&full[(it - 1) % stages]);
     }
-  } else if (warp == 4) {
+  } else if (warp == kStemMmaWarp) {
     // ---------------- weights + MMA issuer ----------------
     if (ptx::elect_one()) {
       ptx::mbar_expect_tx(wbar, static_cast<uint32_t>(args.kc) * b_chunk);
@@ -1620,11 +1681,19 @@ stem_fprop_kernel(const __grid_constant__ StemArgs args) {
     ptx::mbar_wait(wbar, 0);
     const uint32_t idesc = ptx::make_idesc_bf16(128, args.e.block_n, 0, 0);
     int it = 0;
+    RT_DECL;
+    const long long rt_m0 = RT_NOW();
+    (void)rt_m0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int s = it % stages;
       const int buf = it & 1;
+      RT_BEGIN;
       ptx::mbar_wait(&tmem_empty[buf], (static_cast<uint32_t>(it >> 1) & 1u) ^ 1u);
+      RT_END2;
+      RT_BEGIN;
       ptx::mbar_wait(&full[s], static_cast<uint32_t>(it / stages) & 1u);
+      RT_END;
+      if (async_full) ptx::fence_proxy_async();   // the gathered tile (generic-proxy writes) -> tensor core
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
         const uint32_t a_addr = ptx::smem_u32(smem + static_cast<size_t>(s) * a_stage);
@@ -1643,13 +1712,22 @@ stem_fprop_kernel(const __grid_constant__ StemArgs args) {
       }
       __syncwarp();
     }
+    if (lane == 0) {
+      RT_FLUSH(1);
+      RT_FLUSH2(2);
+      RT_ADD(7, RT_NOW() - rt_m0);
+      RT_ADD(5, RT_NOW() - rt_m0);
+    }
   } else {
     // ---------------- epilogue (warps 5..8) ----------------
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     uint32_t* stat_stage = reinterpret_cast<uint32_t*>(tail + kBarRegionBytes);
-    float* stat_acc_all = reinterpret_cast<float*>(stat_stage + kStatStageWords);
+    float* stat_acc_all = tma ? reinterpret_cast<float*>(stat_stage)
+                              : reinterpret_cast<float*>(stat_stage + kStatStageWords);
     float* stat_acc = stat_acc_all + quad * kStatAccWarp;
+    uint8_t* stg = stg_all + static_cast<size_t>(quad * args.e.stg_bufs) * kStgBytes;
+    int stg_i = 0;
     stat_stage += quad * 32 * kStatRowWords;
     const bool stats = args.e.stats != nullptr;
     if (stats) {
@@ -1657,30 +1735,47 @@ stem_fprop_kernel(const __grid_constant__ StemArgs args) {
       epi_bar_sync();
     }
     int* stat_flag = reinterpret_cast<int*>(tail + kBarRegionBytes - 16);
-    int it = 0, pending = 0;
+    int it = 0, pending = 0, since = 0;
+    const long long rt_e0 = RT_NOW();
+    (void)rt_e0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
-      if (stats && pending == 8) {
-        stats_flush(args.e, stat_acc_all, 0, row, pending, stat_flag);
-        pending = 0;
+      if (stats && since == 8) {
+        stats_flush(args.e, stat_acc_all, 0, row, pending, stat_flag, false);
+        since = 0;
       }
       ++pending;
+      ++since;
       const long long m = static_cast<long long>(tile) * 128 + row;
       const bool valid = m < args.m_total;
-      epilogue_tile(args.e, tmem_base + static_cast<uint32_t>(buf * args.e.block_n), quad, lane, valid,
-                    valid ? m * args.cout : 0, 0, &tmem_full[buf], static_cast<uint32_t>(it >> 1) & 1u,
-                    &tmem_empty[buf], stat_stage, stat_acc);
+      const uint32_t tacc = tmem_base + static_cast<uint32_t>(buf * args.e.block_n);
+      const uint32_t tph = static_cast<uint32_t>(it >> 1) & 1u;
+      if (tma) {
+        // the tile is 128 consecutive rows of the [M, Cout] output matrix; the hardware clips the last one
+        const OutTile o{tile * 128 + quad * 32, 0, 0};
+        if (stats)
+          epilogue_tile_tma<1>(args.e, &args.mapOut, o, tacc, quad, lane, valid, 0, &tmem_full[buf], tph,
+                               &tmem_empty[buf], stg, stg_i, stat_acc);
+        else
+          epilogue_tile_tma<0>(args.e, &args.mapOut, o, tacc, quad, lane, valid, 0, &tmem_full[buf], tph,
+                               &tmem_empty[buf], stg, stg_i, stat_acc);
+      } else {
+        epilogue_tile(args.e, tacc, quad, lane, valid, valid ? m * args.cout : 0, 0, &tmem_full[buf], tph,
+                      &tmem_empty[buf], stat_stage, stat_acc);
+      }
     }
     if (stats && pending > 0) stats_flush(args.e, stat_acc_all, 0, row, pending, stat_flag);
+    if (tma && lane == 0) ptx::bulk_wait_all();   // the staged tiles must outlive their stores
+    if (row == 0) RT_ADD(4, RT_NOW() - rt_e0);
   }
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 4) ptx::tmem_dealloc(tmem_base, static_cast<uint32_t>(args.tmem_cols));
+  if (warp == kStemMmaWarp) ptx::tmem_dealloc(tmem_base, static_cast<uint32_t>(args.tmem_cols));
 }
 
 // wgrad: warps 0-3 gather, warp 4 loads dy tiles by TMA and issues the MMAs, warps 5-8 write dw.
-__global__ void __launch_bounds__(288, 1)
+__global__ void __launch_bounds__(kStemThreads, 1)
 stem_wgrad_kernel(const __grid_constant__ StemArgs args) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
@@ -1698,6 +1793,7 @@ stem_wgrad_kernel(const __grid_constant__ StemArgs args) {
   uint64_t* tmem_full = empty + stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
   const int split = blockIdx.x;
+  const bool async_full = args.async_full != 0;
   const int t0 = static_cast<int>(static_cast<long long>(split) * args.total_tiles / args.splits);
   const int t1 = static_cast<int>(static_cast<long long>(split + 1) * args.total_tiles / args.splits);
 
@@ -1719,7 +1815,7 @@ stem_wgrad_kernel(const __grid_constant__ StemArgs args) {
     ptx::mbar_init(tmem_full, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 4) {
+  if (warp == kStemMmaWarp) {
     ptx::tmem_alloc(tmem_slot, static_cast<uint32_t>(args.tmem_cols));
     ptx::tmem_relinquish();
   }
@@ -1731,13 +1827,17 @@ stem_wgrad_kernel(const __grid_constant__ StemArgs args) {
   MCN_PDL_PROLOGUE();
   const int m_tiles = args.kc_alloc / 2;     // accumulators of 128 k-rows
 
-  if (warp < 4) {
+  if (warp < kStemProducerWarps) {
     const int t = threadIdx.x;
     int it = 0;
     for (int tile = t0; tile < t1; ++tile, ++it) {
       const int s = it % stages;
       ptx::mbar_wait(&empty[s], (static_cast<uint32_t>(it / stages) & 1u) ^ 1u);
       stem_gather_any(args, smem + static_cast<size_t>(s) * stage_bytes, t, static_cast<uint32_t>(tile) * 128u + t);
+      if (async_full) {
+        cp_async_arrive_noinc(&full[s]);
+        continue;
+      }
       cp_async_commit();
       if (it > 0) {
         cp_async_wait<1>();
@@ -1745,12 +1845,12 @@ stem_wgrad_kernel(const __grid_constant__ StemArgs args) {
         ptx::mbar_arrive(&full[(it - 1) % stages]);
       }
     }
-    if (it > 0) {
+    if (it > 0 && !async_full) {
       cp_async_wait<0>();
       ptx::fence_proxy_async();
       ptx::mbar_arrive(&full[(it - 1) % stages]);
     }
-  } else if (warp == 4) {
+  } else if (warp == kStemMmaWarp) {
     const uint32_t idesc = ptx::make_idesc_bf16(128, args.e.block_n, 1, 1);
     // dy loads run one stage ahead of the MMAs: issue for tile i+1 before consuming tile i
     auto issue_dy = [&](int tile, int it) {
@@ -1772,6 +1872,7 @@ stem_wgrad_kernel(const __grid_constant__ StemArgs args) {
       __syncwarp();
       ptx::mbar_wait(&full[s], ph);
       ptx::mbar_wait(&fullb[s], ph);
+      if (async_full) ptx::fence_proxy_async();
       ptx::tc_fence_after();
       if (leader) {
         const uint32_t a_addr = ptx::smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
@@ -1818,7 +1919,7 @@ stem_wgrad_kernel(const __grid_constant__ StemArgs args) {
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 4) ptx::tmem_dealloc(tmem_base, static_cast<uint32_t>(args.tmem_cols));
+  if (warp == kStemMmaWarp) ptx::tmem_dealloc(tmem_base, static_cast<uint32_t>(args.tmem_cols));
 }
 
 // ------------------------------------------------------------------ host side
@@ -2895,6 +2996,12 @@ bool stem_geometry(const mcn_conv_desc* d, StemArgs* a) {
   a->cout = d->Cout;
   a->m_total = static_cast<long long>(d->N) * d->Ho * d->Wo;
   a->total_tiles = static_cast<int>((a->m_total + 127) / 128);
+  static int async_full = -1;
+  if (async_full < 0) {
+    const char* e = getenv("MCN_STEM_ASYNC_FULL");      // 0: commit / wait_group hand-off (A/B)
+    async_full = (e && e[0] == '0') ? 0 : 1;
+  }
+  a->async_full = async_full;
   return true;
 }
 }  // namespace
@@ -2930,15 +3037,30 @@ extern "C" int mcn_stem_conv_fprop(const mcn_conv_desc* d, const void* x4, const
   a.e.vec_ok = (d->Cout % 16 == 0);
   a.nb_atoms = 0;
   const size_t a_stage = static_cast<size_t>(a.kc_alloc) * kABytes;
+  // TMA-store epilogue (per-role counters: with the direct epilogue, one 128-byte row per thread, the
+  // epilogue warps were busy 94 % of the kernel and the producers idle half of it)
+  static int tma_enabled = -1;
+  if (tma_enabled < 0) {
+    const char* e = getenv("MCN_TMA_STORE");
+    tma_enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  a.use_tma = (tma_enabled && bias == nullptr && d->Cout % 64 == 0 && a.m_total < (1LL << 31) &&
+               (static_cast<size_t>(a.kc) * d->Cout * 128) % 1024 == 0) ? 1 : 0;
+  a.e.stg_bufs = 2;
+  a.e.out_rank4 = 0;
+  if (a.use_tma && (rc = encode_matrix(&a.mapOut, y, a.m_total, d->Cout, 32))) return rc;
   const size_t fixed = static_cast<size_t>(a.kc) * d->Cout * 128 + kBarRegionBytes +
-                       (bn_sums ? kEpiStageBytes + kStatAccBytes : 0) + 1024;
+                       (a.use_tma ? static_cast<size_t>(4 * a.e.stg_bufs) * kStgBytes + (bn_sums ? kStatAccBytes : 0)
+                                  : (bn_sums ? kEpiStageBytes + kStatAccBytes : 0)) + 1024;
   a.stages = static_cast<int>(std::min<size_t>(3, (static_cast<size_t>(smem_optin_limit()) - fixed) / a_stage));
   MCN_REQUIRE(a.stages >= 2, "stem_conv_fprop: shared memory budget too small");
   a.tmem_cols = 2 * tmem_cols_for(d->Cout);
   const size_t smem = a.stages * a_stage + fixed;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(stem_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(stem_fprop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             smem_optin_limit()) != cudaSuccess ||
+        cudaFuncSetAttribute(stem_fprop_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              smem_optin_limit()) != cudaSuccess) {
       set_error("cudaFuncSetAttribute(stem_fprop_kernel) failed");
       return MCN_ECUDA;
@@ -2947,7 +3069,8 @@ extern "C" int mcn_stem_conv_fprop(const mcn_conv_desc* d, const void* x4, const
   }
   if ((rc = attach_xs(&a.e, a.total_tiles, 1))) return rc;
   dim3 grid(static_cast<unsigned>(std::min(a.total_tiles, num_sms())));
-  ::mcn::launch(stem_fprop_kernel, grid, 288, smem, static_cast<cudaStream_t>(stream), a);
+  if (a.use_tma) ::mcn::launch(stem_fprop_kernel<true>, grid, kStemThreads, smem, static_cast<cudaStream_t>(stream), a);
+  else ::mcn::launch(stem_fprop_kernel<false>, grid, kStemThreads, smem, static_cast<cudaStream_t>(stream), a);
   return after_launch("stem_fprop_kernel");
 }
 
@@ -2988,7 +3111,7 @@ static int stem_wgrad_impl(const mcn_conv_desc* d, const void* x4, const void* d
     }
     configured = true;
   }
-  ::mcn::launch(stem_wgrad_kernel, a.splits, 288, smem, static_cast<cudaStream_t>(stream), a);
+  ::mcn::launch(stem_wgrad_kernel, a.splits, kStemThreads, smem, static_cast<cudaStream_t>(stream), a);
   if ((rc = after_launch("stem_wgrad_kernel"))) return rc;
   if (sp.stride)
     return launch_splitk_reduce(sp.base, sp.stride, a.splits, dw_elems, dw, static_cast<cudaStream_t>(stream));

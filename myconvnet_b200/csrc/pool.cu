@@ -330,6 +330,186 @@ maxpool_bwd_tap_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ tap
   }
 }
 
+// ---- 3x3 / stride 2 (the ResNet stem pool, 112^2 -> 56^2 of 411 MB at batch 256).
+// The per-output kernels above fetch every window tap on their own with L1-bypassing loads: 9 vector
+// loads per output of which 5 re-read a neighbour's data (2.25 L2 reads per input element, 925 MB in
+// 185 us = the L2 -> SM streaming rate), and the per-input backward fetches 2.25 (dy, tap) pairs per
+// element written.  Forward: 2-D output tiles per block with L1-allocating loads.  Backward: a thread
+// owns one 2-pixel-wide input column pair of one 16-byte channel vector and walks down a strip of
+// rows, carrying the window row shared with the next pixel pair in registers (293 -> 148 us).
+// Tie-breaking and summation order are those of the kernels above (first maximum in row-major window
+// order; ascending (p, q)): results are bit-identical.
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+maxpool_fwd_tap_tile32_kernel(const T* __restrict__ x, int N, int H, int W, int C, int pad_t, int pad_l, int Ho,
+                              int Wo, int TP, int tiles_p, int tiles_q, T* __restrict__ y,
+                              uint8_t* __restrict__ tap) {
+  MCN_PDL_PROLOGUE();
+  // forward: a block owns a TP x 4 tile of outputs (256 threads = outputs x channel vectors) and loads
+  // with L1 allocation: the taps shared by neighbouring windows hit L1 instead of crossing L2 again
+  const int cv = C / V;
+  const int c0 = (int)(threadIdx.x % (unsigned)cv) * V;
+  const int o = (int)(threadIdx.x / (unsigned)cv);
+  const int dq = o & 3, dp = o >> 2;
+  const int total = N * tiles_p * tiles_q;
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int tq = tile % tiles_q;
+    const int r = tile / tiles_q;
+    const int tp = r % tiles_p, n = r / tiles_p;
+    const int p = tp * TP + dp, q = tq * 4 + dq;
+    if (p >= Ho || q >= Wo) continue;
+    const int h0 = p * 2 - pad_t, w0 = q * 2 - pad_l;
+    const T* img = x + (long long)n * H * W * C + c0;
+    Vec16<T> t[9];
+    bool ok[9];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        const int h = h0 + a, w = w0 + b;
+        ok[a * 3 + b] = h >= 0 && h < H && w >= 0 && w < W;
+        if (ok[a * 3 + b]) t[a * 3 + b] = ld_vec(img + ((long long)h * W + w) * C);
+      }
+    float best[V];
+    int bt[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      best[e] = -FLT_MAX;
+      bt[e] = -1;
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+      if (ok[k]) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          const float v = t[k].get(e);
+          if (v > best[e] || bt[e] < 0) {
+            best[e] = v;
+            bt[e] = k;
+          }
+        }
+      }
+    const long long oo = (((long long)n * Ho + p) * Wo + q) * C + c0;
+    Vec16<T> ov;
+#pragma unroll
+    for (int e = 0; e < V; ++e) ov.set(e, best[e]);
+    st_vec(y + oo, ov);
+    uint32_t pk[V / 4];
+#pragma unroll
+    for (int e = 0; e < V; e += 4)
+      pk[e / 4] = (uint32_t)(bt[e] & 255) | ((uint32_t)(bt[e + 1] & 255) << 8) |
+                  ((uint32_t)(bt[e + 2] & 255) << 16) | ((uint32_t)(bt[e + 3] & 255) << 24);
+    if (V == 8) *reinterpret_cast<uint2*>(tap + oo) = make_uint2(pk[0], pk[1]);
+    else *reinterpret_cast<uint32_t*>(tap + oo) = pk[0];
+  }
+}
+
+// Backward: with u = h + pad_t, v = w + pad_l the pixels (2j | 2j+1, 2k | 2k+1) are covered by the
+// windows (j-1 | j, k-1 | k) only; a thread walks j down a strip, carrying window row j-1.
+template <typename T, int V>
+__device__ __forceinline__ void maxpool_take(const Vec16<T>& g, const uint2& tp, bool ok, int want, float* acc) {
+  if (!ok) return;
+#pragma unroll
+  for (int e = 0; e < V; ++e) {
+    const uint32_t word = e < 4 ? tp.x : tp.y;
+    if ((int)((word >> (8 * (e & 3))) & 255u) == want) acc[e] += g.get(e);
+  }
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+maxpool_bwd_tap_strip32_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ tap, int N, int H, int W,
+                               int C, int pad_t, int pad_l, int Ho, int Wo, int nj, int nk, int strip_rows,
+                               int strips, T* __restrict__ dx) {
+  MCN_PDL_PROLOGUE();
+  const int cv = C / V;
+  const uint32_t total = (uint32_t)N * strips * nk * cv;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % (uint32_t)cv) * V;
+    uint32_t r = i / (uint32_t)cv;
+    const int k = (int)(r % (uint32_t)nk);
+    r /= (uint32_t)nk;
+    const int sidx = (int)(r % (uint32_t)strips);
+    const int n = (int)(r / (uint32_t)strips);
+    const int j0 = sidx * strip_rows, j1 = min(nj, j0 + strip_rows);
+    const T* gimg = dy + (long long)n * Ho * Wo * C + c0;
+    const uint8_t* timg = tap + (long long)n * Ho * Wo * C + c0;
+    T* ximg = dx + (long long)n * H * W * C + c0;
+    const bool okq[2] = {k - 1 >= 0 && k - 1 < Wo, k < Wo};      // window columns k-1, k
+    const int w_a = 2 * k - pad_l, w_b = w_a + 1;                 // the two pixel columns
+    const bool okwa = w_a >= 0 && w_a < W, okwb = w_b >= 0 && w_b < W;
+    Vec16<T> gp[2], gc[2];
+    uint2 tp[2], tc[2];
+    bool okp[2], okc[2];
+    auto load_row = [&](int p, Vec16<T>* g, uint2* t, bool* ok) {
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        ok[m] = p >= 0 && p < Ho && okq[m];
+        if (ok[m]) {
+          const long long o = ((long long)p * Wo + (k - 1 + m)) * C;
+          g[m] = ld_vec(gimg + o);
+          if (V == 8) t[m] = *reinterpret_cast<const uint2*>(timg + o);
+          else t[m] = make_uint2(*reinterpret_cast<const uint32_t*>(timg + o), 0u);
+        }
+      }
+    };
+    load_row(j0 - 1, gp, tp, okp);
+    for (int j = j0; j < j1; ++j) {
+      load_row(j, gc, tc, okc);
+      const int h_a = 2 * j - pad_t, h_b = h_a + 1;
+      float acc[V];
+      Vec16<T> ov;
+      if (h_a >= 0 && h_a < H) {
+        if (okwa) {     // (2j, 2k): windows (j-1,k-1) tap (2,2), (j-1,k) (2,0), (j,k-1) (0,2), (j,k) (0,0)
+#pragma unroll
+          for (int e = 0; e < V; ++e) acc[e] = 0.f;
+          maxpool_take<T, V>(gp[0], tp[0], okp[0], 8, acc);
+          maxpool_take<T, V>(gp[1], tp[1], okp[1], 6, acc);
+          maxpool_take<T, V>(gc[0], tc[0], okc[0], 2, acc);
+          maxpool_take<T, V>(gc[1], tc[1], okc[1], 0, acc);
+#pragma unroll
+          for (int e = 0; e < V; ++e) ov.set(e, acc[e]);
+          st_vec(ximg + ((long long)h_a * W + w_a) * C, ov);
+        }
+        if (okwb) {     // (2j, 2k+1): windows (j-1,k) tap (2,1), (j,k) (0,1)
+#pragma unroll
+          for (int e = 0; e < V; ++e) acc[e] = 0.f;
+          maxpool_take<T, V>(gp[1], tp[1], okp[1], 7, acc);
+          maxpool_take<T, V>(gc[1], tc[1], okc[1], 1, acc);
+#pragma unroll
+          for (int e = 0; e < V; ++e) ov.set(e, acc[e]);
+          st_vec(ximg + ((long long)h_a * W + w_b) * C, ov);
+        }
+      }
+      if (h_b >= 0 && h_b < H) {
+        if (okwa) {     // (2j+1, 2k): windows (j,k-1) tap (1,2), (j,k) (1,0)
+#pragma unroll
+          for (int e = 0; e < V; ++e) acc[e] = 0.f;
+          maxpool_take<T, V>(gc[0], tc[0], okc[0], 5, acc);
+          maxpool_take<T, V>(gc[1], tc[1], okc[1], 3, acc);
+#pragma unroll
+          for (int e = 0; e < V; ++e) ov.set(e, acc[e]);
+          st_vec(ximg + ((long long)h_b * W + w_a) * C, ov);
+        }
+        if (okwb) {     // (2j+1, 2k+1): window (j,k) tap (1,1)
+#pragma unroll
+          for (int e = 0; e < V; ++e) acc[e] = 0.f;
+          maxpool_take<T, V>(gc[1], tc[1], okc[1], 4, acc);
+#pragma unroll
+          for (int e = 0; e < V; ++e) ov.set(e, acc[e]);
+          st_vec(ximg + ((long long)h_b * W + w_b) * C, ov);
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        gp[m] = gc[m];
+        tp[m] = tc[m];
+        okp[m] = okc[m];
+      }
+    }
+  }
+}
+
 __global__ void maxpool_tap_to_argmax_kernel(const uint8_t* __restrict__ tap, long long total, int W, int C,
                                              int kw, int sh, int sw, int pad_t, int pad_l, int Ho, int Wo,
                                              int32_t* __restrict__ argmax) {
@@ -536,6 +716,38 @@ static void launch_maxpool_tap(bool fwd, const void* in, const uint8_t* tap_in, 
     ::mcn::launch(maxpool_bwd_tap_kernel<T, V, KK, SS>, grid, 256, 0, st, static_cast<const T*>(in), tap_in, N, H, W, C, kh, \
                                                              kw, sh, sw, pad_t, pad_l, Ho, Wo, static_cast<T*>(out))
   const bool sq = kh == kw && sh == sw;
+  static int strip = -1;
+  if (strip < 0) {
+    const char* e = getenv("MCN_POOL_STRIP");      // 0: the per-output kernels (A/B)
+    strip = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (strip && sq && kh == 3 && sh == 2 && pad_t >= 0 && pad_t <= 2 && pad_l >= 0 && pad_l <= 2) {
+    const int cv = C / V;
+    if (fwd) {
+      if (256 % cv == 0 && 256 / cv >= 4) {
+        const int TP = 256 / cv / 4, tiles_p = (Ho + TP - 1) / TP, tiles_q = (Wo + 3) / 4;
+        const long long tiles = (long long)N * tiles_p * tiles_q;
+        const int tgrid = (int)std::max<long long>(1, std::min<long long>(tiles, (long long)bps * num_sms()));
+        ::mcn::launch(maxpool_fwd_tap_tile32_kernel<T, V>, tgrid, 256, 0, st, static_cast<const T*>(in), N, H, W, C,
+                      pad_t, pad_l, Ho, Wo, TP, tiles_p, tiles_q, static_cast<T*>(out), tap_out);
+        return;
+      }
+    } else {
+      // strips of rows: enough threads to fill the chip several times over, strips as long as that allows
+      const int rows = (H + pad_t + 1) / 2, cols = (W + pad_l + 1) / 2;
+      const long long per_strip = (long long)N * cols * cv;
+      const long long want = (long long)num_sms() * 2048 * 2;
+      int strips = (int)std::max<long long>(1, std::min<long long>(rows, (want + per_strip - 1) / per_strip));
+      int strip_rows = (rows + strips - 1) / strips;
+      if (const char* e = getenv("MCN_POOL_STRIP_ROWS")) strip_rows = std::max(1, std::min(rows, atoi(e)));   // tests
+      strips = (rows + strip_rows - 1) / strip_rows;
+      const long long threads = per_strip * strips;
+      const int sgrid = (int)std::max<long long>(1, std::min<long long>((threads + 255) / 256, (long long)bps * num_sms()));
+      ::mcn::launch(maxpool_bwd_tap_strip32_kernel<T, V>, sgrid, 256, 0, st, static_cast<const T*>(in), tap_in, N, H,
+                    W, C, pad_t, pad_l, Ho, Wo, rows, cols, strip_rows, strips, static_cast<T*>(out));
+      return;
+    }
+  }
   if (sq && kh == 3 && sh == 2) { MCN_POOL_CASE(3, 2); }
   else if (sq && kh == 2 && sh == 2) { MCN_POOL_CASE(2, 2); }
   else if (sq && kh == 3 && sh == 1) { MCN_POOL_CASE(3, 1); }

@@ -37,6 +37,8 @@ CASES = [
     ("b4 conv_0 1x1 2048->512", "w", 7, 2048, 512, 1, 1, 0),
     ("b4 conv_1 3x3 512->512", "w", 7, 512, 512, 3, 1, 0),
 ]
+if os.environ.get("ONLY_STEM") == "1":
+    CASES = []
 SLOTS = ["prod_wait_empty", "mma_wait_full", "mma_wait_acc", "epi_wait_acc", "epi_total", "cta_life", "ctas", "mma_total"]
 
 
@@ -90,3 +92,33 @@ for name, op, hw, ci, co, k, s, stats in CASES:
     per[6] = c[6] / iters
     print("%-34s %-3s %8.1f | %s" % (name, op, us, " ".join("%9.0f" % v for v in per)))
     del x, dy, y, dx
+
+# ---- the RGB stem (stem_fprop_kernel): 7x7 stride 2, 224^2 x 4 -> 112^2 x 64
+if os.environ.get("STEM", "1") == "1":
+    n, h, co, k = N, 224, 64, 7
+    d4 = L.ConvDescC(n, h, h, 4, co, k, k, 2, 2, 1, 1, 2, 2, 112, 112)
+    kpad = lib.mcn_stem_conv_kpad(d4)
+    x4 = torch.randn(n, h, h, 4, device="cuda").bfloat16()
+    w_t = (torch.randn(co, kpad, device="cuda") * 0.05).bfloat16()
+    y = torch.empty(n, 112, 112, co, device="cuda", dtype=torch.bfloat16)
+    sums = torch.zeros(2 * co, device="cuda", dtype=torch.float64)
+    st = torch.cuda.current_stream().cuda_stream
+    for with_stats in (1, 0):
+        run = lambda: L.check(lib.mcn_stem_conv_fprop(d4, x4.data_ptr(), w_t.data_ptr(), None, y.data_ptr(),
+                                                      sums.data_ptr() if with_stats else None, st))
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        cycles(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        c = cycles(True)
+        nc = max(1, c[6])
+        names = ["prod_wait_empty", "mma_wait_full", "mma_wait_acc", "epi_wait_acc", "epi_total", "mma_life", "ctas",
+                 "mma_total", "prod_wait_copies", "prod_life"]
+        print("stem fprop 7x7 s2 (stats=%d) %8.1f us | %s" % (with_stats, e0.elapsed_time(e1) * 100,
+              " ".join("%s=%.0f" % (nm, (c[i] / nc) if i != 6 else c[i] / 10) for i, nm in enumerate(names))))

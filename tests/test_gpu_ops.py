@@ -533,3 +533,45 @@ def test_maxpool_argmax_bit_exact():
             assert np.array_equal(am2.cpu().numpy().astype(np.int64), ref_idx)
             assert torch.equal(y2.float(), y)
             assert torch.equal(dx1, dx2)
+
+
+@pytest.mark.parametrize("strip_rows", [None, 1, 3, 100])
+@pytest.mark.parametrize("shape", [(2, 9, 11, 16), (3, 12, 10, 8), (2, 16, 14, 24), (1, 7, 8, 8), (2, 112, 112, 64)])
+def test_maxpool_3x3s2_strip_kernels(shape, strip_rows, monkeypatch):
+    """The strip-walking 3x3 / stride-2 max-pool kernels (forward: one output column per thread, the
+    shared input row carried in registers; backward: one 2-pixel input column pair per thread) give
+    the oracle's values and first-max argmax bit for bit, and the int32-argmax backward's gradient
+    bit for bit, for odd / even sizes (TF SAME puts the odd padding at the bottom / right) and any
+    strip length."""
+    from myconvnet_b200 import lib as L
+    lib = L.load()
+    if strip_rows is not None:
+        monkeypatch.setenv("MCN_POOL_STRIP_ROWS", str(strip_rows))
+    n, h, w, c = shape
+    rng = np.random.default_rng(5)
+    x = (rng.integers(0, 6, size=shape).astype(np.float32)) * 0.5 - 1.0       # frequent ties
+    k, s = 3, 2
+    ho, pt, _ = tf_ops.same_pad(h, k, s, 1, "SAME")
+    wo, pl, _ = tf_ops.same_pad(w, k, s, 1, "SAME")
+    ref_idx = tf_ops.max_pool_argmax(torch.from_numpy(x), [k, k], [s, s], "SAME").numpy()
+    ref_val = tf_ops.max_pool(torch.from_numpy(x), [k, k], [s, s], "SAME")
+    xt = torch.from_numpy(x).cuda()
+    for code, dt in ((0, torch.float32), (1, torch.bfloat16)):
+        xc = xt.to(dt)
+        y = torch.empty(n, ho, wo, c, device="cuda", dtype=dt)
+        tap = torch.empty(n, ho, wo, c, dtype=torch.uint8, device="cuda")
+        am = torch.empty(n, ho, wo, c, dtype=torch.int32, device="cuda")
+        L.check(lib.mcn_maxpool_fwd_tap(code, xc.data_ptr(), n, h, w, c, k, k, s, s, pt, pl, ho, wo,
+                                        y.data_ptr(), tap.data_ptr(), None))
+        L.check(lib.mcn_maxpool_tap_to_argmax(tap.data_ptr(), n, h, w, c, k, k, s, s, pt, pl, ho, wo,
+                                              am.data_ptr(), None))
+        gy = torch.randn(n, ho, wo, c, device="cuda").to(dt)
+        dx1, dx2 = torch.empty_like(xc), torch.full_like(xc, 7.0)
+        L.check(lib.mcn_maxpool_bwd(code, gy.data_ptr(), am.data_ptr(), n, h, w, c, k, k, s, s, pt, pl, ho, wo,
+                                    dx1.data_ptr(), None))
+        L.check(lib.mcn_maxpool_bwd_tap(code, gy.data_ptr(), tap.data_ptr(), n, h, w, c, k, k, s, s, pt, pl,
+                                        ho, wo, dx2.data_ptr(), None))
+        torch.cuda.synchronize()
+        assert np.array_equal(am.cpu().numpy().astype(np.int64), ref_idx)
+        assert torch.equal(y.float().cpu(), ref_val)          # the test values are exact in bf16
+        assert torch.equal(dx1, dx2)
