@@ -233,6 +233,15 @@ def launch_work(name, args, esz):
     if name == "mcn_bn_apply_stats":
         n = args[2] * args[3]
         return n * esz * (2 + (1 if args[10] else 0)), 0.0
+    if name == "mcn_bn_apply_stats_mask":          # x + residual in, y + one mask bit per element out
+        n = args[2] * args[3]
+        return n * (esz * 3 + 0.125), 0.0
+    if name == "mcn_bn_bwd_reduce_mask":           # dy, x and the bit mask
+        n = args[4] * args[5]
+        return n * (esz * 2 + 0.125), 0.0
+    if name == "mcn_bn_bwd_apply_mask":            # dy, x, mask in; dx (+ residual gradient) out
+        n = args[4] * args[5]
+        return n * (esz * (3 + (1 if args[13] else 0)) + 0.125), 0.0
     if name == "mcn_bn_bwd_reduce":
         n = args[4] * args[5]
         return n * esz * (2 + (1 if args[3] else 0)), 0.0
@@ -268,7 +277,8 @@ KERNEL_OF = {
     "mcn_conv2d_wgrad_tc": "wgrad_tc (wgrad_kernel / wgrad_halo_kernel + splitk_reduce)",
     "mcn_stem_conv_fprop": "stem (stem_fprop_kernel / stem_wgrad_kernel)",
     "mcn_stem_conv_wgrad": "stem (stem_fprop_kernel / stem_wgrad_kernel)",
-    "mcn_bn_apply_stats": "bn_apply", "mcn_bn_apply": "bn_apply",
+    "mcn_bn_apply_stats": "bn_apply", "mcn_bn_apply": "bn_apply", "mcn_bn_apply_stats_mask": "bn_apply",
+    "mcn_bn_bwd_reduce_mask": "bn_bwd_reduce", "mcn_bn_bwd_apply_mask": "bn_bwd_apply",
     "mcn_maxpool_fwd_tap": "maxpool", "mcn_maxpool_bwd_tap": "maxpool",
     "mcn_dwconv2d_fwd": "dwconv", "mcn_dwconv2d_bwd_data": "dwconv", "mcn_dwconv2d_bwd_filter": "dwconv",
     "mcn_conv2d_fprop_direct": "conv_direct (igemm_kernel)", "mcn_conv2d_dgrad_direct": "conv_direct (igemm_kernel)",

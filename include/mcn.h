@@ -171,6 +171,24 @@ int mcn_bn_apply_stats(int dtype, const void* x, long long rows, int C, const do
                        const float* beta, const void* residual, int act, float act_alpha, void* y,
                        float* save_mean, float* save_invstd, float* moving_mean,
                        float* moving_var, void* stream);
+/* ReLU bit mask for the layers with a fused residual (bf16, C % 8 == 0, 256 % (C/8) == 0, act = RELU).
+ * Their backward passes need the sign of the OUTPUT y (the pre-activation cannot be rebuilt from x alone);
+ * mcn_bn_apply_stats_mask is mcn_bn_apply_stats that also writes relu_mask: bit (e & 7) of byte (e >> 3)
+ * is set iff the stored y[e] > 0 (rows*C/8 bytes; the buffer must be 4-byte aligned and readable up to
+ * the next multiple of 4).  mcn_bn_bwd_reduce_mask / mcn_bn_bwd_apply_mask are mcn_bn_bwd_reduce /
+ * mcn_bn_bwd_apply reading that mask instead of y: one bit per element instead of two bytes, twice. */
+int mcn_bn_apply_stats_mask(int dtype, const void* x, long long rows, int C, const double* sums,
+                            double count, float eps, float momentum, const float* gamma,
+                            const float* beta, const void* residual, int act, float act_alpha, void* y,
+                            void* relu_mask, float* save_mean, float* save_invstd, float* moving_mean,
+                            float* moving_var, void* stream);
+int mcn_bn_bwd_reduce_mask(int dtype, const void* dy, const void* x, const void* relu_mask,
+                           long long rows, int C, const float* mean, const float* invstd,
+                           float* sum_dz, float* sum_dz_xhat, void* stream);
+int mcn_bn_bwd_apply_mask(int dtype, const void* dy, const void* x, const void* relu_mask,
+                          long long rows, int C, const float* mean, const float* invstd,
+                          const float* gamma, const float* sum_dz, const float* sum_dz_xhat,
+                          double count, void* dx, void* d_residual, void* stream);
 /* Backward reduction fused into the dgrad that PRODUCES the BN output's gradient (the conv consuming
  * the BN+ReLU output): stride-1 bf16 dgrad with dx = d(loss)/d(BN output), plus, from the same
  * epilogue tile, sums[c] += sum dz and sums[C + c] += sum dz*x over all pixels, where x = bn_x is

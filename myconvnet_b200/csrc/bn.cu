@@ -439,8 +439,10 @@ __device__ __forceinline__ float dz_of(float dy, float xv, float yv, bool have_y
 // U rows per thread are in flight at once (U*2 or U*3 16-byte loads): at 768 threads per SM two rows
 // keep ~49 KB in flight, about what 6.5 TB/s x ~1 us of loaded latency needs per SM and no more
 // (measured 0.65 of the copy peak); four rows double that.
-template <typename T, int U, bool kHaveY>
-__global__ void __launch_bounds__(256, (U > 2 && kHaveY) ? 2 : 3)
+// kMask: `y` is the ReLU bit mask written by the forward pass (bn_apply_pipe_kernel), one byte per
+// 8-element vector, instead of the output tensor.
+template <typename T, int U, bool kHaveY, bool kMask = false>
+__global__ void __launch_bounds__(256, (U > 2 && kHaveY && !kMask) ? 2 : 3)
 bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
                      long long rows, int C, int slab_v, int rowlanes,
                      const float* __restrict__ mean, const float* __restrict__ invstd,
@@ -465,9 +467,11 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T*
       sc[i] = (gamma ? gamma[c0 + i] : 1.f) * invstd[c0 + i];
       sf[i] = (beta ? beta[c0 + i] : 0.f) - mean[c0 + i] * sc[i];
     }
-    constexpr bool have_y = kHaveY;
+    constexpr bool have_y = kHaveY && !kMask;
+    const uint8_t* mask = reinterpret_cast<const uint8_t*>(y);
     for (long long r = r0 + rl; r < r1; r += (long long)U * rowlanes) {
-      Vec16<T> g[U], a[U], o[kHaveY ? U : 1];
+      Vec16<T> g[U], a[U], o[have_y ? U : 1];
+      uint32_t mb[kMask ? U : 1];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         long long rr = r + (long long)u * rowlanes;
@@ -476,6 +480,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T*
           g[u] = ld_vec_stream(dy + off);
           a[u] = ld_vec_stream(x + off);
           if (have_y) o[u] = ld_vec_stream(y + off);
+          if (kMask) mb[u] = __ldg(mask + (off >> 3));
         }
       }
 #pragma unroll
@@ -485,8 +490,10 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T*
 #pragma unroll
           for (int i = 0; i < V; ++i) {
             float xv = a[u].get(i);
-            float dz = dz_of<T>(g[u].get(i), xv, have_y ? o[kHaveY ? u : 0].get(i) : 0.f, have_y, sc[i], sf[i],
-                                act, alpha);
+            float dz;
+            if (kMask) dz = ((mb[kMask ? u : 0] >> i) & 1u) ? g[u].get(i) : 0.f;
+            else dz = dz_of<T>(g[u].get(i), xv, have_y ? o[have_y ? u : 0].get(i) : 0.f, have_y, sc[i], sf[i],
+                               act, alpha);
             s1[i] += dz;
             s2[i] = fmaf(dz, xv, s2[i]);          // sum dz*x; turned into sum dz*xhat below
           }
@@ -678,13 +685,13 @@ inline bool bn_reduce_pipe() {
 }
 
 // forward apply (+ residual): S = 1 or 2 streams
-template <typename T, int kMode, bool kRes>
+template <typename T, int kMode, bool kRes, bool kMaskOut = false>
 __global__ void __launch_bounds__(256, 3)
 bn_apply_pipe_kernel(const T* __restrict__ x, long long nvec, int cv, const float* __restrict__ mean,
                      const float* __restrict__ invstd_or_var, float eps,
                      const float* __restrict__ gamma, const float* __restrict__ beta,
                      const T* __restrict__ residual, int act, float alpha, T* __restrict__ y,
-                     BnSumsArgs fs) {
+                     BnSumsArgs fs, uint8_t* __restrict__ relu_mask) {
   MCN_PDL_PROLOGUE();
   constexpr int V = Vec16<T>::N;
   constexpr int S = kRes ? 2 : 1, D = kPipeSlots / S;
@@ -720,6 +727,14 @@ bn_apply_pipe_kernel(const T* __restrict__ x, long long nvec, int cv, const floa
       o.set(i, act_fwd(act, f, alpha));
     }
     st_vec(y + v * V, o);
+    if (kMaskOut) {
+      // one bit per element of the STORED output (bit i of byte v <=> y[v*8 + i] > 0): what the backward
+      // passes need from y, in 1/16 of its bytes (bf16 only: V == 8)
+      uint32_t m = 0;
+#pragma unroll
+      for (int i = 0; i < V; ++i) m |= (o.get(i) > 0.f ? 1u : 0u) << i;
+      relu_mask[v] = static_cast<uint8_t>(m);
+    }
     const long long vn = v + D * stride;
     if (vn < nvec) {
       cp_async16(base + d * kSlot, x + vn * V);
@@ -731,8 +746,15 @@ bn_apply_pipe_kernel(const T* __restrict__ x, long long nvec, int cv, const floa
   cp_async_wait<0>();
 }
 
-// backward apply: S = 2 (dy, x) or 3 (+ y)
-template <typename T, bool kHaveY, bool kRes>
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+constexpr int kMaskRingBytes = (kPipeSlots / 2) * 256 * 4;   // bit-mask ring of the masked backward apply
+
+// backward apply: S = 2 (dy, x) or 3 (+ y).  kY: 0 no y, 1 y is the output tensor, 2 y is the ReLU bit
+// mask of the forward pass (one byte per vector): two full rings (D = 6) plus a ring of 4-byte words —
+// each thread fetches the aligned word that holds its byte.
+template <typename T, int kY, bool kRes>
 __global__ void __launch_bounds__(256, 3)
 bn_bwd_apply_pipe_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
                          long long nvec, int cv, const float* __restrict__ mean,
@@ -742,10 +764,13 @@ bn_bwd_apply_pipe_kernel(const T* __restrict__ dy, const T* __restrict__ x, cons
                          float inv_count, T* __restrict__ dx, T* __restrict__ d_residual) {
   MCN_PDL_PROLOGUE();
   constexpr int V = Vec16<T>::N;
+  constexpr bool kHaveY = kY == 1, kMask = kY == 2;
   constexpr int S = kHaveY ? 3 : 2, D = kPipeSlots / S;
   extern __shared__ uint4 pipe_smem[];
   const uint32_t base = static_cast<uint32_t>(__cvta_generic_to_shared(pipe_smem)) + threadIdx.x * 16u;
   constexpr uint32_t kSlot = 256u * 16u;
+  const uint32_t mbase = static_cast<uint32_t>(__cvta_generic_to_shared(pipe_smem)) + kPipeBytes + threadIdx.x * 4u;
+  const uint8_t* mask = reinterpret_cast<const uint8_t*>(y);
   const long long stride = (long long)gridDim.x * 256;
   long long v = (long long)blockIdx.x * 256 + threadIdx.x;
 #pragma unroll
@@ -755,6 +780,7 @@ bn_bwd_apply_pipe_kernel(const T* __restrict__ dy, const T* __restrict__ x, cons
       cp_async16(base + d * kSlot, dy + vv * V);
       cp_async16(base + (D + d) * kSlot, x + vv * V);
       if (kHaveY) cp_async16(base + (2 * D + d) * kSlot, y + vv * V);
+      if (kMask) cp_async4(mbase + d * 1024u, mask + (vv & ~3LL));
     }
     cp_async_commit();
   }
@@ -777,11 +803,18 @@ bn_bwd_apply_pipe_kernel(const T* __restrict__ dy, const T* __restrict__ x, cons
     const Vec16<T> a = lds_vec<T>(base + (D + d) * kSlot);
     Vec16<T> o;
     if (kHaveY) o = lds_vec<T>(base + (2 * D + d) * kSlot);
+    uint32_t mb = 0;
+    if (kMask) {
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(mb) : "r"(mbase + d * 1024u) : "memory");
+      mb >>= 8u * (static_cast<uint32_t>(v) & 3u);
+    }
     Vec16<T> ox, orr;
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       const float xv = a.get(i);
-      const float dz = dz_of<T>(g.get(i), xv, kHaveY ? o.get(i) : 0.f, kHaveY, A[i], sf[i], act, alpha);
+      float dz;
+      if (kMask) dz = ((mb >> i) & 1u) ? g.get(i) : 0.f;
+      else dz = dz_of<T>(g.get(i), xv, kHaveY ? o.get(i) : 0.f, kHaveY, A[i], sf[i], act, alpha);
       ox.set(i, fmaf(A[i], dz, fmaf(B[i], xv, Cc[i])));
       if (kRes) orr.set(i, dz);
     }
@@ -792,6 +825,7 @@ bn_bwd_apply_pipe_kernel(const T* __restrict__ dy, const T* __restrict__ x, cons
       cp_async16(base + d * kSlot, dy + vn * V);
       cp_async16(base + (D + d) * kSlot, x + vn * V);
       if (kHaveY) cp_async16(base + (2 * D + d) * kSlot, y + vn * V);
+      if (kMask) cp_async4(mbase + d * 1024u, mask + (vn & ~3LL));
     }
     cp_async_commit();
     d = (d + 1 == D) ? 0 : d + 1;
@@ -1001,7 +1035,7 @@ template <int kMode>
 static int bn_apply_impl(int dtype, const void* x, long long rows, int C, const float* mean,
                          const float* is_or_var, float eps, const float* gamma, const float* beta,
                          const void* residual, int act, float alpha, void* y, const BnSumsArgs& fs,
-                         void* stream) {
+                         void* stream, uint8_t* relu_mask = nullptr) {
   MCN_REQUIRE(x && y && rows > 0, "bn_apply: bad argument");
   MCN_REQUIRE(kMode == 2 || (mean && is_or_var), "bn_apply: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1014,14 +1048,25 @@ static int bn_apply_impl(int dtype, const void* x, long long rows, int C, const 
     if (cvr > 0 && cvr <= 256 && 256 % cvr == 0 && bn_use_pipe()) {
       const long long nvec = rows * cvr;
       const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((nvec + 255) / 256, 3LL * num_sms()));
-      if (residual != nullptr)
+      if (relu_mask != nullptr) {
+        if (residual == nullptr || sizeof(T) != 2) {
+          set_error("bn_apply_stats_mask: bf16 tensors with a fused residual only");
+          return MCN_EINVAL;
+        }
+        ::mcn::launch(bn_apply_pipe_kernel<T, kMode, true, true>, grid, 256, kPipeBytes, st, static_cast<const T*>(x),
+                      nvec, cvr, mean, is_or_var, eps, gamma, beta, static_cast<const T*>(residual), act, alpha,
+                      static_cast<T*>(y), fs, relu_mask);
+      } else if (residual != nullptr)
         ::mcn::launch(bn_apply_pipe_kernel<T, kMode, true>, grid, 256, kPipeBytes, st, static_cast<const T*>(x), nvec,
                       cvr, mean, is_or_var, eps, gamma, beta, static_cast<const T*>(residual), act, alpha,
-                      static_cast<T*>(y), fs);
+                      static_cast<T*>(y), fs, relu_mask);
       else
         ::mcn::launch(bn_apply_pipe_kernel<T, kMode, false>, grid, 256, kPipeBytes, st, static_cast<const T*>(x), nvec,
                       cvr, mean, is_or_var, eps, gamma, beta, static_cast<const T*>(nullptr), act, alpha,
-                      static_cast<T*>(y), fs);
+                      static_cast<T*>(y), fs, relu_mask);
+    } else if (relu_mask != nullptr) {
+      set_error("bn_apply_stats_mask: needs bf16, C %% 8 == 0 and 256 %% (C / 8) == 0 (the pipe kernel)");
+      return MCN_EINVAL;
     } else if (cvr > 0 && cvr <= 256 && 256 % cvr == 0 && bn_use_runs() && residual == nullptr) {
       const long long nvec = rows * cvr;
       const bool res = residual != nullptr;
@@ -1096,6 +1141,33 @@ extern "C" int mcn_bn_apply_stats(int dtype, const void* x, long long rows, int 
                           act_alpha, y, fs, stream);
 }
 
+// As mcn_bn_apply_stats, and also writes the ReLU bit mask of the stored output (bit e & 7 of byte
+// e >> 3 <=> y[e] > 0; rows*C/8 bytes, rounded up to a multiple of 4) for mcn_bn_bwd_reduce_mask /
+// mcn_bn_bwd_apply_mask: the layers with a fused residual need the sign of y in both backward passes,
+// and 1 bit per element replaces two 2-byte reads.
+extern "C" int mcn_bn_apply_stats_mask(int dtype, const void* x, long long rows, int C,
+                                       const double* sums, double count, float eps, float momentum,
+                                       const float* gamma, const float* beta, const void* residual,
+                                       int act, float act_alpha, void* y, void* relu_mask,
+                                       float* save_mean, float* save_invstd, float* moving_mean,
+                                       float* moving_var, void* stream) {
+  MCN_REQUIRE(sums && save_mean && save_invstd && count > 0 && relu_mask, "bn_apply_stats_mask: bad argument");
+  MCN_REQUIRE(dtype == MCN_BF16 && act == MCN_ACT_RELU && bn_use_pipe(),
+              "bn_apply_stats_mask: bf16 tensors with a ReLU only");
+  BnSumsArgs fs;
+  fs.sums = sums;
+  fs.inv_count = 1.0 / count;
+  fs.bessel = count > 1.0 ? count / (count - 1.0) : 1.0;
+  fs.eps = eps;
+  fs.momentum = momentum;
+  fs.save_mean = save_mean;
+  fs.save_invstd = save_invstd;
+  fs.moving_mean = moving_mean;
+  fs.moving_var = moving_var;
+  return bn_apply_impl<2>(dtype, x, rows, C, nullptr, nullptr, eps, gamma, beta, residual, act,
+                          act_alpha, y, fs, stream, static_cast<uint8_t*>(relu_mask));
+}
+
 template <typename T>
 static void launch_bn_bwd_reduce(const SlabLaunch& L, size_t smem, cudaStream_t st, const void* dy, const void* x,
                                  const void* y, long long rows, int C, const float* mean, const float* invstd,
@@ -1158,6 +1230,32 @@ extern "C" int mcn_bn_bwd_reduce(int dtype, const void* dy, const void* x, const
   return after_launch("bn_bwd_reduce");
 }
 
+extern "C" int mcn_bn_bwd_reduce_mask(int dtype, const void* dy, const void* x, const void* relu_mask,
+                                      long long rows, int C, const float* mean, const float* invstd,
+                                      float* sum_dz, float* sum_dz_xhat, void* stream) {
+  MCN_REQUIRE(dy && x && relu_mask && mean && invstd && sum_dz && sum_dz_xhat, "bn_bwd_reduce_mask: bad argument");
+  MCN_REQUIRE(dtype == MCN_BF16 && C % 8 == 0, "bn_bwd_reduce_mask: bf16 tensors with C %% 8 == 0 only");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  XsScratch xsc = xs_scratch(2 * C, "bn_bwd_reduce_mask");
+  if (xsc.limbs == nullptr) return MCN_EINVAL;
+  typedef __nv_bfloat16 T;
+  SlabLaunch L;
+  MCN_REQUIRE(plan_slab<T>(rows, C, &L, 3 * num_sms()), "bn_bwd_reduce_mask: no slab plan for %lld x %d", rows, C);
+  const size_t smem = 2 * (size_t)L.rowlanes * L.slab_v * Vec16<T>::N * sizeof(float);
+  const T* py = static_cast<const T*>(relu_mask);
+  const float* nul = nullptr;
+  // the mask variant has two 16-byte streams like the y-less one: same unroll choice
+  if (bn_noy_unroll() == 4)
+    ::mcn::launch(bn_bwd_reduce_kernel<T, 4, true, true>, L.grid, 256, smem, st, static_cast<const T*>(dy),
+                  static_cast<const T*>(x), py, rows, C, L.slab_v, L.rowlanes, mean, invstd, nul, nul,
+                  (int)MCN_ACT_RELU, 0.f, sum_dz, sum_dz_xhat, xsc);
+  else
+    ::mcn::launch(bn_bwd_reduce_kernel<T, 2, true, true>, L.grid, 256, smem, st, static_cast<const T*>(dy),
+                  static_cast<const T*>(x), py, rows, C, L.slab_v, L.rowlanes, mean, invstd, nul, nul,
+                  (int)MCN_ACT_RELU, 0.f, sum_dz, sum_dz_xhat, xsc);
+  return after_launch("bn_bwd_reduce_mask");
+}
+
 // Backward sums taken in a dgrad epilogue (mcn_conv2d_dgrad_tc_bnred) -> the two vectors the backward
 // apply pass (and dbeta / dgamma) want: sum_dz += S1, sum_dz_xhat += invstd * (S2 - mean * S1), in fp64.
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ mean,
@@ -1205,7 +1303,7 @@ static void launch_bwd_apply_runs(unsigned grid, cudaStream_t st, const void* dy
 }
 
 #define MCN_BWD_APPLY_PIPE(Y_, R_)                                                                         \
-  ::mcn::launch(bn_bwd_apply_pipe_kernel<T, Y_, R_>, grid, 256, kPipeBytes, st, static_cast<const T*>(dy), \
+  ::mcn::launch(bn_bwd_apply_pipe_kernel<T, (Y_) ? 1 : 0, R_>, grid, 256, kPipeBytes, st, static_cast<const T*>(dy), \
                 static_cast<const T*>(x), static_cast<const T*>(y), nvec, cvr, mean, invstd, gamma, beta,  \
                 act, act_alpha, sum_dz, sum_dz_xhat, inv_count, static_cast<T*>(dx),                       \
                 static_cast<T*>(d_residual))
@@ -1215,6 +1313,38 @@ static void launch_bwd_apply_runs(unsigned grid, cudaStream_t st, const void* dy
       static_cast<const T*>(dy), static_cast<const T*>(x), static_cast<const T*>(y), rows * L.cv,  \
       L.cv, mean, invstd, gamma, beta, act, act_alpha, sum_dz, sum_dz_xhat, inv_count,             \
       static_cast<T*>(dx), static_cast<T*>(d_residual))
+
+extern "C" int mcn_bn_bwd_apply_mask(int dtype, const void* dy, const void* x, const void* relu_mask,
+                                     long long rows, int C, const float* mean, const float* invstd,
+                                     const float* gamma, const float* sum_dz, const float* sum_dz_xhat,
+                                     double count, void* dx, void* d_residual, void* stream) {
+  MCN_REQUIRE(dy && x && relu_mask && dx && mean && invstd && sum_dz && sum_dz_xhat && count > 0,
+              "bn_bwd_apply_mask: bad argument");
+  typedef __nv_bfloat16 T;
+  const int cvr = (C % 8 == 0) ? C / 8 : 0;
+  MCN_REQUIRE(dtype == MCN_BF16 && cvr > 0 && cvr <= 256 && 256 % cvr == 0 && bn_use_pipe(),
+              "bn_bwd_apply_mask: bf16 tensors with C %% 8 == 0 and 256 %% (C / 8) == 0 only");
+  MCN_REQUIRE(reinterpret_cast<uintptr_t>(relu_mask) % 4 == 0, "bn_bwd_apply_mask: the mask must be 4-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const float inv_count = (float)(1.0 / count);
+  const long long nvec = rows * cvr;
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((nvec + 255) / 256, 3LL * num_sms()));
+  static bool ok_r = pipe_smem_ok(bn_bwd_apply_pipe_kernel<T, 2, true>, kPipeBytes + kMaskRingBytes);
+  static bool ok_n = pipe_smem_ok(bn_bwd_apply_pipe_kernel<T, 2, false>, kPipeBytes + kMaskRingBytes);
+  MCN_REQUIRE(ok_r && ok_n, "bn_bwd_apply_mask: cannot opt in to %d bytes of shared memory", kPipeBytes + kMaskRingBytes);
+  const float* nul = nullptr;
+  if (d_residual != nullptr)
+    ::mcn::launch(bn_bwd_apply_pipe_kernel<T, 2, true>, grid, 256, kPipeBytes + kMaskRingBytes, st,
+                  static_cast<const T*>(dy), static_cast<const T*>(x), static_cast<const T*>(relu_mask), nvec, cvr,
+                  mean, invstd, gamma, nul, (int)MCN_ACT_RELU, 0.f, sum_dz, sum_dz_xhat, inv_count,
+                  static_cast<T*>(dx), static_cast<T*>(d_residual));
+  else
+    ::mcn::launch(bn_bwd_apply_pipe_kernel<T, 2, false>, grid, 256, kPipeBytes + kMaskRingBytes, st,
+                  static_cast<const T*>(dy), static_cast<const T*>(x), static_cast<const T*>(relu_mask), nvec, cvr,
+                  mean, invstd, gamma, nul, (int)MCN_ACT_RELU, 0.f, sum_dz, sum_dz_xhat, inv_count,
+                  static_cast<T*>(dx), static_cast<T*>(nullptr));
+  return after_launch("bn_bwd_apply_mask");
+}
 
 extern "C" int mcn_bn_bwd_apply(int dtype, const void* dy, const void* x, const void* y,
                                 long long rows, int C, const float* mean, const float* invstd,

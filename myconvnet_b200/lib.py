@@ -51,6 +51,9 @@ SIGNATURES = {
     "mcn_bn_apply_stats": "iplipdffpppifppppp",
     "mcn_bn_infer": "iplippfpppifp",
     "mcn_bn_bwd_reduce": "ippplippppifpp",
+    "mcn_bn_apply_stats_mask": "iplipdffpppifpppppp",
+    "mcn_bn_bwd_reduce_mask": "ippplipppp",
+    "mcn_bn_bwd_apply_mask": "ippplipppppdpp",
     "mcn_bn_bwd_apply": "ippplippppifppdpp",
     "mcn_maxpool_fwd": "ipiiiiiiiiiiiipp",
     "mcn_maxpool_bwd": "ippiiiiiiiiiiiip",

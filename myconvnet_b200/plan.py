@@ -812,6 +812,21 @@ class Plan(object):
             self.bn_layers.append(node)
             return
         # finalize (mean / invstd / moving statistics) happens in the apply kernel's prologue
+        cv = c // 8
+        if (self.cdt == "bf16" and res is not None and node.attrs["act"] == 1 and c % 8 == 0 and cv <= 256
+                and 256 % cv == 0 and os.environ.get("MCN_BN_RELU_MASK", "1") != "0"
+                and os.environ.get("MCN_BN_PIPE", "1") != "0"):
+            # residual fused: backward needs the sign of the OUTPUT; the apply pass leaves it as one bit
+            # per element, so neither backward pass re-reads y (mcn_bn_bwd_*_mask)
+            mask = self.node_buf(node, "relu_mask", "bn_relu_mask:%s" % node.scope, (rows * cv + 3) // 4 * 4)
+            node.attrs["relu_mask"] = mask
+            self.L("f", "mcn_bn_apply_stats_mask", self.ccode, self.tbuf[x], rows, c, Ptr(sums),
+                   float(rows * (self.world if self.sync_bn else 1)), node.attrs["eps"], node.attrs["momentum"],
+                   pg, pbeta, pres, node.attrs["act"], node.attrs["alpha"], py, Ptr(mask), Ptr(save),
+                   Ptr(save, c * 4), self.pvar(v["mu"]) if upd else NULL, self.pvar(v["sigma"]) if upd else NULL,
+                   tag=node.scope + "/apply")
+            self.bn_layers.append(node)
+            return
         self.L("f", "mcn_bn_apply_stats", self.ccode, self.tbuf[x], rows, c, Ptr(sums),
                float(rows * (self.world if self.sync_bn else 1)), node.attrs["eps"], node.attrs["momentum"],
                pg, pbeta, pres, node.attrs["act"], node.attrs["alpha"], py, Ptr(save), Ptr(save, c * 4),
@@ -1316,10 +1331,14 @@ class Plan(object):
             self.L("b", "mcn_fill_f32", sp, 2 * c, 0.0, tag="zero")
             s1, s2 = sp, sp + c * 4
         fused = node.attrs.pop("bwd_sums", None)
+        mask = node.attrs.get("relu_mask")      # bit mask of y > 0 written by the forward apply pass
         if fused is not None:
             # the dgrad that produced gy already took sum dz / sum dz*x in its epilogue
             self.L("b", "mcn_bn_bwd_finalize", Ptr(fused), Ptr(save), Ptr(save, c * 4), c, s1, s2,
                    tag=node.scope + "/bwd_finalize")
+        elif mask is not None:
+            self.L("b", "mcn_bn_bwd_reduce_mask", self.ccode, gy, self.tbuf[x], Ptr(mask), rows, c, Ptr(save),
+                   Ptr(save, c * 4), s1, s2, tag=node.scope + "/bwd_reduce")
         else:
             self.L("b", "mcn_bn_bwd_reduce", self.ccode, gy, self.tbuf[x], py, rows, c, Ptr(save),
                    Ptr(save, c * 4), pg, pbeta, act, node.attrs["alpha"], s1, s2, tag=node.scope + "/bwd_reduce")
@@ -1351,18 +1370,20 @@ class Plan(object):
                     pres = p
                 else:
                     pres, res_tmp = self.talloc(res.size * esz)
-            if not need_x:
-                dxp, dxh = self.talloc(x.size * esz)
-                self.L("b", "mcn_bn_bwd_apply", self.ccode, gy, self.tbuf[x], py, rows, c, Ptr(save),
-                       Ptr(save, c * 4), pg, pbeta, act, node.attrs["alpha"], g1, g2, count, dxp, pres,
-                       tag=node.scope + "/bwd_apply")
-                self.tfree(dxh)
-            if need_x:
-                def emit(p):
+            def bwd_apply(p):
+                if mask is not None:
+                    self.L("b", "mcn_bn_bwd_apply_mask", self.ccode, gy, self.tbuf[x], Ptr(mask), rows, c,
+                           Ptr(save), Ptr(save, c * 4), pg, g1, g2, count, p, pres, tag=node.scope + "/bwd_apply")
+                else:
                     self.L("b", "mcn_bn_bwd_apply", self.ccode, gy, self.tbuf[x], py, rows, c, Ptr(save),
                            Ptr(save, c * 4), pg, pbeta, act, node.attrs["alpha"], g1, g2, count, p, pres,
                            tag=node.scope + "/bwd_apply")
-                self.contribute(x, x.size * esz, emit)
+            if not need_x:
+                dxp, dxh = self.talloc(x.size * esz)
+                bwd_apply(dxp)
+                self.tfree(dxh)
+            if need_x:
+                self.contribute(x, x.size * esz, bwd_apply)
             if res_tmp is not None:
                 self.L("b", "mcn_accumulate", self.ccode, self.g[res][0], pres, res.size,
                        tag="grad_accumulate")

@@ -491,3 +491,65 @@ def test_dgrad_with_fused_bn_backward_sums(L, case, act):
     scale = float(s_ref.abs().max())
     assert float((outs[0][1] - s_ref).abs().max()) <= 2e-5 * scale + 1e-4, (outs[0][1] - s_ref).abs().max()
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+# ------------------------------------------------------------------ ReLU bit mask of the residual BN layers
+@pytest.mark.parametrize("shape", [(4, 14, 14, 256), (2, 7, 9, 64), (3, 5, 5, 2048), (1, 3, 3, 8)])
+def test_bn_relu_bit_mask_variants_equal_the_output_reading_ones(L, shape):
+    """mcn_bn_apply_stats_mask writes the same y / saved statistics as mcn_bn_apply_stats plus one bit
+    per element (y > 0); mcn_bn_bwd_reduce_mask / mcn_bn_bwd_apply_mask reading that mask give exactly
+    what mcn_bn_bwd_reduce / mcn_bn_bwd_apply give reading y (bf16, fused residual, ReLU)."""
+    lib = L.load()
+    n, h, w, c = shape
+    rows = n * h * w
+    rng = np.random.default_rng(21)
+    x = dev(rng.standard_normal(shape).astype(np.float32), torch.bfloat16)
+    res = dev(rng.standard_normal(shape).astype(np.float32), torch.bfloat16)
+    gy = dev(rng.standard_normal(shape).astype(np.float32), torch.bfloat16)
+    gamma = dev(rng.uniform(0.5, 1.5, c).astype(np.float32))
+    beta = dev(rng.standard_normal(c).astype(np.float32) * 0.2)
+    sums = torch.zeros(2 * c, device="cuda", dtype=torch.float64)
+    L.check(lib.mcn_bn_stats(1, x.data_ptr(), rows, c, sums.data_ptr(), None))
+    outs = []
+    for use_mask in (False, True):
+        y = torch.empty_like(x)
+        save = torch.zeros(2, c, device="cuda")
+        mm, mv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+        mask = torch.full(((rows * c // 8 + 3) // 4 * 4,), 0xAA, device="cuda", dtype=torch.uint8)
+        if use_mask:
+            L.check(lib.mcn_bn_apply_stats_mask(1, x.data_ptr(), rows, c, sums.data_ptr(), float(rows), 1e-3, 0.9,
+                                                gamma.data_ptr(), beta.data_ptr(), res.data_ptr(), 1, 0.0,
+                                                y.data_ptr(), mask.data_ptr(), save[0].data_ptr(),
+                                                save[1].data_ptr(), mm.data_ptr(), mv.data_ptr(), None))
+        else:
+            L.check(lib.mcn_bn_apply_stats(1, x.data_ptr(), rows, c, sums.data_ptr(), float(rows), 1e-3, 0.9,
+                                           gamma.data_ptr(), beta.data_ptr(), res.data_ptr(), 1, 0.0, y.data_ptr(),
+                                           save[0].data_ptr(), save[1].data_ptr(), mm.data_ptr(), mv.data_ptr(),
+                                           None))
+        s = torch.zeros(2, c, device="cuda")
+        dx, dres = torch.empty_like(x), torch.empty_like(x)
+        if use_mask:
+            L.check(lib.mcn_bn_bwd_reduce_mask(1, gy.data_ptr(), x.data_ptr(), mask.data_ptr(), rows, c,
+                                               save[0].data_ptr(), save[1].data_ptr(), s[0].data_ptr(),
+                                               s[1].data_ptr(), None))
+            L.check(lib.mcn_bn_bwd_apply_mask(1, gy.data_ptr(), x.data_ptr(), mask.data_ptr(), rows, c,
+                                              save[0].data_ptr(), save[1].data_ptr(), gamma.data_ptr(),
+                                              s[0].data_ptr(), s[1].data_ptr(), float(rows), dx.data_ptr(),
+                                              dres.data_ptr(), None))
+        else:
+            L.check(lib.mcn_bn_bwd_reduce(1, gy.data_ptr(), x.data_ptr(), y.data_ptr(), rows, c, save[0].data_ptr(),
+                                          save[1].data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1, 0.0,
+                                          s[0].data_ptr(), s[1].data_ptr(), None))
+            L.check(lib.mcn_bn_bwd_apply(1, gy.data_ptr(), x.data_ptr(), y.data_ptr(), rows, c, save[0].data_ptr(),
+                                         save[1].data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1, 0.0,
+                                         s[0].data_ptr(), s[1].data_ptr(), float(rows), dx.data_ptr(),
+                                         dres.data_ptr(), None))
+        torch.cuda.synchronize()
+        outs.append((y, save, mm, mv, s, dx, dres, mask))
+    a, b = outs
+    for i in range(7):
+        assert torch.equal(a[i], b[i]), i
+    # the mask itself: bit e & 7 of byte e >> 3 <=> y[e] > 0
+    bits = (b[0].float().reshape(-1) > 0).to(torch.uint8).reshape(-1, 8)
+    weights = torch.tensor([1, 2, 4, 8, 16, 32, 64, 128], device="cuda", dtype=torch.uint8)
+    assert torch.equal((bits * weights).sum(1).to(torch.uint8), b[7][:rows * c // 8])

@@ -59,11 +59,15 @@ def test_plan_fusion_and_launch_counts(r50):
     # backward sums in their epilogue, which replaces its reduction pass
     assert h["mcn_conv2d_dgrad_tc"] + h["mcn_conv2d_dgrad_tc_bnred"] == 53
     assert h["mcn_conv2d_dgrad_tc_bnred"] == 29 == h["mcn_bn_bwd_finalize"]
-    assert h["mcn_bn_bwd_reduce"] == 53 - 29
-    assert h["mcn_bn_apply_stats"] == 53 and "mcn_act_fwd" not in h and "mcn_add_act_fwd" not in h
+    # the 16 layers with a fused residual leave a ReLU bit mask in the forward pass; their backward
+    # passes read it instead of the output tensor
+    assert h["mcn_bn_bwd_reduce_mask"] == 16 == h["mcn_bn_apply_stats_mask"] == h["mcn_bn_bwd_apply_mask"]
+    assert h["mcn_bn_bwd_reduce"] == 53 - 29 - 16
+    assert h["mcn_bn_apply_stats"] + h["mcn_bn_apply_stats_mask"] == 53
+    assert "mcn_act_fwd" not in h and "mcn_add_act_fwd" not in h
     # the unfused plan keeps the separate statistics pass
     hu = Plan(r50.graph, fuse_bn_stats=False).launch_histogram()
-    assert hu["mcn_conv2d_fprop_tc"] == 53 and hu["mcn_bn_stats"] == 53 and hu["mcn_bn_apply_stats"] == 53
+    assert hu["mcn_conv2d_fprop_tc"] == 53 and hu["mcn_bn_stats"] == 53 and hu["mcn_bn_apply_stats"] + hu["mcn_bn_apply_stats_mask"] == 53
     assert "mcn_accumulate" not in h                    # multi-consumer gradients add in the dgrad epilogue
     fused = [n for n in r50.graph.nodes if n.op == "bn"]
     assert sum(n.attrs["residual"] is not None for n in fused) == 16
@@ -219,7 +223,7 @@ def test_every_launch_pointer_lies_inside_its_buffer(r50):
         assert all(spans[i][1] <= spans[i + 1][0] for i in range(len(spans) - 1))
         sums_of_apply = {}
         for l in p.fwd:
-            if l.fn == "mcn_bn_apply_stats":
+            if l.fn in ("mcn_bn_apply_stats", "mcn_bn_apply_stats_mask"):
                 sums_of_apply[l.tag.rsplit("/bn/", 1)[0]] = l.args[4].buf
         fused = [l for l in p.fwd if l.fn in ("mcn_conv2d_fprop_tc_stats", "mcn_stem_conv_fprop")]
         assert len(fused) == 36
@@ -230,7 +234,8 @@ def test_every_launch_pointer_lies_inside_its_buffer(r50):
         if world > 1:
             for phase, idx, ptr, nbytes, dt, srcs in p.allreduce_points:
                 nxt = (p.fwd if phase == "f" else p.bwd)[idx]
-                assert nxt.fn == ("mcn_bn_apply_stats" if phase == "f" else "mcn_bn_bwd_apply"), nxt.fn
+                assert nxt.fn in (("mcn_bn_apply_stats", "mcn_bn_apply_stats_mask") if phase == "f"
+                                  else ("mcn_bn_bwd_apply", "mcn_bn_bwd_apply_mask")), nxt.fn
                 assert any(isinstance(a, Ptr) and a.buf is ptr.buf and a.off == ptr.off for a in nxt.args)
 
 
