@@ -441,7 +441,7 @@ __device__ __forceinline__ float dz_of(float dy, float xv, float yv, bool have_y
 // (measured 0.65 of the copy peak); four rows double that.
 // kMask: `y` is the ReLU bit mask written by the forward pass (bn_apply_pipe_kernel), one byte per
 // 8-element vector, instead of the output tensor.
-template <typename T, int U, bool kHaveY, bool kMask = false>
+template <typename T, int U, bool kHaveY, bool kMask = false, int kAct = -1>
 __global__ void __launch_bounds__(256, (U > 2 && kHaveY && !kMask) ? 2 : 3)
 bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
                      long long rows, int C, int slab_v, int rowlanes,
@@ -493,7 +493,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T*
             float dz;
             if (kMask) dz = ((mb[kMask ? u : 0] >> i) & 1u) ? g[u].get(i) : 0.f;
             else dz = dz_of<T>(g[u].get(i), xv, have_y ? o[have_y ? u : 0].get(i) : 0.f, have_y, sc[i], sf[i],
-                               act, alpha);
+                               kAct >= 0 ? kAct : act, alpha);
             s1[i] += dz;
             s2[i] = fmaf(dz, xv, s2[i]);          // sum dz*x; turned into sum dz*xhat below
           }
@@ -685,7 +685,9 @@ inline bool bn_reduce_pipe() {
 }
 
 // forward apply (+ residual): S = 1 or 2 streams
-template <typename T, int kMode, bool kRes, bool kMaskOut = false>
+// kAct >= 0: the activation is a compile-time constant (ReLU / none: the per-element run-time switch
+// over seven activations costs the streaming loop measurably), -1: run-time `act`.
+template <typename T, int kMode, bool kRes, bool kMaskOut = false, int kAct = -1>
 __global__ void __launch_bounds__(256, 3)
 bn_apply_pipe_kernel(const T* __restrict__ x, long long nvec, int cv, const float* __restrict__ mean,
                      const float* __restrict__ invstd_or_var, float eps,
@@ -724,7 +726,7 @@ bn_apply_pipe_kernel(const T* __restrict__ x, long long nvec, int cv, const floa
     for (int i = 0; i < V; ++i) {
       float f = fmaf(a.get(i), sc[i], sf[i]);
       if (kRes) f += r.get(i);
-      o.set(i, act_fwd(act, f, alpha));
+      o.set(i, act_fwd(kAct >= 0 ? kAct : act, f, alpha));
     }
     st_vec(y + v * V, o);
     if (kMaskOut) {
@@ -754,7 +756,7 @@ constexpr int kMaskRingBytes = (kPipeSlots / 2) * 256 * 4;   // bit-mask ring of
 // backward apply: S = 2 (dy, x) or 3 (+ y).  kY: 0 no y, 1 y is the output tensor, 2 y is the ReLU bit
 // mask of the forward pass (one byte per vector): two full rings (D = 6) plus a ring of 4-byte words —
 // each thread fetches the aligned word that holds its byte.
-template <typename T, int kY, bool kRes>
+template <typename T, int kY, bool kRes, int kAct = -1>
 __global__ void __launch_bounds__(256, 3)
 bn_bwd_apply_pipe_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
                          long long nvec, int cv, const float* __restrict__ mean,
@@ -814,7 +816,7 @@ bn_bwd_apply_pipe_kernel(const T* __restrict__ dy, const T* __restrict__ x, cons
       const float xv = a.get(i);
       float dz;
       if (kMask) dz = ((mb >> i) & 1u) ? g.get(i) : 0.f;
-      else dz = dz_of<T>(g.get(i), xv, kHaveY ? o.get(i) : 0.f, kHaveY, A[i], sf[i], act, alpha);
+      else dz = dz_of<T>(g.get(i), xv, kHaveY ? o.get(i) : 0.f, kHaveY, A[i], sf[i], kAct >= 0 ? kAct : act, alpha);
       ox.set(i, fmaf(A[i], dz, fmaf(B[i], xv, Cc[i])));
       if (kRes) orr.set(i, dz);
     }
@@ -1048,22 +1050,26 @@ static int bn_apply_impl(int dtype, const void* x, long long rows, int C, const 
     if (cvr > 0 && cvr <= 256 && 256 % cvr == 0 && bn_use_pipe()) {
       const long long nvec = rows * cvr;
       const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((nvec + 255) / 256, 3LL * num_sms()));
+      auto go = [&](auto kern) {
+        ::mcn::launch(kern, grid, 256, kPipeBytes, st, static_cast<const T*>(x), nvec, cvr, mean, is_or_var, eps,
+                      gamma, beta, static_cast<const T*>(residual), act, alpha, static_cast<T*>(y), fs, relu_mask);
+      };
+      // the training pass (kMode 2) gets activation-specialised instantiations for ReLU / none
+      constexpr bool kSpec = kMode == 2;
       if (relu_mask != nullptr) {
-        if (residual == nullptr || sizeof(T) != 2) {
-          set_error("bn_apply_stats_mask: bf16 tensors with a fused residual only");
+        if (residual == nullptr || sizeof(T) != 2 || act != MCN_ACT_RELU) {
+          set_error("bn_apply_stats_mask: bf16 tensors with a fused residual and a ReLU only");
           return MCN_EINVAL;
         }
-        ::mcn::launch(bn_apply_pipe_kernel<T, kMode, true, true>, grid, 256, kPipeBytes, st, static_cast<const T*>(x),
-                      nvec, cvr, mean, is_or_var, eps, gamma, beta, static_cast<const T*>(residual), act, alpha,
-                      static_cast<T*>(y), fs, relu_mask);
-      } else if (residual != nullptr)
-        ::mcn::launch(bn_apply_pipe_kernel<T, kMode, true>, grid, 256, kPipeBytes, st, static_cast<const T*>(x), nvec,
-                      cvr, mean, is_or_var, eps, gamma, beta, static_cast<const T*>(residual), act, alpha,
-                      static_cast<T*>(y), fs, relu_mask);
-      else
-        ::mcn::launch(bn_apply_pipe_kernel<T, kMode, false>, grid, 256, kPipeBytes, st, static_cast<const T*>(x), nvec,
-                      cvr, mean, is_or_var, eps, gamma, beta, static_cast<const T*>(nullptr), act, alpha,
-                      static_cast<T*>(y), fs, relu_mask);
+        go(bn_apply_pipe_kernel<T, kMode, true, true, MCN_ACT_RELU>);
+      } else if (residual != nullptr) {
+        if (kSpec && act == MCN_ACT_RELU) go(bn_apply_pipe_kernel<T, kMode, true, false, kSpec ? MCN_ACT_RELU : -1>);
+        else go(bn_apply_pipe_kernel<T, kMode, true>);
+      } else {
+        if (kSpec && act == MCN_ACT_RELU) go(bn_apply_pipe_kernel<T, kMode, false, false, kSpec ? MCN_ACT_RELU : -1>);
+        else if (kSpec && act == MCN_ACT_NONE) go(bn_apply_pipe_kernel<T, kMode, false, false, kSpec ? MCN_ACT_NONE : -1>);
+        else go(bn_apply_pipe_kernel<T, kMode, false>);
+      }
     } else if (relu_mask != nullptr) {
       set_error("bn_apply_stats_mask: needs bf16, C %% 8 == 0 and 256 %% (C / 8) == 0 (the pipe kernel)");
       return MCN_EINVAL;
@@ -1194,6 +1200,12 @@ static void launch_bn_bwd_reduce(const SlabLaunch& L, size_t smem, cudaStream_t 
   if (four && y != nullptr)
     ::mcn::launch(bn_bwd_reduce_kernel<T, 4, true>, L.grid, 256, smem, st, pdy, px, py, rows, C, L.slab_v, L.rowlanes, mean, invstd,
                                                                gamma, beta, act, alpha, sum_dz, sum_dz_xhat, xsc);
+  else if (four && act == MCN_ACT_RELU)
+    ::mcn::launch(bn_bwd_reduce_kernel<T, 4, false, false, MCN_ACT_RELU>, L.grid, 256, smem, st, pdy, px, py, rows, C,
+                  L.slab_v, L.rowlanes, mean, invstd, gamma, beta, act, alpha, sum_dz, sum_dz_xhat, xsc);
+  else if (four && act == MCN_ACT_NONE)
+    ::mcn::launch(bn_bwd_reduce_kernel<T, 4, false, false, MCN_ACT_NONE>, L.grid, 256, smem, st, pdy, px, py, rows, C,
+                  L.slab_v, L.rowlanes, mean, invstd, gamma, beta, act, alpha, sum_dz, sum_dz_xhat, xsc);
   else if (four)
     ::mcn::launch(bn_bwd_reduce_kernel<T, 4, false>, L.grid, 256, smem, st, pdy, px, py, rows, C, L.slab_v, L.rowlanes, mean, invstd,
                                                                 gamma, beta, act, alpha, sum_dz, sum_dz_xhat, xsc);
@@ -1362,9 +1374,16 @@ extern "C" int mcn_bn_bwd_apply(int dtype, const void* dy, const void* x, const 
     if (cvr > 0 && cvr <= 256 && 256 % cvr == 0 && bn_use_pipe()) {
       const long long nvec = rows * cvr;
       const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((nvec + 255) / 256, 3LL * num_sms()));
+      auto go = [&](auto kern) {
+        ::mcn::launch(kern, grid, 256, kPipeBytes, st, static_cast<const T*>(dy), static_cast<const T*>(x),
+                      static_cast<const T*>(y), nvec, cvr, mean, invstd, gamma, beta, act, act_alpha, sum_dz,
+                      sum_dz_xhat, inv_count, static_cast<T*>(dx), static_cast<T*>(d_residual));
+      };
       if (y != nullptr && d_residual != nullptr) MCN_BWD_APPLY_PIPE(true, true);
       else if (y != nullptr) MCN_BWD_APPLY_PIPE(true, false);
       else if (d_residual != nullptr) MCN_BWD_APPLY_PIPE(false, true);
+      else if (act == MCN_ACT_RELU) go(bn_bwd_apply_pipe_kernel<T, 0, false, MCN_ACT_RELU>);
+      else if (act == MCN_ACT_NONE) go(bn_bwd_apply_pipe_kernel<T, 0, false, MCN_ACT_NONE>);
       else MCN_BWD_APPLY_PIPE(false, false);
     } else if (cvr > 0 && cvr <= 256 && 256 % cvr == 0 && bn_bwd_use_runs()) {
       const long long nvec = rows * cvr;
