@@ -377,8 +377,12 @@ int mcn_transpose_add_f32(const float* in, int taps, int rows, int cols, float* 
  *              (sequence & 1) starts at mail_off + (sequence & 1)*parity_stride and holds
  *              [world][n0+n1] elements (double-buffered so that reuse can never overtake a slower
  *              peer's read, whatever the number of collective points per step)
- *   flag_off : byte offset of its flag row ([world] uint64, zero-initialised)
- *   The wait for the peers' flags is bounded by MCN_PEER_TIMEOUT_S seconds (default 1800).
+ *              Default protocol ("LL"): every 8-byte word on the wire is {32 data bits | 32-bit sequence
+ *              tag} (an fp64 value = two words), the receiver polls the words themselves: no system
+ *              fence, no flag.  A mailbox then holds [world][n0+n1] values of 2*sizeof(T) bytes, i.e.
+ *              parity_stride >= world*(n0+n1)*2*sizeof(T).  MCN_PEER_LL=0 selects the fence + flag protocol.
+ *   flag_off : byte offset of its flag row ([world] uint64, zero-initialised; fence + flag protocol only)
+ *   The wait for the peers is bounded by MCN_PEER_TIMEOUT_S seconds (default 1800).
  *   counter  : local device uint64 sequence number of this collective point (starts at 0)
  *   src0/src1: local source segments (n0, n1 elements; src1 may be NULL when n1 == 0)
  *   dst      : local destination, n0+n1 elements (may alias src0) */

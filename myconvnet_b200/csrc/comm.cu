@@ -92,6 +92,89 @@ peer_allreduce_kernel(const unsigned long long* __restrict__ peers, long long ma
   }
 }
 
+// "LL" variant (default): every 8-byte word that crosses NVLink carries its own validity tag —
+// {32 data bits | 32-bit sequence number} (an fp64 value travels as two such words) — so the receiver
+// needs neither the sender's system-scope fence nor a separate flag: it polls the words themselves.
+// An 8-byte aligned store is indivisible, a word is either old (tag != seq) or complete.  That takes
+// one NVLink round trip (the fence) and one one-way trip (the flag) off every exchange: 106 of them
+// sit on the critical path of a ResNet-50 step.  Mailbox slots are twice as large; reuse is safe by the
+// same parity argument as above (a rank sends seq + 1 only after it has finished reading seq).
+__device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(512)
+peer_allreduce_ll_kernel(const unsigned long long* __restrict__ peers, long long mail_off,
+                         long long parity_stride, unsigned long long* counter,
+                         const T* __restrict__ src0, int n0, const T* __restrict__ src1, int n1,
+                         T* __restrict__ dst, int rank, int world, unsigned long long timeout_ns) {
+  MCN_PDL_PROLOGUE();
+  constexpr int W = sizeof(T) / 4;                 // tagged words per value: 1 (fp32) or 2 (fp64)
+  __shared__ unsigned long long seq_s;
+  const int n = n0 + n1;
+  if (threadIdx.x == 0) {
+    seq_s = *counter + 1;
+    *counter = seq_s;
+  }
+  __syncthreads();
+  const unsigned long long seq = seq_s;
+  const unsigned long long tag = ((seq & 0xFFFFFFFFull) == 0 ? 0xFFFFFFFFull : (seq & 0xFFFFFFFFull)) << 32;
+  const long long box_off = mail_off + static_cast<long long>(seq & 1ull) * parity_stride;
+  // 1. push my tagged vector into slot [rank] of every rank's mailbox (my own included)
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const T v = i < n0 ? src0[i] : src1[i - n0];
+    unsigned long long w0, w1 = 0;
+    if (W == 1) {
+      w0 = tag | static_cast<unsigned long long>(__float_as_uint(static_cast<float>(v)));
+    } else {
+      const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(static_cast<double>(v)));
+      w0 = tag | (bits & 0xFFFFFFFFull);
+      w1 = tag | (bits >> 32);
+    }
+    for (int p = 0; p < world; ++p) {
+      unsigned long long* slot = reinterpret_cast<unsigned long long*>(peers[p] + box_off) +
+                                 (static_cast<size_t>(rank) * n + i) * W;
+      st_sys_u64(slot, w0);
+      if (W == 2) st_sys_u64(slot + 1, w1);
+    }
+  }
+  // 2. every thread waits for ITS elements from every rank and sums them in rank order
+  const unsigned long long* box = reinterpret_cast<const unsigned long long*>(peers[rank] + box_off);
+  unsigned long long t0 = 0, spins = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    T acc = 0;
+    for (int q = 0; q < world; ++q) {
+      const unsigned long long* slot = box + (static_cast<size_t>(q) * n + i) * W;
+      unsigned long long w0, w1 = tag;
+      for (;;) {
+        w0 = ld_sys_u64(slot);
+        if (W == 2) w1 = ld_sys_u64(slot + 1);
+        if ((w0 & 0xFFFFFFFF00000000ull) == tag && (w1 & 0xFFFFFFFF00000000ull) == tag) break;
+        if ((++spins & 0xFFFFull) == 0) {            // look at the clock every 64k polls
+          unsigned long long now;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+          if (t0 == 0) t0 = now;
+          if (now - t0 > timeout_ns) {               // a peer that is really gone: fail the launch
+            printf("mcn: peer all-reduce timeout rank=%d waiting for rank=%d seq=%llu\n", rank, q, seq);
+            __trap();
+          }
+        }
+      }
+      T v;
+      if (W == 1) v = static_cast<T>(__uint_as_float(static_cast<unsigned int>(w0 & 0xFFFFFFFFull)));
+      else v = static_cast<T>(__longlong_as_double(static_cast<long long>((w0 & 0xFFFFFFFFull) | (w1 << 32))));
+      acc = q == 0 ? v : acc + v;
+    }
+    dst[i] = acc;
+  }
+}
+
 }  // namespace
 }  // namespace mcn
 
@@ -117,6 +200,23 @@ extern "C" int mcn_peer_allreduce(const unsigned long long* peers, long long mai
               "peer_allreduce: bad argument");
   const unsigned long long tmo = peer_timeout_ns();
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static int ll = -1;
+  if (ll < 0) {
+    const char* e = getenv("MCN_PEER_LL");      // 0: fence + flag protocol (A/B)
+    ll = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (ll) {
+    // the mailbox slots hold tagged 8-byte words: parity_stride must cover world * n * 2 * sizeof(T)
+    if (is_f64)
+      ::mcn::launch(peer_allreduce_ll_kernel<double>, 1, 512, 0, st, peers, mail_off, parity_stride, counter,
+                    static_cast<const double*>(src0), n0, static_cast<const double*>(src1), n1,
+                    static_cast<double*>(dst), rank, world, tmo);
+    else
+      ::mcn::launch(peer_allreduce_ll_kernel<float>, 1, 512, 0, st, peers, mail_off, parity_stride, counter,
+                    static_cast<const float*>(src0), n0, static_cast<const float*>(src1), n1,
+                    static_cast<float*>(dst), rank, world, tmo);
+    return after_launch("peer_allreduce");
+  }
   if (is_f64)
     ::mcn::launch(peer_allreduce_kernel<double>, 1, 512, 0, st, peers, mail_off, parity_stride, flag_off, counter,
                                                      static_cast<const double*>(src0), n0,

@@ -1104,6 +1104,13 @@ struct WgradArgs {
   float* dw;          // split-K partial slices, or the gradient itself when K is not split
   long long ws_stride;  // elements between the slices of consecutive splits;
                         // dw; -1 = K is not split: every element has one owner, added in place
+  // In-kernel ordered reduction (fuse_reduce): the CTAs of one output tile meet at a ticket counter
+  // once their partial tiles are written (all CTAs of the grid are co-resident: one per SM), then
+  // split s sums share s of the tile over the slices 0 .. splits-1 IN THAT ORDER and adds it into
+  // dw_final: the separate splitk_reduce launch (and its kernel boundary) disappears, the order stays fixed.
+  int fuse_reduce;
+  float* dw_final;
+  unsigned int* tickets;   // one per output tile, zero at launch, zero again at exit
   TapTab tab;
 };
 
@@ -1302,6 +1309,75 @@ wgrad_kernel(const __grid_constant__ WgradArgs args) {
             if (rmw) o[j] += __uint_as_float(r[j]);
             else o[j] = __uint_as_float(r[j]);
           }
+      }
+    }
+    if (args.fuse_reduce) {
+      const int et = threadIdx.x - 64;
+      const int S = args.splits;
+      unsigned int* tk = args.tickets + (blockIdx.x - split * (gridDim.x / S));
+      __threadfence();          // this thread's partial-tile stores are visible device-wide ...
+      epi_bar_sync();           // ... for all 128 epilogue threads before the ticket is taken
+      if (et == 0) {
+        atomicAdd(tk, 1u);
+        unsigned int seen;
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(tk) : "memory");
+          if (seen < static_cast<unsigned int>(S)) __nanosleep(100);
+        } while (seen < static_cast<unsigned int>(S));
+      }
+      epi_bar_sync();
+      // share `split` of the tile's rows; rows >= cin were never written (and are not summed)
+      const int rows = m_halves * 128;
+      const int r0 = static_cast<int>(static_cast<long long>(split) * rows / S);
+      const int r1 = static_cast<int>(static_cast<long long>(split + 1) * rows / S);
+      const int vec_per_row = args.block_n >> 2;
+      const int items = (r1 - r0) * vec_per_row;
+      const long long tile_off = (static_cast<long long>(tap) * args.cin + mi * 64 * args.a_atoms) * args.cout +
+                                 ni * args.block_n;
+      for (int i0 = et; i0 < items; i0 += 256) {
+        // two items in flight per thread: 2*S independent 16-byte loads
+        float4 acc[2];
+        long long off[2];
+        bool ok[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int i = i0 + u * 128;
+          const int r = r0 + i / vec_per_row, c4 = i - (i / vec_per_row) * vec_per_row;
+          ok[u] = i < items && mi * 64 * args.a_atoms + r < args.cin;
+          off[u] = tile_off + static_cast<long long>(r) * args.cout + c4 * 4;
+          acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        for (int sl = 0; sl < S; ++sl) {
+          float4 p[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+            if (ok[u]) p[u] = __ldcg(reinterpret_cast<const float4*>(args.dw + sl * args.ws_stride + off[u]));
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+            if (ok[u]) {
+              acc[u].x += p[u].x;
+              acc[u].y += p[u].y;
+              acc[u].z += p[u].z;
+              acc[u].w += p[u].w;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          if (ok[u]) {
+            float4* o = reinterpret_cast<float4*>(args.dw_final + off[u]);
+            float4 v = *o;
+            v.x += acc[u].x;
+            v.y += acc[u].y;
+            v.z += acc[u].z;
+            v.w += acc[u].w;
+            *o = v;
+          }
+      }
+      // second pass through the ticket: the last CTA to finish reading leaves the counter at zero
+      epi_bar_sync();
+      if (et == 0) {
+        const unsigned int old = atomicAdd(tk, 1u);
+        if (old == 2u * static_cast<unsigned int>(S) - 1u) *tk = 0u;
       }
     }
     if (threadIdx.x == 64) RT_ADD(4, RT_NOW() - rt_e0);
@@ -2961,9 +3037,28 @@ static int wgrad_tc_impl(const mcn_conv_desc* d, const void* x, const void* dy, 
     configured = true;
   }
   dim3 grid((unsigned)(taps * a.tiles_mi * a.tiles_ni * a.splits));
+  // in-kernel reduction: needs every CTA resident at once (the tiles' CTAs wait for each other), whole
+  // 16-byte vectors and full tiles along Cout
+  static int fuse_enabled = -1;
+  if (fuse_enabled < 0) {
+    // Off by default — measured SLOWER (wgrad class 4.10 -> 4.84 ms per step, +20 us on every 1x1
+    // layer): 128 epilogue threads per SM keep ~4 KB of loads in flight where the stand-alone
+    // splitk_reduce grid (16 x 148 blocks) keeps the whole memory system busy.  MCN_WGRAD_FUSE_REDUCE=1
+    // selects it (tests / A-B).
+    const char* e = getenv("MCN_WGRAD_FUSE_REDUCE");
+    fuse_enabled = (e && e[0] == '1') ? 1 : 0;
+  }
+  a.fuse_reduce = 0;
+  if (fuse_enabled && sp.stride && (int)grid.x <= num_sms() && d->Cout % a.block_n == 0 &&
+      taps * a.tiles_mi * a.tiles_ni <= kWsCounters) {
+    const Workspace w = current_workspace();
+    a.fuse_reduce = 1;
+    a.dw_final = dw;
+    a.tickets = reinterpret_cast<unsigned int*>(w.base + kWsCounterOff);
+  }
   ::mcn::launch(wgrad_kernel, grid, 192, smem, static_cast<cudaStream_t>(stream), a);
   if ((rc = after_launch("wgrad_kernel"))) return rc;
-  if (sp.stride)
+  if (sp.stride && !a.fuse_reduce)
     return launch_splitk_reduce(sp.base, sp.stride, a.splits, dw_elems, dw, static_cast<cudaStream_t>(stream));
   return MCN_OK;
 }

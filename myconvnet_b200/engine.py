@@ -239,7 +239,8 @@ class Engine(object):
         p = self.plan
         self._flat_grads = self.view(Ptr(p.b_grad), p.n_train, torch.float32)
         self._buckets = BucketOverlap(
-            self._flat_grads, p.grad_bucket_schedule(int(self.kw.get("bucket_elems", 4 * 1024 * 1024))),
+            self._flat_grads, p.grad_bucket_schedule(int(self.kw.get("bucket_elems",
+                                                                    int(os.environ.get("MCN_BUCKET_ELEMS", 4 * 1024 * 1024))))),
             group=self.pg, overlap=os.environ.get("MCN_OVERLAP_GRADS", "1") != "0")
         self._bucket_ready = self._buckets.ready
         self._bucket_tail = self._buckets.tail
@@ -256,7 +257,8 @@ class Engine(object):
             mail, stride, off = [], [], 0
             for _, _, _, nbytes, _, _ in pts:
                 mail.append(off)
-                stride.append((self.world * nbytes + 255) // 256 * 256)
+                # tagged 8-byte words (csrc/comm.cu, "LL" protocol): a slot is twice the payload
+                stride.append((self.world * nbytes * 2 + 255) // 256 * 256)
                 off += 2 * stride[-1]                      # two mailboxes per point (sequence parity)
             flag = [off + 512 * k for k in range(len(pts))]       # [world] uint64 per point, world <= 64
             off += 512 * len(pts)
