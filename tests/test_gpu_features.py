@@ -226,6 +226,49 @@ def test_loss_variants(L, opts):
     assert rel_l2(dl.cpu().numpy().reshape(z.shape), z.grad) < 2e-5
 
 
+@pytest.mark.parametrize("opts", [dict(), dict(label_smoothing=0.1), dict(label_smoothing=0.2, spatial=True),
+                                  dict(spatial=True, label_smoothing=0.1, focal_gamma=2.0, sigmoid_focal_alpha=3.0),
+                                  dict(spatial=True)])
+@pytest.mark.parametrize("C", [21, 16, 5])
+def test_loss_thread_per_row_kernel(L, opts, C, monkeypatch):
+    """The thread-per-row softmax-CE kernel (C <= 47 and >= 4096 rows: segmentation heads) against the
+    oracle and against the warp-per-row kernel: loss, gradient and probabilities, with class weights,
+    ignored rows, uniform and 5x5 spatial label smoothing, focal factors, odd and even class counts."""
+    lib = L.load()
+    opts = dict(opts)
+    rng = np.random.default_rng(13)
+    spatial = opts.pop("spatial", False)
+    shape = (2, 50, 47) if spatial else (4700,)
+    rows = int(np.prod(shape))
+    z = torch.tensor((rng.standard_normal(shape + (C,)) * 2).astype(np.float32), requires_grad=True)
+    y = rng.integers(-1, C, size=shape).astype(np.int32)
+    cw = rng.uniform(0.5, 2.0, C).astype(np.float32)
+    ls = opts.get("label_smoothing", 0.0)
+    ref = tf_ops.classification_loss(z, torch.tensor(y).long(), C, cw, ls, focal_gamma=opts.get("focal_gamma", 0.0),
+                                     sigmoid_focal_alpha=opts.get("sigmoid_focal_alpha", 0.0),
+                                     spatial_smoothing=spatial)
+    ref.backward()
+    zd, yd, cwd = z.detach().cuda(), dev(y), dev(cw)
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("MCN_XENT_ROWS", mode)
+        loss = torch.zeros(3, dtype=torch.int64, device="cuda")
+        dl = torch.full((rows, C), 7.0, device="cuda")
+        pr = torch.full((rows, C), 7.0, device="cuda")
+        args = (rows, C, cwd.data_ptr(), ls, opts.get("focal_gamma", 0.0), opts.get("sigmoid_focal_alpha", 0.0),
+                shape[1] if spatial else 0, shape[2] if spatial else 0, 1.0 / rows)
+        L.check(lib.mcn_softmax_xent(zd.data_ptr(), yd.data_ptr(), *args, loss.data_ptr(), dl.data_ptr(), None, None))
+        L.check(lib.mcn_softmax_xent(zd.data_ptr(), None, *args, None, None, pr.data_ptr(), None))
+        torch.cuda.synchronize()
+        res[mode] = (L.xsum_value(loss.cpu().numpy()) / rows, dl.cpu().numpy(), pr.cpu().numpy())
+    for mode in ("1", "0"):
+        lv, dl, pr = res[mode]
+        assert abs(lv - ref.item()) < 2e-5 * abs(ref.item()), mode
+        assert rel_l2(dl.reshape(z.shape), z.grad) < 2e-5, mode
+        assert rel_l2(pr.reshape(z.shape), torch.softmax(z.detach(), -1)) < 1e-6, mode
+    assert rel_l2(res["1"][1], res["0"][1]) < 1e-6 and abs(res["1"][0] - res["0"][0]) < 1e-6 * abs(res["0"][0])
+
+
 SMALL_SHAPE, SMALL_BATCH, SMALL_NCLS = [128, 128, 3], 16, 16     # block_4 BN over 256 values per channel
 
 
@@ -553,3 +596,35 @@ def test_bn_relu_bit_mask_variants_equal_the_output_reading_ones(L, shape):
     bits = (b[0].float().reshape(-1) > 0).to(torch.uint8).reshape(-1, 8)
     weights = torch.tensor([1, 2, 4, 8, 16, 32, 64, 128], device="cuda", dtype=torch.uint8)
     assert torch.equal((bits * weights).sum(1).to(torch.uint8), b[7][:rows * c // 8])
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("case", [(2, 9, 7, 16, 36, 28, torch.bfloat16), (1, 8, 8, 21, 32, 32, torch.float32),
+                                  (2, 12, 10, 8, 5, 7, torch.float32), (1, 5, 6, 24, 17, 11, torch.bfloat16)])
+def test_resize_backward_table_kernel_equals_candidate_scan(L, case, mode, monkeypatch):
+    """The table-driven bilinear-resize backward (per-axis weight tables in shared memory, 16-byte channel
+    vectors where C allows) is bit-identical to the coordinate-per-candidate kernel it replaces, for the
+    three coordinate conventions, up- and down-sampling, vector and scalar channel counts."""
+    lib = L.load()
+    n, h, w, c, ho, wo, dt = case
+    code = 0 if dt == torch.float32 else 1
+    rng = np.random.default_rng(31)
+    dy = dev(rng.standard_normal((n, ho, wo, c)).astype(np.float32), dt)
+    outs = []
+    for tab in ("1", "0"):
+        monkeypatch.setenv("MCN_RESIZE_TABLE", tab)
+        dx = torch.full((n, h, w, c), 3.0, device="cuda", dtype=dt)
+        L.check(lib.mcn_resize_bilinear_bwd(code, dy.data_ptr(), n, h, w, c, ho, wo, mode, dx.data_ptr(), None))
+        torch.cuda.synchronize()
+        outs.append(dx)
+    assert torch.equal(outs[0], outs[1])
+    # and the vectorised forward agrees with the adjoint identity <resize(x), dy> == <x, resize_bwd(dy)>
+    x = dev(rng.standard_normal((n, h, w, c)).astype(np.float32), dt)
+    y = torch.empty(n, ho, wo, c, device="cuda", dtype=dt)
+    L.check(lib.mcn_resize_bilinear_fwd(code, x.data_ptr(), n, h, w, c, ho, wo, mode, y.data_ptr(), None))
+    torch.cuda.synchronize()
+    lhs = float((y.double() * dy.double()).sum())
+    rhs = float((x.double() * outs[0].double()).sum())
+    # bf16: both sides carry the rounding of ~numel stored values of unit scale
+    tol = 8e-3 * float(np.sqrt(y.numel() + x.numel())) if code else 1e-4 * (abs(lhs) + abs(rhs) + 1.0)
+    assert abs(lhs - rhs) <= tol
