@@ -2246,8 +2246,17 @@ int launch_gemm_conv(GemmConvArgs& a, int tiles_m, bool dense_out, cudaStream_t 
     const char* e = getenv("MCN_TMA_STORE");      // MCN_TMA_STORE=0: direct epilogue everywhere (A/B)
     tma_enabled = (e && e[0] == '0') ? 0 : 1;
   }
+  // n_total % 8 == 0: the output row pitch is a multiple of 16 bytes; a partial last 64-channel chunk
+  // (EfficientNet's 24 / 40 / 96 / 144 ... channels) is clipped by the hardware, its accumulator columns
+  // are exact zeros (the weight rows beyond Cout are zero-filled on load) and stats_flush skips them.
+  // MCN_TMA_STORE_MIN64=1 restores the n_total % 64 == 0 rule (A/B).
+  static int min64 = -1;
+  if (min64 < 0) {
+    const char* e = getenv("MCN_TMA_STORE_MIN64");
+    min64 = (e && e[0] == '1') ? 1 : 0;
+  }
   const bool tma = tma_enabled && dense_out && !a.e.out_f32 && a.e.bias == nullptr &&
-                   a.e.n_total % 64 == 0 && reinterpret_cast<uintptr_t>(a.e.out) % 16 == 0 &&
+                   a.e.n_total % (min64 ? 64 : 8) == 0 && reinterpret_cast<uintptr_t>(a.e.out) % 16 == 0 &&
                    a.g.m_total < (1LL << 31);
   a.e.out_rank4 = 0;
   if (tma) {

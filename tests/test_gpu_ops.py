@@ -91,6 +91,12 @@ TC_CASES = [
     (3, 16, 16, 64, 64, 5, 2, 1, "SAME"),
     (2, 12, 12, 72, 40, 3, 1, 1, "SAME"),
     (4, 7, 7, 128, 256, 3, 1, 1, "SAME"),
+    # EfficientNet-B0 pointwise shapes: channel counts that are multiples of 8 but not of 64 (the
+    # TMA-store epilogue clips the partial last 64-channel chunk; dgrad writes Cin = 16 / 24 / 96 ...)
+    (2, 28, 28, 16, 96, 1, 1, 1, "SAME"),
+    (2, 14, 14, 96, 24, 1, 1, 1, "SAME"),
+    (3, 14, 14, 144, 40, 1, 1, 1, "SAME"),
+    (2, 7, 7, 320, 1280, 1, 1, 1, "SAME"),
 ]
 
 
