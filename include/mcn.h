@@ -171,7 +171,7 @@ int mcn_bn_apply_stats(int dtype, const void* x, long long rows, int C, const do
                        const float* beta, const void* residual, int act, float act_alpha, void* y,
                        float* save_mean, float* save_invstd, float* moving_mean,
                        float* moving_var, void* stream);
-/* ReLU bit mask for the layers with a fused residual (bf16, C % 8 == 0, 256 % (C/8) == 0, act = RELU).
+/* ReLU bit mask for the layers with a fused residual (bf16, C % 8 == 0, C <= 2048, act = RELU).
  * Their backward passes need the sign of the OUTPUT y (the pre-activation cannot be rebuilt from x alone);
  * mcn_bn_apply_stats_mask is mcn_bn_apply_stats that also writes relu_mask: bit (e & 7) of byte (e >> 3)
  * is set iff the stored y[e] > 0 (rows*C/8 bytes; the buffer must be 4-byte aligned and readable up to

@@ -700,8 +700,11 @@ bn_apply_pipe_kernel(const T* __restrict__ x, long long nvec, int cv, const floa
   extern __shared__ uint4 pipe_smem[];
   const uint32_t base = static_cast<uint32_t>(__cvta_generic_to_shared(pipe_smem)) + threadIdx.x * 16u;
   constexpr uint32_t kSlot = 256u * 16u;
-  const long long stride = (long long)gridDim.x * 256;
-  long long v = (long long)blockIdx.x * 256 + threadIdx.x;
+  // (256 / cv) * cv threads work: a thread keeps its channel group from item to item for ANY cv <= 256
+  const int nthr = (256 / cv) * cv;
+  if (static_cast<int>(threadIdx.x) >= nthr) return;
+  const long long stride = (long long)gridDim.x * nthr;
+  long long v = (long long)blockIdx.x * nthr + threadIdx.x;
   // the loads do not depend on the coefficients: start them first
 #pragma unroll
   for (int d = 0; d < D; ++d) {
@@ -773,8 +776,11 @@ bn_bwd_apply_pipe_kernel(const T* __restrict__ dy, const T* __restrict__ x, cons
   constexpr uint32_t kSlot = 256u * 16u;
   const uint32_t mbase = static_cast<uint32_t>(__cvta_generic_to_shared(pipe_smem)) + kPipeBytes + threadIdx.x * 4u;
   const uint8_t* mask = reinterpret_cast<const uint8_t*>(y);
-  const long long stride = (long long)gridDim.x * 256;
-  long long v = (long long)blockIdx.x * 256 + threadIdx.x;
+  // (256 / cv) * cv threads work: a thread keeps its channel group from item to item for ANY cv <= 256
+  const int nthr = (256 / cv) * cv;
+  if (static_cast<int>(threadIdx.x) >= nthr) return;
+  const long long stride = (long long)gridDim.x * nthr;
+  long long v = (long long)blockIdx.x * nthr + threadIdx.x;
 #pragma unroll
   for (int d = 0; d < D; ++d) {
     const long long vv = v + d * stride;
@@ -1047,9 +1053,10 @@ static int bn_apply_impl(int dtype, const void* x, long long rows, int C, const 
     const int cvr = (C % V == 0) ? C / V : 0;
     // measured in the training step (profiles/r01_bn_runs_ab.txt): the run-based kernel wins for
     // the single-stream case (170 -> 140 us on 411 MB) and loses once a residual stream is added
-    if (cvr > 0 && cvr <= 256 && 256 % cvr == 0 && bn_use_pipe()) {
+    if (cvr > 0 && cvr <= 256 && bn_use_pipe()) {
       const long long nvec = rows * cvr;
-      const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((nvec + 255) / 256, 3LL * num_sms()));
+      const int nthr = (256 / cvr) * cvr;
+      const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((nvec + nthr - 1) / nthr, 3LL * num_sms()));
       auto go = [&](auto kern) {
         ::mcn::launch(kern, grid, 256, kPipeBytes, st, static_cast<const T*>(x), nvec, cvr, mean, is_or_var, eps,
                       gamma, beta, static_cast<const T*>(residual), act, alpha, static_cast<T*>(y), fs, relu_mask);
@@ -1071,7 +1078,7 @@ static int bn_apply_impl(int dtype, const void* x, long long rows, int C, const 
         else go(bn_apply_pipe_kernel<T, kMode, false>);
       }
     } else if (relu_mask != nullptr) {
-      set_error("bn_apply_stats_mask: needs bf16, C %% 8 == 0 and 256 %% (C / 8) == 0 (the pipe kernel)");
+      set_error("bn_apply_stats_mask: needs bf16, C %% 8 == 0 and C <= 2048 (the pipe kernel)");
       return MCN_EINVAL;
     } else if (cvr > 0 && cvr <= 256 && 256 % cvr == 0 && bn_use_runs() && residual == nullptr) {
       const long long nvec = rows * cvr;
@@ -1334,13 +1341,14 @@ extern "C" int mcn_bn_bwd_apply_mask(int dtype, const void* dy, const void* x, c
               "bn_bwd_apply_mask: bad argument");
   typedef __nv_bfloat16 T;
   const int cvr = (C % 8 == 0) ? C / 8 : 0;
-  MCN_REQUIRE(dtype == MCN_BF16 && cvr > 0 && cvr <= 256 && 256 % cvr == 0 && bn_use_pipe(),
-              "bn_bwd_apply_mask: bf16 tensors with C %% 8 == 0 and 256 %% (C / 8) == 0 only");
+  MCN_REQUIRE(dtype == MCN_BF16 && cvr > 0 && cvr <= 256 && bn_use_pipe(),
+              "bn_bwd_apply_mask: bf16 tensors with C %% 8 == 0 and C <= 2048 only");
   MCN_REQUIRE(reinterpret_cast<uintptr_t>(relu_mask) % 4 == 0, "bn_bwd_apply_mask: the mask must be 4-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const float inv_count = (float)(1.0 / count);
   const long long nvec = rows * cvr;
-  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((nvec + 255) / 256, 3LL * num_sms()));
+  const int nthr = (256 / cvr) * cvr;
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((nvec + nthr - 1) / nthr, 3LL * num_sms()));
   static bool ok_r = pipe_smem_ok(bn_bwd_apply_pipe_kernel<T, 2, true>, kPipeBytes + kMaskRingBytes);
   static bool ok_n = pipe_smem_ok(bn_bwd_apply_pipe_kernel<T, 2, false>, kPipeBytes + kMaskRingBytes);
   MCN_REQUIRE(ok_r && ok_n, "bn_bwd_apply_mask: cannot opt in to %d bytes of shared memory", kPipeBytes + kMaskRingBytes);
@@ -1371,9 +1379,10 @@ extern "C" int mcn_bn_bwd_apply(int dtype, const void* dy, const void* x, const 
     ChanLaunch L;
     constexpr int V = Vec16<T>::N;
     const int cvr = (C % V == 0) ? C / V : 0;
-    if (cvr > 0 && cvr <= 256 && 256 % cvr == 0 && bn_use_pipe()) {
+    if (cvr > 0 && cvr <= 256 && bn_use_pipe()) {
       const long long nvec = rows * cvr;
-      const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((nvec + 255) / 256, 3LL * num_sms()));
+      const int nthr = (256 / cvr) * cvr;
+      const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((nvec + nthr - 1) / nthr, 3LL * num_sms()));
       auto go = [&](auto kern) {
         ::mcn::launch(kern, grid, 256, kPipeBytes, st, static_cast<const T*>(dy), static_cast<const T*>(x),
                       static_cast<const T*>(y), nvec, cvr, mean, invstd, gamma, beta, act, act_alpha, sum_dz,

@@ -814,7 +814,7 @@ class Plan(object):
         # finalize (mean / invstd / moving statistics) happens in the apply kernel's prologue
         cv = c // 8
         if (self.cdt == "bf16" and res is not None and node.attrs["act"] == 1 and c % 8 == 0 and cv <= 256
-                and 256 % cv == 0 and os.environ.get("MCN_BN_RELU_MASK", "1") != "0"
+                and os.environ.get("MCN_BN_RELU_MASK", "1") != "0"
                 and os.environ.get("MCN_BN_PIPE", "1") != "0"):
             # residual fused: backward needs the sign of the OUTPUT; the apply pass leaves it as one bit
             # per element, so neither backward pass re-reads y (mcn_bn_bwd_*_mask)

@@ -1,0 +1,13 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_features.py -m gpu -q --no-header -p no:cacheprovider --tb=short -x -k "bn or batch or mask or norm" 2>&1 | grep -v "^  warnings\|UserWarning" > gpurun_out/pytest_am0.log
+grep -n "Error\|assert \|^E  \|FAILED\|passed\|failed" gpurun_out/pytest_am0.log | cut -c1-600 | head -20
+for c in effnet_b0 deeplab_r50_512 dcgan_64 r50; do
+timeout 600 python bench.py --config $c --no-cpu-baseline --steps 10 --profile-json gpurun_out/prof_r02am_$c.json 2> gpurun_out/bench_r02am_$c.err > gpurun_out/bench_r02am_$c.json
+grep "timed region" gpurun_out/bench_r02am_$c.err | tail -1; tail -2 gpurun_out/bench_r02am_$c.err | cut -c1-300
+python -c "
+import json;d=json.load(open('gpurun_out/prof_r02am_$c.json'))
+print({k[:14]:round(v['ms'],3) for k,v in d['classes'].items() if v['ms']>0.5})"
+done
+timeout 900 python -m pytest tests/test_gpu_models.py -m gpu -q --no-header -p no:cacheprovider --tb=short -x 2>&1 | grep -v "^  warnings\|UserWarning" > gpurun_out/pytest_am1.log
+grep -n "Error\|assert \|^E  \|FAILED\|passed\|failed" gpurun_out/pytest_am1.log | cut -c1-600 | head -20

@@ -537,7 +537,8 @@ def test_dgrad_with_fused_bn_backward_sums(L, case, act):
 
 
 # ------------------------------------------------------------------ ReLU bit mask of the residual BN layers
-@pytest.mark.parametrize("shape", [(4, 14, 14, 256), (2, 7, 9, 64), (3, 5, 5, 2048), (1, 3, 3, 8)])
+@pytest.mark.parametrize("shape", [(4, 14, 14, 256), (2, 7, 9, 64), (3, 5, 5, 2048), (1, 3, 3, 8), (2, 9, 7, 96),
+                                   (2, 5, 5, 1152)])
 def test_bn_relu_bit_mask_variants_equal_the_output_reading_ones(L, shape):
     """mcn_bn_apply_stats_mask writes the same y / saved statistics as mcn_bn_apply_stats plus one bit
     per element (y > 0); mcn_bn_bwd_reduce_mask / mcn_bn_bwd_apply_mask reading that mask give exactly
