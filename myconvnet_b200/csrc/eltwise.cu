@@ -109,6 +109,98 @@ __global__ void scale_bcast_bwd_kernel(const T* __restrict__ dy, const T* __rest
   }
 }
 
+// 16-byte channel vectors (C % V == 0): one index computation per V channels, 16-byte accesses.
+template <typename T>
+__global__ void __launch_bounds__(256)
+scale_bcast_fwd_vec_kernel(const T* __restrict__ x, const T* __restrict__ m, int HW, int cv, long long nvec,
+                           T* __restrict__ y) {
+  MCN_PDL_PROLOGUE();
+  constexpr int V = Vec16<T>::N;
+  const long long per_img = (long long)HW * cv;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long v0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; v0 < nvec; v0 += 4 * stride) {
+    Vec16<T> a[4], b[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long v = v0 + u * stride;
+      if (v < nvec) {
+        const long long n = v / per_img;
+        const int c = (int)(v % cv);
+        a[u] = ld_vec_stream(x + v * V);
+        b[u] = ld_vec(m + (n * cv + c) * V);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long v = v0 + u * stride;
+      if (v < nvec) {
+        Vec16<T> o;
+#pragma unroll
+        for (int e = 0; e < V; ++e) o.set(e, a[u].get(e) * b[u].get(e));
+        st_vec(y + v * V, o);
+      }
+    }
+  }
+}
+// dx = dy*m; dm[n,c] = sum_hw dy*x.  One block per (image, slab of kSlab channel vectors): 256 threads =
+// kSlab vector lanes x 256/kSlab row lanes, four rows in flight per thread, fixed-order reduction over the
+// row lanes in shared memory (no atomics).
+template <typename T, int kSlab>
+__global__ void __launch_bounds__(256)
+scale_bcast_bwd_vec_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ m, int HW,
+                           int cv, T* __restrict__ dx, float* __restrict__ dm) {
+  MCN_PDL_PROLOGUE();
+  constexpr int V = Vec16<T>::N;
+  constexpr int kRows = 256 / kSlab;
+  __shared__ float sh[kRows][kSlab * V + 1];
+  const int n = blockIdx.y;
+  const int sv = threadIdx.x % kSlab, rl = threadIdx.x / kSlab;
+  const int vec = blockIdx.x * kSlab + sv;
+  float acc[V];
+#pragma unroll
+  for (int e = 0; e < V; ++e) acc[e] = 0.f;
+  if (vec < cv) {
+    const Vec16<T> mv = ld_vec(m + ((long long)n * cv + vec) * V);
+    const long long base = (long long)n * HW * cv + vec;
+    for (int i0 = rl; i0 < HW; i0 += 4 * kRows) {
+      Vec16<T> g[4], a[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kRows;
+        if (i < HW) {
+          const long long o = (base + (long long)i * cv) * V;
+          g[u] = ld_vec_stream(dy + o);
+          a[u] = ld_vec_stream(x + o);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kRows;
+        if (i < HW) {
+          Vec16<T> o;
+#pragma unroll
+          for (int e = 0; e < V; ++e) {
+            acc[e] = fmaf(g[u].get(e), a[u].get(e), acc[e]);
+            o.set(e, g[u].get(e) * mv.get(e));
+          }
+          st_vec(dx + (base + (long long)i * cv) * V, o);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < V; ++e) sh[rl][sv * V + e] = acc[e];
+  __syncthreads();
+  for (int j = threadIdx.x; j < kSlab * V; j += 256) {
+    const int c = blockIdx.x * kSlab * V + j;
+    if (c < cv * V) {
+      float sum = 0.f;
+      for (int r = 0; r < kRows; ++r) sum += sh[r][j];
+      dm[(long long)n * cv * V + c] = sum;
+    }
+  }
+}
+
 template <typename T>
 __global__ void bias_add_kernel(T* __restrict__ y, long long total, int C,
                                 const float* __restrict__ bias) {
@@ -461,8 +553,15 @@ extern "C" int mcn_scale_bcast_fwd(int dtype, const void* x, const void* m, int 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   long long total = (long long)N * HW * C;
   MCN_DISPATCH_DTYPE(dtype, T, {
-    ::mcn::launch(scale_bcast_fwd_kernel<T>, grid_for(total, 256), 256, 0, st, 
-        static_cast<const T*>(x), static_cast<const T*>(m), HW, C, total, static_cast<T*>(y));
+    constexpr int V = Vec16<T>::N;
+    const bool vec = C % V == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(y) % 16 == 0 &&
+                     reinterpret_cast<uintptr_t>(m) % 16 == 0;
+    if (vec)
+      ::mcn::launch(scale_bcast_fwd_vec_kernel<T>, grid_for((total / V + 3) / 4, 256), 256, 0, st,
+                    static_cast<const T*>(x), static_cast<const T*>(m), HW, C / V, total / V, static_cast<T*>(y));
+    else
+      ::mcn::launch(scale_bcast_fwd_kernel<T>, grid_for(total, 256), 256, 0, st, 
+          static_cast<const T*>(x), static_cast<const T*>(m), HW, C, total, static_cast<T*>(y));
   });
   return after_launch("scale_bcast_fwd");
 }
@@ -472,9 +571,20 @@ extern "C" int mcn_scale_bcast_bwd(int dtype, const void* dy, const void* x, con
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 grid((C + 31) / 32, N), block(32, 8);
   MCN_DISPATCH_DTYPE(dtype, T, {
-    ::mcn::launch(scale_bcast_bwd_kernel<T>, grid, block, 0, st, 
-        static_cast<const T*>(dy), static_cast<const T*>(x), static_cast<const T*>(m), HW, C,
-        static_cast<T*>(dx), dm);
+    constexpr int V = Vec16<T>::N;
+    constexpr int kSlab = 4;
+    const bool vec = C % V == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(dy) % 16 == 0 &&
+                     reinterpret_cast<uintptr_t>(dx) % 16 == 0 && reinterpret_cast<uintptr_t>(m) % 16 == 0;
+    if (vec) {
+      const int cv = C / V;
+      dim3 vgrid((cv + kSlab - 1) / kSlab, N);
+      ::mcn::launch(scale_bcast_bwd_vec_kernel<T, kSlab>, vgrid, 256, 0, st, static_cast<const T*>(dy),
+                    static_cast<const T*>(x), static_cast<const T*>(m), HW, cv, static_cast<T*>(dx), dm);
+    } else {
+      ::mcn::launch(scale_bcast_bwd_kernel<T>, grid, block, 0, st, 
+          static_cast<const T*>(dy), static_cast<const T*>(x), static_cast<const T*>(m), HW, C,
+          static_cast<T*>(dx), dm);
+    }
   });
   return after_launch("scale_bcast_bwd");
 }
