@@ -383,7 +383,8 @@ int mcn_transpose_add_f32(const float* in, int taps, int rows, int cols, float* 
  *              parity_stride >= world*(n0+n1)*2*sizeof(T).  MCN_PEER_LL=0 selects the fence + flag protocol.
  *   flag_off : byte offset of its flag row ([world] uint64, zero-initialised; fence + flag protocol only)
  *   The wait for the peers is bounded by MCN_PEER_TIMEOUT_S seconds (default 1800).
- *   counter  : local device uint64 sequence number of this collective point (starts at 0)
+ *   counter  : local device uint64[2] of this collective point, zero-initialised: the sequence number
+ *              and the finishing ticket of the kernel's blocks (large vectors are shared by up to 8 blocks)
  *   src0/src1: local source segments (n0, n1 elements; src1 may be NULL when n1 == 0)
  *   dst      : local destination, n0+n1 elements (may alias src0) */
 int mcn_peer_allreduce(const unsigned long long* peers, long long mail_off, long long parity_stride,

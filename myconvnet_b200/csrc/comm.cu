@@ -20,6 +20,7 @@
 // 1800 s like a process-group timeout): ranks legitimately drift apart by seconds (checkpoint
 // writes on rank 0, lazy initialisation, a data stall), and only a peer that is really gone should
 // turn into a launch failure.
+#include <algorithm>
 #include <cstdlib>
 
 #include "mcn_common.cuh"
@@ -118,16 +119,17 @@ peer_allreduce_ll_kernel(const unsigned long long* __restrict__ peers, long long
   constexpr int W = sizeof(T) / 4;                 // tagged words per value: 1 (fp32) or 2 (fp64)
   __shared__ unsigned long long seq_s;
   const int n = n0 + n1;
-  if (threadIdx.x == 0) {
-    seq_s = *counter + 1;
-    *counter = seq_s;
-  }
+  // Several blocks share the vector (the protocol is element-wise: no block ever waits for another):
+  // every block reads the sequence number, the LAST block to finish advances it (counter[1] is its
+  // ticket) — a block can only finish after it has read the number, so nobody sees the new value early.
+  if (threadIdx.x == 0) seq_s = *counter + 1;
   __syncthreads();
   const unsigned long long seq = seq_s;
   const unsigned long long tag = ((seq & 0xFFFFFFFFull) == 0 ? 0xFFFFFFFFull : (seq & 0xFFFFFFFFull)) << 32;
   const long long box_off = mail_off + static_cast<long long>(seq & 1ull) * parity_stride;
   // 1. push my tagged vector into slot [rank] of every rank's mailbox (my own included)
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  const int first = blockIdx.x * blockDim.x + threadIdx.x, step = gridDim.x * blockDim.x;
+  for (int i = first; i < n; i += step) {
     const T v = i < n0 ? src0[i] : src1[i - n0];
     unsigned long long w0, w1 = 0;
     if (W == 1) {
@@ -147,7 +149,7 @@ peer_allreduce_ll_kernel(const unsigned long long* __restrict__ peers, long long
   // 2. every thread waits for ITS elements from every rank and sums them in rank order
   const unsigned long long* box = reinterpret_cast<const unsigned long long*>(peers[rank] + box_off);
   unsigned long long t0 = 0, spins = 0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  for (int i = first; i < n; i += step) {
     T acc = 0;
     for (int q = 0; q < world; ++q) {
       const unsigned long long* slot = box + (static_cast<size_t>(q) * n + i) * W;
@@ -172,6 +174,15 @@ peer_allreduce_ll_kernel(const unsigned long long* __restrict__ peers, long long
       acc = q == 0 ? v : acc + v;
     }
     dst[i] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long t = atomicAdd(counter + 1, 1ull);
+    if (t == gridDim.x - 1) {
+      counter[0] = seq;
+      counter[1] = 0ull;
+    }
   }
 }
 
@@ -206,13 +217,15 @@ extern "C" int mcn_peer_allreduce(const unsigned long long* peers, long long mai
     ll = (e && e[0] == '0') ? 0 : 1;
   }
   if (ll) {
-    // the mailbox slots hold tagged 8-byte words: parity_stride must cover world * n * 2 * sizeof(T)
+    // the mailbox slots hold tagged 8-byte words: parity_stride must cover world * n * 2 * sizeof(T);
+    // `counter` is two uint64: the sequence number and the finishing ticket of the blocks
+    const int blocks = std::max(1, std::min(8, (n0 + n1 + 511) / 512));
     if (is_f64)
-      ::mcn::launch(peer_allreduce_ll_kernel<double>, 1, 512, 0, st, peers, mail_off, parity_stride, counter,
+      ::mcn::launch(peer_allreduce_ll_kernel<double>, blocks, 512, 0, st, peers, mail_off, parity_stride, counter,
                     static_cast<const double*>(src0), n0, static_cast<const double*>(src1), n1,
                     static_cast<double*>(dst), rank, world, tmo);
     else
-      ::mcn::launch(peer_allreduce_ll_kernel<float>, 1, 512, 0, st, peers, mail_off, parity_stride, counter,
+      ::mcn::launch(peer_allreduce_ll_kernel<float>, blocks, 512, 0, st, peers, mail_off, parity_stride, counter,
                     static_cast<const float*>(src0), n0, static_cast<const float*>(src1), n1,
                     static_cast<float*>(dst), rank, world, tmo);
     return after_launch("peer_allreduce");

@@ -35,7 +35,12 @@ def dp_parity(rank, world, dtype="bf16", graph=True, steps=3, group=None):
     eng = Engine(pm, world_size=world, rank=rank, process_group=group, use_cuda_graph=graph,
                  base_learning_rate=0.05)
     eng.set_variables(vals)
-    losses = [eng.train_step(X, Y) for _ in range(steps)]
+    # variables are compared after ONE step from identical state (two separately rounded bf16 pipelines
+    # drift apart chaotically afterwards: 3e-2 after four steps on 2 ranks, 6e-2 after three on 8); the
+    # later steps are reported as loss curves and as the final drift
+    losses = [eng.train_step(X, Y)]
+    v_dp_first = eng.get_variables()
+    losses += [eng.train_step(X, Y) for _ in range(steps - 1)]
     v_dp = eng.get_variables()
     lt = torch.tensor(losses, dtype=torch.float64, device="cuda")
     dist.all_reduce(lt, group=group)
@@ -52,13 +57,18 @@ def dp_parity(rank, world, dtype="bf16", graph=True, steps=3, group=None):
         pm1, _ = resnet50(shape, ncls, batch_size=b * world, compute_dtype=dtype)
         e1 = Engine(pm1, base_learning_rate=0.05)
         e1.set_variables(vals)
-        l1 = [e1.train_step(Xg, Yg) for _ in range(steps)]
+        l1 = [e1.train_step(Xg, Yg)]
+        v1_first = e1.get_variables()
+        l1 += [e1.train_step(Xg, Yg) for _ in range(steps - 1)]
         v1 = e1.get_variables()
-        worst = max((_rel_l2(v_dp[k], v1[k]), k) for k in v1 if "weights" in k or k.endswith("gamma"))
-        tol_v = 2e-3 if dtype == "f32" else 6e-2
+        worst = max((_rel_l2(v_dp_first[k], v1_first[k]), k) for k in v1 if "weights" in k or k.endswith("gamma"))
+        final = max((_rel_l2(v_dp[k], v1[k]), k) for k in v1 if "weights" in k or k.endswith("gamma"))
+        tol_v = 2e-3 if dtype == "f32" else 3e-2
         tol_l = 1e-3 * abs(l1[0]) + (1e-4 if dtype == "f32" else 3e-2)
         out.update({"loss_dp": [float(x) for x in lt.tolist()], "loss_one_device": [float(x) for x in l1],
                     "worst_variable": worst[1], "worst_variable_rel_l2": worst[0],
+                    "compared": "all weights and gammas after the first step (identical initial state)",
+                    "final_drift_variable": final[1], "final_drift_rel_l2": final[0],
                     "pass": bool(worst[0] < tol_v and abs(float(lt[0]) - l1[0]) < tol_l and out["replicas_identical"])})
         del e1
     return out

@@ -218,7 +218,7 @@ class Engine(object):
                         else:
                             a0, n0, a1, n1 = seg[0].data_ptr(), seg[0].numel(), seg[1].data_ptr(), seg[1].numel()
                         check(self.lib.mcn_peer_allreduce(
-                            peer["peers"], peer["mail"][k], peer["stride"][k], peer["flag"][k], peer["ctr"] + 8 * k,
+                            peer["peers"], peer["mail"][k], peer["stride"][k], peer["flag"][k], peer["ctr"] + 16 * k,
                             1 if t.dtype == torch.float64 else 0, a0, n0, a1, n1, t.data_ptr(), self.rank,
                             self.world, stream), "peer_allreduce")
                     else:
@@ -267,7 +267,7 @@ class Engine(object):
             torch.cuda.synchronize(self.device)
             group = self.pg if self.pg is not None else dist.group.WORLD
             hdl = symm.rendezvous(buf, group)
-            ctr = torch.zeros(len(pts), dtype=torch.int64, device=self.device)
+            ctr = torch.zeros(2 * len(pts), dtype=torch.int64, device=self.device)   # [sequence, ticket] per point
             torch.cuda.synchronize(self.device)
             dist.barrier(group=group)                          # every region is zeroed before any push
             self._peer = {"buf": buf, "hdl": hdl, "ctr_t": ctr, "ctr": ctr.data_ptr(),

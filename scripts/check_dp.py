@@ -56,16 +56,21 @@ def main():
             report("peer memory mapped", eng._peer is not None)
             if eng._peer is not None:
                 # 1. the collective itself, on the first BN layer's mailbox
-                t = torch.arange(128, dtype=torch.float64, device="cuda") * (rank + 1) + 0.25 * rank
                 pr = eng._peer
-                for rep in range(3):
-                    u = t.clone() + rep
-                    L.check(eng.lib.mcn_peer_allreduce(pr["peers"], pr["mail"][0], pr["stride"][0], pr["flag"][0], pr["ctr"], 1,
-                                                       u.data_ptr(), 128, None, 0, u.data_ptr(), rank, world,
-                                                       torch.cuda.current_stream().cuda_stream))
-                    torch.cuda.synchronize()
-                    ref = sum(torch.arange(128, dtype=torch.float64) * (r + 1) + 0.25 * r + rep for r in range(world))
-                    report("peer all-reduce rep %d" % rep, bool(torch.equal(u.cpu(), ref)))
+                pts = eng.plan.allreduce_points
+                # the first BN layer's mailbox (one block) and the largest fp64 one (several blocks share the vector)
+                big = max((k for k in range(len(pts)) if pts[k][4] == "f64"), key=lambda k: pts[k][3])
+                for k in (0, big):
+                    n = pts[k][3] // 8
+                    t = torch.arange(n, dtype=torch.float64, device="cuda") * (rank + 1) + 0.25 * rank
+                    for rep in range(3):
+                        u = t.clone() + rep
+                        L.check(eng.lib.mcn_peer_allreduce(pr["peers"], pr["mail"][k], pr["stride"][k], pr["flag"][k],
+                                                           pr["ctr"] + 16 * k, 1, u.data_ptr(), n, None, 0, u.data_ptr(),
+                                                           rank, world, torch.cuda.current_stream().cuda_stream))
+                        torch.cuda.synchronize()
+                        ref = sum(torch.arange(n, dtype=torch.float64) * (r + 1) + 0.25 * r + rep for r in range(world))
+                        report("peer all-reduce n=%d rep %d" % (n, rep), bool(torch.equal(u.cpu(), ref)))
         steps = 4 if graph else 2
         losses = [eng.train_step(X, Y) for _ in range(steps)]
         v_dp = eng.get_variables()
