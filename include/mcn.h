@@ -196,12 +196,15 @@ int mcn_bn_bwd_apply_mask(int dtype, const void* dy, const void* x, const void* 
  * MCN_ACT_NONE or MCN_ACT_RELU (the forward pass's own constants: same fmaf, same mask).  sums is an
  * fp64 [2*C] accumulator (zero it first; exact, order-independent like the forward statistics).
  * mcn_bn_bwd_finalize turns it into what mcn_bn_bwd_apply (and dbeta / dgamma) expect:
- * sum_dz += S1, sum_dz_xhat += invstd*(S2 - mean*S1).  Replaces mcn_bn_bwd_reduce for that layer. */
+ * sum_dz += S1, sum_dz_xhat += invstd*(S2 - mean*S1).  Replaces mcn_bn_bwd_reduce for that layer.
+ * With sum_dz / sum_dz_xhat given (both or neither), the block that completes a channel group applies
+ * that very formula itself and no mcn_bn_bwd_finalize launch is needed (sums then stays untouched but
+ * must still be a valid [2*C] buffer). */
 int mcn_conv2d_dgrad_bnred_supported(const mcn_conv_desc* d, int a_mode);
 int mcn_conv2d_dgrad_tc_bnred(const mcn_conv_desc* d, const void* dy, const void* w_hwio, void* dx,
                               int a_mode, const void* bn_x, const float* mean, const float* invstd,
                               const float* gamma, const float* beta, int act, double* sums,
-                              void* stream);
+                              float* sum_dz, float* sum_dz_xhat, void* stream);
 int mcn_bn_bwd_finalize(const double* sums, const float* mean, const float* invstd, int C,
                         float* sum_dz, float* sum_dz_xhat, void* stream);
 /* inference mode: y = act(gamma*(x-mean)/sqrt(var+eps)+beta [+ residual]) */

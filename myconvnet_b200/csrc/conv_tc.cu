@@ -144,6 +144,10 @@ struct EpiArgs {
   const float* red_invstd;
   const float* red_gamma;
   const float* red_beta;
+  // when set, the block that completes a channel group writes the FINAL backward sums itself:
+  // red_out1[c] += sum dz, red_out2[c] += invstd*(sum dz*x - mean*sum dz)  (no finalize launch)
+  float* red_out1;
+  float* red_out2;
 };
 
 // Fused BN statistics (conv -> BN): the epilogue already holds every output element in
@@ -209,11 +213,23 @@ __device__ __forceinline__ void stats_flush(const EpiArgs& e, float* acc, int n_
   if (*flag) {
     const int c0 = n_t * e.block_n;
     const int w = min(e.n_total - c0, e.block_n);
-    for (int i = et; i < 2 * w; i += 128) {
-      const int which = i >= w ? 1 : 0;
-      const int idx = which * e.n_total + c0 + i - which * w;
-      const double prev = e.stats[idx];
-      e.stats[idx] = prev + xs::read_clear(e.xs, 2 * e.n_total, idx);
+    if (e.red && e.red_out1 != nullptr) {
+      // same arithmetic as bn_bwd_finalize_kernel (bn.cu), on the exact sums
+      for (int i = et; i < w; i += 128) {
+        const int c = c0 + i;
+        const double s1 = xs::read_clear(e.xs, 2 * e.n_total, c);
+        const double s2 = xs::read_clear(e.xs, 2 * e.n_total, e.n_total + c);
+        e.red_out1[c] += static_cast<float>(s1);
+        e.red_out2[c] += static_cast<float>(static_cast<double>(e.red_invstd[c]) *
+                                            (s2 - static_cast<double>(e.red_mean[c]) * s1));
+      }
+    } else {
+      for (int i = et; i < 2 * w; i += 128) {
+        const int which = i >= w ? 1 : 0;
+        const int idx = which * e.n_total + c0 + i - which * w;
+        const double prev = e.stats[idx];
+        e.stats[idx] = prev + xs::read_clear(e.xs, 2 * e.n_total, idx);
+      }
     }
     if (et == 0) xs::release(e.xs_counter + n_t);
   }
@@ -2206,6 +2222,8 @@ struct BnRed {
   const float *mean, *invstd, *gamma, *beta;
   int act;         // MCN_ACT_NONE or MCN_ACT_RELU
   double* sums;    // [2*C]: += sum dz | sum dz*x
+  float* out1;     // optional: final sums written by the kernel itself (sum_dz += ...,
+  float* out2;     //           sum_dz_xhat += ...): no mcn_bn_bwd_finalize launch
 };
 void attach_red(EpiArgs* e, const BnRed* red) {
   e->red = 0;
@@ -2216,6 +2234,8 @@ void attach_red(EpiArgs* e, const BnRed* red) {
   e->red_invstd = red->invstd;
   e->red_gamma = red->gamma;
   e->red_beta = red->beta;
+  e->red_out1 = red->out1;
+  e->red_out2 = red->out2;
 }
 
 // dense_out: the output is a plain [m_total, n_total] matrix whose row order is the tile order (1x1
@@ -2750,14 +2770,16 @@ extern "C" int mcn_conv2d_dgrad_bnred_supported(const mcn_conv_desc* d, int a_mo
 extern "C" int mcn_conv2d_dgrad_tc_bnred(const mcn_conv_desc* d, const void* dy, const void* w_hwio,
                                          void* dx, int a_mode, const void* bn_x, const float* mean,
                                          const float* invstd, const float* gamma, const float* beta,
-                                         int act, double* sums, void* stream) {
+                                         int act, double* sums, float* sum_dz, float* sum_dz_xhat,
+                                         void* stream) {
   MCN_REQUIRE(d && dy && w_hwio && dx && bn_x && mean && invstd && sums, "dgrad_tc_bnred: null argument");
+  MCN_REQUIRE((sum_dz == nullptr) == (sum_dz_xhat == nullptr), "dgrad_tc_bnred: sum_dz and sum_dz_xhat go together");
   MCN_REQUIRE(act == MCN_ACT_NONE || act == MCN_ACT_RELU, "dgrad_tc_bnred: activation %d not supported", act);
   MCN_REQUIRE(mcn_conv2d_dgrad_bnred_supported(d, a_mode), "dgrad_tc_bnred: geometry not supported");
   MCN_REQUIRE(reinterpret_cast<uintptr_t>(dx) % 16 == 0 && reinterpret_cast<uintptr_t>(bn_x) % 16 == 0,
               "dgrad_tc_bnred: dx and bn_x must be 16-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const BnRed red{bn_x, mean, invstd, gamma, beta, act, sums};
+  const BnRed red{bn_x, mean, invstd, gamma, beta, act, sums, sum_dz, sum_dz_xhat};
   if (a_mode == 2) {
     if (halo_eligible(d->Cout, d->kh, d->kw, d->sh, d->sw, d->dh, d->dw, d->H, d->W))
       return launch_halo(dy, d->Cout, d->Wo, d->Ho, d->N, w_hwio, d->Cin, d->Cin, d->kh, d->kw, d->dh,

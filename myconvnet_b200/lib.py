@@ -90,7 +90,7 @@ SIGNATURES = {
     "mcn_transpose_add_f32": "piiip",
     "mcn_peer_allreduce": "plllpipipipii",
     "mcn_xsum_decode": "pippi",
-    "mcn_conv2d_dgrad_tc_bnred": "Dpppipppppip",
+    "mcn_conv2d_dgrad_tc_bnred": "Dpppipppppippp",
     "mcn_bn_bwd_finalize": "pppipp",
     "mcn_gn_fwd": "ipiliifpppp",
     "mcn_gn_bwd": "ippiliipppppp",

@@ -1213,10 +1213,16 @@ class Plan(object):
                 sums = self.node_buf(bn, "bwd_sums", "bn_bwd_sums:%s" % bn.scope, 2 * cb * 8, "zero")
                 bn.attrs["bwd_sums"] = sums
                 bv, sv = bn.vars, bn.attrs["save"]
+                # when the layer's sums go straight into dbeta / dgamma (the usual case) the dgrad's last
+                # block writes the final values itself: no finalize launch
+                o1 = o2 = NULL
+                if self._bn_sums_direct(bn) and os.environ.get("MCN_BN_BWD_FINALIZE_LAUNCH", "0") != "1":
+                    o1, o2 = self.pgrad(bv["beta"]), self.pgrad(bv["gamma"])
+                    bn.attrs["bwd_sums_final"] = True
                 self.L("b", "mcn_conv2d_dgrad_tc_bnred", d, gy, self._w_bf16(node), p, self.conv_mode,
                        self.tbuf[bx], Ptr(sv), Ptr(sv, cb * 4),
                        self.pvar(bv["gamma"]) if "gamma" in bv else NULL,
-                       self.pvar(bv["beta"]) if "beta" in bv else NULL, bn.attrs["act"], Ptr(sums),
+                       self.pvar(bv["beta"]) if "beta" in bv else NULL, bn.attrs["act"], Ptr(sums), o1, o2,
                        tag=node.scope + "/dgrad+bn_bwd_sums")
             self.contribute(x, x.size * 2, emit_dgrad,
                             emit_acc=lambda p: self.L("b", "mcn_conv2d_dgrad_tc", d, gy, self._w_bf16(node), p, 1,
@@ -1306,6 +1312,13 @@ class Plan(object):
                                                   1, self.conv_mode, 1, tag=node.scope + "/dgrad+"))
         self._ws_finish(node)
 
+    def _bn_sums_direct(self, node):
+        """The layer's local backward sums double as dbeta / dgamma (both trained, used by this node only)."""
+        v = node.vars
+        return ("beta" in v and self._var_trains(v["beta"]) and "gamma" in v
+                and self._var_trains(v["gamma"]) and self._bn_var_uses[v["beta"]] == 1
+                and self._bn_var_uses[v["gamma"]] == 1)
+
     def _b_bn(self, node, gy):
         x = node.inputs[0]
         y = node.attrs["final"]
@@ -1322,9 +1335,7 @@ class Plan(object):
         py = self.tbuf[y] if (res is not None and act != 0) else NULL
         # local sums double as dbeta / dgamma; without a trainable beta/gamma they go to scratch
         scratch = None
-        direct = ("beta" in v and self._var_trains(v["beta"]) and "gamma" in v
-                  and self._var_trains(v["gamma"]) and self._bn_var_uses[v["beta"]] == 1
-                  and self._bn_var_uses[v["gamma"]] == 1)
+        direct = self._bn_sums_direct(node)
         if direct:
             s1, s2 = self.pgrad(v["beta"]), self.pgrad(v["gamma"])
         else:
@@ -1335,7 +1346,9 @@ class Plan(object):
             s1, s2 = sp, sp + c * 4
         fused = node.attrs.pop("bwd_sums", None)
         mask = node.attrs.get("relu_mask")      # bit mask of y > 0 written by the forward apply pass
-        if fused is not None:
+        if fused is not None and node.attrs.pop("bwd_sums_final", False):
+            pass        # ... and its last block already wrote the final sums into s1 / s2
+        elif fused is not None:
             # the dgrad that produced gy already took sum dz / sum dz*x in its epilogue
             self.L("b", "mcn_bn_bwd_finalize", Ptr(fused), Ptr(save), Ptr(save, c * 4), c, s1, s2,
                    tag=node.scope + "/bwd_finalize")

@@ -524,10 +524,20 @@ def test_dgrad_with_fused_bn_backward_sums(L, case, act):
         sums = torch.zeros(2 * ci, device="cuda", dtype=torch.float64)
         L.check(lib.mcn_conv2d_dgrad_tc_bnred(d, dy.data_ptr(), w_hwio.data_ptr(), dx.data_ptr(), 2, x.data_ptr(),
                                               mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
-                                              beta.data_ptr(), act, sums.data_ptr(), None))
+                                              beta.data_ptr(), act, sums.data_ptr(), None, None, None))
         s = torch.zeros(2, ci, device="cuda")
         L.check(lib.mcn_bn_bwd_finalize(sums.data_ptr(), mean.data_ptr(), invstd.data_ptr(), ci,
                                         s[0].data_ptr(), s[1].data_ptr(), None))
+        # the variant whose last block writes the final sums itself: same values, bit for bit
+        dx3 = torch.full_like(dx_ref, 5.0)
+        sums3 = torch.zeros(2 * ci, device="cuda", dtype=torch.float64)
+        s3 = torch.zeros(2, ci, device="cuda")
+        L.check(lib.mcn_conv2d_dgrad_tc_bnred(d, dy.data_ptr(), w_hwio.data_ptr(), dx3.data_ptr(), 2, x.data_ptr(),
+                                              mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
+                                              beta.data_ptr(), act, sums3.data_ptr(), s3[0].data_ptr(),
+                                              s3[1].data_ptr(), None))
+        torch.cuda.synchronize()
+        assert torch.equal(dx3, dx) and torch.equal(s3, s)
         outs.append((dx, s))
     torch.cuda.synchronize()
     assert torch.equal(outs[0][0], dx_ref)
