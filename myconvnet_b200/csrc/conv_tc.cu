@@ -1127,6 +1127,12 @@ struct WgradArgs {
   int fuse_reduce;
   float* dw_final;
   unsigned int* tickets;   // one per output tile, zero at launch, zero again at exit
+  // Partial tiles through TMA stores (tma_out): each epilogue warp stages 32 rows x 32 fp32 columns
+  // (128-byte rows, the map's swizzle) in the idle pipeline buffers and one lane issues a bulk store
+  // into the 4-D view (Cout, Cin, tap, split) of the slices; rows >= Cin are clipped by the map.
+  // (The direct write-out is one 128-byte row per thread: 256 KB per CTA took ~20k cycles.)
+  int tma_out;
+  CUtensorMap mapOut;
   TapTab tab;
 };
 
@@ -1305,6 +1311,36 @@ wgrad_kernel(const __grid_constant__ WgradArgs args) {
     if (threadIdx.x == 64) RT_ADD(3, RT_NOW() - rt_e0);
     ptx::tc_fence_after();
     const int quad = warp & 3;
+    if (args.tma_out) {
+      // every MMA has completed (tmem_full): the operand ring is free — two 4 KB staging tiles per warp
+      uint8_t* stg = smem + static_cast<size_t>(quad) * 2 * 4096;
+      const uint32_t swz = static_cast<uint32_t>(lane & 7) << 4;
+      int bi = 0;
+      for (int hc = 0; hc < m_halves * args.block_n; hc += 32) {
+        const int half = hc / args.block_n, c0 = hc - half * args.block_n;
+        const int row0 = mi * 64 * args.a_atoms + half * 128 + quad * 32;     // warp-uniform
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(hc), r);
+        ptx::tmem_ld_wait();
+        if (row0 >= args.cin || ni * args.block_n + c0 >= args.cout) continue;
+        uint8_t* buf = stg + bi * 4096;
+        if (lane == 0) ptx::bulk_wait_read<1>();      // the store that last used this buffer has read it
+        __syncwarp();
+        const uint32_t rowaddr = ptx::smem_u32(buf) + static_cast<uint32_t>(lane) * 128u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          ptx::st_shared_v4(rowaddr + ((static_cast<uint32_t>(j) << 4) ^ swz), r[4 * j], r[4 * j + 1], r[4 * j + 2],
+                            r[4 * j + 3]);
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::tma_store_4d(&args.mapOut, buf, ni * args.block_n + c0, row0, tap, split);
+          ptx::bulk_commit();
+        }
+        bi ^= 1;
+      }
+      if (lane == 0) ptx::bulk_wait_all();
+    } else
     for (int hc = 0; hc < m_halves * args.block_n; hc += 32) {
       const int half = hc / args.block_n, c0 = hc - half * args.block_n;
       const int ci = mi * 64 * args.a_atoms + half * 128 + quad * 32 + lane;
@@ -2059,6 +2095,29 @@ int encode_tiled(CUtensorMap* m, const void* base, int rank, const uint64_t* dim
               (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
               (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
               box[0], box[1], rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+    return MCN_ECUDA;
+  }
+  return MCN_OK;
+}
+
+// fp32 4-D view (Cout, Cin, tap, split) of the split-K slices, box 32 x 32 x 1 x 1 (128-byte rows)
+int encode_wgrad_slices(CUtensorMap* m, const float* base, int cout, int cin, int taps, int splits,
+                        long long slice_stride) {
+  static EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(driver_symbol("cuTensorMapEncodeTiled"));
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled unavailable");
+    return MCN_ECUDA;
+  }
+  cuuint64_t gd[4] = {(cuuint64_t)cout, (cuuint64_t)cin, (cuuint64_t)taps, (cuuint64_t)splits};
+  cuuint64_t gs[3] = {(cuuint64_t)cout * 4, (cuuint64_t)cin * cout * 4, (cuuint64_t)slice_stride * 4};
+  cuuint32_t bx[4] = {32, 32, 1, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gd, gs, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (wgrad slices) failed (%d): cout %d cin %d taps %d splits %d stride %lld",
+              (int)r, cout, cin, taps, splits, slice_stride);
     return MCN_ECUDA;
   }
   return MCN_OK;
@@ -3016,7 +3075,12 @@ static int wgrad_tc_impl(const mcn_conv_desc* d, const void* x, const void* dy, 
     // two full waves of one-CTA-per-SM at most: rounding the split count UP (304 CTAs for a base of
     // 16) left a third, nearly empty wave behind.  Wide tiles: one wave (every extra split is another
     // 256 KB partial tile to write and sum)
-    int want = std::max(1, ((wide ? 1 : 2) * num_sms()) / base);
+    static int wave_pct = -1;      // MCN_WGRAD_WAVE_PCT: fraction of the SMs a wave of splits may fill (A/B)
+    if (wave_pct < 0) {
+      const char* e = getenv("MCN_WGRAD_WAVE_PCT");
+      wave_pct = e ? std::max(10, std::min(100, atoi(e))) : 100;
+    }
+    int want = std::max(1, ((wide ? 1 : 2) * num_sms() * wave_pct / 100) / base);
     // one CTA per SM is resident at a time, so a grid that already fills 3/4 of the SMs gains
     // nothing from splitting K — and an un-split K needs no slices and no second pass
     if (4 * base >= 3 * num_sms()) want = 1;
@@ -3086,6 +3150,18 @@ static int wgrad_tc_impl(const mcn_conv_desc* d, const void* x, const void* dy, 
     a.fuse_reduce = 1;
     a.dw_final = dw;
     a.tickets = reinterpret_cast<unsigned int*>(w.base + kWsCounterOff);
+  }
+  // partial tiles through TMA stores: split-K slices only, 16-byte aligned rows, staging fits the ring
+  static int tma_out_enabled = -1;
+  if (tma_out_enabled < 0) {
+    const char* e = getenv("MCN_WGRAD_TMA_OUT");      // 0: one 128-byte row per thread (A/B)
+    tma_out_enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  a.tma_out = 0;
+  if (tma_out_enabled && sp.stride && !a.fuse_reduce && d->Cout % 4 == 0 && d->Cout % 32 == 0 &&
+      (size_t)a.stages * stage_bytes >= 8 * 4096) {
+    if ((rc = encode_wgrad_slices(&a.mapOut, sp.base, d->Cout, d->Cin, taps, a.splits, sp.stride))) return rc;
+    a.tma_out = 1;
   }
   ::mcn::launch(wgrad_kernel, grid, 192, smem, static_cast<cudaStream_t>(stream), a);
   if ((rc = after_launch("wgrad_kernel"))) return rc;
