@@ -1473,6 +1473,8 @@ struct WgradHaloArgs {
   int lbo[kWhMaxGroups][kWhMaxAcc];    // byte distance to the operand's second 64-row atom
   short tap_lo[kWhMaxGroups][kWhMaxAcc];  // tap written by accumulator rows 0..63 (-1: discard)
   short tap_hi[kWhMaxGroups][kWhMaxAcc];  // tap of rows 64..127 (-2: same tap, channels + 64)
+  int tma_out;          // partial tiles through TMA stores (see WgradArgs::tma_out)
+  CUtensorMap mapOut;   // fp32 4-D view (Cout, Cin, tap, split) of the slices
 };
 
 __global__ void __launch_bounds__(192, 1)
@@ -1583,6 +1585,42 @@ wgrad_halo_kernel(const __grid_constant__ WgradHaloArgs args) {
     ptx::tc_fence_after();
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
+    if (args.tma_out) {
+      // a warp's 32 accumulator rows are 32 consecutive input channels of ONE tap: one 32 x 32 box
+      uint8_t* stg = smem + static_cast<size_t>(quad) * 2 * 4096;
+      const uint32_t swz = static_cast<uint32_t>(lane & 7) << 4;
+      int bi = 0;
+      for (int acc = 0; acc < args.n_acc; ++acc) {
+        const int tlo = args.tap_lo[g][acc], thi = args.tap_hi[g][acc];
+        const int row_w = quad * 32;
+        const int tap = (thi == -2) ? tlo : (row_w < 64 ? tlo : thi);
+        const int ci0 = ci_t * args.ci_tile + ((thi == -2) ? row_w : (row_w & 63));
+        for (int c0 = 0; c0 < args.block_n; c0 += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                                 static_cast<uint32_t>(acc * args.block_n + c0), r);
+          ptx::tmem_ld_wait();
+          const int co0 = co_t * args.block_n + c0;
+          if (tap < 0 || ci0 >= args.cin || co0 >= args.cout) continue;
+          uint8_t* buf = stg + bi * 4096;
+          if (lane == 0) ptx::bulk_wait_read<1>();
+          __syncwarp();
+          const uint32_t rowaddr = ptx::smem_u32(buf) + static_cast<uint32_t>(lane) * 128u;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            ptx::st_shared_v4(rowaddr + ((static_cast<uint32_t>(j) << 4) ^ swz), r[4 * j], r[4 * j + 1],
+                              r[4 * j + 2], r[4 * j + 3]);
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_4d(&args.mapOut, buf, co0, ci0, tap, split);
+            ptx::bulk_commit();
+          }
+          bi ^= 1;
+        }
+      }
+      if (lane == 0) ptx::bulk_wait_all();
+    } else
     for (int acc = 0; acc < args.n_acc; ++acc) {
       const int tlo = args.tap_lo[g][acc], thi = args.tap_hi[g][acc];
       int tap, ci;
@@ -2962,6 +3000,18 @@ static int try_wgrad_halo(const mcn_conv_desc* d, const void* x, const void* dy,
     configured = true;
   }
   dim3 grid((unsigned)(units * a.splits));
+  {
+    static int tma_out_enabled = -1;
+    if (tma_out_enabled < 0) {
+      const char* e = getenv("MCN_WGRAD_TMA_OUT");
+      tma_out_enabled = (e && e[0] == '0') ? 0 : 1;
+    }
+    a.tma_out = 0;
+    if (tma_out_enabled && sp.stride && d->Cout % 32 == 0 && (size_t)a.stages * stage_bytes >= 8 * 4096) {
+      if ((rc = encode_wgrad_slices(&a.mapOut, sp.base, d->Cout, d->Cin, taps, a.splits, sp.stride))) return rc;
+      a.tma_out = 1;
+    }
+  }
   ::mcn::launch(wgrad_halo_kernel, grid, 192, smem, st, a);
   rc = after_launch("wgrad_halo_kernel");
   if (rc) return rc;
