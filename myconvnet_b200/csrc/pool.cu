@@ -404,6 +404,69 @@ maxpool_fwd_tap_tile32_kernel(const T* __restrict__ x, int N, int H, int W, int 
   }
 }
 
+// bf16 forward on packed pairs.  ncu on the kernel above: ALU pipe 80 % busy, DRAM 36 % — the per-channel
+// unpack / compare / two selects (~500 instructions per output vector) bound it, not memory.  bf16 values
+// compare exactly as packed pairs: one HSET2 mask + two LOP3 (value, tap id) per PAIR of channels and
+// tap; outputs and tap bytes leave without any float conversion.  Same rule as above: the first valid
+// tap initialises, later taps win only when strictly greater (padding acts as -inf).
+__global__ void __launch_bounds__(256)
+maxpool_fwd_tap_tile32_bf16_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C, int pad_t,
+                                   int pad_l, int Ho, int Wo, int TP, int tiles_p, int tiles_q,
+                                   __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ tap) {
+  MCN_PDL_PROLOGUE();
+  const int cv = C / 8;
+  const int c0 = (int)(threadIdx.x % (unsigned)cv) * 8;
+  const int o = (int)(threadIdx.x / (unsigned)cv);
+  const int dq = o & 3, dp = o >> 2;
+  const int total = N * tiles_p * tiles_q;
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int tq = tile % tiles_q;
+    const int r = tile / tiles_q;
+    const int tp = r % tiles_p, n = r / tiles_p;
+    const int p = tp * TP + dp, q = tq * 4 + dq;
+    if (p >= Ho || q >= Wo) continue;
+    const int h0 = p * 2 - pad_t, w0 = q * 2 - pad_l;
+    const __nv_bfloat16* img = x + (long long)n * H * W * C + c0;
+    uint4 t[9];
+    uint32_t first = 255u;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        const int h = h0 + a, w = w0 + b;
+        const bool ok = h >= 0 && h < H && w >= 0 && w < W;
+        if (ok) {
+          t[a * 3 + b] = *reinterpret_cast<const uint4*>(img + ((long long)h * W + w) * C);
+          if (first == 255u) first = (uint32_t)(a * 3 + b);
+        } else {
+          t[a * 3 + b] = make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);      // -inf
+        }
+      }
+    uint32_t best[4], bt[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      best[j] = 0xFF80FF80u;
+      bt[j] = first | (first << 16);
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const uint32_t w4[4] = {t[k].x, t[k].y, t[k].z, t[k].w};
+      const uint32_t kk = (uint32_t)k | ((uint32_t)k << 16);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t m = __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&w4[j]),
+                                       *reinterpret_cast<const __nv_bfloat162*>(&best[j]));
+        best[j] = (w4[j] & m) | (best[j] & ~m);
+        bt[j] = (kk & m) | (bt[j] & ~m);
+      }
+    }
+    const long long oo = (((long long)n * Ho + p) * Wo + q) * C + c0;
+    *reinterpret_cast<uint4*>(y + oo) = make_uint4(best[0], best[1], best[2], best[3]);
+    // tap ids sit in the low byte of each 16-bit half
+    *reinterpret_cast<uint2*>(tap + oo) = make_uint2(__byte_perm(bt[0], bt[1], 0x6420), __byte_perm(bt[2], bt[3], 0x6420));
+  }
+}
+
 // Backward: with u = h + pad_t, v = w + pad_l the pixels (2j | 2j+1, 2k | 2k+1) are covered by the
 // windows (j-1 | j, k-1 | k) only; a thread walks j down a strip, carrying window row j-1.
 template <typename T, int V>
@@ -728,8 +791,18 @@ static void launch_maxpool_tap(bool fwd, const void* in, const uint8_t* tap_in, 
         const int TP = 256 / cv / 4, tiles_p = (Ho + TP - 1) / TP, tiles_q = (Wo + 3) / 4;
         const long long tiles = (long long)N * tiles_p * tiles_q;
         const int tgrid = (int)std::max<long long>(1, std::min<long long>(tiles, (long long)bps * num_sms()));
-        ::mcn::launch(maxpool_fwd_tap_tile32_kernel<T, V>, tgrid, 256, 0, st, static_cast<const T*>(in), N, H, W, C,
-                      pad_t, pad_l, Ho, Wo, TP, tiles_p, tiles_q, static_cast<T*>(out), tap_out);
+        static int packed = -1;
+        if (packed < 0) {
+          const char* e = getenv("MCN_POOL_PACKED");      // 0: the per-channel fp32 compare kernel (A/B)
+          packed = (e && e[0] == '0') ? 0 : 1;
+        }
+        if (sizeof(T) == 2 && packed)
+          ::mcn::launch(maxpool_fwd_tap_tile32_bf16_kernel, tgrid, 256, 0, st,
+                        static_cast<const __nv_bfloat16*>(in), N, H, W, C, pad_t, pad_l, Ho, Wo, TP, tiles_p, tiles_q,
+                        static_cast<__nv_bfloat16*>(out), tap_out);
+        else
+          ::mcn::launch(maxpool_fwd_tap_tile32_kernel<T, V>, tgrid, 256, 0, st, static_cast<const T*>(in), N, H, W, C,
+                        pad_t, pad_l, Ho, Wo, TP, tiles_p, tiles_q, static_cast<T*>(out), tap_out);
         return;
       }
     } else {
