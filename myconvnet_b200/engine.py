@@ -696,6 +696,10 @@ class Engine(object):
         if "loss" not in p.loss_slots:
             return
         n = 9 if "loss_g" in p.loss_slots else 6
+        if len(self._loss_queue) >= 3:
+            # the ring has four slots and a slot is only protected against the COPY still being in flight,
+            # not against the host not having read it yet
+            raise RuntimeError("enqueue_loss_read: at most 3 losses may be pending; call pop_loss() first")
         pin = self._pinned_slot("loss", (n,), torch.int64, slots=4)
         pin.copy_(self.view(p.loss_slots["loss"], n, torch.int64), non_blocking=True)
         self._pinned_done("loss")
